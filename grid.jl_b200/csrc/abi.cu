@@ -1,0 +1,777 @@
+// abi.cu -- the extern "C" surface of libgridb200.so (see include/gridb200.h).
+// Host-side logic only: argument checking in the reference's error vocabulary, the grid handle,
+// host<->device staging (chunked, copy/compute overlapped over a small ring of streams) and
+// dispatch to the kernels in eval_*.cu / prefilter.cu / multigrid.cu.  No CPU compute fallback.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace gb {
+
+static thread_local std::string t_error;
+std::atomic<long long> g_launches{0};
+
+void set_error(const std::string& msg) { t_error = msg; }
+int fail(int code, const std::string& msg) {
+    t_error = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    t_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+    return GB_ERR_CUDA;
+}
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
+        else n = 148;
+    }
+    return n;
+}
+
+static void pool_keep_memory() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return;
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) return;
+        unsigned long long keep = ~0ull;  // staging buffers are reused call after call
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    });
+}
+
+static size_t esize(int dtype) { return dtype == GB_F64 ? 8 : 4; }
+static bool ok_dtype(int d) { return d == GB_F32 || d == GB_F64; }
+
+}  // namespace gb
+
+using namespace gb;
+
+struct gb_grid {
+    int dtype, ndim, bc, order;
+    double fill;
+    i64 user_dims[MAXD], stored_dims[MAXD];
+    i64 total;
+    void* coefs;
+    int device;
+    int shift;
+};
+
+static int check_grid_args(int dtype, int ndim, const int64_t* dims, int bc, int order) {
+    if (!ok_dtype(dtype)) return fail(GB_ERR_ARG, "dtype must be GB_F32 or GB_F64");
+    if (ndim < 1) return fail(GB_ERR_ARG, "ndim must be >= 1");
+    if (ndim > MAXD) return fail(GB_ERR_UNSUPPORTED, "ndim > 4 is not supported by the dimension-specialised kernels");
+    if (bc < GB_BC_NIL || bc > GB_BC_FILL) return fail(GB_ERR_ARG, "bad boundary condition");
+    if (order < GB_NEAREST || order > GB_CUBIC) return fail(GB_ERR_ARG, "bad interpolation order");
+    if (order == GB_CUBIC && bc > GB_BC_NA) return fail(GB_ERR_UNSUPPORTED, "InterpCubic supports only BCnil/BCnan/BCna (README.md:146)");
+    if (!dims) return fail(GB_ERR_ARG, "dims is NULL");
+    for (int d = 0; d < ndim; d++)
+        if (dims[d] < 1 || dims[d] > (1ll << 30)) return fail(GB_ERR_ARG, "every dimension must be in [1, 2^30]");
+    return GB_OK;
+}
+
+static int min_len(int bc, int order) {
+    if (order == GB_CUBIC) return 4;
+    if (order == GB_QUADRATIC) return bc <= GB_BC_NA ? 3 : (bc == GB_BC_PERIODIC || bc == GB_BC_REFLECT ? 3 : 3);
+    return 1;
+}
+
+extern "C" {
+
+int gb_version(void) { return GB_VERSION; }
+const char* gb_last_error(void) { return t_error.c_str(); }
+int64_t gb_launch_count(void) { return g_launches.load(); }
+
+int gb_device_count(int* n) {
+    if (!n) return fail(GB_ERR_ARG, "n is NULL");
+    GB_CUDA(cudaGetDeviceCount(n));
+    return GB_OK;
+}
+int gb_set_device(int device) {
+    GB_CUDA(cudaSetDevice(device));
+    return GB_OK;
+}
+
+int gb_device_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return fail(GB_ERR_ARG, "ptr is NULL");
+    GB_CUDA(cudaMalloc(ptr, bytes ? bytes : 1));
+    return GB_OK;
+}
+int gb_device_free(void* ptr) {
+    GB_CUDA(cudaFree(ptr));
+    return GB_OK;
+}
+int gb_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream) {
+    GB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return GB_OK;
+}
+int gb_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream) {
+    GB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return GB_OK;
+}
+int gb_host_alloc_pinned(void** ptr, size_t bytes) {
+    if (!ptr) return fail(GB_ERR_ARG, "ptr is NULL");
+    GB_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return GB_OK;
+}
+int gb_host_free_pinned(void* ptr) {
+    GB_CUDA(cudaFreeHost(ptr));
+    return GB_OK;
+}
+int gb_host_register(void* ptr, size_t bytes) {
+    GB_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    return GB_OK;
+}
+int gb_host_unregister(void* ptr) {
+    GB_CUDA(cudaHostUnregister(ptr));
+    return GB_OK;
+}
+int gb_stream_synchronize(void* stream) {
+    GB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return GB_OK;
+}
+
+int gb_synth_uniform(int dtype, void* device_out, int64_t n, uint64_t seed, double lo, double hi, int64_t first, void* stream) {
+    if (!ok_dtype(dtype)) return fail(GB_ERR_ARG, "bad dtype");
+    return synth_device(dtype, device_out, n, seed, lo, hi, first, (cudaStream_t)stream);
+}
+
+// ---- prefilter ------------------------------------------------------------------------------
+int gb_invert(int dtype, int ndim, const int64_t* dims, void* data, int mem, int bc, int order, const int* dimlist,
+              int ndimlist, void* stream) {
+    if (!ok_dtype(dtype)) return fail(GB_ERR_ARG, "bad dtype");
+    if (ndim < 1 || !dims || !data) return fail(GB_ERR_ARG, "bad array arguments");
+    if (bc < GB_BC_NIL || bc > GB_BC_FILL || order < GB_NEAREST || order > GB_CUBIC) return fail(GB_ERR_ARG, "bad bc/order");
+    if (order < GB_QUADRATIC) return GB_OK;
+    std::vector<int> all;
+    if (!dimlist) {
+        for (int d = 0; d < ndim; d++) all.push_back(d);
+        dimlist = all.data();
+        ndimlist = ndim;
+    }
+    i64 total = 1;
+    for (int d = 0; d < ndim; d++) total *= dims[d];
+    cudaStream_t s = (cudaStream_t)stream;
+    pool_keep_memory();
+    if (mem == GB_DEVICE) return invert_device(dtype, ndim, (const i64*)dims, data, bc, order, dimlist, ndimlist, s);
+    void* dev = nullptr;
+    const size_t bytes = (size_t)total * esize(dtype);
+    GB_CUDA(cudaMallocAsync(&dev, bytes, s));
+    GB_CUDA(cudaMemcpyAsync(dev, data, bytes, cudaMemcpyHostToDevice, s));
+    int rc = invert_device(dtype, ndim, (const i64*)dims, dev, bc, order, dimlist, ndimlist, s);
+    if (rc == GB_OK) {
+        cudaError_t e = cudaMemcpyAsync(data, dev, bytes, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync D2H");
+    }
+    cudaFreeAsync(dev, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (rc == GB_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize");
+    return rc;
+}
+
+int gb_pad1(int dtype, int ndim, const int64_t* dims, const void* in, double fill, void* out, int mem, void* stream) {
+    if (!ok_dtype(dtype) || ndim < 1 || ndim > MAXD || !dims || !in || !out) return fail(GB_ERR_ARG, "bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    pool_keep_memory();
+    if (mem == GB_DEVICE) return pad1_device(dtype, ndim, (const i64*)dims, in, fill, out, s);
+    i64 it = 1, ot = 1;
+    for (int d = 0; d < ndim; d++) { it *= dims[d]; ot *= dims[d] + 2; }
+    void *di = nullptr, *dout = nullptr;
+    GB_CUDA(cudaMallocAsync(&di, it * esize(dtype), s));
+    GB_CUDA(cudaMallocAsync(&dout, ot * esize(dtype), s));
+    GB_CUDA(cudaMemcpyAsync(di, in, it * esize(dtype), cudaMemcpyHostToDevice, s));
+    int rc = pad1_device(dtype, ndim, (const i64*)dims, di, fill, dout, s);
+    if (rc == GB_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, dout, ot * esize(dtype), cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync D2H");
+    }
+    cudaFreeAsync(di, s);
+    cudaFreeAsync(dout, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (rc == GB_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize");
+    return rc;
+}
+
+// ---- grid lifetime ----------------------------------------------------------------------------
+static int new_grid(gb_grid** out, int dtype, int ndim, int bc, int order, double fill) {
+    gb_grid* g = new gb_grid();
+    g->dtype = dtype; g->ndim = ndim; g->bc = bc; g->order = order; g->fill = fill;
+    g->coefs = nullptr; g->total = 0;
+    g->shift = needs_shift(bc, order) ? 1 : 0;
+    for (int d = 0; d < MAXD; d++) g->user_dims[d] = g->stored_dims[d] = 1;
+    if (cudaGetDevice(&g->device) != cudaSuccess) g->device = 0;
+    *out = g;
+    return GB_OK;
+}
+
+int gb_grid_create(gb_grid** out, int dtype, int ndim, const int64_t* dims, const void* samples, int mem, int bc,
+                   int order, double fill, void* stream) {
+    if (!out || !samples) return fail(GB_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    int rc = check_grid_args(dtype, ndim, dims, bc, order);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    pool_keep_memory();
+    const bool pad = needs_shift(bc, order);              // src/interp.jl:58-72
+    const int pf_bc = bc == GB_BC_FILL ? GB_BC_NEAREST : bc;  // :68
+    const double padval = bc == GB_BC_FILL ? fill : 0.0;      // :60,:67
+    i64 ut = 1, st = 1, sd[MAXD];
+    for (int d = 0; d < ndim; d++) {
+        sd[d] = dims[d] + (pad ? 2 : 0);
+        ut *= dims[d];
+        st *= sd[d];
+        if (sd[d] < min_len(bc, order)) return fail(GB_ERR_ARG, "grid too small for this interpolation order");
+    }
+    gb_grid* g = nullptr;
+    new_grid(&g, dtype, ndim, bc, order, fill);
+    for (int d = 0; d < ndim; d++) { g->user_dims[d] = dims[d]; g->stored_dims[d] = sd[d]; }
+    g->total = st;
+    const size_t es = esize(dtype);
+    cudaError_t e = cudaMalloc(&g->coefs, (size_t)st * es);
+    if (e != cudaSuccess) { delete g; return cuda_fail(e, "cudaMalloc(coefs)"); }
+    void* staged = nullptr;
+    const void* src = samples;
+    auto cleanup = [&](int code) {
+        if (staged) cudaFreeAsync(staged, s);
+        cudaStreamSynchronize(s);
+        cudaFree(g->coefs);
+        delete g;
+        return code;
+    };
+    if (pad) {
+        if (mem == GB_HOST) {
+            e = cudaMallocAsync(&staged, (size_t)ut * es, s);
+            if (e != cudaSuccess) return cleanup(cuda_fail(e, "cudaMallocAsync"));
+            e = cudaMemcpyAsync(staged, samples, (size_t)ut * es, cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) return cleanup(cuda_fail(e, "cudaMemcpyAsync H2D"));
+            src = staged;
+        }
+        rc = pad1_device(dtype, ndim, (const i64*)dims, src, padval, g->coefs, s);
+        if (rc) return cleanup(rc);
+    } else {
+        e = cudaMemcpyAsync(g->coefs, samples, (size_t)ut * es, mem == GB_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) return cleanup(cuda_fail(e, "cudaMemcpyAsync"));
+    }
+    std::vector<int> all;
+    for (int d = 0; d < ndim; d++) all.push_back(d);
+    rc = invert_device(dtype, ndim, sd, g->coefs, pf_bc, order, all.data(), ndim, s);
+    if (rc) return cleanup(rc);
+    if (staged) cudaFreeAsync(staged, s);
+    if (mem == GB_HOST) {
+        e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { staged = nullptr; return cleanup(cuda_fail(e, "cudaStreamSynchronize")); }
+    }
+    *out = g;
+    return GB_OK;
+}
+
+int gb_grid_create_from_coefs(gb_grid** out, int dtype, int ndim, const int64_t* stored_dims, const void* coefs, int mem,
+                              int bc, int order, double fill, void* stream) {
+    if (!out || !coefs) return fail(GB_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    int rc = check_grid_args(dtype, ndim, stored_dims, bc, order);
+    if (rc) return rc;
+    const bool pad = needs_shift(bc, order);
+    i64 st = 1;
+    for (int d = 0; d < ndim; d++) {
+        if (stored_dims[d] < min_len(bc, order) || (pad && stored_dims[d] < 3)) return fail(GB_ERR_ARG, "stored grid too small");
+        st *= stored_dims[d];
+    }
+    gb_grid* g = nullptr;
+    new_grid(&g, dtype, ndim, bc, order, fill);
+    for (int d = 0; d < ndim; d++) { g->stored_dims[d] = stored_dims[d]; g->user_dims[d] = stored_dims[d] - (pad ? 2 : 0); }
+    g->total = st;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMalloc(&g->coefs, (size_t)st * esize(dtype));
+    if (e != cudaSuccess) { delete g; return cuda_fail(e, "cudaMalloc(coefs)"); }
+    e = cudaMemcpyAsync(g->coefs, coefs, (size_t)st * esize(dtype), mem == GB_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess && mem == GB_HOST) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { cudaFree(g->coefs); delete g; return cuda_fail(e, "copy coefs"); }
+    *out = g;
+    return GB_OK;
+}
+
+int gb_grid_info(const gb_grid* g, int* dtype, int* ndim, int64_t* user_dims, int64_t* stored_dims, int* bc, int* order, double* fill) {
+    if (!g) return fail(GB_ERR_ARG, "grid is NULL");
+    if (dtype) *dtype = g->dtype;
+    if (ndim) *ndim = g->ndim;
+    if (bc) *bc = g->bc;
+    if (order) *order = g->order;
+    if (fill) *fill = g->fill;
+    for (int d = 0; d < g->ndim; d++) {
+        if (user_dims) user_dims[d] = g->user_dims[d];
+        if (stored_dims) stored_dims[d] = g->stored_dims[d];
+    }
+    return GB_OK;
+}
+int gb_grid_coefs_device(const gb_grid* g, void** device_ptr) {
+    if (!g || !device_ptr) return fail(GB_ERR_ARG, "NULL argument");
+    *device_ptr = g->coefs;
+    return GB_OK;
+}
+int gb_grid_coefs_download(const gb_grid* g, void* host_out) {
+    if (!g || !host_out) return fail(GB_ERR_ARG, "NULL argument");
+    GB_CUDA(cudaMemcpy(host_out, g->coefs, (size_t)g->total * esize(g->dtype), cudaMemcpyDeviceToHost));
+    return GB_OK;
+}
+int gb_grid_destroy(gb_grid* g) {
+    if (!g) return GB_OK;
+    cudaFree(g->coefs);
+    delete g;
+    return GB_OK;
+}
+
+}  // extern "C"
+
+// ---- evaluation dispatch ------------------------------------------------------------------------
+namespace {
+
+struct EvalCall {
+    const gb_grid* g;
+    int outmode, flags, xdtype;
+    const double* affine;
+    i64 nq;
+    const void* xp[MAXD];  // device pointers
+    i64 xqs;
+    void *val, *grad, *hess;  // device
+    u64* first_invalid;       // device or NULL
+    i64 q0;
+};
+
+template <int N> int launch_n(const EvalCall& c, cudaStream_t s) {
+    const gb_grid* g = c.g;
+    EvalParams<N> p;
+    p.coefs = g->coefs;
+    p.total = g->total;
+    i64 str = 1;
+    for (int d = 0; d < N; d++) {
+        p.len[d] = (int)g->stored_dims[d];
+        p.stride[d] = str;
+        str *= g->stored_dims[d];
+        p.xp[d] = c.xp[d];
+        for (int k = 0; k < 4; k++) p.aff[d][k] = c.affine ? c.affine[4 * d + k] : 0.0;
+    }
+    p.xqs = c.xqs;
+    p.xdtype = c.xdtype;
+    p.has_aff = c.affine ? 1 : 0;
+    p.shift = g->shift;
+    p.val = c.val; p.grad = c.grad; p.hess = c.hess;
+    p.nq = c.nq;
+    p.q0 = c.q0;
+    p.first_invalid = c.first_invalid;
+    const int bcf = bc_family(g->bc);
+    if (g->dtype == GB_F64) {
+        if constexpr (N == 1) return launch_eval_double_1(p, g->order, bcf, c.outmode, c.flags, s);
+        if constexpr (N == 2) return launch_eval_double_2(p, g->order, bcf, c.outmode, c.flags, s);
+        if constexpr (N == 3) return launch_eval_double_3(p, g->order, bcf, c.outmode, c.flags, s);
+        if constexpr (N == 4) return launch_eval_double_4(p, g->order, bcf, c.outmode, c.flags, s);
+    } else {
+        if constexpr (N == 1) return launch_eval_float_1(p, g->order, bcf, c.outmode, c.flags, s);
+        if constexpr (N == 2) return launch_eval_float_2(p, g->order, bcf, c.outmode, c.flags, s);
+        if constexpr (N == 3) return launch_eval_float_3(p, g->order, bcf, c.outmode, c.flags, s);
+        if constexpr (N == 4) return launch_eval_float_4(p, g->order, bcf, c.outmode, c.flags, s);
+    }
+    return GB_ERR_ARG;
+}
+
+int launch_eval(const EvalCall& c, cudaStream_t s) {
+    if (c.nq <= 0) return GB_OK;
+    switch (c.g->ndim) {
+    case 1: return launch_n<1>(c, s);
+    case 2: return launch_n<2>(c, s);
+    case 3: return launch_n<3>(c, s);
+    case 4: return launch_n<4>(c, s);
+    }
+    return fail(GB_ERR_UNSUPPORTED, "ndim > 4");
+}
+
+int outmode_of(const gb_grid* g, int out_mask, void* val, void* grad, void* hess, int* outmode) {
+    if (out_mask & ~(GB_OUT_VAL | GB_OUT_GRAD | GB_OUT_HESS) || out_mask == 0) return fail(GB_ERR_ARG, "bad out_mask");
+    *outmode = (out_mask & GB_OUT_HESS) ? 2 : (out_mask & GB_OUT_GRAD) ? 1 : 0;
+    if ((out_mask & GB_OUT_HESS) && g->order < GB_QUADRATIC)
+        return fail(GB_ERR_UNSUPPORTED, "valgradhess is not defined for InterpNearest/InterpLinear (no interp_hcoefs_1d method)");
+    if ((out_mask & GB_OUT_VAL) && !val) return fail(GB_ERR_ARG, "val is NULL");
+    if ((out_mask & GB_OUT_GRAD) && !grad) return fail(GB_ERR_ARG, "Wrong number of components for the gradient");
+    if ((out_mask & GB_OUT_HESS) && !hess) return fail(GB_ERR_ARG, "Wrong number of components for the hessian");
+    return GB_OK;
+}
+
+int check_affine(const gb_grid* g, const double* affine) {
+    if (!affine) return GB_OK;
+    for (int d = 0; d < g->ndim; d++) {
+        const double kind = affine[4 * d];
+        if (!(kind == 0.0 || kind == 1.0 || kind == 2.0)) return fail(GB_ERR_ARG, "affine kind must be 0 (FloatRange), 1 (StepRange) or 2 (UnitRange)");
+        if (kind != 2.0 && affine[4 * d + 2] == 0.0) return fail(GB_ERR_ARG, "range step cannot be zero");
+    }
+    return GB_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+
+// Host-resident evaluation: chunks of the batch flow H2D -> kernel -> D2H over a ring of streams so
+// PCIe traffic in both directions overlaps the kernels.
+int eval_host(const gb_grid* g, int out_mask, int outmode, i64 nq, const void* const* xcols, const void* xaos, int xdtype,
+              const double* affine, void* val, void* grad, void* hess, int flags, int64_t* first_invalid) {
+    const int N = g->ndim;
+    const size_t xs = esize(xdtype), es = esize(g->dtype);
+    static const i64 chunk_env = [] {
+        const char* e = getenv("GB_EVAL_CHUNK");
+        long long v = e ? atoll(e) : 0;
+        return (i64)(v > 0 ? v : (1ll << 20));
+    }();
+    const i64 chunk = std::max<i64>(1, std::min<i64>(chunk_env, nq));
+    constexpr int NSLOT = 3;
+    const int nslot = (int)std::min<i64>(NSLOT, (nq + chunk - 1) / chunk);
+    struct Slot {
+        cudaStream_t s = nullptr;
+        void *x = nullptr, *v = nullptr, *gr = nullptr, *h = nullptr;
+    } slots[NSLOT];
+    u64* d_bad = nullptr;
+    int rc = GB_OK;
+    auto cu = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess && rc == GB_OK) rc = cuda_fail(e, what);
+        return e == cudaSuccess;
+    };
+    for (int i = 0; i < nslot && rc == GB_OK; i++) {
+        Slot& sl = slots[i];
+        if (!cu(cudaStreamCreateWithFlags(&sl.s, cudaStreamNonBlocking), "cudaStreamCreate")) break;
+        cu(cudaMallocAsync(&sl.x, (size_t)chunk * N * xs, sl.s), "cudaMallocAsync");
+        if (out_mask & GB_OUT_VAL) cu(cudaMallocAsync(&sl.v, (size_t)chunk * es, sl.s), "cudaMallocAsync");
+        if (out_mask & GB_OUT_GRAD) cu(cudaMallocAsync(&sl.gr, (size_t)chunk * N * es, sl.s), "cudaMallocAsync");
+        if (out_mask & GB_OUT_HESS) cu(cudaMallocAsync(&sl.h, (size_t)chunk * N * N * es, sl.s), "cudaMallocAsync");
+    }
+    if (rc == GB_OK && first_invalid && g->bc == GB_BC_NIL) {
+        cu(cudaMallocAsync((void**)&d_bad, sizeof(u64), slots[0].s), "cudaMallocAsync");
+        cu(cudaMemsetAsync(d_bad, 0xFF, sizeof(u64), slots[0].s), "cudaMemsetAsync");
+        cu(cudaStreamSynchronize(slots[0].s), "cudaStreamSynchronize");
+    }
+    for (i64 q0 = 0, c = 0; q0 < nq && rc == GB_OK; q0 += chunk, c++) {
+        Slot& sl = slots[c % nslot];
+        const i64 n = std::min(chunk, nq - q0);
+        EvalCall call;
+        call.g = g; call.outmode = outmode; call.flags = flags; call.xdtype = xdtype; call.affine = affine;
+        call.nq = n; call.q0 = q0; call.first_invalid = d_bad;
+        if (xaos) {  // N contiguous coordinates per query
+            cu(cudaMemcpyAsync(sl.x, (const char*)xaos + (size_t)q0 * N * xs, (size_t)n * N * xs, cudaMemcpyHostToDevice, sl.s), "cudaMemcpyAsync H2D");
+            for (int d = 0; d < N; d++) call.xp[d] = (const char*)sl.x + (size_t)d * xs;
+            call.xqs = N;
+        } else {  // one vector per dimension
+            for (int d = 0; d < N; d++) {
+                cu(cudaMemcpyAsync((char*)sl.x + (size_t)d * chunk * xs, (const char*)xcols[d] + (size_t)q0 * xs, (size_t)n * xs, cudaMemcpyHostToDevice, sl.s), "cudaMemcpyAsync H2D");
+                call.xp[d] = (const char*)sl.x + (size_t)d * chunk * xs;
+            }
+            call.xqs = 1;
+        }
+        call.val = sl.v; call.grad = sl.gr; call.hess = sl.h;
+        if (rc != GB_OK) break;
+        rc = launch_eval(call, sl.s);
+        if (rc != GB_OK) break;
+        if (sl.v) cu(cudaMemcpyAsync((char*)val + (size_t)q0 * es, sl.v, (size_t)n * es, cudaMemcpyDeviceToHost, sl.s), "cudaMemcpyAsync D2H");
+        if (sl.gr) cu(cudaMemcpyAsync((char*)grad + (size_t)q0 * N * es, sl.gr, (size_t)n * N * es, cudaMemcpyDeviceToHost, sl.s), "cudaMemcpyAsync D2H");
+        if (sl.h) cu(cudaMemcpyAsync((char*)hess + (size_t)q0 * N * N * es, sl.h, (size_t)n * N * N * es, cudaMemcpyDeviceToHost, sl.s), "cudaMemcpyAsync D2H");
+    }
+    for (int i = 0; i < nslot; i++) {
+        Slot& sl = slots[i];
+        if (!sl.s) continue;
+        if (sl.x) cudaFreeAsync(sl.x, sl.s);
+        if (sl.v) cudaFreeAsync(sl.v, sl.s);
+        if (sl.gr) cudaFreeAsync(sl.gr, sl.s);
+        if (sl.h) cudaFreeAsync(sl.h, sl.s);
+        cu(cudaStreamSynchronize(sl.s), "cudaStreamSynchronize");
+    }
+    if (first_invalid) *first_invalid = -1;
+    if (d_bad) {
+        u64 bad = ~0ull;
+        cu(cudaMemcpy(&bad, d_bad, sizeof(u64), cudaMemcpyDeviceToHost), "cudaMemcpy");
+        cudaFree(d_bad);
+        if (rc == GB_OK && bad != ~0ull) {
+            *first_invalid = (int64_t)bad;
+            rc = fail(GB_ERR_INVALID_LOCATION, "Invalid location");
+        }
+    }
+    for (int i = 0; i < nslot; i++)
+        if (slots[i].s) cudaStreamDestroy(slots[i].s);
+    return rc;
+}
+
+int eval_device(const gb_grid* g, int outmode, i64 nq, const void* const* xp, i64 xqs, int xdtype, const double* affine,
+                void* val, void* grad, void* hess, int flags, int64_t* first_invalid, cudaStream_t s) {
+    EvalCall call;
+    call.g = g; call.outmode = outmode; call.flags = flags; call.xdtype = xdtype; call.affine = affine;
+    call.nq = nq; call.q0 = 0; call.xqs = xqs;
+    for (int d = 0; d < g->ndim; d++) call.xp[d] = xp[d];
+    call.val = val; call.grad = grad; call.hess = hess;
+    u64* d_bad = nullptr;
+    const bool check = first_invalid && g->bc == GB_BC_NIL;
+    if (check) {
+        GB_CUDA(cudaMallocAsync((void**)&d_bad, sizeof(u64), s));
+        GB_CUDA(cudaMemsetAsync(d_bad, 0xFF, sizeof(u64), s));
+    }
+    call.first_invalid = d_bad;
+    int rc = launch_eval(call, s);
+    if (first_invalid) *first_invalid = -1;
+    if (check) {
+        u64 bad = ~0ull;
+        cudaError_t e = cudaMemcpyAsync(&bad, d_bad, sizeof(u64), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        cudaFreeAsync(d_bad, s);
+        if (rc == GB_OK && e != cudaSuccess) rc = cuda_fail(e, "read first_invalid");
+        if (rc == GB_OK && bad != ~0ull) {
+            *first_invalid = (int64_t)bad;
+            rc = fail(GB_ERR_INVALID_LOCATION, "Invalid location");
+        }
+    }
+    return rc;
+}
+
+// out[i1,i2,...] = G[v1[i1], v2[i2], ...]: expand the vectors into per-dimension coordinate columns.
+template <typename XT> __global__ void expand_outer_kernel(XT* __restrict__ cols, i64 nq, int N, const XT* const* __restrict__ vecs, const i64* __restrict__ lens) {
+    const i64 step = (i64)gridDim.x * blockDim.x;
+    for (i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += step) {
+        i64 rem = q;
+        for (int d = 0; d < N; d++) {
+            const i64 i = rem % lens[d];
+            rem /= lens[d];
+            cols[(i64)d * nq + q] = vecs[d][i];
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int gb_eval(const gb_grid* g, int out_mask, int64_t nq, const void* x, int xdtype, int64_t x_qstride, int64_t x_dstride,
+            const double* affine, void* val, void* grad, void* hess, int mem, int flags, int64_t* first_invalid, void* stream) {
+    if (!g) return fail(GB_ERR_ARG, "grid is NULL");
+    if (nq < 0) return fail(GB_ERR_ARG, "nq < 0");
+    if (!ok_dtype(xdtype)) return fail(GB_ERR_ARG, "xdtype must be GB_F32 or GB_F64");
+    int outmode = 0;
+    int rc = outmode_of(g, out_mask, val, grad, hess, &outmode);
+    if (rc) return rc;
+    rc = check_affine(g, affine);
+    if (rc) return rc;
+    if (first_invalid) *first_invalid = -1;
+    if (nq == 0) return GB_OK;
+    if (!x) return fail(GB_ERR_ARG, "x is NULL");
+    DeviceGuard guard(g->device);
+    pool_keep_memory();
+    const int N = g->ndim;
+    const void* cols[MAXD];
+    for (int d = 0; d < N; d++) cols[d] = (const char*)x + (size_t)d * x_dstride * esize(xdtype);
+    if (mem == GB_DEVICE)
+        return eval_device(g, outmode, nq, cols, x_qstride, xdtype, affine, (out_mask & GB_OUT_VAL) ? val : nullptr,
+                           (out_mask & GB_OUT_GRAD) ? grad : nullptr, (out_mask & GB_OUT_HESS) ? hess : nullptr, flags, first_invalid, (cudaStream_t)stream);
+    if (x_qstride == N && x_dstride == 1)
+        return eval_host(g, out_mask, outmode, nq, nullptr, x, xdtype, affine, val, grad, hess, flags, first_invalid);
+    if (x_qstride == 1)
+        return eval_host(g, out_mask, outmode, nq, cols, nullptr, xdtype, affine, val, grad, hess, flags, first_invalid);
+    return fail(GB_ERR_ARG, "host query batches must be N x nq (x_qstride=N, x_dstride=1) or column vectors (x_qstride=1)");
+}
+
+int gb_eval_soa(const gb_grid* g, int out_mask, int64_t nq, const void* const* xs, int xdtype, const double* affine, void* val,
+                void* grad, void* hess, int mem, int flags, int64_t* first_invalid, void* stream) {
+    if (!g) return fail(GB_ERR_ARG, "grid is NULL");
+    if (nq < 0) return fail(GB_ERR_ARG, "nq < 0");
+    if (!ok_dtype(xdtype)) return fail(GB_ERR_ARG, "xdtype must be GB_F32 or GB_F64");
+    int outmode = 0;
+    int rc = outmode_of(g, out_mask, val, grad, hess, &outmode);
+    if (rc) return rc;
+    rc = check_affine(g, affine);
+    if (rc) return rc;
+    if (first_invalid) *first_invalid = -1;
+    if (nq == 0) return GB_OK;
+    if (!xs) return fail(GB_ERR_ARG, "xs is NULL");
+    for (int d = 0; d < g->ndim; d++)
+        if (!xs[d]) return fail(GB_ERR_ARG, "Incorrect number of dimensions supplied");
+    DeviceGuard guard(g->device);
+    pool_keep_memory();
+    if (mem == GB_DEVICE)
+        return eval_device(g, outmode, nq, xs, 1, xdtype, affine, (out_mask & GB_OUT_VAL) ? val : nullptr,
+                           (out_mask & GB_OUT_GRAD) ? grad : nullptr, (out_mask & GB_OUT_HESS) ? hess : nullptr, flags, first_invalid, (cudaStream_t)stream);
+    return eval_host(g, out_mask, outmode, nq, xs, nullptr, xdtype, affine, val, grad, hess, flags, first_invalid);
+}
+
+int gb_eval_outer(const gb_grid* g, const int64_t* lens, const void* const* vecs, int xdtype, const double* affine, void* out,
+                  int mem, int flags, void* stream) {
+    if (!g || !lens || !vecs || !out) return fail(GB_ERR_ARG, "NULL argument");
+    if (!ok_dtype(xdtype)) return fail(GB_ERR_ARG, "xdtype must be GB_F32 or GB_F64");
+    int rc = check_affine(g, affine);
+    if (rc) return rc;
+    const int N = g->ndim;
+    i64 nq = 1;
+    for (int d = 0; d < N; d++) {
+        if (lens[d] < 0 || !vecs[d]) return fail(GB_ERR_ARG, "Dimensionality mismatch");
+        nq *= lens[d];
+    }
+    if (nq == 0) return GB_OK;
+    DeviceGuard guard(g->device);
+    pool_keep_memory();
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t xs = esize(xdtype), es = esize(g->dtype);
+    // device copies of the vectors (host mode), the pointer table, lens, the expanded columns
+    void* dvec[MAXD] = {nullptr, nullptr, nullptr, nullptr};
+    const void* vptr[MAXD];
+    void *d_tab = nullptr, *d_lens = nullptr, *d_cols = nullptr, *d_out = nullptr;
+    auto cleanup = [&](int code) {
+        for (int d = 0; d < N; d++)
+            if (dvec[d]) cudaFreeAsync(dvec[d], s);
+        if (d_tab) cudaFreeAsync(d_tab, s);
+        if (d_lens) cudaFreeAsync(d_lens, s);
+        if (d_cols) cudaFreeAsync(d_cols, s);
+        if (d_out) cudaFreeAsync(d_out, s);
+        if (mem == GB_HOST) cudaStreamSynchronize(s);
+        return code;
+    };
+#define GB_TRY(expr)                                                   \
+    do {                                                               \
+        cudaError_t _e = (expr);                                       \
+        if (_e != cudaSuccess) return cleanup(cuda_fail(_e, #expr));   \
+    } while (0)
+    for (int d = 0; d < N; d++) {
+        if (mem == GB_HOST) {
+            GB_TRY(cudaMallocAsync(&dvec[d], std::max<size_t>(1, lens[d] * xs), s));
+            GB_TRY(cudaMemcpyAsync(dvec[d], vecs[d], lens[d] * xs, cudaMemcpyHostToDevice, s));
+            vptr[d] = dvec[d];
+        } else
+            vptr[d] = vecs[d];
+    }
+    GB_TRY(cudaMallocAsync(&d_tab, sizeof(void*) * MAXD, s));
+    GB_TRY(cudaMemcpyAsync(d_tab, vptr, sizeof(void*) * N, cudaMemcpyHostToDevice, s));
+    GB_TRY(cudaMallocAsync(&d_lens, sizeof(i64) * MAXD, s));
+    GB_TRY(cudaMemcpyAsync(d_lens, lens, sizeof(i64) * N, cudaMemcpyHostToDevice, s));
+    GB_TRY(cudaMallocAsync(&d_cols, (size_t)nq * N * xs, s));
+    const int grid = (int)std::max<i64>(1, std::min<i64>((nq + 255) / 256, (i64)num_sms() * 16));
+    if (xdtype == GB_F64) expand_outer_kernel<double><<<grid, 256, 0, s>>>((double*)d_cols, nq, N, (const double* const*)d_tab, (const i64*)d_lens);
+    else expand_outer_kernel<float><<<grid, 256, 0, s>>>((float*)d_cols, nq, N, (const float* const*)d_tab, (const i64*)d_lens);
+    count_launch();
+    GB_TRY(cudaGetLastError());
+    void* dst = out;
+    if (mem == GB_HOST) {
+        GB_TRY(cudaMallocAsync(&d_out, (size_t)nq * es, s));
+        dst = d_out;
+    }
+    const void* cols[MAXD];
+    for (int d = 0; d < N; d++) cols[d] = (const char*)d_cols + (size_t)d * nq * xs;
+    int64_t bad = -1;
+    rc = eval_device(g, 0, nq, cols, 1, xdtype, affine, dst, nullptr, nullptr, flags, g->bc == GB_BC_NIL ? &bad : nullptr, s);
+    if (rc == GB_OK && mem == GB_HOST) GB_TRY(cudaMemcpyAsync(out, d_out, (size_t)nq * es, cudaMemcpyDeviceToHost, s));
+#undef GB_TRY
+    return cleanup(rc);
+}
+
+// ---- restrict / prolong -----------------------------------------------------------------------
+int64_t gb_restrict_size(int64_t len) { return (len & 1) ? (len + 1) / 2 : len / 2 + 1; }
+int gb_prolong_size(int64_t n, int64_t len, int64_t* newlen) {
+    const int64_t newsz = (len & 1) ? 2 * n - 1 : 2 * (n - 1);
+    if (newsz != len) return fail(GB_ERR_PROLONG_SIZE, "Cannot prolong a dimension of length " + std::to_string(n) + " to " + std::to_string(len));
+    if (newlen) *newlen = newsz;
+    return GB_OK;
+}
+
+static int mg_host(int dtype, i64 in_elems, i64 out_elems, const void* in, void* out, cudaStream_t s,
+                   int (*run)(void*, const void*, void*, cudaStream_t), void* ctx) {
+    void *di = nullptr, *dout = nullptr;
+    GB_CUDA(cudaMallocAsync(&di, std::max<size_t>(1, in_elems * esize(dtype)), s));
+    GB_CUDA(cudaMallocAsync(&dout, std::max<size_t>(1, out_elems * esize(dtype)), s));
+    GB_CUDA(cudaMemcpyAsync(di, in, in_elems * esize(dtype), cudaMemcpyHostToDevice, s));
+    int rc = run(ctx, di, dout, s);
+    if (rc == GB_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, dout, out_elems * esize(dtype), cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync D2H");
+    }
+    cudaFreeAsync(di, s);
+    cudaFreeAsync(dout, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (rc == GB_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize");
+    return rc;
+}
+
+int gb_restrict(int dtype, int ndim, const int64_t* dims, const void* in, int dim, double scale, void* out, int mem, void* stream) {
+    if (!ok_dtype(dtype) || ndim < 1 || !dims || !in || !out) return fail(GB_ERR_ARG, "bad arguments");
+    if (dim < 0 || dim >= ndim) return fail(GB_ERR_ARG, "restrict: dim out of range");
+    cudaStream_t s = (cudaStream_t)stream;
+    pool_keep_memory();
+    if (mem == GB_DEVICE) return restrict_device(dtype, ndim, (const i64*)dims, in, dim, scale, out, s);
+    i64 it = 1, ot = 1;
+    for (int d = 0; d < ndim; d++) { it *= dims[d]; ot *= (d == dim) ? gb_restrict_size(dims[d]) : dims[d]; }
+    struct Ctx { int dtype, ndim, dim; const i64* dims; double scale; } ctx{dtype, ndim, dim, (const i64*)dims, scale};
+    return mg_host(dtype, it, ot, in, out, s, [](void* c, const void* i, void* o, cudaStream_t st) {
+        Ctx* x = (Ctx*)c;
+        return restrict_device(x->dtype, x->ndim, x->dims, i, x->dim, x->scale, o, st);
+    }, &ctx);
+}
+
+int gb_prolong(int dtype, int ndim, const int64_t* dims, const void* in, int dim, int64_t len, void* out, int mem, void* stream) {
+    if (!ok_dtype(dtype) || ndim < 1 || !dims || !in || !out) return fail(GB_ERR_ARG, "bad arguments");
+    if (dim < 0 || dim >= ndim) return fail(GB_ERR_ARG, "prolong: dim out of range");
+    int rc = gb_prolong_size(dims[dim], len, nullptr);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    pool_keep_memory();
+    if (mem == GB_DEVICE) return prolong_device(dtype, ndim, (const i64*)dims, in, dim, len, out, s);
+    i64 it = 1, ot = 1;
+    for (int d = 0; d < ndim; d++) { it *= dims[d]; ot *= (d == dim) ? len : dims[d]; }
+    struct Ctx { int dtype, ndim, dim; const i64* dims; i64 len; } ctx{dtype, ndim, dim, (const i64*)dims, len};
+    return mg_host(dtype, it, ot, in, out, s, [](void* c, const void* i, void* o, cudaStream_t st) {
+        Ctx* x = (Ctx*)c;
+        return prolong_device(x->dtype, x->ndim, x->dims, i, x->dim, x->len, o, st);
+    }, &ctx);
+}
+
+int gb_restrict3(int dtype, const int64_t* dims, const void* in, double scale, void* out, int mem, void* stream) {
+    if (!ok_dtype(dtype) || !dims || !in || !out) return fail(GB_ERR_ARG, "bad arguments");
+    for (int d = 0; d < 3; d++)
+        if (dims[d] < 1) return fail(GB_ERR_ARG, "bad dims");
+    cudaStream_t s = (cudaStream_t)stream;
+    pool_keep_memory();
+    if (mem == GB_DEVICE) return restrict3_device(dtype, (const i64*)dims, in, scale, out, s);
+    i64 it = dims[0] * dims[1] * dims[2];
+    i64 ot = gb_restrict_size(dims[0]) * gb_restrict_size(dims[1]) * gb_restrict_size(dims[2]);
+    struct Ctx { int dtype; const i64* dims; double scale; } ctx{dtype, (const i64*)dims, scale};
+    return mg_host(dtype, it, ot, in, out, s, [](void* c, const void* i, void* o, cudaStream_t st) {
+        Ctx* x = (Ctx*)c;
+        return restrict3_device(x->dtype, x->dims, i, x->scale, o, st);
+    }, &ctx);
+}
+
+int gb_prolong3(int dtype, const int64_t* dims, const void* in, const int64_t* out_dims, void* out, int mem, void* stream) {
+    if (!ok_dtype(dtype) || !dims || !out_dims || !in || !out) return fail(GB_ERR_ARG, "bad arguments");
+    i64 it = 1, ot = 1;
+    for (int d = 0; d < 3; d++) {
+        if (dims[d] < 1) return fail(GB_ERR_ARG, "bad dims");
+        i64 m = dims[d];
+        if (out_dims[d] > dims[d]) {
+            int rc = gb_prolong_size(dims[d], out_dims[d], nullptr);
+            if (rc) return rc;
+            m = out_dims[d];
+        }
+        it *= dims[d];
+        ot *= m;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    pool_keep_memory();
+    if (mem == GB_DEVICE) return prolong3_device(dtype, (const i64*)dims, in, (const i64*)out_dims, out, s);
+    struct Ctx { int dtype; const i64* dims; const i64* od; } ctx{dtype, (const i64*)dims, (const i64*)out_dims};
+    return mg_host(dtype, it, ot, in, out, s, [](void* c, const void* i, void* o, cudaStream_t st) {
+        Ctx* x = (Ctx*)c;
+        return prolong3_device(x->dtype, x->dims, i, x->od, o, st);
+    }, &ctx);
+}
+
+}  // extern "C"

@@ -1,0 +1,90 @@
+// common.cuh -- shared definitions of libgridb200 (sm_100a only).
+//
+// Numerics contract: every translation unit of this library is compiled with -fmad=false, so a
+// plain `a*b + c` is a rounded multiply followed by a rounded add exactly as the reference's
+// Julia code evaluates it.  The GB_FAST paths call fma() explicitly.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/gridb200.h"
+
+namespace gb {
+
+typedef long long i64;
+typedef unsigned long long u64;
+
+constexpr int MAXD = 4;  // dimension-specialised kernels (the reference unrolls 1..4, src/interp.jl:1047-1125)
+
+// BC families with identical index rules (src/interp.jl:594-783): nil/nan/na share one
+// (they differ only in how an invalid location is reported), nearest/fill share one.
+enum { BCF_NIL = 0, BCF_REFLECT = 1, BCF_PERIODIC = 2, BCF_CLAMP = 3 };
+__host__ __device__ constexpr int bc_family(int bc) {
+    return bc <= GB_BC_NA ? BCF_NIL : bc == GB_BC_REFLECT ? BCF_REFLECT : bc == GB_BC_PERIODIC ? BCF_PERIODIC : BCF_CLAMP;
+}
+inline bool needs_shift(int bc, int order) {  // setx, src/interp.jl:97-139
+    return bc == GB_BC_FILL || (order == GB_CUBIC && bc <= GB_BC_NA);
+}
+
+// ---- error plumbing -----------------------------------------------------------------------
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+#define GB_CUDA(expr)                                              \
+    do {                                                           \
+        cudaError_t _e = (expr);                                   \
+        if (_e != cudaSuccess) return gb::cuda_fail(_e, #expr);    \
+    } while (0)
+
+extern std::atomic<long long> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int num_sms();
+
+template <typename T> struct dtype_of;
+template <> struct dtype_of<float> { static constexpr int value = GB_F32; };
+template <> struct dtype_of<double> { static constexpr int value = GB_F64; };
+
+// ---- evaluation launch interface (eval_f32_*.cu / eval_f64_*.cu) -----------------------------
+template <int N> struct EvalParams {
+    const void* coefs;
+    i64 total;            // elements in the stored array
+    int len[N];           // stored dims
+    i64 stride[N];        // element strides (column-major)
+    const void* xp[N];    // per-dimension coordinate base pointers
+    i64 xqs;              // element stride between consecutive queries
+    int xdtype;           // GB_F32 / GB_F64
+    int has_aff;
+    double aff[N][4];     // kind, start, step, divisor
+    int shift;            // +1 of setx
+    void* val;
+    void* grad;
+    void* hess;
+    i64 nq;
+    i64 q0;               // index of this launch's first query in the caller's batch
+    u64* first_invalid;   // device, atomicMin target (BCnil) or NULL
+};
+
+// One entry per (dtype, N); each dispatches on (order, bc family, output mode, flags).
+// outmode: 0 value, 1 value+gradient, 2 value+gradient+hessian.
+#define GB_DECL_EVAL(T, N) int launch_eval_##T##_##N(const EvalParams<N>& p, int order, int bcf, int outmode, int flags, cudaStream_t s);
+GB_DECL_EVAL(float, 1) GB_DECL_EVAL(float, 2) GB_DECL_EVAL(float, 3) GB_DECL_EVAL(float, 4)
+GB_DECL_EVAL(double, 1) GB_DECL_EVAL(double, 2) GB_DECL_EVAL(double, 3) GB_DECL_EVAL(double, 4)
+#undef GB_DECL_EVAL
+
+// ---- prefilter (prefilter.cu) -------------------------------------------------------------------
+int invert_device(int dtype, int ndim, const i64* dims, void* data, int bc, int order, const int* dimlist, int ndl,
+                  cudaStream_t s);
+int pad1_device(int dtype, int ndim, const i64* dims, const void* in, double fill, void* out, cudaStream_t s);
+
+// ---- restrict / prolong (multigrid.cu) ------------------------------------------------------------
+int restrict_device(int dtype, int ndim, const i64* dims, const void* in, int dim, double scale, void* out, cudaStream_t s);
+int prolong_device(int dtype, int ndim, const i64* dims, const void* in, int dim, i64 len, void* out, cudaStream_t s);
+int restrict3_device(int dtype, const i64* dims, const void* in, double scale, void* out, cudaStream_t s);
+int prolong3_device(int dtype, const i64* dims, const void* in, const i64* odims, void* out, cudaStream_t s);
+
+int synth_device(int dtype, void* out, i64 n, u64 seed, double lo, double hi, i64 first, cudaStream_t s);
+
+}  // namespace gb

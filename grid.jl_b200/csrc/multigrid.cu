@@ -1,0 +1,320 @@
+// multigrid.cu -- restrict / prolong (src/restrict_prolong.jl:10-48, 103-140) on sm_100a.
+//
+// The reference accumulates each output line with 3-4 strided BLAS axpy! calls into a zeroed
+// array.  Per output element that is a fixed, short sequence   acc = 0; acc = acc + a_k*x_k ...
+// in the order of the axpy! calls; the kernels below evaluate exactly that sequence (unfused
+// multiply and add; the library is built with -fmad=false), one thread per output element.
+// HBM-bound streaming stencils: no tensor cores, grid sized in multiples of the SM count.
+//
+// restrict3 / prolong3 fuse the reference's dim-by-dim application (mapdim, src/utilities.jl:7-20)
+// for 3-D arrays into one kernel: a CTA stages the input brick it needs in shared memory and
+// applies the three 1-D operators in the reference's order (dim 1, then 2, then 3), rounding every
+// intermediate to T exactly where the staged reference stores it, so the result is bit-identical
+// to the three separate passes while the fine grid is read from HBM once.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace gb {
+namespace {
+
+__host__ __device__ inline i64 rsize(i64 len) { return (len & 1) ? (len + 1) / 2 : len / 2 + 1; }
+
+template <typename T> struct RCoef { T s1, s2, s75, s25; };
+
+// One restricted element j of a line of length L (stride st) starting at a.  axpy! order:
+//  odd  L (:117-122): R[j] += s*A[2j] ; R[j] += s/2*A[2j+1] (j<=n-2) ; R[j] += s/2*A[2j-1] (j>=1)
+//  even L (:130-136): R[j] += .75s*A[2j] (j<=n-2) ; += .25s*A[2j+1] (j<=n-2) ; += .75s*A[2j-1] (j>=1) ; += .25s*A[2j-2] (j>=1)
+template <typename T, typename Load> __device__ __forceinline__ T restrict_elem(Load ld, i64 j, i64 L, i64 n, const RCoef<T>& c) {
+    T acc = (T)0;
+    if (L & 1) {
+        acc = acc + c.s1 * ld(2 * j);
+        if (j <= n - 2) acc = acc + c.s2 * ld(2 * j + 1);
+        if (j >= 1) acc = acc + c.s2 * ld(2 * j - 1);
+    } else {
+        if (j <= n - 2) {
+            acc = acc + c.s75 * ld(2 * j);
+            acc = acc + c.s25 * ld(2 * j + 1);
+        }
+        if (j >= 1) {
+            acc = acc + c.s75 * ld(2 * j - 1);
+            acc = acc + c.s25 * ld(2 * j - 2);
+        }
+    }
+    return acc;
+}
+
+// One prolonged element k of a line of n inputs to len outputs.
+//  odd  len (:26-30): P[2i] = A[i] (copy!) ; P[2i+1] = (0 + .5*A[i]) + .5*A[i+1]
+//  even len (:41-44): P[2i] = (0 + .75*A[i]) + .25*A[i+1] ; P[2i+1] = (0 + .25*A[i]) + .75*A[i+1]
+template <typename T, typename Load> __device__ __forceinline__ T prolong_elem(Load ld, i64 k, i64 len) {
+    const i64 i = k >> 1;
+    if (len & 1) {
+        if ((k & 1) == 0) return ld(i);
+        T acc = (T)0;
+        acc = acc + (T)0.5 * ld(i);
+        acc = acc + (T)0.5 * ld(i + 1);
+        return acc;
+    }
+    T acc = (T)0;
+    if ((k & 1) == 0) {
+        acc = acc + (T)0.75 * ld(i);
+        acc = acc + (T)0.25 * ld(i + 1);
+    } else {
+        acc = acc + (T)0.25 * ld(i);
+        acc = acc + (T)0.75 * ld(i + 1);
+    }
+    return acc;
+}
+
+// ---- per-dimension kernels: array viewed as (inner, L, outer) ---------------------------------
+template <typename T> __global__ void __launch_bounds__(256) restrict_dim_kernel(const T* __restrict__ A, T* __restrict__ R, i64 inner, i64 L, i64 n, i64 outer, RCoef<T> c) {
+    const i64 total = inner * n * outer;
+    const i64 step = (i64)gridDim.x * blockDim.x;
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
+        const i64 lo = e % inner, r = e / inner;
+        const i64 j = r % n, o = r / n;
+        const T* a = A + lo + o * inner * L;
+        R[e] = restrict_elem<T>([&](i64 k) { return __ldg(a + k * inner); }, j, L, n, c);
+    }
+}
+template <typename T> __global__ void __launch_bounds__(256) prolong_dim_kernel(const T* __restrict__ A, T* __restrict__ P, i64 inner, i64 n, i64 len, i64 outer) {
+    const i64 total = inner * len * outer;
+    const i64 step = (i64)gridDim.x * blockDim.x;
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
+        const i64 lo = e % inner, r = e / inner;
+        const i64 k = r % len, o = r / len;
+        const T* a = A + lo + o * inner * n;
+        P[e] = prolong_elem<T>([&](i64 i) { return __ldg(a + i * inner); }, k, len);
+    }
+}
+
+template <typename T> RCoef<T> make_coef(double scale) {
+    RCoef<T> c;
+    c.s1 = (T)scale; c.s2 = (T)(scale / 2); c.s75 = (T)(0.75 * scale); c.s25 = (T)(0.25 * scale);
+    return c;
+}
+inline int grid_for(i64 total, int block) {
+    const i64 need = (total + block - 1) / block;
+    const i64 cap = (i64)num_sms() * 16;
+    return (int)std::max<i64>(1, std::min(need, cap));
+}
+
+template <typename T> int restrict_impl(int ndim, const i64* dims, const T* in, int dim, double scale, T* out, cudaStream_t s) {
+    if (dim < 0 || dim >= ndim) return fail(GB_ERR_ARG, "restrict: dim out of range");
+    i64 inner = 1, outer = 1;
+    for (int d = 0; d < dim; d++) inner *= dims[d];
+    for (int d = dim + 1; d < ndim; d++) outer *= dims[d];
+    const i64 L = dims[dim], n = rsize(L);
+    if (inner * n * outer == 0) return GB_OK;
+    restrict_dim_kernel<T><<<grid_for(inner * n * outer, 256), 256, 0, s>>>(in, out, inner, L, n, outer, make_coef<T>(scale));
+    count_launch();
+    GB_CUDA(cudaGetLastError());
+    return GB_OK;
+}
+template <typename T> int prolong_impl(int ndim, const i64* dims, const T* in, int dim, i64 len, T* out, cudaStream_t s) {
+    if (dim < 0 || dim >= ndim) return fail(GB_ERR_ARG, "prolong: dim out of range");
+    const i64 n = dims[dim];
+    const i64 newsz = (len & 1) ? 2 * n - 1 : 2 * (n - 1);
+    if (newsz != len) return fail(GB_ERR_PROLONG_SIZE, "Cannot prolong a dimension of length " + std::to_string(n) + " to " + std::to_string(len));
+    i64 inner = 1, outer = 1;
+    for (int d = 0; d < dim; d++) inner *= dims[d];
+    for (int d = dim + 1; d < ndim; d++) outer *= dims[d];
+    if (inner * len * outer == 0) return GB_OK;
+    prolong_dim_kernel<T><<<grid_for(inner * len * outer, 256), 256, 0, s>>>(in, out, inner, n, len, outer);
+    count_launch();
+    GB_CUDA(cudaGetLastError());
+    return GB_OK;
+}
+
+// ---- fused 3-D restrict -----------------------------------------------------------------------
+// Output brick (BX,BY,BZ) per CTA.  Needed input range along a dim for outputs [j0, j0+B):
+// odd L: 2*j0-1 .. 2*(j0+B-1)+1 ; even L: 2*j0-2 .. 2*(j0+B-1)+1  -> at most 2B+2 elements.
+// Stage 1 reduces dim 1 straight from global memory into smem S1[(2BZ+2)][(2BY+2)][BX];
+// stage 2 reduces dim 2 into S2[(2BZ+2)][BY][BX]; stage 3 reduces dim 3 and stores.
+template <typename T, int BX, int BY, int BZ> __global__ void __launch_bounds__(256) restrict3_kernel(const T* __restrict__ A, T* __restrict__ R, i64 L1, i64 L2, i64 L3, i64 n1, i64 n2, i64 n3, RCoef<T> c) {
+    constexpr int IY = 2 * BY + 2, IZ = 2 * BZ + 2;
+    extern __shared__ unsigned char smem_raw[];
+    T* S1 = reinterpret_cast<T*>(smem_raw);          // [IZ][IY][BX]
+    T* S2 = S1 + IZ * IY * BX;                        // [IZ][BY][BX]
+    const i64 j1 = (i64)blockIdx.x * BX, j2 = (i64)blockIdx.y * BY, j3 = (i64)blockIdx.z * BZ;
+    const i64 y0 = 2 * j2 - 2, z0 = 2 * j3 - 2;  // input origin of the staged brick in dims 2,3
+    // stage 1: dim-1 restriction for every (y,z) row of the brick
+    for (int e = threadIdx.x; e < IZ * IY * BX; e += blockDim.x) {
+        const int x = e % BX, y = (e / BX) % IY, z = e / (BX * IY);
+        const i64 gx = j1 + x, gy = y0 + y, gz = z0 + z;
+        T v = (T)0;
+        if (gx < n1 && gy >= 0 && gy < L2 && gz >= 0 && gz < L3) {
+            const T* a = A + gy * L1 + gz * L1 * L2;
+            v = restrict_elem<T>([&](i64 k) { return __ldg(a + k); }, gx, L1, n1, c);
+        }
+        S1[e] = v;
+    }
+    __syncthreads();
+    // stage 2: dim-2 restriction
+    for (int e = threadIdx.x; e < IZ * BY * BX; e += blockDim.x) {
+        const int x = e % BX, y = (e / BX) % BY, z = e / (BX * BY);
+        const i64 gy = j2 + y;
+        T v = (T)0;
+        if (gy < n2) {
+            const T* a = S1 + x + (i64)z * IY * BX;
+            v = restrict_elem<T>([&](i64 k) { return a[(k - y0) * BX]; }, gy, L2, n2, c);
+        }
+        S2[e] = v;
+    }
+    __syncthreads();
+    // stage 3: dim-3 restriction + store
+    for (int e = threadIdx.x; e < BZ * BY * BX; e += blockDim.x) {
+        const int x = e % BX, y = (e / BX) % BY, z = e / (BX * BY);
+        const i64 gx = j1 + x, gy = j2 + y, gz = j3 + z;
+        if (gx < n1 && gy < n2 && gz < n3) {
+            const T* a = S2 + x + y * BX;
+            R[gx + gy * n1 + gz * n1 * n2] = restrict_elem<T>([&](i64 k) { return a[(k - z0) * BY * BX]; }, gz, L3, n3, c);
+        }
+    }
+}
+
+template <typename T> int restrict3_impl(const i64* dims, const T* in, double scale, T* out, cudaStream_t s) {
+    const i64 L1 = dims[0], L2 = dims[1], L3 = dims[2];
+    const i64 n1 = rsize(L1), n2 = rsize(L2), n3 = rsize(L3);
+    if (L1 < 2 || L2 < 2 || L3 < 2) {  // degenerate: fall back to the staged path
+        T *t1 = nullptr, *t2 = nullptr;
+        GB_CUDA(cudaMallocAsync((void**)&t1, sizeof(T) * n1 * L2 * L3, s));
+        GB_CUDA(cudaMallocAsync((void**)&t2, sizeof(T) * n1 * n2 * L3, s));
+        i64 d0[3] = {L1, L2, L3}, d1[3] = {n1, L2, L3}, d2[3] = {n1, n2, L3};
+        int rc = restrict_impl<T>(3, d0, in, 0, scale, t1, s);
+        if (!rc) rc = restrict_impl<T>(3, d1, t1, 1, scale, t2, s);
+        if (!rc) rc = restrict_impl<T>(3, d2, t2, 2, scale, out, s);
+        cudaFreeAsync(t1, s);
+        cudaFreeAsync(t2, s);
+        return rc;
+    }
+    constexpr int BX = 32, BY = 4, BZ = 4;
+    constexpr int IY = 2 * BY + 2, IZ = 2 * BZ + 2;
+    const size_t smem = sizeof(T) * (IZ * IY * BX + IZ * BY * BX);
+    auto kern = restrict3_kernel<T, BX, BY, BZ>;
+    GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((n1 + BX - 1) / BX), (unsigned)((n2 + BY - 1) / BY), (unsigned)((n3 + BZ - 1) / BZ));
+    kern<<<grid, 256, smem, s>>>(in, out, L1, L2, L3, n1, n2, n3, make_coef<T>(scale));
+    count_launch();
+    GB_CUDA(cudaGetLastError());
+    return GB_OK;
+}
+
+// ---- fused 3-D prolong ------------------------------------------------------------------------
+// Output brick (BX,BY,BZ); inputs needed along a dim for outputs [k0,k0+B): k0/2 .. (k0+B-1)/2+1.
+template <typename T, int BX, int BY, int BZ> __global__ void __launch_bounds__(256) prolong3_kernel(const T* __restrict__ A, T* __restrict__ P, i64 n1, i64 n2, i64 n3, i64 m1, i64 m2, i64 m3, int do1, int do2, int do3) {
+    constexpr int IY = BY / 2 + 2, IZ = BZ / 2 + 2;
+    extern __shared__ unsigned char smem_raw[];
+    static_assert(IY <= BY && IZ <= BZ, "staging buffers are sized BZ*BY*BX");
+    T* S1 = reinterpret_cast<T*>(smem_raw);  // [nz][ny][BX]  after dim-1 prolongation
+    T* S2 = S1 + BZ * BY * BX;                // [nz][BY][BX]  after dim-2
+    const i64 k1 = (i64)blockIdx.x * BX, k2 = (i64)blockIdx.y * BY, k3 = (i64)blockIdx.z * BZ;
+    const i64 y0 = do2 ? k2 / 2 : k2, z0 = do3 ? k3 / 2 : k3;
+    const int ny = do2 ? IY : BY, nz = do3 ? IZ : BZ;  // staged extents (input coordinates)
+    for (int e = threadIdx.x; e < nz * ny * BX; e += blockDim.x) {
+        const int x = e % BX, y = (e / BX) % ny, z = e / (BX * ny);
+        const i64 gx = k1 + x, gy = y0 + y, gz = z0 + z;
+        T v = (T)0;
+        if (gx < m1 && gy < n2 && gz < n3) {
+            const T* a = A + gy * n1 + gz * n1 * n2;
+            v = do1 ? prolong_elem<T>([&](i64 i) { return i < n1 ? __ldg(a + i) : (T)0; }, gx, m1) : __ldg(a + gx);
+        }
+        S1[e] = v;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nz * BY * BX; e += blockDim.x) {
+        const int x = e % BX, y = (e / BX) % BY, z = e / (BX * BY);
+        const i64 gy = k2 + y;
+        T v = (T)0;
+        if (gy < m2) {
+            const T* a = S1 + x + (i64)z * BX * ny;
+            v = do2 ? prolong_elem<T>([&](i64 i) { return a[(i - y0) * BX]; }, gy, m2) : a[y * BX];
+        }
+        S2[e] = v;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < BZ * BY * BX; e += blockDim.x) {
+        const int x = e % BX, y = (e / BX) % BY, z = e / (BX * BY);
+        const i64 gx = k1 + x, gy = k2 + y, gz = k3 + z;
+        if (gx < m1 && gy < m2 && gz < m3) {
+            const T* a = S2 + x + y * BX;
+            P[gx + gy * m1 + gz * m1 * m2] = do3 ? prolong_elem<T>([&](i64 i) { return a[(i - z0) * BY * BX]; }, gz, m3) : a[z * BY * BX];
+        }
+    }
+}
+
+template <typename T> int prolong3_impl(const i64* dims, const T* in, const i64* odims, T* out, cudaStream_t s) {
+    const i64 n1 = dims[0], n2 = dims[1], n3 = dims[2];
+    i64 m[3];
+    int doit[3];
+    for (int d = 0; d < 3; d++) {  // prolong only if the target is larger (src/restrict_prolong.jl:94)
+        doit[d] = odims[d] > dims[d];
+        m[d] = dims[d];
+        if (doit[d]) {
+            const i64 newsz = (odims[d] & 1) ? 2 * dims[d] - 1 : 2 * (dims[d] - 1);
+            if (newsz != odims[d]) return fail(GB_ERR_PROLONG_SIZE, "Cannot prolong a dimension of length " + std::to_string(dims[d]) + " to " + std::to_string(odims[d]));
+            m[d] = odims[d];
+        }
+    }
+    if (m[0] * m[1] * m[2] == 0) return GB_OK;
+    constexpr int BX = 64, BY = 8, BZ = 8;
+    const size_t smem = sizeof(T) * 2 * (size_t)BZ * BY * BX;  // S1 and S2, each at most BZ*BY*BX
+    auto kern = prolong3_kernel<T, BX, BY, BZ>;
+    GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((m[0] + BX - 1) / BX), (unsigned)((m[1] + BY - 1) / BY), (unsigned)((m[2] + BZ - 1) / BZ));
+    kern<<<grid, 256, smem, s>>>(in, out, n1, n2, n3, m[0], m[1], m[2], doit[0], doit[1], doit[2]);
+    count_launch();
+    GB_CUDA(cudaGetLastError());
+    return GB_OK;
+}
+
+// ---- synthetic inputs ---------------------------------------------------------------------------
+__device__ __forceinline__ u64 splitmix64(u64 z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+template <typename T> __global__ void __launch_bounds__(256) synth_kernel(T* out, i64 n, u64 seed, double lo, double hi, i64 first) {
+    const i64 step = (i64)gridDim.x * blockDim.x;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += step) {
+        const double u = (double)(splitmix64(seed + (u64)(first + k)) >> 11) * (1.0 / 9007199254740992.0);
+        out[k] = (T)(lo + (hi - lo) * u);
+    }
+}
+
+}  // namespace
+
+int restrict_device(int dtype, int ndim, const i64* dims, const void* in, int dim, double scale, void* out, cudaStream_t s) {
+    if (dtype == GB_F64) return restrict_impl<double>(ndim, dims, (const double*)in, dim, scale, (double*)out, s);
+    if (dtype == GB_F32) return restrict_impl<float>(ndim, dims, (const float*)in, dim, scale, (float*)out, s);
+    return fail(GB_ERR_ARG, "bad dtype");
+}
+int prolong_device(int dtype, int ndim, const i64* dims, const void* in, int dim, i64 len, void* out, cudaStream_t s) {
+    if (dtype == GB_F64) return prolong_impl<double>(ndim, dims, (const double*)in, dim, len, (double*)out, s);
+    if (dtype == GB_F32) return prolong_impl<float>(ndim, dims, (const float*)in, dim, len, (float*)out, s);
+    return fail(GB_ERR_ARG, "bad dtype");
+}
+int restrict3_device(int dtype, const i64* dims, const void* in, double scale, void* out, cudaStream_t s) {
+    if (dtype == GB_F64) return restrict3_impl<double>(dims, (const double*)in, scale, (double*)out, s);
+    if (dtype == GB_F32) return restrict3_impl<float>(dims, (const float*)in, scale, (float*)out, s);
+    return fail(GB_ERR_ARG, "bad dtype");
+}
+int prolong3_device(int dtype, const i64* dims, const void* in, const i64* odims, void* out, cudaStream_t s) {
+    if (dtype == GB_F64) return prolong3_impl<double>(dims, (const double*)in, odims, (double*)out, s);
+    if (dtype == GB_F32) return prolong3_impl<float>(dims, (const float*)in, odims, (float*)out, s);
+    return fail(GB_ERR_ARG, "bad dtype");
+}
+int synth_device(int dtype, void* out, i64 n, u64 seed, double lo, double hi, i64 first, cudaStream_t s) {
+    if (n <= 0) return GB_OK;
+    const int grid = grid_for(n, 256);
+    if (dtype == GB_F64) synth_kernel<double><<<grid, 256, 0, s>>>((double*)out, n, seed, lo, hi, first);
+    else if (dtype == GB_F32) synth_kernel<float><<<grid, 256, 0, s>>>((float*)out, n, seed, lo, hi, first);
+    else return fail(GB_ERR_ARG, "bad dtype");
+    count_launch();
+    GB_CUDA(cudaGetLastError());
+    return GB_OK;
+}
+
+}  // namespace gb

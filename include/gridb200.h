@@ -1,0 +1,157 @@
+/* gridb200.h -- C ABI of libgridb200.so, the B200 (sm_100a) engine behind Grid.jl's batched
+ * evaluation hot path.
+ *
+ * The reference (timholy/Grid.jl) is pure Julia and has no FFI boundary of its own; its
+ * "operator API" is the set of exported generic functions (src/Grid.jl:28-70).  Each entry point
+ * below names the reference function(s) it replaces (file:line under the reference tree); the
+ * Julia `ccall` stubs that bind them are in INTEGRATION.md and grid.jl_b200/julia/GridB200.jl.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns an int status (GB_OK == 0) and never
+ *     throws or aborts; gb_last_error() gives a thread-local message for the last failure.
+ *   - arrays are dense, column-major (Julia layout, dim 1 contiguous), dims are int64.
+ *   - `mem` says where EVERY data pointer of that call lives: GB_HOST (the library stages the
+ *     copies itself; the call returns when the results are in the caller's buffers) or GB_DEVICE
+ *     (pointers are device pointers valid on the current device; work is enqueued on `stream`,
+ *     a cudaStream_t passed as void*, NULL = default stream, and the call does not synchronise
+ *     unless it has to report a per-query error).
+ *   - query batches: coordinate d of query q is read at x[q*x_qstride + d*x_dstride] (elements of
+ *     `xdtype`), so a Julia N x nq Matrix is (x_qstride=N, x_dstride=1) and an nq x N one is (1, nq).
+ *   - outputs: val[nq], grad[N*nq] (N contiguous per query), hess[N*N*nq] (full symmetric N x N
+ *     per query, both triangles stored, src/interp.jl:223-227).
+ *   - handles are immutable after creation: any number of host threads may evaluate one grid.
+ */
+#ifndef GRIDB200_H
+#define GRIDB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GB_VERSION 10100 /* 1.1.0 */
+
+typedef struct gb_grid gb_grid; /* opaque: InterpGrid{T,N,BC,IT} (src/interp.jl:42-47) on the device */
+
+enum { GB_F32 = 0, GB_F64 = 1 };
+/* src/boundaryconditions.jl:5-12 */
+enum { GB_BC_NIL = 0, GB_BC_NAN = 1, GB_BC_NA = 2, GB_BC_REFLECT = 3, GB_BC_PERIODIC = 4, GB_BC_NEAREST = 5, GB_BC_FILL = 6 };
+/* src/interpflags.jl:4-7 (npoints = order+1, src/interp.jl:579-582) */
+enum { GB_NEAREST = 0, GB_LINEAR = 1, GB_QUADRATIC = 2, GB_CUBIC = 3 };
+enum { GB_OUT_VAL = 1, GB_OUT_GRAD = 2, GB_OUT_HESS = 4 };
+enum { GB_HOST = 0, GB_DEVICE = 1 };
+enum {
+    GB_OK = 0,
+    GB_ERR_ARG = 1,              /* ErrorException: arity / shape (src/interp.jl:88-90,159-161,206-211) */
+    GB_ERR_INVALID_LOCATION = 2, /* ErrorException("Invalid location"), BCnil only (src/interp.jl:402-404) */
+    GB_ERR_UNSUPPORTED = 3,      /* MethodError in the reference: Cubic with reflect/periodic/nearest/fill,
+                                    valgradhess on Nearest/Linear, ndim > 4 */
+    GB_ERR_CUDA = 4,
+    GB_ERR_DIM = 5,              /* DimensionMismatch (src/coord.jl:7) */
+    GB_ERR_PROLONG_SIZE = 6      /* "Cannot prolong a dimension of length n to len" (src/restrict_prolong.jl:328-330) */
+};
+/* gb_eval flags */
+enum {
+    GB_EXACT = 0, /* default: the reference's operation order (weight products, sequential sum,
+                     no FMA contraction) -> bit-identical to the CPU oracle */
+    GB_FAST = 1   /* separable dimension-by-dimension contraction with FMA; same taps and weights,
+                     different rounding (validated to a few ulp of sum|w_i a_i|) */
+};
+
+int gb_version(void);
+const char* gb_last_error(void);
+int gb_device_count(int* n);
+int gb_set_device(int device); /* device used by subsequent calls from the calling thread */
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t gb_launch_count(void);
+
+/* ---- grid lifetime ------------------------------------------------------------------------ */
+/* InterpGrid(A, BC, IT) / InterpGrid(A, fill::Number, IT)  (src/interp.jl:48-72): copies the
+ * samples, pads by one element per side where the reference does (BCfill with `fill`; Cubic with
+ * BCnil/nan/na with 0), runs interp_invert! on the device and keeps the coefficients resident.
+ * bc == GB_BC_FILL selects the fill constructor (prefilter uses the BCnearest system, :68). */
+int gb_grid_create(gb_grid** out, int dtype, int ndim, const int64_t* dims, const void* samples, int mem,
+                   int bc, int order, double fill, void* stream);
+/* Adopt an already padded + prefiltered coefficient array (a copy is made).  This is how a
+ * replica is built on every other GPU after one rank has prefiltered and broadcast the
+ * coefficients; `stored_dims` are the padded dims. */
+int gb_grid_create_from_coefs(gb_grid** out, int dtype, int ndim, const int64_t* stored_dims, const void* coefs,
+                              int mem, int bc, int order, double fill, void* stream);
+/* size(G) (src/interp.jl:853-856) and the stored (padded) size; any out pointer may be NULL */
+int gb_grid_info(const gb_grid* g, int* dtype, int* ndim, int64_t* user_dims, int64_t* stored_dims, int* bc,
+                 int* order, double* fill);
+int gb_grid_coefs_device(const gb_grid* g, void** device_ptr); /* borrowed, read-only */
+int gb_grid_coefs_download(const gb_grid* g, void* host_out);  /* G.coefs */
+int gb_grid_destroy(gb_grid* g);
+
+/* ---- prefilter ---------------------------------------------------------------------------- */
+/* interp_invert!(A, BC, IT, dimlist) in place (src/interp.jl:909-953); dimlist is 0-based;
+ * a no-op for Nearest/Linear (:909-912). */
+int gb_invert(int dtype, int ndim, const int64_t* dims, void* data, int mem, int bc, int order,
+              const int* dimlist, int ndimlist, void* stream);
+/* pad1(A, f, 1:N) (src/interp.jl:1305-1310): out has dims+2 */
+int gb_pad1(int dtype, int ndim, const int64_t* dims, const void* in, double fill, void* out, int mem, void* stream);
+
+/* ---- evaluation --------------------------------------------------------------------------- */
+/* Batched getindex / valgrad / valgradhess == a loop of the scalar calls
+ * (src/interp.jl:142-156, 158-203, 205-270).  x holds USER coordinates (the +1 of setx for
+ * BCfill / padded Cubic, :97-139, is applied inside, in the coordinate's own type).
+ * affine: NULL, or ndim rows [kind, start, step, divisor] for CoordInterpGrid
+ *   (kind 0 FloatRange, 1 StepRange, 2 UnitRange: coordlookup src/coord.jl:30-32; gradients are
+ *   scaled by coordiscale :54-56).
+ * val/grad/hess may be NULL when not in out_mask.  Invalid locations produce NaN in every
+ * requested output; for GB_BC_NIL the call additionally returns GB_ERR_INVALID_LOCATION and the
+ * index of the first offending query in *first_invalid (-1 if none; pass NULL to skip the check
+ * and keep a GB_DEVICE call fully asynchronous). */
+int gb_eval(const gb_grid* g, int out_mask, int64_t nq, const void* x, int xdtype, int64_t x_qstride,
+            int64_t x_dstride, const double* affine, void* val, void* grad, void* hess, int mem, int flags,
+            int64_t* first_invalid, void* stream);
+/* Same, coordinates as ndim separate vectors (a Julia tuple of Vectors): xs[d][q]. */
+int gb_eval_soa(const gb_grid* g, int out_mask, int64_t nq, const void* const* xs, int xdtype,
+                const double* affine, void* val, void* grad, void* hess, int mem, int flags,
+                int64_t* first_invalid, void* stream);
+/* Tensor-product getindex(G, xvec, yvec, ...) (src/interp.jl:273-306): out[i1,i2,...] =
+ * G[vecs[0][i1], vecs[1][i2], ...], column-major, lens[d] = length of vecs[d]. */
+int gb_eval_outer(const gb_grid* g, const int64_t* lens, const void* const* vecs, int xdtype,
+                  const double* affine, void* out, int mem, int flags, void* stream);
+
+/* ---- restrict / prolong ------------------------------------------------------------------- */
+int64_t gb_restrict_size(int64_t len);                           /* src/restrict_prolong.jl:334 */
+int gb_prolong_size(int64_t n, int64_t len, int64_t* newlen);    /* :322-332, GB_ERR_PROLONG_SIZE on mismatch */
+/* restrict(A, dim, scale) (:103-140), dim 0-based; out has dims with dims[dim] -> restrict_size */
+int gb_restrict(int dtype, int ndim, const int64_t* dims, const void* in, int dim, double scale, void* out,
+                int mem, void* stream);
+/* prolong(A, dim, len) (:10-48); out has dims with dims[dim] -> len */
+int gb_prolong(int dtype, int ndim, const int64_t* dims, const void* in, int dim, int64_t len, void* out,
+               int mem, void* stream);
+/* restrict(A, [true,true,true], scale) on a 3-D array as ONE pass over the fine grid; the
+ * per-dim intermediates are rounded exactly as the staged reference does, so the result is
+ * bit-identical to gb_restrict applied to dims 0,1,2 in turn (src/utilities.jl:7-20). */
+int gb_restrict3(int dtype, const int64_t* dims, const void* in, double scale, void* out, int mem, void* stream);
+/* prolong(A, [s1,s2,s3]) on a 3-D array as one pass (src/restrict_prolong.jl:87-100). */
+int gb_prolong3(int dtype, const int64_t* dims, const void* in, const int64_t* out_dims, void* out, int mem,
+                void* stream);
+
+/* ---- device / pinned memory helpers (device-resident query and output buffers) -------------- */
+int gb_device_alloc(void** ptr, size_t bytes);
+int gb_device_free(void* ptr);
+int gb_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream);
+int gb_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream);
+int gb_host_alloc_pinned(void** ptr, size_t bytes);
+int gb_host_free_pinned(void* ptr);
+int gb_host_register(void* ptr, size_t bytes);
+int gb_host_unregister(void* ptr);
+int gb_stream_synchronize(void* stream);
+
+/* ---- synthetic inputs ------------------------------------------------------ */
+/* out[k] = (T)(lo + (hi-lo)*u(splitmix64(seed + first + k))), u from the top 53 bits; replayable
+ * on the CPU for any index subset. */
+int gb_synth_uniform(int dtype, void* device_out, int64_t n, uint64_t seed, double lo, double hi, int64_t first,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRIDB200_H */
