@@ -61,9 +61,10 @@ template <typename T> __device__ __forceinline__ bool representable(T x) {
 // Returns validity (src/interp.jl:585-591 with D2/D4); c[] receives 0-based coordinates.  A
 // coordinate may lie outside [0,len) only for a tap the reference would not dereference or that
 // the D1 guard skips.
-template <typename T, int ORDER, int BCF> __device__ __forceinline__ bool dim_taps(T x, int len, int (&c)[ORDER + 1], T& dx) {
+template <typename T, int ORDER, int BCF> __device__ __forceinline__ bool dim_taps(T x, int len, int (&c)[ORDER + 1], T& dx, bool& iswrap) {
     constexpr bool F32 = sizeof(T) == 4;
     bool valid = representable(x);
+    iswrap = false;  // only consulted for InterpLinear (see the kernel)
     const double xd = (double)x;
     if constexpr (ORDER == GB_NEAREST) {  // :620-624
         if constexpr (BCF == BCF_NIL) {
@@ -94,12 +95,13 @@ template <typename T, int ORDER, int BCF> __device__ __forceinline__ bool dim_ta
             }
             c[0] = ix - 1;
             c[1] = (int)wrap1<BCF_REFLECT>(ixp, len) - 1;
+            iswrap = (ix == ixp && dx > (T)0);
         } else {  // :632-641
             i64 ifx = floor_ll(xs);
             dx = xs - (T)ifx;
             ifx -= (xs < (T)ifx) ? 1 : 0;
             i64 ix = wrap1<BCF>(ifx, len);
-            bool iswrap = (ix == len && dx > (T)0) || (ix == 1 && ifx < 1);
+            iswrap = (ix == len && dx > (T)0) || (ix == 1 && ifx < 1);
             c[0] = (int)ix - 1;
             c[1] = iswrap ? (int)ix - 1 : (int)wrap1<BCF>(ix + 1, len) - 1;
         }
@@ -416,22 +418,40 @@ template <typename T, int N, int ORDER, int BCF, int OUTMODE, bool FAST>
 __global__ void __launch_bounds__(128) eval_kernel(const EvalParams<N> p) {
     constexpr int L = ORDER + 1;
     constexpr int NP = num_passes(N, OUTMODE);
-    constexpr bool GUARD = (BCF == BCF_NIL) && (ORDER == GB_LINEAR || ORDER == GB_CUBIC);
+    // D1 guard: taps that can fall outside the array (upper-edge tap of Linear on the offset path,
+    // 4th tap of Cubic at x == len-1).
+    constexpr bool GUARD = (ORDER == GB_LINEAR) || (BCF == BCF_NIL && ORDER == GB_CUBIC);
     const T* __restrict__ A = (const T*)p.coefs;
     const i64 step = (i64)gridDim.x * blockDim.x;
     for (i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x; q < p.nq; q += step) {
         i64 off[N][L];
+        int c[N][L];
         T w[3][N][L];
-        bool valid = true;
+        bool valid = true, anywrap = false;
 #pragma unroll
         for (int d = 0; d < N; d++) {
             const T x = fetch_coord<T, N>(p, d, q);
-            int c[L];
             T dx;
-            valid = dim_taps<T, ORDER, BCF>(x, p.len[d], c, dx) && valid;
+            bool iswrap;
+            valid = dim_taps<T, ORDER, BCF>(x, p.len[d], c[d], dx, iswrap) && valid;
+            anywrap = anywrap || iswrap;
             weights<ORDER, (OUTMODE >= 1), (OUTMODE >= 2)>(dx, w[0][d], w[1][d], w[2][d]);
+        }
+        // set_position (src/interp.jl:406-428): unless SOME dimension reported a wrap, the reference
+        // addresses taps through the precomputed offset table (ix + 0, ix + 1, ...) and ignores
+        // coord1d.  The two differ only for InterpLinear exactly on a grid line at the upper edge
+        // (ix == len, dx == 0): the second tap is then ix+1 (its value weight is 0, its gradient
+        // weight is not).  Reproduced for bit-parity; the D1 guard keeps the load in bounds.
+        if constexpr (ORDER == GB_LINEAR && BCF != BCF_NIL) {
+            if (!anywrap) {
 #pragma unroll
-            for (int i = 0; i < L; i++) off[d][i] = (i64)c[i] * p.stride[d];
+                for (int d = 0; d < N; d++) c[d][1] = c[d][0] + 1;
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < N; d++) {
+#pragma unroll
+            for (int i = 0; i < L; i++) off[d][i] = (i64)c[d][i] * p.stride[d];
         }
         T acc[NP];
         if constexpr (!FAST) {
