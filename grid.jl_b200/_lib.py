@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libgridb200.so")
 GB_F32, GB_F64 = 0, 1
 GB_HOST, GB_DEVICE = 0, 1
 GB_OUT_VAL, GB_OUT_GRAD, GB_OUT_HESS = 1, 2, 4
-GB_EXACT, GB_FAST = 0, 1
+GB_EXACT, GB_FAST, GB_TILED, GB_PLAIN = 0, 1, 2, 4
 (GB_OK, GB_ERR_ARG, GB_ERR_INVALID_LOCATION, GB_ERR_UNSUPPORTED, GB_ERR_CUDA, GB_ERR_DIM, GB_ERR_PROLONG_SIZE) = range(7)
 
 vp, i64, i32, f64, u64 = C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_uint64

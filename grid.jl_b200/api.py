@@ -424,7 +424,7 @@ class InterpGrid(AbstractInterpGrid):
         L.check(fn(C.byref(self._h), a.dtype, a.ndim, _i64s(a.shape), a.ptr, a.mem, bcode, order, fill, a.stream()))
         self._lib = lib
         dt, nd = C.c_int(), C.c_int()
-        ud, sd = (C.c_int64 * 4)(), (C.c_int64 * 4)()
+        ud, sd = (C.c_int64 * 8)(), (C.c_int64 * 8)()
         L.check(lib.gb_grid_info(self._h, C.byref(dt), C.byref(nd), ud, sd, None, None, None))
         self.ndim = nd.value
         self.dtype_code = dt.value
@@ -491,7 +491,7 @@ class InterpGrid(AbstractInterpGrid):
         return flat.reshape(self._stored[::-1]).permute(*range(self.ndim - 1, -1, -1))
 
     # -- evaluation core --
-    def _eval(self, X, mask, val=None, grad=None, hess=None, fast=False, affine=None):
+    def _eval(self, X, mask, val=None, grad=None, hess=None, fast=False, affine=None, tiled=None):
         N = self.ndim
         q = X if isinstance(X, _Queries) else _Queries(X, N)
         dt = self.dtype_code
@@ -512,7 +512,7 @@ class InterpGrid(AbstractInterpGrid):
             aff = (C.c_double * (4 * N))(*[v for row in affine for v in row])
         bad = C.c_int64(-1)
         pbad = C.byref(bad) if self.BC is BCnil else None
-        flags = L.GB_FAST if fast else L.GB_EXACT
+        flags = (L.GB_FAST if fast else L.GB_EXACT) | (0 if tiled is None else (L.GB_TILED if tiled else L.GB_PLAIN))
         if q.cols is not None:
             rc = self._lib.gb_eval_soa(self._h, mask, q.nq, q.ptrs, q.xdtype, aff, pv, pg, ph, q.mem, flags, pbad, q.stream())
         else:
@@ -618,39 +618,43 @@ def valgradhess(*args):
 # ---- batched entry points ----------------------------------------------------------------------------------
 
 
-def getindex_(out, G, X, fast=False):
+# `fast` selects the GB_FAST contraction; `tiled` (None = library heuristic, True / False = force)
+# only changes scheduling (binned shared-memory bricks vs plain global gathers), never results.
+
+
+def getindex_(out, G, X, fast=False, tiled=None):
     ig = _grid_of(G)
-    ig._eval(X, L.GB_OUT_VAL, val=out, fast=fast, affine=G.affine)
+    ig._eval(X, L.GB_OUT_VAL, val=out, fast=fast, affine=G.affine, tiled=tiled)
     return out
 
 
-def valgrad_(v, g, G, X, fast=False):
+def valgrad_(v, g, G, X, fast=False, tiled=None):
     ig = _grid_of(G)
-    ig._eval(X, L.GB_OUT_VAL | L.GB_OUT_GRAD, val=v, grad=g, fast=fast, affine=G.affine)
+    ig._eval(X, L.GB_OUT_VAL | L.GB_OUT_GRAD, val=v, grad=g, fast=fast, affine=G.affine, tiled=tiled)
     return v
 
 
-def valgradhess_(v, g, h, G, X, fast=False):
+def valgradhess_(v, g, h, G, X, fast=False, tiled=None):
     if isinstance(G, CoordInterpGrid):
         raise MethodError(L.GB_ERR_UNSUPPORTED, "valgradhess has no method for CoordInterpGrid")
-    G._eval(X, L.GB_OUT_VAL | L.GB_OUT_GRAD | L.GB_OUT_HESS, val=v, grad=g, hess=h, fast=fast)
+    G._eval(X, L.GB_OUT_VAL | L.GB_OUT_GRAD | L.GB_OUT_HESS, val=v, grad=g, hess=h, fast=fast, tiled=tiled)
     return v
 
 
-def getindex_batch(G, X, fast=False):
-    return _grid_of(G)._eval(X, L.GB_OUT_VAL, fast=fast, affine=G.affine)[0]
+def getindex_batch(G, X, fast=False, tiled=None):
+    return _grid_of(G)._eval(X, L.GB_OUT_VAL, fast=fast, affine=G.affine, tiled=tiled)[0]
 
 
-def valgrad_batch(G, X, fast=False):
-    v, g, _ = _grid_of(G)._eval(X, L.GB_OUT_VAL | L.GB_OUT_GRAD, fast=fast, affine=G.affine)
+def valgrad_batch(G, X, fast=False, tiled=None):
+    v, g, _ = _grid_of(G)._eval(X, L.GB_OUT_VAL | L.GB_OUT_GRAD, fast=fast, affine=G.affine, tiled=tiled)
     return v, g
 
 
-def valgradhess_batch(G, X, fast=False):
+def valgradhess_batch(G, X, fast=False, tiled=None):
     """h[q] is the symmetric N x N Hessian of query q."""
     if isinstance(G, CoordInterpGrid):
         raise MethodError(L.GB_ERR_UNSUPPORTED, "valgradhess has no method for CoordInterpGrid")
-    return G._eval(X, L.GB_OUT_VAL | L.GB_OUT_GRAD | L.GB_OUT_HESS, fast=fast)
+    return G._eval(X, L.GB_OUT_VAL | L.GB_OUT_GRAD | L.GB_OUT_HESS, fast=fast, tiled=tiled)
 
 
 # ---- CoordInterpGrid (src/coord.jl:3-69) ----------------------------------------------------------------------

@@ -56,7 +56,7 @@ using namespace gb;
 struct gb_grid {
     int dtype, ndim, bc, order;
     double fill;
-    i64 user_dims[MAXD], stored_dims[MAXD];
+    i64 user_dims[MAXG], stored_dims[MAXG];
     i64 total;
     void* coefs;
     int device;
@@ -66,13 +66,16 @@ struct gb_grid {
 static int check_grid_args(int dtype, int ndim, const int64_t* dims, int bc, int order) {
     if (!ok_dtype(dtype)) return fail(GB_ERR_ARG, "dtype must be GB_F32 or GB_F64");
     if (ndim < 1) return fail(GB_ERR_ARG, "ndim must be >= 1");
-    if (ndim > MAXD) return fail(GB_ERR_UNSUPPORTED, "ndim > 4 is not supported by the dimension-specialised kernels");
+    if (ndim > MAXG) return fail(GB_ERR_UNSUPPORTED, "ndim > 8 is not supported");
     if (bc < GB_BC_NIL || bc > GB_BC_FILL) return fail(GB_ERR_ARG, "bad boundary condition");
     if (order < GB_NEAREST || order > GB_CUBIC) return fail(GB_ERR_ARG, "bad interpolation order");
     if (order == GB_CUBIC && bc > GB_BC_NA) return fail(GB_ERR_UNSUPPORTED, "InterpCubic supports only BCnil/BCnan/BCna (README.md:146)");
     if (!dims) return fail(GB_ERR_ARG, "dims is NULL");
     for (int d = 0; d < ndim; d++)
         if (dims[d] < 1 || dims[d] > (1ll << 30)) return fail(GB_ERR_ARG, "every dimension must be in [1, 2^30]");
+    double tot = 1;
+    for (int d = 0; d < ndim; d++) tot *= (double)(dims[d] + 2);
+    if (tot > 2147483648.0) return fail(GB_ERR_ARG, "grids are limited to 2^31 stored elements (32-bit tap offsets)");
     return GB_OK;
 }
 
@@ -176,7 +179,7 @@ int gb_invert(int dtype, int ndim, const int64_t* dims, void* data, int mem, int
 }
 
 int gb_pad1(int dtype, int ndim, const int64_t* dims, const void* in, double fill, void* out, int mem, void* stream) {
-    if (!ok_dtype(dtype) || ndim < 1 || ndim > MAXD || !dims || !in || !out) return fail(GB_ERR_ARG, "bad arguments");
+    if (!ok_dtype(dtype) || ndim < 1 || ndim > MAXG || !dims || !in || !out) return fail(GB_ERR_ARG, "bad arguments");
     cudaStream_t s = (cudaStream_t)stream;
     pool_keep_memory();
     if (mem == GB_DEVICE) return pad1_device(dtype, ndim, (const i64*)dims, in, fill, out, s);
@@ -204,7 +207,7 @@ static int new_grid(gb_grid** out, int dtype, int ndim, int bc, int order, doubl
     g->dtype = dtype; g->ndim = ndim; g->bc = bc; g->order = order; g->fill = fill;
     g->coefs = nullptr; g->total = 0;
     g->shift = needs_shift(bc, order) ? 1 : 0;
-    for (int d = 0; d < MAXD; d++) g->user_dims[d] = g->stored_dims[d] = 1;
+    for (int d = 0; d < MAXG; d++) g->user_dims[d] = g->stored_dims[d] = 1;
     if (cudaGetDevice(&g->device) != cudaSuccess) g->device = 0;
     *out = g;
     return GB_OK;
@@ -221,7 +224,7 @@ int gb_grid_create(gb_grid** out, int dtype, int ndim, const int64_t* dims, cons
     const bool pad = needs_shift(bc, order);              // src/interp.jl:58-72
     const int pf_bc = bc == GB_BC_FILL ? GB_BC_NEAREST : bc;  // :68
     const double padval = bc == GB_BC_FILL ? fill : 0.0;      // :60,:67
-    i64 ut = 1, st = 1, sd[MAXD];
+    i64 ut = 1, st = 1, sd[MAXG];
     for (int d = 0; d < ndim; d++) {
         sd[d] = dims[d] + (pad ? 2 : 0);
         ut *= dims[d];
@@ -337,7 +340,7 @@ struct EvalCall {
     int outmode, flags, xdtype;
     const double* affine;
     i64 nq;
-    const void* xp[MAXD];  // device pointers
+    const void* xp[MAXG];  // device pointers
     i64 xqs;
     void *val, *grad, *hess;  // device
     u64* first_invalid;       // device or NULL
@@ -365,23 +368,57 @@ template <int N> int launch_n(const EvalCall& c, cudaStream_t s) {
     p.nq = c.nq;
     p.q0 = c.q0;
     p.first_invalid = c.first_invalid;
+    p.tiled = 0;
+    p.perm = nullptr; p.work = nullptr; p.nwork = nullptr;
+    for (int d = 0; d < N; d++) { p.tile[d] = 1; p.ntile[d] = 1; }
     const int bcf = bc_family(g->bc);
-    if (g->dtype == GB_F64) {
-        if constexpr (N == 1) return launch_eval_double_1(p, g->order, bcf, c.outmode, c.flags, s);
-        if constexpr (N == 2) return launch_eval_double_2(p, g->order, bcf, c.outmode, c.flags, s);
-        if constexpr (N == 3) return launch_eval_double_3(p, g->order, bcf, c.outmode, c.flags, s);
-        if constexpr (N == 4) return launch_eval_double_4(p, g->order, bcf, c.outmode, c.flags, s);
-    } else {
-        if constexpr (N == 1) return launch_eval_float_1(p, g->order, bcf, c.outmode, c.flags, s);
-        if constexpr (N == 2) return launch_eval_float_2(p, g->order, bcf, c.outmode, c.flags, s);
-        if constexpr (N == 3) return launch_eval_float_3(p, g->order, bcf, c.outmode, c.flags, s);
-        if constexpr (N == 4) return launch_eval_float_4(p, g->order, bcf, c.outmode, c.flags, s);
+#define GB_CALL(T, O) return launch_eval_##T##_##O(p, bcf, c.outmode, c.flags, s)
+#define GB_ORDERS(TN)                                    \
+    switch (g->order) {                                  \
+    case GB_NEAREST: GB_CALL(TN, 0);                     \
+    case GB_LINEAR: GB_CALL(TN, 1);                      \
+    case GB_QUADRATIC: GB_CALL(TN, 2);                   \
+    case GB_CUBIC: GB_CALL(TN, 3);                       \
     }
+    if (g->dtype == GB_F64) {
+        if constexpr (N == 1) { GB_ORDERS(double_1) }
+        if constexpr (N == 2) { GB_ORDERS(double_2) }
+        if constexpr (N == 3) { GB_ORDERS(double_3) }
+        if constexpr (N == 4) { if (g->order == GB_NEAREST) GB_CALL(double_4, 0); GB_CALL(double_4, 1); }
+    } else {
+        if constexpr (N == 1) { GB_ORDERS(float_1) }
+        if constexpr (N == 2) { GB_ORDERS(float_2) }
+        if constexpr (N == 3) { GB_ORDERS(float_3) }
+        if constexpr (N == 4) { if (g->order == GB_NEAREST) GB_CALL(float_4, 0); GB_CALL(float_4, 1); }
+    }
+#undef GB_ORDERS
+#undef GB_CALL
     return GB_ERR_ARG;
+}
+
+int launch_generic(const EvalCall& c, cudaStream_t s) {
+    const gb_grid* g = c.g;
+    GenericParams p;
+    p.coefs = g->coefs;
+    p.total = g->total;
+    p.N = g->ndim; p.order = g->order; p.bcf = bc_family(g->bc);
+    i64 str = 1;
+    for (int d = 0; d < g->ndim; d++) {
+        p.len[d] = (int)g->stored_dims[d];
+        p.stride[d] = str;
+        str *= g->stored_dims[d];
+        p.xp[d] = c.xp[d];
+        for (int k = 0; k < 4; k++) p.aff[d][k] = c.affine ? c.affine[4 * d + k] : 0.0;
+    }
+    p.xqs = c.xqs; p.xdtype = c.xdtype; p.has_aff = c.affine ? 1 : 0; p.shift = g->shift;
+    p.val = c.val; p.grad = c.grad; p.hess = c.hess;
+    p.nq = c.nq; p.q0 = c.q0; p.first_invalid = c.first_invalid; p.outmode = c.outmode;
+    return launch_eval_generic(p, g->dtype, s);
 }
 
 int launch_eval(const EvalCall& c, cudaStream_t s) {
     if (c.nq <= 0) return GB_OK;
+    if (c.g->ndim > MAXD || (c.g->ndim == 4 && c.g->order >= GB_QUADRATIC)) return launch_generic(c, s);
     switch (c.g->ndim) {
     case 1: return launch_n<1>(c, s);
     case 2: return launch_n<2>(c, s);
@@ -572,7 +609,7 @@ int gb_eval(const gb_grid* g, int out_mask, int64_t nq, const void* x, int xdtyp
     DeviceGuard guard(g->device);
     pool_keep_memory();
     const int N = g->ndim;
-    const void* cols[MAXD];
+    const void* cols[MAXG];
     for (int d = 0; d < N; d++) cols[d] = (const char*)x + (size_t)d * x_dstride * esize(xdtype);
     if (mem == GB_DEVICE)
         return eval_device(g, outmode, nq, cols, x_qstride, xdtype, affine, (out_mask & GB_OUT_VAL) ? val : nullptr,
@@ -625,8 +662,8 @@ int gb_eval_outer(const gb_grid* g, const int64_t* lens, const void* const* vecs
     cudaStream_t s = (cudaStream_t)stream;
     const size_t xs = esize(xdtype), es = esize(g->dtype);
     // device copies of the vectors (host mode), the pointer table, lens, the expanded columns
-    void* dvec[MAXD] = {nullptr, nullptr, nullptr, nullptr};
-    const void* vptr[MAXD];
+    void* dvec[MAXG] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    const void* vptr[MAXG];
     void *d_tab = nullptr, *d_lens = nullptr, *d_cols = nullptr, *d_out = nullptr;
     auto cleanup = [&](int code) {
         for (int d = 0; d < N; d++)
@@ -651,9 +688,9 @@ int gb_eval_outer(const gb_grid* g, const int64_t* lens, const void* const* vecs
         } else
             vptr[d] = vecs[d];
     }
-    GB_TRY(cudaMallocAsync(&d_tab, sizeof(void*) * MAXD, s));
+    GB_TRY(cudaMallocAsync(&d_tab, sizeof(void*) * MAXG, s));
     GB_TRY(cudaMemcpyAsync(d_tab, vptr, sizeof(void*) * N, cudaMemcpyHostToDevice, s));
-    GB_TRY(cudaMallocAsync(&d_lens, sizeof(i64) * MAXD, s));
+    GB_TRY(cudaMallocAsync(&d_lens, sizeof(i64) * MAXG, s));
     GB_TRY(cudaMemcpyAsync(d_lens, lens, sizeof(i64) * N, cudaMemcpyHostToDevice, s));
     GB_TRY(cudaMallocAsync(&d_cols, (size_t)nq * N * xs, s));
     const int grid = (int)std::max<i64>(1, std::min<i64>((nq + 255) / 256, (i64)num_sms() * 16));
@@ -666,7 +703,7 @@ int gb_eval_outer(const gb_grid* g, const int64_t* lens, const void* const* vecs
         GB_TRY(cudaMallocAsync(&d_out, (size_t)nq * es, s));
         dst = d_out;
     }
-    const void* cols[MAXD];
+    const void* cols[MAXG];
     for (int d = 0; d < N; d++) cols[d] = (const char*)d_cols + (size_t)d * nq * xs;
     int64_t bad = -1;
     rc = eval_device(g, 0, nq, cols, 1, xdtype, affine, dst, nullptr, nullptr, flags, g->bc == GB_BC_NIL ? &bad : nullptr, s);

@@ -16,8 +16,10 @@ namespace gb {
 
 typedef long long i64;
 typedef unsigned long long u64;
+typedef unsigned int u32;
 
 constexpr int MAXD = 4;  // dimension-specialised kernels (the reference unrolls 1..4, src/interp.jl:1047-1125)
+constexpr int MAXG = 8;  // the rolled generic kernel (src/interp.jl:1189-1283) covers N up to 8
 
 // BC families with identical index rules (src/interp.jl:594-783): nil/nan/na share one
 // (they differ only in how an invalid location is reported), nearest/fill share one.
@@ -65,14 +67,41 @@ template <int N> struct EvalParams {
     i64 nq;
     i64 q0;               // index of this launch's first query in the caller's batch
     u64* first_invalid;   // device, atomicMin target (BCnil) or NULL
+    // tiled (spatially binned) evaluation, filled in by launch_one; tiled == 0 -> plain
+    int tiled;
+    int tile[N];          // cells per tile
+    int ntile[N];         // tiles per dimension
+    const u32* perm;      // query indices sorted by tile
+    const u32* work;      // 3 words per work item: tile, begin, end (into perm)
+    const u32* nwork;     // device scalar: number of work items
 };
 
-// One entry per (dtype, N); each dispatches on (order, bc family, output mode, flags).
+// One entry per (dtype, N, order) -- eval_inst.cu; each dispatches on (bc family, output mode, flags).
 // outmode: 0 value, 1 value+gradient, 2 value+gradient+hessian.
-#define GB_DECL_EVAL(T, N) int launch_eval_##T##_##N(const EvalParams<N>& p, int order, int bcf, int outmode, int flags, cudaStream_t s);
-GB_DECL_EVAL(float, 1) GB_DECL_EVAL(float, 2) GB_DECL_EVAL(float, 3) GB_DECL_EVAL(float, 4)
-GB_DECL_EVAL(double, 1) GB_DECL_EVAL(double, 2) GB_DECL_EVAL(double, 3) GB_DECL_EVAL(double, 4)
+#define GB_DECL_EVAL(T, N, O) int launch_eval_##T##_##N##_##O(const EvalParams<N>& p, int bcf, int outmode, int flags, cudaStream_t s);
+#define GB_DECL_EVAL_N(T, N) GB_DECL_EVAL(T, N, 0) GB_DECL_EVAL(T, N, 1) GB_DECL_EVAL(T, N, 2) GB_DECL_EVAL(T, N, 3)
+GB_DECL_EVAL_N(float, 1) GB_DECL_EVAL_N(float, 2) GB_DECL_EVAL_N(float, 3) GB_DECL_EVAL(float, 4, 0) GB_DECL_EVAL(float, 4, 1)
+GB_DECL_EVAL_N(double, 1) GB_DECL_EVAL_N(double, 2) GB_DECL_EVAL_N(double, 3) GB_DECL_EVAL(double, 4, 0) GB_DECL_EVAL(double, 4, 1)
+#undef GB_DECL_EVAL_N
 #undef GB_DECL_EVAL
+
+// ---- rolled generic N-d kernel (eval_generic.cu): N >= 5 and 4-D Quadratic/Cubic ---------------------
+struct GenericParams {
+    const void* coefs;
+    i64 total;
+    int N, order, bcf;
+    int len[MAXG];
+    i64 stride[MAXG];
+    const void* xp[MAXG];
+    i64 xqs;
+    int xdtype, has_aff, shift;
+    double aff[MAXG][4];
+    void *val, *grad, *hess;
+    i64 nq, q0;
+    u64* first_invalid;
+    int outmode;
+};
+int launch_eval_generic(const GenericParams& p, int dtype, cudaStream_t s);
 
 // ---- prefilter (prefilter.cu) -------------------------------------------------------------------
 int invert_device(int dtype, int ndim, const i64* dims, void* data, int bc, int order, const int* dimlist, int ndl,

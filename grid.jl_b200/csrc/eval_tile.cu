@@ -1,0 +1,165 @@
+// eval_tile.cu -- order-independent pieces of the binned ("tiled") evaluation path: the histogram
+// scan that turns per-tile counts into bin offsets and a work-item list, the scatter that writes
+// the tile-sorted query order, and the tile-shape heuristic.  See eval.cuh for the kernels that
+// compute the keys and evaluate the bricks.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace gb {
+
+// One CTA of 1024 threads.  Each thread owns a contiguous slice of bins; block-wide exclusive scans
+// of (queries per slice) and (work items per slice) give every thread its starting offsets.
+__global__ void __launch_bounds__(1024) tile_scan_kernel(const u32* __restrict__ hist, u32 nbins, u32* __restrict__ offs, u32* __restrict__ work,
+                                                         u32* __restrict__ nwork, u32 chunk) {
+    __shared__ u32 s_cnt[1024], s_itm[1024];
+    const u32 t = threadIdx.x;
+    const u32 per = (nbins + 1023) / 1024;
+    const u32 b0 = min(t * per, nbins), b1 = min(b0 + per, nbins);
+    u32 cnt = 0, itm = 0;
+    for (u32 b = b0; b < b1; b++) {
+        const u32 h = hist[b];
+        cnt += h;
+        itm += (h + chunk - 1) / chunk;
+    }
+    s_cnt[t] = cnt;
+    s_itm[t] = itm;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over 1024 entries
+    for (u32 d = 1; d < 1024; d <<= 1) {
+        u32 a = 0, b = 0;
+        if (t >= d) { a = s_cnt[t - d]; b = s_itm[t - d]; }
+        __syncthreads();
+        s_cnt[t] += a;
+        s_itm[t] += b;
+        __syncthreads();
+    }
+    u32 o = s_cnt[t] - cnt, w = s_itm[t] - itm;  // exclusive
+    for (u32 b = b0; b < b1; b++) {
+        const u32 h = hist[b];
+        offs[b] = o;
+        const u32 n = (h + chunk - 1) / chunk;           // items of this bin ...
+        const u32 sz = n ? (h + n - 1) / n : 0;          // ... of equal size
+        for (u32 k = 0; k < n; k++) {
+            work[3 * w] = b;
+            work[3 * w + 1] = o + k * sz;
+            work[3 * w + 2] = o + min((k + 1) * sz, h);
+            w++;
+        }
+        o += h;
+    }
+    if (t == 1023) { nwork[0] = s_itm[1023]; nwork[1] = 0; }  // item count, and the counter CTAs pull items from
+}
+
+// Each CTA replays its slice of the batch: slot = its private cursor for the query's bin.
+__global__ void __launch_bounds__(256) tile_scatter_kernel(const u32* __restrict__ keys, i64 nq, const u32* __restrict__ boff, u32* __restrict__ perm,
+                                                           u32 nbins, i64 per_cta) {
+    extern __shared__ u32 s_cur[];
+    for (u32 b = threadIdx.x; b < nbins; b += blockDim.x) s_cur[b] = boff[(size_t)b * gridDim.x + blockIdx.x];
+    __syncthreads();
+    const i64 q0 = (i64)blockIdx.x * per_cta;
+    const i64 q1 = q0 + per_cta < nq ? q0 + per_cta : nq;
+#pragma unroll 4
+    for (i64 q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
+        const u32 slot = atomicAdd(s_cur + keys[q], 1u);
+        perm[slot] = (u32)q;
+    }
+}
+
+// hist[b] = sum over CTAs of bh[b][cta]; one warp per bin.
+__global__ void __launch_bounds__(256) bin_totals_kernel(const u32* __restrict__ bh, u32 nbins, u32 nctas, u32* __restrict__ hist) {
+    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= nbins) return;
+    u32 sum = 0;
+    for (u32 c = lane; c < nctas; c += 32) sum += bh[(size_t)warp * nctas + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) hist[warp] = sum;
+}
+
+// boff[b][cta] = offs[b] + (queries of bin b owned by CTAs < cta); one warp per bin.
+__global__ void __launch_bounds__(256) bin_cursors_kernel(const u32* __restrict__ bh, u32 nbins, u32 nctas, const u32* __restrict__ offs, u32* __restrict__ boff) {
+    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= nbins) return;
+    u32 carry = offs[warp];
+    for (u32 c0 = 0; c0 < nctas; c0 += 32) {
+        const u32 c = c0 + lane;
+        const u32 v = c < nctas ? bh[(size_t)warp * nctas + c] : 0;
+        u32 incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += t;
+        }
+        if (c < nctas) boff[(size_t)warp * nctas + c] = carry + incl - v;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
+int tile_offsets(const u32* bh, u32 nbins, u32 nctas, u32* hist, u32* offs, u32* boff, u32* work, u32* nwork, u32 chunk, cudaStream_t s) {
+    const u32 wgrid = (nbins * 32 + 255) / 256;
+    bin_totals_kernel<<<wgrid, 256, 0, s>>>(bh, nbins, nctas, hist);
+    tile_scan_kernel<<<1, 1024, 0, s>>>(hist, nbins, offs, work, nwork, chunk);
+    bin_cursors_kernel<<<wgrid, 256, 0, s>>>(bh, nbins, nctas, offs, boff);
+    count_launch(3);
+    GB_CUDA(cudaGetLastError());
+    return GB_OK;
+}
+
+// Tile shape: the brick (tile + L-1 halo per dimension) must fit the shared-memory budget
+// (GB_TILE_KB, default 56 KB -> two 256-thread CTAs per SM); dimension 1 is kept longest so brick
+// rows are loaded in long coalesced runs; the number of tiles must fit the per-CTA shared-memory
+// histogram of the counting sort.  Returns false when tiling cannot pay off (too many tiles for the
+// sort, or fewer than ~128 queries per tile to amortise staging a brick) -> plain path.
+// GB_TILE="a,b,c" overrides the shape.
+bool choose_tile(int N, int L, size_t esz, const int* len, i64 nq, int* tile, int* ntile) {
+    constexpr u32 MAX_BINS = 12000 - 1;
+    size_t budget = 56 * 1024;
+    if (const char* e = getenv("GB_TILE_KB")) {
+        long v = atol(e);
+        if (v >= 4 && v <= 200) budget = (size_t)v * 1024;
+    }
+    for (int d = 0; d < N; d++) tile[d] = d == 0 ? 32 : 16;
+    bool forced = false;
+    if (const char* e = getenv("GB_TILE")) {
+        int v[4] = {0, 0, 0, 0};
+        int n = sscanf(e, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]);
+        for (int d = 0; d < N && d < n; d++)
+            if (v[d] >= 1 && v[d] <= 4096) { tile[d] = v[d]; forced = true; }
+    }
+    for (int d = 0; d < N; d++) tile[d] = std::max(1, std::min(tile[d], len[d]));
+    auto bytes = [&]() {
+        size_t v = esz;
+        for (int d = 0; d < N; d++) v *= (size_t)(tile[d] + L - 1);
+        return v;
+    };
+    auto tiles = [&]() {
+        unsigned long long v = 1;
+        for (int d = 0; d < N; d++) { ntile[d] = (len[d] + tile[d] - 1) / tile[d]; v *= (unsigned long long)ntile[d]; }
+        return v;
+    };
+    while (bytes() > budget) {
+        int best = -1;
+        for (int d = 0; d < N; d++)  // halve the largest extent; ties go to the slowest dimension
+            if (tile[d] > 1 && (best < 0 || tile[d] >= tile[best])) best = d;
+        if (best < 0) break;
+        tile[best] = (tile[best] + 1) / 2;
+    }
+    if (bytes() > 200 * 1024) return false;
+    while (!forced && tiles() > MAX_BINS) {  // grow the dimension with the most tiles while the brick still fits
+        int best = -1;
+        for (int d = 0; d < N; d++)
+            if (tile[d] < len[d] && (best < 0 || ntile[d] > ntile[best])) best = d;
+        if (best < 0) return false;
+        const int old = tile[best];
+        tile[best] = std::min(len[best], old * 2);
+        if (bytes() > budget) { tile[best] = old; return false; }
+    }
+    const unsigned long long nt = tiles();
+    if (nt > MAX_BINS) return false;
+    return nq / (i64)nt >= 128;
+}
+
+}  // namespace gb

@@ -292,8 +292,12 @@ template <typename T> int pad1_impl(int ndim, const i64* dims, const T* in, T f,
     case 2: return pad1_n<T, 2>(dims, in, f, out, s);
     case 3: return pad1_n<T, 3>(dims, in, f, out, s);
     case 4: return pad1_n<T, 4>(dims, in, f, out, s);
+    case 5: return pad1_n<T, 5>(dims, in, f, out, s);
+    case 6: return pad1_n<T, 6>(dims, in, f, out, s);
+    case 7: return pad1_n<T, 7>(dims, in, f, out, s);
+    case 8: return pad1_n<T, 8>(dims, in, f, out, s);
     }
-    return fail(GB_ERR_UNSUPPORTED, "pad1: ndim must be 1..4");
+    return fail(GB_ERR_UNSUPPORTED, "pad1: ndim must be 1..8");
 }
 
 }  // namespace

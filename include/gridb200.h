@@ -47,7 +47,7 @@ enum {
     GB_ERR_ARG = 1,              /* ErrorException: arity / shape (src/interp.jl:88-90,159-161,206-211) */
     GB_ERR_INVALID_LOCATION = 2, /* ErrorException("Invalid location"), BCnil only (src/interp.jl:402-404) */
     GB_ERR_UNSUPPORTED = 3,      /* MethodError in the reference: Cubic with reflect/periodic/nearest/fill,
-                                    valgradhess on Nearest/Linear, ndim > 4 */
+                                    valgradhess on Nearest/Linear, ndim > 8 */
     GB_ERR_CUDA = 4,
     GB_ERR_DIM = 5,              /* DimensionMismatch (src/coord.jl:7) */
     GB_ERR_PROLONG_SIZE = 6      /* "Cannot prolong a dimension of length n to len" (src/restrict_prolong.jl:328-330) */
@@ -56,8 +56,13 @@ enum {
 enum {
     GB_EXACT = 0, /* default: the reference's operation order (weight products, sequential sum,
                      no FMA contraction) -> bit-identical to the CPU oracle */
-    GB_FAST = 1   /* separable dimension-by-dimension contraction with FMA; same taps and weights,
+    GB_FAST = 1,  /* separable dimension-by-dimension contraction with FMA; same taps and weights,
                      different rounding (validated to a few ulp of sum|w_i a_i|) */
+    /* Scheduling only -- results are bit-identical either way.  By default the library bins large
+       batches on big grids by grid tile and evaluates them out of shared-memory bricks ("tiled");
+       small batches / small grids gather straight from global memory ("plain"). */
+    GB_TILED = 2, /* force the binned shared-memory path */
+    GB_PLAIN = 4  /* force the plain path */
 };
 
 int gb_version(void);

@@ -379,3 +379,56 @@ def test_full_size_properties_c2(gb):
     g2 = gb.InterpGrid(2.0 * A, gb.BCnan, gb.InterpCubic)
     v2 = gb.getindex_batch(g2, X[:1_000_000])
     assert torch.equal(v2, 2.0 * val[:1_000_000])
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("bc,order,shape", [("nan", "cubic", (40, 37, 35)), ("reflect", "quadratic", (300, 200)), ("periodic", "quadratic", (70, 80)),
+                                            ("periodic", "linear", (9, 20, 17, 12)), ("fill", "linear", (30, 30, 30)), ("nearest", "quadratic", (50, 3, 40)),
+                                            ("reflect", "linear", (33, 65)), ("nil", "cubic", (36, 5, 5, 6)), ("reflect", "nearest", (64, 64)),
+                                            ("nan", "quadratic", (100,))])
+def test_tiled_path_is_bit_identical(gb, oracle, dtype, bc, order, shape):
+    """The binned shared-memory path (GB_TILED) only reschedules work: bit-identical to the plain
+    path and to the oracle, including wrapped taps at the boundaries, invalid queries and NaN."""
+    import torch
+
+    rng = np.random.default_rng(17)
+    A = rng.standard_normal(shape).astype(dtype)
+    g, co = build(gb, oracle, A, bc, order)
+    X = make_queries(rng, shape, 60_000, dtype, wide=(bc != "nil"))
+    mask = V | G | (H if order in ("quadratic", "cubic") else 0)
+    ov, og, oh, obad = oracle.evaluate(co, bc, order, X, mask, raise_invalid=False)
+    if bc == "nil":
+        X = np.ascontiguousarray(X[~np.isnan(ov)])
+        ov, og, oh, obad = oracle.evaluate(co, bc, order, X, mask)
+    Xd = torch.from_numpy(X).cuda()
+    for fast in (False, True):
+        outs = {}
+        for tiled in (False, True):
+            v, gr, h = g._eval(Xd, mask, fast=fast, tiled=tiled)
+            outs[tiled] = [None if a is None else a.cpu().numpy() for a in (v, gr, h)]
+        for a, b in zip(outs[False], outs[True]):
+            assert (a is None and b is None) or same(a, b)
+        if not fast:
+            assert same(outs[True][0], ov) and same(outs[True][1], og) and (oh is None or same(outs[True][2], oh))
+
+
+@pytest.mark.parametrize("bc,order", [("nil", "linear"), ("reflect", "quadratic"), ("nan", "cubic"), ("periodic", "nearest"), ("fill", "linear")])
+def test_generic_nd_kernel(gb, oracle, bc, order):
+    """N >= 5 (and 4-D Quadratic/Cubic) run on the rolled generic kernel (src/interp.jl:1189-1283);
+    test/grid.jl:260-264 is the reference's own 5-D smoke test."""
+    rng = np.random.default_rng(23)
+    B = rng.random((4, 4, 4, 4, 4))
+    Bi = gb.InterpGrid(B, gb.BCnil, gb.InterpLinear)
+    assert Bi[2, 2, 2, 2, 2] == B[1, 1, 1, 1, 1]
+    for shape in [(5, 4, 6, 5, 4), (4, 5, 4, 4, 5, 4)]:
+        A = rng.standard_normal(shape)
+        g, co = build(gb, oracle, A, bc, order)
+        assert same(g.coefs, co)
+        X = make_queries(rng, shape, 300, np.float64, wide=(bc != "nil"))
+        mask = V | G | (H if order in ("quadratic", "cubic") else 0)
+        ov, og, oh, obad = oracle.evaluate(co, bc, order, X, mask, raise_invalid=False)
+        if bc == "nil":
+            X = np.ascontiguousarray(X[~np.isnan(ov)])
+            ov, og, oh, obad = oracle.evaluate(co, bc, order, X, mask)
+        v, gr, h = g._eval(X, mask)
+        assert same(v, ov) and same(gr, og) and (oh is None or same(h, oh))
