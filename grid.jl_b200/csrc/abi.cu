@@ -771,6 +771,40 @@ int gb_prolong(int dtype, int ndim, const int64_t* dims, const void* in, int dim
     }, &ctx);
 }
 
+int gb_restrict_slab(int dtype, int ndim, const int64_t* dims, const void* in, int dim, double scale, int64_t global_len, int64_t in_first,
+                     int64_t out_first, int64_t out_count, void* out, int mem, void* stream) {
+    if (!ok_dtype(dtype) || ndim < 1 || !dims || !in || !out) return fail(GB_ERR_ARG, "bad arguments");
+    if (dim < 0 || dim >= ndim) return fail(GB_ERR_ARG, "restrict: dim out of range");
+    cudaStream_t s = (cudaStream_t)stream;
+    pool_keep_memory();
+    if (mem == GB_DEVICE) return restrict_slab_device(dtype, ndim, (const i64*)dims, in, dim, scale, global_len, in_first, out_first, out_count, out, s);
+    i64 it = 1, ot = 1;
+    for (int d = 0; d < ndim; d++) { it *= dims[d]; ot *= (d == dim) ? out_count : dims[d]; }
+    struct Ctx { int dtype, ndim, dim; const i64* dims; double scale; i64 L, f, o, c; } ctx{dtype, ndim, dim, (const i64*)dims, scale, global_len, in_first, out_first, out_count};
+    return mg_host(dtype, it, ot, in, out, s, [](void* c, const void* i, void* o, cudaStream_t st) {
+        Ctx* x = (Ctx*)c;
+        return restrict_slab_device(x->dtype, x->ndim, x->dims, i, x->dim, x->scale, x->L, x->f, x->o, x->c, o, st);
+    }, &ctx);
+}
+
+int gb_prolong_slab(int dtype, int ndim, const int64_t* dims, const void* in, int dim, int64_t global_n, int64_t global_len, int64_t in_first,
+                    int64_t out_first, int64_t out_count, void* out, int mem, void* stream) {
+    if (!ok_dtype(dtype) || ndim < 1 || !dims || !in || !out) return fail(GB_ERR_ARG, "bad arguments");
+    if (dim < 0 || dim >= ndim) return fail(GB_ERR_ARG, "prolong: dim out of range");
+    int rc = gb_prolong_size(global_n, global_len, nullptr);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    pool_keep_memory();
+    if (mem == GB_DEVICE) return prolong_slab_device(dtype, ndim, (const i64*)dims, in, dim, global_n, global_len, in_first, out_first, out_count, out, s);
+    i64 it = 1, ot = 1;
+    for (int d = 0; d < ndim; d++) { it *= dims[d]; ot *= (d == dim) ? out_count : dims[d]; }
+    struct Ctx { int dtype, ndim, dim; const i64* dims; i64 n, len, f, o, c; } ctx{dtype, ndim, dim, (const i64*)dims, global_n, global_len, in_first, out_first, out_count};
+    return mg_host(dtype, it, ot, in, out, s, [](void* c, const void* i, void* o, cudaStream_t st) {
+        Ctx* x = (Ctx*)c;
+        return prolong_slab_device(x->dtype, x->ndim, x->dims, i, x->dim, x->n, x->len, x->f, x->o, x->c, o, st);
+    }, &ctx);
+}
+
 int gb_restrict3(int dtype, const int64_t* dims, const void* in, double scale, void* out, int mem, void* stream) {
     if (!ok_dtype(dtype) || !dims || !in || !out) return fail(GB_ERR_ARG, "bad arguments");
     for (int d = 0; d < 3; d++)

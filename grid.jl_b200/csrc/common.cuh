@@ -111,6 +111,10 @@ int pad1_device(int dtype, int ndim, const i64* dims, const void* in, double fil
 // ---- restrict / prolong (multigrid.cu) ------------------------------------------------------------
 int restrict_device(int dtype, int ndim, const i64* dims, const void* in, int dim, double scale, void* out, cudaStream_t s);
 int prolong_device(int dtype, int ndim, const i64* dims, const void* in, int dim, i64 len, void* out, cudaStream_t s);
+int restrict_slab_device(int dtype, int ndim, const i64* dims, const void* in, int dim, double scale, i64 L, i64 in_first, i64 out_first, i64 ocount, void* out,
+                         cudaStream_t s);
+int prolong_slab_device(int dtype, int ndim, const i64* dims, const void* in, int dim, i64 n, i64 len, i64 in_first, i64 out_first, i64 ocount, void* out,
+                        cudaStream_t s);
 int restrict3_device(int dtype, const i64* dims, const void* in, double scale, void* out, cudaStream_t s);
 int prolong3_device(int dtype, const i64* dims, const void* in, const i64* odims, void* out, cudaStream_t s);
 

@@ -67,24 +67,31 @@ template <typename T, typename Load> __device__ __forceinline__ T prolong_elem(L
     return acc;
 }
 
-// ---- per-dimension kernels: array viewed as (inner, L, outer) ---------------------------------
-template <typename T> __global__ void __launch_bounds__(256) restrict_dim_kernel(const T* __restrict__ A, T* __restrict__ R, i64 inner, i64 L, i64 n, i64 outer, RCoef<T> c) {
-    const i64 total = inner * n * outer;
+// ---- per-dimension kernels: array viewed as (inner, extent, outer) -------------------------------
+// Slab form: the input holds planes [in_first, in_first + Lloc) of a global extent L along the
+// dimension, the output receives global planes [out_first, out_first + ocount).  The whole-array
+// operators are the special case in_first = out_first = 0.  This is what a slab-sharded multigrid
+// level runs after its halo exchange: same per-element arithmetic, so the assembled
+// result is bit-identical to the single-device one.
+template <typename T> __global__ void __launch_bounds__(256) restrict_dim_kernel(const T* __restrict__ A, T* __restrict__ R, i64 inner, i64 L, i64 n, i64 outer,
+                                                                                 i64 Lloc, i64 in_first, i64 out_first, i64 ocount, RCoef<T> c) {
+    const i64 total = inner * ocount * outer;
     const i64 step = (i64)gridDim.x * blockDim.x;
     for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
         const i64 lo = e % inner, r = e / inner;
-        const i64 j = r % n, o = r / n;
-        const T* a = A + lo + o * inner * L;
+        const i64 j = out_first + r % ocount, o = r / ocount;
+        const T* a = A + lo + o * inner * Lloc - in_first * inner;
         R[e] = restrict_elem<T>([&](i64 k) { return __ldg(a + k * inner); }, j, L, n, c);
     }
 }
-template <typename T> __global__ void __launch_bounds__(256) prolong_dim_kernel(const T* __restrict__ A, T* __restrict__ P, i64 inner, i64 n, i64 len, i64 outer) {
-    const i64 total = inner * len * outer;
+template <typename T> __global__ void __launch_bounds__(256) prolong_dim_kernel(const T* __restrict__ A, T* __restrict__ P, i64 inner, i64 n, i64 len, i64 outer,
+                                                                                i64 nloc, i64 in_first, i64 out_first, i64 ocount) {
+    const i64 total = inner * ocount * outer;
     const i64 step = (i64)gridDim.x * blockDim.x;
     for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
         const i64 lo = e % inner, r = e / inner;
-        const i64 k = r % len, o = r / len;
-        const T* a = A + lo + o * inner * n;
+        const i64 k = out_first + r % ocount, o = r / ocount;
+        const T* a = A + lo + o * inner * nloc - in_first * inner;
         P[e] = prolong_elem<T>([&](i64 i) { return __ldg(a + i * inner); }, k, len);
     }
 }
@@ -100,31 +107,62 @@ inline int grid_for(i64 total, int block) {
     return (int)std::max<i64>(1, std::min(need, cap));
 }
 
-template <typename T> int restrict_impl(int ndim, const i64* dims, const T* in, int dim, double scale, T* out, cudaStream_t s) {
+// input planes an output range needs: restrict output j reads 2j-2..2j+1 (even L) / 2j-1..2j+1 (odd L)
+inline void restrict_needs(i64 L, i64 n, i64 k0, i64 k1, i64* lo, i64* hi) {
+    *lo = k0 == 0 ? 0 : ((L & 1) ? 2 * k0 - 1 : 2 * k0 - 2);
+    *hi = (k1 - 1 <= n - 2) ? 2 * (k1 - 1) + 1 : L - 1;
+    if (*hi > L - 1) *hi = L - 1;
+}
+inline void prolong_needs(i64 n, i64 len, i64 k0, i64 k1, i64* lo, i64* hi) {
+    *lo = k0 >> 1;
+    const i64 kl = k1 - 1;
+    const bool copy_only = (len & 1) && !(kl & 1);  // P[2i] = A[i]
+    *hi = std::min(n - 1, (kl >> 1) + (copy_only ? 0 : 1));
+}
+
+template <typename T> int restrict_slab_impl(int ndim, const i64* dims, const T* in, int dim, double scale, i64 L, i64 in_first, i64 out_first, i64 ocount,
+                                             T* out, cudaStream_t s) {
     if (dim < 0 || dim >= ndim) return fail(GB_ERR_ARG, "restrict: dim out of range");
     i64 inner = 1, outer = 1;
     for (int d = 0; d < dim; d++) inner *= dims[d];
     for (int d = dim + 1; d < ndim; d++) outer *= dims[d];
-    const i64 L = dims[dim], n = rsize(L);
-    if (inner * n * outer == 0) return GB_OK;
-    restrict_dim_kernel<T><<<grid_for(inner * n * outer, 256), 256, 0, s>>>(in, out, inner, L, n, outer, make_coef<T>(scale));
+    const i64 Lloc = dims[dim], n = rsize(L);
+    if (ocount < 0 || out_first < 0 || out_first + ocount > n) return fail(GB_ERR_ARG, "restrict: output planes out of range");
+    if (inner * ocount * outer == 0) return GB_OK;
+    i64 lo, hi;
+    restrict_needs(L, n, out_first, out_first + ocount, &lo, &hi);
+    if (lo < in_first || hi >= in_first + Lloc) return fail(GB_ERR_ARG, "restrict: the slab does not hold every input plane the requested outputs need");
+    restrict_dim_kernel<T><<<grid_for(inner * ocount * outer, 256), 256, 0, s>>>(in, out, inner, L, n, outer, Lloc, in_first, out_first, ocount, make_coef<T>(scale));
+    count_launch();
+    GB_CUDA(cudaGetLastError());
+    return GB_OK;
+}
+template <typename T> int restrict_impl(int ndim, const i64* dims, const T* in, int dim, double scale, T* out, cudaStream_t s) {
+    if (dim < 0 || dim >= ndim) return fail(GB_ERR_ARG, "restrict: dim out of range");
+    return restrict_slab_impl<T>(ndim, dims, in, dim, scale, dims[dim], 0, 0, rsize(dims[dim]), out, s);
+}
+template <typename T> int prolong_slab_impl(int ndim, const i64* dims, const T* in, int dim, i64 n, i64 len, i64 in_first, i64 out_first, i64 ocount, T* out,
+                                            cudaStream_t s) {
+    if (dim < 0 || dim >= ndim) return fail(GB_ERR_ARG, "prolong: dim out of range");
+    const i64 newsz = (len & 1) ? 2 * n - 1 : 2 * (n - 1);
+    if (newsz != len) return fail(GB_ERR_PROLONG_SIZE, "Cannot prolong a dimension of length " + std::to_string(n) + " to " + std::to_string(len));
+    i64 inner = 1, outer = 1;
+    for (int d = 0; d < dim; d++) inner *= dims[d];
+    for (int d = dim + 1; d < ndim; d++) outer *= dims[d];
+    const i64 nloc = dims[dim];
+    if (ocount < 0 || out_first < 0 || out_first + ocount > len) return fail(GB_ERR_ARG, "prolong: output planes out of range");
+    if (inner * ocount * outer == 0) return GB_OK;
+    i64 lo, hi;
+    prolong_needs(n, len, out_first, out_first + ocount, &lo, &hi);
+    if (lo < in_first || hi >= in_first + nloc) return fail(GB_ERR_ARG, "prolong: the slab does not hold every input plane the requested outputs need");
+    prolong_dim_kernel<T><<<grid_for(inner * ocount * outer, 256), 256, 0, s>>>(in, out, inner, n, len, outer, nloc, in_first, out_first, ocount);
     count_launch();
     GB_CUDA(cudaGetLastError());
     return GB_OK;
 }
 template <typename T> int prolong_impl(int ndim, const i64* dims, const T* in, int dim, i64 len, T* out, cudaStream_t s) {
     if (dim < 0 || dim >= ndim) return fail(GB_ERR_ARG, "prolong: dim out of range");
-    const i64 n = dims[dim];
-    const i64 newsz = (len & 1) ? 2 * n - 1 : 2 * (n - 1);
-    if (newsz != len) return fail(GB_ERR_PROLONG_SIZE, "Cannot prolong a dimension of length " + std::to_string(n) + " to " + std::to_string(len));
-    i64 inner = 1, outer = 1;
-    for (int d = 0; d < dim; d++) inner *= dims[d];
-    for (int d = dim + 1; d < ndim; d++) outer *= dims[d];
-    if (inner * len * outer == 0) return GB_OK;
-    prolong_dim_kernel<T><<<grid_for(inner * len * outer, 256), 256, 0, s>>>(in, out, inner, n, len, outer);
-    count_launch();
-    GB_CUDA(cudaGetLastError());
-    return GB_OK;
+    return prolong_slab_impl<T>(ndim, dims, in, dim, dims[dim], len, 0, 0, len, out, s);
 }
 
 // ---- fused 3-D restrict -----------------------------------------------------------------------
@@ -294,6 +332,18 @@ int restrict_device(int dtype, int ndim, const i64* dims, const void* in, int di
 int prolong_device(int dtype, int ndim, const i64* dims, const void* in, int dim, i64 len, void* out, cudaStream_t s) {
     if (dtype == GB_F64) return prolong_impl<double>(ndim, dims, (const double*)in, dim, len, (double*)out, s);
     if (dtype == GB_F32) return prolong_impl<float>(ndim, dims, (const float*)in, dim, len, (float*)out, s);
+    return fail(GB_ERR_ARG, "bad dtype");
+}
+int restrict_slab_device(int dtype, int ndim, const i64* dims, const void* in, int dim, double scale, i64 L, i64 in_first, i64 out_first, i64 ocount, void* out,
+                         cudaStream_t s) {
+    if (dtype == GB_F64) return restrict_slab_impl<double>(ndim, dims, (const double*)in, dim, scale, L, in_first, out_first, ocount, (double*)out, s);
+    if (dtype == GB_F32) return restrict_slab_impl<float>(ndim, dims, (const float*)in, dim, scale, L, in_first, out_first, ocount, (float*)out, s);
+    return fail(GB_ERR_ARG, "bad dtype");
+}
+int prolong_slab_device(int dtype, int ndim, const i64* dims, const void* in, int dim, i64 n, i64 len, i64 in_first, i64 out_first, i64 ocount, void* out,
+                        cudaStream_t s) {
+    if (dtype == GB_F64) return prolong_slab_impl<double>(ndim, dims, (const double*)in, dim, n, len, in_first, out_first, ocount, (double*)out, s);
+    if (dtype == GB_F32) return prolong_slab_impl<float>(ndim, dims, (const float*)in, dim, n, len, in_first, out_first, ocount, (float*)out, s);
     return fail(GB_ERR_ARG, "bad dtype");
 }
 int restrict3_device(int dtype, const i64* dims, const void* in, double scale, void* out, cudaStream_t s) {

@@ -131,6 +131,17 @@ int gb_restrict(int dtype, int ndim, const int64_t* dims, const void* in, int di
 /* prolong(A, dim, len) (:10-48); out has dims with dims[dim] -> len */
 int gb_prolong(int dtype, int ndim, const int64_t* dims, const void* in, int dim, int64_t len, void* out,
                int mem, void* stream);
+/* Slab forms for a grid sharded along `dim`: `in` holds planes
+ * [in_first, in_first + dims[dim]) of an array whose full extent along dim is global_len (restrict)
+ * / global_n (prolong); the call writes output planes [out_first, out_first + out_count) of the
+ * full result (out has extent out_count along dim).  Every input plane those outputs read must be
+ * in the slab (own planes + the halo received from the neighbours), else GB_ERR_ARG.  Per-element
+ * arithmetic is that of gb_restrict / gb_prolong, so the assembled slabs equal the unsharded result
+ * bit for bit. */
+int gb_restrict_slab(int dtype, int ndim, const int64_t* dims, const void* in, int dim, double scale, int64_t global_len,
+                     int64_t in_first, int64_t out_first, int64_t out_count, void* out, int mem, void* stream);
+int gb_prolong_slab(int dtype, int ndim, const int64_t* dims, const void* in, int dim, int64_t global_n, int64_t global_len,
+                    int64_t in_first, int64_t out_first, int64_t out_count, void* out, int mem, void* stream);
 /* restrict(A, [true,true,true], scale) on a 3-D array as ONE pass over the fine grid; the
  * per-dim intermediates are rounded exactly as the staged reference does, so the result is
  * bit-identical to gb_restrict applied to dims 0,1,2 in turn (src/utilities.jl:7-20). */

@@ -106,7 +106,7 @@ def test_argument_validation_without_gpu(gb):
     buf = np.zeros(16)
     rc = lib.gb_grid_create(C.byref(h), 1, 2, dims, buf.ctypes.data, 0, gb.BCreflect.code, gb.InterpCubic.code, 0.0, None)
     assert rc == gb._lib.GB_ERR_UNSUPPORTED and b"InterpCubic" in lib.gb_last_error()
-    rc = lib.gb_grid_create(C.byref(h), 1, 5, (C.c_int64 * 5)(2, 2, 2, 2, 2), buf.ctypes.data, 0, 0, 1, 0.0, None)
+    rc = lib.gb_grid_create(C.byref(h), 1, 9, (C.c_int64 * 9)(*([2] * 9)), buf.ctypes.data, 0, 0, 1, 0.0, None)
     assert rc == gb._lib.GB_ERR_UNSUPPORTED
     rc = lib.gb_grid_create(C.byref(h), 7, 2, dims, buf.ctypes.data, 0, 0, 1, 0.0, None)
     assert rc == gb._lib.GB_ERR_ARG

@@ -432,3 +432,33 @@ def test_generic_nd_kernel(gb, oracle, bc, order):
             ov, og, oh, obad = oracle.evaluate(co, bc, order, X, mask)
         v, gr, h = g._eval(X, mask)
         assert same(v, ov) and same(gr, og) and (oh is None or same(h, oh))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape,world", [((9, 8, 20), 2), ((8, 9, 21), 3), ((12, 6, 64), 4), ((5, 7, 33), 8)])
+def test_slab_kernels_assemble_to_unsharded(gb, oracle, dtype, shape, world):
+    """gb_restrict_slab / gb_prolong_slab: every rank's slab (own planes + halo, cut straight out of
+    the global array here instead of exchanged) reproduces its planes of the unsharded result."""
+    import grid_jl_b200.dist as D
+
+    eng = D.GpuEngine()
+    A = oracle.synth(dtype, int(np.prod(shape)), seed=31).reshape(shape, order="F")
+    L3 = shape[2]
+    n3 = D.restrict_size(L3)
+    ref = oracle.restrict_flags(A, [True, True, True])
+    refp = oracle.prolong_sizes(ref, list(shape))
+    rplan, pplan = D.SlabPlan("restrict", L3, n3, world), D.SlabPlan("prolong", n3, L3, world)
+    for r in range(world):
+        e0, e1 = rplan.ext_range(r)
+        k0, k1 = rplan.out[r]
+        r12 = eng.restrict_dims12(gb.jl_from_numpy(np.asfortranarray(A[:, :, e0:e1])), 1.0)
+        mine = eng.restrict_slab(r12, 1.0, L3, e0, k0, k1 - k0)
+        assert same(gb.jl_to_numpy(mine), ref[:, :, k0:k1])
+        e0, e1 = pplan.ext_range(r)
+        k0, k1 = pplan.out[r]
+        p12 = eng.prolong_dims12(gb.jl_from_numpy(np.asfortranarray(ref[:, :, e0:e1])), shape[0], shape[1])
+        up = eng.prolong_slab(p12, n3, L3, e0, k0, k1 - k0)
+        assert same(gb.jl_to_numpy(up), refp[:, :, k0:k1])
+    # a slab that lacks a needed plane is refused
+    with pytest.raises(gb.ErrorException):
+        eng.restrict_slab(gb.jl_from_numpy(np.asfortranarray(A[:, :, 4:8])), 1.0, L3, 4, 1, 3)
