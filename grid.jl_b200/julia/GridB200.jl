@@ -1,0 +1,220 @@
+# GridB200.jl -- Julia (>= 1.6) host side of the B200 engine: Grid.jl's names over `ccall`s into
+# libgridb200.so (include/gridb200.h).
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no `julia` binary (see DESIGN.md);
+# the Python mirror grid.jl_b200/api.py binds the very same entry points with ctypes and is what
+# the tests drive.  This file is deliberately thin -- every decision lives behind the C ABI.
+#
+# Reference surface being preserved (timholy/Grid.jl): src/Grid.jl:28-70 (exports),
+# src/interp.jl:42-72,146-306 (InterpGrid, getindex, valgrad, valgradhess), src/coord.jl:3-69
+# (CoordInterpGrid), src/interp.jl:909-953 (interp_invert!), src/restrict_prolong.jl:10-185,322-355.
+module GridB200
+
+export BoundaryCondition, BCnil, BCnan, BCna, BCreflect, BCperiodic, BCnearest, BCfill,
+       InterpType, InterpNearest, InterpLinear, InterpQuadratic, InterpCubic,
+       AbstractInterpGrid, InterpGrid, CoordInterpGrid,
+       valgrad, valgradhess, getindex!, valgrad!, valgradhess!,
+       interp_invert!, pad1, restrict, prolong, restrict_size, prolong_size
+
+const LIB = get(ENV, "GRIDB200_LIB", joinpath(@__DIR__, "..", "libgridb200.so"))
+
+abstract type BoundaryCondition end
+struct BCnil <: BoundaryCondition end
+struct BCnan <: BoundaryCondition end
+struct BCna <: BoundaryCondition end
+struct BCreflect <: BoundaryCondition end
+struct BCperiodic <: BoundaryCondition end
+struct BCnearest <: BoundaryCondition end
+struct BCfill <: BoundaryCondition end
+abstract type InterpType end
+struct InterpNearest <: InterpType end
+struct InterpLinear <: InterpType end
+struct InterpQuadratic <: InterpType end
+struct InterpCubic <: InterpType end
+
+bccode(::Type{BCnil}) = 0; bccode(::Type{BCnan}) = 1; bccode(::Type{BCna}) = 2
+bccode(::Type{BCreflect}) = 3; bccode(::Type{BCperiodic}) = 4; bccode(::Type{BCnearest}) = 5; bccode(::Type{BCfill}) = 6
+itcode(::Type{InterpNearest}) = 0; itcode(::Type{InterpLinear}) = 1; itcode(::Type{InterpQuadratic}) = 2; itcode(::Type{InterpCubic}) = 3
+dtcode(::Type{Float32}) = 0; dtcode(::Type{Float64}) = 1
+const GB_HOST, GB_DEVICE = 0, 1
+const OUT_VAL, OUT_GRAD, OUT_HESS = 1, 2, 4
+
+lasterror() = unsafe_string(ccall((:gb_last_error, LIB), Cstring, ()))
+function check(rc::Cint, bad::Int64 = -1)
+    rc == 0 && return
+    msg = lasterror()
+    rc == 2 && error("Invalid location" * (bad >= 0 ? " (query $(bad + 1))" : ""))   # src/interp.jl:402-404
+    rc == 3 && throw(MethodError(getindex, ()))                                      # no method in the reference
+    rc == 5 && throw(DimensionMismatch(msg))                                         # src/coord.jl:7
+    error(msg)                                                                       # ErrorException
+end
+
+abstract type AbstractInterpGrid{T,N,BC<:BoundaryCondition,IT<:InterpType} <: AbstractArray{T,N} end
+
+mutable struct InterpGrid{T<:AbstractFloat,N,BC<:BoundaryCondition,IT<:InterpType} <: AbstractInterpGrid{T,N,BC,IT}
+    handle::Ptr{Cvoid}
+    dims::NTuple{N,Int}
+    fillval::T
+end
+
+function _create(A::Array{T,N}, ::Type{BC}, ::Type{IT}, fill::Float64) where {T,N,BC,IT}
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    dims = Int64[size(A)...]
+    GC.@preserve A dims begin
+        check(ccall((:gb_grid_create, LIB), Cint,
+                    (Ref{Ptr{Cvoid}}, Cint, Cint, Ptr{Int64}, Ptr{Cvoid}, Cint, Cint, Cint, Cdouble, Ptr{Cvoid}),
+                    h, dtcode(T), N, dims, A, GB_HOST, bccode(BC), itcode(IT), fill, C_NULL))
+    end
+    G = InterpGrid{T,N,BC,IT}(h[], size(A), T(fill))
+    finalizer(g -> ccall((:gb_grid_destroy, LIB), Cint, (Ptr{Cvoid},), g.handle), G)
+    G
+end
+# src/interp.jl:48-57 (generic), :58-65 (Cubic pads inside the library), :66-72 (fill value)
+function InterpGrid(A::Array{T,N}, ::Type{BC}, ::Type{IT}) where {T<:AbstractFloat,N,BC<:BoundaryCondition,IT<:InterpType}
+    BC == BCfill && error("Construct BCfill InterpGrids by supplying the fill value")
+    _create(A, BC, IT, NaN)
+end
+InterpGrid(A::Array{T,N}, f::Number, ::Type{IT}) where {T<:AbstractFloat,N,IT<:InterpType} = _create(A, BCfill, IT, Float64(f))
+
+Base.size(G::InterpGrid) = G.dims
+
+# ---- batched entry points (new; semantics = a loop of the scalar call) -------------------------
+# X is N x nq (one query per column), host memory.
+function _eval!(G::InterpGrid{T,N,BC}, mask::Int, X::Matrix{XT}, v, g, h; affine = C_NULL, flags::Int = 0) where {T,N,BC,XT<:Union{Float32,Float64}}
+    size(X, 1) == N || error("Incorrect number of dimensions supplied")           # src/interp.jl:88-90
+    nq = size(X, 2)
+    bad = Ref{Int64}(-1)
+    GC.@preserve X v g h begin
+        rc = ccall((:gb_eval, LIB), Cint,
+                   (Ptr{Cvoid}, Cint, Int64, Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Cdouble}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Ref{Int64}, Ptr{Cvoid}),
+                   G.handle, mask, nq, X, dtcode(XT), N, 1, affine,
+                   v === nothing ? C_NULL : pointer(v), g === nothing ? C_NULL : pointer(g), h === nothing ? C_NULL : pointer(h),
+                   GB_HOST, flags, bad, C_NULL)
+    end
+    check(rc, bad[])
+end
+getindex!(out::Vector{T}, G::InterpGrid{T,N}, X::Matrix) where {T,N} = (length(out) == size(X, 2) || error("output length"); _eval!(G, OUT_VAL, X, out, nothing, nothing); out)
+function valgrad!(v::Vector{T}, g::Matrix{T}, G::InterpGrid{T,N}, X::Matrix) where {T,N}
+    size(g) == (N, size(X, 2)) || error("Wrong number of components for the gradient")   # src/interp.jl:159-161
+    _eval!(G, OUT_VAL | OUT_GRAD, X, v, g, nothing); v
+end
+function valgradhess!(v::Vector{T}, g::Matrix{T}, h::Array{T,3}, G::InterpGrid{T,N}, X::Matrix) where {T,N}
+    size(g) == (N, size(X, 2)) || error("Wrong number of components for the gradient")   # :206-208
+    size(h) == (N, N, size(X, 2)) || error("Wrong number of components for the hessian") # :209-211
+    _eval!(G, OUT_VAL | OUT_GRAD | OUT_HESS, X, v, g, h); v
+end
+
+# ---- scalar API (src/interp.jl:146-270) ---------------------------------------------------------
+function Base.getindex(G::InterpGrid{T,N}, x::Real...) where {T,N}
+    if N == 1 && length(x) == 2
+        x[2] == 1 || throw(BoundsError())                                               # :147-153
+        x = x[1:1]
+    end
+    length(x) == N || error("Incorrect number of dimensions supplied")
+    out = Vector{T}(undef, 1)
+    getindex!(out, G, reshape(Float64[x...], N, 1))[1]
+end
+function valgrad(G::InterpGrid{T,N}, x::Real...) where {T,N}
+    v = Vector{T}(undef, 1); g = Matrix{T}(undef, N, 1)
+    valgrad!(v, g, G, reshape(Float64[x...], N, 1))
+    N == 1 ? (v[1], g[1]) : (v[1], vec(g))
+end
+function valgrad(g::AbstractVector{T}, G::InterpGrid{T,N}, x::Real...) where {T,N}
+    length(g) == N || error("Wrong number of components for the gradient")
+    v, gg = valgrad(G, x...); g .= gg; v
+end
+function valgradhess(G::InterpGrid{T,N}, x::Real...) where {T,N}
+    v = Vector{T}(undef, 1); g = Matrix{T}(undef, N, 1); h = Array{T,3}(undef, N, N, 1)
+    valgradhess!(v, g, h, G, reshape(Float64[x...], N, 1))
+    N == 1 ? (v[1], g[1], h[1]) : (v[1], vec(g), h[:, :, 1])
+end
+# tensor-product getindex (src/interp.jl:273-306)
+function Base.getindex(G::InterpGrid{T,N}, xs::AbstractVector{<:Real}...) where {T,N}
+    length(xs) == 1 && N > 1 && error("Linear indexing not supported")
+    length(xs) == N || error("Dimensionality mismatch")
+    vecs = [Vector{Float64}(x) for x in xs]
+    lens = Int64[length(v) for v in vecs]
+    out = Array{T,N}(undef, lens...)
+    ptrs = Ptr{Cvoid}[pointer(v) for v in vecs]
+    GC.@preserve vecs out ptrs lens check(ccall((:gb_eval_outer, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Int64}, Ptr{Ptr{Cvoid}}, Cint, Ptr{Cdouble}, Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}),
+        G.handle, lens, ptrs, 1, C_NULL, out, GB_HOST, 0, C_NULL))
+    out
+end
+
+# ---- CoordInterpGrid (src/coord.jl) ------------------------------------------------------------------
+struct CoordInterpGrid{T,N,BC,IT,R} <: AbstractInterpGrid{T,N,BC,IT}
+    coord::R
+    grid::InterpGrid{T,N,BC,IT}
+    affine::Matrix{Float64}      # 4 x N: kind, start, step, divisor  (coordlookup :30-32)
+end
+# Julia >= 1.0 ranges: StepRangeLen(ref, step, len, offset) plays FloatRange's role
+_row(r::StepRangeLen) = Float64[0, Float64(first(r)), Float64(step(r)), 1]
+_row(r::StepRange{<:Integer}) = Float64[1, first(r), step(r), 1]
+_row(r::UnitRange{<:Integer}) = Float64[2, first(r), 1, 1]
+function CoordInterpGrid(coord::NTuple{N,AbstractRange}, grid::InterpGrid{T,N,BC,IT}) where {T,N,BC,IT}
+    map(length, coord) == size(grid) || throw(DimensionMismatch("Coordinate lengths do not match grid size."))
+    CoordInterpGrid{T,N,BC,IT,typeof(coord)}(coord, grid, hcat(map(_row, coord)...))
+end
+CoordInterpGrid(coord::NTuple{N,AbstractRange}, A::Array{T,N}, args...) where {T<:AbstractFloat,N} = CoordInterpGrid(coord, InterpGrid(A, args...))
+CoordInterpGrid(coord::AbstractRange, A::Vector{T}, args...) where {T<:AbstractFloat} = CoordInterpGrid((coord,), InterpGrid(A, args...))
+Base.size(C::CoordInterpGrid) = size(C.grid)
+getindex!(out::Vector{T}, C::CoordInterpGrid{T,N}, X::Matrix) where {T,N} = (_eval!(C.grid, OUT_VAL, X, out, nothing, nothing; affine = pointer(C.affine)); out)
+valgrad!(v::Vector{T}, g::Matrix{T}, C::CoordInterpGrid{T,N}, X::Matrix) where {T,N} = (_eval!(C.grid, OUT_VAL | OUT_GRAD, X, v, g, nothing; affine = pointer(C.affine)); v)
+Base.getindex(C::CoordInterpGrid{T,N}, x::Real...) where {T,N} = getindex!(Vector{T}(undef, 1), C, reshape(Float64[x...], N, 1))[1]
+function valgrad(C::CoordInterpGrid{T,N}, x::Real...) where {T,N}
+    v = Vector{T}(undef, 1); g = Matrix{T}(undef, N, 1)
+    valgrad!(v, g, C, reshape(Float64[x...], N, 1))
+    N == 1 ? (v[1], g[1]) : (v[1], vec(g))
+end
+
+# ---- prefilter / padding ----------------------------------------------------------------------------
+function interp_invert!(A::Array{T,N}, ::Type{BC}, ::Type{IT}, dimlist = 1:N) where {T<:Union{Float32,Float64},N,BC<:BoundaryCondition,IT<:InterpType}
+    dims = Int64[size(A)...]; dl = Cint[d - 1 for d in dimlist]
+    GC.@preserve A dims dl check(ccall((:gb_invert, LIB), Cint,
+        (Cint, Cint, Ptr{Int64}, Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cint}, Cint, Ptr{Cvoid}),
+        dtcode(T), N, dims, A, GB_HOST, bccode(BC), itcode(IT), dl, length(dl), C_NULL))
+    A
+end
+function pad1(A::Array{T,N}, f::Number) where {T<:Union{Float32,Float64},N}
+    out = Array{T,N}(undef, (size(A) .+ 2)...); dims = Int64[size(A)...]
+    GC.@preserve A out dims check(ccall((:gb_pad1, LIB), Cint, (Cint, Cint, Ptr{Int64}, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+        dtcode(T), N, dims, A, Float64(f), out, GB_HOST, C_NULL))
+    out
+end
+
+# ---- restrict / prolong (src/restrict_prolong.jl) --------------------------------------------------
+restrict_size(len::Int) = isodd(len) ? div(len + 1, 2) : div(len, 2) + 1
+function prolong_size(sz::Int, len::Int)
+    newsz = isodd(len) ? 2sz - 1 : 2(sz - 1)
+    newsz == len || error("Cannot prolong a dimension of length ", sz, " to ", len)
+    newsz
+end
+function restrict(A::Array{T,N}, dim::Integer, scale::Real = one(T)) where {T<:Union{Float32,Float64},N}
+    sz = [size(A)...]; sz[dim] = restrict_size(sz[dim]); R = Array{T,N}(undef, sz...); dims = Int64[size(A)...]
+    GC.@preserve A R dims check(ccall((:gb_restrict, LIB), Cint, (Cint, Cint, Ptr{Int64}, Ptr{Cvoid}, Cint, Cdouble, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+        dtcode(T), N, dims, A, dim - 1, Float64(scale), R, GB_HOST, C_NULL))
+    R
+end
+function restrict(A::Array, flag::Union{Array{Bool},BitArray}, scale::Real = one(eltype(A)))     # mapdim, src/utilities.jl:7-20
+    ndims(A) == size(flag, 1) || error("Boolean flag must have as many rows as dimensions of A")
+    for j = 1:size(flag, 2), i = 1:size(flag, 1)
+        flag[i, j] && (A = restrict(A, i, scale))
+    end
+    A
+end
+function prolong(A::Array{T,N}, dim::Integer, len::Integer) where {T<:Union{Float32,Float64},N}
+    sz = [size(A)...]; sz[dim] = prolong_size(sz[dim], len); P = Array{T,N}(undef, sz...); dims = Int64[size(A)...]
+    GC.@preserve A P dims check(ccall((:gb_prolong, LIB), Cint, (Cint, Cint, Ptr{Int64}, Ptr{Cvoid}, Cint, Int64, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+        dtcode(T), N, dims, A, dim - 1, len, P, GB_HOST, C_NULL))
+    P
+end
+function prolong(A::Array, sz::Array{Int})
+    ndims(A) == size(sz, 1) || error("Array of sizes must have as many rows as dimensions of A")
+    for j = 1:size(sz, 2), i = 1:size(sz, 1)
+        sz[i, j] > size(A, i) && (A = prolong(A, i, sz[i, j]))
+    end
+    A
+end
+
+end # module
