@@ -369,6 +369,7 @@ template <int N> int launch_n(const EvalCall& c, cudaStream_t s) {
     p.q0 = c.q0;
     p.first_invalid = c.first_invalid;
     p.tiled = 0;
+    p.aos = 0;
     p.perm = nullptr; p.work = nullptr; p.nwork = nullptr;
     for (int d = 0; d < N; d++) { p.tile[d] = 1; p.ntile[d] = 1; }
     const int bcf = bc_family(g->bc);

@@ -49,6 +49,16 @@ template <typename T> struct dtype_of;
 template <> struct dtype_of<float> { static constexpr int value = GB_F32; };
 template <> struct dtype_of<double> { static constexpr int value = GB_F64; };
 
+// ---- brick geometry of the tiled evaluation (eval.cuh, eval_tile.cu) -------------------------------
+// fixed leading tile extents (cells), so that brick strides are compile-time constants; the extent
+// along the LAST dimension is chosen at run time (choose_tile): N=1 -, N=2 64, N=3 16x16, N=4 8x8x8
+__host__ __device__ constexpr int brick_tile(int N, int d) { return N == 2 ? 64 : N == 3 ? 16 : 8; }
+__host__ __device__ constexpr int brick_stride(int N, int L, int d) {
+    int s = 1;
+    for (int e = 0; e < d; e++) s *= brick_tile(N, e) + L - 1;
+    return s;
+}
+
 // ---- evaluation launch interface (eval_f32_*.cu / eval_f64_*.cu) -----------------------------
 template <int N> struct EvalParams {
     const void* coefs;
@@ -69,9 +79,10 @@ template <int N> struct EvalParams {
     u64* first_invalid;   // device, atomicMin target (BCnil) or NULL
     // tiled (spatially binned) evaluation, filled in by launch_one; tiled == 0 -> plain
     int tiled;
+    int aos;              // != 0: outputs are records of `aos` words per sorted slot at `val` (tiled mode)
     int tile[N];          // cells per tile
     int ntile[N];         // tiles per dimension
-    const u32* perm;      // query indices sorted by tile
+    const u32* perm;      // unused (records carry the query index)
     const u32* work;      // 3 words per work item: tile, begin, end (into perm)
     const u32* nwork;     // device scalar: number of work items
 };

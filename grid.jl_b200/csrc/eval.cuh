@@ -15,6 +15,7 @@
 // Compiled with -fmad=false: plain * and + never fuse.
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -182,7 +183,8 @@ template <typename T, int ORDER, int BCF> __device__ __forceinline__ bool dim_ta
 // ---- 1-D weights (src/interp.jl:785-847).  Julia's promotion rules for Float32 are spelled out:
 // Float64 literals (0.5, 0.75, 2/3, 1/2, 3/2, 1.0) promote the expression to Float64 and the
 // store rounds to T; Int literals keep T.  x^2 = x*x, x^3 = (x*x)*x.
-template <int ORDER, bool G, bool H>
+// FW (GB_FAST only): the two cubic divisions by 6 become multiplications by the rounded reciprocal.
+template <int ORDER, bool G, bool H, bool FW = false>
 __device__ __forceinline__ void weights(double dx, double (&w)[ORDER + 1], double (&g)[ORDER + 1], double (&h)[ORDER + 1]) {
     if constexpr (ORDER == GB_NEAREST) {
         w[0] = 1.0;
@@ -197,10 +199,10 @@ __device__ __forceinline__ void weights(double dx, double (&w)[ORDER + 1], doubl
         if (H) { h[0] = 1.0; h[1] = -2.0; h[2] = 1.0; }
     } else {
         double t = 1 - dx, u = dx - 1, d2 = dx * dx;
-        w[0] = ((t * t) * t) / 6;
+        w[0] = FW ? ((t * t) * t) * (1.0 / 6.0) : ((t * t) * t) / 6;
         w[1] = 2.0 / 3.0 - (d2 * (2 - dx)) / 2;
         w[2] = 2.0 / 3.0 - ((u * u) * (1 + dx)) / 2;
-        w[3] = (d2 * dx) / 6;
+        w[3] = FW ? (d2 * dx) * (1.0 / 6.0) : (d2 * dx) / 6;
         if (G) {
             g[0] = (-(t * t)) / 2;
             g[1] = (3 * d2) / 2 - 2 * dx;
@@ -210,7 +212,7 @@ __device__ __forceinline__ void weights(double dx, double (&w)[ORDER + 1], doubl
         if (H) { h[0] = 1 - dx; h[1] = 3 * dx - 2; h[2] = 1 - 3 * dx; h[3] = dx; }
     }
 }
-template <int ORDER, bool G, bool H>
+template <int ORDER, bool G, bool H, bool FW = false>
 __device__ __forceinline__ void weights(float dx, float (&w)[ORDER + 1], float (&g)[ORDER + 1], float (&h)[ORDER + 1]) {
     if constexpr (ORDER == GB_NEAREST) {
         w[0] = 1.0f;
@@ -267,44 +269,55 @@ __host__ __device__ constexpr int sel(int N, int k, int d) {
 }
 
 
-// ---- tap loads -----------------------------------------------------------------------------------
-// `base` is a generic pointer: the CTA's shared-memory brick (tiled mode, all taps inside) or the
-// coefficient array in global memory.  Offsets are 32-bit element offsets (grids are limited to
-// 2^32-1 elements at creation).
+// ---- tap sources ---------------------------------------------------------------------------------
+// The contractions below walk the l^N neighbourhood through a `cursor` (element offset) that a tap
+// source advances per dimension:
+//   GlobalTaps  the coefficient array in global memory; per-dimension offsets of the (possibly
+//               wrapped, possibly repeated) taps; GUARD = D1 (a tap past the array contributes c*0)
+//   BrickTaps   the CTA's shared-memory brick (eval_brick_kernel); taps of every dimension are
+//               consecutive cells and the brick strides are compile-time constants, so every tap is
+//               one LDS at base + immediate
 template <typename T> __device__ __forceinline__ bool nonfinite(T a);
 template <> __device__ __forceinline__ bool nonfinite<double>(double a) { return (__double2hiint(a) & 0x7ff00000) == 0x7ff00000; }
 template <> __device__ __forceinline__ bool nonfinite<float>(float a) { return (__float_as_int(a) & 0x7f800000) == 0x7f800000; }
-// running maximum of |a|'s high word over the taps of a query: >= expo_all_ones() iff some tap was NaN/Inf
-__device__ __forceinline__ u32 mag_hi(double a) { return (u32)__double2hiint(a) & 0x7fffffffu; }
-__device__ __forceinline__ u32 mag_hi(float a) { return (u32)__float_as_int(a) & 0x7fffffffu; }
-template <typename T> __device__ __forceinline__ constexpr u32 expo_all_ones() { return sizeof(T) == 8 ? 0x7ff00000u : 0x7f800000u; }
 
-template <typename T, bool GUARD> __device__ __forceinline__ T load_tap(const T* __restrict__ base, u32 j, u32 total) {
-    if constexpr (GUARD) return j < total ? base[j] : (T)0;  // D1: a tap past the array contributes c*0 = 0
-    return base[j];
-}
+template <typename T, int N, int L, bool GUARD> struct GlobalTaps {
+    const T* __restrict__ A;
+    u32 total;
+    u32 off[N][L];
+    template <int D> __device__ __forceinline__ u32 step(u32 cur, int i) const { return cur + off[D][i]; }
+    __device__ __forceinline__ T load(u32 j) const {
+        if constexpr (GUARD) return j < total ? A[j] : (T)0;
+        else return A[j];
+    }
+};
+
+template <typename T, int N, int L> struct BrickTaps {
+    const T* b;  // brick + offset of the query's first tap
+    template <int D> __device__ __forceinline__ u32 step(u32 cur, int i) const { return cur + (u32)(i * brick_stride(N, L, D)); }
+    __device__ __forceinline__ T load(u32 j) const { return b[j]; }
+};
 
 // ---- EXACT contraction -------------------------------------------------------------------------
 // acc_k += c_k * a per tap, tap order dim-1-fastest, c_k = ((w_N*w_{N-1})*...)*w_1 per pass k.
 // The reference's `c == 0 ? 0 : c*a` (src/interp.jl:504) differs from the plain product only when
 // a is NaN/Inf (0*a is then NaN instead of 0); adding the resulting +-0 never changes an
 // accumulator that started at +0.  So the hot loop forms the product unconditionally, with no
-// branch between the tap loads, and records whether any tap was non-finite (`mag`); such a query
-// is re-evaluated by eval_one_slow with the literal select.  Same bits, a third of the instructions.
-// Taps are loaded a plane (L x L) at a time so that the loads of a plane are in flight together.
-template <typename T, int N, int L, int NP, bool GUARD, int D> struct ExactRec {
-    static __device__ __forceinline__ void run(const T* __restrict__ A, u32 base, u32 total, const u32 (&off)[N][L],
-                                               const T (&w)[3][N][L], const T (&pp)[NP], T (&acc)[NP], u32& mag) {
+// branch between the tap loads.  A non-finite tap always leaves the VALUE accumulator non-finite
+// (every tap enters pass 0, c is finite, and Inf/NaN survive finite additions), so the caller
+// re-evaluates exactly those queries with the literal select (eval_one_slow).  Same bits, a third
+// of the instructions.  Taps are loaded a plane (L x L) at a time so the loads are in flight together.
+template <typename T, int N, int L, int NP, typename SRC, int D> struct ExactRec {
+    static __device__ __forceinline__ void run(const SRC& src, u32 cur, const T (&w)[3][N][L], const T (&pp)[NP], T (&acc)[NP]) {
         if constexpr (D <= 1) {
             constexpr int L1 = (D == 1) ? L : 1;
             T a[L1][L];
 #pragma unroll
-            for (int i1 = 0; i1 < L1; i1++)
+            for (int i1 = 0; i1 < L1; i1++) {
+                const u32 row = (D == 1) ? src.template step<D>(cur, i1) : cur;
 #pragma unroll
-                for (int i0 = 0; i0 < L; i0++) {
-                    a[i1][i0] = load_tap<T, GUARD>(A, base + (D == 1 ? off[D][i1] : 0u) + off[0][i0], total);
-                    mag = max(mag, mag_hi(a[i1][i0]));
-                }
+                for (int i0 = 0; i0 < L; i0++) a[i1][i0] = src.load(src.template step<0>(row, i0));
+            }
 #pragma unroll
             for (int i1 = 0; i1 < L1; i1++) {
                 T p1[NP];
@@ -336,7 +349,7 @@ template <typename T, int N, int L, int NP, bool GUARD, int D> struct ExactRec {
                     const T s = w[sel(N, k, D)][D][i];
                     p[k] = (D == N - 1) ? s : pp[k] * s;
                 }
-                ExactRec<T, N, L, NP, GUARD, D - 1>::run(A, base + off[D][i], total, off, w, p, acc, mag);
+                ExactRec<T, N, L, NP, SRC, D - 1>::run(src, src.template step<D>(cur, i), w, p, acc);
             }
         }
     }
@@ -344,8 +357,7 @@ template <typename T, int N, int L, int NP, bool GUARD, int D> struct ExactRec {
 
 // ---- FAST contraction: separable, FMA --------------------------------------------------------
 // Q = value, gradient components 0..D and Hessian entries (i<=j<=D) of the partial contraction
-// over dimensions 0..D.  Taps are loaded a plane (L x L) at a time so that the loads of a plane
-// are in flight together.  Non-finite taps are handled like in EXACT (mag -> eval_one_slow).
+// over dimensions 0..D.  Non-finite taps are handled like in EXACT (value non-finite -> eval_one_slow).
 template <typename T, int N, int OUTMODE> struct FastQ {
     T v;
     T g[OUTMODE >= 1 ? N : 1];
@@ -399,23 +411,21 @@ __device__ __forceinline__ void fast_fold(FastQ<T, N, OUTMODE>& out, const FastQ
         }
     }
 }
-template <typename T, int N, int L, int OUTMODE, bool GUARD, int D> struct FastRec {
-    static __device__ __forceinline__ FastQ<T, N, OUTMODE> run(const T* __restrict__ A, u32 base, u32 total,
-                                                              const u32 (&off)[N][L], const T (&w)[3][N][L], u32& mag) {
+template <typename T, int N, int L, int OUTMODE, typename SRC, int D> struct FastRec {
+    static __device__ __forceinline__ FastQ<T, N, OUTMODE> run(const SRC& src, u32 cur, const T (&w)[3][N][L]) {
         if constexpr (D == 0) {  // N == 1
             T a[L];
 #pragma unroll
-            for (int i = 0; i < L; i++) { a[i] = load_tap<T, GUARD>(A, base + off[0][i], total); mag = max(mag, mag_hi(a[i])); }
+            for (int i = 0; i < L; i++) a[i] = src.load(src.template step<0>(cur, i));
             return fast_row<T, N, L, OUTMODE>(a, w);
         } else if constexpr (D == 1) {  // one plane: L*L loads issued together
             T a[L][L];
 #pragma unroll
-            for (int i1 = 0; i1 < L; i1++)
+            for (int i1 = 0; i1 < L; i1++) {
+                const u32 row = src.template step<1>(cur, i1);
 #pragma unroll
-                for (int i0 = 0; i0 < L; i0++) {
-                    a[i1][i0] = load_tap<T, GUARD>(A, base + off[1][i1] + off[0][i0], total);
-                    mag = max(mag, mag_hi(a[i1][i0]));
-                }
+                for (int i0 = 0; i0 < L; i0++) a[i1][i0] = src.load(src.template step<0>(row, i0));
+            }
             FastQ<T, N, OUTMODE> out;
             fastq_zero<T, N, OUTMODE, 1>(out);
 #pragma unroll
@@ -429,13 +439,36 @@ template <typename T, int N, int L, int OUTMODE, bool GUARD, int D> struct FastR
             fastq_zero<T, N, OUTMODE, D>(out);
 #pragma unroll
             for (int i = 0; i < L; i++) {
-                const FastQ<T, N, OUTMODE> in = FastRec<T, N, L, OUTMODE, GUARD, D - 1>::run(A, base + off[D][i], total, off, w, mag);
+                const FastQ<T, N, OUTMODE> in = FastRec<T, N, L, OUTMODE, SRC, D - 1>::run(src, src.template step<D>(cur, i), w);
                 fast_fold<T, N, L, OUTMODE, D>(out, in, w, i);
             }
             return out;
         }
     }
 };
+
+// both schemes behind one call: acc[0] value, acc[1..N] gradient, then Hessian entries (i<=j), i-major
+template <typename T, int N, int L, int OUTMODE, bool FAST, typename SRC>
+__device__ __forceinline__ void contract(const SRC& src, const T (&w)[3][N][L], T (&acc)[num_passes(N, OUTMODE)]) {
+    constexpr int NP = num_passes(N, OUTMODE);
+    if constexpr (!FAST) {
+        T pp[NP];
+#pragma unroll
+        for (int k = 0; k < NP; k++) { acc[k] = (T)0; pp[k] = (T)1; }
+        ExactRec<T, N, L, NP, SRC, N - 1>::run(src, 0u, w, pp, acc);
+    } else {
+        const FastQ<T, N, OUTMODE> r = FastRec<T, N, L, OUTMODE, SRC, N - 1>::run(src, 0u, w);
+        acc[0] = r.v;
+        if constexpr (OUTMODE >= 1) {
+#pragma unroll
+            for (int d = 0; d < N; d++) acc[1 + d] = r.g[d];
+        }
+        if constexpr (OUTMODE >= 2) {
+#pragma unroll
+            for (int k = 0; k < N * (N + 1) / 2; k++) acc[1 + N + k] = r.h[hess_i(N, k) * N + hess_j(N, k)];
+        }
+    }
+}
 
 // ---- coordinate fetch: user coordinate -> index coordinate in T --------------------------------
 // (coordlookup src/coord.jl:30-32, setx src/interp.jl:75-139), each operation in Julia's type.
@@ -498,13 +531,12 @@ template <typename T, int N> __device__ __forceinline__ T scale_grad(const EvalP
 // dx == 0): the second tap is then ix+1 (its value weight is 0, its gradient weight is not).
 // Reproduced for bit-parity; the D1 guard keeps the load in bounds.
 template <typename T, int N, int ORDER, int BCF>
-__device__ __forceinline__ bool query_taps(const EvalParams<N>& p, const double (&raw)[N], int (&c)[N][ORDER + 1], T (&dx)[N]) {
+__device__ __forceinline__ bool query_taps(const EvalParams<N>& p, const T (&x)[N], int (&c)[N][ORDER + 1], T (&dx)[N]) {
     bool valid = true, anywrap = false;
 #pragma unroll
     for (int d = 0; d < N; d++) {
-        const T x = index_coord<T, N>(p, d, raw[d]);
         bool iswrap;
-        valid = dim_taps<T, ORDER, BCF>(x, p.len[d], c[d], dx[d], iswrap) && valid;
+        valid = dim_taps<T, ORDER, BCF>(x[d], p.len[d], c[d], dx[d], iswrap) && valid;
         anywrap = anywrap || iswrap;
     }
     if constexpr (ORDER == GB_LINEAR && BCF != BCF_NIL) {
@@ -515,19 +547,85 @@ __device__ __forceinline__ bool query_taps(const EvalParams<N>& p, const double 
     }
     return valid;
 }
+template <typename T, int N> __device__ __forceinline__ void load_index_coords(const EvalParams<N>& p, i64 q, T (&x)[N]) {
+#pragma unroll
+    for (int d = 0; d < N; d++) x[d] = index_coord<T, N>(p, d, load_raw<N>(p, d, q));
+}
+
+// outputs of one query (getindex / valgrad / valgradhess layouts, src/interp.jl:142-270).
+// `pos` addresses the outputs, `q` is the query's index in the caller's batch (BCnil reporting).
+// Plain mode: pos == q and val / grad / hess are the caller's arrays.  Tiled mode (p.aos != 0): pos is
+// the query's sorted slot and the outputs of a slot form one record of p.aos words at p.val
+// (value, gradient, full Hessian) -- written coalesced here, brought back to the caller's order and
+// arrays by unpermute_kernel.
+template <int N> __host__ __device__ constexpr int out_words(int outmode) { return 1 + (outmode >= 1 ? N : 0) + (outmode >= 2 ? N * N : 0); }
+template <typename T, int N, int OUTMODE>
+__device__ __forceinline__ void store_outputs(const EvalParams<N>& p, i64 pos, i64 q, bool valid, T (&acc)[num_passes(N, OUTMODE)]) {
+    constexpr int NP = num_passes(N, OUTMODE);
+    if (!valid) {
+#pragma unroll
+        for (int k = 0; k < NP; k++) acc[k] = qnan<T>();
+        if (p.first_invalid) atomicMin(p.first_invalid, (u64)(q + p.q0));
+    }
+    if (p.aos) {
+        constexpr int W = out_words<N>(OUTMODE);
+        alignas(16) T o[W];
+        o[0] = acc[0];
+        if constexpr (OUTMODE >= 1) {
+#pragma unroll
+            for (int d = 0; d < N; d++) o[1 + d] = valid ? scale_grad<T, N>(p, d, acc[1 + d]) : acc[1 + d];
+        }
+        if constexpr (OUTMODE >= 2) {
+#pragma unroll
+            for (int k = 0; k < N * (N + 1) / 2; k++) {
+                const int i = hess_i(N, k), j = hess_j(N, k);
+                o[1 + N + j * N + i] = acc[1 + N + k];
+                o[1 + N + i * N + j] = acc[1 + N + k];
+            }
+        }
+        T* dst = (T*)p.val + pos * W;
+        if constexpr (W * sizeof(T) == 32) {
+            reinterpret_cast<float4*>(dst)[0] = reinterpret_cast<const float4*>(o)[0];
+            reinterpret_cast<float4*>(dst)[1] = reinterpret_cast<const float4*>(o)[1];
+        } else if constexpr (W * sizeof(T) == 16) {
+            reinterpret_cast<float4*>(dst)[0] = reinterpret_cast<const float4*>(o)[0];
+        } else {
+#pragma unroll
+            for (int k = 0; k < W; k++) dst[k] = o[k];
+        }
+        return;
+    }
+    if (p.val) ((T*)p.val)[pos] = acc[0];
+    if constexpr (OUTMODE >= 1) {
+        if (p.grad) {
+            T* g = (T*)p.grad + pos * N;
+#pragma unroll
+            for (int d = 0; d < N; d++) g[d] = valid ? scale_grad<T, N>(p, d, acc[1 + d]) : acc[1 + d];
+        }
+    }
+    if constexpr (OUTMODE >= 2) {
+        T* h = (T*)p.hess + pos * (N * N);
+#pragma unroll
+        for (int k = 0; k < N * (N + 1) / 2; k++) {
+            const int i = hess_i(N, k), j = hess_j(N, k);
+            h[j * N + i] = acc[1 + N + k];
+            h[i * N + j] = acc[1 + N + k];
+        }
+    }
+}
 
 // ---- rare path: a query that touched a NaN/Inf coefficient ----------------------------------------
 // Literal restatement of interp (src/interp.jl:501-505) with the `c == 0 ? 0 : c*a` select, rolled
 // loops, global memory only, one pass per output.  Executed for (almost) no query; kept out of line.
 template <typename T, int N, int ORDER, int BCF>
-__device__ __noinline__ void eval_one_slow(const EvalParams<N>& p, const double (&raw)[N], const i64 q, const int outmode) {
+__device__ __noinline__ void eval_one_slow(const EvalParams<N>& p, const T (&x)[N], const i64 pos, const i64 q, const int outmode) {
     constexpr int L = ORDER + 1;
     constexpr bool GUARD = (ORDER == GB_LINEAR) || (BCF == BCF_NIL && ORDER == GB_CUBIC);
     const T* __restrict__ A = (const T*)p.coefs;
     int c[N][L];
     T dx[N];
     T w[3][N][L];
-    const bool valid = query_taps<T, N, ORDER, BCF>(p, raw, c, dx);
+    const bool valid = query_taps<T, N, ORDER, BCF>(p, x, c, dx);
 #pragma unroll
     for (int d = 0; d < N; d++) {
 #pragma unroll
@@ -576,12 +674,17 @@ __device__ __noinline__ void eval_one_slow(const EvalParams<N>& p, const double 
             }
         }
         if (!valid) acc = qnan<T>();
-        if (k == 0) {
-            if (p.val) ((T*)p.val)[q] = acc;
+        if (p.aos) {  // sorted-slot records (see store_outputs)
+            T* o = (T*)p.val + pos * p.aos;
+            if (k == 0) o[0] = acc;
+            else if (k <= N) o[k] = valid ? scale_grad<T, N>(p, k - 1, acc) : acc;
+            else { o[1 + N + hj * N + hi] = acc; o[1 + N + hi * N + hj] = acc; }
+        } else if (k == 0) {
+            if (p.val) ((T*)p.val)[pos] = acc;
         } else if (k <= N) {
-            if (p.grad) ((T*)p.grad)[q * N + (k - 1)] = valid ? scale_grad<T, N>(p, k - 1, acc) : acc;
+            if (p.grad) ((T*)p.grad)[pos * N + (k - 1)] = valid ? scale_grad<T, N>(p, k - 1, acc) : acc;
         } else {
-            T* h = (T*)p.hess + q * (N * N);
+            T* h = (T*)p.hess + pos * (N * N);
             h[hj * N + hi] = acc;
             h[hi * N + hj] = acc;
         }
@@ -589,313 +692,611 @@ __device__ __noinline__ void eval_one_slow(const EvalParams<N>& p, const double 
     if (!valid && p.first_invalid) atomicMin(p.first_invalid, (u64)(q + p.q0));
 }
 
-// ---- one query -------------------------------------------------------------------------------
-// Box<N>: the coefficient brick a CTA staged in shared memory (tiled mode).  A query whose taps all
-// fall inside the brick gathers from shared memory, any other query (wrapped taps at the grid
-// boundary, taps past the last sample, plain mode) gathers from global memory.
-template <int N> struct Box {
-    int lo[N];    // first coordinate of the brick
-    int clip[N];  // usable extent: min(tile + L - 1, len - lo)
-    int sb[N];    // element strides inside the brick
-    bool have;
-};
-
+// ---- one query, taps gathered from global memory ---------------------------------------------------
 template <typename T, int N, int ORDER, int BCF, int OUTMODE, bool FAST>
-__device__ __forceinline__ void eval_one(const EvalParams<N>& p, const double (&raw)[N], const i64 q, const T* __restrict__ A, const T* box,
-                                         const Box<N>& bx) {
+__device__ __forceinline__ void eval_one(const EvalParams<N>& p, const T (&x)[N], const i64 pos, const i64 q) {
     constexpr int L = ORDER + 1;
     constexpr int NP = num_passes(N, OUTMODE);
     // D1 guard: taps that can fall outside the array (upper-edge tap of Linear on the offset path,
     // 4th tap of Cubic at x == len-1).
     constexpr bool GUARD = (ORDER == GB_LINEAR) || (BCF == BCF_NIL && ORDER == GB_CUBIC);
-    u32 off[N][L];
     int c[N][L];
     T dx[N];
     T w[3][N][L];
-    const bool valid = query_taps<T, N, ORDER, BCF>(p, raw, c, dx);
+    const bool valid = query_taps<T, N, ORDER, BCF>(p, x, c, dx);
 #pragma unroll
-    for (int d = 0; d < N; d++) weights<ORDER, (OUTMODE >= 1), (OUTMODE >= 2)>(dx[d], w[0][d], w[1][d], w[2][d]);
-    bool allin = bx.have;
-    if (bx.have) {
-#pragma unroll
-        for (int d = 0; d < N; d++) {
-#pragma unroll
-            for (int i = 0; i < L; i++) allin = allin && (unsigned)(c[d][i] - bx.lo[d]) < (unsigned)bx.clip[d];
-        }
-    }
-    const T* base = allin ? box : A;
-    const u32 total = allin ? 0xffffffffu : (u32)p.total;
+    for (int d = 0; d < N; d++) weights<ORDER, (OUTMODE >= 1), (OUTMODE >= 2), FAST>(dx[d], w[0][d], w[1][d], w[2][d]);
+    GlobalTaps<T, N, L, GUARD> src;
+    src.A = (const T*)p.coefs;
+    src.total = (u32)p.total;
 #pragma unroll
     for (int d = 0; d < N; d++) {
 #pragma unroll
-        for (int i = 0; i < L; i++) off[d][i] = allin ? (u32)((c[d][i] - bx.lo[d]) * bx.sb[d]) : (u32)c[d][i] * (u32)p.stride[d];
+        for (int i = 0; i < L; i++) src.off[d][i] = (u32)c[d][i] * (u32)p.stride[d];
     }
     T acc[NP];
-    u32 mag = 0;
-    if constexpr (!FAST) {
-#pragma unroll
-        for (int k = 0; k < NP; k++) acc[k] = (T)0;
-        T pp[NP];
-#pragma unroll
-        for (int k = 0; k < NP; k++) pp[k] = (T)1;
-        ExactRec<T, N, L, NP, GUARD, N - 1>::run(base, 0u, total, off, w, pp, acc, mag);
-    } else {
-        const FastQ<T, N, OUTMODE> r = FastRec<T, N, L, OUTMODE, GUARD, N - 1>::run(base, 0u, total, off, w, mag);
-        acc[0] = r.v;
-        if constexpr (OUTMODE >= 1) {
-#pragma unroll
-            for (int d = 0; d < N; d++) acc[1 + d] = r.g[d];
-        }
-        if constexpr (OUTMODE >= 2) {
-#pragma unroll
-            for (int k = 0; k < N * (N + 1) / 2; k++) acc[1 + N + k] = r.h[hess_i(N, k) * N + hess_j(N, k)];
-        }
-    }
-    if (mag >= expo_all_ones<T>()) {  // a NaN/Inf coefficient was touched: literal zero-weight semantics
-        eval_one_slow<T, N, ORDER, BCF>(p, raw, q, OUTMODE);
+    contract<T, N, L, OUTMODE, FAST>(src, w, acc);
+    if (nonfinite(acc[0])) {  // a NaN/Inf coefficient may have been touched: literal zero-weight semantics
+        eval_one_slow<T, N, ORDER, BCF>(p, x, pos, q, OUTMODE);
         return;
     }
-    if (!valid) {
-#pragma unroll
-        for (int k = 0; k < NP; k++) acc[k] = qnan<T>();
-        if (p.first_invalid) atomicMin(p.first_invalid, (u64)(q + p.q0));
-    }
-    if (p.val) ((T*)p.val)[q] = acc[0];
-    if constexpr (OUTMODE >= 1) {
-        if (p.grad) {
-            T* g = (T*)p.grad + q * N;
-#pragma unroll
-            for (int d = 0; d < N; d++) g[d] = valid ? scale_grad<T, N>(p, d, acc[1 + d]) : acc[1 + d];
-        }
-    }
-    if constexpr (OUTMODE >= 2) {
-        T* h = (T*)p.hess + q * (N * N);
-#pragma unroll
-        for (int k = 0; k < N * (N + 1) / 2; k++) {
-            const int i = hess_i(N, k), j = hess_j(N, k);
-            h[j * N + i] = acc[1 + N + k];
-            h[i * N + j] = acc[1 + N + k];
-        }
-    }
+    store_outputs<T, N, OUTMODE>(p, pos, q, valid, acc);
 }
-
-// ---- the evaluation kernel ---------------------------------------------------------------------
-// The batch is a list of work items, each a range [begin,end) of query slots handled by one CTA.
-// plain mode : item w = slots [w*EVAL_BLOCK, (w+1)*EVAL_BLOCK) in the caller's order; taps are
-//              gathered from global memory.
-// tiled mode : the queries were binned by grid tile (tile_hist / tile_offsets / tile_scatter
-//              below); perm[j] is the original index of the query in sorted slot j.  For each item the CTA stages the tile's coefficient brick (tile +
-//              L-1 halo) in shared memory with coalesced loads, then evaluates the item's queries
-//              out of it: random 8-byte gathers that would each cost an HBM sector become
-//              shared-memory reads and the grid is read from HBM about once per step.
+// ---- plain evaluation kernel -----------------------------------------------------------------------
+// One thread per query in the caller's order, CTAs stride over blocks of EVAL_BLOCK queries; taps
+// are gathered from global memory through L1/L2.  The next query's coordinates are in flight
+// while the current one is evaluated.
 constexpr int EVAL_BLOCK = 256;
-constexpr u32 EVAL_CHUNK = 2048;  // queries per work item in tiled mode
 
 template <typename T, int N, int ORDER, int BCF, int OUTMODE, bool FAST>
 __global__ void __launch_bounds__(EVAL_BLOCK, 2) eval_kernel(const EvalParams<N> p) {
-    constexpr int L = ORDER + 1;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* box = reinterpret_cast<T*>(smem_raw);
-    const T* __restrict__ A = (const T*)p.coefs;
-    const bool tiled = p.tiled != 0;
-    Box<N> bx;
-    bx.have = false;
-    int full[N];  // brick extents (shared-memory layout)
-    int vol = 1, ntot = 1;
+    const i64 step = (i64)gridDim.x * EVAL_BLOCK;
+    i64 q = (i64)blockIdx.x * EVAL_BLOCK + threadIdx.x;
+    double raw_n[N];
+    if (q < p.nq) {
 #pragma unroll
-    for (int d = 0; d < N; d++) {
-        full[d] = p.tile[d] + L - 1;
-        bx.lo[d] = 0;
-        bx.clip[d] = 0;
-        bx.sb[d] = vol;
-        vol *= full[d];
-        ntot *= p.ntile[d];
+        for (int d = 0; d < N; d++) raw_n[d] = load_raw<N>(p, d, q);
     }
-    const i64 nwork = tiled ? (i64)p.nwork[0] : (p.nq + EVAL_BLOCK - 1) / EVAL_BLOCK;
-    __shared__ u32 s_item;
-    for (i64 wi = blockIdx.x;; wi += gridDim.x) {
-        if (tiled) {  // items differ in cost: CTAs pull them from a shared counter
-            if (threadIdx.x == 0) s_item = atomicAdd(const_cast<u32*>(p.nwork) + 1, 1u);
-            __syncthreads();
-            wi = s_item;
+    while (q < p.nq) {
+        T x[N];
+#pragma unroll
+        for (int d = 0; d < N; d++) x[d] = index_coord<T, N>(p, d, raw_n[d]);
+        const i64 qc = q;
+        q += step;
+        if (q < p.nq) {
+#pragma unroll
+            for (int d = 0; d < N; d++) raw_n[d] = load_raw<N>(p, d, q);
         }
-        if (wi >= nwork) break;
-        i64 begin, end;
-        if (tiled) {
-            const u32 tile = p.work[3 * wi];
-            begin = p.work[3 * wi + 1];
-            end = p.work[3 * wi + 2];
-            bx.have = tile < (u32)ntot;  // the last bin holds invalid queries: no brick needed
-            if (bx.have) {
-                u32 rem = tile;
-#pragma unroll
-                for (int d = 0; d < N; d++) {
-                    const int t = rem % p.ntile[d];
-                    rem /= p.ntile[d];
-                    bx.lo[d] = t * p.tile[d];
-                    const int left = p.len[d] - bx.lo[d];
-                    bx.clip[d] = full[d] < left ? full[d] : left;
-                }
-#pragma unroll 4
-                for (int e = threadIdx.x; e < vol; e += EVAL_BLOCK) {
-                    int r = e;
-                    u32 g = 0;
-                    bool inside = true;
-#pragma unroll
-                    for (int d = 0; d < N; d++) {
-                        const int rd = r % full[d];
-                        r /= full[d];
-                        inside = inside && rd < bx.clip[d];
-                        g += (u32)(bx.lo[d] + rd) * (u32)p.stride[d];
-                    }
-                    box[e] = inside ? __ldg(A + g) : (T)0;
-                }
-            }
-            __syncthreads();
-        } else {
-            begin = wi * EVAL_BLOCK;
-            end = begin + EVAL_BLOCK < p.nq ? begin + EVAL_BLOCK : p.nq;
-        }
-        // software pipeline: the next query's coordinates are in flight while the current one is
-        // evaluated (tiled mode: its original index perm[j] is fetched one step further ahead, the
-        // coordinates are gathered through it)
-        i64 j = begin + threadIdx.x;
-        double raw_n[N];
-        i64 q_n = 0, q_nn = 0;
-        if (j < end) {
-            q_n = tiled ? (i64)p.perm[j] : j;
-#pragma unroll
-            for (int d = 0; d < N; d++) raw_n[d] = load_raw<N>(p, d, q_n);
-            if (j + EVAL_BLOCK < end) q_nn = tiled ? (i64)p.perm[j + EVAL_BLOCK] : j + EVAL_BLOCK;
-        }
-        while (j < end) {
-            double raw[N];
-#pragma unroll
-            for (int d = 0; d < N; d++) raw[d] = raw_n[d];
-            const i64 q = q_n;
-            j += EVAL_BLOCK;
-            if (j < end) {
-                q_n = q_nn;
-#pragma unroll
-                for (int d = 0; d < N; d++) raw_n[d] = load_raw<N>(p, d, q_n);
-                if (j + EVAL_BLOCK < end) q_nn = tiled ? (i64)p.perm[j + EVAL_BLOCK] : j + EVAL_BLOCK;
-            }
-            eval_one<T, N, ORDER, BCF, OUTMODE, FAST>(p, raw, q, A, box, bx);
-        }
-        if (tiled) __syncthreads();
+        eval_one<T, N, ORDER, BCF, OUTMODE, FAST>(p, x, qc, qc);
     }
 }
 
-// ---- binning ----------------------------------------------------------------------------------------
-// Counting sort of the batch by grid tile without global atomics.  SORT_CTAS CTAs each own a
-// contiguous slice of the batch:
-//   tile_hist     key of every query (tile of its lowest tap per dimension; a locality hint only --
-//                 eval_one falls back to global memory for taps outside the brick) + a per-CTA
-//                 histogram in shared memory, written bin-major to bh[bin][cta]
-//   tile_offsets  (eval_tile.cu) per-bin totals, scan, work-item list, per-(bin,cta) write cursors
-//   tile_scatter  (eval_tile.cu) each CTA replays its slice: slot = its cursor for the key
-//                 (shared-memory atomic); writes perm[slot] = query index.  perm (4 B/query) stays
-//                 L2-resident, so the scattered 4-byte writes merge before they reach HBM; the
-//                 coordinates themselves are never moved (the evaluation gathers them through perm)
+// ====================================================================================================
+// Tiled ("brick") evaluation: the batch is counting-sorted by grid tile, then evaluated tile by tile
+// out of shared memory.
+//   tile_hist      key of every query (tile of its lowest tap per dimension) + per-CTA histograms in
+//                  shared memory (no global atomics), written bin-major to bh[bin][cta]
+//   tile_offsets   (eval_tile.cu) per-bin totals, scan, work-item list (a tile's queries split into
+//                  items of <= EVAL_CHUNK), per-(bin,cta) write cursors
+//   tile_scatter   each CTA replays its slice and writes one RECORD per query at its sorted slot:
+//                  the N index coordinates (already in T, affine map and setx shift applied) and the
+//                  query's original index -- (N+1) words of T, a full 32-byte sector for f64 N=3
+//   eval_brick     CTAs pull work items from an atomic counter.  The tile's coefficient brick
+//                  (tile + L-1 halo) is staged with cp.async into one of two shared-memory buffers
+//                  while the previous item is being evaluated; records are read coalesced (the first
+//                  record of the next item is prefetched across the item boundary); every tap is an
+//                  LDS at a compile-time offset from the query's first tap; outputs go to the
+//                  query's original position.
+//   eval_deferred  a query whose taps are not L consecutive cells inside the brick (wrapped /
+//                  repeated taps at the grid boundary, taps past the last sample, invalid location)
+//                  or that met a NaN/Inf coefficient is not evaluated by eval_brick: its slot goes
+//                  to a list and this kernel runs the global-memory path (eval_one) on the list, so
+//                  no boundary condition needs special bricks and results are bit-identical to plain.
+constexpr int BRICK_BLOCK = 256;
+constexpr u32 EVAL_CHUNK = 2048;  // queries per work item
+constexpr int SORT_BLOCK = 256;
+constexpr int SORT_UNROLL = 4;    // queries in flight per thread in the two sort passes
+constexpr int PASS1_UNROLL = 4;   // records in flight per thread in the brick kernel's locate pass
+
+template <typename T> __device__ __forceinline__ T bits_to(u32 q);
+template <> __device__ __forceinline__ double bits_to<double>(u32 q) { return __longlong_as_double((long long)q); }
+template <> __device__ __forceinline__ float bits_to<float>(u32 q) { return __uint_as_float(q); }
+__device__ __forceinline__ u32 bits_of(double v) { return (u32)__double_as_longlong(v); }
+__device__ __forceinline__ u32 bits_of(float v) { return __float_as_uint(v); }
+
+template <typename T, int N> __device__ __forceinline__ void store_record(T* __restrict__ rec, u32 slot, const T (&x)[N], u32 q) {
+    T* r = rec + (size_t)slot * (N + 1);
+    if constexpr (sizeof(T) == 8 && N == 3) {
+        reinterpret_cast<double2*>(r)[0] = make_double2(x[0], x[1]);
+        reinterpret_cast<double2*>(r)[1] = make_double2(x[2], bits_to<double>(q));
+    } else if constexpr (sizeof(T) == 8 && N == 1) {
+        reinterpret_cast<double2*>(r)[0] = make_double2(x[0], bits_to<double>(q));
+    } else if constexpr (sizeof(T) == 4 && N == 3) {
+        reinterpret_cast<float4*>(r)[0] = make_float4(x[0], x[1], x[2], bits_to<float>(q));
+    } else if constexpr (sizeof(T) == 4 && N == 1) {
+        reinterpret_cast<float2*>(r)[0] = make_float2(x[0], bits_to<float>(q));
+    } else {
+#pragma unroll
+        for (int d = 0; d < N; d++) r[d] = x[d];
+        r[N] = bits_to<T>(q);
+    }
+}
+template <typename T, int N> __device__ __forceinline__ void load_record(const T* __restrict__ rec, u32 slot, T (&x)[N], u32& q) {
+    const T* r = rec + (size_t)slot * (N + 1);
+    if constexpr (sizeof(T) == 8 && N == 3) {
+        const double2 a = __ldg(reinterpret_cast<const double2*>(r)), b = __ldg(reinterpret_cast<const double2*>(r) + 1);
+        x[0] = a.x; x[1] = a.y; x[2] = b.x; q = bits_of(b.y);
+    } else if constexpr (sizeof(T) == 8 && N == 1) {
+        const double2 a = __ldg(reinterpret_cast<const double2*>(r));
+        x[0] = a.x; q = bits_of(a.y);
+    } else if constexpr (sizeof(T) == 4 && N == 3) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(r));
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; q = bits_of(a.w);
+    } else if constexpr (sizeof(T) == 4 && N == 1) {
+        const float2 a = __ldg(reinterpret_cast<const float2*>(r));
+        x[0] = a.x; q = bits_of(a.y);
+    } else {
+#pragma unroll
+        for (int d = 0; d < N; d++) x[d] = __ldg(r + d);
+        q = bits_of(__ldg(r + N));
+    }
+}
+
 template <typename T, int N, int ORDER, int BCF>
-__global__ void __launch_bounds__(256) tile_hist_kernel(const EvalParams<N> p, u32* __restrict__ keys, u32* __restrict__ bh, u32 nbins, i64 per_cta) {
+__global__ void __launch_bounds__(SORT_BLOCK) tile_hist_kernel(const EvalParams<N> p, u32* __restrict__ keys, u32* __restrict__ bh, u32 nbins, i64 per_cta) {
     extern __shared__ u32 s_hist[];
-    for (u32 b = threadIdx.x; b < nbins; b += blockDim.x) s_hist[b] = 0;
+    for (u32 b = threadIdx.x; b < nbins; b += SORT_BLOCK) s_hist[b] = 0;
     __syncthreads();
     int ntot = 1;
 #pragma unroll
     for (int d = 0; d < N; d++) ntot *= p.ntile[d];
+    int shift[N];  // tile extents are powers of two (choose_tile)
+#pragma unroll
+    for (int d = 0; d < N; d++) shift[d] = __ffs(p.tile[d]) - 1;
     const i64 q0 = (i64)blockIdx.x * per_cta;
     const i64 q1 = q0 + per_cta < p.nq ? q0 + per_cta : p.nq;
-    for (i64 q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
-        double raw[N];
+    for (i64 qb = q0 + threadIdx.x; qb < q1; qb += SORT_BLOCK * SORT_UNROLL) {
+        double raw[SORT_UNROLL][N];
 #pragma unroll
-        for (int d = 0; d < N; d++) raw[d] = load_raw<N>(p, d, q);
-        int c[N][ORDER + 1];
-        T dx[N];
-        const bool valid = query_taps<T, N, ORDER, BCF>(p, raw, c, dx);
-        u32 key = 0, mul = 1;
+        for (int u = 0; u < SORT_UNROLL; u++) {
+            const i64 q = qb + u * SORT_BLOCK;
+            if (q < q1) {
 #pragma unroll
-        for (int d = 0; d < N; d++) {
-            int lo = c[d][0];
-#pragma unroll
-            for (int i = 1; i <= ORDER; i++) lo = c[d][i] < lo ? c[d][i] : lo;
-            lo = lo < 0 ? 0 : (lo >= p.len[d] ? p.len[d] - 1 : lo);
-            key += (u32)(lo / p.tile[d]) * mul;
-            mul *= (u32)p.ntile[d];
+                for (int d = 0; d < N; d++) raw[u][d] = load_raw<N>(p, d, q);
+            }
         }
-        if (!valid) key = (u32)ntot;
-        keys[q] = key;
-        atomicAdd(s_hist + key, 1u);
+#pragma unroll
+        for (int u = 0; u < SORT_UNROLL; u++) {
+            const i64 q = qb + u * SORT_BLOCK;
+            if (q < q1) {
+                T x[N];
+#pragma unroll
+                for (int d = 0; d < N; d++) x[d] = index_coord<T, N>(p, d, raw[u][d]);
+                int c[N][ORDER + 1];
+                T dx[N];
+                const bool valid = query_taps<T, N, ORDER, BCF>(p, x, c, dx);
+                u32 key = 0, mul = 1;
+#pragma unroll
+                for (int d = 0; d < N; d++) {
+                    int lo = c[d][0];
+#pragma unroll
+                    for (int i = 1; i <= ORDER; i++) lo = c[d][i] < lo ? c[d][i] : lo;
+                    lo = lo < 0 ? 0 : (lo >= p.len[d] ? p.len[d] - 1 : lo);
+                    key += (u32)(lo >> shift[d]) * mul;
+                    mul *= (u32)p.ntile[d];
+                }
+                if (!valid) key = (u32)ntot;
+                keys[q] = key;
+                atomicAdd(s_hist + key, 1u);
+            }
+        }
     }
     __syncthreads();
-    for (u32 b = threadIdx.x; b < nbins; b += blockDim.x) bh[(size_t)b * gridDim.x + blockIdx.x] = s_hist[b];
+    for (u32 b = threadIdx.x; b < nbins; b += SORT_BLOCK) bh[(size_t)b * gridDim.x + blockIdx.x] = s_hist[b];
 }
 
-__global__ void __launch_bounds__(256) tile_scatter_kernel(const u32* __restrict__ keys, i64 nq, const u32* __restrict__ boff, u32* __restrict__ perm,
-                                                           u32 nbins, i64 per_cta);
+template <typename T, int N>
+__global__ void __launch_bounds__(SORT_BLOCK) tile_scatter_kernel(const EvalParams<N> p, const u32* __restrict__ keys, const u32* __restrict__ boff,
+                                                                  T* __restrict__ rec, u32* __restrict__ inv, u32 nbins, i64 per_cta) {
+    extern __shared__ u32 s_cur[];
+    for (u32 b = threadIdx.x; b < nbins; b += SORT_BLOCK) s_cur[b] = boff[(size_t)b * gridDim.x + blockIdx.x];
+    __syncthreads();
+    const i64 q0 = (i64)blockIdx.x * per_cta;
+    const i64 q1 = q0 + per_cta < p.nq ? q0 + per_cta : p.nq;
+    for (i64 qb = q0 + threadIdx.x; qb < q1; qb += SORT_BLOCK * SORT_UNROLL) {
+        double raw[SORT_UNROLL][N];
+        u32 key[SORT_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SORT_UNROLL; u++) {
+            const i64 q = qb + u * SORT_BLOCK;
+            if (q < q1) {
+                key[u] = keys[q];
+#pragma unroll
+                for (int d = 0; d < N; d++) raw[u][d] = load_raw<N>(p, d, q);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < SORT_UNROLL; u++) {
+            const i64 q = qb + u * SORT_BLOCK;
+            if (q < q1) {
+                T x[N];
+#pragma unroll
+                for (int d = 0; d < N; d++) x[d] = index_coord<T, N>(p, d, raw[u][d]);
+                const u32 slot = atomicAdd(s_cur + key[u], 1u);
+                store_record<T, N>(rec, slot, x, (u32)q);
+                inv[q] = slot;
+            }
+        }
+    }
+}
+
+// ---- cp.async (Ampere-style async copies are the right granule here: brick rows are short and
+// arbitrarily aligned, so elements travel one by one; zero-fill handles cells past the array) ---------
+template <int BYTES> __device__ __forceinline__ void cp_async_zfill(u32 saddr, const void* g, bool pred) {
+    const int sz = pred ? BYTES : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(saddr), "l"(g), "n"(BYTES), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int KEEP> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(KEEP) : "memory"); }
+
+template <int N, int L> __device__ __forceinline__ void brick_geo(const EvalParams<N>& p, u32 tile, int (&lo)[N], int (&clip)[N]) {
+    u32 rem = tile;
+#pragma unroll
+    for (int d = 0; d < N; d++) {
+        const int t = rem % (u32)p.ntile[d];
+        rem /= (u32)p.ntile[d];
+        lo[d] = t * p.tile[d];
+        const int full = p.tile[d] + L - 1, left = p.len[d] - lo[d];
+        clip[d] = full < left ? full : left;
+    }
+}
+template <typename T, int N, int L> __device__ __forceinline__ void brick_fill(const EvalParams<N>& p, const T* __restrict__ A, T* brick, u32 tile, int vol) {
+    int lo[N], clip[N];
+    brick_geo<N, L>(p, tile, lo, clip);
+    const u32 sbase = (u32)__cvta_generic_to_shared(brick);
+#pragma unroll 4
+    for (int e = threadIdx.x; e < vol; e += BRICK_BLOCK) {
+        int r = e;
+        u32 g = 0;
+        bool inside = true;
+#pragma unroll
+        for (int d = 0; d < N - 1; d++) {
+            const int F = brick_tile(N, d) + L - 1;  // a constant after unrolling
+            const int rd = r % F;
+            r /= F;
+            inside = inside && rd < clip[d];
+            g += (u32)(lo[d] + rd) * (u32)p.stride[d];
+        }
+        inside = inside && r < clip[N - 1];
+        g += (u32)(lo[N - 1] + r) * (u32)p.stride[N - 1];
+        cp_async_zfill<(int)sizeof(T)>(sbase + (u32)e * (u32)sizeof(T), inside ? (const void*)(A + g) : (const void*)A, inside);
+    }
+}
+
+// Deferral: append sorted slot j to the list of queries the brick kernel does not evaluate itself
+// (warp-aggregated: one atomic per group of lanes deferring together).  defer[0] = count.
+__device__ __forceinline__ void defer_slot(u32* __restrict__ defer, u32 j) {
+    const unsigned m = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    u32 base = 0;
+    if (lane == leader) base = atomicAdd(defer, (u32)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    defer[1 + base + __popc(m & ((1u << lane) - 1u))] = j;
+}
+
+// Brick offset of a query's first tap, or BRICK_DEFER if the brick path cannot take the query (taps
+// that are not L consecutive cells inside the brick, invalid location); dx = fractional offsets.
+constexpr u32 BRICK_DEFER = 0xffffu;
+template <typename T, int N, int ORDER, int BCF>
+__device__ __forceinline__ u32 brick_locate(const EvalParams<N>& p, const T (&x)[N], const int (&lo)[N], const int (&clip)[N], const bool have, T (&dx)[N]) {
+    constexpr int L = ORDER + 1;
+    int c[N][L];
+    const bool valid = query_taps<T, N, ORDER, BCF>(p, x, c, dx);
+    bool ok = valid && have;
+    u32 boff = 0;
+#pragma unroll
+    for (int d = 0; d < N; d++) {
+        const int rel = c[d][0] - lo[d];
+        ok = ok && rel >= 0 && rel + L <= clip[d];
+#pragma unroll
+        for (int i = 1; i < L; i++) ok = ok && c[d][i] == c[d][0] + i;
+        boff += (u32)rel * (u32)brick_stride(N, L, d);
+    }
+    return ok ? boff : BRICK_DEFER;
+}
+// one located query out of the brick: weights, contraction, outputs to sorted slot j
+template <typename T, int N, int ORDER, int BCF, int OUTMODE, bool FAST>
+__device__ __forceinline__ void brick_eval_one(const EvalParams<N>& p, const T (&dx)[N], const i64 q, const u32 j, const T* brick, const u32 boff,
+                                               u32* __restrict__ defer) {
+    constexpr int L = ORDER + 1;
+    constexpr int NP = num_passes(N, OUTMODE);
+    T w[3][N][L];
+#pragma unroll
+    for (int d = 0; d < N; d++) weights<ORDER, (OUTMODE >= 1), (OUTMODE >= 2), FAST>(dx[d], w[0][d], w[1][d], w[2][d]);
+    BrickTaps<T, N, L> src;
+    src.b = brick + boff;
+    T acc[NP];
+    contract<T, N, L, OUTMODE, FAST>(src, w, acc);
+    if (nonfinite(acc[0])) {  // a NaN/Inf coefficient may have been touched (see ExactRec): literal path, later
+        defer_slot(defer, j);
+        return;
+    }
+    store_outputs<T, N, OUTMODE>(p, (i64)j, q, true, acc);
+}
+
+// the deferred queries: plain evaluation (eval_one) of the records whose slots are listed
+template <typename T, int N, int ORDER, int BCF, int OUTMODE, bool FAST>
+__global__ void __launch_bounds__(EVAL_BLOCK, 2) eval_deferred_kernel(const EvalParams<N> p, const T* __restrict__ rec, const u32* __restrict__ defer) {
+    const u32 n = defer[0];
+    for (u32 i = blockIdx.x * EVAL_BLOCK + threadIdx.x; i < n; i += gridDim.x * EVAL_BLOCK) {
+        T x[N];
+        u32 q;
+        const u32 j = defer[1 + i];
+        load_record<T, N>(rec, j, x, q);
+        eval_one<T, N, ORDER, BCF, OUTMODE, FAST>(p, x, (i64)j, (i64)q);
+    }
+}
+
+// Shared-memory bank classes.  A warp's 64-bit shared loads are served per half-warp, 16 lanes x 8
+// bytes = the 32 banks once.  Within an item the queries sit at random brick offsets, so a tap load
+// (same compile-time offset from every lane's first tap) would hit random banks -- measured 2.9
+// wavefronts per half-warp instead of 1, and the LSU pipe at 93 %.  Therefore lane t only evaluates
+// queries whose first-tap offset is congruent to t modulo 16: every tap load of a half-warp then
+// touches 16 different bank pairs.  Per item the records are bucketed by class (two short passes
+// over the item with shared-memory counters); class c is served by the 16 threads t = c (mod 16).
+// Classes are never equally full: each thread runs T = ceil(n/256) rounds, and a thread whose class
+// runs dry pulls from the overflow of fuller classes (those few loads may conflict).
+template <typename T, int N, int ORDER, int BCF, int OUTMODE, bool FAST>
+__global__ void __launch_bounds__(BRICK_BLOCK, 2) eval_brick_kernel(const EvalParams<N> p, const T* __restrict__ rec, u32* __restrict__ defer) {
+    constexpr int L = ORDER + 1;
+    // Bank-class binning pays where the shared-memory pipe is the limiter (FAST: 64 loads per ~270
+    // FP64 operations); EXACT is bound by the FP64 pipe (816 dependent multiply/add per query) and
+    // keeps the direct schedule, which has fewer barriers per item.
+    constexpr bool BINNED = FAST;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ u32 s_it[2];
+    __shared__ u32 s_cnt[2][16], s_cur[2][16], s_opull[2], s_off[17], s_ooff[17];  // counters: one set per item parity
+    __shared__ unsigned short s_boff[EVAL_CHUNK], s_idx[EVAL_CHUNK];
+    T* bricks = reinterpret_cast<T*>(smem_raw);
+    const T* __restrict__ A = (const T*)p.coefs;
+    const int vol = brick_stride(N, L, N - 1) * (p.tile[N - 1] + L - 1);
+    const int volp = (vol + 3) & ~3;
+    u32 ntot = 1;
+#pragma unroll
+    for (int d = 0; d < N; d++) ntot *= (u32)p.ntile[d];
+    const u32 nwork = p.nwork[0];
+    u32* ctr = const_cast<u32*>(p.nwork) + 1;
+    const u32* __restrict__ work = p.work;
+    const u32 tid = threadIdx.x;
+    // items differ in cost: CTAs pull them from a shared counter, one item ahead of the one being
+    // staged (thread 0 keeps the next ticket in a register, so the atomic's latency is hidden)
+    u32 pend = 0;
+    if (tid == 0) {
+        s_it[0] = atomicAdd(ctr, 1u);
+        pend = atomicAdd(ctr, 1u);
+    }
+    if (tid < 16) { s_cnt[0][tid] = 0; s_cur[0][tid] = 0; }
+    if (tid == 16) s_opull[0] = 0;
+    __syncthreads();
+    u32 cur = s_it[0];
+    u32 tile_c = 0, beg_c = 0, end_c = 0;
+    if (cur < nwork) {
+        tile_c = work[3 * cur]; beg_c = work[3 * cur + 1]; end_c = work[3 * cur + 2];
+        if (tile_c < ntot) brick_fill<T, N, L>(p, A, bricks, tile_c, vol);
+    }
+    cp_async_commit();
+    T xn[N];  // direct mode: the prefetched record
+    u32 qn = 0;
+#pragma unroll
+    for (int d = 0; d < N; d++) xn[d] = (T)0;
+    for (int k = 0; cur < nwork; k++) {
+        const int par = k & 1;
+        if (tid == 0) {
+            s_it[par ^ 1] = pend;
+            pend = atomicAdd(ctr, 1u);
+        }
+        __syncthreads();  // ticket visible; every thread is done with item k-1, whose buffer is refilled now
+        if (tid < 16) { s_cnt[par ^ 1][tid] = 0; s_cur[par ^ 1][tid] = 0; }  // the next item's counters (idle since item k-1)
+        if (tid == 16) s_opull[par ^ 1] = 0;
+        const u32 nxt = s_it[par ^ 1];
+        u32 tile_n = 0, beg_n = 0, end_n = 0;
+        if (nxt < nwork) {
+            tile_n = work[3 * nxt]; beg_n = work[3 * nxt + 1]; end_n = work[3 * nxt + 2];
+            if (tile_n < ntot) brick_fill<T, N, L>(p, A, bricks + (size_t)(par ^ 1) * volp, tile_n, vol);
+        }
+        cp_async_commit();
+        int lo[N], clip[N];
+        const bool have = tile_c < ntot;  // the last bin holds invalid queries: no brick
+        brick_geo<N, L>(p, have ? tile_c : 0u, lo, clip);
+        const u32 n = end_c - beg_c;
+        if constexpr (BINNED) {
+            // ---- pass 1 over the item's records: locate, count the bank classes (the brick is not needed yet)
+            for (u32 r0 = tid; r0 < n; r0 += BRICK_BLOCK * PASS1_UNROLL) {
+                T x[PASS1_UNROLL][N];
+                u32 q;
+#pragma unroll
+                for (int u = 0; u < PASS1_UNROLL; u++)  // the loads of PASS1_UNROLL records in flight together
+                    if (r0 + u * BRICK_BLOCK < n) load_record<T, N>(rec, beg_c + r0 + u * BRICK_BLOCK, x[u], q);
+#pragma unroll
+                for (int u = 0; u < PASS1_UNROLL; u++) {
+                    const u32 r = r0 + u * BRICK_BLOCK;
+                    if (r < n) {
+                        T dxu[N];
+                        const u32 boff = brick_locate<T, N, ORDER, BCF>(p, x[u], lo, clip, have, dxu);
+                        s_boff[r] = (unsigned short)boff;
+                        if (boff == BRICK_DEFER) defer_slot(defer, beg_c + r);  // global-memory path, later
+                        else atomicAdd(&s_cnt[par][boff & 15u], 1u);
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid < 32) {  // exclusive scans of the class counts and of the class overflows
+                const u32 cnt = tid < 16 ? s_cnt[par][tid] : 0u;
+                u32 incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if ((int)tid >= o) incl += t;
+                }
+                const u32 n_ok = __shfl_sync(0xffffffffu, incl, 15);
+                const u32 cap = 16u * ((n_ok + BRICK_BLOCK - 1) / BRICK_BLOCK);
+                const u32 over = cnt > cap ? cnt - cap : 0u;
+                u32 oincl = over;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const u32 t = __shfl_up_sync(0xffffffffu, oincl, o);
+                    if ((int)tid >= o) oincl += t;
+                }
+                if (tid <= 16) { s_off[tid] = incl - cnt; s_ooff[tid] = oincl - over; }
+            }
+            __syncthreads();
+            // ---- pass 2: class-sorted index list
+            for (u32 r = tid; r < n; r += BRICK_BLOCK) {
+                const u32 b = s_boff[r];
+                if (b != BRICK_DEFER) {
+                    const u32 cl = b & 15u;
+                    s_idx[s_off[cl] + atomicAdd(&s_cur[par][cl], 1u)] = (unsigned short)r;
+                }
+            }
+            cp_async_wait<1>();  // this thread's copies for item k have landed ...
+            __syncthreads();     // ... and everybody else's; the index list is complete
+            // ---- evaluation: T rounds, thread t serves class t mod 16
+            const T* brick = bricks + (size_t)par * volp;
+            const u32 cls = tid & 15u, rank = tid >> 4;
+            const u32 n_ok = s_off[16], rounds = (n_ok + BRICK_BLOCK - 1) / BRICK_BLOCK, cap = 16u * rounds;
+            const u32 mine = min(s_cnt[par][cls], cap), base = s_off[cls], n_over = s_ooff[16];
+            // next_record: index of this thread's record for round i (own class, else overflow of a fuller class)
+            auto next_record = [&](u32 i, u32& r) -> bool {
+                if (i >= rounds) return false;
+                const u32 e = rank + 16u * i;
+                if (e < mine) {
+                    r = s_idx[base + e];
+                    return true;
+                }
+                const u32 o = atomicAdd(&s_opull[par], 1u);  // my class ran dry
+                if (o >= n_over) return false;
+                u32 cl = 0;
+                while (o >= s_ooff[cl + 1]) cl++;
+                r = s_idx[s_off[cl] + cap + (o - s_ooff[cl])];
+                return true;
+            };
+            u32 rn = 0;
+            bool more = next_record(0, rn);
+            if (more) load_record<T, N>(rec, beg_c + rn, xn, qn);
+            for (u32 i = 0; more; i++) {
+                T x[N];
+#pragma unroll
+                for (int d = 0; d < N; d++) x[d] = xn[d];
+                const u32 q = qn, r = rn;
+                more = next_record(i + 1, rn);
+                if (more) load_record<T, N>(rec, beg_c + rn, xn, qn);  // in flight during this round's evaluation
+                int cc[N][L];
+                T dx[N];
+                query_taps<T, N, ORDER, BCF>(p, x, cc, dx);
+                brick_eval_one<T, N, ORDER, BCF, OUTMODE, FAST>(p, dx, (i64)q, beg_c + r, brick, (u32)s_boff[r], defer);
+            }
+        } else {
+            // ---- direct: thread t takes records t, t+256, ... of the item; the next record is in flight
+            // while the current one is evaluated (across the item boundary too)
+            cp_async_wait<1>();  // this thread's copies for item k have landed ...
+            __syncthreads();     // ... and everybody else's
+            const T* brick = bricks + (size_t)par * volp;
+            const bool next_has = nxt < nwork && beg_n + tid < end_n;
+            u32 j = beg_c + tid;
+            if (k == 0 && j < end_c) load_record<T, N>(rec, j, xn, qn);
+            if (j >= end_c) {
+                if (next_has) load_record<T, N>(rec, beg_n + tid, xn, qn);
+            } else {
+                while (true) {
+                    T x[N];
+#pragma unroll
+                    for (int d = 0; d < N; d++) x[d] = xn[d];
+                    const u32 q = qn, jc = j;
+                    j += BRICK_BLOCK;
+                    const bool more = j < end_c;
+                    if (more) load_record<T, N>(rec, j, xn, qn);
+                    else if (next_has) load_record<T, N>(rec, beg_n + tid, xn, qn);
+                    T dx[N];
+                    const u32 boff = brick_locate<T, N, ORDER, BCF>(p, x, lo, clip, have, dx);
+                    if (boff == BRICK_DEFER) defer_slot(defer, jc);  // global-memory path, later
+                    else brick_eval_one<T, N, ORDER, BCF, OUTMODE, FAST>(p, dx, (i64)q, jc, brick, boff, defer);
+                    if (!more) break;
+                }
+            }
+        }
+        cur = nxt; tile_c = tile_n; beg_c = beg_n; end_c = end_n;
+    }
+    cp_async_wait<0>();
+}
+
+// caller's order <- sorted slots: thread q gathers its slot's output record (one 32-byte sector for
+// f64 valgrad in 3-D) and writes the caller's val / grad / hess arrays coalesced.
+template <typename T, int N, int OUTMODE>
+__global__ void __launch_bounds__(256) unpermute_kernel(const T* __restrict__ osorted, const u32* __restrict__ inv, T* __restrict__ val, T* __restrict__ grad,
+                                                        T* __restrict__ hess, i64 nq) {
+    constexpr int W = out_words<N>(OUTMODE);
+    for (i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (i64)gridDim.x * blockDim.x) {
+        const T* src = osorted + (size_t)inv[q] * W;
+        alignas(16) T o[W];
+        if constexpr (W * sizeof(T) == 32) {
+            reinterpret_cast<float4*>(o)[0] = __ldcs(reinterpret_cast<const float4*>(src));
+            reinterpret_cast<float4*>(o)[1] = __ldcs(reinterpret_cast<const float4*>(src) + 1);
+        } else if constexpr (W * sizeof(T) == 16) {
+            reinterpret_cast<float4*>(o)[0] = __ldcs(reinterpret_cast<const float4*>(src));
+        } else {
+#pragma unroll
+            for (int k = 0; k < W; k++) o[k] = __ldcs(src + k);
+        }
+        if (val) val[q] = o[0];
+        if constexpr (OUTMODE >= 1) {
+            if (grad) {
+#pragma unroll
+                for (int d = 0; d < N; d++) grad[q * N + d] = o[1 + d];
+            }
+        }
+        if constexpr (OUTMODE >= 2) {
+            if (hess) {
+#pragma unroll
+                for (int k = 0; k < N * N; k++) hess[q * (N * N) + k] = o[1 + N + k];
+            }
+        }
+    }
+}
 
 // eval_tile.cu
 int tile_offsets(const u32* bh, u32 nbins, u32 nctas, u32* hist, u32* offs, u32* boff, u32* work, u32* nwork, u32 chunk, cudaStream_t s);
-bool choose_tile(int N, int L, size_t esz, const int* len, i64 nq, int* tile, int* ntile);
+bool choose_tile(int N, int L, size_t esz, const int* len, i64 nq, bool forced, int* tile, int* ntile);
 constexpr u32 SORT_MAX_BINS = 12000;  // per-CTA histogram lives in shared memory (<= 48 KB)
+// Larger batches are evaluated in slices: bounds the record scratch, and (more importantly) keeps the
+// randomly written regions -- the slice's records and its outputs -- small enough to live in L2.
+inline i64 tiled_max_batch() {
+    static const i64 v = [] {
+        const char* e = getenv("GB_TILED_BATCH");
+        const long long x = e ? atoll(e) : 0;
+        return (i64)(x >= 1024 ? x : ((i64)1 << 26));
+    }();
+    return v;
+}
 
 template <typename T, int N, int ORDER, int BCF, int OUTMODE, bool FAST>
-int launch_one(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
+int launch_tiled(const EvalParams<N>& p_in, cudaStream_t s) {
     constexpr int L = ORDER + 1;
-    auto kern = eval_kernel<T, N, ORDER, BCF, OUTMODE, FAST>;
+    auto kern = eval_brick_kernel<T, N, ORDER, BCF, OUTMODE, FAST>;
     EvalParams<N> p = p_in;
-    static int blocks_plain = 0;  // benign race: every thread computes the same value
-    if (blocks_plain == 0) {
-        int b = 0;
-        GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, EVAL_BLOCK, 0));
-        blocks_plain = b > 0 ? b : 1;
-    }
-    const size_t grid_bytes = (size_t)p.total * sizeof(T);
-    bool tiled = (flags & GB_TILED) != 0;
-    if (!(flags & (GB_TILED | GB_PLAIN))) tiled = N >= 2 && ORDER >= GB_LINEAR && p.nq >= (1ll << 20) && grid_bytes >= (48u << 20);
-    if (p.nq >= 0xfffffff0ll) tiled = false;
-    if (tiled) tiled = choose_tile(N, L, sizeof(T), p.len, (flags & GB_TILED) ? (i64)1 << 40 : p.nq, p.tile, p.ntile);
-    p.tiled = 0;
-    if (!tiled) {
-        for (int d = 0; d < N; d++) { p.tile[d] = 1; p.ntile[d] = 1; }
-        const i64 need = (p.nq + EVAL_BLOCK - 1) / EVAL_BLOCK;
-        const i64 cap = (i64)num_sms() * blocks_plain * 4;  // a few waves, then CTAs stride over the items
-        const int grid = (int)(need < cap ? (need > 0 ? need : 1) : cap);
-        kern<<<grid, EVAL_BLOCK, 0, s>>>(p);
-        count_launch();
-        GB_CUDA(cudaGetLastError());
-        return GB_OK;
-    }
-    // ---- tiled path: bin the queries by tile, then evaluate tile by tile out of shared memory ----
     u32 nbins = 1;
     size_t vol = 1;
     for (int d = 0; d < N; d++) { nbins *= (u32)p.ntile[d]; vol *= (size_t)(p.tile[d] + L - 1); }
     nbins += 1;  // + the bin of invalid queries
-    const size_t smem = vol * sizeof(T);
+    const size_t smem = 2 * ((vol + 3) & ~(size_t)3) * sizeof(T);
     const u32 nctas = (u32)std::max<i64>(1, std::min<i64>((i64)num_sms() * 2, (p.nq + 4095) / 4096));
     const i64 per_cta = (p.nq + nctas - 1) / nctas;
     const size_t max_items = (size_t)nbins + (size_t)(p.nq / EVAL_CHUNK) + 2;
-    const i64 pitch = (p.nq + 15) & ~(i64)15;
-    // one scratch allocation: keys | perm | bh | boff | hist | offs | nwork | work
+    const size_t pitch = ((size_t)p.nq + 15) & ~(size_t)15;
+    // one scratch allocation: records | sorted outputs | inv | keys | bh | boff | hist | offs | nwork | work
+    constexpr int W = out_words<N>(OUTMODE);
     const size_t nbc = (size_t)nbins * nctas;
-    const size_t words = 2 * (size_t)pitch + 2 * nbc + 2 * (size_t)(nbins + 4) + 4 + 3 * max_items;
-    u32* scratch = nullptr;
-    GB_CUDA(cudaMallocAsync((void**)&scratch, words * sizeof(u32), s));
-    u32* keys = scratch;
-    u32* perm = keys + pitch;
-    u32* bh = perm + pitch;
+    const size_t rec_bytes = (pitch * (N + 1) * sizeof(T) + 31) & ~(size_t)31;
+    const size_t out_bytes = (pitch * W * sizeof(T) + 31) & ~(size_t)31;
+    const size_t words = (pitch + 16) + 2 * nbc + 2 * (size_t)(nbins + 4) + 4 + 3 * max_items;
+    unsigned char* scratch = nullptr;
+    GB_CUDA(cudaMallocAsync((void**)&scratch, rec_bytes + out_bytes + (pitch + words) * sizeof(u32), s));
+    T* rec = reinterpret_cast<T*>(scratch);
+    T* osorted = reinterpret_cast<T*>(scratch + rec_bytes);
+    u32* inv = reinterpret_cast<u32*>(scratch + rec_bytes + out_bytes);
+    u32* keys = inv + pitch;
+    u32* bh = keys + pitch + 16;
     u32* boff = bh + nbc;
     u32* hist = boff + nbc;
     u32* offs = hist + (nbins + 4);
     u32* nwork = offs + (nbins + 4);
     u32* work = nwork + 4;
     const size_t hsmem = (size_t)nbins * sizeof(u32);
-    tile_hist_kernel<T, N, ORDER, BCF><<<nctas, 256, hsmem, s>>>(p, keys, bh, nbins, per_cta);
+    tile_hist_kernel<T, N, ORDER, BCF><<<nctas, SORT_BLOCK, hsmem, s>>>(p, keys, bh, nbins, per_cta);
     count_launch();
     int rc = tile_offsets(bh, nbins, nctas, hist, offs, boff, work, nwork, EVAL_CHUNK, s);
     if (rc) { cudaFreeAsync(scratch, s); return rc; }
-    tile_scatter_kernel<<<nctas, 256, hsmem, s>>>(keys, p.nq, boff, perm, nbins, per_cta);
+    tile_scatter_kernel<T, N><<<nctas, SORT_BLOCK, hsmem, s>>>(p, keys, boff, rec, inv, nbins, per_cta);
     count_launch();
     GB_CUDA(cudaGetLastError());
     static size_t smem_set = 0;
@@ -904,17 +1305,73 @@ int launch_one(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
         smem_set = smem;
     }
     int bt = 0;
-    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt, kern, EVAL_BLOCK, smem));
+    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt, kern, BRICK_BLOCK, smem));
     if (bt < 1) { cudaFreeAsync(scratch, s); return fail(GB_ERR_CUDA, "tiled evaluation: brick does not fit in shared memory"); }
     p.tiled = 1;
-    p.perm = perm;
+    p.perm = nullptr;
     p.work = work;
     p.nwork = nwork;
     const i64 grid = std::min<i64>((i64)max_items, (i64)num_sms() * bt);
-    kern<<<(int)grid, EVAL_BLOCK, smem, s>>>(p);
-    count_launch();
+    // the keys are dead after the scatter: their buffer becomes the deferred-slot list (count first)
+    u32* defer = keys;
+    GB_CUDA(cudaMemsetAsync(defer, 0, sizeof(u32), s));
+    p.aos = W;  // both kernels write one output record per sorted slot ...
+    p.val = osorted;
+    p.grad = nullptr;
+    p.hess = nullptr;
+    kern<<<(int)grid, BRICK_BLOCK, smem, s>>>(p, rec, defer);
+    eval_deferred_kernel<T, N, ORDER, BCF, OUTMODE, FAST><<<num_sms() * 2, EVAL_BLOCK, 0, s>>>(p, rec, defer);
+    // ... and the records go back to the caller's order and arrays
+    const int ugrid = (int)std::min<i64>((p.nq + 255) / 256, (i64)num_sms() * 32);
+    unpermute_kernel<T, N, OUTMODE><<<ugrid, 256, 0, s>>>(osorted, inv, (T*)p_in.val, (T*)p_in.grad, (T*)p_in.hess, p.nq);
+    count_launch(3);
     GB_CUDA(cudaGetLastError());
     GB_CUDA(cudaFreeAsync(scratch, s));
+    return GB_OK;
+}
+
+template <typename T, int N, int ORDER, int BCF, int OUTMODE, bool FAST>
+int launch_one(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
+    constexpr int L = ORDER + 1;
+    auto kern = eval_kernel<T, N, ORDER, BCF, OUTMODE, FAST>;
+    EvalParams<N> p = p_in;
+    const size_t grid_bytes = (size_t)p.total * sizeof(T);
+    const bool forced = (flags & GB_TILED) != 0;
+    bool tiled = forced;
+    if (!(flags & (GB_TILED | GB_PLAIN))) tiled = N >= 2 && ORDER >= GB_LINEAR && p.nq >= (1ll << 20) && grid_bytes >= (48u << 20);
+    if (tiled) tiled = choose_tile(N, L, sizeof(T), p.len, std::min<i64>(p.nq, tiled_max_batch()), forced, p.tile, p.ntile);
+    p.tiled = 0;
+    p.aos = 0;
+    if (!tiled) {
+        static int blocks_plain = 0;  // benign race: every thread computes the same value
+        if (blocks_plain == 0) {
+            int b = 0;
+            GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, EVAL_BLOCK, 0));
+            blocks_plain = b > 0 ? b : 1;
+        }
+        for (int d = 0; d < N; d++) { p.tile[d] = 1; p.ntile[d] = 1; }
+        const i64 need = (p.nq + EVAL_BLOCK - 1) / EVAL_BLOCK;
+        const i64 cap = (i64)num_sms() * blocks_plain * 4;  // a few waves, then CTAs stride over the blocks
+        const int grid = (int)(need < cap ? (need > 0 ? need : 1) : cap);
+        kern<<<grid, EVAL_BLOCK, 0, s>>>(p);
+        count_launch();
+        GB_CUDA(cudaGetLastError());
+        return GB_OK;
+    }
+    // slices of at most tiled_max_batch() queries, one after the other on the stream
+    const i64 slice = tiled_max_batch();
+    const size_t xs = p.xdtype == GB_F64 ? 8 : 4;
+    for (i64 q0 = 0; q0 < p_in.nq; q0 += slice) {
+        EvalParams<N> sp = p;
+        sp.nq = std::min<i64>(slice, p_in.nq - q0);
+        sp.q0 = p_in.q0 + q0;
+        for (int d = 0; d < N; d++) sp.xp[d] = (const char*)p.xp[d] + (size_t)q0 * (size_t)p.xqs * xs;
+        if (p.val) sp.val = (T*)p.val + q0;
+        if (p.grad) sp.grad = (T*)p.grad + q0 * N;
+        if (p.hess) sp.hess = (T*)p.hess + q0 * N * N;
+        const int rc = launch_tiled<T, N, ORDER, BCF, OUTMODE, FAST>(sp, s);
+        if (rc) return rc;
+    }
     return GB_OK;
 }
 

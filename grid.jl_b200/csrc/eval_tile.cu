@@ -1,6 +1,5 @@
 // eval_tile.cu -- order-independent pieces of the binned ("tiled") evaluation path: the histogram
-// scan that turns per-tile counts into bin offsets and a work-item list, the scatter that writes
-// the tile-sorted query order, and the tile-shape heuristic.  See eval.cuh for the kernels that
+// scan that turns per-tile counts into bin offsets and a work-item list, and the tile-shape heuristic.  See eval.cuh for the kernels that
 // compute the keys and evaluate the bricks.
 #include <algorithm>
 #include <cstdlib>
@@ -53,21 +52,6 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const u32* __restrict__
     if (t == 1023) { nwork[0] = s_itm[1023]; nwork[1] = 0; }  // item count, and the counter CTAs pull items from
 }
 
-// Each CTA replays its slice of the batch: slot = its private cursor for the query's bin.
-__global__ void __launch_bounds__(256) tile_scatter_kernel(const u32* __restrict__ keys, i64 nq, const u32* __restrict__ boff, u32* __restrict__ perm,
-                                                           u32 nbins, i64 per_cta) {
-    extern __shared__ u32 s_cur[];
-    for (u32 b = threadIdx.x; b < nbins; b += blockDim.x) s_cur[b] = boff[(size_t)b * gridDim.x + blockIdx.x];
-    __syncthreads();
-    const i64 q0 = (i64)blockIdx.x * per_cta;
-    const i64 q1 = q0 + per_cta < nq ? q0 + per_cta : nq;
-#pragma unroll 4
-    for (i64 q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
-        const u32 slot = atomicAdd(s_cur + keys[q], 1u);
-        perm[slot] = (u32)q;
-    }
-}
-
 // hist[b] = sum over CTAs of bh[b][cta]; one warp per bin.
 __global__ void __launch_bounds__(256) bin_totals_kernel(const u32* __restrict__ bh, u32 nbins, u32 nctas, u32* __restrict__ hist) {
     const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -108,58 +92,39 @@ int tile_offsets(const u32* bh, u32 nbins, u32 nctas, u32* hist, u32* offs, u32*
     return GB_OK;
 }
 
-// Tile shape: the brick (tile + L-1 halo per dimension) must fit the shared-memory budget
-// (GB_TILE_KB, default 56 KB -> two 256-thread CTAs per SM); dimension 1 is kept longest so brick
-// rows are loaded in long coalesced runs; the number of tiles must fit the per-CTA shared-memory
-// histogram of the counting sort.  Returns false when tiling cannot pay off (too many tiles for the
-// sort, or fewer than ~128 queries per tile to amortise staging a brick) -> plain path.
-// GB_TILE="a,b,c" overrides the shape.
-bool choose_tile(int N, int L, size_t esz, const int* len, i64 nq, int* tile, int* ntile) {
+// Tile shape.  The leading extents are fixed (brick_tile); the extent along the last dimension is
+// the largest power of two whose brick (tile + L-1 halo per dimension) fits the shared-memory
+// budget per buffer (GB_TILE_KB, default 40 KB: two buffers x two 256-thread CTAs per SM) -- grown
+// further only if the number of tiles would not fit the per-CTA shared-memory histogram of the
+// counting sort.  Returns false when tiling cannot pay off (too many tiles for the sort, brick too
+// large, or fewer than ~128 queries per tile to amortise staging a brick) -> plain path.
+bool choose_tile(int N, int L, size_t esz, const int* len, i64 nq, bool forced, int* tile, int* ntile) {
     constexpr u32 MAX_BINS = 12000 - 1;
-    size_t budget = 56 * 1024;
+    size_t budget = 40 * 1024;
     if (const char* e = getenv("GB_TILE_KB")) {
         long v = atol(e);
-        if (v >= 4 && v <= 200) budget = (size_t)v * 1024;
+        if (v >= 4 && v <= 100) budget = (size_t)v * 1024;
     }
-    for (int d = 0; d < N; d++) tile[d] = d == 0 ? 32 : 16;
-    bool forced = false;
-    if (const char* e = getenv("GB_TILE")) {
-        int v[4] = {0, 0, 0, 0};
-        int n = sscanf(e, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]);
-        for (int d = 0; d < N && d < n; d++)
-            if (v[d] >= 1 && v[d] <= 4096) { tile[d] = v[d]; forced = true; }
+    size_t lead = esz;
+    unsigned long long nt = 1;
+    for (int d = 0; d < N - 1; d++) {
+        tile[d] = brick_tile(N, d);
+        ntile[d] = (len[d] + tile[d] - 1) / tile[d];
+        lead *= (size_t)(tile[d] + L - 1);
+        nt *= (unsigned long long)ntile[d];
     }
-    for (int d = 0; d < N; d++) tile[d] = std::max(1, std::min(tile[d], len[d]));
-    auto bytes = [&]() {
-        size_t v = esz;
-        for (int d = 0; d < N; d++) v *= (size_t)(tile[d] + L - 1);
-        return v;
-    };
-    auto tiles = [&]() {
-        unsigned long long v = 1;
-        for (int d = 0; d < N; d++) { ntile[d] = (len[d] + tile[d] - 1) / tile[d]; v *= (unsigned long long)ntile[d]; }
-        return v;
-    };
-    while (bytes() > budget) {
-        int best = -1;
-        for (int d = 0; d < N; d++)  // halve the largest extent; ties go to the slowest dimension
-            if (tile[d] > 1 && (best < 0 || tile[d] >= tile[best])) best = d;
-        if (best < 0) break;
-        tile[best] = (tile[best] + 1) / 2;
+    const int last = len[N - 1];
+    int t = 1;
+    while (t * 2 <= last && lead * (size_t)(t * 2 + L - 1) <= budget) t *= 2;
+    if (lead * (size_t)(t + L - 1) > 100 * 1024) return false;
+    while (nt * (unsigned long long)((last + t - 1) / t) > MAX_BINS) {
+        if (t >= last || lead * (size_t)(t * 2 + L - 1) > 100 * 1024) return false;
+        t *= 2;
     }
-    if (bytes() > 200 * 1024) return false;
-    while (!forced && tiles() > MAX_BINS) {  // grow the dimension with the most tiles while the brick still fits
-        int best = -1;
-        for (int d = 0; d < N; d++)
-            if (tile[d] < len[d] && (best < 0 || ntile[d] > ntile[best])) best = d;
-        if (best < 0) return false;
-        const int old = tile[best];
-        tile[best] = std::min(len[best], old * 2);
-        if (bytes() > budget) { tile[best] = old; return false; }
-    }
-    const unsigned long long nt = tiles();
-    if (nt > MAX_BINS) return false;
-    return nq / (i64)nt >= 128;
+    tile[N - 1] = t;
+    ntile[N - 1] = (last + t - 1) / t;
+    nt *= (unsigned long long)ntile[N - 1];
+    return forced || nq / (i64)nt >= 128;
 }
 
 }  // namespace gb

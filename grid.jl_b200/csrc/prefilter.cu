@@ -30,77 +30,174 @@ template <typename T> struct LineSys {
     T cp[4];  // column-major 2x2
 };
 
-// forward + backward substitution of one strided line held in global memory.
-// RHS: b (in place).  A_ldiv_B!(::LU{T,Tridiagonal{T}}, B), Julia Base linalg/lu.jl ("See dgtts2.f").
-template <typename T> __device__ __forceinline__ void lu_solve_inplace(T* b, i64 s, i64 n, const LineSys<T>& sys) {
-    T cur = b[0];
-    for (i64 i = 0; i < n - 1; i++) {
-        const T nxt = b[(i + 1) * s];
-        const T m = __ldg(sys.dl + i);
-        T keep, tmp;
-        if (__ldg(sys.swap + i)) { tmp = cur - m * nxt; keep = nxt; }
-        else { tmp = nxt - m * cur; keep = cur; }
-        b[i * s] = keep;
-        cur = tmp;
+// ---- line IO policies -------------------------------------------------------------------------------
+// The substitutions are sequential along a line, so a thread can only hide memory latency by having
+// the NEXT elements of its line in flight: lines are processed in chunks of U elements that are
+// loaded (and later stored) together.
+//   GlobalLine  element i of the line at b[i*s]; used for sweeps along dims >= 2, where the 32 lines
+//               of a warp are adjacent in memory and every chunk access is coalesced.
+//   TileLine    contiguous lines (sweep along dim 1): the warp's 32 lines x U elements travel through
+//               a shared-memory tile so that global accesses stay coalesced (row r = U consecutive
+//               elements of line r) while each lane consumes its own line (column access, odd pitch).
+template <typename T, int U> struct GlobalLine {
+    T* b;
+    i64 s;
+    __device__ __forceinline__ void load(T (&v)[U], i64 start, int dir, int cnt) const {
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (u < cnt) v[u] = b[(start + dir * u) * s];
     }
-    T x1 = cur / __ldg(sys.d + (n - 1));
-    b[(n - 1) * s] = x1;
-    if (n > 1) {
-        T x0 = (b[(n - 2) * s] - __ldg(sys.du + (n - 2)) * x1) / __ldg(sys.d + (n - 2));
-        b[(n - 2) * s] = x0;
-        T x2 = x1;
-        x1 = x0;
-        for (i64 i = n - 3; i >= 0; i--) {
-            const T y = b[i * s];
-            const T x = (y - __ldg(sys.du + i) * x1 - __ldg(sys.du2 + i) * x2) / __ldg(sys.d + i);
-            b[i * s] = x;
-            x2 = x1;
-            x1 = x;
+    __device__ __forceinline__ void store(const T (&v)[U], i64 start, int dir, int cnt) const {
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (u < cnt) b[(start + dir * u) * s] = v[u];
+    }
+    __device__ __forceinline__ T get(i64 i) const { return b[i * s]; }
+    __device__ __forceinline__ void put(i64 i, T v) const { b[i * s] = v; }
+};
+template <typename T, int U> struct TileLine {  // U == 32; all 32 lanes of the warp call together
+    T* base;   // line 0 of this warp
+    i64 n;     // line length (line r starts at base + r*n)
+    int nl;    // lines this warp really has (<= 32)
+    T* tile;   // shared memory [32][U+1]
+    __device__ __forceinline__ void load(T (&v)[U], i64 start, int dir, int cnt) const {
+        const int lane = threadIdx.x & 31;
+        T g[32];
+#pragma unroll
+        for (int r = 0; r < 32; r++)  // 32 independent coalesced row loads in flight
+            if (r < nl && lane < cnt) g[r] = base[r * n + start + dir * lane];
+#pragma unroll
+        for (int r = 0; r < 32; r++) tile[r * (U + 1) + lane] = g[r];
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < U; u++) v[u] = tile[lane * (U + 1) + u];
+        __syncwarp();
+    }
+    __device__ __forceinline__ void store(const T (&v)[U], i64 start, int dir, int cnt) const {
+        const int lane = threadIdx.x & 31;
+#pragma unroll
+        for (int u = 0; u < U; u++) tile[lane * (U + 1) + u] = v[u];
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 32; r++)
+            if (r < nl && lane < cnt) base[r * n + start + dir * lane] = tile[r * (U + 1) + lane];
+        __syncwarp();
+    }
+    __device__ __forceinline__ T get(i64 i) const {
+        const int lane = threadIdx.x & 31;
+        __syncwarp();
+        return lane < nl ? base[lane * n + i] : (T)0;
+    }
+    __device__ __forceinline__ void put(i64 i, T v) const {
+        const int lane = threadIdx.x & 31;
+        if (lane < nl) base[lane * n + i] = v;
+        __syncwarp();
+    }
+};
+
+// ---- the substitutions: A_ldiv_B!(::LU{T,Tridiagonal{T}}, B), Julia Base linalg/lu.jl ("See dgtts2.f").
+// forward elimination of a dense RHS held in `io` (in place)
+template <typename T, int U, typename IO> __device__ __forceinline__ T lu_forward_dense(const IO& io, i64 n, const LineSys<T>& sys) {
+    T cur = io.get(0);
+    for (i64 c0 = 0; c0 < n - 1; c0 += U) {
+        const int cnt = (int)min((i64)U, n - 1 - c0);
+        T v[U];
+        io.load(v, c0 + 1, +1, cnt);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (u < cnt) {
+                const T m = __ldg(sys.dl + c0 + u);
+                const T nxt = v[u];
+                if (__ldg(sys.swap + c0 + u)) { v[u] = nxt; const T t = cur - m * nxt; cur = t; }
+                else { v[u] = cur; const T t = nxt - m * cur; cur = t; }
+            }
         }
+        io.store(v, c0, +1, cnt);
+    }
+    return cur;  // the eliminated last element
+}
+// forward elimination of the Woodbury RHS k0*e_0 + k1*e_{n-1}; results go to `out`
+template <typename T, int U, typename IO> __device__ __forceinline__ T lu_forward_sparse(const IO& out, i64 n, const LineSys<T>& sys, T k0, T k1) {
+    T cur = k0;
+    for (i64 c0 = 0; c0 < n - 1; c0 += U) {
+        const int cnt = (int)min((i64)U, n - 1 - c0);
+        T v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (u < cnt) {
+                const T m = __ldg(sys.dl + c0 + u);
+                const T nxt = (c0 + u + 1 == n - 1) ? k1 : (T)0;
+                if (__ldg(sys.swap + c0 + u)) { v[u] = nxt; const T t = cur - m * nxt; cur = t; }
+                else { v[u] = cur; const T t = nxt - m * cur; cur = t; }
+            } else
+                v[u] = (T)0;
+        }
+        out.store(v, c0, +1, cnt);
+    }
+    return cur;
+}
+// back substitution reading the eliminated RHS from `rhs`; SUB == false: results overwrite `dst`;
+// SUB == true (Woodbury): dst[i] = dst[i] - x[i], i.e. B = tmpN1 - tmpN2 fused into the sweep.
+template <typename T, int U, bool SUB, typename IO> __device__ __forceinline__ void lu_backward(const IO& rhs, const IO& dst, i64 n, const LineSys<T>& sys, T last) {
+    T x1 = last / __ldg(sys.d + (n - 1));
+    dst.put(n - 1, SUB ? dst.get(n - 1) - x1 : x1);
+    if (n < 2) return;
+    const T x0 = (rhs.get(n - 2) - __ldg(sys.du + (n - 2)) * x1) / __ldg(sys.d + (n - 2));
+    dst.put(n - 2, SUB ? dst.get(n - 2) - x0 : x0);
+    T x2 = x1;
+    x1 = x0;
+    for (i64 c0 = n - 3; c0 >= 0; c0 -= U) {
+        const int cnt = (int)min((i64)U, c0 + 1);
+        T v[U], o[SUB ? U : 1];
+        rhs.load(v, c0, -1, cnt);
+        if constexpr (SUB) dst.load(o, c0, -1, cnt);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (u < cnt) {
+                const i64 i = c0 - u;
+                const T x = (v[u] - __ldg(sys.du + i) * x1 - __ldg(sys.du2 + i) * x2) / __ldg(sys.d + i);
+                if constexpr (SUB) v[u] = o[u] - x;
+                else v[u] = x;
+                x2 = x1;
+                x1 = x;
+            }
+        }
+        dst.store(v, c0, -1, cnt);
     }
 }
 
-// Woodbury second solve: RHS = k2[0]*e_0 + k2[1]*e_{n-1}; forward results go to t (same layout as
-// b), the backward pass is fused with B[i] = tmpN1[i] - tmpN2[i] (WoodburyMatrices A_ldiv_B!).
-template <typename T> __device__ __forceinline__ void woodbury_correct(T* b, T* t, i64 s, i64 n, const LineSys<T>& sys) {
-    const T k10 = b[(i64)sys.vcol0 * s], k11 = b[(i64)sys.vcol1 * s];  // tmpk1 = V*tmpN1
-    const T k20 = ((T)0 + sys.cp[0] * k10) + sys.cp[2] * k11;           // tmpk2 = Cp*tmpk1 (gemv column order)
-    const T k21 = ((T)0 + sys.cp[1] * k10) + sys.cp[3] * k11;
-    T cur = k20;
-    for (i64 i = 0; i < n - 1; i++) {
-        const T nxt = (i + 1 == n - 1) ? k21 : (T)0;
-        const T m = __ldg(sys.dl + i);
-        T keep, tmp;
-        if (__ldg(sys.swap + i)) { tmp = cur - m * nxt; keep = nxt; }
-        else { tmp = nxt - m * cur; keep = cur; }
-        t[i * s] = keep;
-        cur = tmp;
-    }
-    T x1 = cur / __ldg(sys.d + (n - 1));
-    b[(n - 1) * s] = b[(n - 1) * s] - x1;
-    if (n > 1) {
-        T x0 = (t[(n - 2) * s] - __ldg(sys.du + (n - 2)) * x1) / __ldg(sys.d + (n - 2));
-        b[(n - 2) * s] = b[(n - 2) * s] - x0;
-        T x2 = x1;
-        x1 = x0;
-        for (i64 i = n - 3; i >= 0; i--) {
-            const T y = t[i * s];
-            const T x = (y - __ldg(sys.du + i) * x1 - __ldg(sys.du2 + i) * x2) / __ldg(sys.d + i);
-            b[i * s] = b[i * s] - x;
-            x2 = x1;
-            x1 = x;
-        }
+template <typename T, int U, typename IO> __device__ __forceinline__ void solve_line(const IO& b, const IO& t, i64 n, const LineSys<T>& sys) {
+    const T last = lu_forward_dense<T, U>(b, n, sys);
+    lu_backward<T, U, false>(b, b, n, sys, last);
+    if (sys.woodbury) {                                            // WoodburyMatrices A_ldiv_B!
+        const T k10 = b.get(sys.vcol0), k11 = b.get(sys.vcol1);    // tmpk1 = V*tmpN1
+        const T k20 = ((T)0 + sys.cp[0] * k10) + sys.cp[2] * k11;  // tmpk2 = Cp*tmpk1 (gemv column order)
+        const T k21 = ((T)0 + sys.cp[1] * k10) + sys.cp[3] * k11;
+        const T last2 = lu_forward_sparse<T, U>(t, n, sys, k20, k21);  // A_ldiv_B!(W.A, tmpN2 = U*tmpk2)
+        lu_backward<T, U, true>(t, b, n, sys, last2);                  // B = tmpN1 - tmpN2
     }
 }
 
-// one thread per line; the line lives in global memory (L1/L2 resident while it is being swept).
+// sweeps along dims >= 2: one thread per line, 32 adjacent lines per warp -> coalesced chunk IO
+constexpr int PF_U = 8;
 template <typename T> __global__ void __launch_bounds__(128) line_solve_global(T* A, T* tmp, i64 n, i64 s, i64 inner, i64 nlines, const LineSys<T> sys) {
     const i64 l = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nlines) return;
     const i64 lo = l % inner, hi = l / inner;
     const i64 base = lo + hi * inner * n;
-    lu_solve_inplace<T>(A + base, s, n, sys);
-    if (sys.woodbury) woodbury_correct<T>(A + base, tmp + base, s, n, sys);
+    const GlobalLine<T, PF_U> b{A + base, s}, t{tmp ? tmp + base : nullptr, s};
+    solve_line<T, PF_U>(b, t, n, sys);
+}
+// sweep along dim 1 (contiguous lines): one warp per 32 lines, shared-memory transposing tile
+constexpr int PF_TU = 32, PF_WARPS = 4;
+template <typename T> __global__ void __launch_bounds__(32 * PF_WARPS) line_solve_tile(T* A, T* tmp, i64 n, i64 nlines, const LineSys<T> sys) {
+    __shared__ T tiles[PF_WARPS][32 * (PF_TU + 1)];
+    const int warp = threadIdx.x >> 5;
+    const i64 first = ((i64)blockIdx.x * PF_WARPS + warp) * 32;
+    if (first >= nlines) return;
+    const int nl = (int)min((i64)32, nlines - first);
+    const TileLine<T, PF_TU> b{A + first * n, n, nl, tiles[warp]}, t{tmp ? tmp + first * n : nullptr, n, nl, tiles[warp]};
+    solve_line<T, PF_TU>(b, t, n, sys);
 }
 
 // ---- host: factorisation (dgttrf order) + Woodbury capacitance ---------------------------------
@@ -248,8 +345,13 @@ template <typename T> int invert_impl(T* A, int ndim, const i64* dims, int bc, i
         for (int i = 0; i < 4; i++) sys.cp[i] = hs.cp[i];
 
         if (hs.woodbury && !tmp) GB_CUDA(cudaMallocAsync((void**)&tmp, (size_t)total * sizeof(T), s));
-        const i64 grid = (nlines + 127) / 128;
-        line_solve_global<T><<<(unsigned)grid, 128, 0, s>>>(A, tmp, n, str, str, nlines, sys);
+        if (str == 1 && nlines >= 32) {
+            const i64 grid = (nlines + 32 * PF_WARPS - 1) / (32 * PF_WARPS);
+            line_solve_tile<T><<<(unsigned)grid, 32 * PF_WARPS, 0, s>>>(A, tmp, n, nlines, sys);
+        } else {
+            const i64 grid = (nlines + 127) / 128;
+            line_solve_global<T><<<(unsigned)grid, 128, 0, s>>>(A, tmp, n, str, str, nlines, sys);
+        }
         count_launch();
         GB_CUDA(cudaGetLastError());
         GB_CUDA(cudaFreeAsync(dblob, s));
