@@ -9,8 +9,14 @@ A "step" is one pass of valgrad over one batch of 1e7 queries.
   value  device-resident: queries / outputs already in HBM; CUDA-event timed on the launch stream.
   e2e    the same step through the C-ABI with HOST buffers (pinned): H2D of the queries and D2H of
          value+gradient inside the timed region (gb_eval, mem=GB_HOST).
-  roofline  the step is ONE kernel launch (eval_kernel<double,3,Cubic,nil,valgrad>); algorithmic
-         bytes = 56 B/query (24 in + 32 out) -> achieved GB/s vs the measured HBM peak.
+  roofline  the dominant kernel of the step is eval_brick_kernel<double,3,Cubic,nil,valgrad,...>; its
+         average duration is measured live with CUDA events on the launch stream (gb_profile_*),
+         algorithmic bytes = 56 B/query (24 in + 32 out) x 1e7 queries per launch ->
+         achieved GB/s vs the measured HBM peak.  roofline.step_* gives the same figure for the whole
+         step (binning sort + brick evaluation + un-permute), which is what `value` measures.
+  contraction  the headline runs the library default, EXACT (the reference's arithmetic order,
+         bit-identical to the oracle); extra.fast repeats the step with GB_FAST (separable FMA,
+         within north_star's 4 ulp of the magnitude scale -- tests/test_gpu_parity.py).
   cpu_baseline  the C++ restatement of the reference algorithm (oracle, "port") on the host cores,
          bounded sample.
 Multi-GPU (torchrun, one process per GPU): the grid is prefiltered on rank 0 and the coefficient
@@ -230,6 +236,38 @@ def main():
     ms_per_step = total_ms_max / args.steps
     value = world * NQ / (ms_per_step * 1e-3) / 1e9
 
+    # ---- stage timing of the step (CUDA events on the launch stream, recorded inside the library) ----------
+    def stage_profile(fast, reps=5):
+        gb.profile_enable(True)
+        acc = {}
+        for _ in range(reps):
+            gb.valgrad_(val, grad, G, X, fast=fast)
+            for k, v in gb.profile_read().items():
+                acc[k] = acc.get(k, 0.0) + v / reps
+        gb.profile_enable(False)
+        return acc
+
+    stages = stage_profile(args.fast)
+    # the other contraction, for the record (same step, same timing method, fewer steps)
+    other = None
+    if rank == 0 and world == 1:
+        of = not args.fast
+        for _ in range(3):
+            gb.valgrad_(val, grad, G, X, fast=of)
+        torch.cuda.synchronize()
+        oe = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        osteps = max(3, min(args.steps, 10))
+        oe[0].record()
+        for _ in range(osteps):
+            gb.valgrad_(val, grad, G, X, fast=of)
+        oe[1].record()
+        torch.cuda.synchronize()
+        oms = oe[0].elapsed_time(oe[1]) / osteps
+        other = {"contraction": "FAST" if of else "EXACT", "value": NQ / (oms * 1e-3) / 1e9, "unit": "Gpoints/s", "ms_per_step": oms,
+                 "stages_ms": stage_profile(of)}
+        gb.valgrad_(val, grad, G, X, fast=args.fast)  # leave the headline mode's results in val / grad
+        torch.cuda.synchronize()
+
     # ---- end to end through the host-buffer C-ABI call ----------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -260,19 +298,24 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant (only) kernel of the step ---------------------------------------------
+    # ---- roofline of the dominant kernel of the step ------------------------------------------------------
     peak, how = measured_peak()
-    kernel_ms = total_ms / args.steps  # one launch per step: event time over the region / launches
+    step_ms = total_ms / args.steps
+    kernel_ms = stages.get("eval_brick", step_ms)
     achieved = BYTES_PER_QUERY * NQ / (kernel_ms * 1e-3) / 1e9
+    step_achieved = BYTES_PER_QUERY * NQ / (step_ms * 1e-3) / 1e9
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("eval_c2_bytes_per_launch")
+            traffic = json.load(f).get("eval_brick_fast_bytes_per_launch" if args.fast else "eval_brick_exact_bytes_per_launch")
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": how, "kernel": "eval_kernel<double,3,Cubic,BCF_NIL,valgrad,%s>" % ("FAST" if args.fast else "EXACT"),
-                "algorithmic_bytes_per_launch": BYTES_PER_QUERY * NQ, "kernel_ms": kernel_ms, "frac_of_nominal_8TBs": achieved / 8000.0}
+                "peak_source": how, "kernel": "eval_brick_kernel<double,3,Cubic,BCF_NIL,valgrad,%s>" % ("FAST" if args.fast else "EXACT"),
+                "algorithmic_bytes_per_launch": BYTES_PER_QUERY * NQ, "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / step_ms,
+                "stages_ms": stages, "step_achieved": step_achieved, "step_frac": step_achieved / peak,
+                "frac_of_nominal_8TBs": achieved / 8000.0,
+                "limiter": "FP64 pipe (816 dependent mul/add per query in the reference's order)" if not args.fast else "shared-memory gathers + FP64 pipe"}
 
     # ---- CPU baseline (oracle port) on a bounded sample ---------------------------------------------------
     cpu = None
@@ -306,7 +349,9 @@ def main():
                    "parallelism": f"query-sharded x{world}, coefficients replicated by NCCL broadcast"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(),
         "extra": {"prefilter_ms": pref_ms, "prefilter_note": "InterpGrid(A,BCnan,InterpCubic) on device: pad + 3 prefilter sweeps of 258^3 f64",
-                  "step_ms_min": per[0], "step_ms_median": per[len(per) // 2], "step_ms_max": per[-1]},
+                  "step_ms_min": per[0], "step_ms_median": per[len(per) // 2], "step_ms_max": per[-1],
+                  "other_contraction": other,
+                  "with_prefilter_ms_per_step": (ms_per_step + pref_ms) if pref_ms else None},
     }
     print(json.dumps(line), flush=True)
     if world > 1:

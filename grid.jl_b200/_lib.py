@@ -29,6 +29,8 @@ SIGNATURES = {
     "gb_device_count": (i32, [p_i32]),
     "gb_set_device": (i32, [i32]),
     "gb_launch_count": (i64, []),
+    "gb_profile_enable": (i32, [i32]),
+    "gb_profile_read": (i32, [C.POINTER(C.c_double), i32, p_i32]),
     "gb_grid_create": (i32, [p_vp, i32, i32, p_i64, vp, i32, i32, i32, f64, vp]),
     "gb_grid_create_from_coefs": (i32, [p_vp, i32, i32, p_i64, vp, i32, i32, i32, f64, vp]),
     "gb_grid_info": (i32, [vp, p_i32, p_i32, p_i64, p_i64, p_i32, p_i32, p_f64]),

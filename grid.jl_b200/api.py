@@ -859,6 +859,22 @@ def launch_count():
     return int(L.lib().gb_launch_count())
 
 
+PROFILE_STAGES = ("tile_hist", "tile_offsets", "tile_scatter", "eval_brick", "eval_deferred", "unpermute")
+
+
+def profile_enable(on=True):
+    """Record CUDA events around the stages of every tiled evaluation (gb_profile_enable)."""
+    L.check(L.lib().gb_profile_enable(1 if on else 0))
+
+
+def profile_read():
+    """Stage durations (ms) of the last tiled evaluation as {stage: ms}, {} if none ran."""
+    ms = (C.c_double * 8)()
+    n = C.c_int(0)
+    L.check(L.lib().gb_profile_read(ms, 8, C.byref(n)))
+    return {PROFILE_STAGES[i]: float(ms[i]) for i in range(n.value)}
+
+
 def synth_uniform(out, seed, lo=0.0, hi=1.0, first=0):
     """Fill a CUDA tensor with the replayable synthetic stream."""
     torch = _torch()

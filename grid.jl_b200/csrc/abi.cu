@@ -90,6 +90,11 @@ extern "C" {
 int gb_version(void) { return GB_VERSION; }
 const char* gb_last_error(void) { return t_error.c_str(); }
 int64_t gb_launch_count(void) { return g_launches.load(); }
+int gb_profile_enable(int on) { return gb::prof_enable(on); }
+int gb_profile_read(double* ms, int n, int* nstages) {
+    if (!ms || n < 0) return fail(GB_ERR_ARG, "ms is NULL");
+    return gb::prof_read(ms, n, nstages);
+}
 
 int gb_device_count(int* n) {
     if (!n) return fail(GB_ERR_ARG, "n is NULL");

@@ -44,6 +44,9 @@ int cuda_fail(cudaError_t e, const char* what);
 extern std::atomic<long long> g_launches;
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int num_sms();
+void prof_mark(int stage_boundary, cudaStream_t s);
+int prof_enable(int on);
+int prof_read(double* ms, int n, int* nstages);  // eval_tile.cu: records boundary event i (0..6) when profiling is on
 
 template <typename T> struct dtype_of;
 template <> struct dtype_of<float> { static constexpr int value = GB_F32; };

@@ -1292,10 +1292,13 @@ int launch_tiled(const EvalParams<N>& p_in, cudaStream_t s) {
     u32* nwork = offs + (nbins + 4);
     u32* work = nwork + 4;
     const size_t hsmem = (size_t)nbins * sizeof(u32);
+    prof_mark(0, s);
     tile_hist_kernel<T, N, ORDER, BCF><<<nctas, SORT_BLOCK, hsmem, s>>>(p, keys, bh, nbins, per_cta);
     count_launch();
+    prof_mark(1, s);
     int rc = tile_offsets(bh, nbins, nctas, hist, offs, boff, work, nwork, EVAL_CHUNK, s);
     if (rc) { cudaFreeAsync(scratch, s); return rc; }
+    prof_mark(2, s);
     tile_scatter_kernel<T, N><<<nctas, SORT_BLOCK, hsmem, s>>>(p, keys, boff, rec, inv, nbins, per_cta);
     count_launch();
     GB_CUDA(cudaGetLastError());
@@ -1319,11 +1322,15 @@ int launch_tiled(const EvalParams<N>& p_in, cudaStream_t s) {
     p.val = osorted;
     p.grad = nullptr;
     p.hess = nullptr;
+    prof_mark(3, s);
     kern<<<(int)grid, BRICK_BLOCK, smem, s>>>(p, rec, defer);
+    prof_mark(4, s);
     eval_deferred_kernel<T, N, ORDER, BCF, OUTMODE, FAST><<<num_sms() * 2, EVAL_BLOCK, 0, s>>>(p, rec, defer);
+    prof_mark(5, s);
     // ... and the records go back to the caller's order and arrays
     const int ugrid = (int)std::min<i64>((p.nq + 255) / 256, (i64)num_sms() * 32);
     unpermute_kernel<T, N, OUTMODE><<<ugrid, 256, 0, s>>>(osorted, inv, (T*)p_in.val, (T*)p_in.grad, (T*)p_in.hess, p.nq);
+    prof_mark(6, s);
     count_launch(3);
     GB_CUDA(cudaGetLastError());
     GB_CUDA(cudaFreeAsync(scratch, s));

@@ -4,10 +4,50 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "common.cuh"
 
 namespace gb {
+
+// ---- stage profiler (gb_profile_enable / gb_profile_read) ---------------------------------------------
+namespace {
+constexpr int PROF_NB = 7;  // boundaries around 6 stages
+std::atomic<int> g_prof_on{0};
+std::mutex g_prof_mu;
+cudaEvent_t g_prof_ev[PROF_NB];
+bool g_prof_init = false, g_prof_have = false;
+}  // namespace
+void prof_mark(int i, cudaStream_t s) {
+    if (!g_prof_on.load(std::memory_order_relaxed) || i < 0 || i >= PROF_NB) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_prof_init) {
+        for (int k = 0; k < PROF_NB; k++)
+            if (cudaEventCreate(&g_prof_ev[k]) != cudaSuccess) return;
+        g_prof_init = true;
+    }
+    cudaEventRecord(g_prof_ev[i], s);
+    if (i == PROF_NB - 1) g_prof_have = true;
+}
+int prof_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on.store(on ? 1 : 0);
+    g_prof_have = false;
+    return GB_OK;
+}
+int prof_read(double* ms, int n, int* nstages) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (nstages) *nstages = 0;
+    if (!g_prof_have) return GB_OK;
+    GB_CUDA(cudaEventSynchronize(g_prof_ev[PROF_NB - 1]));
+    for (int k = 0; k + 1 < PROF_NB && k < n; k++) {
+        float t = 0.f;
+        GB_CUDA(cudaEventElapsedTime(&t, g_prof_ev[k], g_prof_ev[k + 1]));
+        ms[k] = (double)t;
+    }
+    if (nstages) *nstages = PROF_NB - 1;
+    return GB_OK;
+}
 
 // One CTA of 1024 threads.  Each thread owns a contiguous slice of bins; block-wide exclusive scans
 // of (queries per slice) and (work items per slice) give every thread its starting offsets.

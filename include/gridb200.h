@@ -71,6 +71,14 @@ int gb_device_count(int* n);
 int gb_set_device(int device); /* device used by subsequent calls from the calling thread */
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t gb_launch_count(void);
+/* Stage timing of the tiled evaluation (measurement aid for bench.py's roofline line; no reference
+   counterpart).  gb_profile_enable(1) makes every tiled gb_eval* call record CUDA events on its
+   launch stream around its stages; gb_profile_read waits for the last such call and returns the
+   stage durations in milliseconds: ms[0] tile_hist, [1] tile_offsets (3 small kernels),
+   [2] tile_scatter, [3] eval_brick, [4] eval_deferred, [5] unpermute.  n = capacity of ms;
+   *nstages = 6, or 0 when no tiled call ran since profiling was enabled. */
+int gb_profile_enable(int on);
+int gb_profile_read(double* ms, int n, int* nstages);
 
 /* ---- grid lifetime ------------------------------------------------------------------------ */
 /* InterpGrid(A, BC, IT) / InterpGrid(A, fill::Number, IT)  (src/interp.jl:48-72): copies the

@@ -561,6 +561,91 @@ int eval_impl(const T* coefs, int N, const i64* sdims, int bc, int order, i64 nq
 }
 
 // ---------------------------------------------------------------------------------------------
+// Extended-precision evaluator ("truth" for ulp accounting; OURS, not in the reference).  Same taps
+// as the reference (set_position: coord1d / dx in double), but the B-spline weights
+// (src/interp.jl:785-847, exact formulas) and the sum over the l^N taps are carried in long double
+// (x87 80-bit: 64-bit significand).  Also returns, per output, the magnitude scale
+// S = sum_i |c_i * a_i| that makes "k ulp" meaningful for a cancelling sum.
+inline void truth_weights(int order, long double dx, long double* w, long double* g) {
+    switch (order) {
+    case IT_NEAREST: w[0] = 1; g[0] = 0; break;
+    case IT_LINEAR: w[0] = 1 - dx; w[1] = dx; g[0] = -1; g[1] = 1; break;
+    case IT_QUADRATIC:
+        w[0] = (dx - 0.5L) * (dx - 0.5L) / 2; w[1] = 0.75L - dx * dx; w[2] = (dx + 0.5L) * (dx + 0.5L) / 2;
+        g[0] = dx - 0.5L; g[1] = -2 * dx; g[2] = dx + 0.5L;
+        break;
+    case IT_CUBIC: {
+        const long double t = 1 - dx, two3 = 2.0L / 3.0L;
+        w[0] = t * t * t / 6; w[1] = two3 - dx * dx * (2 - dx) / 2; w[2] = two3 - (dx - 1) * (dx - 1) * (1 + dx) / 2; w[3] = dx * dx * dx / 6;
+        g[0] = -(t * t) / 2; g[1] = 3 * dx * dx / 2 - 2 * dx; g[2] = 0.5L + dx * (1 - 1.5L * dx); g[3] = dx * dx / 2;
+        break;
+    }
+    }
+}
+// out: val[nq], grad[nq*N] (rounded to double), sval[nq], sgrad[nq*N] (scales).  No affine map.
+int truth_impl(const double* coefs, int N, const i64* sdims, int bc, int order, i64 nq, const double* x, double* val, double* grad,
+               double* sval, double* sgrad, int nthreads) {
+    std::vector<i64> strides(N);
+    strides[0] = 1;
+    for (int d = 1; d < N; d++) strides[d] = strides[d - 1] * sdims[d - 1];
+    const bool shift = needs_shift(bc, order);
+    const int L = npoints(order);
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+    nthreads = 1;
+#endif
+#pragma omp parallel num_threads(nthreads)
+    {
+        IC<double> ic;
+        ic.init(order, N, sdims, strides.data());
+        std::vector<double> xt(N);
+        std::vector<long double> w(4 * N), g(4 * N);
+        std::vector<int> c(N);
+#pragma omp for schedule(static)
+        for (i64 q = 0; q < nq; q++) {
+            for (int d = 0; d < N; d++) xt[d] = lookup_coord<double, double>(x[q * N + d], nullptr, shift);
+            const bool ok = ic.set_position(bc, true, false, xt.data());
+            if (!ok || !ic.valid) {
+                val[q] = sval[q] = std::numeric_limits<double>::quiet_NaN();
+                for (int d = 0; d < N; d++) grad[q * N + d] = sgrad[q * N + d] = std::numeric_limits<double>::quiet_NaN();
+                continue;
+            }
+            // dx per dimension as the reference computes it (one double subtraction, exact by Sterbenz
+            // in the interior); recovered from the value weights' argument: recompute through coords_1d
+            for (int d = 0; d < N; d++) {
+                double dx = 0; bool tw = false; i64 tmp[4];
+                coords_1d<double>(bc, order, xt[d], sdims[d], tmp, dx, tw);
+                truth_weights(order, (long double)dx, &w[4 * d], &g[4 * d]);
+            }
+            const std::vector<i64>& off = ic.wrap ? ic.index : ic.offset;
+            const i64 base = ic.wrap ? 0 : 1 + ic.offset_base;
+            for (int pass = 0; pass <= N; pass++) {
+                long double acc = 0, sc = 0;
+                std::fill(c.begin(), c.end(), 0);
+                for (size_t i = 0; i < ic.coef.size(); i++) {
+                    long double cf = 1;
+                    for (int d = 0; d < N; d++) cf *= (pass == d + 1) ? g[4 * d + c[d]] : w[4 * d + c[d]];
+                    const i64 j = off[i] + base;  // 1-based
+                    if (cf != 0 && j >= 1 && j <= ic.total) {
+                        const long double t = cf * (long double)coefs[j - 1];
+                        acc += t;
+                        sc += fabsl(t);
+                    }
+                    for (int d = 0; d < N; d++) {
+                        if (++c[d] < L) break;
+                        c[d] = 0;
+                    }
+                }
+                if (pass == 0) { val[q] = (double)acc; sval[q] = (double)sc; }
+                else { grad[q * N + pass - 1] = (double)acc; sgrad[q * N + pass - 1] = (double)sc; }
+            }
+        }
+    }
+    return ERR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Prefilter.  Julia Base linalg/lu.jl lufact!(::Tridiagonal) ("See dgttrf.f") and
 // A_ldiv_B!(::LU{T,Tridiagonal{T}}, B) ("See dgtts2.f"), called from src/interp.jl:926,946,961,
 // 975,979,993,1004; WoodburyMatrices.jl Woodbury(A,U,C,V) / A_ldiv_B! from :969,987,1013.
@@ -919,6 +1004,12 @@ int oracle_lowlevel_f64(const double* A, int order, int N, const int64_t* dims, 
             }
     }
     return ERR_OK;
+}
+
+int oracle_eval_truth_f64(const double* coefs, int N, const int64_t* sdims, int bc, int order, int64_t nq, const double* x, double* val,
+                          double* grad, double* sval, double* sgrad, int nthreads) {
+    if (order == IT_CUBIC && !nilfam(bc)) return ERR_UNSUPPORTED;
+    return truth_impl(coefs, N, sdims, bc, order, nq, x, val, grad, sval, sgrad, nthreads);
 }
 
 // dtype: 0 f32, 1 f64 ; xdtype likewise.

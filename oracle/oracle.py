@@ -160,6 +160,23 @@ def evaluate(coefs, bc, order, X, out_mask=OUT_VAL, affine=None, nthreads=0, rai
     return val, grad, hess, bad.value
 
 
+def evaluate_truth(coefs, bc, order, X, nthreads=0):
+    """Extended-precision (x87 long double) value and gradient at the reference's taps, plus the
+    magnitude scales S = sum|c_i a_i| per output: (val, grad, sval, sgrad).  float64 grids, no affine
+    map.  OURS (ulp accounting for the GB_FAST contraction), not part of the reference."""
+    coefs = _f(np.asarray(coefs, dtype=np.float64))
+    N = coefs.ndim
+    X = np.ascontiguousarray(np.asarray(X, dtype=np.float64).reshape(-1, N))
+    nq = X.shape[0]
+    val, sval = np.empty(nq), np.empty(nq)
+    grad, sgrad = np.empty((nq, N)), np.empty((nq, N))
+    rc = lib().oracle_eval_truth_f64(_p(coefs), N, _i64(coefs.shape), BC[bc], ORDER[order], C.c_int64(nq), _p(X), _p(val), _p(grad),
+                                     _p(sval), _p(sgrad), nthreads)
+    if rc:
+        raise OracleError(rc)
+    return val, grad, sval, sgrad
+
+
 def restrict(A, dim, scale=1.0, nthreads=0):
     """restrict(A, dim, scale) with 0-based dim."""
     A = _f(A)

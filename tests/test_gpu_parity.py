@@ -267,28 +267,42 @@ def test_restrict_prolong_chain_roundtrip(gb, oracle):
     assert same(up, oracle.prolong_sizes(down, up_sizes))
 
 
-@pytest.mark.parametrize("dtype,tol", [(np.float64, 16 * 2.2e-16), (np.float32, 1e-5)])
+EPS64 = 2.220446049250313e-16
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("bc,order,shape", [("nan", "cubic", (20, 21, 22)), ("reflect", "quadratic", (50, 60)),
                                             ("periodic", "linear", (8, 9, 7, 8)), ("fill", "quadratic", (12, 11, 10)),
                                             ("nearest", "nearest", (9, 9)), ("nan", "cubic", (30,)), ("nan", "cubic", (7, 8, 6, 7))])
-def test_fast_mode_tolerance(gb, oracle, dtype, tol, bc, order, shape):
-    """GB_FAST (separable FMA contraction): same taps/weights, different rounding.  Tolerance:
-    |fast - exact| <= tol * sum_i |w_i a_i|  (scale bounded here by max|coef| * sum|w|)."""
+def test_fast_mode_tolerance(gb, oracle, dtype, bc, order, shape):
+    """GB_FAST (separable FMA contraction): same taps, weights to 1 ulp, different rounding order.
+    north_star's tolerance -- 4 ulp (Float64) / 1e-5 relative (Float32) -- is taken relative to the
+    magnitude scale S = sum_i |c_i a_i| of each output (a cancelling sum has no other meaningful
+    ulp), S from the oracle's extended-precision evaluator.  FAST is held to it against the
+    long-double truth, and to twice it against the reference arithmetic (EXACT, bit-identical to
+    the oracle), which itself sits up to ~4.6 ulp(S) from the truth."""
     rng = np.random.default_rng(9)
     A = rng.random(shape).astype(dtype)
     g, co = build(gb, oracle, A, bc, order)
     X = make_queries(rng, shape, 2000, dtype, wide=(bc not in ("nan", "nil")))
-    mask = V | G | (H if order in ("quadratic", "cubic") else 0)
-    e = g._eval(X, mask)
-    f = g._eval(X, mask, fast=True)
-    cmax = np.max(np.abs(co))
-    scales = [1.0, 4.0, 16.0]  # sum|w| <= 1, sum|g| <= ~2^N, sum|h| <= ~4^N per dimension product
-    for a, b, s in zip(e, f, scales):
-        if a is None:
-            continue
+    e = g._eval(X, V | G)
+    f = g._eval(X, V | G, fast=True)
+    tv, tg, sv, sg = oracle.evaluate_truth(co.astype(np.float64), bc, order, X.astype(np.float64))
+    tol = 4 * EPS64 if dtype == np.float64 else 1e-5
+    for a, b, t, s in ((e[0], f[0], tv, sv), (e[1], f[1], tg, sg)):
         assert np.array_equal(np.isnan(a), np.isnan(b))
-        ok = ~np.isnan(a)
-        assert np.max(np.abs(a[ok] - b[ok]), initial=0.0) <= tol * cmax * s * (2 ** len(shape))
+        ok = ~np.isnan(a) & ~np.isnan(s)
+        # FAST vs the reference arithmetic: 2 x tol, because the reference's own rounding noise reaches
+        # 4.6 ulp(S) on large batches (profiles/README.md) while FAST stays within 2.7 ulp(S) of the truth
+        assert np.all(np.abs(a[ok].astype(np.float64) - b[ok]) <= 2 * tol * s[ok])
+        if dtype == np.float64:  # (a Float32 grid rounds the coordinates differently from the double truth)
+            assert np.array_equal(np.isnan(a), np.isnan(t))
+            assert np.all(np.abs(b[ok] - t[ok]) <= tol * s[ok])                  # FAST vs truth
+    if order in ("quadratic", "cubic"):  # Hessians: bounded through the coefficient magnitude
+        eh, fh = g._eval(X, V | G | H)[2], g._eval(X, V | G | H, fast=True)[2]
+        ok = ~np.isnan(eh)
+        assert np.array_equal(np.isnan(eh), np.isnan(fh))
+        assert np.max(np.abs(eh[ok].astype(np.float64) - fh[ok]), initial=0.0) <= tol * np.max(np.abs(co)) * 4.0 ** len(shape)
 
 
 def test_nan_under_zero_weight_does_not_poison(gb, oracle):
@@ -368,8 +382,20 @@ def test_full_size_properties_c2(gb):
     assert bool(torch.isfinite(val).all()) and bool(torch.isfinite(grad).all())
     v_only = gb.getindex_batch(g, X)
     assert torch.equal(v_only, val)
+    # FAST within north_star's 4 ulp of the magnitude scale S = sum|c_i a_i| (extended-precision oracle)
+    # on a 200k-query sample, against the reference arithmetic and against the truth
     vf, gf = gb.valgrad_batch(g, X, fast=True)
-    assert float((vf - val).abs().max()) < 64 * 2.2e-16 * 2 and float((gf - grad).abs().max()) < 64 * 2.2e-16 * 8
+    ns = 200_000
+    from oracle import oracle as O
+
+    tv, tg, sv, sg = O.evaluate_truth(g.coefs, "nan", "cubic", X[:ns].cpu().numpy())
+    ve, ge, vfn, gfn = val[:ns].cpu().numpy(), grad[:ns].cpu().numpy(), vf[:ns].cpu().numpy(), gf[:ns].cpu().numpy()
+    # measured on 1e6 queries (profiles/README.md): FAST vs truth max 2.6 / 2.3 ulp(S) (value / gradient), the
+    # reference arithmetic (EXACT) vs truth max 4.6 / 3.7 -- so FAST is held to 4 ulp(S) of the TRUTH and
+    # to 8 ulp(S) of the reference arithmetic, whose own rounding noise exceeds 4 for a few queries in a million
+    assert np.all(np.abs(vfn - tv) <= 4 * EPS64 * sv) and np.all(np.abs(gfn - tg) <= 4 * EPS64 * sg)
+    assert np.all(np.abs(vfn - ve) <= 8 * EPS64 * sv) and np.all(np.abs(gfn - ge) <= 8 * EPS64 * sg)
+    assert np.all(np.abs(ve - tv) <= 8 * EPS64 * sv) and np.all(np.abs(ge - tg) <= 8 * EPS64 * sg)
     Xo = X[:100_000].clone()
     Xo[::2, 1] = n + 0.25
     Xo[1::2, 2] = 0.75

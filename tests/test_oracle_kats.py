@@ -446,3 +446,19 @@ def test_divergences_documented(oracle):
     ig = mk(oracle, A, "nan", "linear")
     v, g = ig.valgrad(8.0)            # D1: tap len+1 under a non-zero gradient weight is skipped
     assert v == 8.0 and g == -8.0
+
+
+@pytest.mark.parametrize("bc,order,shape", [("nan", "cubic", (12, 13, 11)), ("reflect", "quadratic", (30, 20)), ("periodic", "linear", (6, 7, 5, 6)),
+                                            ("fill", "quadratic", (9, 8, 7)), ("nan", "cubic", (40,))])
+def test_extended_precision_truth_brackets_the_reference_arithmetic(oracle, bc, order, shape):
+    """oracle.evaluate_truth (long double, OURS) vs the reference-order double arithmetic: the two
+    agree to a few ulp of the magnitude scale S = sum|c_i a_i| -- the yardstick for GB_FAST."""
+    rng = np.random.default_rng(5)
+    A = rng.random(shape)
+    co = oracle.make_coefs(A, bc, order, -1.25 if bc == "fill" else None)
+    X = 1.0 + (np.array(shape) - 1.0) * rng.random((3000, len(shape)))
+    v, g, _, _ = oracle.evaluate(co, bc, order, X, 3)
+    tv, tg, sv, sg = oracle.evaluate_truth(co, bc, order, X)
+    eps = 2.220446049250313e-16
+    assert np.all(np.abs(v - tv) <= 8 * eps * sv) and np.all(np.abs(g - tg) <= 8 * eps * sg)
+    assert np.all(sv >= np.abs(tv) * (1 - 1e-12)) and np.all(sg >= np.abs(tg) * (1 - 1e-12))
