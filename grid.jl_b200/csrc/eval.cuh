@@ -1345,7 +1345,13 @@ int launch_one(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     const size_t grid_bytes = (size_t)p.total * sizeof(T);
     const bool forced = (flags & GB_TILED) != 0;
     bool tiled = forced;
-    if (!(flags & (GB_TILED | GB_PLAIN))) tiled = N >= 2 && ORDER >= GB_LINEAR && p.nq >= (1ll << 20) && grid_bytes >= (48u << 20);
+    // Heuristic (measured, profiles/README.md): binning costs two random 32-byte-class permutations of the
+    // batch (records out, results back), which only pays when a query's neighbourhood is heavy -- 3-D cubic
+    // f64 (64 taps, 512 B): tiled 1.4 ms vs plain 3 ms per 1e7; 2-D quadratic f32 (36 B) and 4-D linear f64
+    // (128 B): plain is 3-5x faster -- and the grid is too large to be served out of L2.
+    size_t tap_bytes = sizeof(T);
+    for (int d = 0; d < N; d++) tap_bytes *= (size_t)L;
+    if (!(flags & (GB_TILED | GB_PLAIN))) tiled = N >= 2 && tap_bytes >= 256 && p.nq >= (1ll << 20) && grid_bytes >= (48u << 20);
     if (tiled) tiled = choose_tile(N, L, sizeof(T), p.len, std::min<i64>(p.nq, tiled_max_batch()), forced, p.tile, p.ntile);
     p.tiled = 0;
     p.aos = 0;

@@ -7,10 +7,19 @@
 // lines in parallel.  The substitution order is the reference's, so results are bit-identical
 // to the CPU oracle.
 //
-// Kernel shape: one thread per line, lines enumerated with the contiguous dimension fastest, so
-// for sweeps along dims >= 2 a warp touches 32 consecutive elements per step (coalesced).  The
-// sweep along dim 1 walks 32 different lines per warp; each thread then consumes its own 128-byte
-// line over 16 (f64) / 32 (f32) consecutive steps out of L1.
+// Kernel shape: one thread per line (the substitutions are sequential along a line and must keep the
+// reference's order), all lines of a sweep resident at once; a line is streamed in chunks of 8
+// elements with the next chunk's loads in flight while the current one is computed (line IO
+// policies below).  Sweeps along dims >= 2: 32 adjacent lines per warp, every access a coalesced
+// 256-byte row.  Sweep along dim 1: 8 lanes fetch 64 contiguous bytes of one line and a
+// shared-memory tile turns the chunk so that lane r owns line r.  The pivot divisions use the
+// host-computed reciprocals with FMA refinement (exact_div: same bits as a / d, 5 dependent
+// operations).  Measured on 258^3 f64 (cubic, Woodbury): 0.27 ms per sweep along dims 2/3
+// (64 B/point of traffic -> 63 % of the HBM copy rate), 0.49 ms along dim 1.  A variant that kept
+// whole lines in shared memory (16 B/point of HBM traffic) was built and measured at 0.5 ms per
+// sweep -- too few lines per SM in flight to hide the dependent FP64 chain -- and dropped.
+#include <cstdlib>
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -22,6 +31,7 @@ namespace {
 template <typename T> struct LineSys {
     const T* dl;   // n-1 multipliers
     const T* d;    // n
+    const T* rd;   // n: correctly rounded 1/d[i] (for exact_div)
     const T* du;   // n-1
     const T* du2;  // n-2
     const int* swap;  // n-1 flags: row interchange at step i (ipiv[i] == i+1)
@@ -30,22 +40,49 @@ template <typename T> struct LineSys {
     T cp[4];  // column-major 2x2
 };
 
+// ---- a / d, correctly rounded, without the division routine ------------------------------------------
+// The back substitution divides by the pivot d[i], which is the same for every line, so rd = RN(1/d)
+// comes from the host and the quotient is refined with exact FMA residuals (Markstein): q0 = RN(a*rd)
+// is within 2 ulp of a/d, one correction makes it faithful, the second one rounds correctly -- the
+// same bits as a / d (checked against the hardware division over 5e8 random numerators per pivot,
+// oracle/check_exact_div.c) in 5 dependent operations instead of ~30.  Numerators whose exponent
+// is far from 1 (possible underflow of the residuals, Inf/NaN) take the real division; a zero
+// numerator returns the correctly signed zero directly.
+__device__ __forceinline__ bool div_safe(double a) { return (unsigned)(((unsigned)__double2hiint(a) >> 20) & 0x7ffu) - 200u < 1600u; }
+__device__ __forceinline__ bool div_safe(float a) { return (unsigned)(((unsigned)__float_as_int(a) >> 23) & 0xffu) - 40u < 170u; }
+template <typename T> __device__ __forceinline__ T exact_div(T a, T d, T rd) {
+    const T q0 = a * rd;
+    if (a == (T)0) return q0;  // +-0 with the sign of a/d (rd has the sign of d): zero lines (padding planes) stay cheap
+    if (div_safe(a)) {
+        const T r0 = fma(-d, q0, a);
+        const T q1 = fma(r0, rd, q0);
+        const T r1 = fma(-d, q1, a);
+        return fma(r1, rd, q1);
+    }
+    return a / d;
+}
+
 // ---- line IO policies -------------------------------------------------------------------------------
-// The substitutions are sequential along a line, so a thread can only hide memory latency by having
-// the NEXT elements of its line in flight: lines are processed in chunks of U elements that are
-// loaded (and later stored) together.
-//   GlobalLine  element i of the line at b[i*s]; used for sweeps along dims >= 2, where the 32 lines
-//               of a warp are adjacent in memory and every chunk access is coalesced.
-//   TileLine    contiguous lines (sweep along dim 1): the warp's 32 lines x U elements travel through
-//               a shared-memory tile so that global accesses stay coalesced (row r = U consecutive
-//               elements of line r) while each lane consumes its own line (column access, odd pitch).
+// The substitutions are sequential along a line, so a thread hides memory latency only by having the
+// NEXT elements of its line in flight: lines are processed in chunks of U elements; fetch() issues
+// the global loads of a chunk into a staging register array (while the previous chunk is being
+// computed), unpack() hands the chunk to the owning thread, store() writes a finished chunk back.
+//   GlobalLine  element i of the line at b[i*s]; for sweeps along dims >= 2, where the 32 lines of a
+//               warp are adjacent in memory and every access is coalesced.  unpack is a copy.
+//   TileLine    contiguous lines (sweep along dim 1): U lanes read U consecutive elements of one
+//               line, so a warp load covers 32/U lines and U loads cover the warp's 32 lines;
+//               a shared-memory tile (odd pitch) turns the chunk so that lane r owns line r.
 template <typename T, int U> struct GlobalLine {
     T* b;
     i64 s;
-    __device__ __forceinline__ void load(T (&v)[U], i64 start, int dir, int cnt) const {
+    __device__ __forceinline__ void fetch(T (&g)[U], i64 start, int dir, int cnt) const {
 #pragma unroll
         for (int u = 0; u < U; u++)
-            if (u < cnt) v[u] = b[(start + dir * u) * s];
+            if (u < cnt) g[u] = b[(start + dir * u) * s];
+    }
+    __device__ __forceinline__ void unpack(T (&v)[U], const T (&g)[U]) const {
+#pragma unroll
+        for (int u = 0; u < U; u++) v[u] = g[u];
     }
     __device__ __forceinline__ void store(const T (&v)[U], i64 start, int dir, int cnt) const {
 #pragma unroll
@@ -55,43 +92,48 @@ template <typename T, int U> struct GlobalLine {
     __device__ __forceinline__ T get(i64 i) const { return b[i * s]; }
     __device__ __forceinline__ void put(i64 i, T v) const { b[i * s] = v; }
 };
-template <typename T, int U> struct TileLine {  // U == 32; all 32 lanes of the warp call together
+template <typename T, int U> struct TileLine {  // U in {8, 16}; all 32 lanes of the warp call together
+    static constexpr int LP = 32 / U;  // lines covered by one warp load (U lanes x sizeof(T) contiguous bytes per line)
     T* base;   // line 0 of this warp
     i64 n;     // line length (line r starts at base + r*n)
     int nl;    // lines this warp really has (<= 32)
     T* tile;   // shared memory [32][U+1]
-    __device__ __forceinline__ void load(T (&v)[U], i64 start, int dir, int cnt) const {
-        const int lane = threadIdx.x & 31;
-        T g[32];
+    __device__ __forceinline__ void fetch(T (&g)[U], i64 start, int dir, int cnt) const {
+        const int lane = threadIdx.x & 31, e = lane % U, l0 = lane / U;
 #pragma unroll
-        for (int r = 0; r < 32; r++)  // 32 independent coalesced row loads in flight
-            if (r < nl && lane < cnt) g[r] = base[r * n + start + dir * lane];
+        for (int r = 0; r < U; r++) {
+            const int line = l0 + LP * r;
+            if (line < nl && e < cnt) g[r] = base[(i64)line * n + start + dir * e];
+        }
+    }
+    __device__ __forceinline__ void unpack(T (&v)[U], const T (&g)[U]) const {
+        const int lane = threadIdx.x & 31, e = lane % U, l0 = lane / U;
+        __syncwarp();
 #pragma unroll
-        for (int r = 0; r < 32; r++) tile[r * (U + 1) + lane] = g[r];
+        for (int r = 0; r < U; r++) tile[(l0 + LP * r) * (U + 1) + e] = g[r];
         __syncwarp();
 #pragma unroll
         for (int u = 0; u < U; u++) v[u] = tile[lane * (U + 1) + u];
-        __syncwarp();
     }
     __device__ __forceinline__ void store(const T (&v)[U], i64 start, int dir, int cnt) const {
-        const int lane = threadIdx.x & 31;
+        const int lane = threadIdx.x & 31, e = lane % U, l0 = lane / U;
+        __syncwarp();
 #pragma unroll
         for (int u = 0; u < U; u++) tile[lane * (U + 1) + u] = v[u];
         __syncwarp();
 #pragma unroll
-        for (int r = 0; r < 32; r++)
-            if (r < nl && lane < cnt) base[r * n + start + dir * lane] = tile[r * (U + 1) + lane];
-        __syncwarp();
+        for (int r = 0; r < U; r++) {
+            const int line = l0 + LP * r;
+            if (line < nl && e < cnt) base[(i64)line * n + start + dir * e] = tile[line * (U + 1) + e];
+        }
     }
     __device__ __forceinline__ T get(i64 i) const {
         const int lane = threadIdx.x & 31;
-        __syncwarp();
-        return lane < nl ? base[lane * n + i] : (T)0;
+        return lane < nl ? base[(i64)lane * n + i] : (T)0;
     }
     __device__ __forceinline__ void put(i64 i, T v) const {
         const int lane = threadIdx.x & 31;
-        if (lane < nl) base[lane * n + i] = v;
-        __syncwarp();
+        if (lane < nl) base[(i64)lane * n + i] = v;
     }
 };
 
@@ -99,10 +141,13 @@ template <typename T, int U> struct TileLine {  // U == 32; all 32 lanes of the 
 // forward elimination of a dense RHS held in `io` (in place)
 template <typename T, int U, typename IO> __device__ __forceinline__ T lu_forward_dense(const IO& io, i64 n, const LineSys<T>& sys) {
     T cur = io.get(0);
+    T g[U];
+    if (n > 1) io.fetch(g, 1, +1, (int)min((i64)U, n - 1));
     for (i64 c0 = 0; c0 < n - 1; c0 += U) {
         const int cnt = (int)min((i64)U, n - 1 - c0);
         T v[U];
-        io.load(v, c0 + 1, +1, cnt);
+        io.unpack(v, g);
+        if (c0 + U < n - 1) io.fetch(g, c0 + U + 1, +1, (int)min((i64)U, n - 1 - c0 - U));  // next chunk in flight
 #pragma unroll
         for (int u = 0; u < U; u++) {
             if (u < cnt) {
@@ -139,23 +184,40 @@ template <typename T, int U, typename IO> __device__ __forceinline__ T lu_forwar
 // back substitution reading the eliminated RHS from `rhs`; SUB == false: results overwrite `dst`;
 // SUB == true (Woodbury): dst[i] = dst[i] - x[i], i.e. B = tmpN1 - tmpN2 fused into the sweep.
 template <typename T, int U, bool SUB, typename IO> __device__ __forceinline__ void lu_backward(const IO& rhs, const IO& dst, i64 n, const LineSys<T>& sys, T last) {
-    T x1 = last / __ldg(sys.d + (n - 1));
-    dst.put(n - 1, SUB ? dst.get(n - 1) - x1 : x1);
+    T x1 = exact_div(last, __ldg(sys.d + (n - 1)), __ldg(sys.rd + (n - 1)));
+    {
+        const T o = SUB ? dst.get(n - 1) : (T)0;
+        dst.put(n - 1, SUB ? o - x1 : x1);
+    }
     if (n < 2) return;
-    const T x0 = (rhs.get(n - 2) - __ldg(sys.du + (n - 2)) * x1) / __ldg(sys.d + (n - 2));
-    dst.put(n - 2, SUB ? dst.get(n - 2) - x0 : x0);
+    const T x0 = exact_div(rhs.get(n - 2) - __ldg(sys.du + (n - 2)) * x1, __ldg(sys.d + (n - 2)), __ldg(sys.rd + (n - 2)));
+    {
+        const T o = SUB ? dst.get(n - 2) : (T)0;
+        dst.put(n - 2, SUB ? o - x0 : x0);
+    }
     T x2 = x1;
     x1 = x0;
+    T g[U], go[SUB ? U : 1];
+    if (n > 2) {
+        const int c = (int)min((i64)U, n - 2);
+        rhs.fetch(g, n - 3, -1, c);
+        if constexpr (SUB) dst.fetch(go, n - 3, -1, c);
+    }
     for (i64 c0 = n - 3; c0 >= 0; c0 -= U) {
         const int cnt = (int)min((i64)U, c0 + 1);
         T v[U], o[SUB ? U : 1];
-        rhs.load(v, c0, -1, cnt);
-        if constexpr (SUB) dst.load(o, c0, -1, cnt);
+        rhs.unpack(v, g);
+        if constexpr (SUB) dst.unpack(o, go);
+        if (c0 - U >= 0) {  // next chunk in flight
+            const int c = (int)min((i64)U, c0 - U + 1);
+            rhs.fetch(g, c0 - U, -1, c);
+            if constexpr (SUB) dst.fetch(go, c0 - U, -1, c);
+        }
 #pragma unroll
         for (int u = 0; u < U; u++) {
             if (u < cnt) {
                 const i64 i = c0 - u;
-                const T x = (v[u] - __ldg(sys.du + i) * x1 - __ldg(sys.du2 + i) * x2) / __ldg(sys.d + i);
+                const T x = exact_div(v[u] - __ldg(sys.du + i) * x1 - __ldg(sys.du2 + i) * x2, __ldg(sys.d + i), __ldg(sys.rd + i));
                 if constexpr (SUB) v[u] = o[u] - x;
                 else v[u] = x;
                 x2 = x1;
@@ -180,7 +242,7 @@ template <typename T, int U, typename IO> __device__ __forceinline__ void solve_
 
 // sweeps along dims >= 2: one thread per line, 32 adjacent lines per warp -> coalesced chunk IO
 constexpr int PF_U = 8;
-template <typename T> __global__ void __launch_bounds__(128) line_solve_global(T* A, T* tmp, i64 n, i64 s, i64 inner, i64 nlines, const LineSys<T> sys) {
+template <typename T> __global__ void __launch_bounds__(128, 4) line_solve_global(T* A, T* tmp, i64 n, i64 s, i64 inner, i64 nlines, const LineSys<T> sys) {
     const i64 l = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nlines) return;
     const i64 lo = l % inner, hi = l / inner;
@@ -189,15 +251,15 @@ template <typename T> __global__ void __launch_bounds__(128) line_solve_global(T
     solve_line<T, PF_U>(b, t, n, sys);
 }
 // sweep along dim 1 (contiguous lines): one warp per 32 lines, shared-memory transposing tile
-constexpr int PF_TU = 32, PF_WARPS = 4;
-template <typename T> __global__ void __launch_bounds__(32 * PF_WARPS) line_solve_tile(T* A, T* tmp, i64 n, i64 nlines, const LineSys<T> sys) {
-    __shared__ T tiles[PF_WARPS][32 * (PF_TU + 1)];
+constexpr int PF_WARPS = 4;
+template <typename T, int TU> __global__ void __launch_bounds__(32 * PF_WARPS, TU == 8 ? 4 : 3) line_solve_tile(T* A, T* tmp, i64 n, i64 nlines, const LineSys<T> sys) {
+    __shared__ T tiles[PF_WARPS][32 * (TU + 1)];
     const int warp = threadIdx.x >> 5;
     const i64 first = ((i64)blockIdx.x * PF_WARPS + warp) * 32;
     if (first >= nlines) return;
     const int nl = (int)min((i64)32, nlines - first);
-    const TileLine<T, PF_TU> b{A + first * n, n, nl, tiles[warp]}, t{tmp ? tmp + first * n : nullptr, n, nl, tiles[warp]};
-    solve_line<T, PF_TU>(b, t, n, sys);
+    const TileLine<T, TU> b{A + first * n, n, nl, tiles[warp]}, t{tmp ? tmp + first * n : nullptr, n, nl, tiles[warp]};
+    solve_line<T, TU>(b, t, n, sys);
 }
 
 // ---- host: factorisation (dgttrf order) + Woodbury capacitance ---------------------------------
@@ -321,8 +383,8 @@ template <typename T> int invert_impl(T* A, int ndim, const i64* dims, int bc, i
         HostSys<T> hs;
         rc = hs.setup(bc, order, n);
         if (rc) break;
-        // one device blob: dl | d | du | du2 | swap
-        const size_t nT = (size_t)(4 * n);
+        // one device blob: dl | d | du | du2 | rd | swap
+        const size_t nT = (size_t)(5 * n);
         const size_t bytes = nT * sizeof(T) + (size_t)n * sizeof(int);
         std::vector<unsigned char> blob(bytes, 0);
         T* hb = reinterpret_cast<T*>(blob.data());
@@ -330,6 +392,7 @@ template <typename T> int invert_impl(T* A, int ndim, const i64* dims, int bc, i
         std::copy(hs.d.begin(), hs.d.end(), hb + n);
         std::copy(hs.du.begin(), hs.du.end(), hb + 2 * n);
         std::copy(hs.du2.begin(), hs.du2.end(), hb + 3 * n);
+        for (i64 i = 0; i < n; i++) hb[4 * n + i] = (T)1 / hs.d[i];  // correctly rounded reciprocals of the pivots
         int* hsw = reinterpret_cast<int*>(blob.data() + nT * sizeof(T));
         std::copy(hs.swap.begin(), hs.swap.end(), hsw);
         unsigned char* dblob = nullptr;
@@ -338,7 +401,7 @@ template <typename T> int invert_impl(T* A, int ndim, const i64* dims, int bc, i
         GB_CUDA(cudaMemcpyAsync(dblob, blob.data(), bytes, cudaMemcpyHostToDevice, s));
         LineSys<T> sys;
         T* db = reinterpret_cast<T*>(dblob);
-        sys.dl = db; sys.d = db + n; sys.du = db + 2 * n; sys.du2 = db + 3 * n;
+        sys.dl = db; sys.d = db + n; sys.du = db + 2 * n; sys.du2 = db + 3 * n; sys.rd = db + 4 * n;
         sys.swap = reinterpret_cast<const int*>(dblob + nT * sizeof(T));
         sys.woodbury = hs.woodbury ? 1 : 0;
         sys.vcol0 = (int)hs.vcol[0]; sys.vcol1 = (int)hs.vcol[1];
@@ -347,7 +410,7 @@ template <typename T> int invert_impl(T* A, int ndim, const i64* dims, int bc, i
         if (hs.woodbury && !tmp) GB_CUDA(cudaMallocAsync((void**)&tmp, (size_t)total * sizeof(T), s));
         if (str == 1 && nlines >= 32) {
             const i64 grid = (nlines + 32 * PF_WARPS - 1) / (32 * PF_WARPS);
-            line_solve_tile<T><<<(unsigned)grid, 32 * PF_WARPS, 0, s>>>(A, tmp, n, nlines, sys);
+            line_solve_tile<T, 8><<<(unsigned)grid, 32 * PF_WARPS, 0, s>>>(A, tmp, n, nlines, sys);  // 8: measured faster than 16
         } else {
             const i64 grid = (nlines + 127) / 128;
             line_solve_global<T><<<(unsigned)grid, 128, 0, s>>>(A, tmp, n, str, str, nlines, sys);
