@@ -33,6 +33,9 @@ SIGNATURES = {
     "gb_profile_read": (i32, [C.POINTER(C.c_double), i32, p_i32]),
     "gb_grid_create": (i32, [p_vp, i32, i32, p_i64, vp, i32, i32, i32, f64, vp]),
     "gb_grid_create_from_coefs": (i32, [p_vp, i32, i32, p_i64, vp, i32, i32, i32, f64, vp]),
+    "gb_grid_create_channels": (i32, [p_vp, i32, i32, p_i64, i64, vp, i32, i32, i32, f64, vp]),
+    "gb_grid_create_from_coefs_channels": (i32, [p_vp, i32, i32, p_i64, i64, vp, i32, i32, i32, f64, i32, vp]),
+    "gb_grid_channels": (i32, [vp, p_i64]),
     "gb_grid_info": (i32, [vp, p_i32, p_i32, p_i64, p_i64, p_i32, p_i32, p_f64]),
     "gb_grid_coefs_device": (i32, [vp, p_vp]),
     "gb_grid_coefs_download": (i32, [vp, vp]),

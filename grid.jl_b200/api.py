@@ -569,6 +569,102 @@ class InterpGrid(AbstractInterpGrid):
         return out
 
 
+class InterpGridChannels(InterpGrid):
+    """Multi-valued InterpGrid: A has one trailing channel dimension, A[..., c] is channel c.
+
+    The reference serves multi-valued functions (RGB images, spectra) through its low-level
+    interface -- `set_position` once, `interp(ic, A, index)` per channel (README.md:151-209,
+    src/interp.jl:390-429,489-508) -- so that the taps and weights of a location are computed once.
+    This is the batched form: every evaluation returns one value (gradient, Hessian) per channel,
+    `val[q, c]`, `grad[q, c, :]`, `hess[q, c, :, :]`, each identical to what InterpGrid(A[..., c], BC, IT)
+    returns.  `InterpGridChannels.from_coefs(coefs, bc, it, raw=True)` adopts coefficients prepared
+    with `interp_invert_(A, bc, it, dimlist=1:N)` and takes ARRAY index coordinates like
+    `set_position` does (no setx shift)."""
+
+    def __init__(self, A, bc, it, _from_coefs=False, _raw=False):
+        lib = L.lib()
+        order = _it(it)
+        fill = float("nan")
+        if isinstance(bc, (int, float, np.integer, np.floating)) and not isinstance(bc, bool):
+            fill, bcode, bc = float(bc), 6, BCfill
+        else:
+            bcode = _bc(bc)
+            if bcode == 6 and not _from_coefs:
+                raise ErrorException(L.GB_ERR_ARG, "Construct BCfill InterpGrids by supplying the fill value")
+        a = _Arr(A, name="A")
+        if a.ndim < 2:
+            raise ErrorException(L.GB_ERR_ARG, "InterpGridChannels needs at least one interpolated dimension and the channel dimension")
+        nd, nchan = a.ndim - 1, int(a.shape[-1])
+        self.BC, self.IT = bc, it
+        self._h = C.c_void_p()
+        if _from_coefs:
+            L.check(lib.gb_grid_create_from_coefs_channels(C.byref(self._h), a.dtype, nd, _i64s(a.shape[:-1]), nchan, a.ptr, a.mem, bcode, order,
+                                                           fill, 1 if _raw else 0, a.stream()))
+        else:
+            L.check(lib.gb_grid_create_channels(C.byref(self._h), a.dtype, nd, _i64s(a.shape[:-1]), nchan, a.ptr, a.mem, bcode, order, fill, a.stream()))
+        self._lib = lib
+        dt, ndc = C.c_int(), C.c_int()
+        ud, sd = (C.c_int64 * 8)(), (C.c_int64 * 8)()
+        L.check(lib.gb_grid_info(self._h, C.byref(dt), C.byref(ndc), ud, sd, None, None, None))
+        self.ndim = ndc.value
+        self.nchan = nchan
+        self.dtype_code = dt.value
+        self.eltype = np.float32 if dt.value == L.GB_F32 else np.float64
+        self._size = tuple(ud[i] for i in range(self.ndim))
+        self._stored = tuple(sd[i] for i in range(self.ndim))
+        self.fillval = fill
+        self.affine = None
+
+    @classmethod
+    def from_coefs(cls, coefs, bc, it, raw=False):
+        g = cls.__new__(cls)
+        InterpGridChannels.__init__(g, coefs, bc, it, _from_coefs=True, _raw=raw)
+        return g
+
+    @property
+    def coefs(self):
+        out = np.empty(self._stored + (self.nchan,), dtype=self.eltype, order="F")
+        L.check(self._lib.gb_grid_coefs_download(self._h, out.ctypes.data))
+        return out
+
+    def coefs_device(self):
+        raise MethodError(L.GB_ERR_UNSUPPORTED, "coefs_device is not provided for multi-valued grids")
+
+    def _eval(self, X, mask, val=None, grad=None, hess=None, fast=False, affine=None, tiled=None):
+        N, Cn = self.ndim, self.nchan
+        q = X if isinstance(X, _Queries) else _Queries(X, N)
+        dt = self.dtype_code
+        if val is None:
+            val = _out_array(q, (q.nq, Cn), dt)
+        pv = _out_ptr(val, q, (q.nq, Cn), dt, "value")
+        pg = ph = None
+        if mask & L.GB_OUT_GRAD:
+            if grad is None:
+                grad = _out_array(q, (q.nq, Cn, N), dt)
+            pg = _out_ptr(grad, q, (q.nq, Cn, N), dt, "gradient")
+        if mask & L.GB_OUT_HESS:
+            if hess is None:
+                hess = _out_array(q, (q.nq, Cn, N, N), dt)
+            ph = _out_ptr(hess, q, (q.nq, Cn, N, N), dt, "hessian")
+        aff = None
+        if affine is not None:
+            aff = (C.c_double * (4 * N))(*[v for row in affine for v in row])
+        bad = C.c_int64(-1)
+        pbad = C.byref(bad) if self.BC is BCnil else None
+        flags = L.GB_FAST if fast else L.GB_EXACT
+        if q.cols is not None:
+            rc = self._lib.gb_eval_soa(self._h, mask, q.nq, q.ptrs, q.xdtype, aff, pv, pg, ph, q.mem, flags, pbad, q.stream())
+        else:
+            rc = self._lib.gb_eval(self._h, mask, q.nq, q.ptr, q.xdtype, N, 1, aff, pv, pg, ph, q.mem, flags, pbad, q.stream())
+        L.check(rc, bad.value)
+        return val, grad, hess
+
+    def __getitem__(self, idx):
+        idx = idx if isinstance(idx, tuple) else (idx,)
+        v, _, _ = self._eval(self._scalar_args(idx), L.GB_OUT_VAL)
+        return v[0]
+
+
 def _grid_of(G):
     return G.grid if isinstance(G, CoordInterpGrid) else G
 

@@ -57,7 +57,8 @@ struct gb_grid {
     int dtype, ndim, bc, order;
     double fill;
     i64 user_dims[MAXG], stored_dims[MAXG];
-    i64 total;
+    i64 total;   // stored elements of ONE channel
+    i64 nchan;   // channels (multi-valued grids), 1 for a scalar grid; the channel is the slowest dimension
     void* coefs;
     int device;
     int shift;
@@ -210,7 +211,7 @@ int gb_pad1(int dtype, int ndim, const int64_t* dims, const void* in, double fil
 static int new_grid(gb_grid** out, int dtype, int ndim, int bc, int order, double fill) {
     gb_grid* g = new gb_grid();
     g->dtype = dtype; g->ndim = ndim; g->bc = bc; g->order = order; g->fill = fill;
-    g->coefs = nullptr; g->total = 0;
+    g->coefs = nullptr; g->total = 0; g->nchan = 1;
     g->shift = needs_shift(bc, order) ? 1 : 0;
     for (int d = 0; d < MAXG; d++) g->user_dims[d] = g->stored_dims[d] = 1;
     if (cudaGetDevice(&g->device) != cudaSuccess) g->device = 0;
@@ -218,30 +219,37 @@ static int new_grid(gb_grid** out, int dtype, int ndim, int bc, int order, doubl
     return GB_OK;
 }
 
-int gb_grid_create(gb_grid** out, int dtype, int ndim, const int64_t* dims, const void* samples, int mem, int bc,
-                   int order, double fill, void* stream) {
+// InterpGrid(A, BC, IT) for `nchan` arrays sharing one geometry (channel = slowest dimension of
+// `samples`): copy (or pad by one sample per interpolated dimension, src/interp.jl:58-72), then
+// interp_invert! along the interpolated dimensions only (the README's dimlist = 1:3 usage).
+static int grid_create_impl(gb_grid** out, int dtype, int ndim, const int64_t* dims, int64_t nchan, const void* samples, int mem, int bc,
+                            int order, double fill, void* stream) {
     if (!out || !samples) return fail(GB_ERR_ARG, "NULL argument");
     *out = nullptr;
     int rc = check_grid_args(dtype, ndim, dims, bc, order);
     if (rc) return rc;
+    if (nchan < 1) return fail(GB_ERR_ARG, "nchan must be >= 1");
+    if (nchan > 1 && ndim + 1 > MAXG) return fail(GB_ERR_UNSUPPORTED, "multi-valued grids: ndim + 1 must be <= 8");
     cudaStream_t s = (cudaStream_t)stream;
     pool_keep_memory();
     const bool pad = needs_shift(bc, order);              // src/interp.jl:58-72
     const int pf_bc = bc == GB_BC_FILL ? GB_BC_NEAREST : bc;  // :68
     const double padval = bc == GB_BC_FILL ? fill : 0.0;      // :60,:67
-    i64 ut = 1, st = 1, sd[MAXG];
+    i64 ut = 1, st = 1, sd[MAXG + 1];
     for (int d = 0; d < ndim; d++) {
         sd[d] = dims[d] + (pad ? 2 : 0);
         ut *= dims[d];
         st *= sd[d];
         if (sd[d] < min_len(bc, order)) return fail(GB_ERR_ARG, "grid too small for this interpolation order");
     }
+    if ((double)st * (double)nchan > 4.0e12) return fail(GB_ERR_ARG, "grid too large");
     gb_grid* g = nullptr;
     new_grid(&g, dtype, ndim, bc, order, fill);
     for (int d = 0; d < ndim; d++) { g->user_dims[d] = dims[d]; g->stored_dims[d] = sd[d]; }
     g->total = st;
+    g->nchan = nchan;
     const size_t es = esize(dtype);
-    cudaError_t e = cudaMalloc(&g->coefs, (size_t)st * es);
+    cudaError_t e = cudaMalloc(&g->coefs, (size_t)st * (size_t)nchan * es);
     if (e != cudaSuccess) { delete g; return cuda_fail(e, "cudaMalloc(coefs)"); }
     void* staged = nullptr;
     const void* src = samples;
@@ -254,21 +262,24 @@ int gb_grid_create(gb_grid** out, int dtype, int ndim, const int64_t* dims, cons
     };
     if (pad) {
         if (mem == GB_HOST) {
-            e = cudaMallocAsync(&staged, (size_t)ut * es, s);
+            e = cudaMallocAsync(&staged, (size_t)ut * (size_t)nchan * es, s);
             if (e != cudaSuccess) return cleanup(cuda_fail(e, "cudaMallocAsync"));
-            e = cudaMemcpyAsync(staged, samples, (size_t)ut * es, cudaMemcpyHostToDevice, s);
+            e = cudaMemcpyAsync(staged, samples, (size_t)ut * (size_t)nchan * es, cudaMemcpyHostToDevice, s);
             if (e != cudaSuccess) return cleanup(cuda_fail(e, "cudaMemcpyAsync H2D"));
             src = staged;
         }
-        rc = pad1_device(dtype, ndim, (const i64*)dims, src, padval, g->coefs, s);
-        if (rc) return cleanup(rc);
+        for (i64 c = 0; c < nchan; c++) {
+            rc = pad1_device(dtype, ndim, (const i64*)dims, (const char*)src + (size_t)c * ut * es, padval, (char*)g->coefs + (size_t)c * st * es, s);
+            if (rc) return cleanup(rc);
+        }
     } else {
-        e = cudaMemcpyAsync(g->coefs, samples, (size_t)ut * es, mem == GB_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s);
+        e = cudaMemcpyAsync(g->coefs, samples, (size_t)ut * (size_t)nchan * es, mem == GB_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s);
         if (e != cudaSuccess) return cleanup(cuda_fail(e, "cudaMemcpyAsync"));
     }
     std::vector<int> all;
     for (int d = 0; d < ndim; d++) all.push_back(d);
-    rc = invert_device(dtype, ndim, sd, g->coefs, pf_bc, order, all.data(), ndim, s);
+    sd[ndim] = nchan;  // lines of every channel are solved in the same sweeps
+    rc = invert_device(dtype, nchan > 1 ? ndim + 1 : ndim, sd, g->coefs, pf_bc, order, all.data(), ndim, s);
     if (rc) return cleanup(rc);
     if (staged) cudaFreeAsync(staged, s);
     if (mem == GB_HOST) {
@@ -278,14 +289,14 @@ int gb_grid_create(gb_grid** out, int dtype, int ndim, const int64_t* dims, cons
     *out = g;
     return GB_OK;
 }
-
-int gb_grid_create_from_coefs(gb_grid** out, int dtype, int ndim, const int64_t* stored_dims, const void* coefs, int mem,
-                              int bc, int order, double fill, void* stream) {
+static int grid_from_coefs_impl(gb_grid** out, int dtype, int ndim, const int64_t* stored_dims, int64_t nchan, const void* coefs, int mem,
+                                int bc, int order, double fill, int raw_coords, void* stream) {
     if (!out || !coefs) return fail(GB_ERR_ARG, "NULL argument");
     *out = nullptr;
     int rc = check_grid_args(dtype, ndim, stored_dims, bc, order);
     if (rc) return rc;
-    const bool pad = needs_shift(bc, order);
+    if (nchan < 1) return fail(GB_ERR_ARG, "nchan must be >= 1");
+    const bool pad = needs_shift(bc, order) && !raw_coords;
     i64 st = 1;
     for (int d = 0; d < ndim; d++) {
         if (stored_dims[d] < min_len(bc, order) || (pad && stored_dims[d] < 3)) return fail(GB_ERR_ARG, "stored grid too small");
@@ -293,15 +304,40 @@ int gb_grid_create_from_coefs(gb_grid** out, int dtype, int ndim, const int64_t*
     }
     gb_grid* g = nullptr;
     new_grid(&g, dtype, ndim, bc, order, fill);
+    if (raw_coords) g->shift = 0;  // low-level interface: coordinates index the array as stored (no setx shift)
     for (int d = 0; d < ndim; d++) { g->stored_dims[d] = stored_dims[d]; g->user_dims[d] = stored_dims[d] - (pad ? 2 : 0); }
     g->total = st;
+    g->nchan = nchan;
     cudaStream_t s = (cudaStream_t)stream;
-    cudaError_t e = cudaMalloc(&g->coefs, (size_t)st * esize(dtype));
+    const size_t bytes = (size_t)st * (size_t)nchan * esize(dtype);
+    cudaError_t e = cudaMalloc(&g->coefs, bytes);
     if (e != cudaSuccess) { delete g; return cuda_fail(e, "cudaMalloc(coefs)"); }
-    e = cudaMemcpyAsync(g->coefs, coefs, (size_t)st * esize(dtype), mem == GB_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s);
+    e = cudaMemcpyAsync(g->coefs, coefs, bytes, mem == GB_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s);
     if (e == cudaSuccess && mem == GB_HOST) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) { cudaFree(g->coefs); delete g; return cuda_fail(e, "copy coefs"); }
     *out = g;
+    return GB_OK;
+}
+
+int gb_grid_create(gb_grid** out, int dtype, int ndim, const int64_t* dims, const void* samples, int mem, int bc,
+                   int order, double fill, void* stream) {
+    return grid_create_impl(out, dtype, ndim, dims, 1, samples, mem, bc, order, fill, stream);
+}
+int gb_grid_create_from_coefs(gb_grid** out, int dtype, int ndim, const int64_t* stored_dims, const void* coefs, int mem,
+                              int bc, int order, double fill, void* stream) {
+    return grid_from_coefs_impl(out, dtype, ndim, stored_dims, 1, coefs, mem, bc, order, fill, 0, stream);
+}
+int gb_grid_create_channels(gb_grid** out, int dtype, int ndim, const int64_t* dims, int64_t nchan, const void* samples, int mem,
+                            int bc, int order, double fill, void* stream) {
+    return grid_create_impl(out, dtype, ndim, dims, nchan, samples, mem, bc, order, fill, stream);
+}
+int gb_grid_create_from_coefs_channels(gb_grid** out, int dtype, int ndim, const int64_t* stored_dims, int64_t nchan, const void* coefs,
+                                       int mem, int bc, int order, double fill, int raw_coords, void* stream) {
+    return grid_from_coefs_impl(out, dtype, ndim, stored_dims, nchan, coefs, mem, bc, order, fill, raw_coords, stream);
+}
+int gb_grid_channels(const gb_grid* g, int64_t* nchan) {
+    if (!g || !nchan) return fail(GB_ERR_ARG, "NULL argument");
+    *nchan = g->nchan;
     return GB_OK;
 }
 
@@ -325,7 +361,7 @@ int gb_grid_coefs_device(const gb_grid* g, void** device_ptr) {
 }
 int gb_grid_coefs_download(const gb_grid* g, void* host_out) {
     if (!g || !host_out) return fail(GB_ERR_ARG, "NULL argument");
-    GB_CUDA(cudaMemcpy(host_out, g->coefs, (size_t)g->total * esize(g->dtype), cudaMemcpyDeviceToHost));
+    GB_CUDA(cudaMemcpy(host_out, g->coefs, (size_t)g->total * (size_t)g->nchan * esize(g->dtype), cudaMemcpyDeviceToHost));
     return GB_OK;
 }
 int gb_grid_destroy(gb_grid* g) {
@@ -375,6 +411,8 @@ template <int N> int launch_n(const EvalCall& c, cudaStream_t s) {
     p.first_invalid = c.first_invalid;
     p.tiled = 0;
     p.aos = 0;
+    p.nchan = (int)g->nchan;
+    p.cstride = g->total;
     p.perm = nullptr; p.work = nullptr; p.nwork = nullptr;
     for (int d = 0; d < N; d++) { p.tile[d] = 1; p.ntile[d] = 1; }
     const int bcf = bc_family(g->bc);
@@ -404,6 +442,7 @@ template <int N> int launch_n(const EvalCall& c, cudaStream_t s) {
 
 int launch_generic(const EvalCall& c, cudaStream_t s) {
     const gb_grid* g = c.g;
+    if (g->nchan > 1) return fail(GB_ERR_UNSUPPORTED, "multi-valued grids are supported for N <= 4 (N = 4: InterpNearest / InterpLinear)");
     GenericParams p;
     p.coefs = g->coefs;
     p.total = g->total;
@@ -471,7 +510,7 @@ struct DeviceGuard {
 int eval_host(const gb_grid* g, int out_mask, int outmode, i64 nq, const void* const* xcols, const void* xaos, int xdtype,
               const double* affine, void* val, void* grad, void* hess, int flags, int64_t* first_invalid) {
     const int N = g->ndim;
-    const size_t xs = esize(xdtype), es = esize(g->dtype);
+    const size_t xs = esize(xdtype), es = esize(g->dtype) * (size_t)g->nchan;  // es: bytes of one query's values (all channels)
     static const i64 chunk_env = [] {
         const char* e = getenv("GB_EVAL_CHUNK");
         long long v = e ? atoll(e) : 0;
@@ -666,7 +705,7 @@ int gb_eval_outer(const gb_grid* g, const int64_t* lens, const void* const* vecs
     DeviceGuard guard(g->device);
     pool_keep_memory();
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t xs = esize(xdtype), es = esize(g->dtype);
+    const size_t xs = esize(xdtype), es = esize(g->dtype) * (size_t)g->nchan;
     // device copies of the vectors (host mode), the pointer table, lens, the expanded columns
     void* dvec[MAXG] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     const void* vptr[MAXG];

@@ -82,6 +82,8 @@ template <int N> struct EvalParams {
     u64* first_invalid;   // device, atomicMin target (BCnil) or NULL
     // tiled (spatially binned) evaluation, filled in by launch_one; tiled == 0 -> plain
     int tiled;
+    int nchan;            // channels sharing the taps/weights of a query (multi-valued grids); 1 = scalar grid
+    i64 cstride;          // elements between consecutive channels of the coefficient array
     int aos;              // != 0: outputs are records of `aos` words per sorted slot at `val` (tiled mode)
     int tile[N];          // cells per tile
     int ntile[N];         // tiles per dimension

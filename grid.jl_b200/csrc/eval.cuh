@@ -618,10 +618,9 @@ __device__ __forceinline__ void store_outputs(const EvalParams<N>& p, i64 pos, i
 // Literal restatement of interp (src/interp.jl:501-505) with the `c == 0 ? 0 : c*a` select, rolled
 // loops, global memory only, one pass per output.  Executed for (almost) no query; kept out of line.
 template <typename T, int N, int ORDER, int BCF>
-__device__ __noinline__ void eval_one_slow(const EvalParams<N>& p, const T (&x)[N], const i64 pos, const i64 q, const int outmode) {
+__device__ __noinline__ void eval_one_slow(const EvalParams<N>& p, const T* __restrict__ A, const T (&x)[N], const i64 pos, const i64 q, const int outmode) {
     constexpr int L = ORDER + 1;
     constexpr bool GUARD = (ORDER == GB_LINEAR) || (BCF == BCF_NIL && ORDER == GB_CUBIC);
-    const T* __restrict__ A = (const T*)p.coefs;
     int c[N][L];
     T dx[N];
     T w[3][N][L];
@@ -714,13 +713,19 @@ __device__ __forceinline__ void eval_one(const EvalParams<N>& p, const T (&x)[N]
 #pragma unroll
         for (int i = 0; i < L; i++) src.off[d][i] = (u32)c[d][i] * (u32)p.stride[d];
     }
-    T acc[NP];
-    contract<T, N, L, OUTMODE, FAST>(src, w, acc);
-    if (nonfinite(acc[0])) {  // a NaN/Inf coefficient may have been touched: literal zero-weight semantics
-        eval_one_slow<T, N, ORDER, BCF>(p, x, pos, q, OUTMODE);
-        return;
+    // Multi-valued grids (README.md:151-209: set_position once, interp(ic, A, index) per channel): the
+    // taps and weights above serve every channel; channel ch of a query lands at output pos*nchan + ch.
+    for (int ch = 0; ch < p.nchan; ch++) {
+        T acc[NP];
+        contract<T, N, L, OUTMODE, FAST>(src, w, acc);
+        const i64 opos = pos * p.nchan + ch;
+        if (nonfinite(acc[0])) {  // a NaN/Inf coefficient may have been touched: literal zero-weight semantics
+            eval_one_slow<T, N, ORDER, BCF>(p, src.A, x, opos, q, OUTMODE);
+        } else {
+            store_outputs<T, N, OUTMODE>(p, opos, q, valid, acc);
+        }
+        src.A += p.cstride;
     }
-    store_outputs<T, N, OUTMODE>(p, pos, q, valid, acc);
 }
 // ---- plain evaluation kernel -----------------------------------------------------------------------
 // One thread per query in the caller's order, CTAs stride over blocks of EVAL_BLOCK queries; taps
@@ -1352,6 +1357,7 @@ int launch_one(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     size_t tap_bytes = sizeof(T);
     for (int d = 0; d < N; d++) tap_bytes *= (size_t)L;
     if (!(flags & (GB_TILED | GB_PLAIN))) tiled = N >= 2 && tap_bytes >= 256 && p.nq >= (1ll << 20) && grid_bytes >= (48u << 20);
+    if (p.nchan > 1) tiled = false;  // multi-valued grids: plain path (one brick per channel would not fit)
     if (tiled) tiled = choose_tile(N, L, sizeof(T), p.len, std::min<i64>(p.nq, tiled_max_batch()), forced, p.tile, p.ntile);
     p.tiled = 0;
     p.aos = 0;

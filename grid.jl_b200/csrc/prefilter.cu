@@ -45,7 +45,7 @@ template <typename T> struct LineSys {
 // comes from the host and the quotient is refined with exact FMA residuals (Markstein): q0 = RN(a*rd)
 // is within 2 ulp of a/d, one correction makes it faithful, the second one rounds correctly -- the
 // same bits as a / d (checked against the hardware division over 5e8 random numerators per pivot,
-// oracle/check_exact_div.c) in 5 dependent operations instead of ~30.  Numerators whose exponent
+// the check_exact_div.c program of the test infrastructure) in 5 dependent operations instead of ~30.  Numerators whose exponent
 // is far from 1 (possible underflow of the residuals, Inf/NaN) take the real division; a zero
 // numerator returns the correctly signed zero directly.
 __device__ __forceinline__ bool div_safe(double a) { return (unsigned)(((unsigned)__double2hiint(a) >> 20) & 0x7ffu) - 200u < 1600u; }

@@ -93,6 +93,23 @@ int gb_grid_create(gb_grid** out, int dtype, int ndim, const int64_t* dims, cons
 int gb_grid_create_from_coefs(gb_grid** out, int dtype, int ndim, const int64_t* stored_dims, const void* coefs,
                               int mem, int bc, int order, double fill, void* stream);
 /* size(G) (src/interp.jl:853-856) and the stored (padded) size; any out pointer may be NULL */
+/* Multi-valued grids -- the reference's low-level interface (README.md:151-209; InterpGridCoefs /
+   set_position / interp(ic, A, index), src/interp.jl:390-429,489-508): `nchan` arrays share one
+   geometry, the channel is the slowest dimension of `samples` / `coefs` (element stride = product of
+   the stored dims), taps and weights are computed once per query and reused for every channel.
+   gb_eval* on such a handle write nchan values per query, channel fastest:
+   val[q*nchan + c], grad[(q*nchan + c)*N + d], hess[(q*nchan + c)*N*N + ...].
+   gb_grid_create_channels  = InterpGrid(A[..., c], BC, IT) for every c (padding + prefilter along the
+                              interpolated dims only, i.e. interp_invert!(A, BC, IT, 1:N)).
+   gb_grid_create_from_coefs_channels  adopts prefiltered coefficients; raw_coords != 0 gives the
+                              low-level semantics: query coordinates index the stored array directly
+                              (set_position's x), no +1 shift of setx.  N <= 4 (N = 4: nearest/linear). */
+int gb_grid_create_channels(gb_grid** out, int dtype, int ndim, const int64_t* dims, int64_t nchan, const void* samples,
+                            int mem, int bc, int order, double fill, void* stream);
+int gb_grid_create_from_coefs_channels(gb_grid** out, int dtype, int ndim, const int64_t* stored_dims, int64_t nchan,
+                                       const void* coefs, int mem, int bc, int order, double fill, int raw_coords,
+                                       void* stream);
+int gb_grid_channels(const gb_grid* g, int64_t* nchan);
 int gb_grid_info(const gb_grid* g, int* dtype, int* ndim, int64_t* user_dims, int64_t* stored_dims, int* bc,
                  int* order, double* fill);
 int gb_grid_coefs_device(const gb_grid* g, void** device_ptr); /* borrowed, read-only */

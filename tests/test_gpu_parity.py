@@ -488,3 +488,57 @@ def test_slab_kernels_assemble_to_unsharded(gb, oracle, dtype, shape, world):
     # a slab that lacks a needed plane is refused
     with pytest.raises(gb.ErrorException):
         eng.restrict_slab(gb.jl_from_numpy(np.asfortranarray(A[:, :, 4:8])), 1.0, L3, 4, 1, 3)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("bc,order,shape,nchan", [("reflect", "quadratic", (40, 30), 3), ("nan", "cubic", (10, 10, 10), 7), ("periodic", "linear", (6, 7, 5, 6), 2),
+                                                  ("fill", "quadratic", (12, 9), 4), ("nil", "linear", (20,), 5), ("nearest", "nearest", (9, 8, 7), 3)])
+def test_multivalued_grid_matches_per_channel_grids(gb, oracle, dtype, bc, order, shape, nchan):
+    """(f)-1: multi-valued evaluation (README.md:151-209).  One InterpGridChannels == nchan InterpGrids
+    on A[..., c]: coefficients, values, gradients and Hessians bit-identical to the oracle per channel,
+    host and device queries."""
+    import torch
+
+    rng = np.random.default_rng(41)
+    A = np.asfortranarray(rng.standard_normal(shape + (nchan,)).astype(dtype))
+    BC, IT = tags(gb)
+    fill = -1.25
+    g = gb.InterpGridChannels(A, fill if bc == "fill" else BC[bc], IT[order])
+    assert g.nchan == nchan and g.shape == shape
+    co = g.coefs
+    X = make_queries(rng, shape, 1500, dtype, wide=(bc != "nil"))
+    mask = V | G | (H if order in ("quadratic", "cubic") else 0)
+    if bc == "nil":
+        ov0 = oracle.evaluate(oracle.make_coefs(A[..., 0], bc, order), bc, order, X, V, raise_invalid=False)[0]
+        X = np.ascontiguousarray(X[~np.isnan(ov0)])
+    v, gr, h = g._eval(X, mask)
+    vd, grd, hd = g._eval(torch.from_numpy(X).cuda(), mask)
+    for c in range(nchan):
+        oc = oracle.make_coefs(np.ascontiguousarray(A[..., c]), bc, order, fill if bc == "fill" else None)
+        assert same(co[..., c], oc)
+        ov, og, oh, _ = oracle.evaluate(oc, bc, order, X, mask, raise_invalid=False)
+        assert same(v[:, c], ov) and same(gr[:, c], og) and (oh is None or same(h[:, c], oh))
+        assert same(vd.cpu().numpy()[:, c], ov) and same(grd.cpu().numpy()[:, c], og)
+
+
+def test_multivalued_lowlevel_spectra_example(gb, oracle):
+    """README.md:178-209: a 10x10x10 grid of 200-pixel spectra, interp_invert! along dims 1:3, then one
+    set_position and interp(ic, grid, index) per pixel -- here all pixels of many positions at once,
+    with array index coordinates (raw) like set_position takes."""
+    rng = np.random.default_rng(43)
+    npix = 200
+    grid = np.asfortranarray(rng.random((10, 10, 10, npix)))
+    co = grid.copy(order="F")
+    gb.interp_invert_(co, gb.BCnil, gb.InterpCubic, dimlist=[1, 2, 3])
+    for c in (0, 17, npix - 1):
+        assert same(co[..., c], oracle.invert(np.ascontiguousarray(grid[..., c]).copy(order="F"), "nil", "cubic"))
+    g = gb.InterpGridChannels.from_coefs(co, gb.BCnil, gb.InterpCubic, raw=True)
+    # (the README's own x = 1.5 reads index 0 of the unpadded array under InterpCubic -- Q1 / D2; use 2.5)
+    X = np.concatenate([[[2.5, 2.5, 2.5]], 2.0 + 6.9 * rng.random((300, 3))])
+    spec = g._eval(X, V)[0]
+    assert spec.shape == (301, npix)
+    for c in (0, 1, 99, npix - 1):
+        # the low-level call on channel c: raw coordinates on the unpadded array == oracle.lowlevel
+        for qi in (0, 5, 300):
+            ref = oracle.lowlevel(np.ascontiguousarray(co[..., c]), "cubic", "nil", X[qi], hess=False)
+            assert spec[qi, c] == ref[0]
