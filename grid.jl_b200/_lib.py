@@ -49,6 +49,10 @@ SIGNATURES = {
     "gb_prolong_size": (i32, [i64, i64, p_i64]),
     "gb_restrict": (i32, [i32, i32, p_i64, vp, i32, f64, vp, i32, vp]),
     "gb_prolong": (i32, [i32, i32, p_i64, vp, i32, i64, vp, i32, vp]),
+    "gb_interp_irregular": (i32, [i32, i64, vp, vp, i32, i32, f64, i64, vp, vp, i32, p_i64, vp]),
+    "gb_restrictb": (i32, [i32, i32, p_i64, vp, i32, f64, vp, i32, vp]),
+    "gb_restrict_extrap": (i32, [i32, i32, p_i64, vp, i32, f64, vp, i32, vp]),
+    "gb_prolongb": (i32, [i32, i32, p_i64, vp, i32, i64, vp, i32, vp]),
     "gb_restrict_slab": (i32, [i32, i32, p_i64, vp, i32, f64, i64, i64, i64, i64, vp, i32, vp]),
     "gb_prolong_slab": (i32, [i32, i32, p_i64, vp, i32, i64, i64, i64, i64, i64, vp, i32, vp]),
     "gb_restrict3": (i32, [i32, p_i64, vp, f64, vp, i32, vp]),

@@ -79,6 +79,14 @@ class InterpCubic(InterpType):
     code = 3
 
 
+class InterpForward(InterpType):  # InterpIrregular only (src/interp.jl:371)
+    code = 4
+
+
+class InterpBackward(InterpType):  # InterpIrregular only (:372)
+    code = 5
+
+
 def npoints(it):  # src/interp.jl:577-582
     return _it(it) + 1
 
@@ -665,6 +673,75 @@ class InterpGridChannels(InterpGrid):
         return v[0]
 
 
+class InterpIrregular(AbstractInterpGrid):
+    """InterpIrregular(knots, A, BC, IT) / InterpIrregular(knots, A, fill::Number, IT) (src/interp.jl:318-350):
+    1-D interpolation on sorted, non-uniform knots; IT in InterpForward / InterpBackward / InterpNearest /
+    InterpLinear; BCreflect and BCperiodic are rejected like in the reference.  `G[x]` for a scalar,
+    `G[xs]` / `getindex_batch(G, xs)` for a vector (host array or CUDA tensor)."""
+
+    def __init__(self, knots, A, bc, it):
+        if isinstance(knots, (tuple, list)) and len(knots) > 0 and np.ndim(knots[0]) == 1:
+            if len(knots) != 1:
+                raise ErrorException(L.GB_ERR_UNSUPPORTED, "Sorry, for now only 1d is supported")  # :332-334
+            knots = knots[0]
+        self.fillval = float("nan")
+        if isinstance(bc, (int, float, np.integer, np.floating)) and not isinstance(bc, bool):
+            self.fillval, bc = float(bc), BCfill  # :345-349
+        code = _bc(bc)
+        if code in (3, 4):
+            raise ErrorException(L.GB_ERR_UNSUPPORTED, "Sorry, reflecting or periodic boundary conditions not yet supported")  # :335-337
+        self.order = it.code if isinstance(it, type) else it().code
+        if self.order not in (0, 1, 4, 5):
+            raise MethodError(L.GB_ERR_UNSUPPORTED, "InterpIrregular: InterpForward, InterpBackward, InterpNearest or InterpLinear")
+        self.BC, self.IT, self.bcode, self.ndim = bc, it, code, 1
+        a = np.asarray(A)
+        dt = np.float32 if (a.dtype == np.float32 and np.asarray(knots).dtype == np.float32) else np.float64
+        self.eltype = dt
+        self.grid = np.ascontiguousarray(knots, dtype=dt).copy()
+        self.coefs = np.ascontiguousarray(a, dtype=dt).copy()
+        if self.grid.ndim != 1 or self.coefs.shape != self.grid.shape:
+            raise DimensionMismatch(L.GB_ERR_DIM, "InterpIrregular: knots and samples must be vectors of equal length")
+        if np.any(self.grid[1:] < self.grid[:-1]):
+            raise ErrorException(L.GB_ERR_ARG, "Coordinates must be supplied in increasing order")  # :340-342
+        self._dev = None
+
+    @property
+    def shape(self):
+        return self.coefs.shape
+
+    def _device_arrays(self, device):
+        if self._dev is None or self._dev[0].device != device:
+            torch = _torch()
+            self._dev = (torch.from_numpy(self.grid).to(device), torch.from_numpy(self.coefs).to(device))
+        return self._dev
+
+    def _eval(self, x):
+        lib = L.lib()
+        dtc = L.GB_F32 if self.eltype == np.float32 else L.GB_F64
+        bad = C.c_int64(-1)
+        if _is_tensor(x):
+            torch = _torch()
+            xt = x.to(torch.float32 if self.eltype == np.float32 else torch.float64).contiguous().reshape(-1)
+            g, c = self._device_arrays(xt.device)
+            out = torch.empty_like(xt)
+            rc = lib.gb_interp_irregular(dtc, self.grid.shape[0], g.data_ptr(), c.data_ptr(), self.bcode, self.order, self.fillval, xt.numel(),
+                                         xt.data_ptr(), out.data_ptr(), L.GB_DEVICE, C.byref(bad), torch.cuda.current_stream(xt.device).cuda_stream)
+        else:
+            xa = np.ascontiguousarray(np.atleast_1d(x), dtype=self.eltype)
+            out = np.empty_like(xa)
+            rc = lib.gb_interp_irregular(dtc, self.grid.shape[0], self.grid.ctypes.data, self.coefs.ctypes.data, self.bcode, self.order, self.fillval,
+                                         xa.shape[0], xa.ctypes.data, out.ctypes.data, L.GB_HOST, C.byref(bad), None)
+        if rc == L.GB_ERR_INVALID_LOCATION:
+            raise BoundsError(rc, f"BoundsError (query {bad.value})")  # :356-360
+        L.check(rc)
+        return out
+
+    def __getitem__(self, x):
+        if np.ndim(x) == 0 and not _is_tensor(x):
+            return self._eval([x])[0]
+        return self._eval(x)
+
+
 def _grid_of(G):
     return G.grid if isinstance(G, CoordInterpGrid) else G
 
@@ -949,6 +1026,75 @@ def prolong(A, *args, fused=True):
 
 
 # ---- misc --------------------------------------------------------------------------------------------------------
+
+
+# ---- restrictb / prolongb / restrict_extrap (src/restrict_prolong.jl:187-320) ----------------------------
+
+
+def _edge_dim(fn_name, a, dim, arg):
+    lib = L.lib()
+    shp = list(a.shape)
+    if fn_name == "gb_prolongb":
+        prolong_size(a.shape[dim], arg)
+        shp[dim] = int(arg)
+    else:
+        shp[dim] = restrict_size(shp[dim])
+    out = a.empty_like_shape(shp)
+    o = _Arr(out, name="out")
+    val = int(arg) if fn_name == "gb_prolongb" else float(arg)
+    L.check(getattr(lib, fn_name)(a.dtype, a.ndim, _i64s(a.shape), a.ptr, dim, val, o.ptr, a.mem, a.stream()))
+    return out
+
+
+def _edge_restrict(fn_name, A, dim_or_flag, scale):
+    a = _Arr(A, name="A")
+    if np.ndim(dim_or_flag) == 0 and not isinstance(dim_or_flag, (bool, np.bool_)):
+        dim = int(dim_or_flag)
+        if not 1 <= dim <= a.ndim:
+            raise ErrorException(L.GB_ERR_ARG, "dim out of range")
+        return _edge_dim(fn_name, a, dim - 1, scale)
+    flag = _flags(dim_or_flag, a.ndim)
+    cur, out = a, A
+    for j in range(flag.shape[1]):  # mapdim, src/utilities.jl:7-20
+        for i in range(flag.shape[0]):
+            if flag[i, j]:
+                out = _edge_dim(fn_name, cur, i, scale)
+                cur = _Arr(out, name="out")
+    return out
+
+
+def restrictb(A, dim_or_flag, scale=1.0):
+    """restrictb(A, dim[, scale]) / restrictb(A, flags[, scale]): "balanced" restriction, edge planes
+    weighted (2,1)*scale/sqrt(3) (odd length) or (3,1)*scale/(2 sqrt(2)) (even) (:196-229)."""
+    return _edge_restrict("gb_restrictb", A, dim_or_flag, scale)
+
+
+def restrict_extrap(A, dim_or_flag, scale=1.0):
+    """restrict_extrap(A, dim[, scale]) / (A, flags[, scale]): restrict, then linear extrapolation at the
+    edges (:287-320)."""
+    return _edge_restrict("gb_restrict_extrap", A, dim_or_flag, scale)
+
+
+def prolongb(A, *args):
+    """prolongb(A, dim, len) (1-based dim) or prolongb(A, sizes) (:231-281)."""
+    a = _Arr(A, name="A")
+    if len(args) == 2:
+        dim, length = int(args[0]), int(args[1])
+        if not 1 <= dim <= a.ndim:
+            raise ErrorException(L.GB_ERR_ARG, "prolongb: dim out of range")
+        return _edge_dim("gb_prolongb", a, dim - 1, length)
+    sz = np.asarray(args[0], dtype=np.int64)
+    if sz.ndim == 1:
+        sz = sz[:, None]
+    if sz.shape[0] != a.ndim:
+        raise ErrorException(L.GB_ERR_ARG, "Array of sizes must have as many rows as dimensions of A")
+    cur, out = a, A
+    for j in range(sz.shape[1]):
+        for i in range(sz.shape[0]):
+            if sz[i, j] > cur.shape[i]:
+                out = _edge_dim("gb_prolongb", cur, i, int(sz[i, j]))
+                cur = _Arr(out, name="out")
+    return out
 
 
 def launch_count():

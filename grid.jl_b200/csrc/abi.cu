@@ -3,6 +3,7 @@
 // host<->device staging (chunked, copy/compute overlapped over a small ring of streams) and
 // dispatch to the kernels in eval_*.cu / prefilter.cu / multigrid.cu.  No CPU compute fallback.
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -757,6 +758,63 @@ int gb_eval_outer(const gb_grid* g, const int64_t* lens, const void* const* vecs
     return cleanup(rc);
 }
 
+// ---- InterpIrregular -------------------------------------------------------------------------------
+int gb_interp_irregular(int dtype, int64_t n, const void* knots, const void* samples, int bc, int order, double fill, int64_t nq, const void* x, void* out,
+                        int mem, int64_t* first_invalid, void* stream) {
+    if (!ok_dtype(dtype)) return fail(GB_ERR_ARG, "dtype must be GB_F32 or GB_F64");
+    if (n < 1 || !knots || !samples) return fail(GB_ERR_ARG, "InterpIrregular needs at least one knot");
+    if (nq < 0 || (nq > 0 && (!x || !out))) return fail(GB_ERR_ARG, "bad query arguments");
+    if (bc == GB_BC_REFLECT || bc == GB_BC_PERIODIC) return fail(GB_ERR_UNSUPPORTED, "Sorry, reflecting or periodic boundary conditions not yet supported");
+    if (bc < GB_BC_NIL || bc > GB_BC_FILL) return fail(GB_ERR_ARG, "bad boundary condition");
+    if (!(order == GB_FORWARD || order == GB_BACKWARD || order == GB_NEAREST || order == GB_LINEAR))
+        return fail(GB_ERR_UNSUPPORTED, "InterpIrregular supports InterpForward, InterpBackward, InterpNearest and InterpLinear");
+    if (first_invalid) *first_invalid = -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    pool_keep_memory();
+    const size_t es = esize(dtype);
+    const double fv = (bc == GB_BC_FILL) ? fill : std::nan("");
+    void *dk = nullptr, *dc = nullptr, *dx = nullptr, *dout = nullptr;
+    u64* d_bad = nullptr;
+    int rc = GB_OK;
+    auto cu = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess && rc == GB_OK) rc = cuda_fail(e, what);
+        return e == cudaSuccess;
+    };
+    const void *pk = knots, *pc = samples, *px = x;
+    void* po = out;
+    if (mem == GB_HOST) {
+        cu(cudaMallocAsync(&dk, n * es, s), "cudaMallocAsync");
+        cu(cudaMallocAsync(&dc, n * es, s), "cudaMallocAsync");
+        cu(cudaMallocAsync(&dx, std::max<size_t>(1, nq * es), s), "cudaMallocAsync");
+        cu(cudaMallocAsync(&dout, std::max<size_t>(1, nq * es), s), "cudaMallocAsync");
+        if (rc == GB_OK) {
+            cu(cudaMemcpyAsync(dk, knots, n * es, cudaMemcpyHostToDevice, s), "H2D");
+            cu(cudaMemcpyAsync(dc, samples, n * es, cudaMemcpyHostToDevice, s), "H2D");
+            if (nq) cu(cudaMemcpyAsync(dx, x, nq * es, cudaMemcpyHostToDevice, s), "H2D");
+        }
+        pk = dk; pc = dc; px = dx; po = dout;
+    }
+    if (rc == GB_OK && bc == GB_BC_NIL) {
+        cu(cudaMallocAsync((void**)&d_bad, sizeof(u64), s), "cudaMallocAsync");
+        cu(cudaMemsetAsync(d_bad, 0xFF, sizeof(u64), s), "cudaMemsetAsync");
+    }
+    if (rc == GB_OK) rc = irregular_device(dtype, pk, pc, n, bc, order, fv, px, po, nq, d_bad, s);
+    if (rc == GB_OK && mem == GB_HOST && nq) cu(cudaMemcpyAsync(out, dout, nq * es, cudaMemcpyDeviceToHost, s), "D2H");
+    u64 bad = ~0ull;
+    if (rc == GB_OK && d_bad) {
+        cu(cudaMemcpyAsync(&bad, d_bad, sizeof(u64), cudaMemcpyDeviceToHost, s), "D2H");
+        cu(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+    }
+    for (void* p : {dk, dc, dx, dout, (void*)d_bad})
+        if (p) cudaFreeAsync(p, s);
+    if (mem == GB_HOST) cu(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+    if (rc == GB_OK && bad != ~0ull) {
+        if (first_invalid) *first_invalid = (int64_t)bad;
+        rc = fail(GB_ERR_INVALID_LOCATION, "BoundsError");
+    }
+    return rc;
+}
+
 // ---- restrict / prolong -----------------------------------------------------------------------
 int64_t gb_restrict_size(int64_t len) { return (len & 1) ? (len + 1) / 2 : len / 2 + 1; }
 int gb_prolong_size(int64_t n, int64_t len, int64_t* newlen) {
@@ -814,6 +872,36 @@ int gb_prolong(int dtype, int ndim, const int64_t* dims, const void* in, int dim
         Ctx* x = (Ctx*)c;
         return prolong_device(x->dtype, x->ndim, x->dims, i, x->dim, x->len, o, st);
     }, &ctx);
+}
+
+// restrictb / restrict_extrap / prolongb (src/restrict_prolong.jl:187-320): the plain operator, then the edge planes
+static int edge_variant(int variant, int dtype, int ndim, const int64_t* dims, const void* in, int dim, double scale, int64_t len, void* out, int mem,
+                        void* stream) {
+    if (!ok_dtype(dtype) || ndim < 1 || !dims || !in || !out) return fail(GB_ERR_ARG, "bad arguments");
+    if (dim < 0 || dim >= ndim) return fail(GB_ERR_ARG, "dim out of range");
+    if (variant == 3) {
+        int rc = gb_prolong_size(dims[dim], len, nullptr);
+        if (rc) return rc;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    pool_keep_memory();
+    if (mem == GB_DEVICE) return edge_variant_device(variant, dtype, ndim, (const i64*)dims, in, dim, scale, len, out, s);
+    i64 it = 1, ot = 1;
+    for (int d = 0; d < ndim; d++) { it *= dims[d]; ot *= (d == dim) ? (variant == 3 ? len : gb_restrict_size(dims[d])) : dims[d]; }
+    struct Ctx { int variant, dtype, ndim, dim; const i64* dims; double scale; i64 len; } ctx{variant, dtype, ndim, dim, (const i64*)dims, scale, len};
+    return mg_host(dtype, it, ot, in, out, s, [](void* c, const void* i, void* o, cudaStream_t st) {
+        Ctx* x = (Ctx*)c;
+        return edge_variant_device(x->variant, x->dtype, x->ndim, x->dims, i, x->dim, x->scale, x->len, o, st);
+    }, &ctx);
+}
+int gb_restrictb(int dtype, int ndim, const int64_t* dims, const void* in, int dim, double scale, void* out, int mem, void* stream) {
+    return edge_variant(1, dtype, ndim, dims, in, dim, scale, 0, out, mem, stream);
+}
+int gb_restrict_extrap(int dtype, int ndim, const int64_t* dims, const void* in, int dim, double scale, void* out, int mem, void* stream) {
+    return edge_variant(2, dtype, ndim, dims, in, dim, scale, 0, out, mem, stream);
+}
+int gb_prolongb(int dtype, int ndim, const int64_t* dims, const void* in, int dim, int64_t len, void* out, int mem, void* stream) {
+    return edge_variant(3, dtype, ndim, dims, in, dim, 1.0, len, out, mem, stream);
 }
 
 int gb_restrict_slab(int dtype, int ndim, const int64_t* dims, const void* in, int dim, double scale, int64_t global_len, int64_t in_first,

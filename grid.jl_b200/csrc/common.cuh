@@ -127,6 +127,7 @@ int pad1_device(int dtype, int ndim, const i64* dims, const void* in, double fil
 // ---- restrict / prolong (multigrid.cu) ------------------------------------------------------------
 int restrict_device(int dtype, int ndim, const i64* dims, const void* in, int dim, double scale, void* out, cudaStream_t s);
 int prolong_device(int dtype, int ndim, const i64* dims, const void* in, int dim, i64 len, void* out, cudaStream_t s);
+int edge_variant_device(int variant, int dtype, int ndim, const i64* dims, const void* in, int dim, double scale, i64 len, void* out, cudaStream_t s);
 int restrict_slab_device(int dtype, int ndim, const i64* dims, const void* in, int dim, double scale, i64 L, i64 in_first, i64 out_first, i64 ocount, void* out,
                          cudaStream_t s);
 int prolong_slab_device(int dtype, int ndim, const i64* dims, const void* in, int dim, i64 n, i64 len, i64 in_first, i64 out_first, i64 ocount, void* out,
@@ -134,6 +135,8 @@ int prolong_slab_device(int dtype, int ndim, const i64* dims, const void* in, in
 int restrict3_device(int dtype, const i64* dims, const void* in, double scale, void* out, cudaStream_t s);
 int prolong3_device(int dtype, const i64* dims, const void* in, const i64* odims, void* out, cudaStream_t s);
 
+int irregular_device(int dtype, const void* knots, const void* coefs, i64 n, int bc, int it, double fill, const void* x, void* out, i64 nq, u64* first_invalid,
+                     cudaStream_t s);
 int synth_device(int dtype, void* out, i64 n, u64 seed, double lo, double hi, i64 first, cudaStream_t s);
 
 }  // namespace gb

@@ -12,6 +12,7 @@
 // intermediate to T exactly where the staged reference stores it, so the result is bit-identical
 // to the three separate passes while the fine grid is read from HBM once.
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -164,6 +165,79 @@ template <typename T> int prolong_slab_impl(int ndim, const i64* dims, const T* 
 template <typename T> int prolong_impl(int ndim, const i64* dims, const T* in, int dim, i64 len, T* out, cudaStream_t s) {
     if (dim < 0 || dim >= ndim) return fail(GB_ERR_ARG, "prolong: dim out of range");
     return prolong_slab_impl<T>(ndim, dims, in, dim, dims[dim], len, 0, 0, len, out, s);
+}
+
+// ---- edge-corrected variants: restrictb / prolongb / restrict_extrap (src/restrict_prolong.jl:187-320) ----
+// The reference computes the plain operator and then overwrites the two edge planes along `dim`
+// (prolongb: the two outermost planes on each side), in a fixed assignment order; this kernel does
+// the same on the finished output, one thread per 1-D line, same order (so degenerate short lines,
+// where the planes coincide, end up with the value the reference's last assignment leaves).
+// Constants are formed as the reference forms them: b = scale/sqrt(3) (Float64) converted to T,
+// a = 2*b in T; (3/4)*x promotes a Float32 x to Float64 before the sum is stored.
+enum { EDGE_RESTRICTB = 1, EDGE_RESTRICT_EXTRAP = 2, EDGE_PROLONGB = 3 };
+template <typename T> struct EdgeCoef { T a, b, c2, c3, s; };
+template <typename T> __device__ __forceinline__ T three_quarters_plus(T bx, T y) {  // b*A[i] + (3/4)*A[j]
+    if constexpr (sizeof(T) == 4) return (T)((double)bx + 0.75 * (double)y);
+    else return bx + 0.75 * y;
+}
+template <typename T> __global__ void __launch_bounds__(256) edge_kernel(int kind, const T* __restrict__ A, T* __restrict__ O, i64 inner, i64 Lin, i64 Lout, i64 outer,
+                                                                         EdgeCoef<T> c) {
+    const i64 total = inner * outer, st = inner;
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+        const i64 lo = e % inner, o = e / inner;
+        const T* x = A + lo + o * inner * Lin;
+        T* y = O + lo + o * inner * Lout;
+        const T x0 = x[0], x1 = x[st], xe = x[(Lin - 1) * st], xe1 = x[(Lin - 2) * st];
+        if (kind == EDGE_RESTRICTB) {  // :196-224
+            y[0] = c.a * x0 + c.b * x1;
+            y[(Lout - 1) * st] = c.a * xe + c.b * xe1;
+        } else if (kind == EDGE_RESTRICT_EXTRAP) {  // :287-313
+            if (Lin & 1) {
+                y[0] = c.c2 * x0;
+                y[(Lout - 1) * st] = c.c2 * xe;
+            } else {
+                y[0] = c.c3 * x0 - c.s * x1;
+                y[(Lout - 1) * st] = c.c3 * xe - c.s * xe1;
+            }
+        } else {  // EDGE_PROLONGB :231-267
+            if (Lout & 1) {
+                y[0] = c.a * x0;
+                y[st] = c.b * x0 + x1 / (T)2;
+                y[(Lout - 1) * st] = c.a * xe;
+                y[(Lout - 2) * st] = c.b * xe + xe1 / (T)2;
+            } else {
+                y[0] = c.a * x0 + x1 / (T)4;
+                y[st] = three_quarters_plus<T>(c.b * x0, x1);
+                y[(Lout - 1) * st] = c.a * xe + xe1 / (T)4;
+                y[(Lout - 2) * st] = three_quarters_plus<T>(c.b * xe, xe1);
+            }
+        }
+    }
+}
+template <typename T> int edge_impl(int kind, int ndim, const i64* dims, const T* in, int dim, double scale, i64 Lout, T* out, cudaStream_t s) {
+    if (dim < 0 || dim >= ndim) return fail(GB_ERR_ARG, "dim out of range");
+    const i64 Lin = dims[dim];
+    if (Lin < 2) return fail(GB_ERR_ARG, "the edge-corrected operators need at least 2 samples along the dimension");
+    i64 inner = 1, outer = 1;
+    for (int d = 0; d < dim; d++) inner *= dims[d];
+    for (int d = dim + 1; d < ndim; d++) outer *= dims[d];
+    if (inner * outer == 0) return GB_OK;
+    EdgeCoef<T> c;
+    const T sc = (T)scale;  // the reference's default scale is one(T)
+    c.s = sc;
+    c.c2 = (T)2 * sc;
+    c.c3 = (T)3 * sc;
+    if (kind == EDGE_PROLONGB) {
+        if (Lout & 1) { c.b = (T)(1.0 / std::sqrt(3.0)); c.a = (T)2 * c.b; }
+        else { c.b = (T)(1.0 / (2.0 * std::sqrt(2.0))); c.a = (T)3 * c.b; }
+    } else {
+        if (Lin & 1) { c.b = (T)((double)sc / std::sqrt(3.0)); c.a = (T)2 * c.b; }
+        else { c.b = (T)((double)sc / (2.0 * std::sqrt(2.0))); c.a = (T)3 * c.b; }
+    }
+    edge_kernel<T><<<grid_for(inner * outer, 256), 256, 0, s>>>(kind, in, out, inner, Lin, Lout, outer, c);
+    count_launch();
+    GB_CUDA(cudaGetLastError());
+    return GB_OK;
 }
 
 // ---- fused 3-D restrict -----------------------------------------------------------------------
@@ -445,6 +519,22 @@ int restrict_device(int dtype, int ndim, const i64* dims, const void* in, int di
     if (dtype == GB_F64) return restrict_impl<double>(ndim, dims, (const double*)in, dim, scale, (double*)out, s);
     if (dtype == GB_F32) return restrict_impl<float>(ndim, dims, (const float*)in, dim, scale, (float*)out, s);
     return fail(GB_ERR_ARG, "bad dtype");
+}
+// variant: 1 restrictb, 2 restrict_extrap (restrict, then the edge planes); 3 prolongb (prolong, then the edge planes)
+int edge_variant_device(int variant, int dtype, int ndim, const i64* dims, const void* in, int dim, double scale, i64 len, void* out, cudaStream_t s) {
+    if (dim < 0 || dim >= ndim) return fail(GB_ERR_ARG, "dim out of range");
+    int rc;
+    i64 Lout;
+    if (variant == EDGE_PROLONGB) {
+        Lout = len;
+        rc = prolong_device(dtype, ndim, dims, in, dim, len, out, s);
+    } else {
+        Lout = rsize(dims[dim]);
+        rc = restrict_device(dtype, ndim, dims, in, dim, scale, out, s);
+    }
+    if (rc) return rc;
+    if (dtype == GB_F64) return edge_impl<double>(variant, ndim, dims, (const double*)in, dim, scale, Lout, (double*)out, s);
+    return edge_impl<float>(variant, ndim, dims, (const float*)in, dim, scale, Lout, (float*)out, s);
 }
 int prolong_device(int dtype, int ndim, const i64* dims, const void* in, int dim, i64 len, void* out, cudaStream_t s) {
     if (dtype == GB_F64) return prolong_impl<double>(ndim, dims, (const double*)in, dim, len, (double*)out, s);

@@ -39,7 +39,8 @@ enum { GB_F32 = 0, GB_F64 = 1 };
 /* src/boundaryconditions.jl:5-12 */
 enum { GB_BC_NIL = 0, GB_BC_NAN = 1, GB_BC_NA = 2, GB_BC_REFLECT = 3, GB_BC_PERIODIC = 4, GB_BC_NEAREST = 5, GB_BC_FILL = 6 };
 /* src/interpflags.jl:4-7 (npoints = order+1, src/interp.jl:579-582) */
-enum { GB_NEAREST = 0, GB_LINEAR = 1, GB_QUADRATIC = 2, GB_CUBIC = 3 };
+enum { GB_NEAREST = 0, GB_LINEAR = 1, GB_QUADRATIC = 2, GB_CUBIC = 3,
+       GB_FORWARD = 4, GB_BACKWARD = 5 /* InterpForward / InterpBackward: gb_interp_irregular only */ };
 enum { GB_OUT_VAL = 1, GB_OUT_GRAD = 2, GB_OUT_HESS = 4 };
 enum { GB_HOST = 0, GB_DEVICE = 1 };
 enum {
@@ -147,6 +148,17 @@ int gb_eval_soa(const gb_grid* g, int out_mask, int64_t nq, const void* const* x
 int gb_eval_outer(const gb_grid* g, const int64_t* lens, const void* const* vecs, int xdtype,
                   const double* affine, void* out, int mem, int flags, void* stream);
 
+/* ---- InterpIrregular (src/interp.jl:318-377) -----------------------------------------------------
+   1-D interpolation on `n` sorted, non-uniform knots: out[q] = G[x[q]] for G = InterpIrregular(knots,
+   samples, BC, IT).  order: GB_FORWARD, GB_BACKWARD, GB_NEAREST or GB_LINEAR; bc: GB_BC_NIL, GB_BC_NAN,
+   GB_BC_NA, GB_BC_FILL (fill value `fill`; NaN for the BC-type constructor) or GB_BC_NEAREST
+   (BCreflect / BCperiodic: GB_ERR_UNSUPPORTED like the reference's error, :335-337).  Knots, samples,
+   queries and outputs share one element type.  Unsorted knots: GB_ERR_ARG ("Coordinates must be supplied
+   in increasing order").  BCnil outside the knots: outputs NaN, GB_ERR_INVALID_LOCATION (the reference's
+   BoundsError) with the first offending query in *first_invalid. */
+int gb_interp_irregular(int dtype, int64_t n, const void* knots, const void* samples, int bc, int order, double fill,
+                        int64_t nq, const void* x, void* out, int mem, int64_t* first_invalid, void* stream);
+
 /* ---- restrict / prolong ------------------------------------------------------------------- */
 int64_t gb_restrict_size(int64_t len);                           /* src/restrict_prolong.jl:334 */
 int gb_prolong_size(int64_t n, int64_t len, int64_t* newlen);    /* :322-332, GB_ERR_PROLONG_SIZE on mismatch */
@@ -156,6 +168,16 @@ int gb_restrict(int dtype, int ndim, const int64_t* dims, const void* in, int di
 /* prolong(A, dim, len) (:10-48); out has dims with dims[dim] -> len */
 int gb_prolong(int dtype, int ndim, const int64_t* dims, const void* in, int dim, int64_t len, void* out,
                int mem, void* stream);
+/* "Balanced" and edge-extrapolating variants (src/restrict_prolong.jl:187-320): the plain operator
+   followed by the reference's overwrite of the edge planes along `dim` (constants 1/sqrt(3), 2/sqrt(3),
+   1/(2 sqrt(2)), 3/(2 sqrt(2)) formed as the reference forms them).  Same array conventions as
+   gb_restrict / gb_prolong; the extent along `dim` must be >= 2. */
+int gb_restrictb(int dtype, int ndim, const int64_t* dims, const void* in, int dim, double scale, void* out, int mem,
+                 void* stream);
+int gb_restrict_extrap(int dtype, int ndim, const int64_t* dims, const void* in, int dim, double scale, void* out,
+                       int mem, void* stream);
+int gb_prolongb(int dtype, int ndim, const int64_t* dims, const void* in, int dim, int64_t len, void* out, int mem,
+                void* stream);
 /* Slab forms for a grid sharded along `dim`: `in` holds planes
  * [in_first, in_first + dims[dim]) of an array whose full extent along dim is global_len (restrict)
  * / global_n (prolong); the call writes output planes [out_first, out_first + out_count) of the

@@ -938,6 +938,120 @@ template <typename T> int prolong_impl(const T* A, int N, const i64* dims, int d
     return ERR_OK;
 }
 
+// restrictb (src/restrict_prolong.jl:196-224), restrict_extrap (:287-313), prolongb (:231-267):
+// the plain operator, then the edge planes along `dim` overwritten in the reference's assignment
+// order.  variant 1 restrictb, 2 restrict_extrap, 3 prolongb.  Constants as the reference forms them:
+// `local a::T, b::T; b = scale/sqrt(3); a = 2*b` (Float64 quotient converted to T, product in T);
+// `(3/4)*x` promotes a Float32 x to Float64 and the sum is rounded when stored.
+template <typename T> inline T q34(T bx, T y) {
+    if (sizeof(T) == 4) return (T)((double)bx + 0.75 * (double)y);
+    return (T)(bx + (T)0.75 * y);
+}
+template <typename T> int edge_variant_impl(int variant, const T* A, int N, const i64* dims, int dim, double scale, i64 len, T* O, int nthreads) {
+    if (dim < 0 || dim >= N) return ERR_ARG;
+    const i64 Lin = dims[dim];
+    if (Lin < 2) return ERR_ARG;  // the reference reads A[index+Astep]
+    int rc;
+    i64 Lout;
+    if (variant == 3) { Lout = len; rc = prolong_impl<T>(A, N, dims, dim, len, O, nthreads); }
+    else { Lout = restrict_size1(Lin); rc = restrict_impl<T>(A, N, dims, dim, scale, O, nthreads); }
+    if (rc) return rc;
+    i64 inner = 1, outer = 1;
+    for (int d = 0; d < dim; d++) inner *= dims[d];
+    for (int d = dim + 1; d < N; d++) outer *= dims[d];
+    const T sc = (T)scale;
+    T a, b;
+    if (variant == 3) {
+        if (Lout & 1) { b = (T)(1.0 / std::sqrt(3.0)); a = (T)2 * b; }
+        else { b = (T)(1.0 / (2.0 * std::sqrt(2.0))); a = (T)3 * b; }
+    } else {
+        if (Lin & 1) { b = (T)((double)sc / std::sqrt(3.0)); a = (T)2 * b; }
+        else { b = (T)((double)sc / (2.0 * std::sqrt(2.0))); a = (T)3 * b; }
+    }
+    const i64 st = inner;
+    for (i64 o = 0; o < outer; o++)
+        for (i64 i = 0; i < inner; i++) {
+            const T* x = A + i + o * inner * Lin;
+            T* y = O + i + o * inner * Lout;
+            const i64 e = (Lin - 1) * st, er = (Lout - 1) * st;
+            if (variant == 1) {
+                y[0] = a * x[0] + b * x[st];
+                y[er] = a * x[e] + b * x[e - st];
+            } else if (variant == 2) {
+                if (Lin & 1) {
+                    y[0] = ((T)2 * sc) * x[0];
+                    y[er] = ((T)2 * sc) * x[e];
+                } else {
+                    y[0] = ((T)3 * sc) * x[0] - sc * x[st];
+                    y[er] = ((T)3 * sc) * x[e] - sc * x[e - st];
+                }
+            } else if (Lout & 1) {
+                y[0] = a * x[0];
+                y[st] = b * x[0] + x[st] / (T)2;
+                y[er] = a * x[e];
+                y[er - st] = b * x[e] + x[e - st] / (T)2;
+            } else {
+                y[0] = a * x[0] + x[st] / (T)4;
+                y[st] = q34<T>(b * x[0], x[st]);
+                y[er] = a * x[e] + x[e - st] / (T)4;
+                y[er - st] = q34<T>(b * x[e], x[e - st]);
+            }
+        }
+    return ERR_OK;
+}
+
+// InterpIrregular (src/interp.jl:318-377): 1-D, sorted knots.  it: 0 nearest, 1 linear, 4 forward, 5 backward.
+// Returns ERR_INVALID_LOCATION (BoundsError under BCnil) with the first offending query; outputs NaN there.
+template <typename T> inline bool jl_isless(T a, T b) {  // Julia isless: NaN last, -0.0 < +0.0
+    const bool an = a != a, bn = b != b;
+    if (an || bn) return !an && bn;
+    if (a == (T)0 && b == (T)0) return std::signbit(a) && !std::signbit(b);
+    return a < b;
+}
+template <typename T> int irregular_impl(const T* g, const T* coefs, i64 n, int bc, int it, double fill, const T* x, T* out, i64 nq, i64* first_invalid) {
+    if (n < 1) return ERR_ARG;
+    if (bc == BC_REFLECT || bc == BC_PERIODIC) return ERR_UNSUPPORTED;  // :335-337
+    for (i64 k = 0; k + 1 < n; k++)
+        if (jl_isless(g[k + 1], g[k])) return ERR_ARG;  // issorted, :340-342
+    const T fv = (bc == BC_FILL) ? (T)fill : std::numeric_limits<T>::quiet_NaN();  // :348, :351-355
+    i64 bad = -1;
+    for (i64 q = 0; q < nq; q++) {
+        const T xq = x[q];
+        i64 i;  // 1-based, :352
+        if (xq == g[0]) i = 2;
+        else {  // searchsortedfirst(g, x)
+            i = n + 1;
+            i64 lo = 0, hi = n + 1;
+            while (lo < hi - 1) {
+                const i64 m = (lo + hi) >> 1;
+                if (jl_isless(g[m - 1], xq)) lo = m;
+                else hi = m;
+            }
+            i = hi;
+        }
+        T v;
+        if (i == 1 || i == n + 1) {
+            if (bc == BC_NEAREST) v = (i == 1) ? coefs[0] : coefs[n - 1];  // :361-365
+            else {
+                v = fv;
+                if (bc == BC_NIL && bad < 0) bad = q;  // throw(BoundsError()), :356-360
+            }
+        } else {  // _interpu, :371-377
+            const T g0 = g[i - 2], g1 = g[i - 1], c0 = coefs[i - 2], c1 = coefs[i - 1];
+            if (it == 4) v = c1;
+            else if (it == 5) v = c0;
+            else if (it == IT_NEAREST) v = (xq - g0 < g1 - xq) ? c0 : c1;
+            else {
+                const T f = (xq - g0) / (g1 - g0);
+                v = ((T)1 - f) * c0 + f * c1;
+            }
+        }
+        out[q] = v;
+    }
+    if (first_invalid) *first_invalid = bad;
+    return bad >= 0 ? ERR_INVALID_LOCATION : ERR_OK;
+}
+
 // Synthetic inputs: u(splitmix64(seed + k)) in [0,1) from the top 53 bits.
 inline uint64_t splitmix64(uint64_t z) {
     z += 0x9E3779B97F4A7C15ull;
@@ -1066,6 +1180,20 @@ int oracle_restrict(int dtype, const void* A, int N, const int64_t* dims, int di
 int oracle_prolong(int dtype, const void* A, int N, const int64_t* dims, int dim, int64_t len, void* P, int nthreads) {
     if (dtype == 1) return prolong_impl<double>((const double*)A, N, dims, dim, len, (double*)P, nthreads);
     if (dtype == 0) return prolong_impl<float>((const float*)A, N, dims, dim, len, (float*)P, nthreads);
+    return ERR_ARG;
+}
+
+int oracle_edge_variant(int variant, int dtype, const void* A, int N, const int64_t* dims, int dim, double scale, int64_t len, void* O, int nthreads) {
+    if (variant < 1 || variant > 3) return ERR_ARG;
+    if (dtype == 1) return edge_variant_impl<double>(variant, (const double*)A, N, dims, dim, scale, len, (double*)O, nthreads);
+    if (dtype == 0) return edge_variant_impl<float>(variant, (const float*)A, N, dims, dim, scale, len, (float*)O, nthreads);
+    return ERR_ARG;
+}
+
+int oracle_irregular(int dtype, const void* g, const void* coefs, int64_t n, int bc, int it, double fill, const void* x, void* out, int64_t nq,
+                     int64_t* first_invalid) {
+    if (dtype == 1) return irregular_impl<double>((const double*)g, (const double*)coefs, n, bc, it, fill, (const double*)x, (double*)out, nq, first_invalid);
+    if (dtype == 0) return irregular_impl<float>((const float*)g, (const float*)coefs, n, bc, it, fill, (const float*)x, (float*)out, nq, first_invalid);
     return ERR_ARG;
 }
 

@@ -200,6 +200,55 @@ def prolong(A, dim, length, nthreads=0):
     return P
 
 
+def _edge(variant, A, dim, scale, length):
+    A = _f(A)
+    shp = list(A.shape)
+    shp[dim] = int(length) if variant == 3 else restrict_size(shp[dim])
+    out = np.empty(shp, dtype=A.dtype, order="F")
+    rc = lib().oracle_edge_variant(variant, _dt(A), _p(A), A.ndim, _i64(A.shape), dim, C.c_double(scale), C.c_int64(length), _p(out), 0)
+    if rc:
+        raise OracleError(rc)
+    return out
+
+
+def restrictb(A, dim, scale=1.0):
+    """restrictb(A, dim, scale), 0-based dim (src/restrict_prolong.jl:196-224)."""
+    return _edge(1, A, dim, scale, 0)
+
+
+def restrict_extrap(A, dim, scale=1.0):
+    """restrict_extrap(A, dim, scale), 0-based dim (:287-313)."""
+    return _edge(2, A, dim, scale, 0)
+
+
+def prolongb(A, dim, length):
+    """prolongb(A, dim, len), 0-based dim (:231-267)."""
+    return _edge(3, A, dim, 1.0, length)
+
+
+IRR_ORDER = {"nearest": 0, "linear": 1, "forward": 4, "backward": 5}
+
+
+def irregular(knots, samples, bc, it, x, fill=float("nan"), raise_invalid=True):
+    """InterpIrregular(knots, samples, BC, IT)[x] for a vector x (src/interp.jl:318-377).  All arrays of one
+    float type.  Returns (values, first_invalid)."""
+    g = np.ascontiguousarray(knots)
+    dt = g.dtype if g.dtype in (np.float32, np.float64) else np.dtype(np.float64)
+    g = np.ascontiguousarray(g, dtype=dt)
+    c = np.ascontiguousarray(samples, dtype=dt)
+    x = np.ascontiguousarray(np.atleast_1d(x), dtype=dt)
+    out = np.empty(x.shape[0], dtype=dt)
+    bad = C.c_int64(-1)
+    rc = lib().oracle_irregular(_dt(g), _p(g), _p(c), C.c_int64(g.shape[0]), BC[bc], IRR_ORDER[it], C.c_double(fill), _p(x), _p(out),
+                                C.c_int64(x.shape[0]), C.byref(bad))
+    if rc == ERR_INVALID_LOCATION:
+        if raise_invalid:
+            raise OracleError(rc, f"BoundsError (query {bad.value})")
+    elif rc:
+        raise OracleError(rc)
+    return out, bad.value
+
+
 def restrict_flags(A, flags, scale=1.0):
     """restrict(A, flag[, scale]) via mapdim (src/utilities.jl:7-20); flags: (ndims, ncols) bools."""
     flags = np.atleast_2d(np.asarray(flags, dtype=bool).T).T if np.ndim(flags) == 1 else np.asarray(flags, dtype=bool)

@@ -542,3 +542,68 @@ def test_multivalued_lowlevel_spectra_example(gb, oracle):
         for qi in (0, 5, 300):
             ref = oracle.lowlevel(np.ascontiguousarray(co[..., c]), "cubic", "nil", X[qi], hess=False)
             assert spec[qi, c] == ref[0]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", [(9,), (8,), (2,), (3,), (7, 10), (6, 5, 9), (4, 5, 6, 3)])
+def test_balanced_and_extrapolating_variants(gb, oracle, dtype, shape):
+    """(f)-2: restrictb / restrict_extrap / prolongb (src/restrict_prolong.jl:187-320) -- the plain operator
+    with the reference's edge planes; bit-identical to the oracle's restatement, every dim, host and device."""
+    import torch
+
+    rng = np.random.default_rng(47)
+    A = np.asfortranarray(rng.standard_normal(shape).astype(dtype))
+    for d in range(len(shape)):
+        for scale in (1.0, 0.5):
+            assert same(gb.restrictb(A, d + 1, scale), oracle.restrictb(A, d, scale))
+            assert same(gb.restrict_extrap(A, d + 1, scale), oracle.restrict_extrap(A, d, scale))
+        R = oracle.restrictb(A, d, 1.0)
+        assert same(gb.prolongb(R, d + 1, shape[d]), oracle.prolongb(R, d, shape[d]))
+    # device arrays and the mapdim forms
+    Ad = gb.jl_from_numpy(A)
+    flags = [True] * len(shape)
+    ref = A
+    for d in range(len(shape)):
+        ref = oracle.restrictb(ref, d, 1.0)
+    assert same(gb.jl_to_numpy(gb.restrictb(Ad, flags)), ref) and same(gb.restrictb(A, flags), ref)
+    up = ref
+    for d in range(len(shape)):
+        if shape[d] > up.shape[d]:  # :274 -- prolong only where the target is larger
+            up = oracle.prolongb(up, d, shape[d])
+    assert same(gb.prolongb(ref, list(shape)), up)
+    with pytest.raises(gb.ErrorException):
+        gb.prolongb(ref, 1, shape[0] + 5)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("it", ["forward", "backward", "nearest", "linear"])
+@pytest.mark.parametrize("bc", ["nil", "nan", "na", "fill", "nearest"])
+def test_interp_irregular(gb, oracle, dtype, it, bc):
+    """(f)-4: InterpIrregular (src/interp.jl:318-377): binary search on sorted knots, bit-identical to the
+    oracle's restatement for every (BC, IT), including hits on knots, the x == g[1] rule, duplicates,
+    out-of-range points, NaN queries and signed zeros."""
+    import torch
+
+    rng = np.random.default_rng(53)
+    IT = dict(forward=gb.InterpForward, backward=gb.InterpBackward, nearest=gb.InterpNearest, linear=gb.InterpLinear)[it]
+    BC = tags(gb)[0]
+    knots = np.sort(np.concatenate([rng.uniform(-3, 7, 40), [0.0, -0.0, 2.5, 2.5]])).astype(dtype)
+    vals = rng.standard_normal(knots.shape[0]).astype(dtype)
+    x = np.concatenate([rng.uniform(-4, 8, 3000), knots.astype(np.float64), [knots[0], knots[-1], -0.0, 0.0, np.nan, np.inf, -np.inf,
+                                                                           np.nextafter(knots[0], -np.inf), np.nextafter(knots[-1], np.inf)]]).astype(dtype)
+    fill = 4.5
+    G = gb.InterpIrregular(knots, vals, fill if bc == "fill" else BC[bc], IT)
+    ov, obad = oracle.irregular(knots, vals, bc, it, x, fill=fill, raise_invalid=False)
+    if bc == "nil":
+        with pytest.raises(gb.BoundsError, match=rf"query {obad}\b"):
+            G[x]
+        inside = ~np.isnan(ov)
+        x = x[inside]
+        ov, obad = oracle.irregular(knots, vals, bc, it, x, fill=fill)
+    assert same(G[x], ov)
+    assert same(G[torch.from_numpy(x).cuda()].cpu().numpy(), ov)
+    assert G[float(x[3])] == ov[3]
+    with pytest.raises(gb.ErrorException):
+        gb.InterpIrregular(knots[::-1].copy(), vals, gb.BCnan, IT)
+    with pytest.raises(gb.ErrorException):
+        gb.InterpIrregular(knots, vals, gb.BCperiodic, IT)

@@ -462,3 +462,42 @@ def test_extended_precision_truth_brackets_the_reference_arithmetic(oracle, bc, 
     eps = 2.220446049250313e-16
     assert np.all(np.abs(v - tv) <= 8 * eps * sv) and np.all(np.abs(g - tg) <= 8 * eps * sg)
     assert np.all(sv >= np.abs(tv) * (1 - 1e-12)) and np.all(sg >= np.abs(tg) * (1 - 1e-12))
+
+
+@pytest.mark.parametrize("L", [9, 10, 17, 32])
+def test_balanced_restrict_prolong_uses_every_point_equally(oracle, L):
+    """src/restrict_prolong.jl:189-195: with the "b" variants sum(P*R, 1) is constant (the plain pair lets
+    the edges decay); restrict_extrap reproduces a linear ramp at the edges."""
+    n = oracle.restrict_size(L)
+    PRb = np.zeros((L, L))
+    PR = np.zeros((L, L))
+    for k in range(L):
+        e = np.zeros(L)
+        e[k] = 1.0
+        PRb[:, k] = oracle.prolongb(oracle.restrictb(e, 0, 1.0), 0, L)
+        PR[:, k] = oracle.prolong(oracle.restrict(e, 0, 1.0), 0, L)
+    cs = PRb.sum(axis=0)
+    assert np.allclose(cs, cs[0], rtol=0, atol=1e-14)
+    cp = PR.sum(axis=0)
+    assert abs(cp[0] - cp[L // 2]) > 0.1  # the plain pair does not
+    ramp = np.arange(1.0, L + 1.0)
+    r = oracle.restrict_extrap(ramp, 0, 0.5)  # scale 1/2: restriction of a ramp is a ramp of half the samples
+    assert r.shape == (n,)
+    d = np.diff(r)
+    assert np.allclose(d, d[0], rtol=0, atol=1e-12)
+
+
+def test_interp_irregular_reference_semantics(oracle):
+    """src/interp.jl:351-377 by hand: knots [1,2,4,8], samples [10,20,40,80]."""
+    g, c = [1.0, 2.0, 4.0, 8.0], [10.0, 20.0, 40.0, 80.0]
+    x = [1.0, 1.5, 2.0, 3.0, 8.0, 0.5, 9.0]
+    lin, _ = oracle.irregular(g, c, "nan", "linear", x)
+    assert np.array_equal(lin[:5], [10.0, 15.0, 20.0, 30.0, 80.0]) and np.isnan(lin[5:]).all()
+    near, _ = oracle.irregular(g, c, "nearest", "nearest", x)
+    assert np.array_equal(near, [10.0, 20.0, 20.0, 40.0, 80.0, 10.0, 80.0])  # ties go to the upper knot (strict <, :373)
+    fwd, _ = oracle.irregular(g, c, "fill", "forward", x, fill=-1.0)
+    assert np.array_equal(fwd, [20.0, 20.0, 20.0, 40.0, 80.0, -1.0, -1.0])
+    bwd, _ = oracle.irregular(g, c, "fill", "backward", x, fill=-1.0)
+    assert np.array_equal(bwd, [10.0, 10.0, 10.0, 20.0, 40.0, -1.0, -1.0])
+    with pytest.raises(oracle.OracleError):
+        oracle.irregular(g, c, "nil", "linear", [0.0])
