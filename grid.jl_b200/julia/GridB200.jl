@@ -14,7 +14,8 @@ export BoundaryCondition, BCnil, BCnan, BCna, BCreflect, BCperiodic, BCnearest, 
        InterpType, InterpNearest, InterpLinear, InterpQuadratic, InterpCubic,
        AbstractInterpGrid, InterpGrid, CoordInterpGrid,
        valgrad, valgradhess, getindex!, valgrad!, valgradhess!,
-       interp_invert!, pad1, restrict, prolong, restrict_size, prolong_size
+       interp_invert!, pad1, restrict, prolong, restrict_size, prolong_size,
+       restrictb, restrict_extrap, prolongb, interp_channels!, InterpIrregular, InterpForward, InterpBackward
 
 const LIB = get(ENV, "GRIDB200_LIB", joinpath(@__DIR__, "..", "libgridb200.so"))
 
@@ -216,5 +217,82 @@ function prolong(A::Array, sz::Array{Int})
     end
     A
 end
+
+# ---- restrictb / restrict_extrap / prolongb (src/restrict_prolong.jl:187-320) ------------------------
+for (fname, sym) in ((:restrictb, :gb_restrictb), (:restrict_extrap, :gb_restrict_extrap))
+    @eval begin
+        function $fname(A::Array{T,N}, dim::Integer, scale::Real = one(T)) where {T<:Union{Float32,Float64},N}
+            sz = [size(A)...]; sz[dim] = restrict_size(sz[dim]); R = Array{T,N}(undef, sz...); dims = Int64[size(A)...]
+            GC.@preserve A R dims check(ccall(($(QuoteNode(sym)), LIB), Cint, (Cint, Cint, Ptr{Int64}, Ptr{Cvoid}, Cint, Cdouble, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+                dtcode(T), N, dims, A, dim - 1, Float64(scale), R, GB_HOST, C_NULL))
+            R
+        end
+        function $fname(A::Array, flag::Union{Array{Bool},BitArray}, scale::Real = one(eltype(A)))
+            ndims(A) == size(flag, 1) || error("Boolean flag must have as many rows as dimensions of A")
+            for j = 1:size(flag, 2), i = 1:size(flag, 1)
+                flag[i, j] && (A = $fname(A, i, scale))
+            end
+            A
+        end
+    end
+end
+function prolongb(A::Array{T,N}, dim::Integer, len::Integer) where {T<:Union{Float32,Float64},N}
+    sz = [size(A)...]; sz[dim] = prolong_size(sz[dim], len); P = Array{T,N}(undef, sz...); dims = Int64[size(A)...]
+    GC.@preserve A P dims check(ccall((:gb_prolongb, LIB), Cint, (Cint, Cint, Ptr{Int64}, Ptr{Cvoid}, Cint, Int64, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+        dtcode(T), N, dims, A, dim - 1, len, P, GB_HOST, C_NULL))
+    P
+end
+function prolongb(A::Array, sz::Array{Int})
+    ndims(A) == size(sz, 1) || error("Array of sizes must have as many rows as dimensions of A")
+    for j = 1:size(sz, 2), i = 1:size(sz, 1)
+        sz[i, j] > size(A, i) && (A = prolongb(A, i, sz[i, j]))
+    end
+    A
+end
+
+# ---- multi-valued grids: the low-level interface, batched (README.md:151-209) -------------------------
+# interp_channels!(out, coefs, BC, IT, X): coefs has size (dims..., nchan) and was prepared with
+# interp_invert!(coefs, BC, IT, 1:N); X is N x nq in ARRAY index coordinates (what set_position takes);
+# out[c, q] = interp(ic, coefs, 1 + (c-1)*stride) after set_position(ic, BC, false, false, X[:, q]).
+function interp_channels!(out::Matrix{T}, coefs::Array{T}, ::Type{BC}, ::Type{IT}, X::Matrix{Float64}) where {T<:Union{Float32,Float64},BC,IT}
+    N = ndims(coefs) - 1; nchan = size(coefs, N + 1); dims = Int64[size(coefs)[1:N]...]
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve coefs dims check(ccall((:gb_grid_create_from_coefs_channels, LIB), Cint,
+        (Ref{Ptr{Cvoid}}, Cint, Cint, Ptr{Int64}, Int64, Ptr{Cvoid}, Cint, Cint, Cint, Cdouble, Cint, Ptr{Cvoid}),
+        h, dtcode(T), N, dims, nchan, coefs, GB_HOST, bccode(BC), itcode(IT), NaN, 1, C_NULL))
+    bad = Ref{Int64}(-1)
+    rc = GC.@preserve X out ccall((:gb_eval, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Int64, Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Cdouble}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Ref{Int64}, Ptr{Cvoid}),
+        h[], OUT_VAL, size(X, 2), X, 1, N, 1, C_NULL, out, C_NULL, C_NULL, GB_HOST, 0, bad, C_NULL)
+    ccall((:gb_grid_destroy, LIB), Cint, (Ptr{Cvoid},), h[])
+    check(rc, bad[])
+    out
+end
+
+# ---- InterpIrregular (src/interp.jl:318-377) -----------------------------------------------------------
+struct InterpForward <: InterpType end
+struct InterpBackward <: InterpType end
+itcode(::Type{InterpForward}) = 4; itcode(::Type{InterpBackward}) = 5
+struct InterpIrregular{T<:Union{Float32,Float64},BC<:BoundaryCondition,IT<:InterpType}
+    grid::Vector{T}
+    coefs::Vector{T}
+    fillval::T
+end
+function InterpIrregular(grid::Vector{T}, A::Vector{T}, ::Type{BC}, ::Type{IT}) where {T,BC<:BoundaryCondition,IT<:InterpType}
+    (BC == BCreflect || BC == BCperiodic) && error("Sorry, reflecting or periodic boundary conditions not yet supported")
+    issorted(grid) || error("Coordinates must be supplied in increasing order")
+    InterpIrregular{T,BC,IT}(copy(grid), copy(A), T(NaN))
+end
+InterpIrregular(grid::Vector{T}, A::Vector{T}, f::Number, ::Type{IT}) where {T,IT<:InterpType} = InterpIrregular{T,BCfill,IT}(copy(grid), copy(A), T(f))
+function getindex!(out::Vector{T}, G::InterpIrregular{T,BC,IT}, x::Vector{T}) where {T,BC,IT}
+    bad = Ref{Int64}(-1)
+    rc = GC.@preserve G x out ccall((:gb_interp_irregular, LIB), Cint,
+        (Cint, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cdouble, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ref{Int64}, Ptr{Cvoid}),
+        dtcode(T), length(G.grid), G.grid, G.coefs, bccode(BC), itcode(IT), Float64(G.fillval), length(x), x, out, GB_HOST, bad, C_NULL)
+    rc == 2 && throw(BoundsError(G.grid, bad[] + 1))   # src/interp.jl:356-360
+    check(rc)
+    out
+end
+Base.getindex(G::InterpIrregular{T}, x::Real) where {T} = getindex!(Vector{T}(undef, 1), G, T[x])[1]
 
 end # module
