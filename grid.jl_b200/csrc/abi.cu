@@ -389,9 +389,8 @@ struct EvalCall {
     i64 q0;
 };
 
-template <int N> int launch_n(const EvalCall& c, cudaStream_t s) {
+template <int N> void fill_params(const EvalCall& c, EvalParams<N>& p) {
     const gb_grid* g = c.g;
-    EvalParams<N> p;
     p.coefs = g->coefs;
     p.total = g->total;
     i64 str = 1;
@@ -416,6 +415,11 @@ template <int N> int launch_n(const EvalCall& c, cudaStream_t s) {
     p.cstride = g->total;
     p.perm = nullptr; p.work = nullptr; p.nwork = nullptr;
     for (int d = 0; d < N; d++) { p.tile[d] = 1; p.ntile[d] = 1; }
+}
+template <int N> int launch_n(const EvalCall& c, cudaStream_t s) {
+    const gb_grid* g = c.g;
+    EvalParams<N> p;
+    fill_params<N>(c, p);
     const int bcf = bc_family(g->bc);
 #define GB_CALL(T, O) return launch_eval_##T##_##O(p, bcf, c.outmode, c.flags, s)
 #define GB_ORDERS(TN)                                    \
@@ -439,6 +443,41 @@ template <int N> int launch_n(const EvalCall& c, cudaStream_t s) {
 #undef GB_ORDERS
 #undef GB_CALL
     return GB_ERR_ARG;
+}
+
+// separable tensor-product getindex: c.xp[d] = device vector of axis d, lens[d] its length
+template <int N> int launch_outer_n(const EvalCall& c, const i64* lens, void* out, cudaStream_t s) {
+    const gb_grid* g = c.g;
+    EvalParams<N> p;
+    fill_params<N>(c, p);
+    p.xqs = 1;
+    p.val = out;
+    const int bcf = bc_family(g->bc);
+#define GB_CALL(T, O) return launch_outer_##T##_##O(p, bcf, lens, c.flags, out, s)
+#define GB_ORDERS(TN)                                    \
+    switch (g->order) {                                  \
+    case GB_NEAREST: GB_CALL(TN, 0);                     \
+    case GB_LINEAR: GB_CALL(TN, 1);                      \
+    case GB_QUADRATIC: GB_CALL(TN, 2);                   \
+    case GB_CUBIC: GB_CALL(TN, 3);                       \
+    }
+    if (g->dtype == GB_F64) {
+        if constexpr (N == 1) { GB_ORDERS(double_1) }
+        if constexpr (N == 2) { GB_ORDERS(double_2) }
+        if constexpr (N == 3) { GB_ORDERS(double_3) }
+        if constexpr (N == 4) { if (g->order == GB_NEAREST) GB_CALL(double_4, 0); GB_CALL(double_4, 1); }
+    } else {
+        if constexpr (N == 1) { GB_ORDERS(float_1) }
+        if constexpr (N == 2) { GB_ORDERS(float_2) }
+        if constexpr (N == 3) { GB_ORDERS(float_3) }
+        if constexpr (N == 4) { if (g->order == GB_NEAREST) GB_CALL(float_4, 0); GB_CALL(float_4, 1); }
+    }
+#undef GB_ORDERS
+#undef GB_CALL
+    return GB_ERR_ARG;
+}
+static bool outer_separable(const gb_grid* g) {
+    return g->nchan == 1 && g->ndim <= MAXD && !(g->ndim == 4 && g->order >= GB_QUADRATIC);
 }
 
 int launch_generic(const EvalCall& c, cudaStream_t s) {
@@ -733,6 +772,40 @@ int gb_eval_outer(const gb_grid* g, const int64_t* lens, const void* const* vecs
             vptr[d] = dvec[d];
         } else
             vptr[d] = vecs[d];
+    }
+    if (outer_separable(g)) {  // weights / taps once per axis point, then a pure gather-contract kernel
+        void* dst = out;
+        if (mem == GB_HOST) {
+            GB_TRY(cudaMallocAsync(&d_out, (size_t)nq * es, s));
+            dst = d_out;
+        }
+        u64* d_bad = nullptr;
+        if (g->bc == GB_BC_NIL) {
+            GB_TRY(cudaMallocAsync((void**)&d_bad, sizeof(u64), s));
+            GB_TRY(cudaMemsetAsync(d_bad, 0xFF, sizeof(u64), s));
+        }
+        EvalCall call;
+        call.g = g; call.outmode = 0; call.flags = flags; call.xdtype = xdtype; call.affine = affine;
+        call.nq = nq; call.q0 = 0; call.xqs = 1; call.first_invalid = d_bad;
+        for (int d = 0; d < N; d++) call.xp[d] = vptr[d];
+        call.val = dst; call.grad = nullptr; call.hess = nullptr;
+        switch (N) {
+        case 1: rc = launch_outer_n<1>(call, (const i64*)lens, dst, s); break;
+        case 2: rc = launch_outer_n<2>(call, (const i64*)lens, dst, s); break;
+        case 3: rc = launch_outer_n<3>(call, (const i64*)lens, dst, s); break;
+        default: rc = launch_outer_n<4>(call, (const i64*)lens, dst, s); break;
+        }
+        if (rc == GB_OK && mem == GB_HOST) GB_TRY(cudaMemcpyAsync(out, d_out, (size_t)nq * es, cudaMemcpyDeviceToHost, s));
+        if (d_bad) {
+            u64 bad = ~0ull;
+            if (rc == GB_OK) {
+                GB_TRY(cudaMemcpyAsync(&bad, d_bad, sizeof(u64), cudaMemcpyDeviceToHost, s));
+                GB_TRY(cudaStreamSynchronize(s));
+            }
+            cudaFreeAsync(d_bad, s);
+            if (rc == GB_OK && bad != ~0ull) rc = fail(GB_ERR_INVALID_LOCATION, "Invalid location");
+        }
+        return cleanup(rc);
     }
     GB_TRY(cudaMallocAsync(&d_tab, sizeof(void*) * MAXG, s));
     GB_TRY(cudaMemcpyAsync(d_tab, vptr, sizeof(void*) * N, cudaMemcpyHostToDevice, s));

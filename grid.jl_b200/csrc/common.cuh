@@ -94,7 +94,9 @@ template <int N> struct EvalParams {
 
 // One entry per (dtype, N, order) -- eval_inst.cu; each dispatches on (bc family, output mode, flags).
 // outmode: 0 value, 1 value+gradient, 2 value+gradient+hessian.
-#define GB_DECL_EVAL(T, N, O) int launch_eval_##T##_##N##_##O(const EvalParams<N>& p, int bcf, int outmode, int flags, cudaStream_t s);
+#define GB_DECL_EVAL(T, N, O)                                                                                          \
+    int launch_eval_##T##_##N##_##O(const EvalParams<N>& p, int bcf, int outmode, int flags, cudaStream_t s);        \
+    int launch_outer_##T##_##N##_##O(const EvalParams<N>& p, int bcf, const i64* lens, int flags, void* out, cudaStream_t s);
 #define GB_DECL_EVAL_N(T, N) GB_DECL_EVAL(T, N, 0) GB_DECL_EVAL(T, N, 1) GB_DECL_EVAL(T, N, 2) GB_DECL_EVAL(T, N, 3)
 GB_DECL_EVAL_N(float, 1) GB_DECL_EVAL_N(float, 2) GB_DECL_EVAL_N(float, 3) GB_DECL_EVAL(float, 4, 0) GB_DECL_EVAL(float, 4, 1)
 GB_DECL_EVAL_N(double, 1) GB_DECL_EVAL_N(double, 2) GB_DECL_EVAL_N(double, 3) GB_DECL_EVAL(double, 4, 0) GB_DECL_EVAL(double, 4, 1)

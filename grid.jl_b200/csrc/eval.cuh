@@ -1394,6 +1394,136 @@ int launch_one(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     return GB_OK;
 }
 
+// ====================================================================================================
+// Tensor-product getindex(G, xs, ys, ...) (src/interp.jl:273-306): out[i1,i2,...] = G[xs[i1], ys[i2], ...].
+// Separable set-up: the tap coordinates, the wrap flag and the value weights of an axis point depend on
+// that axis only, so they are computed once per axis point (outer_table_kernel: O(sum n_d) coordinate
+// work instead of O(prod n_d)) and the main kernel only combines table rows and contracts -- in the
+// reference's order, so the result is bit-identical to evaluating the expanded query list.
+template <int N> struct OuterTables {
+    i64 lens[N];
+    const int* tap[N];           // [n_d][L] 0-based tap coordinates
+    const void* w[N];            // [n_d][L] value weights (T)
+    const unsigned char* flg[N];  // bit 0 valid, bit 1 iswrap
+};
+template <typename T, int N, int ORDER, int BCF>
+__global__ void __launch_bounds__(256) outer_table_kernel(const EvalParams<N> p, int d, i64 n, int* __restrict__ tap, T* __restrict__ w, unsigned char* __restrict__ flg) {
+    constexpr int L = ORDER + 1;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const T x = index_coord<T, N>(p, d, load_raw<N>(p, d, i));
+        int c[L];
+        T dx;
+        bool iswrap;
+        const bool valid = dim_taps<T, ORDER, BCF>(x, p.len[d], c, dx, iswrap);
+        T wv[L], g[L], h[L];
+        weights<ORDER, false, false, false>(dx, wv, g, h);
+#pragma unroll
+        for (int k = 0; k < L; k++) { tap[i * L + k] = c[k]; w[i * L + k] = wv[k]; }
+        flg[i] = (unsigned char)((valid ? 1 : 0) | (iswrap ? 2 : 0));
+    }
+}
+template <typename T, int N, int ORDER, int BCF, bool FAST>
+__global__ void __launch_bounds__(256, 2) outer_eval_kernel(const EvalParams<N> p, const OuterTables<N> t, T* __restrict__ out, i64 nq) {
+    constexpr int L = ORDER + 1;
+    constexpr bool GUARD = (ORDER == GB_LINEAR) || (BCF == BCF_NIL && ORDER == GB_CUBIC);
+    for (i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (i64)gridDim.x * blockDim.x) {
+        i64 rem = q, idx[N];
+        bool valid = true, anywrap = false;
+        int c[N][L];
+        T w[3][N][L];
+#pragma unroll
+        for (int d = 0; d < N; d++) {
+            idx[d] = rem % t.lens[d];
+            rem /= t.lens[d];
+            const unsigned char f = __ldg(t.flg[d] + idx[d]);
+            valid = valid && (f & 1);
+            anywrap = anywrap || (f & 2);
+#pragma unroll
+            for (int k = 0; k < L; k++) {
+                c[d][k] = __ldg(t.tap[d] + idx[d] * L + k);
+                w[0][d][k] = __ldg((const T*)t.w[d] + idx[d] * L + k);
+            }
+        }
+        if constexpr (ORDER == GB_LINEAR && BCF != BCF_NIL) {  // the offset-table rule of query_taps
+            if (!anywrap) {
+#pragma unroll
+                for (int d = 0; d < N; d++) c[d][1] = c[d][0] + 1;
+            }
+        }
+        GlobalTaps<T, N, L, GUARD> src;
+        src.A = (const T*)p.coefs;
+        src.total = (u32)p.total;
+#pragma unroll
+        for (int d = 0; d < N; d++) {
+#pragma unroll
+            for (int k = 0; k < L; k++) src.off[d][k] = (u32)c[d][k] * (u32)p.stride[d];
+        }
+        T acc[1];
+        contract<T, N, L, 0, FAST>(src, w, acc);
+        if (nonfinite(acc[0])) {  // literal zero-weight semantics, from the coordinates
+            T x[N];
+#pragma unroll
+            for (int d = 0; d < N; d++) x[d] = index_coord<T, N>(p, d, load_raw<N>(p, d, idx[d]));
+            EvalParams<N> ps = p;
+            ps.val = out;
+            ps.grad = nullptr;
+            ps.hess = nullptr;
+            eval_one_slow<T, N, ORDER, BCF>(ps, src.A, x, q, q, 0);
+            continue;
+        }
+        if (!valid) {
+            acc[0] = qnan<T>();
+            if (p.first_invalid) atomicMin(p.first_invalid, (u64)q);
+        }
+        out[q] = acc[0];
+    }
+}
+template <typename T, int N, int ORDER, int BCF>
+int launch_outer_bc(const EvalParams<N>& p, const i64* lens, int flags, void* out, cudaStream_t s) {
+    constexpr int L = ORDER + 1;
+    OuterTables<N> t;
+    i64 rows = 0, nq = 1;
+    for (int d = 0; d < N; d++) { t.lens[d] = lens[d]; rows += lens[d]; nq *= lens[d]; }
+    if (nq == 0) return GB_OK;
+    // one scratch block: taps (int) | weights (T) | flags
+    const size_t tap_b = ((size_t)rows * L * sizeof(int) + 15) & ~(size_t)15, w_b = ((size_t)rows * L * sizeof(T) + 15) & ~(size_t)15;
+    unsigned char* blk = nullptr;
+    GB_CUDA(cudaMallocAsync((void**)&blk, tap_b + w_b + (size_t)rows + 16, s));
+    int* tap = reinterpret_cast<int*>(blk);
+    T* w = reinterpret_cast<T*>(blk + tap_b);
+    unsigned char* flg = blk + tap_b + w_b;
+    i64 r0 = 0;
+    for (int d = 0; d < N; d++) {
+        const int g = (int)std::max<i64>(1, std::min<i64>((lens[d] + 255) / 256, (i64)num_sms() * 8));
+        outer_table_kernel<T, N, ORDER, BCF><<<g, 256, 0, s>>>(p, d, lens[d], tap + r0 * L, w + r0 * L, flg + r0);
+        t.tap[d] = tap + r0 * L;
+        t.w[d] = w + r0 * L;
+        t.flg[d] = flg + r0;
+        r0 += lens[d];
+    }
+    const int grid = (int)std::max<i64>(1, std::min<i64>((nq + 255) / 256, (i64)num_sms() * 16));
+    if (flags & GB_FAST) outer_eval_kernel<T, N, ORDER, BCF, true><<<grid, 256, 0, s>>>(p, t, (T*)out, nq);
+    else outer_eval_kernel<T, N, ORDER, BCF, false><<<grid, 256, 0, s>>>(p, t, (T*)out, nq);
+    count_launch(N + 1);
+    GB_CUDA(cudaGetLastError());
+    GB_CUDA(cudaFreeAsync(blk, s));
+    return GB_OK;
+}
+template <typename T, int N, int ORDER> int launch_outer_order(const EvalParams<N>& p, int bcf, const i64* lens, int flags, void* out, cudaStream_t s) {
+    if constexpr (ORDER == GB_CUBIC) {
+        if (bcf != BCF_NIL) return fail(GB_ERR_UNSUPPORTED, "InterpCubic supports only BCnil/BCnan/BCna");
+        return launch_outer_bc<T, N, ORDER, BCF_NIL>(p, lens, flags, out, s);
+    } else {
+        switch (bcf) {
+        case BCF_NIL: return launch_outer_bc<T, N, ORDER, BCF_NIL>(p, lens, flags, out, s);
+        case BCF_REFLECT: return launch_outer_bc<T, N, ORDER, BCF_REFLECT>(p, lens, flags, out, s);
+        case BCF_PERIODIC: return launch_outer_bc<T, N, ORDER, BCF_PERIODIC>(p, lens, flags, out, s);
+        case BCF_CLAMP: return launch_outer_bc<T, N, ORDER, BCF_CLAMP>(p, lens, flags, out, s);
+        }
+        return fail(GB_ERR_ARG, "bad boundary condition");
+    }
+}
+
 template <typename T, int N, int ORDER, int BCF>
 int launch_mode(const EvalParams<N>& p, int outmode, int flags, cudaStream_t s) {
     const bool fast = (flags & GB_FAST) != 0;

@@ -7,4 +7,7 @@ namespace gb {
 int GB_CAT(launch_eval, GB_T, GB_N, GB_O)(const EvalParams<GB_N>& p, int bcf, int outmode, int flags, cudaStream_t s) {
     return launch_order<GB_T, GB_N, GB_O>(p, bcf, outmode, flags, s);
 }
+int GB_CAT(launch_outer, GB_T, GB_N, GB_O)(const EvalParams<GB_N>& p, int bcf, const i64* lens, int flags, void* out, cudaStream_t s) {
+    return launch_outer_order<GB_T, GB_N, GB_O>(p, bcf, lens, flags, out, s);
+}
 }  // namespace gb

@@ -376,7 +376,9 @@ class OracleGrid:
         """tensor-product getindex (src/interp.jl:273-306)."""
         if len(vecs) != self.N:
             raise OracleError(ERR_ARG, "Dimensionality mismatch")
-        mesh = np.meshgrid(*[np.asarray(v, dtype=np.float64) for v in vecs], indexing="ij")
+        arrs = [np.asarray(v) for v in vecs]
+        dt = np.float32 if all(a.dtype == np.float32 for a in arrs) else np.float64  # setx adds its 1 in the query's type
+        mesh = np.meshgrid(*[a.astype(dt) for a in arrs], indexing="ij")
         X = np.stack([m.ravel(order="F") for m in mesh], axis=1)
         v, _, _, _ = evaluate(self.coefs, self.bc, self.order, X, OUT_VAL, self.affine)
         return v.reshape([len(v_) for v_ in vecs], order="F")

@@ -607,3 +607,35 @@ def test_interp_irregular(gb, oracle, dtype, it, bc):
         gb.InterpIrregular(knots[::-1].copy(), vals, gb.BCnan, IT)
     with pytest.raises(gb.ErrorException):
         gb.InterpIrregular(knots, vals, gb.BCperiodic, IT)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("bc,order,shape", [("reflect", "quadratic", (30, 20)), ("nan", "cubic", (12, 11, 10)), ("periodic", "linear", (6, 7, 5, 6)),
+                                            ("fill", "linear", (9, 8, 7)), ("nearest", "quadratic", (15,)), ("periodic", "nearest", (8, 9)),
+                                            ("nil", "quadratic", (10, 12)), ("nan", "quadratic", (5, 6, 4, 5)), ("reflect", "linear", (4, 5, 4, 3, 4))])
+def test_tensor_product_getindex(gb, oracle, dtype, bc, order, shape):
+    """(f)-3: G[xs, ys, ...] (src/interp.jl:273-306) on the separable path (taps and weights once per axis
+    point; N <= 4) and on the expanded path (N = 5, 4-D quadratic): bit-identical to the oracle's outer
+    product of scalar calls, host vectors and CUDA tensors, including wrapped / out-of-range axis points."""
+    import torch
+
+    rng = np.random.default_rng(59)
+    A = np.asfortranarray(rng.standard_normal(shape).astype(dtype))
+    g, co = build(gb, oracle, A, bc, order)
+    og = oracle.OracleGrid(A, bc, order, fill=-1.25 if bc == "fill" else None)
+    wide = bc not in ("nil",)
+    vecs = []
+    for n in shape:
+        lo, hi = (-1.5 * n, 2.5 * n) if wide else (1.0, float(n))
+        v = np.concatenate([lo + (hi - lo) * rng.random(7), [1.0, float(n), 1.5, n / 2]]).astype(dtype)
+        vecs.append(v)
+    ref = og.outer(*vecs)
+    got = g[tuple(vecs)]
+    assert got.shape == ref.shape and same(got, ref.astype(dtype))
+    gotd = g[tuple(torch.from_numpy(v).cuda() for v in vecs)]
+    assert same(gb.jl_to_numpy(gotd), ref.astype(dtype))
+    if bc == "nil":
+        bad = [v.copy() for v in vecs]
+        bad[-1][3] = shape[-1] + 2.0
+        with pytest.raises(gb.ErrorException, match="Invalid location"):
+            g[tuple(bad)]
