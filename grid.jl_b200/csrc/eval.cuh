@@ -1307,11 +1307,7 @@ int launch_tiled(const EvalParams<N>& p_in, cudaStream_t s) {
     tile_scatter_kernel<T, N><<<nctas, SORT_BLOCK, hsmem, s>>>(p, keys, boff, rec, inv, nbins, per_cta);
     count_launch();
     GB_CUDA(cudaGetLastError());
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
+    GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per device, cheap
     int bt = 0;
     GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt, kern, BRICK_BLOCK, smem));
     if (bt < 1) { cudaFreeAsync(scratch, s); return fail(GB_ERR_CUDA, "tiled evaluation: brick does not fit in shared memory"); }

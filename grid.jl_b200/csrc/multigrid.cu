@@ -394,12 +394,12 @@ template <typename T> __device__ __forceinline__ T prolong_at(bool evenlen, bool
 template <typename T, int BY, int BZ> __global__ void __launch_bounds__(256) prolong3_kernel(const T* __restrict__ A, T* __restrict__ P, int n1, int n2, int n3, int m1, int m2, int m3, int do1, int do2, int do3) {
     constexpr int BX = 64, NW = 8;
     extern __shared__ unsigned char smem_raw[];
-    T* S1 = reinterpret_cast<T*>(smem_raw);  // [nz][ny][BX]  after dim-1 prolongation
-    T* S2 = S1 + BZ * BY * BX;                // [nz][BY][BX]  after dim-2
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int k1 = blockIdx.x * BX, k2 = blockIdx.y * BY, k3 = blockIdx.z * BZ;
     const int y0 = do2 ? k2 / 2 : k2, z0 = do3 ? k3 / 2 : k3;
     const int ny = do2 ? BY / 2 + 1 : BY, nz = do3 ? BZ / 2 + 1 : BZ;  // staged extents (input coordinates)
+    T* S1 = reinterpret_cast<T*>(smem_raw);  // [nz][ny][BX]  after dim-1 prolongation
+    T* S2 = S1 + nz * ny * BX;                // [nz][BY][BX]  after dim-2
     const bool ev1 = !(m1 & 1), ev2 = !(m2 & 1), ev3 = !(m3 & 1);
     // ---- stage 1
     for (int r = warp; r < nz * ny; r += NW) {
@@ -488,7 +488,8 @@ template <typename T> int prolong3_impl(const i64* dims, const T* in, const i64*
     for (int d = 0; d < 3; d++)
         if (m[d] >= (1ll << 30)) return fail(GB_ERR_UNSUPPORTED, "prolong3: extent too large");
     constexpr int BX = 64, BY = 8, BZ = 8;
-    const size_t smem = sizeof(T) * 2 * (size_t)BZ * BY * BX;  // S1 and S2, each at most BZ*BY*BX
+    const int sny = doit[1] ? BY / 2 + 1 : BY, snz = doit[2] ? BZ / 2 + 1 : BZ;
+    const size_t smem = sizeof(T) * ((size_t)snz * sny * BX + (size_t)snz * BY * BX);  // S1 + S2 (33 KB for a full f64 prolongation: 6 CTAs per SM)
     auto kern = prolong3_kernel<T, BY, BZ>;
     GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((m[0] + BX - 1) / BX), (unsigned)((m[1] + BY - 1) / BY), (unsigned)((m[2] + BZ - 1) / BZ));
