@@ -713,13 +713,24 @@ __device__ __forceinline__ void eval_one(const EvalParams<N>& p, const T (&x)[N]
 #pragma unroll
         for (int i = 0; i < L; i++) src.off[d][i] = (u32)c[d][i] * (u32)p.stride[d];
     }
+    if (p.nchan == 1) {  // (kept apart from the channel loop: the loop costs the 3-D cubic kernels their registers)
+        T acc[NP];
+        contract<T, N, L, OUTMODE, FAST>(src, w, acc);
+        if (nonfinite(acc[0])) {  // a NaN/Inf coefficient may have been touched: literal zero-weight semantics
+            eval_one_slow<T, N, ORDER, BCF>(p, src.A, x, pos, q, OUTMODE);
+            return;
+        }
+        store_outputs<T, N, OUTMODE>(p, pos, q, valid, acc);
+        return;
+    }
     // Multi-valued grids (README.md:151-209: set_position once, interp(ic, A, index) per channel): the
     // taps and weights above serve every channel; channel ch of a query lands at output pos*nchan + ch.
+#pragma unroll 1
     for (int ch = 0; ch < p.nchan; ch++) {
         T acc[NP];
         contract<T, N, L, OUTMODE, FAST>(src, w, acc);
         const i64 opos = pos * p.nchan + ch;
-        if (nonfinite(acc[0])) {  // a NaN/Inf coefficient may have been touched: literal zero-weight semantics
+        if (nonfinite(acc[0])) {
             eval_one_slow<T, N, ORDER, BCF>(p, src.A, x, opos, q, OUTMODE);
         } else {
             store_outputs<T, N, OUTMODE>(p, opos, q, valid, acc);
