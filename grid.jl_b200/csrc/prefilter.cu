@@ -228,38 +228,118 @@ template <typename T, int U, bool SUB, typename IO> __device__ __forceinline__ v
     }
 }
 
-template <typename T, int U, typename IO> __device__ __forceinline__ void solve_line(const IO& b, const IO& t, i64 n, const LineSys<T>& sys) {
+// ---- Woodbury second solve without the array-sized scratch -----------------------------------------
+// The eliminated right-hand side t of the second solve (RHS k0*e_0 + k1*e_{n-1}) is a one-multiply
+// recurrence, so instead of writing it to global memory on the way up and reading it back on the way
+// down (16 of the sweep's 64 B/point), the forward pass only CHECKPOINTS the recurrence state at the
+// start of every backward chunk (shared memory, [chunk][thread]) and the backward pass replays the U
+// steps of a chunk from its checkpoint -- the same operations in the same order on the same inputs,
+// hence the same bits.
+template <typename T> __device__ __forceinline__ void sparse_step(const LineSys<T>& sys, i64 i, i64 n, T k1, T& cur, T& v) {
+    const T m = __ldg(sys.dl + i);
+    const T nxt = (i + 1 == n - 1) ? k1 : (T)0;
+    if (__ldg(sys.swap + i)) { v = nxt; cur = cur - m * nxt; }
+    else { v = cur; cur = nxt - m * cur; }
+}
+template <typename T, int U> __device__ __forceinline__ T lu_forward_sparse_ck(i64 n, const LineSys<T>& sys, T k0, T k1, T* ck, int ckstride, T& t_nm2) {
+    T cur = k0;
+    t_nm2 = (T)0;
+    const i64 nck = (n - 2 + U - 1) / U;  // backward chunks cover indices 0 .. n-3
+    i64 j = nck - 1;
+    i64 sj = 0;  // start index of chunk j: max(0, n-2-(j+1)U); the lowest chunk starts at 0
+    for (i64 i = 0; i < n - 1; i++) {
+        if (j >= 0 && i == sj) {
+            ck[j * ckstride] = cur;
+            j--;
+            sj = n - 2 - (j + 1) * U;
+        }
+        T v;
+        sparse_step<T>(sys, i, n, k1, cur, v);
+        if (i == n - 2) t_nm2 = v;
+    }
+    return cur;
+}
+template <typename T, int U, typename IO>
+__device__ __forceinline__ void lu_backward_sub_ck(const IO& dst, i64 n, const LineSys<T>& sys, T last, T t_nm2, T k1, const T* ck, int ckstride) {
+    T x1 = exact_div(last, __ldg(sys.d + (n - 1)), __ldg(sys.rd + (n - 1)));
+    dst.put(n - 1, dst.get(n - 1) - x1);
+    if (n < 2) return;
+    const T x0 = exact_div(t_nm2 - __ldg(sys.du + (n - 2)) * x1, __ldg(sys.d + (n - 2)), __ldg(sys.rd + (n - 2)));
+    dst.put(n - 2, dst.get(n - 2) - x0);
+    T x2 = x1;
+    x1 = x0;
+    T go[U];
+    if (n > 2) dst.fetch(go, n - 3, -1, (int)min((i64)U, n - 2));
+    i64 j = 0;
+    for (i64 c0 = n - 3; c0 >= 0; c0 -= U, j++) {
+        const int cnt = (int)min((i64)U, c0 + 1);
+        T v[U], o[U], tt[U];
+        dst.unpack(o, go);
+        if (c0 - U >= 0) dst.fetch(go, c0 - U, -1, (int)min((i64)U, c0 - U + 1));  // next chunk in flight
+        // replay the chunk's U forward steps from its checkpoint (positions below index 0 are skipped)
+        T cur = ck[j * ckstride];
+        const i64 s = c0 - U + 1;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            tt[u] = (T)0;
+            if (s + u >= 0) sparse_step<T>(sys, s + u, n, k1, cur, tt[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (u < cnt) {
+                const i64 i = c0 - u;
+                const T x = exact_div(tt[U - 1 - u] - __ldg(sys.du + i) * x1 - __ldg(sys.du2 + i) * x2, __ldg(sys.d + i), __ldg(sys.rd + i));
+                v[u] = o[u] - x;
+                x2 = x1;
+                x1 = x;
+            }
+        }
+        dst.store(v, c0, -1, cnt);
+    }
+}
+
+template <typename T, int U, typename IO> __device__ __forceinline__ void solve_line(const IO& b, const IO& t, i64 n, const LineSys<T>& sys, T* ck, int ckstride) {
     const T last = lu_forward_dense<T, U>(b, n, sys);
     lu_backward<T, U, false>(b, b, n, sys, last);
     if (sys.woodbury) {                                            // WoodburyMatrices A_ldiv_B!
         const T k10 = b.get(sys.vcol0), k11 = b.get(sys.vcol1);    // tmpk1 = V*tmpN1
         const T k20 = ((T)0 + sys.cp[0] * k10) + sys.cp[2] * k11;  // tmpk2 = Cp*tmpk1 (gemv column order)
         const T k21 = ((T)0 + sys.cp[1] * k10) + sys.cp[3] * k11;
-        const T last2 = lu_forward_sparse<T, U>(t, n, sys, k20, k21);  // A_ldiv_B!(W.A, tmpN2 = U*tmpk2)
-        lu_backward<T, U, true>(t, b, n, sys, last2);                  // B = tmpN1 - tmpN2
+        if (ck && n >= 3) {  // A_ldiv_B!(W.A, tmpN2 = U*tmpk2), B = tmpN1 - tmpN2; tmpN2 never leaves the chip
+            T t_nm2;
+            const T last2 = lu_forward_sparse_ck<T, U>(n, sys, k20, k21, ck, ckstride, t_nm2);
+            lu_backward_sub_ck<T, U>(b, n, sys, last2, t_nm2, k21, ck, ckstride);
+        } else {
+            const T last2 = lu_forward_sparse<T, U>(t, n, sys, k20, k21);
+            lu_backward<T, U, true>(t, b, n, sys, last2);
+        }
     }
 }
 
 // sweeps along dims >= 2: one thread per line, 32 adjacent lines per warp -> coalesced chunk IO
 constexpr int PF_U = 8;
-template <typename T> __global__ void __launch_bounds__(128, 4) line_solve_global(T* A, T* tmp, i64 n, i64 s, i64 inner, i64 nlines, const LineSys<T> sys) {
+template <typename T> __global__ void __launch_bounds__(128, 4) line_solve_global(T* A, T* tmp, i64 n, i64 s, i64 inner, i64 nlines, const LineSys<T> sys, int use_ck) {
     const i64 l = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nlines) return;
     const i64 lo = l % inner, hi = l / inner;
     const i64 base = lo + hi * inner * n;
     const GlobalLine<T, PF_U> b{A + base, s}, t{tmp ? tmp + base : nullptr, s};
-    solve_line<T, PF_U>(b, t, n, sys);
+    extern __shared__ __align__(16) unsigned char pf_dyn[];
+    T* ck = use_ck ? reinterpret_cast<T*>(pf_dyn) + threadIdx.x : nullptr;
+    solve_line<T, PF_U>(b, t, n, sys, ck, (int)blockDim.x);
 }
 // sweep along dim 1 (contiguous lines): one warp per 32 lines, shared-memory transposing tile
 constexpr int PF_WARPS = 4;
-template <typename T, int TU> __global__ void __launch_bounds__(32 * PF_WARPS, TU == 8 ? 4 : 3) line_solve_tile(T* A, T* tmp, i64 n, i64 nlines, const LineSys<T> sys) {
+template <typename T, int TU> __global__ void __launch_bounds__(32 * PF_WARPS, TU == 8 ? 4 : 3) line_solve_tile(T* A, T* tmp, i64 n, i64 nlines, const LineSys<T> sys, int use_ck) {
     __shared__ T tiles[PF_WARPS][32 * (TU + 1)];
     const int warp = threadIdx.x >> 5;
     const i64 first = ((i64)blockIdx.x * PF_WARPS + warp) * 32;
     if (first >= nlines) return;
     const int nl = (int)min((i64)32, nlines - first);
     const TileLine<T, TU> b{A + first * n, n, nl, tiles[warp]}, t{tmp ? tmp + first * n : nullptr, n, nl, tiles[warp]};
-    solve_line<T, TU>(b, t, n, sys);
+    extern __shared__ __align__(16) unsigned char pf_dyn[];
+    T* ck = use_ck ? reinterpret_cast<T*>(pf_dyn) + threadIdx.x : nullptr;
+    solve_line<T, TU>(b, t, n, sys, ck, (int)blockDim.x);
 }
 
 // ---- host: factorisation (dgttrf order) + Woodbury capacitance ---------------------------------
@@ -407,13 +487,21 @@ template <typename T> int invert_impl(T* A, int ndim, const i64* dims, int bc, i
         sys.vcol0 = (int)hs.vcol[0]; sys.vcol1 = (int)hs.vcol[1];
         for (int i = 0; i < 4; i++) sys.cp[i] = hs.cp[i];
 
-        if (hs.woodbury && !tmp) GB_CUDA(cudaMallocAsync((void**)&tmp, (size_t)total * sizeof(T), s));
+        // Woodbury: checkpoints of the second solve's RHS in shared memory when they fit, else an array-sized scratch
+        const size_t ck_bytes = hs.woodbury && n >= 3 ? (size_t)((n - 2 + PF_U - 1) / PF_U) * 128 * sizeof(T) : 0;
+        const int use_ck = hs.woodbury && ck_bytes > 0 && ck_bytes <= 64 * 1024;
+        const size_t dyn = use_ck ? ck_bytes : 0;
+        if (hs.woodbury && !use_ck && !tmp) GB_CUDA(cudaMallocAsync((void**)&tmp, (size_t)total * sizeof(T), s));
         if (str == 1 && nlines >= 32) {
             const i64 grid = (nlines + 32 * PF_WARPS - 1) / (32 * PF_WARPS);
-            line_solve_tile<T, 8><<<(unsigned)grid, 32 * PF_WARPS, 0, s>>>(A, tmp, n, nlines, sys);  // 8: measured faster than 16
+            auto kern = line_solve_tile<T, 8>;  // 8: measured faster than 16
+            if (dyn) GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            kern<<<(unsigned)grid, 32 * PF_WARPS, dyn, s>>>(A, use_ck ? nullptr : tmp, n, nlines, sys, use_ck);
         } else {
             const i64 grid = (nlines + 127) / 128;
-            line_solve_global<T><<<(unsigned)grid, 128, 0, s>>>(A, tmp, n, str, str, nlines, sys);
+            auto kern = line_solve_global<T>;
+            if (dyn) GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            kern<<<(unsigned)grid, 128, dyn, s>>>(A, use_ck ? nullptr : tmp, n, str, str, nlines, sys, use_ck);
         }
         count_launch();
         GB_CUDA(cudaGetLastError());
