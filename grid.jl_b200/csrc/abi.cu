@@ -409,11 +409,10 @@ template <int N> void fill_params(const EvalCall& c, EvalParams<N>& p) {
     p.nq = c.nq;
     p.q0 = c.q0;
     p.first_invalid = c.first_invalid;
-    p.tiled = 0;
     p.aos = 0;
     p.nchan = (int)g->nchan;
     p.cstride = g->total;
-    p.perm = nullptr; p.work = nullptr; p.nwork = nullptr;
+    p.work = nullptr; p.nwork = nullptr;
     for (int d = 0; d < N; d++) { p.tile[d] = 1; p.ntile[d] = 1; }
 }
 template <int N> int launch_n(const EvalCall& c, cudaStream_t s) {

@@ -62,7 +62,7 @@ __host__ __device__ constexpr int brick_stride(int N, int L, int d) {
     return s;
 }
 
-// ---- evaluation launch interface (eval_f32_*.cu / eval_f64_*.cu) -----------------------------
+// ---- evaluation launch interface (eval_inst.cu, one translation unit per (T, N, order)) ---------
 template <int N> struct EvalParams {
     const void* coefs;
     i64 total;            // elements in the stored array
@@ -80,16 +80,14 @@ template <int N> struct EvalParams {
     i64 nq;
     i64 q0;               // index of this launch's first query in the caller's batch
     u64* first_invalid;   // device, atomicMin target (BCnil) or NULL
-    // tiled (spatially binned) evaluation, filled in by launch_one; tiled == 0 -> plain
-    int tiled;
     int nchan;            // channels sharing the taps/weights of a query (multi-valued grids); 1 = scalar grid
     i64 cstride;          // elements between consecutive channels of the coefficient array
-    int aos;              // != 0: outputs are records of `aos` words per sorted slot at `val` (tiled mode)
+    // brick (spatially binned) evaluation, filled in by launch_one / launch_tiled
+    int aos;              // != 0: outputs are records of `aos` words per sorted slot at `val`
     int tile[N];          // cells per tile
     int ntile[N];         // tiles per dimension
-    const u32* perm;      // unused (records carry the query index)
-    const u32* work;      // 3 words per work item: tile, begin, end (into perm)
-    const u32* nwork;     // device scalar: number of work items
+    const u32* work;      // 3 words per work item: tile, first sorted slot, one past the last
+    const u32* nwork;     // device: [0] number of work items, [1] the ticket counter CTAs pull items from
 };
 
 // One entry per (dtype, N, order) -- eval_inst.cu; each dispatches on (bc family, output mode, flags).

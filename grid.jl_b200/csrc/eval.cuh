@@ -3,8 +3,8 @@
 // One thread evaluates one query: it computes, per dimension, the tap coordinates under the
 // boundary condition (branch structure of src/interp.jl:594-783, resolved at compile time per
 // (order, BC family)), the B-spline value / gradient / Hessian weights in registers
-// (src/interp.jl:785-847), and gathers the l^N coefficient neighbourhood through the read-only
-// path.  Two contraction schemes share the taps and weights:
+// (src/interp.jl:785-847), and contracts the l^N coefficient neighbourhood.  Two contraction schemes
+// share the taps and weights:
 //   EXACT  the reference's arithmetic: coefficient of a tap = ((w_N*w_{N-1})*...)*w_1
 //          (src/interp.jl:1130-1183), value = sequential sum over taps, dim 1 fastest, of
 //          c==0 ? 0 : c*A[idx] (src/interp.jl:501-505); gradient / Hessian passes rebuild the
@@ -12,6 +12,12 @@
 //          the taps (each tap is loaded once); per-pass accumulation order is unchanged, so the
 //          results are bit-identical to the scalar reference algorithm.
 //   FAST   separable contraction, dimension by dimension, with FMA.
+// and two schedules feed them (identical results):
+//   plain  taps gathered from global memory in the caller's order (eval_kernel)
+//   brick  the batch is counting-sorted by grid tile and evaluated tile by tile out of shared
+//          memory (tile_hist / tile_scatter / eval_brick_kernel / eval_deferred_kernel /
+//          unpermute_kernel, second half of this file)
+// plus the separable tensor-product path (outer_table_kernel / outer_eval_kernel).
 // Compiled with -fmad=false: plain * and + never fuse.
 #pragma once
 #include <algorithm>
@@ -1322,8 +1328,6 @@ int launch_tiled(const EvalParams<N>& p_in, cudaStream_t s) {
     int bt = 0;
     GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt, kern, BRICK_BLOCK, smem));
     if (bt < 1) { cudaFreeAsync(scratch, s); return fail(GB_ERR_CUDA, "tiled evaluation: brick does not fit in shared memory"); }
-    p.tiled = 1;
-    p.perm = nullptr;
     p.work = work;
     p.nwork = nwork;
     const i64 grid = std::min<i64>((i64)max_items, (i64)num_sms() * bt);
@@ -1366,7 +1370,6 @@ int launch_one(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     if (!(flags & (GB_TILED | GB_PLAIN))) tiled = N >= 2 && tap_bytes >= 256 && p.nq >= (1ll << 20) && grid_bytes >= (48u << 20);
     if (p.nchan > 1) tiled = false;  // multi-valued grids: plain path (one brick per channel would not fit)
     if (tiled) tiled = choose_tile(N, L, sizeof(T), p.len, std::min<i64>(p.nq, tiled_max_batch()), forced, p.tile, p.ntile);
-    p.tiled = 0;
     p.aos = 0;
     if (!tiled) {
         static int blocks_plain = 0;  // benign race: every thread computes the same value
