@@ -639,3 +639,43 @@ def test_tensor_product_getindex(gb, oracle, dtype, bc, order, shape):
         bad[-1][3] = shape[-1] + 2.0
         with pytest.raises(gb.ErrorException, match="Invalid location"):
             g[tuple(bad)]
+
+
+def test_brick_path_in_slices(gb, oracle):
+    """Batches above the slice limit are evaluated slice by slice (GB_TILED_BATCH, default 2^26): run a
+    child process with a 20000-query limit so that a 70000-query batch takes four slices, with BCnil's
+    first-invalid index falling in the third one."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+
+    rng = np.random.default_rng(61)
+    A = np.asfortranarray(rng.standard_normal((33, 20, 18)))
+    X = make_queries(rng, A.shape, 70_000, np.float64, wide=False)[:70_000]
+    X[45_678, 1] = 25.0  # invalid under BCnil
+    with tempfile.TemporaryDirectory() as d:
+        np.save(os.path.join(d, "A.npy"), A)
+        np.save(os.path.join(d, "X.npy"), X)
+        code = (
+            "import sys, numpy as np, torch\n"
+            f"sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})\n"
+            "import grid_jl_b200 as gb\n"
+            f"A = np.load({os.path.join(d, 'A.npy')!r}); X = np.load({os.path.join(d, 'X.npy')!r})\n"
+            "g = gb.InterpGrid(A, gb.BCnan, gb.InterpCubic)\n"
+            "v, gr, _ = g._eval(torch.from_numpy(X).cuda(), 3, tiled=True)\n"
+            f"np.save({os.path.join(d, 'v.npy')!r}, v.cpu().numpy()); np.save({os.path.join(d, 'g.npy')!r}, gr.cpu().numpy())\n"
+            "n = gb.InterpGrid(A, gb.BCnil, gb.InterpQuadratic)\n"
+            "try:\n"
+            "    n._eval(torch.from_numpy(X).cuda(), 1, tiled=True)\n"
+            "    print('no error')\n"
+            "except gb.ErrorException as e:\n"
+            "    print(str(e))\n"
+        )
+        env = dict(os.environ, GB_TILED_BATCH="20000")
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        assert "Invalid location (query 45678)" in out.stdout
+        co = oracle.make_coefs(A, "nan", "cubic")
+        ov, og, _, _ = oracle.evaluate(co, "nan", "cubic", X, 3)
+        assert same(np.load(os.path.join(d, "v.npy")), ov) and same(np.load(os.path.join(d, "g.npy")), og)
