@@ -40,28 +40,6 @@ template <typename T> struct LineSys {
     T cp[4];  // column-major 2x2
 };
 
-// ---- a / d, correctly rounded, without the division routine ------------------------------------------
-// The back substitution divides by the pivot d[i], which is the same for every line, so rd = RN(1/d)
-// comes from the host and the quotient is refined with exact FMA residuals (Markstein): q0 = RN(a*rd)
-// is within 2 ulp of a/d, one correction makes it faithful, the second one rounds correctly -- the
-// same bits as a / d (checked against the hardware division over 5e8 random numerators per pivot,
-// the check_exact_div.c program of the test infrastructure) in 5 dependent operations instead of ~30.  Numerators whose exponent
-// is far from 1 (possible underflow of the residuals, Inf/NaN) take the real division; a zero
-// numerator returns the correctly signed zero directly.
-__device__ __forceinline__ bool div_safe(double a) { return (unsigned)(((unsigned)__double2hiint(a) >> 20) & 0x7ffu) - 200u < 1600u; }
-__device__ __forceinline__ bool div_safe(float a) { return (unsigned)(((unsigned)__float_as_int(a) >> 23) & 0xffu) - 40u < 170u; }
-template <typename T> __device__ __forceinline__ T exact_div(T a, T d, T rd) {
-    const T q0 = a * rd;
-    if (a == (T)0) return q0;  // +-0 with the sign of a/d (rd has the sign of d): zero lines (padding planes) stay cheap
-    if (div_safe(a)) {
-        const T r0 = fma(-d, q0, a);
-        const T q1 = fma(r0, rd, q0);
-        const T r1 = fma(-d, q1, a);
-        return fma(r1, rd, q1);
-    }
-    return a / d;
-}
-
 // ---- line IO policies -------------------------------------------------------------------------------
 // The substitutions are sequential along a line, so a thread hides memory latency only by having the
 // NEXT elements of its line in flight: lines are processed in chunks of U elements; fetch() issues
