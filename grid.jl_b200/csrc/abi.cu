@@ -243,7 +243,7 @@ static int grid_create_impl(gb_grid** out, int dtype, int ndim, const int64_t* d
         st *= sd[d];
         if (sd[d] < min_len(bc, order)) return fail(GB_ERR_ARG, "grid too small for this interpolation order");
     }
-    if ((double)st * (double)nchan > 4.0e12) return fail(GB_ERR_ARG, "grid too large");
+    if ((double)st * (double)nchan > 2147483648.0) return fail(GB_ERR_ARG, "multi-valued grids are limited to 2^31 stored elements over all channels (32-bit tap offsets)");
     gb_grid* g = nullptr;
     new_grid(&g, dtype, ndim, bc, order, fill);
     for (int d = 0; d < ndim; d++) { g->user_dims[d] = dims[d]; g->stored_dims[d] = sd[d]; }
@@ -282,6 +282,16 @@ static int grid_create_impl(gb_grid** out, int dtype, int ndim, const int64_t* d
     sd[ndim] = nchan;  // lines of every channel are solved in the same sweeps
     rc = invert_device(dtype, nchan > 1 ? ndim + 1 : ndim, sd, g->coefs, pf_bc, order, all.data(), ndim, s);
     if (rc) return cleanup(rc);
+    if (nchan > 1) {  // resident layout of multi-valued grids: channel-interleaved (see interleave_device)
+        void* fin = nullptr;
+        e = cudaMalloc(&fin, (size_t)st * (size_t)nchan * es);
+        if (e != cudaSuccess) return cleanup(cuda_fail(e, "cudaMalloc(coefs)"));
+        rc = interleave_device(dtype, g->coefs, fin, st, nchan, 1, s);
+        if (rc) { cudaFree(fin); return cleanup(rc); }
+        cudaStreamSynchronize(s);
+        cudaFree(g->coefs);
+        g->coefs = fin;
+    }
     if (staged) cudaFreeAsync(staged, s);
     if (mem == GB_HOST) {
         e = cudaStreamSynchronize(s);
@@ -303,6 +313,7 @@ static int grid_from_coefs_impl(gb_grid** out, int dtype, int ndim, const int64_
         if (stored_dims[d] < min_len(bc, order) || (pad && stored_dims[d] < 3)) return fail(GB_ERR_ARG, "stored grid too small");
         st *= stored_dims[d];
     }
+    if ((double)st * (double)nchan > 2147483648.0) return fail(GB_ERR_ARG, "multi-valued grids are limited to 2^31 stored elements over all channels (32-bit tap offsets)");
     gb_grid* g = nullptr;
     new_grid(&g, dtype, ndim, bc, order, fill);
     if (raw_coords) g->shift = 0;  // low-level interface: coordinates index the array as stored (no setx shift)
@@ -313,6 +324,22 @@ static int grid_from_coefs_impl(gb_grid** out, int dtype, int ndim, const int64_
     const size_t bytes = (size_t)st * (size_t)nchan * esize(dtype);
     cudaError_t e = cudaMalloc(&g->coefs, bytes);
     if (e != cudaSuccess) { delete g; return cuda_fail(e, "cudaMalloc(coefs)"); }
+    if (nchan > 1) {  // adopt channel-last coefficients into the channel-interleaved resident layout
+        void* tmp = nullptr;
+        const void* src = coefs;
+        if (mem == GB_HOST) {
+            e = cudaMallocAsync(&tmp, bytes, s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, coefs, bytes, cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) { if (tmp) cudaFreeAsync(tmp, s); cudaFree(g->coefs); delete g; return cuda_fail(e, "copy coefs"); }
+            src = tmp;
+        }
+        rc = interleave_device(dtype, src, g->coefs, st, nchan, 1, s);
+        if (tmp) cudaFreeAsync(tmp, s);
+        e = (mem == GB_HOST) ? cudaStreamSynchronize(s) : cudaSuccess;
+        if (rc || e != cudaSuccess) { cudaFree(g->coefs); delete g; return rc ? rc : cuda_fail(e, "copy coefs"); }
+        *out = g;
+        return GB_OK;
+    }
     e = cudaMemcpyAsync(g->coefs, coefs, bytes, mem == GB_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s);
     if (e == cudaSuccess && mem == GB_HOST) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) { cudaFree(g->coefs); delete g; return cuda_fail(e, "copy coefs"); }
@@ -362,7 +389,18 @@ int gb_grid_coefs_device(const gb_grid* g, void** device_ptr) {
 }
 int gb_grid_coefs_download(const gb_grid* g, void* host_out) {
     if (!g || !host_out) return fail(GB_ERR_ARG, "NULL argument");
-    GB_CUDA(cudaMemcpy(host_out, g->coefs, (size_t)g->total * (size_t)g->nchan * esize(g->dtype), cudaMemcpyDeviceToHost));
+    const size_t bytes = (size_t)g->total * (size_t)g->nchan * esize(g->dtype);
+    if (g->nchan > 1) {  // resident layout is channel-interleaved; the caller gets the reference's channel-last array
+        void* tmp = nullptr;
+        GB_CUDA(cudaMalloc(&tmp, bytes));
+        int rc = interleave_device(g->dtype, g->coefs, tmp, g->total, g->nchan, 0, nullptr);
+        cudaError_t e = rc ? cudaSuccess : cudaMemcpy(host_out, tmp, bytes, cudaMemcpyDeviceToHost);
+        cudaFree(tmp);
+        if (rc) return rc;
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy D2H");
+        return GB_OK;
+    }
+    GB_CUDA(cudaMemcpy(host_out, g->coefs, bytes, cudaMemcpyDeviceToHost));
     return GB_OK;
 }
 int gb_grid_destroy(gb_grid* g) {
@@ -412,6 +450,11 @@ template <int N> void fill_params(const EvalCall& c, EvalParams<N>& p) {
     p.aos = 0;
     p.nchan = (int)g->nchan;
     p.cstride = g->total;
+    if (g->nchan > 1) {  // channel-interleaved resident layout: tap (i, c) at i*nchan + c
+        for (int d = 0; d < N; d++) p.stride[d] *= g->nchan;
+        p.total = g->total * g->nchan;
+        p.cstride = 1;
+    }
     p.work = nullptr; p.nwork = nullptr;
     for (int d = 0; d < N; d++) { p.tile[d] = 1; p.ntile[d] = 1; }
 }

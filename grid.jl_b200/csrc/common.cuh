@@ -158,6 +158,7 @@ int prolong3_device(int dtype, const i64* dims, const void* in, const i64* odims
 
 int irregular_device(int dtype, const void* knots, const void* coefs, i64 n, int bc, int it, double fill, const void* x, void* out, i64 nq, u64* first_invalid,
                      cudaStream_t s);
+int interleave_device(int dtype, const void* in, void* out, i64 st, i64 nchan, int to_interleaved, cudaStream_t s);
 int synth_device(int dtype, void* out, i64 n, u64 seed, double lo, double hi, i64 first, cudaStream_t s);
 
 }  // namespace gb

@@ -516,6 +516,31 @@ template <typename T> __global__ void __launch_bounds__(256) synth_kernel(T* out
 
 }  // namespace
 
+// channel-last (reference layout, element (i, c) at i + c*st) <-> channel-interleaved (i*nchan + c): the
+// resident layout of multi-valued grids, so that the nchan values under one tap are contiguous.
+template <typename T> __global__ void __launch_bounds__(256) interleave_kernel(const T* __restrict__ in, T* __restrict__ out, i64 st, i64 nchan, int to_interleaved) {
+    const i64 total = st * nchan;
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+        if (to_interleaved) {
+            const i64 i = e / nchan, c = e % nchan;
+            out[e] = in[i + c * st];
+        } else {
+            const i64 c = e / st, i = e % st;
+            out[e] = in[i * nchan + c];
+        }
+    }
+}
+int interleave_device(int dtype, const void* in, void* out, i64 st, i64 nchan, int to_interleaved, cudaStream_t s) {
+    if (st * nchan == 0) return GB_OK;
+    const int grid = grid_for(st * nchan, 256);
+    if (dtype == GB_F64) interleave_kernel<double><<<grid, 256, 0, s>>>((const double*)in, (double*)out, st, nchan, to_interleaved);
+    else if (dtype == GB_F32) interleave_kernel<float><<<grid, 256, 0, s>>>((const float*)in, (float*)out, st, nchan, to_interleaved);
+    else return fail(GB_ERR_ARG, "bad dtype");
+    count_launch();
+    GB_CUDA(cudaGetLastError());
+    return GB_OK;
+}
+
 int restrict_device(int dtype, int ndim, const i64* dims, const void* in, int dim, double scale, void* out, cudaStream_t s) {
     if (dtype == GB_F64) return restrict_impl<double>(ndim, dims, (const double*)in, dim, scale, (double*)out, s);
     if (dtype == GB_F32) return restrict_impl<float>(ndim, dims, (const float*)in, dim, scale, (float*)out, s);
