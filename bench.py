@@ -75,7 +75,7 @@ class ClockSampler:
         }
         while not self._stop.is_set():
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.samples.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
@@ -85,7 +85,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.001)  # the timed region is ~30 ms: sample densely
 
     def __enter__(self):
         if self.nv:
@@ -98,9 +98,14 @@ class ClockSampler:
         if self._t:
             self._t.join()
 
-    def summary(self):
-        s = sorted(self.samples)
-        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+    def summary(self, window=None):
+        """Median SM clock over the samples inside `window` = (t0, t1) (the timed region); the sampler runs
+        from the warm-up to the end of the GPU work, so `samples_under_load` covers the whole busy phase."""
+        allv = sorted(v for _, v in self.samples)
+        inw = sorted(v for t, v in self.samples if window and window[0] <= t <= window[1])
+        use = inw if inw else allv
+        return {"sm_mhz": (use[len(use) // 2] if use else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(inw), "samples_under_load": len(allv), "sm_mhz_min_under_load": (allv[0] if allv else None)}
 
 
 def run_reference(args):
@@ -209,6 +214,8 @@ def main():
     def step():
         gb.valgrad_(val, grad, G, X, fast=args.fast)
 
+    clk = ClockSampler(local)
+    clk.__enter__()  # samples SM clock / throttle reasons from the warm-up until the GPU work below is done
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
@@ -217,12 +224,13 @@ def main():
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     l0 = gb.launch_count()
-    with ClockSampler(local) as clk:
-        ev[0].record()
-        for i in range(args.steps):
-            step()
-            ev[i + 1].record()
-        torch.cuda.synchronize()
+    t_win0 = time.perf_counter()
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    t_win1 = time.perf_counter()
     launches = gb.launch_count() - l0
     if world > 1:
         dist.barrier()
@@ -293,6 +301,7 @@ def main():
         e2e = {"value": world * NQ / dt / 1e9, "unit": "Gpoints/s", "h2d_bytes_per_step": NQ * 24, "d2h_bytes_per_step": NQ * 32,
                "ms_per_step": dt * 1e3, "steps": ksteps, "host_memory": "pinned"}
 
+    clk.__exit__()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -347,7 +356,7 @@ def main():
                    "queries_per_gpu_per_step": NQ, "query_distribution": "uniform [1,256]^3, splitmix64", "contraction": "FAST" if args.fast else "EXACT",
                    "l2": "inputs larger than L2 (240 MB in + 320 MB out + 137 MB grid per step vs 126 MB L2)",
                    "parallelism": f"query-sharded x{world}, coefficients replicated by NCCL broadcast"},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(),
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary((t_win0, t_win1)),
         "extra": {"prefilter_ms": pref_ms, "prefilter_note": "InterpGrid(A,BCnan,InterpCubic) on device: pad + 3 prefilter sweeps of 258^3 f64",
                   "step_ms_min": per[0], "step_ms_median": per[len(per) // 2], "step_ms_max": per[-1],
                   "other_contraction": other,
