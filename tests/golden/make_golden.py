@@ -54,6 +54,35 @@ def main():
         R = O.restrict_flags(A, [True] * len(shape))
         P = O.prolong_sizes(R, list(shape))
         np.savez_compressed(os.path.join(HERE, f"mg_{len(shape)}d.npz"), A=A, R=R, P=P)
+    # ---- widening rows: edge-corrected multigrid variants, multi-valued grids, InterpIrregular
+    for k, shape in enumerate([(9, 10), (8, 7, 6)]):
+        for dt in (np.float64, np.float32):
+            A = O.synth(dt, int(np.prod(shape)), seed=950 + k).reshape(shape, order="F")
+            out = dict(A=A)
+            for d in range(len(shape)):
+                out[f"restrictb_{d}"] = O.restrictb(A, d, 1.0)
+                out[f"extrap_{d}"] = O.restrict_extrap(A, d, 1.0)
+                out[f"prolongb_{d}"] = O.prolongb(out[f"restrictb_{d}"], d, shape[d])
+            np.savez_compressed(os.path.join(HERE, f"mgb_{len(shape)}d_{np.dtype(dt).name}.npz"), **out)
+    shape, nchan = (12, 10), 3
+    A = O.synth(np.float64, int(np.prod(shape)) * nchan, seed=970).reshape(shape + (nchan,), order="F")
+    X = 1.0 + O.synth(np.float64, 200 * 2, seed=971).reshape(200, 2) * (np.array(shape) - 1.0)
+    vals, grads, coefs = [], [], []
+    for c in range(nchan):
+        co = O.make_coefs(np.ascontiguousarray(A[..., c]), "reflect", "quadratic")
+        v, g, _, _ = O.evaluate(co, "reflect", "quadratic", X, V | G)
+        coefs.append(co); vals.append(v); grads.append(g)
+    np.savez_compressed(os.path.join(HERE, "channels_quadratic_reflect_2d.npz"), A=A, X=X, coefs=np.stack(coefs, axis=-1), val=np.stack(vals, axis=1),
+                        grad=np.stack(grads, axis=1))
+    knots = np.sort(O.synth(np.float64, 30, seed=980, lo=-2.0, hi=5.0))
+    samples = O.synth(np.float64, 30, seed=981)
+    xq = O.synth(np.float64, 300, seed=982, lo=-3.0, hi=6.0)
+    out = dict(knots=knots, samples=samples, x=xq)
+    for it in ("forward", "backward", "nearest", "linear"):
+        out[f"nan_{it}"] = O.irregular(knots, samples, "nan", it, xq)[0]
+        out[f"nearest_{it}"] = O.irregular(knots, samples, "nearest", it, xq)[0]
+        out[f"fill_{it}"] = O.irregular(knots, samples, "fill", it, xq, fill=-7.5)[0]
+    np.savez_compressed(os.path.join(HERE, "irregular_1d.npz"), **out)
 
 
 if __name__ == "__main__":

@@ -357,6 +357,26 @@ def test_golden_fixtures(gb):
         z = np.load(f)
         assert same(gb.restrict(z["A"], [True] * z["A"].ndim), z["R"])
         assert same(gb.prolong(z["R"], list(z["A"].shape)), z["P"])
+    # widening rows
+    files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "mgb_*.npz")))
+    assert len(files) == 4
+    for f in files:
+        z = np.load(f)
+        A = z["A"]
+        for d in range(A.ndim):
+            assert same(gb.restrictb(A, d + 1), z[f"restrictb_{d}"])
+            assert same(gb.restrict_extrap(A, d + 1), z[f"extrap_{d}"])
+            assert same(gb.prolongb(z[f"restrictb_{d}"], d + 1, A.shape[d]), z[f"prolongb_{d}"])
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "channels_quadratic_reflect_2d.npz"))
+    g = gb.InterpGridChannels(np.asfortranarray(z["A"]), gb.BCreflect, gb.InterpQuadratic)
+    assert same(g.coefs, np.asfortranarray(z["coefs"]))
+    v, gr, _ = g._eval(z["X"], V | G)
+    assert same(v, z["val"]) and same(gr, z["grad"])
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "irregular_1d.npz"))
+    for it, IT in (("forward", gb.InterpForward), ("backward", gb.InterpBackward), ("nearest", gb.InterpNearest), ("linear", gb.InterpLinear)):
+        assert same(gb.InterpIrregular(z["knots"], z["samples"], gb.BCnan, IT)[z["x"]], z[f"nan_{it}"])
+        assert same(gb.InterpIrregular(z["knots"], z["samples"], gb.BCnearest, IT)[z["x"]], z[f"nearest_{it}"])
+        assert same(gb.InterpIrregular(z["knots"], z["samples"], -7.5, IT)[z["x"]], z[f"fill_{it}"])
 
 
 def test_full_size_properties_c2(gb):
