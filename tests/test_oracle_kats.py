@@ -501,3 +501,36 @@ def test_interp_irregular_reference_semantics(oracle):
     assert np.array_equal(bwd, [10.0, 10.0, 10.0, 20.0, 40.0, -1.0, -1.0])
     with pytest.raises(oracle.OracleError):
         oracle.irregular(g, c, "nil", "linear", [0.0])
+
+
+def test_oracle_reproduces_committed_golden_vectors(oracle):
+    """tests/golden/*.npz were written by make_golden.py from this oracle; the CPU suite keeps the two in
+    step (a drift of the restatement would otherwise only show up on the GPU box)."""
+    import glob
+    import os
+
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    files = sorted(glob.glob(os.path.join(here, "eval_*.npz")))
+    assert len(files) >= 9
+    for f in files:
+        z = np.load(f)
+        bc, order, mask = str(z["bc"]), str(z["order"]), int(z["mask"])
+        co = oracle.make_coefs(z["A"], bc, order, float(z["fill"]) if bc == "fill" else None)
+        assert co.dtype == z["coefs"].dtype and np.array_equal(co, z["coefs"], equal_nan=True)
+        v, g, h, _ = oracle.evaluate(co, bc, order, z["X"], mask, raise_invalid=False)
+        assert np.array_equal(v, z["val"], equal_nan=True)
+        if mask & 2:
+            assert np.array_equal(g, z["grad"], equal_nan=True)
+        if mask & 4:
+            assert np.array_equal(h, z["hess"], equal_nan=True)
+    for f in sorted(glob.glob(os.path.join(here, "mg_*.npz"))):
+        z = np.load(f)
+        assert np.array_equal(oracle.restrict_flags(z["A"], [True] * z["A"].ndim), z["R"])
+        assert np.array_equal(oracle.prolong_sizes(z["R"], list(z["A"].shape)), z["P"])
+    for f in sorted(glob.glob(os.path.join(here, "mgb_*.npz"))):
+        z = np.load(f)
+        for d in range(z["A"].ndim):
+            assert np.array_equal(oracle.restrictb(z["A"], d, 1.0), z[f"restrictb_{d}"])
+            assert np.array_equal(oracle.restrict_extrap(z["A"], d, 1.0), z[f"extrap_{d}"])
+    z = np.load(os.path.join(here, "irregular_1d.npz"))
+    assert np.array_equal(oracle.irregular(z["knots"], z["samples"], "nan", "linear", z["x"])[0], z["nan_linear"], equal_nan=True)
