@@ -1380,7 +1380,8 @@ int launch_one(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
         }
         for (int d = 0; d < N; d++) { p.tile[d] = 1; p.ntile[d] = 1; }
         const i64 need = (p.nq + EVAL_BLOCK - 1) / EVAL_BLOCK;
-        const i64 cap = (i64)num_sms() * blocks_plain * 4;  // a few waves, then CTAs stride over the blocks
+        // one resident wave for small batches (measured: 1e6 queries 43 vs 52 us), a few waves otherwise; CTAs stride over the blocks
+        const i64 cap = (i64)num_sms() * blocks_plain * (p.nq < (1ll << 22) ? 1 : 4);
         const int grid = (int)(need < cap ? (need > 0 ? need : 1) : cap);
         kern<<<grid, EVAL_BLOCK, 0, s>>>(p);
         count_launch();
