@@ -49,47 +49,63 @@ int prof_read(double* ms, int n, int* nstages) {
     return GB_OK;
 }
 
-// One CTA of 1024 threads.  Each thread owns a contiguous slice of bins; block-wide exclusive scans
-// of (queries per slice) and (work items per slice) give every thread its starting offsets.
+// One CTA of 1024 threads.  Each thread owns a contiguous slice of at most SCAN_PER bins (held in
+// registers: one pass over global memory); warp-shuffle scans of (queries per slice) and (work items per
+// slice), then a 32-entry scan of the warp totals, give every thread its starting offsets.
+constexpr int SCAN_PER = 12;  // 1024 * 12 >= SORT_MAX_BINS
 __global__ void __launch_bounds__(1024) tile_scan_kernel(const u32* __restrict__ hist, u32 nbins, u32* __restrict__ offs, u32* __restrict__ work,
                                                          u32* __restrict__ nwork, u32 chunk) {
-    __shared__ u32 s_cnt[1024], s_itm[1024];
-    const u32 t = threadIdx.x;
-    const u32 per = (nbins + 1023) / 1024;
-    const u32 b0 = min(t * per, nbins), b1 = min(b0 + per, nbins);
+    __shared__ u32 s_wc[32], s_wi[32];
+    const u32 t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const u32 per = (nbins + 1023) / 1024;  // <= SCAN_PER
+    const u32 b0 = min(t * per, nbins);
+    u32 h[SCAN_PER];
     u32 cnt = 0, itm = 0;
-    for (u32 b = b0; b < b1; b++) {
-        const u32 h = hist[b];
-        cnt += h;
-        itm += (h + chunk - 1) / chunk;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER; k++) {
+        const u32 b = b0 + k;
+        h[k] = ((u32)k < per && b < nbins) ? hist[b] : 0u;
+        cnt += h[k];
+        itm += (h[k] + chunk - 1) / chunk;
     }
-    s_cnt[t] = cnt;
-    s_itm[t] = itm;
+    u32 ic = cnt, ii = itm;  // inclusive scans within the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 a = __shfl_up_sync(0xffffffffu, ic, o), b = __shfl_up_sync(0xffffffffu, ii, o);
+        if ((int)lane >= o) { ic += a; ii += b; }
+    }
+    if (lane == 31) { s_wc[warp] = ic; s_wi[warp] = ii; }
     __syncthreads();
-    // Hillis-Steele inclusive scan over 1024 entries
-    for (u32 d = 1; d < 1024; d <<= 1) {
-        u32 a = 0, b = 0;
-        if (t >= d) { a = s_cnt[t - d]; b = s_itm[t - d]; }
-        __syncthreads();
-        s_cnt[t] += a;
-        s_itm[t] += b;
-        __syncthreads();
-    }
-    u32 o = s_cnt[t] - cnt, w = s_itm[t] - itm;  // exclusive
-    for (u32 b = b0; b < b1; b++) {
-        const u32 h = hist[b];
-        offs[b] = o;
-        const u32 n = (h + chunk - 1) / chunk;           // items of this bin ...
-        const u32 sz = n ? (h + n - 1) / n : 0;          // ... of equal size
-        for (u32 k = 0; k < n; k++) {
-            work[3 * w] = b;
-            work[3 * w + 1] = o + k * sz;
-            work[3 * w + 2] = o + min((k + 1) * sz, h);
-            w++;
+    if (warp == 0) {
+        u32 wc = s_wc[lane], wi = s_wi[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 a = __shfl_up_sync(0xffffffffu, wc, o), b = __shfl_up_sync(0xffffffffu, wi, o);
+            if ((int)lane >= o) { wc += a; wi += b; }
         }
-        o += h;
+        s_wc[lane] = wc;  // inclusive over warps
+        s_wi[lane] = wi;
     }
-    if (t == 1023) { nwork[0] = s_itm[1023]; nwork[1] = 0; }  // item count, and the counter CTAs pull items from
+    __syncthreads();
+    u32 o = (warp ? s_wc[warp - 1] : 0u) + ic - cnt;  // exclusive offsets of this thread's slice
+    u32 w = (warp ? s_wi[warp - 1] : 0u) + ii - itm;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER; k++) {
+        const u32 b = b0 + k;
+        if ((u32)k < per && b < nbins) {
+            offs[b] = o;
+            const u32 n = (h[k] + chunk - 1) / chunk;            // items of this bin ...
+            const u32 sz = n ? (h[k] + n - 1) / n : 0;           // ... of equal size
+            for (u32 j = 0; j < n; j++) {
+                work[3 * w] = b;
+                work[3 * w + 1] = o + j * sz;
+                work[3 * w + 2] = o + min((j + 1) * sz, h[k]);
+                w++;
+            }
+            o += h[k];
+        }
+    }
+    if (t == 1023) { nwork[0] = s_wi[31]; nwork[1] = 0; }  // item count, and the counter CTAs pull items from
 }
 
 // hist[b] = sum over CTAs of bh[b][cta]; one warp per bin.
