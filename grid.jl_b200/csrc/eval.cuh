@@ -844,8 +844,28 @@ template <typename T, int N> __device__ __forceinline__ void load_record(const T
     }
 }
 
+// sort key of a query: the tile of its lowest tap per dimension (a locality hint only -- queries whose taps
+// leave the brick are deferred); invalid locations go to the extra last bin
 template <typename T, int N, int ORDER, int BCF>
-__global__ void __launch_bounds__(SORT_BLOCK) tile_hist_kernel(const EvalParams<N> p, u32* __restrict__ keys, u32* __restrict__ bh, u32 nbins, i64 per_cta) {
+__device__ __forceinline__ u32 tile_key(const EvalParams<N>& p, const T (&x)[N], const int (&shift)[N], int ntot) {
+    int c[N][ORDER + 1];
+    T dx[N];
+    const bool valid = query_taps<T, N, ORDER, BCF>(p, x, c, dx);
+    u32 key = 0, mul = 1;
+#pragma unroll
+    for (int d = 0; d < N; d++) {
+        int lo = c[d][0];
+#pragma unroll
+        for (int i = 1; i <= ORDER; i++) lo = c[d][i] < lo ? c[d][i] : lo;
+        lo = lo < 0 ? 0 : (lo >= p.len[d] ? p.len[d] - 1 : lo);
+        key += (u32)(lo >> shift[d]) * mul;
+        mul *= (u32)p.ntile[d];
+    }
+    return valid ? key : (u32)ntot;
+}
+
+template <typename T, int N, int ORDER, int BCF>
+__global__ void __launch_bounds__(SORT_BLOCK) tile_hist_kernel(const EvalParams<N> p, u32* __restrict__ bh, u32 nbins, i64 per_cta) {
     extern __shared__ u32 s_hist[];
     for (u32 b = threadIdx.x; b < nbins; b += SORT_BLOCK) s_hist[b] = 0;
     __syncthreads();
@@ -874,22 +894,7 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_hist_kernel(const EvalParams<
                 T x[N];
 #pragma unroll
                 for (int d = 0; d < N; d++) x[d] = index_coord<T, N>(p, d, raw[u][d]);
-                int c[N][ORDER + 1];
-                T dx[N];
-                const bool valid = query_taps<T, N, ORDER, BCF>(p, x, c, dx);
-                u32 key = 0, mul = 1;
-#pragma unroll
-                for (int d = 0; d < N; d++) {
-                    int lo = c[d][0];
-#pragma unroll
-                    for (int i = 1; i <= ORDER; i++) lo = c[d][i] < lo ? c[d][i] : lo;
-                    lo = lo < 0 ? 0 : (lo >= p.len[d] ? p.len[d] - 1 : lo);
-                    key += (u32)(lo >> shift[d]) * mul;
-                    mul *= (u32)p.ntile[d];
-                }
-                if (!valid) key = (u32)ntot;
-                keys[q] = key;
-                atomicAdd(s_hist + key, 1u);
+                atomicAdd(s_hist + tile_key<T, N, ORDER, BCF>(p, x, shift, ntot), 1u);
             }
         }
     }
@@ -897,22 +902,24 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_hist_kernel(const EvalParams<
     for (u32 b = threadIdx.x; b < nbins; b += SORT_BLOCK) bh[(size_t)b * gridDim.x + blockIdx.x] = s_hist[b];
 }
 
-template <typename T, int N>
-__global__ void __launch_bounds__(SORT_BLOCK) tile_scatter_kernel(const EvalParams<N> p, const u32* __restrict__ keys, const u32* __restrict__ boff,
-                                                                  T* __restrict__ rec, u32* __restrict__ inv, u32 nbins, i64 per_cta) {
+// (the key is recomputed rather than carried over from tile_hist: this kernel waits on memory, the arithmetic is free)
+template <typename T, int N, int ORDER, int BCF>
+__global__ void __launch_bounds__(SORT_BLOCK) tile_scatter_kernel(const EvalParams<N> p, const u32* __restrict__ boff, T* __restrict__ rec,
+                                                                  u32* __restrict__ inv, u32 nbins, i64 per_cta) {
     extern __shared__ u32 s_cur[];
     for (u32 b = threadIdx.x; b < nbins; b += SORT_BLOCK) s_cur[b] = boff[(size_t)b * gridDim.x + blockIdx.x];
     __syncthreads();
+    int ntot = 1, shift[N];
+#pragma unroll
+    for (int d = 0; d < N; d++) { ntot *= p.ntile[d]; shift[d] = __ffs(p.tile[d]) - 1; }
     const i64 q0 = (i64)blockIdx.x * per_cta;
     const i64 q1 = q0 + per_cta < p.nq ? q0 + per_cta : p.nq;
     for (i64 qb = q0 + threadIdx.x; qb < q1; qb += SORT_BLOCK * SORT_UNROLL) {
         double raw[SORT_UNROLL][N];
-        u32 key[SORT_UNROLL];
 #pragma unroll
         for (int u = 0; u < SORT_UNROLL; u++) {
             const i64 q = qb + u * SORT_BLOCK;
             if (q < q1) {
-                key[u] = keys[q];
 #pragma unroll
                 for (int d = 0; d < N; d++) raw[u][d] = load_raw<N>(p, d, q);
             }
@@ -924,7 +931,7 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_scatter_kernel(const EvalPara
                 T x[N];
 #pragma unroll
                 for (int d = 0; d < N; d++) x[d] = index_coord<T, N>(p, d, raw[u][d]);
-                const u32 slot = atomicAdd(s_cur + key[u], 1u);
+                const u32 slot = atomicAdd(s_cur + tile_key<T, N, ORDER, BCF>(p, x, shift, ntot), 1u);
                 store_record<T, N>(rec, slot, x, (u32)q);
                 inv[q] = slot;
             }
@@ -1295,7 +1302,7 @@ int launch_tiled(const EvalParams<N>& p_in, cudaStream_t s) {
     const i64 per_cta = (p.nq + nctas - 1) / nctas;
     const size_t max_items = (size_t)nbins + (size_t)(p.nq / EVAL_CHUNK) + 2;
     const size_t pitch = ((size_t)p.nq + 15) & ~(size_t)15;
-    // one scratch allocation: records | sorted outputs | inv | keys | bh | boff | hist | offs | nwork | work
+    // one scratch allocation: records | sorted outputs | inv | deferred-slot list (`keys`) | bh | boff | hist | offs | nwork | work
     constexpr int W = out_words<N>(OUTMODE);
     const size_t nbc = (size_t)nbins * nctas;
     const size_t rec_bytes = (pitch * (N + 1) * sizeof(T) + 31) & ~(size_t)31;
@@ -1315,13 +1322,13 @@ int launch_tiled(const EvalParams<N>& p_in, cudaStream_t s) {
     u32* work = nwork + 4;
     const size_t hsmem = (size_t)nbins * sizeof(u32);
     prof_mark(0, s);
-    tile_hist_kernel<T, N, ORDER, BCF><<<nctas, SORT_BLOCK, hsmem, s>>>(p, keys, bh, nbins, per_cta);
+    tile_hist_kernel<T, N, ORDER, BCF><<<nctas, SORT_BLOCK, hsmem, s>>>(p, bh, nbins, per_cta);
     count_launch();
     prof_mark(1, s);
     int rc = tile_offsets(bh, nbins, nctas, hist, offs, boff, work, nwork, EVAL_CHUNK, s);
     if (rc) { cudaFreeAsync(scratch, s); return rc; }
     prof_mark(2, s);
-    tile_scatter_kernel<T, N><<<nctas, SORT_BLOCK, hsmem, s>>>(p, keys, boff, rec, inv, nbins, per_cta);
+    tile_scatter_kernel<T, N, ORDER, BCF><<<nctas, SORT_BLOCK, hsmem, s>>>(p, boff, rec, inv, nbins, per_cta);
     count_launch();
     GB_CUDA(cudaGetLastError());
     GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per device, cheap
@@ -1331,7 +1338,7 @@ int launch_tiled(const EvalParams<N>& p_in, cudaStream_t s) {
     p.work = work;
     p.nwork = nwork;
     const i64 grid = std::min<i64>((i64)max_items, (i64)num_sms() * bt);
-    // the keys are dead after the scatter: their buffer becomes the deferred-slot list (count first)
+    // the deferred-slot list (count first)
     u32* defer = keys;
     GB_CUDA(cudaMemsetAsync(defer, 0, sizeof(u32), s));
     p.aos = W;  // both kernels write one output record per sorted slot ...
