@@ -490,29 +490,36 @@ template <typename T> int invert_impl(T* A, int ndim, const i64* dims, int bc, i
 }
 
 template <typename T, int N> struct PadParams { i64 od[N]; i64 id[N]; };
-template <typename T, int N> __global__ void pad1_kernel(const T* __restrict__ in, T* __restrict__ out, i64 ototal, PadParams<T, N> p, T f) {
-    const i64 step = (i64)gridDim.x * blockDim.x;
-    for (i64 o = (i64)blockIdx.x * blockDim.x + threadIdx.x; o < ototal; o += step) {
-        i64 rem = o, src = 0, mul = 1;
+// One warp per output row (dim-0 line): the row's coordinates are decoded once, the lanes stream the row.
+template <typename T, int N> __global__ void __launch_bounds__(256) pad1_kernel(const T* __restrict__ in, T* __restrict__ out, i64 orows, PadParams<T, N> p, T f) {
+    const int lane = threadIdx.x & 31;
+    const i64 wstep = (i64)gridDim.x * (blockDim.x >> 5);
+    const int n0 = (int)p.od[0], i0 = (int)p.id[0];
+    for (i64 r = (i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < orows; r += wstep) {
+        i64 rem = r, src = 0, mul = p.id[0];
         bool inside = true;
 #pragma unroll
-        for (int d = 0; d < N; d++) {
+        for (int d = 1; d < N; d++) {
             const i64 c = rem % p.od[d];
             rem /= p.od[d];
             inside = inside && c >= 1 && c <= p.id[d];
             src += (c - 1) * mul;
             mul *= p.id[d];
         }
-        out[o] = inside ? in[src] : f;
+        T* o = out + r * n0;
+        const T* a = in + src - 1;  // a[x] for output column x in [1, i0]
+        for (int x = lane; x < n0; x += 32) o[x] = (inside && x >= 1 && x <= i0) ? a[x] : f;
     }
 }
 template <typename T, int N> int pad1_n(const i64* dims, const T* in, T f, T* out, cudaStream_t s) {
     PadParams<T, N> p;
     i64 ototal = 1;
     for (int d = 0; d < N; d++) { p.id[d] = dims[d]; p.od[d] = dims[d] + 2; ototal *= p.od[d]; }
-    const i64 need = (ototal + 255) / 256;
-    const int grid = (int)std::min<i64>(need, (i64)num_sms() * 32);
-    pad1_kernel<T, N><<<grid, 256, 0, s>>>(in, out, ototal, p, f);
+    if (p.od[0] >= (1ll << 31)) return fail(GB_ERR_UNSUPPORTED, "pad1: extent too large");
+    const i64 orows = ototal / p.od[0];
+    const i64 need = (orows + 7) / 8;
+    const int grid = (int)std::max<i64>(1, std::min<i64>(need, (i64)num_sms() * 32));
+    pad1_kernel<T, N><<<grid, 256, 0, s>>>(in, out, orows, p, f);
     count_launch();
     GB_CUDA(cudaGetLastError());
     return GB_OK;
