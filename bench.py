@@ -330,6 +330,13 @@ def main():
                 "algorithmic_bytes_per_launch": BYTES_PER_QUERY * NQ, "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / step_ms,
                 "stages_ms": stages, "step_achieved": step_achieved, "step_frac": step_achieved / peak,
                 "frac_of_nominal_8TBs": achieved / 8000.0,
+                # what actually bounds the EXACT kernel: the FP64 pipe (64 lanes/SM, one mul or add per lane per clock;
+                # ncu sm__pipe_fp64_cycles_active 80 %, profiles/r1_v12_exact_full.txt).  816 unfusable mul/add of the
+                # reference's contraction + ~130 for weights / coordinates per query; FAST: 192 FMA + ~75.
+                "fp64_pipe": (lambda ops, clk: {"ops_per_query": ops, "achieved_Tops": ops * NQ / (kernel_ms * 1e-3) / 1e12,
+                                                "peak_Tops": 64 * 148 * clk * 1e6 / 1e12,
+                                                "frac": ops * NQ / (kernel_ms * 1e-3) / (64 * 148 * clk * 1e6)})(
+                                                    267 if args.fast else 945, (clk.max_mhz or 1965)),
                 "limiter": "FP64 pipe (816 dependent mul/add per query in the reference's order)" if not args.fast else "shared-memory gathers + FP64 pipe"}
 
     # ---- CPU baseline (oracle port) on a bounded sample ---------------------------------------------------
