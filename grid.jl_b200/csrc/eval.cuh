@@ -1066,7 +1066,7 @@ __global__ void __launch_bounds__(BRICK_BLOCK, 2) eval_brick_kernel(const EvalPa
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ u32 s_it[2];
     __shared__ u32 s_cnt[2][16], s_cur[2][16], s_opull[2], s_off[17], s_ooff[17];  // counters: one set per item parity
-    __shared__ unsigned short s_boff[EVAL_CHUNK], s_idx[EVAL_CHUNK];
+    __shared__ unsigned short s_boff[BINNED ? EVAL_CHUNK : 1], s_idx[BINNED ? EVAL_CHUNK : 1];  // bank-class lists (FAST only)
     T* bricks = reinterpret_cast<T*>(smem_raw);
     const T* __restrict__ A = (const T*)p.coefs;
     const int vol = brick_stride(N, L, N - 1) * (p.tile[N - 1] + L - 1);
