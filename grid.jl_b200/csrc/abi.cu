@@ -777,6 +777,7 @@ int gb_eval_outer(const gb_grid* g, const int64_t* lens, const void* const* vecs
     if (!ok_dtype(xdtype)) return fail(GB_ERR_ARG, "xdtype must be GB_F32 or GB_F64");
     int rc = check_affine(g, affine);
     if (rc) return rc;
+    if (g->nchan > 1) return fail(GB_ERR_UNSUPPORTED, "tensor-product getindex is not provided for multi-valued grids");
     const int N = g->ndim;
     i64 nq = 1;
     for (int d = 0; d < N; d++) {

@@ -699,3 +699,23 @@ def test_brick_path_in_slices(gb, oracle):
         co = oracle.make_coefs(A, "nan", "cubic")
         ov, og, _, _ = oracle.evaluate(co, "nan", "cubic", X, 3)
         assert same(np.load(os.path.join(d, "v.npy")), ov) and same(np.load(os.path.join(d, "g.npy")), og)
+
+
+def test_stage_profiler(gb):
+    """gb_profile_enable / gb_profile_read (bench.py's roofline line): six positive stage times after a brick-path
+    call, nothing after a plain one."""
+    import torch
+
+    rng = np.random.default_rng(67)
+    A = np.asfortranarray(rng.standard_normal((40, 30, 20)))
+    g = gb.InterpGrid(A, gb.BCnan, gb.InterpCubic)
+    X = torch.from_numpy(make_queries(rng, A.shape, 50_000, np.float64, wide=False)).cuda()
+    gb.profile_enable(True)
+    try:
+        g._eval(X, 3, tiled=False)
+        assert gb.profile_read() == {}
+        g._eval(X, 3, tiled=True)
+        st = gb.profile_read()
+        assert tuple(st) == gb.PROFILE_STAGES and all(v > 0 for v in st.values())
+    finally:
+        gb.profile_enable(False)
