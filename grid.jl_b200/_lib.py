@@ -39,6 +39,7 @@ SIGNATURES = {
     "gb_grid_info": (i32, [vp, p_i32, p_i32, p_i64, p_i64, p_i32, p_i32, p_f64]),
     "gb_grid_coefs_device": (i32, [vp, p_vp]),
     "gb_grid_coefs_download": (i32, [vp, vp]),
+    "gb_grid_coefs_copy": (i32, [vp, vp, vp]),
     "gb_grid_destroy": (i32, [vp]),
     "gb_invert": (i32, [i32, i32, p_i64, vp, i32, i32, i32, p_i32, i32, vp]),
     "gb_pad1": (i32, [i32, i32, p_i64, vp, f64, vp, i32, vp]),

@@ -485,7 +485,12 @@ class InterpGrid(AbstractInterpGrid):
         """Borrowed column-major CUDA view of the resident coefficients (zero copy)."""
         torch = _torch()
         p = C.c_void_p()
-        L.check(self._lib.gb_grid_coefs_device(self._h, C.byref(p)))
+        rc = self._lib.gb_grid_coefs_device(self._h, C.byref(p))
+        if rc == L.GB_ERR_UNSUPPORTED:  # resident layout differs from the reference's (blocked): hand out a copy
+            out = jl_empty(self._stored, torch.float32 if self.dtype_code == L.GB_F32 else torch.float64)
+            L.check(self._lib.gb_grid_coefs_copy(self._h, out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+            return out
+        L.check(rc)
         n = int(np.prod(self._stored))
         esz = 4 if self.dtype_code == L.GB_F32 else 8
 

@@ -61,6 +61,7 @@ struct gb_grid {
     i64 total;   // stored elements of ONE channel
     i64 nchan;   // channels (multi-valued grids), 1 for a scalar grid; the channel is the slowest dimension
     void* coefs;
+    int blocked;  // resident layout: 4^N-element Morton blocks instead of column-major (wants_blocked below)
     int device;
     int shift;
 };
@@ -212,11 +213,38 @@ int gb_pad1(int dtype, int ndim, const int64_t* dims, const void* in, double fil
 static int new_grid(gb_grid** out, int dtype, int ndim, int bc, int order, double fill) {
     gb_grid* g = new gb_grid();
     g->dtype = dtype; g->ndim = ndim; g->bc = bc; g->order = order; g->fill = fill;
-    g->coefs = nullptr; g->total = 0; g->nchan = 1;
+    g->coefs = nullptr; g->total = 0; g->nchan = 1; g->blocked = 0;
     g->shift = needs_shift(bc, order) ? 1 : 0;
     for (int d = 0; d < MAXG; d++) g->user_dims[d] = g->stored_dims[d] = 1;
     if (cudaGetDevice(&g->device) != cudaSuccess) g->device = 0;
     *out = g;
+    return GB_OK;
+}
+
+// Blocked resident layout (tap_offset, eval.cuh): 2-D to 4-D scalar grids that L2 cannot hold and whose
+// neighbourhoods are too light for the brick path ever to be chosen (l^N * sizeof(T) < 256 B, launch_one), so
+// every evaluation is a random gather bound by DRAM granules.  GB_BLOCK_MIN_MB overrides the 48 MB threshold
+// (tests use 0).
+static bool wants_blocked(const gb_grid* g) {
+    static const double min_mb = [] { const char* e = getenv("GB_BLOCK_MIN_MB"); return e ? atof(e) : 48.0; }();
+    if (g->nchan != 1 || g->ndim < 2 || g->ndim > MAXD || (g->ndim == 4 && g->order >= GB_QUADRATIC)) return false;
+    double tap_bytes = (double)esize(g->dtype);
+    for (int d = 0; d < g->ndim; d++) tap_bytes *= g->order + 1;
+    const i64 be = blocked_elems(g->ndim, g->stored_dims);
+    return tap_bytes < 256 && (double)g->total * (double)esize(g->dtype) >= min_mb * 1048576.0 && be < (1ll << 32) &&
+           (double)be <= 1.25 * (double)g->total + 4096;
+}
+// g->coefs holds the column-major array: replace it by the blocked one
+static int to_blocked_layout(gb_grid* g, cudaStream_t s) {
+    void* fin = nullptr;
+    const size_t bytes = (size_t)blocked_elems(g->ndim, g->stored_dims) * esize(g->dtype);
+    GB_CUDA(cudaMalloc(&fin, bytes));
+    int rc = blocked_device(g->dtype, g->ndim, g->stored_dims, g->coefs, fin, 1, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (rc || e != cudaSuccess) { cudaFree(fin); return rc ? rc : cuda_fail(e, "cudaStreamSynchronize"); }
+    cudaFree(g->coefs);
+    g->coefs = fin;
+    g->blocked = 1;
     return GB_OK;
 }
 
@@ -292,6 +320,10 @@ static int grid_create_impl(gb_grid** out, int dtype, int ndim, const int64_t* d
         cudaFree(g->coefs);
         g->coefs = fin;
     }
+    if (wants_blocked(g)) {
+        rc = to_blocked_layout(g, s);
+        if (rc) return cleanup(rc);
+    }
     if (staged) cudaFreeAsync(staged, s);
     if (mem == GB_HOST) {
         e = cudaStreamSynchronize(s);
@@ -343,6 +375,10 @@ static int grid_from_coefs_impl(gb_grid** out, int dtype, int ndim, const int64_
     e = cudaMemcpyAsync(g->coefs, coefs, bytes, mem == GB_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s);
     if (e == cudaSuccess && mem == GB_HOST) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) { cudaFree(g->coefs); delete g; return cuda_fail(e, "copy coefs"); }
+    if (wants_blocked(g)) {
+        rc = to_blocked_layout(g, s);
+        if (rc) { cudaFree(g->coefs); delete g; return rc; }
+    }
     *out = g;
     return GB_OK;
 }
@@ -384,16 +420,28 @@ int gb_grid_info(const gb_grid* g, int* dtype, int* ndim, int64_t* user_dims, in
 }
 int gb_grid_coefs_device(const gb_grid* g, void** device_ptr) {
     if (!g || !device_ptr) return fail(GB_ERR_ARG, "NULL argument");
+    if (g->blocked || g->nchan > 1)
+        return fail(GB_ERR_UNSUPPORTED, "the resident coefficients of this grid are not in the reference layout (blocked / channel-interleaved); use gb_grid_coefs_copy");
     *device_ptr = g->coefs;
+    return GB_OK;
+}
+// G.coefs in the reference layout written to a caller-provided DEVICE buffer (any resident layout)
+int gb_grid_coefs_copy(const gb_grid* g, void* device_out, void* stream) {
+    if (!g || !device_out) return fail(GB_ERR_ARG, "NULL argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t bytes = (size_t)g->total * (size_t)g->nchan * esize(g->dtype);
+    if (g->blocked) return blocked_device(g->dtype, g->ndim, g->stored_dims, g->coefs, device_out, 0, s);
+    if (g->nchan > 1) return interleave_device(g->dtype, g->coefs, device_out, g->total, g->nchan, 0, s);
+    GB_CUDA(cudaMemcpyAsync(device_out, g->coefs, bytes, cudaMemcpyDeviceToDevice, s));
     return GB_OK;
 }
 int gb_grid_coefs_download(const gb_grid* g, void* host_out) {
     if (!g || !host_out) return fail(GB_ERR_ARG, "NULL argument");
     const size_t bytes = (size_t)g->total * (size_t)g->nchan * esize(g->dtype);
-    if (g->nchan > 1) {  // resident layout is channel-interleaved; the caller gets the reference's channel-last array
+    if (g->nchan > 1 || g->blocked) {  // resident layout is channel-interleaved / blocked; the caller gets the reference's array
         void* tmp = nullptr;
         GB_CUDA(cudaMalloc(&tmp, bytes));
-        int rc = interleave_device(g->dtype, g->coefs, tmp, g->total, g->nchan, 0, nullptr);
+        int rc = gb_grid_coefs_copy(g, tmp, nullptr);
         cudaError_t e = rc ? cudaSuccess : cudaMemcpy(host_out, tmp, bytes, cudaMemcpyDeviceToHost);
         cudaFree(tmp);
         if (rc) return rc;
@@ -448,6 +496,14 @@ template <int N> void fill_params(const EvalCall& c, EvalParams<N>& p) {
     p.q0 = c.q0;
     p.first_invalid = c.first_invalid;
     p.aos = 0;
+    p.blocked = g->blocked;
+    {
+        u32 bs = 1u << (2 * N);
+        for (int d = 0; d < N; d++) {
+            p.bstride[d] = bs;
+            bs *= (u32)((g->stored_dims[d] + 3) / 4);
+        }
+    }
     p.nchan = (int)g->nchan;
     p.cstride = g->total;
     if (g->nchan > 1) {  // channel-interleaved resident layout: tap (i, c) at i*nchan + c

@@ -101,6 +101,8 @@ template <int N> struct EvalParams {
     i64 nq;
     i64 q0;               // index of this launch's first query in the caller's batch
     u64* first_invalid;   // device, atomicMin target (BCnil) or NULL
+    int blocked;          // coefficients stored as 4^N-element Morton blocks (tap_offset, eval.cuh); N = 2..4
+    u32 bstride[N];       // elements between consecutive blocks along each dimension
     int nchan;            // channels sharing the taps/weights of a query (multi-valued grids); 1 = scalar grid
     i64 cstride;          // elements between consecutive channels of the coefficient array
     // brick (spatially binned) evaluation, filled in by launch_one / launch_tiled
@@ -159,6 +161,8 @@ int prolong3_device(int dtype, const i64* dims, const void* in, const i64* odims
 int irregular_device(int dtype, const void* knots, const void* coefs, i64 n, int bc, int it, double fill, const void* x, void* out, i64 nq, u64* first_invalid,
                      cudaStream_t s);
 int interleave_device(int dtype, const void* in, void* out, i64 st, i64 nchan, int to_interleaved, cudaStream_t s);
+int blocked_device(int dtype, int ndim, const i64* len, const void* in, void* out, int to_blocked, cudaStream_t s);
+i64 blocked_elems(int ndim, const i64* len);
 int synth_device(int dtype, void* out, i64 n, u64 seed, double lo, double hi, i64 first, cudaStream_t s);
 
 }  // namespace gb

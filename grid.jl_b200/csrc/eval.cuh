@@ -529,6 +529,51 @@ template <typename T, int N> __device__ __forceinline__ T scale_grad(const EvalP
     return g;
 }
 
+// Element offset contributed by coordinate c of dimension d.  Linear (column-major) layout: c * stride[d].
+// Blocked layout (p.blocked; 2-D to 4-D grids too large for L2 whose neighbourhoods are too light for the brick
+// path): the array is stored as 4^N-element blocks, Morton order inside a block (bit 0 of every coordinate,
+// then bit 1), blocks in column-major order.  The DRAM granule (64 B) then holds a 4x4 (f32) / 4x2 (f64) patch of
+// a 2-D grid or a 4x2x2 / 2x2x2 patch of a 3-D grid instead of 16 / 8 elements of one row, so the l^N
+// neighbourhood of a random query costs ~(1 + (l-1)/4)(1 + (l-1)/2)... granules instead of l^(N-1) or more:
+// the plain path on such grids is bound by exactly that traffic (profiles/README.md).  The offset stays a
+// SUM of per-dimension terms, so the contractions are untouched; results are bit-identical.
+template <int N> __device__ __forceinline__ u32 tap_offset(const EvalParams<N>& p, int d, int c) {
+    if constexpr (N >= 2 && N <= 4) {
+        if (p.blocked) return (u32)(c >> 2) * p.bstride[d] + (u32)((((c >> 1) & 1) << (N + d)) | ((c & 1) << d));
+    }
+    return (u32)c * (u32)p.stride[d];
+}
+// column-major element index -> index in the resident array (rare paths only)
+template <int N> __device__ __forceinline__ i64 resident_index(const EvalParams<N>& p, i64 j) {
+    if constexpr (N >= 2 && N <= 4) {
+        if (p.blocked) {
+            u32 o = 0;
+#pragma unroll
+            for (int d = 0; d < N; d++) {
+                o += tap_offset<N>(p, d, (int)(j % p.len[d]));
+                j /= p.len[d];
+            }
+            return (i64)o;
+        }
+    }
+    return j;
+}
+// Blocked layout and the D1 taps (one past a dimension's end: the reference's offset arithmetic carries them into
+// the next column / plane): such queries take eval_one_slow, which addresses through resident_index.
+template <int N, int L> __device__ __forceinline__ bool blocked_carry(const EvalParams<N>& p, const int (&c)[N][L]) {
+    bool carry = false;
+    if constexpr (N >= 2 && N <= 4) {
+        if (p.blocked) {
+#pragma unroll
+            for (int d = 0; d < N; d++) {
+#pragma unroll
+                for (int i = 0; i < L; i++) carry = carry || c[d][i] >= p.len[d];
+            }
+        }
+    }
+    return carry;
+}
+
 // taps of one query: validity + 0-based tap coordinates, including the reference's offset-table
 // addressing for InterpLinear.
 // set_position (src/interp.jl:406-428): unless SOME dimension reported a wrap, the reference
@@ -664,7 +709,7 @@ __device__ __noinline__ void eval_one_slow(const EvalParams<N>& p, const T* __re
             const T cf = pr[0];
             const i64 j = off[0];
             T term = (T)0;
-            if (cf != (T)0 && (!GUARD || (u64)j < (u64)p.total)) term = cf * A[j];
+            if (cf != (T)0 && (!GUARD || (u64)j < (u64)p.total)) term = cf * A[resident_index<N>(p, j)];
             acc = acc + term;
             int d = 0;
             for (; d < N; d++) {
@@ -713,11 +758,17 @@ __device__ __forceinline__ void eval_one(const EvalParams<N>& p, const T (&x)[N]
     for (int d = 0; d < N; d++) weights<ORDER, (OUTMODE >= 1), (OUTMODE >= 2), FAST>(dx[d], w[0][d], w[1][d], w[2][d]);
     GlobalTaps<T, N, L, GUARD> src;
     src.A = (const T*)p.coefs;
-    src.total = (u32)p.total;
+    src.total = p.blocked ? 0xffffffffu : (u32)p.total;
+    if constexpr (GUARD) {
+        if (blocked_carry<N, L>(p, c)) {
+            eval_one_slow<T, N, ORDER, BCF>(p, src.A, x, pos, q, OUTMODE);
+            return;
+        }
+    }
 #pragma unroll
     for (int d = 0; d < N; d++) {
 #pragma unroll
-        for (int i = 0; i < L; i++) src.off[d][i] = (u32)c[d][i] * (u32)p.stride[d];
+        for (int i = 0; i < L; i++) src.off[d][i] = tap_offset<N>(p, d, c[d][i]);
     }
     if (p.nchan == 1) {  // (kept apart from the channel loop: the loop costs the 3-D cubic kernels their registers)
         T acc[NP];
@@ -1375,7 +1426,7 @@ int launch_one(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     size_t tap_bytes = sizeof(T);
     for (int d = 0; d < N; d++) tap_bytes *= (size_t)L;
     if (!(flags & (GB_TILED | GB_PLAIN))) tiled = N >= 2 && tap_bytes >= 256 && p.nq >= (1ll << 20) && grid_bytes >= (48u << 20);
-    if (p.nchan > 1) tiled = false;  // multi-valued grids: plain path (one brick per channel would not fit)
+    if (p.nchan > 1 || p.blocked) tiled = false;  // multi-valued / blocked grids: plain path
     if (tiled) tiled = choose_tile(N, L, sizeof(T), p.len, std::min<i64>(p.nq, tiled_max_batch()), forced, p.tile, p.ntile);
     p.aos = 0;
     if (!tiled) {
@@ -1470,15 +1521,20 @@ __global__ void __launch_bounds__(256, 2) outer_eval_kernel(const EvalParams<N> 
         }
         GlobalTaps<T, N, L, GUARD> src;
         src.A = (const T*)p.coefs;
-        src.total = (u32)p.total;
-#pragma unroll
-        for (int d = 0; d < N; d++) {
-#pragma unroll
-            for (int k = 0; k < L; k++) src.off[d][k] = (u32)c[d][k] * (u32)p.stride[d];
-        }
+        src.total = p.blocked ? 0xffffffffu : (u32)p.total;
+        bool slow = false;
+        if constexpr (GUARD) slow = blocked_carry<N, L>(p, c);
         T acc[1];
-        contract<T, N, L, 0, FAST>(src, w, acc);
-        if (nonfinite(acc[0])) {  // literal zero-weight semantics, from the coordinates
+        if (!slow) {
+#pragma unroll
+            for (int d = 0; d < N; d++) {
+#pragma unroll
+                for (int k = 0; k < L; k++) src.off[d][k] = tap_offset<N>(p, d, c[d][k]);
+            }
+            contract<T, N, L, 0, FAST>(src, w, acc);
+            slow = nonfinite(acc[0]);
+        }
+        if (slow) {  // literal zero-weight semantics, from the coordinates
             T x[N];
 #pragma unroll
             for (int d = 0; d < N; d++) x[d] = index_coord<T, N>(p, d, load_raw<N>(p, d, idx[d]));

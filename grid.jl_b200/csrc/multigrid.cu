@@ -541,6 +541,46 @@ int interleave_device(int dtype, const void* in, void* out, i64 st, i64 nchan, i
     return GB_OK;
 }
 
+// column-major <-> blocked resident layout of a 2-D to 4-D coefficient array (tap_offset, eval.cuh): 4^N-element
+// blocks in column-major order, Morton order inside a block; cells past the array's edges are zero.
+i64 blocked_elems(int ndim, const i64* len) {
+    i64 n = 1;
+    for (int d = 0; d < ndim; d++) n *= 4 * ((len[d] + 3) / 4);
+    return n;
+}
+struct BlockedGeo { i64 len[4]; i64 nb[4]; int ndim; };
+template <typename T> __global__ void __launch_bounds__(256) blocked_kernel(const T* __restrict__ in, T* __restrict__ out, BlockedGeo g, i64 total, int to_blocked) {
+    const int N = g.ndim;
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+        i64 blk = e >> (2 * N), lin = 0, str = 1;
+        bool inside = true;
+        for (int d = 0; d < N; d++) {
+            const i64 c = 4 * (blk % g.nb[d]) + ((e >> d) & 1) + 2 * ((e >> (N + d)) & 1);
+            blk /= g.nb[d];
+            inside = inside && c < g.len[d];
+            lin += c * str;
+            str *= g.len[d];
+        }
+        if (to_blocked) out[e] = inside ? in[lin] : (T)0;
+        else if (inside) out[lin] = in[e];
+    }
+}
+int blocked_device(int dtype, int ndim, const i64* len, const void* in, void* out, int to_blocked, cudaStream_t s) {
+    if (ndim < 2 || ndim > 4) return fail(GB_ERR_ARG, "blocked layout: 2-D to 4-D arrays");
+    BlockedGeo g;
+    g.ndim = ndim;
+    for (int d = 0; d < ndim; d++) { g.len[d] = len[d]; g.nb[d] = (len[d] + 3) / 4; }
+    const i64 total = blocked_elems(ndim, len);
+    if (total == 0) return GB_OK;
+    const int grid = grid_for(total, 256);
+    if (dtype == GB_F64) blocked_kernel<double><<<grid, 256, 0, s>>>((const double*)in, (double*)out, g, total, to_blocked);
+    else if (dtype == GB_F32) blocked_kernel<float><<<grid, 256, 0, s>>>((const float*)in, (float*)out, g, total, to_blocked);
+    else return fail(GB_ERR_ARG, "bad dtype");
+    count_launch();
+    GB_CUDA(cudaGetLastError());
+    return GB_OK;
+}
+
 int restrict_device(int dtype, int ndim, const i64* dims, const void* in, int dim, double scale, void* out, cudaStream_t s) {
     if (dtype == GB_F64) return restrict_impl<double>(ndim, dims, (const double*)in, dim, scale, (double*)out, s);
     if (dtype == GB_F32) return restrict_impl<float>(ndim, dims, (const float*)in, dim, scale, (float*)out, s);

@@ -118,6 +118,11 @@ int gb_grid_info(const gb_grid* g, int* dtype, int* ndim, int64_t* user_dims, in
                  int* order, double* fill);
 int gb_grid_coefs_device(const gb_grid* g, void** device_ptr); /* borrowed, read-only */
 int gb_grid_coefs_download(const gb_grid* g, void* host_out);  /* G.coefs */
+/* G.coefs in the reference layout into a caller-provided DEVICE buffer.  Works for every grid; gb_grid_coefs_device
+   is refused (GB_ERR_UNSUPPORTED) when the resident layout differs from the reference's (multi-valued grids are kept
+   channel-interleaved; 2-D to 4-D grids of >= 48 MB whose neighbourhoods are lighter than 256 B are kept in 4^N-element
+   Morton blocks -- a pure addressing change, results are bit-identical; GB_BLOCK_MIN_MB overrides the threshold). */
+int gb_grid_coefs_copy(const gb_grid* g, void* device_out, void* stream);
 int gb_grid_destroy(gb_grid* g);
 
 /* ---- prefilter ---------------------------------------------------------------------------- */

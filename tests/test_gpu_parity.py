@@ -701,6 +701,77 @@ def test_brick_path_in_slices(gb, oracle):
         assert same(np.load(os.path.join(d, "v.npy")), ov) and same(np.load(os.path.join(d, "g.npy")), og)
 
 
+def test_blocked_layout(gb, oracle):
+    """Large 2-D to 4-D grids with light neighbourhoods are kept in 4^N-element Morton blocks (a pure addressing
+    change, eval.cuh tap_offset).  GB_BLOCK_MIN_MB=0 in a child process puts small grids in that layout: every
+    order and BC, all output modes, ragged extents (not multiples of 4), queries exactly on the upper edges
+    (the D1 / offset-table taps that carry into the next column), device and host queries, the tensor-product
+    call, and G.coefs back in the reference layout -- all bit-identical to the oracle."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+
+    rng = np.random.default_rng(71)
+    shapes2 = [(37, 22), (8, 4), (5, 6), (4, 9)]
+    shapes3 = [(9, 6, 5), (4, 8, 7), (13, 4, 6), (5, 4, 6, 5)]  # (the 4-D one: Nearest / Linear are blocked, the generic kernel's orders are not)
+    cases = [(bc, order) for order in ORDERS for bc in BCS if not (order == "cubic" and bc in ("reflect", "periodic", "nearest", "fill"))]
+    with tempfile.TemporaryDirectory() as d:
+        code = (
+            "import sys, numpy as np, torch\n"
+            f"sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})\n"
+            "import grid_jl_b200 as gb\n"
+            "BC = dict(nil=gb.BCnil, nan=gb.BCnan, na=gb.BCna, reflect=gb.BCreflect, periodic=gb.BCperiodic, nearest=gb.BCnearest)\n"
+            "IT = dict(nearest=gb.InterpNearest, linear=gb.InterpLinear, quadratic=gb.InterpQuadratic, cubic=gb.InterpCubic)\n"
+            f"d = {d!r}\n"
+            "for line in open(d + '/cases.txt'):\n"
+            "    tag, bc, order, mode = line.split()\n"
+            "    z = np.load(f'{d}/in_{tag}.npz'); A = np.asfortranarray(z['A']); X = z['X']\n"
+            "    g = gb.InterpGrid(A, -1.25, IT[order]) if bc == 'fill' else gb.InterpGrid(A, BC[bc], IT[order])\n"
+            "    v, gr, h = g._eval(torch.from_numpy(X).cuda(), int(mode))\n"
+            "    out = dict(v=v.cpu().numpy(), g=gr.cpu().numpy(), hv=gb.getindex_batch(g, X), c=g.coefs, cd=gb.jl_to_numpy(g.coefs_device()))\n"
+            "    if h is not None: out['h'] = h.cpu().numpy()\n"
+            "    out['o'] = g[tuple(z[f'x{k}'] for k in range(A.ndim))]\n"
+            "    np.savez(f'{d}/out_{tag}.npz', **out)\n"
+        )
+        keep = []
+        with open(os.path.join(d, "cases.txt"), "w") as f:
+            k = 0
+            for bc, order in cases:
+                for shape in (shapes2[k % len(shapes2)], shapes3[k % len(shapes3)]):
+                    dtype = np.float32 if k % 3 == 2 else np.float64
+                    A = np.asfortranarray(rng.standard_normal(shape).astype(dtype))
+                    wide = bc != "nil"
+                    X = make_queries(rng, shape, 3000, dtype, wide=wide)
+                    if bc == "nil":  # keep the valid locations (same validity rule as BCnan, whose answer there is NaN)
+                        ok = ~np.isnan(oracle.evaluate(oracle.make_coefs(A, "nan", order), "nan", order, X, 1)[0])
+                        X = np.ascontiguousarray(X[ok])
+                    vecs = {}
+                    for j, n in enumerate(shape):
+                        lo, hi = (-1.5 * n, 2.5 * n) if wide else (2.0, n - 1.0)
+                        vecs[f"x{j}"] = np.concatenate([lo + rng.random(4) * (hi - lo), [float(n - 1), 2.0]]).astype(dtype)
+                    mode = 7 if order in ("quadratic", "cubic") else 3
+                    tag = f"{k}_{len(shape)}"
+                    np.savez(os.path.join(d, f"in_{tag}.npz"), A=A, X=X, **vecs)
+                    f.write(f"{tag} {bc} {order} {mode}\n")
+                    keep.append((tag, bc, order, A, X, vecs, dtype, mode))
+                k += 1
+        env = dict(os.environ, GB_BLOCK_MIN_MB="0")
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+        assert out.returncode == 0, out.stderr[-3000:]
+        for tag, bc, order, A, X, vecs, dtype, mode in keep:
+            fill = -1.25 if bc == "fill" else None
+            co = oracle.make_coefs(A, bc, order, fill)
+            ov, og, oh, _ = oracle.evaluate(co, bc, order, X, mode)
+            z = np.load(os.path.join(d, f"out_{tag}.npz"))
+            assert same(z["v"], ov) and same(z["g"], og) and same(z["hv"], ov), (tag, bc, order)
+            if mode == 7:
+                assert same(z["h"], oh), (tag, bc, order)
+            assert same(z["c"], co) and same(z["cd"], co), (tag, bc, order)
+            ref = oracle.OracleGrid(A, bc, order, fill=fill).outer(*[vecs[f"x{j}"] for j in range(A.ndim)])
+            assert same(z["o"], ref.astype(dtype)), (tag, bc, order)
+
+
 def test_stage_profiler(gb):
     """gb_profile_enable / gb_profile_read (bench.py's roofline line): six positive stage times after a brick-path
     call, nothing after a plain one."""
