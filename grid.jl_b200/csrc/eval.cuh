@@ -990,6 +990,58 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_scatter_kernel(const EvalPara
     }
 }
 
+// ---- the two sort passes for grids with more tiles than a shared-memory histogram holds (> sort_smem_bins(), e.g.
+// 512^3 f64: 7.1e4 tiles): one histogram / cursor array in global memory, updated with warp-aggregated atomics
+// (lanes of a warp that hit the same tile share one atomic, so a clustered batch does not serialise on one
+// address).  The order of the records inside a tile then depends on scheduling; results do not (every query is
+// evaluated on its own and returned to its own position).
+template <typename T, int N, int ORDER, int BCF, bool SCATTER>
+__global__ void __launch_bounds__(SORT_BLOCK) tile_sort_global_kernel(const EvalParams<N> p, u32* __restrict__ bins, T* __restrict__ rec, u32* __restrict__ inv,
+                                                                      i64 per_cta) {
+    int ntot = 1, shift[N];
+#pragma unroll
+    for (int d = 0; d < N; d++) { ntot *= p.ntile[d]; shift[d] = __ffs(p.tile[d]) - 1; }
+    const i64 q0 = (i64)blockIdx.x * per_cta;
+    const i64 q1 = q0 + per_cta < p.nq ? q0 + per_cta : p.nq;
+    const u32 lane = threadIdx.x & 31;
+    for (i64 qb0 = q0; qb0 < q1; qb0 += SORT_BLOCK * SORT_UNROLL) {  // (uniform trip count: the warp votes below need every lane)
+        const i64 qb = qb0 + threadIdx.x;
+        double raw[SORT_UNROLL][N];
+#pragma unroll
+        for (int u = 0; u < SORT_UNROLL; u++) {
+            const i64 q = qb + u * SORT_BLOCK;
+            if (q < q1) {
+#pragma unroll
+                for (int d = 0; d < N; d++) raw[u][d] = load_raw<N>(p, d, q);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < SORT_UNROLL; u++) {
+            const i64 q = qb + u * SORT_BLOCK;
+            const bool act = q < q1;
+            T x[N];
+            u32 key = 0xffffffffu;
+            if (act) {
+#pragma unroll
+                for (int d = 0; d < N; d++) x[d] = index_coord<T, N>(p, d, raw[u][d]);
+                key = tile_key<T, N, ORDER, BCF>(p, x, shift, ntot);
+            }
+            const u32 peers = __match_any_sync(0xffffffffu, key);
+            const u32 leader = __ffs(peers) - 1;
+            u32 base = 0;
+            if (act && lane == leader) base = atomicAdd(bins + key, (u32)__popc(peers));
+            if constexpr (SCATTER) {
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (act) {
+                    const u32 slot = base + __popc(peers & ((1u << lane) - 1));
+                    store_record<T, N>(rec, slot, x, (u32)q);
+                    inv[q] = slot;
+                }
+            }
+        }
+    }
+}
+
 // ---- cp.async (Ampere-style async copies are the right granule here: brick rows are short and
 // arbitrarily aligned, so elements travel one by one; zero-fill handles cells past the array) ---------
 template <int BYTES> __device__ __forceinline__ void cp_async_zfill(u32 saddr, const void* g, bool pred) {
@@ -1142,7 +1194,7 @@ __global__ void __launch_bounds__(BRICK_BLOCK, 2) eval_brick_kernel(const EvalPa
     u32 cur = s_it[0];
     u32 tile_c = 0, beg_c = 0, end_c = 0;
     if (cur < nwork) {
-        tile_c = work[3 * cur]; beg_c = work[3 * cur + 1]; end_c = work[3 * cur + 2];
+        { const uint4 it = reinterpret_cast<const uint4*>(work)[cur]; tile_c = it.x; beg_c = it.y; end_c = it.z; }
         if (tile_c < ntot) brick_fill<T, N, L>(p, A, bricks, tile_c, vol);
     }
     cp_async_commit();
@@ -1162,7 +1214,7 @@ __global__ void __launch_bounds__(BRICK_BLOCK, 2) eval_brick_kernel(const EvalPa
         const u32 nxt = s_it[par ^ 1];
         u32 tile_n = 0, beg_n = 0, end_n = 0;
         if (nxt < nwork) {
-            tile_n = work[3 * nxt]; beg_n = work[3 * nxt + 1]; end_n = work[3 * nxt + 2];
+            { const uint4 it = reinterpret_cast<const uint4*>(work)[nxt]; tile_n = it.x; beg_n = it.y; end_n = it.z; }
             if (tile_n < ntot) brick_fill<T, N, L>(p, A, bricks + (size_t)(par ^ 1) * volp, tile_n, vol);
         }
         cp_async_commit();
@@ -1326,17 +1378,24 @@ __global__ void __launch_bounds__(256) unpermute_kernel(const T* __restrict__ os
 
 // eval_tile.cu
 int tile_offsets(const u32* bh, u32 nbins, u32 nctas, u32* hist, u32* offs, u32* boff, u32* work, u32* nwork, u32 chunk, cudaStream_t s);
+int tile_offsets_global(const u32* hist, u32 nbins, u32* offs, u32* cursor, u32* work, u32* nwork, u32 chunk, cudaStream_t s);
 bool choose_tile(int N, int L, size_t esz, const int* len, i64 nq, bool forced, int* tile, int* ntile);
-constexpr u32 SORT_MAX_BINS = 12000;  // per-CTA histogram lives in shared memory (<= 48 KB)
-// Larger batches are evaluated in slices: bounds the record scratch, and (more importantly) keeps the
-// randomly written regions -- the slice's records and its outputs -- small enough to live in L2.
-inline i64 tiled_max_batch() {
-    static const i64 v = [] {
+u32 sort_smem_bins();  // 12000: per-CTA histograms live in shared memory (<= 48 KB); more tiles: tile_sort_global_kernel
+// Larger batches are evaluated in slices: bounds the record scratch, and keeps the randomly written regions -- the
+// slice's records and its outputs -- from outgrowing L2 by too much: the two permutations of a 4e7-query batch
+// cost 3.13 ms in one piece, 4 x 0.55 ms in four (256^3 f64: 6.11 -> 5.41 ms).  Slices must stay large against the
+// number of tiles, though (every slice stages every occupied brick again: 512^3, 7.1e4 tiles, 4e7 queries: 6.96 ms
+// in one piece, 8.69 ms in four), and slicing a 1e7 batch loses.  Hence: equal slices of at most
+// clamp(1024 queries per tile, 2^24, 2^26) queries; GB_TILED_BATCH overrides the limit.
+inline i64 tiled_max_batch(i64 ntiles = -1) {
+    static const i64 env = [] {
         const char* e = getenv("GB_TILED_BATCH");
         const long long x = e ? atoll(e) : 0;
-        return (i64)(x >= 1024 ? x : ((i64)1 << 26));
+        return (i64)(x >= 1024 ? x : 0);
     }();
-    return v;
+    if (env) return env;
+    if (ntiles < 0) return (i64)1 << 26;
+    return std::max<i64>((i64)1 << 24, std::min<i64>((i64)1 << 26, ntiles * 1024));
 }
 
 template <typename T, int N, int ORDER, int BCF, int OUTMODE, bool FAST>
@@ -1353,34 +1412,48 @@ int launch_tiled(const EvalParams<N>& p_in, cudaStream_t s) {
     const i64 per_cta = (p.nq + nctas - 1) / nctas;
     const size_t max_items = (size_t)nbins + (size_t)(p.nq / EVAL_CHUNK) + 2;
     const size_t pitch = ((size_t)p.nq + 15) & ~(size_t)15;
-    // one scratch allocation: records | sorted outputs | inv | deferred-slot list (`keys`) | bh | boff | hist | offs | nwork | work
+    // one scratch allocation: records | sorted outputs | inv | deferred-slot list (`keys`) | work | bh | boff | hist | offs | nwork
     constexpr int W = out_words<N>(OUTMODE);
-    const size_t nbc = (size_t)nbins * nctas;
+    const bool global_bins = nbins > sort_smem_bins();
+    const size_t nbc = global_bins ? 16 : (size_t)nbins * nctas;
     const size_t rec_bytes = (pitch * (N + 1) * sizeof(T) + 31) & ~(size_t)31;
     const size_t out_bytes = (pitch * W * sizeof(T) + 31) & ~(size_t)31;
-    const size_t words = (pitch + 16) + 2 * nbc + 2 * (size_t)(nbins + 4) + 4 + 3 * max_items;
+    const size_t words = (pitch + 16) + 2 * nbc + 2 * (size_t)(nbins + 4) + 4 + 4 * max_items;
     unsigned char* scratch = nullptr;
     GB_CUDA(cudaMallocAsync((void**)&scratch, rec_bytes + out_bytes + (pitch + words) * sizeof(u32), s));
     T* rec = reinterpret_cast<T*>(scratch);
     T* osorted = reinterpret_cast<T*>(scratch + rec_bytes);
     u32* inv = reinterpret_cast<u32*>(scratch + rec_bytes + out_bytes);
     u32* keys = inv + pitch;
-    u32* bh = keys + pitch + 16;
+    u32* work = keys + pitch + 16;  // (16-byte aligned: items are uint4 {tile, first slot, end slot, -})
+    u32* bh = work + 4 * max_items;
     u32* boff = bh + nbc;
     u32* hist = boff + nbc;
     u32* offs = hist + (nbins + 4);
     u32* nwork = offs + (nbins + 4);
-    u32* work = nwork + 4;
     const size_t hsmem = (size_t)nbins * sizeof(u32);
     prof_mark(0, s);
-    tile_hist_kernel<T, N, ORDER, BCF><<<nctas, SORT_BLOCK, hsmem, s>>>(p, bh, nbins, per_cta);
-    count_launch();
-    prof_mark(1, s);
-    int rc = tile_offsets(bh, nbins, nctas, hist, offs, boff, work, nwork, EVAL_CHUNK, s);
-    if (rc) { cudaFreeAsync(scratch, s); return rc; }
-    prof_mark(2, s);
-    tile_scatter_kernel<T, N, ORDER, BCF><<<nctas, SORT_BLOCK, hsmem, s>>>(p, boff, rec, inv, nbins, per_cta);
-    count_launch();
+    int rc;
+    if (global_bins) {  // hist doubles as the write cursors after the scan
+        GB_CUDA(cudaMemsetAsync(hist, 0, (size_t)nbins * sizeof(u32), s));
+        tile_sort_global_kernel<T, N, ORDER, BCF, false><<<nctas, SORT_BLOCK, 0, s>>>(p, hist, rec, inv, per_cta);
+        count_launch();
+        prof_mark(1, s);
+        rc = tile_offsets_global(hist, nbins, offs, hist, work, nwork, EVAL_CHUNK, s);
+        if (rc) { cudaFreeAsync(scratch, s); return rc; }
+        prof_mark(2, s);
+        tile_sort_global_kernel<T, N, ORDER, BCF, true><<<nctas, SORT_BLOCK, 0, s>>>(p, hist, rec, inv, per_cta);
+        count_launch();
+    } else {
+        tile_hist_kernel<T, N, ORDER, BCF><<<nctas, SORT_BLOCK, hsmem, s>>>(p, bh, nbins, per_cta);
+        count_launch();
+        prof_mark(1, s);
+        rc = tile_offsets(bh, nbins, nctas, hist, offs, boff, work, nwork, EVAL_CHUNK, s);
+        if (rc) { cudaFreeAsync(scratch, s); return rc; }
+        prof_mark(2, s);
+        tile_scatter_kernel<T, N, ORDER, BCF><<<nctas, SORT_BLOCK, hsmem, s>>>(p, boff, rec, inv, nbins, per_cta);
+        count_launch();
+    }
     GB_CUDA(cudaGetLastError());
     GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per device, cheap
     int bt = 0;
@@ -1446,8 +1519,11 @@ int launch_one(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
         GB_CUDA(cudaGetLastError());
         return GB_OK;
     }
-    // slices of at most tiled_max_batch() queries, one after the other on the stream
-    const i64 slice = tiled_max_batch();
+    // equal slices of at most tiled_max_batch() queries, one after the other on the stream
+    i64 ntiles = 1;
+    for (int d = 0; d < N; d++) ntiles *= p.ntile[d];
+    const i64 limit = tiled_max_batch(ntiles), nslices = (p_in.nq + limit - 1) / limit;
+    const i64 slice = std::min<i64>(limit, (((p_in.nq + nslices - 1) / nslices) + 255) & ~(i64)255);
     const size_t xs = p.xdtype == GB_F64 ? 8 : 4;
     for (i64 q0 = 0; q0 < p_in.nq; q0 += slice) {
         EvalParams<N> sp = p;

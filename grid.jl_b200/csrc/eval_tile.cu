@@ -52,60 +52,67 @@ int prof_read(double* ms, int n, int* nstages) {
 // One CTA of 1024 threads.  Each thread owns a contiguous slice of at most SCAN_PER bins (held in
 // registers: one pass over global memory); warp-shuffle scans of (queries per slice) and (work items per
 // slice), then a 32-entry scan of the warp totals, give every thread its starting offsets.
-constexpr int SCAN_PER = 12;  // 1024 * 12 >= SORT_MAX_BINS
+constexpr int SCAN_PER = 12;  // bins per thread and segment (1024 * 12 >= sort_smem_bins(): one segment for the shared-memory sort)
 __global__ void __launch_bounds__(1024) tile_scan_kernel(const u32* __restrict__ hist, u32 nbins, u32* __restrict__ offs, u32* __restrict__ work,
                                                          u32* __restrict__ nwork, u32 chunk) {
-    __shared__ u32 s_wc[32], s_wi[32];
+    __shared__ u32 s_wc[32], s_wi[32], s_base[2];
     const u32 t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const u32 per = (nbins + 1023) / 1024;  // <= SCAN_PER
-    const u32 b0 = min(t * per, nbins);
-    u32 h[SCAN_PER];
-    u32 cnt = 0, itm = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_PER; k++) {
-        const u32 b = b0 + k;
-        h[k] = ((u32)k < per && b < nbins) ? hist[b] : 0u;
-        cnt += h[k];
-        itm += (h[k] + chunk - 1) / chunk;
-    }
-    u32 ic = cnt, ii = itm;  // inclusive scans within the warp
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const u32 a = __shfl_up_sync(0xffffffffu, ic, o), b = __shfl_up_sync(0xffffffffu, ii, o);
-        if ((int)lane >= o) { ic += a; ii += b; }
-    }
-    if (lane == 31) { s_wc[warp] = ic; s_wi[warp] = ii; }
+    if (t == 0) { s_base[0] = 0; s_base[1] = 0; }
     __syncthreads();
-    if (warp == 0) {
-        u32 wc = s_wc[lane], wi = s_wi[lane];
+    // segments of 1024 * SCAN_PER bins (one for the shared-memory sort; more for tile_sort_global's bin counts)
+    for (u32 seg = 0; seg < nbins; seg += 1024 * SCAN_PER) {
+        const u32 nb = min(nbins - seg, 1024u * SCAN_PER);
+        const u32 per = (nb + 1023) / 1024;  // <= SCAN_PER
+        const u32 b0 = min(t * per, nb);
+        u32 h[SCAN_PER];
+        u32 cnt = 0, itm = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_PER; k++) {
+            const u32 b = b0 + k;
+            h[k] = ((u32)k < per && b < nb) ? hist[seg + b] : 0u;
+            cnt += h[k];
+            itm += (h[k] + chunk - 1) / chunk;
+        }
+        u32 ic = cnt, ii = itm;  // inclusive scans within the warp
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const u32 a = __shfl_up_sync(0xffffffffu, wc, o), b = __shfl_up_sync(0xffffffffu, wi, o);
-            if ((int)lane >= o) { wc += a; wi += b; }
+            const u32 a = __shfl_up_sync(0xffffffffu, ic, o), b = __shfl_up_sync(0xffffffffu, ii, o);
+            if ((int)lane >= o) { ic += a; ii += b; }
         }
-        s_wc[lane] = wc;  // inclusive over warps
-        s_wi[lane] = wi;
-    }
-    __syncthreads();
-    u32 o = (warp ? s_wc[warp - 1] : 0u) + ic - cnt;  // exclusive offsets of this thread's slice
-    u32 w = (warp ? s_wi[warp - 1] : 0u) + ii - itm;
+        if (lane == 31) { s_wc[warp] = ic; s_wi[warp] = ii; }
+        __syncthreads();
+        if (warp == 0) {
+            u32 wc = s_wc[lane], wi = s_wi[lane];
 #pragma unroll
-    for (int k = 0; k < SCAN_PER; k++) {
-        const u32 b = b0 + k;
-        if ((u32)k < per && b < nbins) {
-            offs[b] = o;
-            const u32 n = (h[k] + chunk - 1) / chunk;            // items of this bin ...
-            const u32 sz = n ? (h[k] + n - 1) / n : 0;           // ... of equal size
-            for (u32 j = 0; j < n; j++) {
-                work[3 * w] = b;
-                work[3 * w + 1] = o + j * sz;
-                work[3 * w + 2] = o + min((j + 1) * sz, h[k]);
-                w++;
+            for (int o = 1; o < 32; o <<= 1) {
+                const u32 a = __shfl_up_sync(0xffffffffu, wc, o), b = __shfl_up_sync(0xffffffffu, wi, o);
+                if ((int)lane >= o) { wc += a; wi += b; }
             }
-            o += h[k];
+            s_wc[lane] = wc;  // inclusive over warps
+            s_wi[lane] = wi;
         }
+        __syncthreads();
+        u32 o = s_base[0] + (warp ? s_wc[warp - 1] : 0u) + ic - cnt;  // exclusive offsets of this thread's slice
+        u32 w = s_base[1] + (warp ? s_wi[warp - 1] : 0u) + ii - itm;
+#pragma unroll
+        for (int k = 0; k < SCAN_PER; k++) {
+            const u32 b = b0 + k;
+            if ((u32)k < per && b < nb) {
+                offs[seg + b] = o;
+                const u32 n = (h[k] + chunk - 1) / chunk;            // items of this bin ...
+                const u32 sz = n ? (h[k] + n - 1) / n : 0;           // ... of equal size
+                for (u32 j = 0; j < n; j++) {
+                    reinterpret_cast<uint4*>(work)[w] = make_uint4(seg + b, o + j * sz, o + min((j + 1) * sz, h[k]), 0u);
+                    w++;
+                }
+                o += h[k];
+            }
+        }
+        __syncthreads();
+        if (t == 1023) { s_base[0] += s_wc[31]; s_base[1] += s_wi[31]; }
+        __syncthreads();
     }
-    if (t == 1023) { nwork[0] = s_wi[31]; nwork[1] = 0; }  // item count, and the counter CTAs pull items from
+    if (t == 1023) { nwork[0] = s_base[1]; nwork[1] = 0; }  // item count, and the counter CTAs pull items from
 }
 
 // hist[b] = sum over CTAs of bh[b][cta]; one warp per bin.
@@ -148,14 +155,35 @@ int tile_offsets(const u32* bh, u32 nbins, u32 nctas, u32* hist, u32* offs, u32*
     return GB_OK;
 }
 
+// global-histogram sort (tile_sort_global_kernel): hist holds the totals already; after the scan the write cursors
+// are the bin offsets themselves (cursor may alias hist)
+int tile_offsets_global(const u32* hist, u32 nbins, u32* offs, u32* cursor, u32* work, u32* nwork, u32 chunk, cudaStream_t s) {
+    tile_scan_kernel<<<1, 1024, 0, s>>>(hist, nbins, offs, work, nwork, chunk);
+    count_launch();
+    GB_CUDA(cudaGetLastError());
+    GB_CUDA(cudaMemcpyAsync(cursor, offs, (size_t)nbins * sizeof(u32), cudaMemcpyDeviceToDevice, s));
+    return GB_OK;
+}
+
 // Tile shape.  The leading extents are fixed (brick_tile); the extent along the last dimension is
 // the largest power of two whose brick (tile + L-1 halo per dimension) fits the shared-memory
 // budget per buffer (GB_TILE_KB, default 40 KB: two buffers x two 256-thread CTAs per SM) -- grown
 // further only if the number of tiles would not fit the per-CTA shared-memory histogram of the
-// counting sort.  Returns false when tiling cannot pay off (too many tiles for the sort, brick too
-// large, or fewer than ~32 queries per tile to amortise staging a brick) -> plain path.
+// counting sort; when no brick achieves that, the budget brick is kept and the sort runs on a global
+// histogram.  Returns false when tiling cannot pay off (brick too large, or fewer than ~32 queries per
+// tile to amortise staging a brick) -> plain path.
+// bins the shared-memory sort handles (GB_SORT_SMEM_BINS lowers it: tests of the global-histogram sort)
+u32 sort_smem_bins() {
+    static const u32 v = [] {
+        const char* e = getenv("GB_SORT_SMEM_BINS");
+        const long x = e ? atol(e) : 0;
+        return (u32)(x >= 2 && x <= 12000 ? x : 12000);
+    }();
+    return v;
+}
 bool choose_tile(int N, int L, size_t esz, const int* len, i64 nq, bool forced, int* tile, int* ntile) {
-    constexpr u32 MAX_BINS = 12000 - 1;
+    const u32 MAX_BINS = sort_smem_bins() - 1;        // less the bin of invalid queries
+    constexpr u32 MAX_BINS_GLOBAL = (1u << 24) - 1;
     size_t budget = 40 * 1024;
     if (const char* e = getenv("GB_TILE_KB")) {
         long v = atol(e);
@@ -173,8 +201,15 @@ bool choose_tile(int N, int L, size_t esz, const int* len, i64 nq, bool forced, 
     int t = 1;
     while (t * 2 <= last && lead * (size_t)(t * 2 + L - 1) <= budget) t *= 2;
     if (lead * (size_t)(t + L - 1) > 100 * 1024) return false;
+    const int t_fit = t;
     while (nt * (unsigned long long)((last + t - 1) / t) > MAX_BINS) {
-        if (t >= last || lead * (size_t)(t * 2 + L - 1) > 100 * 1024) return false;
+        if (t >= last || lead * (size_t)(t * 2 + L - 1) > 100 * 1024) {
+            // no brick makes the tiles few enough for the shared-memory histograms: keep the brick that fits
+            // the budget and sort through the global histogram (tile_sort_global_kernel)
+            t = t_fit;
+            if (nt * (unsigned long long)((last + t - 1) / t) > MAX_BINS_GLOBAL) return false;
+            break;
+        }
         t *= 2;
     }
     tile[N - 1] = t;

@@ -701,6 +701,61 @@ def test_brick_path_in_slices(gb, oracle):
         assert same(np.load(os.path.join(d, "v.npy")), ov) and same(np.load(os.path.join(d, "g.npy")), og)
 
 
+def test_brick_path_global_histogram(gb, oracle):
+    """Grids with more tiles than the shared-memory histograms of the counting sort hold (12000; e.g. 512^3) are
+    sorted through one global histogram with warp-aggregated atomics.  GB_SORT_SMEM_BINS=8 in a child process
+    sends small grids down that route: a 3-D cubic grid (19 bins), a 2-D cubic grid with 13001 bins (two segments
+    of the bin scan; GB_TILE_KB=4 keeps the bricks tiny), clustered queries (every lane of a warp in one tile),
+    and BCnil's first-invalid index."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+
+    rng = np.random.default_rng(73)
+    A3 = np.asfortranarray(rng.standard_normal((33, 20, 18)))
+    X3 = make_queries(rng, A3.shape, 70_000, np.float64, wide=False)[:70_000]
+    X3[:5000] = 7.0 + rng.random((5000, 3))  # clustered
+    X3[45_678, 1] = 25.0  # invalid under BCnil
+    A2 = np.asfortranarray(rng.standard_normal((640, 5200)))
+    X2 = make_queries(rng, A2.shape, 150_000, np.float64, wide=True)
+    with tempfile.TemporaryDirectory() as d:
+        np.savez(os.path.join(d, "in.npz"), A3=A3, X3=X3, A2=A2, X2=X2)
+        code = (
+            "import sys, numpy as np, torch\n"
+            f"sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})\n"
+            "import grid_jl_b200 as gb\n"
+            f"z = np.load({os.path.join(d, 'in.npz')!r})\n"
+            "g = gb.InterpGrid(np.asfortranarray(z['A3']), gb.BCnan, gb.InterpCubic)\n"
+            "X3 = torch.from_numpy(z['X3']).cuda()\n"
+            "v, gr, _ = g._eval(X3, 3, tiled=True)\n"
+            "vf = g._eval(X3, 1, tiled=True, fast=True)[0]\n"
+            "g2 = gb.InterpGrid(np.asfortranarray(z['A2']), gb.BCna, gb.InterpCubic)\n"
+            "v2, gr2, h2 = g2._eval(torch.from_numpy(z['X2']).cuda(), 7, tiled=True)\n"
+            f"np.savez({os.path.join(d, 'out.npz')!r}, v=v.cpu().numpy(), g=gr.cpu().numpy(), vf=vf.cpu().numpy(), v2=v2.cpu().numpy(), g2=gr2.cpu().numpy(), h2=h2.cpu().numpy())\n"
+            "n = gb.InterpGrid(np.asfortranarray(z['A3']), gb.BCnil, gb.InterpQuadratic)\n"
+            "try:\n"
+            "    n._eval(X3, 1, tiled=True)\n"
+            "    print('no error')\n"
+            "except gb.ErrorException as e:\n"
+            "    print(str(e))\n"
+        )
+        env = dict(os.environ, GB_SORT_SMEM_BINS="8", GB_TILE_KB="4")
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        assert "Invalid location (query 45678)" in out.stdout
+        z = np.load(os.path.join(d, "out.npz"))
+        co = oracle.make_coefs(A3, "nan", "cubic")
+        ov, og, _, _ = oracle.evaluate(co, "nan", "cubic", X3, 3)
+        assert same(z["v"], ov) and same(z["g"], og)
+        tv, _, sv, _ = oracle.evaluate_truth(co, "nan", "cubic", X3)
+        ok = ~np.isnan(ov)
+        assert np.all(np.abs(z["vf"][ok] - tv[ok]) <= 4 * np.spacing(sv[ok]))
+        co2 = oracle.make_coefs(A2, "na", "cubic")
+        ov, og, oh, _ = oracle.evaluate(co2, "na", "cubic", X2, 7)
+        assert same(z["v2"], ov) and same(z["g2"], og) and same(z["h2"], oh)
+
+
 def test_blocked_layout(gb, oracle):
     """Large 2-D to 4-D grids with light neighbourhoods are kept in 4^N-element Morton blocks (a pure addressing
     change, eval.cuh tap_offset).  GB_BLOCK_MIN_MB=0 in a child process puts small grids in that layout: every
