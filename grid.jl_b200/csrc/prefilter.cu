@@ -14,11 +14,13 @@
 // 256-byte row.  Sweep along dim 1: 8 lanes fetch 64 contiguous bytes of one line and a
 // shared-memory tile turns the chunk so that lane r owns line r.  The pivot divisions use the
 // host-computed reciprocals with FMA refinement (exact_div: same bits as a / d, 5 dependent
-// operations).  Measured on 258^3 f64 (cubic, Woodbury): 0.27 ms per sweep along dims 2/3
-// (64 B/point of traffic -> 63 % of the HBM copy rate), 0.49 ms along dim 1.  A variant that kept
+// operations).  The factors are bit-constant a few rows in (LineSys f0..b1): chunks inside that run use register
+// constants instead of per-element factor loads.  Measured on 258^3 f64 (cubic, Woodbury): 0.17 ms per sweep along
+// dims 2/3, 0.26 ms along dim 1.  A variant that kept
 // whole lines in shared memory (16 B/point of HBM traffic) was built and measured at 0.5 ms per
 // sweep -- too few lines per SM in flight to hide the dependent FP64 chain -- and dropped.
 #include <cstdlib>
+#include <cstring>
 #include <algorithm>
 #include <vector>
 
@@ -38,6 +40,12 @@ template <typename T> struct LineSys {
     int woodbury;
     int vcol0, vcol1;
     T cp[4];  // column-major 2x2
+    // Stationary interior.  The factors of these (Toeplitz but for the ends) matrices reach a floating-point fixed
+    // point a few rows in: forward steps [f0, f1) have swap == 0 and dl == cdl, backward rows [b0, b1) have
+    // du == cdu, du2 == cdu2, d == cd (bit for bit, found by the host).  Chunks inside these ranges run the same
+    // operations on register constants instead of six coefficient loads per element.
+    i64 f0, f1, b0, b1;
+    T cdl, cdu, cdu2, cd, crd;
 };
 
 // ---- line IO policies -------------------------------------------------------------------------------
@@ -126,13 +134,23 @@ template <typename T, int U, typename IO> __device__ __forceinline__ T lu_forwar
         T v[U];
         io.unpack(v, g);
         if (c0 + U < n - 1) io.fetch(g, c0 + U + 1, +1, (int)min((i64)U, n - 1 - c0 - U));  // next chunk in flight
+        if (cnt == U && c0 >= sys.f0 && c0 + U <= sys.f1) {  // stationary chunk
+            const T m = sys.cdl;
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            if (u < cnt) {
-                const T m = __ldg(sys.dl + c0 + u);
+            for (int u = 0; u < U; u++) {
                 const T nxt = v[u];
-                if (__ldg(sys.swap + c0 + u)) { v[u] = nxt; const T t = cur - m * nxt; cur = t; }
-                else { v[u] = cur; const T t = nxt - m * cur; cur = t; }
+                v[u] = cur;
+                cur = nxt - m * cur;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (u < cnt) {
+                    const T m = __ldg(sys.dl + c0 + u);
+                    const T nxt = v[u];
+                    if (__ldg(sys.swap + c0 + u)) { v[u] = nxt; const T t = cur - m * nxt; cur = t; }
+                    else { v[u] = cur; const T t = nxt - m * cur; cur = t; }
+                }
             }
         }
         io.store(v, c0, +1, cnt);
@@ -191,15 +209,26 @@ template <typename T, int U, bool SUB, typename IO> __device__ __forceinline__ v
             rhs.fetch(g, c0 - U, -1, c);
             if constexpr (SUB) dst.fetch(go, c0 - U, -1, c);
         }
+        if (cnt == U && c0 - U + 1 >= sys.b0 && c0 < sys.b1) {  // stationary chunk
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            if (u < cnt) {
-                const i64 i = c0 - u;
-                const T x = exact_div(v[u] - __ldg(sys.du + i) * x1 - __ldg(sys.du2 + i) * x2, __ldg(sys.d + i), __ldg(sys.rd + i));
+            for (int u = 0; u < U; u++) {
+                const T x = exact_div(v[u] - sys.cdu * x1 - sys.cdu2 * x2, sys.cd, sys.crd);
                 if constexpr (SUB) v[u] = o[u] - x;
                 else v[u] = x;
                 x2 = x1;
                 x1 = x;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (u < cnt) {
+                    const i64 i = c0 - u;
+                    const T x = exact_div(v[u] - __ldg(sys.du + i) * x1 - __ldg(sys.du2 + i) * x2, __ldg(sys.d + i), __ldg(sys.rd + i));
+                    if constexpr (SUB) v[u] = o[u] - x;
+                    else v[u] = x;
+                    x2 = x1;
+                    x1 = x;
+                }
             }
         }
         dst.store(v, c0, -1, cnt);
@@ -213,6 +242,10 @@ template <typename T, int U, bool SUB, typename IO> __device__ __forceinline__ v
 // start of every backward chunk (shared memory, [chunk][thread]) and the backward pass replays the U
 // steps of a chunk from its checkpoint -- the same operations in the same order on the same inputs,
 // hence the same bits.
+template <typename T> __device__ __forceinline__ void sparse_step_stationary(const LineSys<T>& sys, T& cur, T& v) {  // f1 <= n-2: nxt == 0
+    v = cur;
+    cur = (T)0 - sys.cdl * cur;
+}
 template <typename T> __device__ __forceinline__ void sparse_step(const LineSys<T>& sys, i64 i, i64 n, T k1, T& cur, T& v) {
     const T m = __ldg(sys.dl + i);
     const T nxt = (i + 1 == n - 1) ? k1 : (T)0;
@@ -232,7 +265,8 @@ template <typename T, int U> __device__ __forceinline__ T lu_forward_sparse_ck(i
             sj = n - 2 - (j + 1) * U;
         }
         T v;
-        sparse_step<T>(sys, i, n, k1, cur, v);
+        if (i >= sys.f0 && i < sys.f1) sparse_step_stationary<T>(sys, cur, v);
+        else sparse_step<T>(sys, i, n, k1, cur, v);
         if (i == n - 2) t_nm2 = v;
     }
     return cur;
@@ -257,19 +291,34 @@ __device__ __forceinline__ void lu_backward_sub_ck(const IO& dst, i64 n, const L
         // replay the chunk's U forward steps from its checkpoint (positions below index 0 are skipped)
         T cur = ck[j * ckstride];
         const i64 s = c0 - U + 1;
+        if (s >= sys.f0 && s + U <= sys.f1) {
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            tt[u] = (T)0;
-            if (s + u >= 0) sparse_step<T>(sys, s + u, n, k1, cur, tt[u]);
+            for (int u = 0; u < U; u++) sparse_step_stationary<T>(sys, cur, tt[u]);
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                tt[u] = (T)0;
+                if (s + u >= 0) sparse_step<T>(sys, s + u, n, k1, cur, tt[u]);
+            }
         }
+        if (cnt == U && s >= sys.b0 && c0 < sys.b1) {
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            if (u < cnt) {
-                const i64 i = c0 - u;
-                const T x = exact_div(tt[U - 1 - u] - __ldg(sys.du + i) * x1 - __ldg(sys.du2 + i) * x2, __ldg(sys.d + i), __ldg(sys.rd + i));
+            for (int u = 0; u < U; u++) {
+                const T x = exact_div(tt[U - 1 - u] - sys.cdu * x1 - sys.cdu2 * x2, sys.cd, sys.crd);
                 v[u] = o[u] - x;
                 x2 = x1;
                 x1 = x;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (u < cnt) {
+                    const i64 i = c0 - u;
+                    const T x = exact_div(tt[U - 1 - u] - __ldg(sys.du + i) * x1 - __ldg(sys.du2 + i) * x2, __ldg(sys.d + i), __ldg(sys.rd + i));
+                    v[u] = o[u] - x;
+                    x2 = x1;
+                    x1 = x;
+                }
             }
         }
         dst.store(v, c0, -1, cnt);
@@ -464,6 +513,27 @@ template <typename T> int invert_impl(T* A, int ndim, const i64* dims, int bc, i
         sys.woodbury = hs.woodbury ? 1 : 0;
         sys.vcol0 = (int)hs.vcol[0]; sys.vcol1 = (int)hs.vcol[1];
         for (int i = 0; i < 4; i++) sys.cp[i] = hs.cp[i];
+        {  // stationary interior: longest runs of bit-identical factors (forward steps end before n-2: sparse_step's k1 row)
+            auto same = [](T a, T b) { return std::memcmp(&a, &b, sizeof(T)) == 0; };
+            auto longest = [&](i64 lo, i64 hi, auto eq, i64& r0, i64& r1) {
+                r0 = r1 = 0;
+                for (i64 i = lo; i < hi;) {
+                    i64 j = i + 1;
+                    while (j < hi && eq(i, j)) j++;
+                    if (j - i > r1 - r0) { r0 = i; r1 = j; }
+                    i = j;
+                }
+            };
+            longest(0, n - 2, [&](i64 i, i64 j) { return !hs.swap[i] && !hs.swap[j] && same(hs.dl[i], hs.dl[j]); }, sys.f0, sys.f1);
+            if (sys.f1 - sys.f0 < 2 || hs.swap[sys.f0]) sys.f0 = sys.f1 = 0;
+            longest(0, n - 2, [&](i64 i, i64 j) { return same(hs.du[i], hs.du[j]) && same(hs.du2[i], hs.du2[j]) && same(hs.d[i], hs.d[j]); }, sys.b0, sys.b1);
+            if (sys.b1 - sys.b0 < 2) sys.b0 = sys.b1 = 0;
+            sys.cdl = n > 1 ? hs.dl[sys.f0] : (T)0;
+            sys.cdu = n > 2 ? hs.du[sys.b0] : (T)0;
+            sys.cdu2 = n > 2 ? hs.du2[sys.b0] : (T)0;
+            sys.cd = hs.d[sys.b0];
+            sys.crd = (T)1 / hs.d[sys.b0];
+        }
 
         // Woodbury: checkpoints of the second solve's RHS in shared memory when they fit, else an array-sized scratch
         const size_t ck_bytes = hs.woodbury && n >= 3 ? (size_t)((n - 2 + PF_U - 1) / PF_U) * 128 * sizeof(T) : 0;
