@@ -357,6 +357,146 @@ template <typename T, int BY, int BZ> int restrict3_launch(const T* in, T* out, 
     GB_CUDA(cudaGetLastError());
     return GB_OK;
 }
+// ---- fused 3-D restrict, marching along dim 3 ---------------------------------------------------
+// The brick kernel above recomputes the dim-1 restriction of its halo rows: (2BY+2)(2BZ+2) staged rows for
+// (2BY)(2BZ) new ones -- 1.56x at (32,4,4), and it is issue-bound (88 instructions per fine-grid point, 12 % of
+// them FP64).  Here a small CTA (NW warps) owns an output tile of 32*XW x BY
+// and walks a chunk of output planes: per INPUT plane it restricts dim 1 into S1[2BY+2][32*XW] (stage A), dim 2
+// into one slot of a four-plane ring S2[4][BY][32*XW] (stage B), and after every second plane restricts dim 3
+// across the ring and stores one output plane (stage C).  Nothing is recomputed along dim 3 (but for the two
+// planes at a chunk boundary), 1.125x along dim 2, nothing along dim 1.  Same restrict_at calls in the same
+// order as the brick kernel, hence the same bits.
+// restrict_at with all four taps present (interior outputs): no per-tap conditions
+template <typename T> __device__ __forceinline__ T restrict_full(bool even, T am2, T am1, T a0, T ap1, const RCoef<T>& c) {
+    T acc = (T)0;
+    if (!even) {
+        acc = acc + c.s1 * a0;
+        acc = acc + c.s2 * ap1;
+        acc = acc + c.s2 * am1;
+    } else {
+        acc = acc + c.s75 * a0;
+        acc = acc + c.s25 * ap1;
+        acc = acc + c.s75 * am1;
+        acc = acc + c.s25 * am2;
+    }
+    return acc;
+}
+// A warp keeps ONE 32-output column segment for the whole kernel (xs = warp % XW) and takes every (NW/XW)-th row,
+// so everything that depends on x -- validity, edge flags, the global column offset -- is loop-invariant, and the
+// interior case (every lane of the segment has all its taps: a warp-uniform test) runs without per-lane branches.
+template <typename T, int BY, int XW, int NW, int UN> __global__ void __launch_bounds__(32 * NW) restrict3_march_kernel(const T* __restrict__ A, T* __restrict__ R, int L1, int L2, int L3, int n1, int n2,
+                                                                                                     int n3, int zc, RCoef<T> c) {
+    constexpr int BX = 32 * XW, IY = 2 * BY + 2, YS = NW / XW;
+    static_assert(NW % XW == 0 && IY % YS == 0 && BY % YS == 0, "row schedule");
+    extern __shared__ unsigned char smem_raw[];
+    T* S1 = reinterpret_cast<T*>(smem_raw);  // [IY][BX]
+    T* S2 = S1 + IY * BX;                     // [4][BY][BX]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int xs = warp % XW, yw = warp / XW;
+    const int j1 = blockIdx.x * BX, j2 = blockIdx.y * BY, j3 = blockIdx.z * zc;
+    const int nzo = min(zc, n3 - j3);
+    const int y0 = 2 * j2 - 2, z0 = 2 * j3 - 2;
+    const bool ev1 = !(L1 & 1), ev2 = !(L2 & 1), ev3 = !(L3 & 1);
+    const bool vec = !(L1 & 1) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);  // rows 16-byte aligned
+    const int col = xs * 32 + lane, gx = j1 + col, seg0 = j1 + xs * 32;
+    const bool segv = seg0 < n1;                                  // warp-uniform: the segment has outputs
+    const bool xfull = seg0 >= 1 && seg0 + 31 <= n1 - 2;          // warp-uniform: every lane has all four taps
+    const bool vx = gx < n1, lo = vx && gx >= 1, hi = vx && gx <= n1 - 2, need0 = vx && (ev1 ? hi : true);
+    const size_t plane = (size_t)L2 * (size_t)L1;
+    for (int p = 0; p < 2 * nzo + 2; p++) {
+        const int gz = z0 + p;
+        const bool zok = gz >= 0 && gz < L3;
+        // ---- stage A: dim-1 restriction of the input plane's rows
+        if (zok && segv) {
+            const T* Ac = A + (size_t)gz * plane + 2 * gx;
+#pragma unroll 1
+            for (int k0 = 0; k0 < IY / YS; k0 += UN) {
+                T am2[UN], am1[UN], a0[UN], ap1[UN];
+#pragma unroll
+                for (int u = 0; u < UN; u++) {
+                    const int gy = y0 + yw + YS * (k0 + u);
+                    if (k0 + u < IY / YS && gy >= 0 && gy < L2) {  // warp-uniform
+                        const T* a = Ac + (ptrdiff_t)gy * (ptrdiff_t)L1;
+                        if (sizeof(T) == 8 && vec && xfull) {
+                            const double2 v = __ldg(reinterpret_cast<const double2*>(a - 2)), w = __ldg(reinterpret_cast<const double2*>(a));
+                            am2[u] = v.x; am1[u] = v.y; a0[u] = w.x; ap1[u] = w.y;
+                        } else {
+                            am2[u] = am1[u] = a0[u] = ap1[u] = (T)0;
+                            if (lo) { am1[u] = __ldg(a - 1); if (ev1) am2[u] = __ldg(a - 2); }
+                            if (need0) a0[u] = __ldg(a);  // A[2j] is read unless (even L, last output)
+                            if (hi) ap1[u] = __ldg(a + 1);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UN; u++) {
+                    const int y = yw + YS * (k0 + u), gy = y0 + y;
+                    if (k0 + u < IY / YS) {
+                        T v = (T)0;
+                        if (gy >= 0 && gy < L2) {
+                            if (xfull) v = restrict_full<T>(ev1, am2[u], am1[u], a0[u], ap1[u], c);
+                            else if (vx) v = restrict_at<T>(ev1, am2[u], am1[u], a0[u], ap1[u], lo, hi, c);
+                        }
+                        S1[y * BX + col] = v;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- stage B: dim-2 restriction into ring slot p & 3; taps of output y are S1 rows 2y .. 2y+3
+        if (zok && segv) {
+            T* dst = S2 + ((p & 3) * BY) * BX + col;
+#pragma unroll
+            for (int k = 0; k < BY / YS; k++) {
+                const int y = yw + YS * k, gy = j2 + y;
+                T v = (T)0;
+                if (gy < n2) {
+                    const T* a = S1 + (2 * y) * BX + col;
+                    if (gy >= 1 && gy <= n2 - 2) v = restrict_full<T>(ev2, a[0], a[BX], a[2 * BX], a[3 * BX], c);
+                    else v = restrict_at<T>(ev2, a[0], a[BX], a[2 * BX], a[3 * BX], gy >= 1, gy <= n2 - 2, c);
+                }
+                dst[y * BX] = v;
+            }
+        }
+        __syncthreads();
+        // ---- stage C: input planes p-3 .. p are the taps of output plane (p-3)/2 of this chunk
+        if (p >= 3 && (p & 1) && vx) {
+            const int gzo = j3 + ((p - 3) >> 1);
+            const bool zlo = gzo >= 1, zhi = gzo <= n3 - 2;
+            const T* s0 = S2 + (((p + 1) & 3) * BY) * BX + col;
+            const T* s1 = S2 + (((p + 2) & 3) * BY) * BX + col;
+            const T* s2 = S2 + (((p + 3) & 3) * BY) * BX + col;
+            const T* s3 = S2 + ((p & 3) * BY) * BX + col;
+            T* Rz = R + (size_t)gzo * (size_t)n2 * (size_t)n1 + gx;
+#pragma unroll
+            for (int k = 0; k < BY / YS; k++) {
+                const int y = yw + YS * k, gy = j2 + y;
+                if (gy < n2) {
+                    const int o = y * BX;
+                    // taps outside the array are never used by restrict_at (zlo / zhi), whatever their slots hold
+                    Rz[(size_t)gy * (size_t)n1] = (zlo && zhi) ? restrict_full<T>(ev3, s0[o], s1[o], s2[o], s3[o], c)
+                                                             : restrict_at<T>(ev3, s0[o], s1[o], s2[o], s3[o], zlo, zhi, c);
+                }
+            }
+        }
+    }
+}
+template <typename T, int BY, int XW, int NW, int UN> int restrict3_march_launch(const T* in, T* out, i64 L1, i64 L2, i64 L3, i64 n1, i64 n2, i64 n3, double scale, cudaStream_t s) {
+    constexpr int BX = 32 * XW, IY = 2 * BY + 2;
+    const size_t smem = sizeof(T) * (size_t)(IY * BX + 4 * BY * BX);
+    auto kern = restrict3_march_kernel<T, BY, XW, NW, UN>;
+    GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const i64 gx = (n1 + BX - 1) / BX, gy = (n2 + BY - 1) / BY;
+    // chunks of output planes: long enough to amortise the two extra input planes of a chunk, short enough for
+    // a few CTAs per SM slot over the whole grid
+    i64 zc = 32;
+    while (zc > 4 && gx * gy * ((n3 + zc - 1) / zc) < (i64)num_sms() * 4 * 4) zc /= 2;
+    dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)((n3 + zc - 1) / zc));
+    kern<<<grid, 32 * NW, smem, s>>>(in, out, (int)L1, (int)L2, (int)L3, (int)n1, (int)n2, (int)n3, (int)zc, make_coef<T>(scale));
+    count_launch();
+    GB_CUDA(cudaGetLastError());
+    return GB_OK;
+}
 template <typename T> int restrict3_impl(const i64* dims, const T* in, double scale, T* out, cudaStream_t s) {
     const i64 L1 = dims[0], L2 = dims[1], L3 = dims[2];
     const i64 n1 = rsize(L1), n2 = rsize(L2), n3 = rsize(L3);
@@ -373,8 +513,14 @@ template <typename T> int restrict3_impl(const i64* dims, const T* in, double sc
         return rc;
     }
     if (L1 >= (1ll << 30) || L2 >= (1ll << 30) || L3 >= (1ll << 30)) return fail(GB_ERR_UNSUPPORTED, "restrict3: extent too large");
-    // brick (32,4,4): measured best on 1024^3 f64 (3.6 ms per 1024->17 chain vs 3.9 for (32,4,8) / (32,8,4))
-    return restrict3_launch<T, 4, 4>(in, out, L1, L2, L3, n1, n2, n3, scale, s);
+    // brick (32,4,4): measured best of the bricks on 1024^3 f64 (3.6 ms per 1024->17 chain vs 3.9 for (32,4,8) / (32,8,4));
+    // GB_RESTRICT3=brick selects it instead of the marching kernel (A/B measurements)
+    static const bool brick = [] { const char* e = getenv("GB_RESTRICT3"); return e && e[0] == 'b'; }();
+    if (brick) return restrict3_launch<T, 4, 4>(in, out, L1, L2, L3, n1, n2, n3, scale, s);
+    // Tile 32 x 8 outputs per CTA of two warps, three rows in flight per warp: measured best on the 1024 -> 17 chain
+    // (2.96 ms; 128 x 8 / 8 warps 3.5-3.9, 64 x 8 / 4 warps 3.25, 32 x 6 3.13, 32 x 4 3.34, 32 x 16 4.8; all rows of a
+    // warp in flight at once 3.86, fully unrolled row loop 4.83; the (32,4,4) brick kernel 3.59)
+    return restrict3_march_launch<T, 8, 1, 2, 3>(in, out, L1, L2, L3, n1, n2, n3, scale, s);
 }
 
 // ---- fused 3-D prolong ------------------------------------------------------------------------
