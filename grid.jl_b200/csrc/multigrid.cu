@@ -23,6 +23,7 @@ namespace {
 __host__ __device__ inline i64 rsize(i64 len) { return (len & 1) ? (len + 1) / 2 : len / 2 + 1; }
 
 template <typename T> struct RCoef { T s1, s2, s75, s25; };
+template <typename T> struct alignas(2 * sizeof(T)) Pair { T x, y; };  // two adjacent elements of a row (marching kernels)
 
 // One restricted element j of a line of length L (stride st) starting at a.  axpy! order:
 //  odd  L (:117-122): R[j] += s*A[2j] ; R[j] += s/2*A[2j+1] (j<=n-2) ; R[j] += s/2*A[2j-1] (j>=1)
@@ -360,12 +361,13 @@ template <typename T, int BY, int BZ> int restrict3_launch(const T* in, T* out, 
 // ---- fused 3-D restrict, marching along dim 3 ---------------------------------------------------
 // The brick kernel above recomputes the dim-1 restriction of its halo rows: (2BY+2)(2BZ+2) staged rows for
 // (2BY)(2BZ) new ones -- 1.56x at (32,4,4), and it is issue-bound (88 instructions per fine-grid point, 12 % of
-// them FP64).  Here a small CTA (NW warps) owns an output tile of 32*XW x BY
-// and walks a chunk of output planes: per INPUT plane it restricts dim 1 into S1[2BY+2][32*XW] (stage A), dim 2
-// into one slot of a four-plane ring S2[4][BY][32*XW] (stage B), and after every second plane restricts dim 3
-// across the ring and stores one output plane (stage C).  Nothing is recomputed along dim 3 (but for the two
-// planes at a chunk boundary), 1.125x along dim 2, nothing along dim 1.  Same restrict_at calls in the same
-// order as the brick kernel, hence the same bits.
+// them FP64).  Here a small CTA (NW warps) owns an output tile of 64 x BY and walks a chunk of output planes: per
+// INPUT plane it restricts dim 1 into S1[2BY+2][64] (stage A), dim 2 into one slot of a four-plane ring
+// S2[4][BY][64] (stage B), and after every second plane restricts dim 3 across the ring and stores one output
+// plane (stage C).  Nothing is recomputed along dims 1 and 3 (but for the two planes at a chunk boundary),
+// (2BY+2)/(2BY) along dim 2.  Everything that depends on x is loop-invariant, and the interior case (every
+// output of the tile has all its taps: a warp-uniform test) runs without per-lane branches.  Same restrict_at
+// sequences in the same order as the brick kernel, hence the same bits.
 // restrict_at with all four taps present (interior outputs): no per-tap conditions
 template <typename T> __device__ __forceinline__ T restrict_full(bool even, T am2, T am1, T a0, T ap1, const RCoef<T>& c) {
     T acc = (T)0;
@@ -381,114 +383,136 @@ template <typename T> __device__ __forceinline__ T restrict_full(bool even, T am
     }
     return acc;
 }
-// A warp keeps ONE 32-output column segment for the whole kernel (xs = warp % XW) and takes every (NW/XW)-th row,
-// so everything that depends on x -- validity, edge flags, the global column offset -- is loop-invariant, and the
-// interior case (every lane of the segment has all its taps: a warp-uniform test) runs without per-lane branches.
-template <typename T, int BY, int XW, int NW, int UN> __global__ void __launch_bounds__(32 * NW) restrict3_march_kernel(const T* __restrict__ A, T* __restrict__ R, int L1, int L2, int L3, int n1, int n2,
-                                                                                                     int n3, int zc, RCoef<T> c) {
-    constexpr int BX = 32 * XW, IY = 2 * BY + 2, YS = NW / XW;
-    static_assert(NW % XW == 0 && IY % YS == 0 && BY % YS == 0, "row schedule");
-    extern __shared__ unsigned char smem_raw[];
-    T* S1 = reinterpret_cast<T*>(smem_raw);  // [IY][BX]
-    T* S2 = S1 + IY * BX;                     // [4][BY][BX]
+// A lane owns outputs x = 2*lane, 2*lane+1 of the 64-wide tile: their eight taps are six consecutive inputs (three
+// aligned 16-byte loads), and shared memory moves pairs (one column per lane: 2.94 instead of 2.63 ms per chain).
+template <typename T, int BY, int NW, int UN> __global__ void __launch_bounds__(32 * NW) restrict3_march_kernel(const T* __restrict__ A, T* __restrict__ R, int L1, int L2, int L3, int n1,
+                                                                                                        int n2, int n3, int zc, RCoef<T> c) {
+    constexpr int HX = 32, BX = 64, IY = 2 * BY + 2;
+    using V = Pair<T>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    V* S1 = reinterpret_cast<V*>(smem_raw);  // [IY][HX]
+    V* S2 = S1 + IY * HX;                     // [4][BY][HX]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int xs = warp % XW, yw = warp / XW;
     const int j1 = blockIdx.x * BX, j2 = blockIdx.y * BY, j3 = blockIdx.z * zc;
     const int nzo = min(zc, n3 - j3);
     const int y0 = 2 * j2 - 2, z0 = 2 * j3 - 2;
     const bool ev1 = !(L1 & 1), ev2 = !(L2 & 1), ev3 = !(L3 & 1);
-    const bool vec = !(L1 & 1) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);  // rows 16-byte aligned
-    const int col = xs * 32 + lane, gx = j1 + col, seg0 = j1 + xs * 32;
-    const bool segv = seg0 < n1;                                  // warp-uniform: the segment has outputs
-    const bool xfull = seg0 >= 1 && seg0 + 31 <= n1 - 2;          // warp-uniform: every lane has all four taps
-    const bool vx = gx < n1, lo = vx && gx >= 1, hi = vx && gx <= n1 - 2, need0 = vx && (ev1 ? hi : true);
+    const bool vec = sizeof(T) == 8 && !(L1 & 1) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);  // rows 16-byte aligned
+    const int gx = j1 + 2 * lane;
+    const bool xfull = j1 >= 1 && j1 + BX - 1 <= n1 - 2;  // warp-uniform: every output of the tile has all four taps
+    const bool vx0 = gx < n1, vx1 = gx + 1 < n1;
+    const bool lo0 = vx0 && gx >= 1, hi0 = vx0 && gx <= n1 - 2, lo1 = vx1, hi1 = vx1 && gx + 1 <= n1 - 2;
     const size_t plane = (size_t)L2 * (size_t)L1;
     for (int p = 0; p < 2 * nzo + 2; p++) {
         const int gz = z0 + p;
         const bool zok = gz >= 0 && gz < L3;
-        // ---- stage A: dim-1 restriction of the input plane's rows
-        if (zok && segv) {
+        // ---- stage A: dim-1 restriction; inputs t[0..5] = A[2gx-2 .. 2gx+3]
+        if (zok && j1 < n1) {
             const T* Ac = A + (size_t)gz * plane + 2 * gx;
 #pragma unroll 1
-            for (int k0 = 0; k0 < IY / YS; k0 += UN) {
-                T am2[UN], am1[UN], a0[UN], ap1[UN];
+            for (int k0 = 0; k0 < (IY + NW - 1) / NW; k0 += UN) {
+                T t[UN][6];
 #pragma unroll
                 for (int u = 0; u < UN; u++) {
-                    const int gy = y0 + yw + YS * (k0 + u);
-                    if (k0 + u < IY / YS && gy >= 0 && gy < L2) {  // warp-uniform
+                    const int y = warp + NW * (k0 + u), gy = y0 + y;
+                    if (y < IY && gy >= 0 && gy < L2) {  // warp-uniform
                         const T* a = Ac + (ptrdiff_t)gy * (ptrdiff_t)L1;
-                        if (sizeof(T) == 8 && vec && xfull) {
-                            const double2 v = __ldg(reinterpret_cast<const double2*>(a - 2)), w = __ldg(reinterpret_cast<const double2*>(a));
-                            am2[u] = v.x; am1[u] = v.y; a0[u] = w.x; ap1[u] = w.y;
+                        if (vec && xfull) {
+                            if constexpr (sizeof(T) == 8) {
+                                const double2 q0 = __ldg(reinterpret_cast<const double2*>(a - 2)), q1 = __ldg(reinterpret_cast<const double2*>(a)),
+                                              q2 = __ldg(reinterpret_cast<const double2*>(a + 2));
+                                t[u][0] = q0.x; t[u][1] = q0.y; t[u][2] = q1.x; t[u][3] = q1.y; t[u][4] = q2.x; t[u][5] = q2.y;
+                            }
                         } else {
-                            am2[u] = am1[u] = a0[u] = ap1[u] = (T)0;
-                            if (lo) { am1[u] = __ldg(a - 1); if (ev1) am2[u] = __ldg(a - 2); }
-                            if (need0) a0[u] = __ldg(a);  // A[2j] is read unless (even L, last output)
-                            if (hi) ap1[u] = __ldg(a + 1);
+#pragma unroll
+                            for (int e = 0; e < 6; e++) t[u][e] = (T)0;
+                            // output 0 taps t[0..3] (am2, am1, a0, ap1), output 1 taps t[2..5]; only taps the reference reads are loaded
+                            if (lo0) { t[u][1] = __ldg(a - 1); if (ev1) t[u][0] = __ldg(a - 2); }
+                            if (vx0 && (ev1 ? hi0 : true)) t[u][2] = __ldg(a);
+                            if (hi0 || lo1) t[u][3] = __ldg(a + 1);
+                            if (vx1 && (ev1 ? hi1 : true)) t[u][4] = __ldg(a + 2);
+                            if (hi1) t[u][5] = __ldg(a + 3);
                         }
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < UN; u++) {
-                    const int y = yw + YS * (k0 + u), gy = y0 + y;
-                    if (k0 + u < IY / YS) {
-                        T v = (T)0;
+                    const int y = warp + NW * (k0 + u), gy = y0 + y;
+                    if (y < IY) {
+                        V v{(T)0, (T)0};
                         if (gy >= 0 && gy < L2) {
-                            if (xfull) v = restrict_full<T>(ev1, am2[u], am1[u], a0[u], ap1[u], c);
-                            else if (vx) v = restrict_at<T>(ev1, am2[u], am1[u], a0[u], ap1[u], lo, hi, c);
+                            if (xfull) {
+                                v.x = restrict_full<T>(ev1, t[u][0], t[u][1], t[u][2], t[u][3], c);
+                                v.y = restrict_full<T>(ev1, t[u][2], t[u][3], t[u][4], t[u][5], c);
+                            } else {
+                                if (vx0) v.x = restrict_at<T>(ev1, t[u][0], t[u][1], t[u][2], t[u][3], lo0, hi0, c);
+                                if (vx1) v.y = restrict_at<T>(ev1, t[u][2], t[u][3], t[u][4], t[u][5], lo1, hi1, c);
+                            }
                         }
-                        S1[y * BX + col] = v;
+                        S1[y * HX + lane] = v;
                     }
                 }
             }
         }
         __syncthreads();
         // ---- stage B: dim-2 restriction into ring slot p & 3; taps of output y are S1 rows 2y .. 2y+3
-        if (zok && segv) {
-            T* dst = S2 + ((p & 3) * BY) * BX + col;
-#pragma unroll
-            for (int k = 0; k < BY / YS; k++) {
-                const int y = yw + YS * k, gy = j2 + y;
-                T v = (T)0;
+        if (zok && j1 < n1) {
+            V* dst = S2 + ((p & 3) * BY) * HX + lane;
+            for (int y = warp; y < BY; y += NW) {
+                const int gy = j2 + y;
+                V v{(T)0, (T)0};
                 if (gy < n2) {
-                    const T* a = S1 + (2 * y) * BX + col;
-                    if (gy >= 1 && gy <= n2 - 2) v = restrict_full<T>(ev2, a[0], a[BX], a[2 * BX], a[3 * BX], c);
-                    else v = restrict_at<T>(ev2, a[0], a[BX], a[2 * BX], a[3 * BX], gy >= 1, gy <= n2 - 2, c);
+                    const V* a = S1 + (2 * y) * HX + lane;
+                    const V b0 = a[0], b1 = a[HX], b2 = a[2 * HX], b3 = a[3 * HX];
+                    if (gy >= 1 && gy <= n2 - 2) {
+                        v.x = restrict_full<T>(ev2, b0.x, b1.x, b2.x, b3.x, c);
+                        v.y = restrict_full<T>(ev2, b0.y, b1.y, b2.y, b3.y, c);
+                    } else {
+                        v.x = restrict_at<T>(ev2, b0.x, b1.x, b2.x, b3.x, gy >= 1, gy <= n2 - 2, c);
+                        v.y = restrict_at<T>(ev2, b0.y, b1.y, b2.y, b3.y, gy >= 1, gy <= n2 - 2, c);
+                    }
                 }
-                dst[y * BX] = v;
+                dst[y * HX] = v;
             }
         }
         __syncthreads();
         // ---- stage C: input planes p-3 .. p are the taps of output plane (p-3)/2 of this chunk
-        if (p >= 3 && (p & 1) && vx) {
+        if (p >= 3 && (p & 1) && vx0) {
             const int gzo = j3 + ((p - 3) >> 1);
             const bool zlo = gzo >= 1, zhi = gzo <= n3 - 2;
-            const T* s0 = S2 + (((p + 1) & 3) * BY) * BX + col;
-            const T* s1 = S2 + (((p + 2) & 3) * BY) * BX + col;
-            const T* s2 = S2 + (((p + 3) & 3) * BY) * BX + col;
-            const T* s3 = S2 + ((p & 3) * BY) * BX + col;
+            const V* s0 = S2 + (((p + 1) & 3) * BY) * HX + lane;
+            const V* s1 = S2 + (((p + 2) & 3) * BY) * HX + lane;
+            const V* s2 = S2 + (((p + 3) & 3) * BY) * HX + lane;
+            const V* s3 = S2 + ((p & 3) * BY) * HX + lane;
             T* Rz = R + (size_t)gzo * (size_t)n2 * (size_t)n1 + gx;
-#pragma unroll
-            for (int k = 0; k < BY / YS; k++) {
-                const int y = yw + YS * k, gy = j2 + y;
+            for (int y = warp; y < BY; y += NW) {
+                const int gy = j2 + y;
                 if (gy < n2) {
-                    const int o = y * BX;
+                    const int o = y * HX;
+                    const V b0 = s0[o], b1 = s1[o], b2 = s2[o], b3 = s3[o];
+                    V v;
                     // taps outside the array are never used by restrict_at (zlo / zhi), whatever their slots hold
-                    Rz[(size_t)gy * (size_t)n1] = (zlo && zhi) ? restrict_full<T>(ev3, s0[o], s1[o], s2[o], s3[o], c)
-                                                             : restrict_at<T>(ev3, s0[o], s1[o], s2[o], s3[o], zlo, zhi, c);
+                    if (zlo && zhi) {
+                        v.x = restrict_full<T>(ev3, b0.x, b1.x, b2.x, b3.x, c);
+                        v.y = restrict_full<T>(ev3, b0.y, b1.y, b2.y, b3.y, c);
+                    } else {
+                        v.x = restrict_at<T>(ev3, b0.x, b1.x, b2.x, b3.x, zlo, zhi, c);
+                        v.y = restrict_at<T>(ev3, b0.y, b1.y, b2.y, b3.y, zlo, zhi, c);
+                    }
+                    T* r = Rz + (size_t)gy * (size_t)n1;
+                    r[0] = v.x;
+                    if (vx1) r[1] = v.y;
                 }
             }
         }
     }
 }
-template <typename T, int BY, int XW, int NW, int UN> int restrict3_march_launch(const T* in, T* out, i64 L1, i64 L2, i64 L3, i64 n1, i64 n2, i64 n3, double scale, cudaStream_t s) {
-    constexpr int BX = 32 * XW, IY = 2 * BY + 2;
+template <typename T, int BY, int NW, int UN> int restrict3_march_launch(const T* in, T* out, i64 L1, i64 L2, i64 L3, i64 n1, i64 n2, i64 n3, double scale, cudaStream_t s) {
+    constexpr int BX = 64, IY = 2 * BY + 2;
     const size_t smem = sizeof(T) * (size_t)(IY * BX + 4 * BY * BX);
-    auto kern = restrict3_march_kernel<T, BY, XW, NW, UN>;
+    auto kern = restrict3_march_kernel<T, BY, NW, UN>;
     GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const i64 gx = (n1 + BX - 1) / BX, gy = (n2 + BY - 1) / BY;
-    // chunks of output planes: long enough to amortise the two extra input planes of a chunk, short enough for
-    // a few CTAs per SM slot over the whole grid
     i64 zc = 32;
     while (zc > 4 && gx * gy * ((n3 + zc - 1) / zc) < (i64)num_sms() * 4 * 4) zc /= 2;
     dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)((n3 + zc - 1) / zc));
@@ -497,6 +521,7 @@ template <typename T, int BY, int XW, int NW, int UN> int restrict3_march_launch
     GB_CUDA(cudaGetLastError());
     return GB_OK;
 }
+
 template <typename T> int restrict3_impl(const i64* dims, const T* in, double scale, T* out, cudaStream_t s) {
     const i64 L1 = dims[0], L2 = dims[1], L3 = dims[2];
     const i64 n1 = rsize(L1), n2 = rsize(L2), n3 = rsize(L3);
@@ -517,10 +542,10 @@ template <typename T> int restrict3_impl(const i64* dims, const T* in, double sc
     // GB_RESTRICT3=brick selects it instead of the marching kernel (A/B measurements)
     static const bool brick = [] { const char* e = getenv("GB_RESTRICT3"); return e && e[0] == 'b'; }();
     if (brick) return restrict3_launch<T, 4, 4>(in, out, L1, L2, L3, n1, n2, n3, scale, s);
-    // Tile 32 x 8 outputs per CTA of two warps, three rows in flight per warp: measured best on the 1024 -> 17 chain
-    // (2.96 ms; 128 x 8 / 8 warps 3.5-3.9, 64 x 8 / 4 warps 3.25, 32 x 6 3.13, 32 x 4 3.34, 32 x 16 4.8; all rows of a
-    // warp in flight at once 3.86, fully unrolled row loop 4.83; the (32,4,4) brick kernel 3.59)
-    return restrict3_march_launch<T, 8, 1, 2, 3>(in, out, L1, L2, L3, n1, n2, n3, scale, s);
+    // Tile 64 x 4 outputs per CTA of five warps (ten staged rows: two per warp, both in flight): measured best on the
+    // 1024 -> 17 chain (2.63 ms; 64 x 4 / 4 warps 2.69, 64 x 8 / 4 warps 2.75-2.81, / 8 warps 2.77, 64 x 6 2.77, 64 x 4 / 8
+    // warps 3.68; one column per lane: 32 x 8 / 2 warps 2.96, 128 x 8 / 8 warps 3.5-3.9; the (32,4,4) brick kernel 3.59)
+    return restrict3_march_launch<T, 4, 5, 2>(in, out, L1, L2, L3, n1, n2, n3, scale, s);
 }
 
 // ---- fused 3-D prolong ------------------------------------------------------------------------
@@ -617,6 +642,111 @@ template <typename T, int BY, int BZ> __global__ void __launch_bounds__(256) pro
     }
 }
 
+// ---- fused 3-D prolong, marching along dim 3 (all three dimensions prolonged) ---------------------
+// Same idea as restrict3_march: a small CTA owns a 64 x BY output tile and walks a chunk of output planes.  Per
+// INPUT plane it prolongs dim 1 from global memory into S1[BY/2+1][64] (stage A) and dim 2 into one of two ring
+// slots S2[2][BY][64] (stage B); two consecutive slots then give two output planes (stage C, coalesced 512-byte
+// rows).  A lane owns the output pair x = 2*lane, 2*lane+1 for the whole kernel: both come from the same two
+// inputs, the parities are compile-time, and shared memory and (for even row lengths) global stores move pairs.  Same prolong_at calls in the same order as the brick kernel, hence the same bits.
+template <typename T, int BY, int NW> __global__ void __launch_bounds__(32 * NW) prolong3_march_kernel(const T* __restrict__ A, T* __restrict__ P, int n1, int n2, int n3, int m1, int m2,
+                                                                                               int m3, int zc) {
+    constexpr int BX = 64, NY = BY / 2 + 1, HX = BX / 2;  // a lane owns the output pair x = 2*lane, 2*lane + 1 (input column `xi`)
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using V = Pair<T>;
+    V* S1 = reinterpret_cast<V*>(smem_raw);  // [NY][HX]
+    V* S2 = S1 + NY * HX;                     // [2][BY][HX]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int k1 = blockIdx.x * BX, k2 = blockIdx.y * BY, k3 = blockIdx.z * zc;  // BX, BY and zc are even
+    const int y0 = k2 >> 1, z0 = k3 >> 1;
+    const bool ev1 = !(m1 & 1), ev2 = !(m2 & 1), ev3 = !(m3 & 1);
+    const int gx = k1 + 2 * lane, xi = gx >> 1;
+    const bool xv0 = gx < m1, xv1 = gx + 1 < m1, xh = xv0 && xi + 1 < n1;
+    const bool vst = xv1 && !(m1 & 1) && ((reinterpret_cast<uintptr_t>(P) & (2 * sizeof(T) - 1)) == 0);  // aligned pair stores
+    const int nplanes = min(zc, m3 - k3);  // output planes of this chunk
+    const size_t iplane = (size_t)n2 * (size_t)n1, oplane = (size_t)m2 * (size_t)m1;
+    for (int ip = 0; 2 * (ip - 1) < nplanes; ip++) {
+        const int lz = z0 + ip;
+        const bool zin = lz < n3;
+        // ---- stage A: dim-1 prolongation of input plane lz, rows y0 .. y0+NY-1
+        if (zin) {
+            const T* Az = A + (size_t)lz * iplane + xi;
+            for (int y = warp; y < NY; y += NW) {
+                const int gy = y0 + y;
+                V v{(T)0, (T)0};
+                if (gy < n2 && xv0) {
+                    const T* a = Az + (size_t)gy * (size_t)n1;
+                    const T a0 = __ldg(a), a1 = xh ? __ldg(a + 1) : (T)0;
+                    v.x = prolong_at<T>(ev1, false, a0, a1);
+                    if (xv1) v.y = prolong_at<T>(ev1, true, a0, a1);
+                }
+                S1[y * HX + lane] = v;
+            }
+        }
+        __syncthreads();
+        // ---- stage B: dim-2 prolongation into ring slot ip & 1
+        if (zin) {
+            V* dst = S2 + ((ip & 1) * BY) * HX + lane;
+            for (int y = warp; y < BY; y += NW) {
+                const int gy = k2 + y;
+                V v{(T)0, (T)0};
+                if (gy < m2) {
+                    const bool has1 = (gy >> 1) + 1 < n2;
+                    const V b0 = S1[(y >> 1) * HX + lane];
+                    V b1{(T)0, (T)0};
+                    if (has1) b1 = S1[((y >> 1) + 1) * HX + lane];
+                    v.x = prolong_at<T>(ev2, gy & 1, b0.x, b1.x);
+                    v.y = prolong_at<T>(ev2, gy & 1, b0.y, b1.y);
+                }
+                dst[y * HX] = v;
+            }
+        }
+        __syncthreads();
+        // ---- stage C: output planes 2(lz-1), 2(lz-1)+1 from slots (ip-1) & 1 (plane lz-1) and ip & 1 (plane lz)
+        if (ip >= 1 && xv0) {
+            const V* s0 = S2 + (((ip - 1) & 1) * BY) * HX + lane;
+            const V* s1 = S2 + ((ip & 1) * BY) * HX + lane;
+#pragma unroll
+            for (int par = 0; par < 2; par++) {
+                const int gz = k3 + 2 * (ip - 1) + par;
+                if (gz < k3 + nplanes) {  // uniform
+                    T* Pz = P + (size_t)gz * oplane + gx;
+                    for (int y = warp; y < BY; y += NW) {
+                        const int gy = k2 + y;
+                        if (gy < m2) {
+                            const V c0 = s0[y * HX];
+                            V c1{(T)0, (T)0};
+                            if (zin) c1 = s1[y * HX];
+                            V o;
+                            o.x = prolong_at<T>(ev3, par, c0.x, c1.x);
+                            o.y = prolong_at<T>(ev3, par, c0.y, c1.y);
+                            T* p = Pz + (size_t)gy * (size_t)m1;
+                            if (vst) *reinterpret_cast<V*>(p) = o;
+                            else {
+                                p[0] = o.x;
+                                if (xv1) p[1] = o.y;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+template <typename T, int BY, int NW> int prolong3_march_launch(const T* in, T* out, i64 n1, i64 n2, i64 n3, const i64* m, cudaStream_t s) {
+    constexpr int BX = 64, NY = BY / 2 + 1;
+    const size_t smem = sizeof(T) * (size_t)(NY * BX + 2 * BY * BX);
+    auto kern = prolong3_march_kernel<T, BY, NW>;
+    GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const i64 gx = (m[0] + BX - 1) / BX, gy = (m[1] + BY - 1) / BY;
+    i64 zc = 64;  // output planes per chunk (even): one extra input plane per chunk
+    while (zc > 8 && gx * gy * ((m[2] + zc - 1) / zc) < (i64)num_sms() * 4 * 4) zc /= 2;
+    dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)((m[2] + zc - 1) / zc));
+    kern<<<grid, 32 * NW, smem, s>>>(in, out, (int)n1, (int)n2, (int)n3, (int)m[0], (int)m[1], (int)m[2], (int)zc);
+    count_launch();
+    GB_CUDA(cudaGetLastError());
+    return GB_OK;
+}
+
 template <typename T> int prolong3_impl(const i64* dims, const T* in, const i64* odims, T* out, cudaStream_t s) {
     const i64 n1 = dims[0], n2 = dims[1], n3 = dims[2];
     i64 m[3];
@@ -633,6 +763,12 @@ template <typename T> int prolong3_impl(const i64* dims, const T* in, const i64*
     if (m[0] * m[1] * m[2] == 0) return GB_OK;
     for (int d = 0; d < 3; d++)
         if (m[d] >= (1ll << 30)) return fail(GB_ERR_UNSUPPORTED, "prolong3: extent too large");
+    if (doit[0] && doit[1] && doit[2]) {  // the full prolongation marches (GB_PROLONG3=brick: A/B measurements)
+        static const bool brick = [] { const char* e = getenv("GB_PROLONG3"); return e && e[0] == 'b'; }();
+        // 64 x 8 tile, 4 warps: measured best on the 17 -> 1024 chain (2.29 ms; 2 warps 2.45, 8 warps 2.46, 64 x 4 2.37-2.62,
+        // 64 x 12 2.31, 64 x 16 2.36-3.4; with one column per lane instead of a pair 2.78; the (64,8,8) brick kernel 3.06)
+        if (!brick) return prolong3_march_launch<T, 8, 4>(in, out, n1, n2, n3, m, s);
+    }
     constexpr int BX = 64, BY = 8, BZ = 8;
     const int sny = doit[1] ? BY / 2 + 1 : BY, snz = doit[2] ? BZ / 2 + 1 : BZ;
     const size_t smem = sizeof(T) * ((size_t)snz * sny * BX + (size_t)snz * BY * BX);  // S1 + S2 (33 KB for a full f64 prolongation: 6 CTAs per SM)
