@@ -29,3 +29,14 @@ t0 = time.perf_counter()
 for _ in range(5):
     vh.copy_(vd, non_blocking=True); gh.copy_(gd, non_blocking=True); torch.cuda.synchronize()
 print("D2H 320 MB alone: %.2f ms" % ((time.perf_counter() - t0) / 5 * 1e3))
+# both directions at once on two streams: the floor of any pipelined host-buffer call
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(5):
+    with torch.cuda.stream(s1):
+        Xd.copy_(Xh, non_blocking=True)
+    with torch.cuda.stream(s2):
+        vh.copy_(vd, non_blocking=True); gh.copy_(gd, non_blocking=True)
+    torch.cuda.synchronize()
+print("H2D 240 MB + D2H 320 MB concurrently: %.2f ms" % ((time.perf_counter() - t0) / 5 * 1e3))

@@ -763,7 +763,8 @@ def test_blocked_layout(gb, oracle):
     change, eval.cuh tap_offset).  GB_BLOCK_MIN_MB=0 in a child process puts small grids in that layout: every
     order and BC, all output modes, ragged extents (not multiples of 4), queries exactly on the upper edges
     (the D1 / offset-table taps that carry into the next column), device and host queries, the tensor-product
-    call, and G.coefs back in the reference layout -- all bit-identical to the oracle."""
+    call, G.coefs back in the reference layout, and a second grid adopted from those coefficients (the multi-GPU
+    broadcast path) -- all bit-identical to the oracle."""
     import os
     import subprocess
     import sys
@@ -789,6 +790,8 @@ def test_blocked_layout(gb, oracle):
             "    out = dict(v=v.cpu().numpy(), g=gr.cpu().numpy(), hv=gb.getindex_batch(g, X), c=g.coefs, cd=gb.jl_to_numpy(g.coefs_device()))\n"
             "    if h is not None: out['h'] = h.cpu().numpy()\n"
             "    out['o'] = g[tuple(z[f'x{k}'] for k in range(A.ndim))]\n"
+            "    g2 = gb.InterpGrid.from_coefs(g.coefs_device(), gb.BCfill if bc == 'fill' else BC[bc], IT[order], fill=-1.25)\n"
+            "    out['v2'] = g2._eval(torch.from_numpy(X).cuda(), 1)[0].cpu().numpy()\n"
             "    np.savez(f'{d}/out_{tag}.npz', **out)\n"
         )
         keep = []
@@ -824,7 +827,7 @@ def test_blocked_layout(gb, oracle):
             assert same(z["v"], ov) and same(z["g"], og) and same(z["hv"], ov), (tag, bc, order)
             if mode == 7:
                 assert same(z["h"], oh), (tag, bc, order)
-            assert same(z["c"], co) and same(z["cd"], co), (tag, bc, order)
+            assert same(z["c"], co) and same(z["cd"], co) and same(z["v2"], ov), (tag, bc, order)
             ref = oracle.OracleGrid(A, bc, order, fill=fill).outer(*[vecs[f"x{j}"] for j in range(A.ndim)])
             assert same(z["o"], ref.astype(dtype)), (tag, bc, order)
 
