@@ -1110,6 +1110,22 @@ int gb_prolong_slab(int dtype, int ndim, const int64_t* dims, const void* in, in
     }, &ctx);
 }
 
+// fused 3-D operators on one slab of an array sharded along dim 3 (device memory: the multi-GPU path keeps slabs resident)
+int gb_restrict3_slab(int dtype, const int64_t* dims, const void* in, double scale, int64_t global_len3, int64_t in_first, int64_t out_first,
+                      int64_t out_count, void* out, int mem, void* stream) {
+    if (!ok_dtype(dtype) || !dims || !in || !out) return fail(GB_ERR_ARG, "bad arguments");
+    if (mem != GB_DEVICE) return fail(GB_ERR_UNSUPPORTED, "gb_restrict3_slab takes device memory");
+    pool_keep_memory();
+    return restrict3_slab_device(dtype, (const i64*)dims, in, scale, global_len3, in_first, out_first, out_count, out, (cudaStream_t)stream);
+}
+int gb_prolong3_slab(int dtype, const int64_t* dims, const void* in, const int64_t* out_dims, int64_t global_n3, int64_t in_first, int64_t out_first,
+                     int64_t out_count, void* out, int mem, void* stream) {
+    if (!ok_dtype(dtype) || !dims || !in || !out || !out_dims) return fail(GB_ERR_ARG, "bad arguments");
+    if (mem != GB_DEVICE) return fail(GB_ERR_UNSUPPORTED, "gb_prolong3_slab takes device memory");
+    pool_keep_memory();
+    return prolong3_slab_device(dtype, (const i64*)dims, in, (const i64*)out_dims, global_n3, in_first, out_first, out_count, out, (cudaStream_t)stream);
+}
+
 int gb_restrict3(int dtype, const int64_t* dims, const void* in, double scale, void* out, int mem, void* stream) {
     if (!ok_dtype(dtype) || !dims || !in || !out) return fail(GB_ERR_ARG, "bad arguments");
     for (int d = 0; d < 3; d++)

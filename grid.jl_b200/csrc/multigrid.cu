@@ -386,15 +386,18 @@ template <typename T> __device__ __forceinline__ T restrict_full(bool even, T am
 // A lane owns outputs x = 2*lane, 2*lane+1 of the 64-wide tile: their eight taps are six consecutive inputs (three
 // aligned 16-byte loads), and shared memory moves pairs (one column per lane: 2.94 instead of 2.63 ms per chain).
 template <typename T, int BY, int NW, int UN> __global__ void __launch_bounds__(32 * NW) restrict3_march_kernel(const T* __restrict__ A, T* __restrict__ R, int L1, int L2, int L3, int n1,
-                                                                                                        int n2, int n3, int zc, RCoef<T> c) {
+                                                                                                        int n2, int n3, int zc, RCoef<T> c, int zin0, int nzin,
+                                                                                                        int zout0, int ocount) {
+    // slab form: A holds input planes [zin0, zin0 + nzin) of the L3 global ones, R output planes [zout0, zout0 + ocount)
+    // of the n3 global ones (whole array: 0, L3, 0, n3); plane indices below are global
     constexpr int HX = 32, BX = 64, IY = 2 * BY + 2;
     using V = Pair<T>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     V* S1 = reinterpret_cast<V*>(smem_raw);  // [IY][HX]
     V* S2 = S1 + IY * HX;                     // [4][BY][HX]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int j1 = blockIdx.x * BX, j2 = blockIdx.y * BY, j3 = blockIdx.z * zc;
-    const int nzo = min(zc, n3 - j3);
+    const int j1 = blockIdx.x * BX, j2 = blockIdx.y * BY, j3 = zout0 + blockIdx.z * zc;
+    const int nzo = min(zc, zout0 + ocount - j3);
     const int y0 = 2 * j2 - 2, z0 = 2 * j3 - 2;
     const bool ev1 = !(L1 & 1), ev2 = !(L2 & 1), ev3 = !(L3 & 1);
     const bool vec = sizeof(T) == 8 && !(L1 & 1) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);  // rows 16-byte aligned
@@ -405,10 +408,10 @@ template <typename T, int BY, int NW, int UN> __global__ void __launch_bounds__(
     const size_t plane = (size_t)L2 * (size_t)L1;
     for (int p = 0; p < 2 * nzo + 2; p++) {
         const int gz = z0 + p;
-        const bool zok = gz >= 0 && gz < L3;
+        const bool zok = gz >= zin0 && gz < zin0 + nzin;  // (planes a needed tap lies on are present: checked by the host)
         // ---- stage A: dim-1 restriction; inputs t[0..5] = A[2gx-2 .. 2gx+3]
         if (zok && j1 < n1) {
-            const T* Ac = A + (size_t)gz * plane + 2 * gx;
+            const T* Ac = A + (size_t)(gz - zin0) * plane + 2 * gx;
 #pragma unroll 1
             for (int k0 = 0; k0 < (IY + NW - 1) / NW; k0 += UN) {
                 T t[UN][6];
@@ -484,7 +487,7 @@ template <typename T, int BY, int NW, int UN> __global__ void __launch_bounds__(
             const V* s1 = S2 + (((p + 2) & 3) * BY) * HX + lane;
             const V* s2 = S2 + (((p + 3) & 3) * BY) * HX + lane;
             const V* s3 = S2 + ((p & 3) * BY) * HX + lane;
-            T* Rz = R + (size_t)gzo * (size_t)n2 * (size_t)n1 + gx;
+            T* Rz = R + (size_t)(gzo - zout0) * (size_t)n2 * (size_t)n1 + gx;
             for (int y = warp; y < BY; y += NW) {
                 const int gy = j2 + y;
                 if (gy < n2) {
@@ -507,16 +510,18 @@ template <typename T, int BY, int NW, int UN> __global__ void __launch_bounds__(
         }
     }
 }
-template <typename T, int BY, int NW, int UN> int restrict3_march_launch(const T* in, T* out, i64 L1, i64 L2, i64 L3, i64 n1, i64 n2, i64 n3, double scale, cudaStream_t s) {
+template <typename T, int BY, int NW, int UN>
+int restrict3_march_launch(const T* in, T* out, i64 L1, i64 L2, i64 L3, i64 n1, i64 n2, i64 n3, double scale, i64 zin0, i64 nzin, i64 zout0, i64 ocount, cudaStream_t s) {
     constexpr int BX = 64, IY = 2 * BY + 2;
     const size_t smem = sizeof(T) * (size_t)(IY * BX + 4 * BY * BX);
     auto kern = restrict3_march_kernel<T, BY, NW, UN>;
     GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const i64 gx = (n1 + BX - 1) / BX, gy = (n2 + BY - 1) / BY;
     i64 zc = 32;
-    while (zc > 4 && gx * gy * ((n3 + zc - 1) / zc) < (i64)num_sms() * 4 * 4) zc /= 2;
-    dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)((n3 + zc - 1) / zc));
-    kern<<<grid, 32 * NW, smem, s>>>(in, out, (int)L1, (int)L2, (int)L3, (int)n1, (int)n2, (int)n3, (int)zc, make_coef<T>(scale));
+    while (zc > 4 && gx * gy * ((ocount + zc - 1) / zc) < (i64)num_sms() * 4 * 4) zc /= 2;
+    dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)((ocount + zc - 1) / zc));
+    kern<<<grid, 32 * NW, smem, s>>>(in, out, (int)L1, (int)L2, (int)L3, (int)n1, (int)n2, (int)n3, (int)zc, make_coef<T>(scale), (int)zin0, (int)nzin, (int)zout0,
+                                     (int)ocount);
     count_launch();
     GB_CUDA(cudaGetLastError());
     return GB_OK;
@@ -545,7 +550,23 @@ template <typename T> int restrict3_impl(const i64* dims, const T* in, double sc
     // Tile 64 x 4 outputs per CTA of five warps (ten staged rows: two per warp, both in flight): measured best on the
     // 1024 -> 17 chain (2.63 ms; 64 x 4 / 4 warps 2.69, 64 x 8 / 4 warps 2.75-2.81, / 8 warps 2.77, 64 x 6 2.77, 64 x 4 / 8
     // warps 3.68; one column per lane: 32 x 8 / 2 warps 2.96, 128 x 8 / 8 warps 3.5-3.9; the (32,4,4) brick kernel 3.59)
-    return restrict3_march_launch<T, 4, 5, 2>(in, out, L1, L2, L3, n1, n2, n3, scale, s);
+    return restrict3_march_launch<T, 4, 5, 2>(in, out, L1, L2, L3, n1, n2, n3, scale, 0, L3, 0, n3, s);
+}
+
+// restrict(A, [true,true,true], scale) on ONE SLAB of a 3-D array sharded along dim 3: `in` holds input planes
+// [in_first, in_first + dims[2]) of the L3 global ones, `out` receives output planes [out_first, out_first + ocount).
+template <typename T> int restrict3_slab_impl(const i64* dims, const T* in, double scale, i64 L3, i64 in_first, i64 out_first, i64 ocount, T* out, cudaStream_t s) {
+    const i64 L1 = dims[0], L2 = dims[1], nloc = dims[2];
+    const i64 n1 = rsize(L1), n2 = rsize(L2), n3 = rsize(L3);
+    if (L1 < 2 || L2 < 2 || L3 < 2) return fail(GB_ERR_UNSUPPORTED, "restrict3 slab: extents below 2 (use gb_restrict_slab per dimension)");
+    if (L1 >= (1ll << 30) || L2 >= (1ll << 30) || L3 >= (1ll << 30)) return fail(GB_ERR_UNSUPPORTED, "restrict3: extent too large");
+    if (ocount < 0 || out_first < 0 || out_first + ocount > n3) return fail(GB_ERR_ARG, "restrict: output planes out of range");
+    if (in_first < 0 || in_first + nloc > L3) return fail(GB_ERR_ARG, "restrict: input planes out of range");
+    if (ocount == 0) return GB_OK;
+    i64 lo, hi;
+    restrict_needs(L3, n3, out_first, out_first + ocount, &lo, &hi);
+    if (lo < in_first || hi >= in_first + nloc) return fail(GB_ERR_ARG, "restrict: the slab does not hold every input plane the requested outputs need");
+    return restrict3_march_launch<T, 4, 5, 2>(in, out, L1, L2, L3, n1, n2, n3, scale, in_first, nloc, out_first, ocount, s);
 }
 
 // ---- fused 3-D prolong ------------------------------------------------------------------------
@@ -649,27 +670,29 @@ template <typename T, int BY, int BZ> __global__ void __launch_bounds__(256) pro
 // rows).  A lane owns the output pair x = 2*lane, 2*lane+1 for the whole kernel: both come from the same two
 // inputs, the parities are compile-time, and shared memory and (for even row lengths) global stores move pairs.  Same prolong_at calls in the same order as the brick kernel, hence the same bits.
 template <typename T, int BY, int NW> __global__ void __launch_bounds__(32 * NW) prolong3_march_kernel(const T* __restrict__ A, T* __restrict__ P, int n1, int n2, int n3, int m1, int m2,
-                                                                                               int m3, int zc) {
+                                                                                               int m3, int zc, int zin0, int nzin, int zout0, int ocount) {
+    // slab form: A holds input planes [zin0, zin0 + nzin) (of the n3 global ones), P output planes [zout0, zout0 + ocount) of the
+    // m3 global ones (whole array: 0, 0, m3); plane indices below are global
     constexpr int BX = 64, NY = BY / 2 + 1, HX = BX / 2;  // a lane owns the output pair x = 2*lane, 2*lane + 1 (input column `xi`)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using V = Pair<T>;
     V* S1 = reinterpret_cast<V*>(smem_raw);  // [NY][HX]
     V* S2 = S1 + NY * HX;                     // [2][BY][HX]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int k1 = blockIdx.x * BX, k2 = blockIdx.y * BY, k3 = blockIdx.z * zc;  // BX, BY and zc are even
+    const int k1 = blockIdx.x * BX, k2 = blockIdx.y * BY, k3 = (zout0 & ~1) + blockIdx.z * zc;  // BX, BY, zc and k3 are even
     const int y0 = k2 >> 1, z0 = k3 >> 1;
     const bool ev1 = !(m1 & 1), ev2 = !(m2 & 1), ev3 = !(m3 & 1);
     const int gx = k1 + 2 * lane, xi = gx >> 1;
     const bool xv0 = gx < m1, xv1 = gx + 1 < m1, xh = xv0 && xi + 1 < n1;
     const bool vst = xv1 && !(m1 & 1) && ((reinterpret_cast<uintptr_t>(P) & (2 * sizeof(T) - 1)) == 0);  // aligned pair stores
-    const int nplanes = min(zc, m3 - k3);  // output planes of this chunk
+    const int nplanes = min(zc, zout0 + ocount - k3);  // output planes of this chunk (those below zout0 are skipped)
     const size_t iplane = (size_t)n2 * (size_t)n1, oplane = (size_t)m2 * (size_t)m1;
     for (int ip = 0; 2 * (ip - 1) < nplanes; ip++) {
         const int lz = z0 + ip;
-        const bool zin = lz < n3;
+        const bool zin = lz < n3 && lz < zin0 + nzin;  // (planes a needed tap lies on are present: checked by the host)
         // ---- stage A: dim-1 prolongation of input plane lz, rows y0 .. y0+NY-1
         if (zin) {
-            const T* Az = A + (size_t)lz * iplane + xi;
+            const T* Az = A + (size_t)(lz - zin0) * iplane + xi;
             for (int y = warp; y < NY; y += NW) {
                 const int gy = y0 + y;
                 V v{(T)0, (T)0};
@@ -708,8 +731,8 @@ template <typename T, int BY, int NW> __global__ void __launch_bounds__(32 * NW)
 #pragma unroll
             for (int par = 0; par < 2; par++) {
                 const int gz = k3 + 2 * (ip - 1) + par;
-                if (gz < k3 + nplanes) {  // uniform
-                    T* Pz = P + (size_t)gz * oplane + gx;
+                if (gz < k3 + nplanes && gz >= zout0) {  // uniform
+                    T* Pz = P + (size_t)(gz - zout0) * oplane + gx;
                     for (int y = warp; y < BY; y += NW) {
                         const int gy = k2 + y;
                         if (gy < m2) {
@@ -732,16 +755,17 @@ template <typename T, int BY, int NW> __global__ void __launch_bounds__(32 * NW)
         }
     }
 }
-template <typename T, int BY, int NW> int prolong3_march_launch(const T* in, T* out, i64 n1, i64 n2, i64 n3, const i64* m, cudaStream_t s) {
+template <typename T, int BY, int NW> int prolong3_march_launch(const T* in, T* out, i64 n1, i64 n2, i64 n3, const i64* m, i64 zin0, i64 nzin, i64 zout0, i64 ocount, cudaStream_t s) {
     constexpr int BX = 64, NY = BY / 2 + 1;
     const size_t smem = sizeof(T) * (size_t)(NY * BX + 2 * BY * BX);
     auto kern = prolong3_march_kernel<T, BY, NW>;
     GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const i64 gx = (m[0] + BX - 1) / BX, gy = (m[1] + BY - 1) / BY;
     i64 zc = 64;  // output planes per chunk (even): one extra input plane per chunk
-    while (zc > 8 && gx * gy * ((m[2] + zc - 1) / zc) < (i64)num_sms() * 4 * 4) zc /= 2;
-    dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)((m[2] + zc - 1) / zc));
-    kern<<<grid, 32 * NW, smem, s>>>(in, out, (int)n1, (int)n2, (int)n3, (int)m[0], (int)m[1], (int)m[2], (int)zc);
+    const i64 span = zout0 + ocount - (zout0 & ~(i64)1);  // planes from the even chunk origin
+    while (zc > 8 && gx * gy * ((span + zc - 1) / zc) < (i64)num_sms() * 4 * 4) zc /= 2;
+    dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)((span + zc - 1) / zc));
+    kern<<<grid, 32 * NW, smem, s>>>(in, out, (int)n1, (int)n2, (int)n3, (int)m[0], (int)m[1], (int)m[2], (int)zc, (int)zin0, (int)nzin, (int)zout0, (int)ocount);
     count_launch();
     GB_CUDA(cudaGetLastError());
     return GB_OK;
@@ -767,7 +791,7 @@ template <typename T> int prolong3_impl(const i64* dims, const T* in, const i64*
         static const bool brick = [] { const char* e = getenv("GB_PROLONG3"); return e && e[0] == 'b'; }();
         // 64 x 8 tile, 4 warps: measured best on the 17 -> 1024 chain (2.29 ms; 2 warps 2.45, 8 warps 2.46, 64 x 4 2.37-2.62,
         // 64 x 12 2.31, 64 x 16 2.36-3.4; with one column per lane instead of a pair 2.78; the (64,8,8) brick kernel 3.06)
-        if (!brick) return prolong3_march_launch<T, 8, 4>(in, out, n1, n2, n3, m, s);
+        if (!brick) return prolong3_march_launch<T, 8, 4>(in, out, n1, n2, n3, m, 0, n3, 0, m[2], s);
     }
     constexpr int BX = 64, BY = 8, BZ = 8;
     const int sny = doit[1] ? BY / 2 + 1 : BY, snz = doit[2] ? BZ / 2 + 1 : BZ;
@@ -779,6 +803,26 @@ template <typename T> int prolong3_impl(const i64* dims, const T* in, const i64*
     count_launch();
     GB_CUDA(cudaGetLastError());
     return GB_OK;
+}
+
+// prolong(A, [m1,m2,m3]) (every dimension prolonged) on ONE SLAB of a 3-D array sharded along dim 3: `in` holds coarse
+// planes [in_first, in_first + dims[2]) of the n3 global ones, `out` receives fine planes [out_first, out_first + ocount).
+template <typename T> int prolong3_slab_impl(const i64* dims, const T* in, const i64* m, i64 n3, i64 in_first, i64 out_first, i64 ocount, T* out, cudaStream_t s) {
+    const i64 n1 = dims[0], n2 = dims[1], nloc = dims[2];
+    const i64 nn[3] = {n1, n2, n3};
+    for (int d = 0; d < 3; d++) {
+        const i64 newsz = (m[d] & 1) ? 2 * nn[d] - 1 : 2 * (nn[d] - 1);
+        if (newsz != m[d]) return fail(GB_ERR_PROLONG_SIZE, "Cannot prolong a dimension of length " + std::to_string(nn[d]) + " to " + std::to_string(m[d]));
+        if (m[d] <= nn[d]) return fail(GB_ERR_UNSUPPORTED, "prolong3 slab: every dimension must grow (use gb_prolong_slab per dimension)");
+        if (m[d] >= (1ll << 30)) return fail(GB_ERR_UNSUPPORTED, "prolong3: extent too large");
+    }
+    if (ocount < 0 || out_first < 0 || out_first + ocount > m[2]) return fail(GB_ERR_ARG, "prolong: output planes out of range");
+    if (in_first < 0 || in_first + nloc > n3) return fail(GB_ERR_ARG, "prolong: input planes out of range");
+    if (ocount == 0) return GB_OK;
+    i64 lo, hi;
+    prolong_needs(n3, m[2], out_first, out_first + ocount, &lo, &hi);
+    if (lo < in_first || hi >= in_first + nloc) return fail(GB_ERR_ARG, "prolong: the slab does not hold every input plane the requested outputs need");
+    return prolong3_march_launch<T, 8, 4>(in, out, n1, n2, n3, m, in_first, nloc, out_first, ocount, s);
 }
 
 // ---- synthetic inputs ---------------------------------------------------------------------------
@@ -893,6 +937,16 @@ int restrict_slab_device(int dtype, int ndim, const i64* dims, const void* in, i
                          cudaStream_t s) {
     if (dtype == GB_F64) return restrict_slab_impl<double>(ndim, dims, (const double*)in, dim, scale, L, in_first, out_first, ocount, (double*)out, s);
     if (dtype == GB_F32) return restrict_slab_impl<float>(ndim, dims, (const float*)in, dim, scale, L, in_first, out_first, ocount, (float*)out, s);
+    return fail(GB_ERR_ARG, "bad dtype");
+}
+int restrict3_slab_device(int dtype, const i64* dims, const void* in, double scale, i64 L3, i64 in_first, i64 out_first, i64 ocount, void* out, cudaStream_t s) {
+    if (dtype == GB_F64) return restrict3_slab_impl<double>(dims, (const double*)in, scale, L3, in_first, out_first, ocount, (double*)out, s);
+    if (dtype == GB_F32) return restrict3_slab_impl<float>(dims, (const float*)in, scale, L3, in_first, out_first, ocount, (float*)out, s);
+    return fail(GB_ERR_ARG, "bad dtype");
+}
+int prolong3_slab_device(int dtype, const i64* dims, const void* in, const i64* m, i64 n3, i64 in_first, i64 out_first, i64 ocount, void* out, cudaStream_t s) {
+    if (dtype == GB_F64) return prolong3_slab_impl<double>(dims, (const double*)in, m, n3, in_first, out_first, ocount, (double*)out, s);
+    if (dtype == GB_F32) return prolong3_slab_impl<float>(dims, (const float*)in, m, n3, in_first, out_first, ocount, (float*)out, s);
     return fail(GB_ERR_ARG, "bad dtype");
 }
 int prolong_slab_device(int dtype, int ndim, const i64* dims, const void* in, int dim, i64 n, i64 len, i64 in_first, i64 out_first, i64 ocount, void* out,

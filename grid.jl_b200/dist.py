@@ -5,10 +5,11 @@ the CPU tests).  Nothing here is on the single-GPU hot path.
   prefiltered once and replicated with ONE broadcast (`broadcast_grid`); no per-call collective.
 * restrict / prolong of a 3-D array shard by slabs along the last (slowest) dimension.  One
   exchange step per level: each rank receives the few boundary planes ("halo") its outputs read
-  from its neighbours, then runs the slab kernels (gb_restrict_slab / gb_prolong_slab).  The
-  per-element arithmetic is unchanged, so the gathered result equals the single-device one bit
-  for bit.  The halo travels where it is smallest: after the local dim-1/2 restriction
-  (planes 4x smaller) for restrict, before the dim-1/2 prolongation for prolong.
+  from its neighbours, then runs the fused slab kernels (gb_restrict3_slab / gb_prolong3_slab: the marching
+  kernels of multigrid.cu with plane offsets, one pass over the slab).  The per-element arithmetic is
+  unchanged, so the gathered result equals the single-device one bit for bit.  Degenerate extents and partial
+  prolongations take the per-dimension slab kernels (gb_restrict_slab / gb_prolong_slab), where the halo travels
+  after the local dim-1/2 restriction / before the dim-1/2 prolongation.
 """
 from __future__ import annotations
 
@@ -150,6 +151,33 @@ class GpuEngine:
     def prolong_slab(self, a, n, length, in_first, out_first, count):
         return self._slab("gb_prolong_slab", a, (int(n), int(length)), in_first, out_first, count)
 
+    # fused 3-D operators on a slab (gb_restrict3_slab / gb_prolong3_slab: the marching kernels, one pass over the slab)
+    fused = True
+
+    def restrict3_slab(self, a, scale, L3, in_first, out_first, count):
+        from . import _lib as L
+        from .api import _Arr, _i64s
+
+        arr = _Arr(a, name="slab")
+        n1, n2 = (restrict_size(int(v)) for v in arr.shape[:2])
+        out = arr.empty_like_shape((n1, n2, int(count)))
+        o = _Arr(out, name="out")
+        L.check(L.lib().gb_restrict3_slab(arr.dtype, _i64s(arr.shape), arr.ptr, float(scale), int(L3), int(in_first), int(out_first), int(count), o.ptr,
+                                          arr.mem, arr.stream()))
+        return out
+
+    def prolong3_slab(self, a, target, n3, in_first, out_first, count):
+        from . import _lib as L
+        from .api import _Arr, _i64s
+
+        arr = _Arr(a, name="slab")
+        m1, m2, m3 = (int(v) for v in target)
+        out = arr.empty_like_shape((m1, m2, int(count)))
+        o = _Arr(out, name="out")
+        L.check(L.lib().gb_prolong3_slab(arr.dtype, _i64s(arr.shape), arr.ptr, _i64s((m1, m2, m3)), int(n3), int(in_first), int(out_first), int(count), o.ptr,
+                                         arr.mem, arr.stream()))
+        return out
+
     def _slab(self, fn, a, head, in_first, out_first, count):
         import ctypes as C
 
@@ -170,6 +198,12 @@ def slab_restrict3(local, global_len3, rank, world, scale=1.0, engine=None, grou
     shard_range(restrict_size(global_len3), rank, world) of the result."""
     engine = engine or GpuEngine()
     plan = SlabPlan("restrict", global_len3, restrict_size(global_len3), world)
+    if getattr(engine, "fused", False) and min(int(local.shape[0]), int(local.shape[1]), int(global_len3)) >= 2:
+        # fused: the halo is the raw fine planes (<= 2 per side; a few MB over NVLink), then ONE pass over the slab
+        # (10 B per fine point of HBM traffic instead of ~24 for the three per-dimension passes)
+        ext, first = exchange_halo(local, plan, rank, group)
+        k0, k1 = plan.out[rank]
+        return engine.restrict3_slab(ext, scale, global_len3, first, k0, k1 - k0)
     r12 = engine.restrict_dims12(local, scale)                  # dims 1,2: planes are independent
     ext, first = exchange_halo(r12, plan, rank, group)          # halo of the 4x smaller planes
     k0, k1 = plan.out[rank]
@@ -183,6 +217,9 @@ def slab_prolong3(local, global_n3, target, rank, world, engine=None, group=None
     m1, m2, m3 = (int(v) for v in target)
     plan = SlabPlan("prolong", global_n3, m3, world)
     ext, first = exchange_halo(local, plan, rank, group)        # halo of the coarse (small) planes
+    if getattr(engine, "fused", False) and m1 > int(local.shape[0]) and m2 > int(local.shape[1]) and m3 > int(global_n3):
+        k0, k1 = plan.out[rank]
+        return engine.prolong3_slab(ext, (m1, m2, m3), global_n3, first, k0, k1 - k0)   # one pass (marching kernel)
     p12 = engine.prolong_dims12(ext, m1, m2)                    # dims 1,2 on own + halo planes
     k0, k1 = plan.out[rank]
     return engine.prolong_slab(p12, global_n3, m3, first, k0, k1 - k0)

@@ -197,6 +197,14 @@ int gb_restrict_slab(int dtype, int ndim, const int64_t* dims, const void* in, i
                      int64_t in_first, int64_t out_first, int64_t out_count, void* out, int mem, void* stream);
 int gb_prolong_slab(int dtype, int ndim, const int64_t* dims, const void* in, int dim, int64_t global_n, int64_t global_len,
                     int64_t in_first, int64_t out_first, int64_t out_count, void* out, int mem, void* stream);
+/* The fused 3-D operators (below) on ONE SLAB of an array sharded along its last dimension: `in` holds planes
+ * [in_first, in_first + dims[2]) of the global array (extent global_len3 / global_n3 along dim 3), `out` receives output
+ * planes [out_first, out_first + out_count).  Device memory only.  The slab must hold every plane the requested outputs
+ * read (GB_ERR_ARG otherwise); gb_prolong3_slab requires every dimension to grow (out_dims = the GLOBAL target). */
+int gb_restrict3_slab(int dtype, const int64_t* dims, const void* in, double scale, int64_t global_len3, int64_t in_first,
+                      int64_t out_first, int64_t out_count, void* out, int mem, void* stream);
+int gb_prolong3_slab(int dtype, const int64_t* dims, const void* in, const int64_t* out_dims, int64_t global_n3,
+                     int64_t in_first, int64_t out_first, int64_t out_count, void* out, int mem, void* stream);
 /* restrict(A, [true,true,true], scale) on a 3-D array as ONE pass over the fine grid; the
  * per-dim intermediates are rounded exactly as the staged reference does, so the result is
  * bit-identical to gb_restrict applied to dims 0,1,2 in turn (src/utilities.jl:7-20). */

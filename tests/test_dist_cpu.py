@@ -48,6 +48,16 @@ class OracleEngine:
         A = self._np(a)
         return self._t(self.O.prolong_sizes(A, [m1, m2, A.shape[2]]))
 
+    # the fused slab operators of GpuEngine, restated as dims 1,2 on the slab followed by the dim-3 slab operator
+    fused = True
+
+    def restrict3_slab(self, a, scale, L3, in_first, out_first, count):
+        return self.restrict_slab(self.restrict_dims12(a, scale), scale, L3, in_first, out_first, count)
+
+    def prolong3_slab(self, a, target, n3, in_first, out_first, count):
+        m1, m2, m3 = (int(v) for v in target)
+        return self.prolong_slab(self.prolong_dims12(a, m1, m2), n3, m3, in_first, out_first, count)
+
     def restrict_slab(self, a, scale, L, in_first, out_first, count):
         A = self._np(a)
         T = A.dtype.type
@@ -115,17 +125,20 @@ def _worker(rank, world, port, shape, q):
     L3 = shape[2]
     f0, f1 = D.shard_range(L3, rank, world)
     local = eng._t(A[:, :, f0:f1])
-    # restrict
-    mine = D.slab_restrict3(local, L3, rank, world, 1.0, engine=eng)
     n3 = D.restrict_size(L3)
     k0, k1 = D.shard_range(n3, rank, world)
     ref = O.restrict_flags(A, [True, True, True])
-    ok_r = np.array_equal(eng._np(mine), ref[:, :, k0:k1])
-    # prolong the (reference) coarse array back to the fine size, sharded
-    coarse_local = eng._t(ref[:, :, k0:k1])
-    up = D.slab_prolong3(coarse_local, n3, shape, rank, world, engine=eng)
     refp = O.prolong_sizes(ref, list(shape))
-    ok_p = np.array_equal(eng._np(up), refp[:, :, f0:f1])
+    ok_r = ok_p = True
+    for fused in (True, False):  # fused slab operators (halo of raw planes) and the per-dimension route
+        eng.fused = fused
+        # restrict
+        mine = D.slab_restrict3(local, L3, rank, world, 1.0, engine=eng)
+        ok_r = ok_r and np.array_equal(eng._np(mine), ref[:, :, k0:k1])
+        # prolong the (reference) coarse array back to the fine size, sharded
+        coarse_local = eng._t(ref[:, :, k0:k1])
+        up = D.slab_prolong3(coarse_local, n3, shape, rank, world, engine=eng)
+        ok_p = ok_p and np.array_equal(eng._np(up), refp[:, :, f0:f1])
     # query sharding: a shard of the batch evaluated alone equals that slice of the full batch
     co = O.make_coefs(A[:, :, :12], "nan", "cubic")
     X = 1.0 + O.synth(np.float64, 3 * 1000, seed=5).reshape(1000, 3) * (np.array([shape[0], shape[1], 12]) - 1.0)

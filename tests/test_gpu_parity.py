@@ -483,10 +483,11 @@ def test_generic_nd_kernel(gb, oracle, bc, order):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-@pytest.mark.parametrize("shape,world", [((9, 8, 20), 2), ((8, 9, 21), 3), ((12, 6, 64), 4), ((5, 7, 33), 8)])
+@pytest.mark.parametrize("shape,world", [((9, 8, 20), 2), ((8, 9, 21), 3), ((12, 6, 64), 4), ((5, 7, 33), 8), ((130, 21, 95), 3), ((66, 40, 128), 5)])
 def test_slab_kernels_assemble_to_unsharded(gb, oracle, dtype, shape, world):
-    """gb_restrict_slab / gb_prolong_slab: every rank's slab (own planes + halo, cut straight out of
-    the global array here instead of exchanged) reproduces its planes of the unsharded result."""
+    """gb_restrict_slab / gb_prolong_slab and the fused gb_restrict3_slab / gb_prolong3_slab: every rank's slab
+    (own planes + halo, cut straight out of the global array here instead of exchanged) reproduces its planes of the
+    unsharded result, odd and even plane offsets included."""
     import grid_jl_b200.dist as D
 
     eng = D.GpuEngine()
@@ -507,9 +508,22 @@ def test_slab_kernels_assemble_to_unsharded(gb, oracle, dtype, shape, world):
         p12 = eng.prolong_dims12(gb.jl_from_numpy(np.asfortranarray(ref[:, :, e0:e1])), shape[0], shape[1])
         up = eng.prolong_slab(p12, n3, L3, e0, k0, k1 - k0)
         assert same(gb.jl_to_numpy(up), refp[:, :, k0:k1])
+        # the fused slab operators (marching kernels with plane offsets) on the same slabs
+        e0, e1 = rplan.ext_range(r)
+        k0, k1 = rplan.out[r]
+        mine = eng.restrict3_slab(gb.jl_from_numpy(np.asfortranarray(A[:, :, e0:e1])), 1.0, L3, e0, k0, k1 - k0)
+        assert same(gb.jl_to_numpy(mine), ref[:, :, k0:k1])
+        e0, e1 = pplan.ext_range(r)
+        k0, k1 = pplan.out[r]
+        up = eng.prolong3_slab(gb.jl_from_numpy(np.asfortranarray(ref[:, :, e0:e1])), shape, n3, e0, k0, k1 - k0)
+        assert same(gb.jl_to_numpy(up), refp[:, :, k0:k1])
     # a slab that lacks a needed plane is refused
     with pytest.raises(gb.ErrorException):
         eng.restrict_slab(gb.jl_from_numpy(np.asfortranarray(A[:, :, 4:8])), 1.0, L3, 4, 1, 3)
+    with pytest.raises(gb.ErrorException):
+        eng.restrict3_slab(gb.jl_from_numpy(np.asfortranarray(A[:, :, 4:8])), 1.0, L3, 4, 1, 3)
+    with pytest.raises(gb.ErrorException):
+        eng.prolong3_slab(gb.jl_from_numpy(np.asfortranarray(ref[:, :, 2:4])), shape, n3, 2, 1, 6)
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
