@@ -400,7 +400,7 @@ template <typename T, int BY, int NW, int UN> __global__ void __launch_bounds__(
     const int nzo = min(zc, zout0 + ocount - j3);
     const int y0 = 2 * j2 - 2, z0 = 2 * j3 - 2;
     const bool ev1 = !(L1 & 1), ev2 = !(L2 & 1), ev3 = !(L3 & 1);
-    const bool vec = sizeof(T) == 8 && !(L1 & 1) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);  // rows 16-byte aligned
+    const bool vec = !(L1 & 1) && ((reinterpret_cast<uintptr_t>(A) & (sizeof(V) - 1)) == 0);  // rows aligned to a pair (16 B for f64, 8 B for f32)
     const int gx = j1 + 2 * lane;
     const bool xfull = j1 >= 1 && j1 + BX - 1 <= n1 - 2;  // warp-uniform: every output of the tile has all four taps
     const bool vx0 = gx < n1, vx1 = gx + 1 < n1;
@@ -421,11 +421,8 @@ template <typename T, int BY, int NW, int UN> __global__ void __launch_bounds__(
                     if (y < IY && gy >= 0 && gy < L2) {  // warp-uniform
                         const T* a = Ac + (ptrdiff_t)gy * (ptrdiff_t)L1;
                         if (vec && xfull) {
-                            if constexpr (sizeof(T) == 8) {
-                                const double2 q0 = __ldg(reinterpret_cast<const double2*>(a - 2)), q1 = __ldg(reinterpret_cast<const double2*>(a)),
-                                              q2 = __ldg(reinterpret_cast<const double2*>(a + 2));
-                                t[u][0] = q0.x; t[u][1] = q0.y; t[u][2] = q1.x; t[u][3] = q1.y; t[u][4] = q2.x; t[u][5] = q2.y;
-                            }
+                            const V q0 = *reinterpret_cast<const V*>(a - 2), q1 = *reinterpret_cast<const V*>(a), q2 = *reinterpret_cast<const V*>(a + 2);
+                            t[u][0] = q0.x; t[u][1] = q0.y; t[u][2] = q1.x; t[u][3] = q1.y; t[u][4] = q2.x; t[u][5] = q2.y;
                         } else {
 #pragma unroll
                             for (int e = 0; e < 6; e++) t[u][e] = (T)0;
