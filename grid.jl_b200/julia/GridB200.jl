@@ -197,10 +197,24 @@ function restrict(A::Array{T,N}, dim::Integer, scale::Real = one(T)) where {T<:U
         dtcode(T), N, dims, A, dim - 1, Float64(scale), R, GB_HOST, C_NULL))
     R
 end
+# One column of flags that restricts every dimension of a 3-D array is ONE pass over the fine grid (gb_restrict3: the
+# intermediates are rounded as the three calls would round them, so the bits are the same).
+function restrict3(A::Array{T,3}, scale::Real = one(T)) where {T<:Union{Float32,Float64}}
+    R = Array{T,3}(undef, map(restrict_size, size(A))...); dims = Int64[size(A)...]
+    GC.@preserve A R dims check(ccall((:gb_restrict3, LIB), Cint, (Cint, Ptr{Int64}, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+        dtcode(T), dims, A, Float64(scale), R, GB_HOST, C_NULL))
+    R
+end
 function restrict(A::Array, flag::Union{Array{Bool},BitArray}, scale::Real = one(eltype(A)))     # mapdim, src/utilities.jl:7-20
     ndims(A) == size(flag, 1) || error("Boolean flag must have as many rows as dimensions of A")
-    for j = 1:size(flag, 2), i = 1:size(flag, 1)
-        flag[i, j] && (A = restrict(A, i, scale))
+    for j = 1:size(flag, 2)
+        if ndims(A) == 3 && eltype(A) <: Union{Float32,Float64} && all(flag[:, j])
+            A = restrict3(A, scale)
+        else
+            for i = 1:size(flag, 1)
+                flag[i, j] && (A = restrict(A, i, scale))
+            end
+        end
     end
     A
 end
@@ -210,10 +224,24 @@ function prolong(A::Array{T,N}, dim::Integer, len::Integer) where {T<:Union{Floa
         dtcode(T), N, dims, A, dim - 1, len, P, GB_HOST, C_NULL))
     P
 end
+# prolong(A, [s1,s2,s3]) of a 3-D array as one pass (gb_prolong3; dimensions whose target is not larger are kept)
+function prolong3(A::Array{T,3}, target::AbstractVector{<:Integer}) where {T<:Union{Float32,Float64}}
+    osz = Int64[target[i] > size(A, i) ? prolong_size(size(A, i), Int(target[i])) : size(A, i) for i = 1:3]
+    P = Array{T,3}(undef, osz...); dims = Int64[size(A)...]
+    GC.@preserve A P dims osz check(ccall((:gb_prolong3, LIB), Cint, (Cint, Ptr{Int64}, Ptr{Cvoid}, Ptr{Int64}, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+        dtcode(T), dims, A, osz, P, GB_HOST, C_NULL))
+    P
+end
 function prolong(A::Array, sz::Array{Int})
     ndims(A) == size(sz, 1) || error("Array of sizes must have as many rows as dimensions of A")
-    for j = 1:size(sz, 2), i = 1:size(sz, 1)
-        sz[i, j] > size(A, i) && (A = prolong(A, i, sz[i, j]))
+    for j = 1:size(sz, 2)
+        if ndims(A) == 3 && eltype(A) <: Union{Float32,Float64}
+            A = prolong3(A, sz[:, j])
+        else
+            for i = 1:size(sz, 1)
+                sz[i, j] > size(A, i) && (A = prolong(A, i, sz[i, j]))
+            end
+        end
     end
     A
 end
