@@ -56,6 +56,8 @@ SIGNATURES = {
     "gb_prolongb": (i32, [i32, i32, p_i64, vp, i32, i64, vp, i32, vp]),
     "gb_restrict_slab": (i32, [i32, i32, p_i64, vp, i32, f64, i64, i64, i64, i64, vp, i32, vp]),
     "gb_prolong_slab": (i32, [i32, i32, p_i64, vp, i32, i64, i64, i64, i64, i64, vp, i32, vp]),
+    "gb_restrict12": (i32, [i32, i32, p_i64, vp, f64, vp, i32, vp]),
+    "gb_prolong12": (i32, [i32, i32, p_i64, vp, i64, i64, vp, i32, vp]),
     "gb_restrict3_slab": (i32, [i32, p_i64, vp, f64, i64, i64, i64, i64, vp, i32, vp]),
     "gb_prolong3_slab": (i32, [i32, p_i64, vp, p_i64, i64, i64, i64, i64, vp, i32, vp]),
     "gb_restrict3": (i32, [i32, p_i64, vp, f64, vp, i32, vp]),

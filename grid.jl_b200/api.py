@@ -970,8 +970,8 @@ def _prolong_dim(a, dim, length):
 def restrict(A, dim_or_flag, scale=1.0, fused=True):
     """restrict(A, dim[, scale]) (1-based dim) or restrict(A, flags[, scale]) via mapdim (:103-185).
 
-    With `fused` a column of flags that is all-true on a 3-D array runs as one pass (gb_restrict3),
-    bit-identical to the three staged passes."""
+    With `fused` a column of flags that is all-true on a 3-D array runs as one pass (gb_restrict3), and one that
+    restricts dims 1 and 2 of a 2-D / 3-D array as one pass (gb_restrict12), bit-identical to the staged passes."""
     a = _Arr(A, name="A")
     if np.ndim(dim_or_flag) == 0 and not isinstance(dim_or_flag, (bool, np.bool_)):
         dim = int(dim_or_flag)
@@ -987,6 +987,14 @@ def restrict(A, dim_or_flag, scale=1.0, fused=True):
             out = cur.empty_like_shape(shp)
             o = _Arr(out, name="out")
             L.check(lib.gb_restrict3(cur.dtype, _i64s(cur.shape), cur.ptr, float(scale), o.ptr, cur.mem, cur.stream()))
+            cur = o
+            continue
+        if fused and cur.ndim in (2, 3) and flag[0, j] and flag[1, j] and min(cur.shape[:2]) >= 2:
+            # dims 1 and 2 in one pass (gb_restrict12: 2-D arrays, or every plane of a 3-D array)
+            shp = [restrict_size(cur.shape[0]), restrict_size(cur.shape[1])] + list(cur.shape[2:])
+            out = cur.empty_like_shape(shp)
+            o = _Arr(out, name="out")
+            L.check(lib.gb_restrict12(cur.dtype, cur.ndim, _i64s(cur.shape), cur.ptr, float(scale), o.ptr, cur.mem, cur.stream()))
             cur = o
             continue
         for i in range(flag.shape[0]):
@@ -1021,6 +1029,13 @@ def prolong(A, *args, fused=True):
             out = cur.empty_like_shape(shp)
             o = _Arr(out, name="out")
             L.check(lib.gb_prolong3(cur.dtype, _i64s(cur.shape), cur.ptr, _i64s(shp), o.ptr, cur.mem, cur.stream()))
+            cur = o
+            continue
+        if fused and cur.ndim == 2 and all(grow):  # both dimensions of a 2-D array in one pass (gb_prolong12)
+            m1, m2 = prolong_size(cur.shape[0], int(sz[0, j])), prolong_size(cur.shape[1], int(sz[1, j]))
+            out = cur.empty_like_shape([m1, m2])
+            o = _Arr(out, name="out")
+            L.check(lib.gb_prolong12(cur.dtype, 2, _i64s(cur.shape), cur.ptr, m1, m2, o.ptr, cur.mem, cur.stream()))
             cur = o
             continue
         for i in range(cur.ndim):

@@ -1166,4 +1166,39 @@ int gb_prolong3(int dtype, const int64_t* dims, const void* in, const int64_t* o
     }, &ctx);
 }
 
+// restrict / prolong along dims 1 and 2 of a 2-D array, or of every plane of a 3-D array, in one pass (the marching
+// kernels without their dim-3 stage); same bits as gb_restrict / gb_prolong applied to dim 0, then dim 1
+int gb_restrict12(int dtype, int ndim, const int64_t* dims, const void* in, double scale, void* out, int mem, void* stream) {
+    if (!ok_dtype(dtype) || !dims || !in || !out || ndim < 2 || ndim > 3) return fail(GB_ERR_ARG, "bad arguments");
+    for (int d = 0; d < ndim; d++)
+        if (dims[d] < 1) return fail(GB_ERR_ARG, "bad dims");
+    const i64 nz = ndim == 3 ? dims[2] : 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    pool_keep_memory();
+    if (mem == GB_DEVICE) return restrict12_device(dtype, dims[0], dims[1], nz, in, scale, out, s);
+    struct Ctx { int dtype; i64 L1, L2, nz; double scale; } ctx{dtype, dims[0], dims[1], nz, scale};
+    return mg_host(dtype, dims[0] * dims[1] * nz, gb_restrict_size(dims[0]) * gb_restrict_size(dims[1]) * nz, in, out, s,
+                   [](void* c, const void* i, void* o, cudaStream_t st) {
+                       Ctx* x = (Ctx*)c;
+                       return restrict12_device(x->dtype, x->L1, x->L2, x->nz, i, x->scale, o, st);
+                   }, &ctx);
+}
+int gb_prolong12(int dtype, int ndim, const int64_t* dims, const void* in, int64_t m1, int64_t m2, void* out, int mem, void* stream) {
+    if (!ok_dtype(dtype) || !dims || !in || !out || ndim < 2 || ndim > 3) return fail(GB_ERR_ARG, "bad arguments");
+    for (int d = 0; d < ndim; d++)
+        if (dims[d] < 1) return fail(GB_ERR_ARG, "bad dims");
+    int rc = gb_prolong_size(dims[0], m1, nullptr);
+    if (!rc) rc = gb_prolong_size(dims[1], m2, nullptr);
+    if (rc) return rc;
+    const i64 nz = ndim == 3 ? dims[2] : 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    pool_keep_memory();
+    if (mem == GB_DEVICE) return prolong12_device(dtype, dims[0], dims[1], nz, in, m1, m2, out, s);
+    struct Ctx { int dtype; i64 n1, n2, nz, m1, m2; } ctx{dtype, dims[0], dims[1], nz, m1, m2};
+    return mg_host(dtype, dims[0] * dims[1] * nz, m1 * m2 * nz, in, out, s, [](void* c, const void* i, void* o, cudaStream_t st) {
+        Ctx* x = (Ctx*)c;
+        return prolong12_device(x->dtype, x->n1, x->n2, x->nz, i, x->m1, x->m2, o, st);
+    }, &ctx);
+}
+
 }  // extern "C"

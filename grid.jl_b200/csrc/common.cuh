@@ -158,6 +158,8 @@ int prolong_slab_device(int dtype, int ndim, const i64* dims, const void* in, in
 int restrict3_device(int dtype, const i64* dims, const void* in, double scale, void* out, cudaStream_t s);
 int prolong3_device(int dtype, const i64* dims, const void* in, const i64* odims, void* out, cudaStream_t s);
 
+int restrict12_device(int dtype, i64 L1, i64 L2, i64 nz, const void* in, double scale, void* out, cudaStream_t s);
+int prolong12_device(int dtype, i64 n1, i64 n2, i64 nz, const void* in, i64 m1, i64 m2, void* out, cudaStream_t s);
 int restrict3_slab_device(int dtype, const i64* dims, const void* in, double scale, i64 L3, i64 in_first, i64 out_first, i64 ocount, void* out, cudaStream_t s);
 int prolong3_slab_device(int dtype, const i64* dims, const void* in, const i64* m, i64 n3, i64 in_first, i64 out_first, i64 ocount, void* out, cudaStream_t s);
 int irregular_device(int dtype, const void* knots, const void* coefs, i64 n, int bc, int it, double fill, const void* x, void* out, i64 nq, u64* first_invalid,

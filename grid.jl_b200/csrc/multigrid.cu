@@ -385,11 +385,12 @@ template <typename T> __device__ __forceinline__ T restrict_full(bool even, T am
 }
 // A lane owns outputs x = 2*lane, 2*lane+1 of the 64-wide tile: their eight taps are six consecutive inputs (three
 // aligned 16-byte loads), and shared memory moves pairs (one column per lane: 2.94 instead of 2.63 ms per chain).
-template <typename T, int BY, int NW, int UN> __global__ void __launch_bounds__(32 * NW) restrict3_march_kernel(const T* __restrict__ A, T* __restrict__ R, int L1, int L2, int L3, int n1,
+template <typename T, int BY, int NW, int UN, bool DO3> __global__ void __launch_bounds__(32 * NW) restrict3_march_kernel(const T* __restrict__ A, T* __restrict__ R, int L1, int L2, int L3, int n1,
                                                                                                         int n2, int n3, int zc, RCoef<T> c, int zin0, int nzin,
                                                                                                         int zout0, int ocount) {
     // slab form: A holds input planes [zin0, zin0 + nzin) of the L3 global ones, R output planes [zout0, zout0 + ocount)
-    // of the n3 global ones (whole array: 0, L3, 0, n3); plane indices below are global
+    // of the n3 global ones (whole array: 0, L3, 0, n3); plane indices below are global.
+    // DO3 == false: dims 1 and 2 only (2-D arrays, restrict(A, [true,true,false])): plane gz of R comes from plane gz of A.
     constexpr int HX = 32, BX = 64, IY = 2 * BY + 2;
     using V = Pair<T>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -398,7 +399,7 @@ template <typename T, int BY, int NW, int UN> __global__ void __launch_bounds__(
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j1 = blockIdx.x * BX, j2 = blockIdx.y * BY, j3 = zout0 + blockIdx.z * zc;
     const int nzo = min(zc, zout0 + ocount - j3);
-    const int y0 = 2 * j2 - 2, z0 = 2 * j3 - 2;
+    const int y0 = 2 * j2 - 2, z0 = DO3 ? 2 * j3 - 2 : j3;
     const bool ev1 = !(L1 & 1), ev2 = !(L2 & 1), ev3 = !(L3 & 1);
     const bool vec = !(L1 & 1) && ((reinterpret_cast<uintptr_t>(A) & (sizeof(V) - 1)) == 0);  // rows aligned to a pair (16 B for f64, 8 B for f32)
     const int gx = j1 + 2 * lane;
@@ -406,7 +407,7 @@ template <typename T, int BY, int NW, int UN> __global__ void __launch_bounds__(
     const bool vx0 = gx < n1, vx1 = gx + 1 < n1;
     const bool lo0 = vx0 && gx >= 1, hi0 = vx0 && gx <= n1 - 2, lo1 = vx1, hi1 = vx1 && gx + 1 <= n1 - 2;
     const size_t plane = (size_t)L2 * (size_t)L1;
-    for (int p = 0; p < 2 * nzo + 2; p++) {
+    for (int p = 0; p < (DO3 ? 2 * nzo + 2 : nzo); p++) {
         const int gz = z0 + p;
         const bool zok = gz >= zin0 && gz < zin0 + nzin;  // (planes a needed tap lies on are present: checked by the host)
         // ---- stage A: dim-1 restriction; inputs t[0..5] = A[2gx-2 .. 2gx+3]
@@ -472,10 +473,16 @@ template <typename T, int BY, int NW, int UN> __global__ void __launch_bounds__(
                         v.y = restrict_at<T>(ev2, b0.y, b1.y, b2.y, b3.y, gy >= 1, gy <= n2 - 2, c);
                     }
                 }
-                dst[y * HX] = v;
+                if constexpr (DO3) dst[y * HX] = v;
+                else if (gy < n2 && vx0) {  // dims 1, 2 only: this is the result
+                    T* r = R + ((size_t)(gz - zout0) * (size_t)n2 + gy) * (size_t)n1 + gx;
+                    r[0] = v.x;
+                    if (vx1) r[1] = v.y;
+                }
             }
         }
         __syncthreads();
+        if constexpr (!DO3) continue;
         // ---- stage C: input planes p-3 .. p are the taps of output plane (p-3)/2 of this chunk
         if (p >= 3 && (p & 1) && vx0) {
             const int gzo = j3 + ((p - 3) >> 1);
@@ -507,11 +514,11 @@ template <typename T, int BY, int NW, int UN> __global__ void __launch_bounds__(
         }
     }
 }
-template <typename T, int BY, int NW, int UN>
+template <typename T, int BY, int NW, int UN, bool DO3 = true>
 int restrict3_march_launch(const T* in, T* out, i64 L1, i64 L2, i64 L3, i64 n1, i64 n2, i64 n3, double scale, i64 zin0, i64 nzin, i64 zout0, i64 ocount, cudaStream_t s) {
     constexpr int BX = 64, IY = 2 * BY + 2;
     const size_t smem = sizeof(T) * (size_t)(IY * BX + 4 * BY * BX);
-    auto kern = restrict3_march_kernel<T, BY, NW, UN>;
+    auto kern = restrict3_march_kernel<T, BY, NW, UN, DO3>;
     GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const i64 gx = (n1 + BX - 1) / BX, gy = (n2 + BY - 1) / BY;
     i64 zc = 32;
@@ -548,6 +555,15 @@ template <typename T> int restrict3_impl(const i64* dims, const T* in, double sc
     // 1024 -> 17 chain (2.63 ms; 64 x 4 / 4 warps 2.69, 64 x 8 / 4 warps 2.75-2.81, / 8 warps 2.77, 64 x 6 2.77, 64 x 4 / 8
     // warps 3.68; one column per lane: 32 x 8 / 2 warps 2.96, 128 x 8 / 8 warps 3.5-3.9; the (32,4,4) brick kernel 3.59)
     return restrict3_march_launch<T, 4, 5, 2>(in, out, L1, L2, L3, n1, n2, n3, scale, 0, L3, 0, n3, s);
+}
+
+// restrict along dims 1 and 2 only, fused: 2-D arrays (nz = 1) and restrict(A, [true,true,false]) on 3-D arrays
+template <typename T> int restrict12_impl(i64 L1, i64 L2, i64 nz, const T* in, double scale, T* out, cudaStream_t s) {
+    const i64 n1 = rsize(L1), n2 = rsize(L2);
+    if (L1 < 2 || L2 < 2) return fail(GB_ERR_UNSUPPORTED, "fused 2-D restrict: extents below 2 (use gb_restrict per dimension)");
+    if (L1 >= (1ll << 30) || L2 >= (1ll << 30) || nz >= (1ll << 30)) return fail(GB_ERR_UNSUPPORTED, "restrict: extent too large");
+    if (nz == 0) return GB_OK;
+    return restrict3_march_launch<T, 4, 5, 2, false>(in, out, L1, L2, nz, n1, n2, nz, scale, 0, nz, 0, nz, s);
 }
 
 // restrict(A, [true,true,true], scale) on ONE SLAB of a 3-D array sharded along dim 3: `in` holds input planes
@@ -666,7 +682,7 @@ template <typename T, int BY, int BZ> __global__ void __launch_bounds__(256) pro
 // slots S2[2][BY][64] (stage B); two consecutive slots then give two output planes (stage C, coalesced 512-byte
 // rows).  A lane owns the output pair x = 2*lane, 2*lane+1 for the whole kernel: both come from the same two
 // inputs, the parities are compile-time, and shared memory and (for even row lengths) global stores move pairs.  Same prolong_at calls in the same order as the brick kernel, hence the same bits.
-template <typename T, int BY, int NW> __global__ void __launch_bounds__(32 * NW) prolong3_march_kernel(const T* __restrict__ A, T* __restrict__ P, int n1, int n2, int n3, int m1, int m2,
+template <typename T, int BY, int NW, bool DO3> __global__ void __launch_bounds__(32 * NW) prolong3_march_kernel(const T* __restrict__ A, T* __restrict__ P, int n1, int n2, int n3, int m1, int m2,
                                                                                                int m3, int zc, int zin0, int nzin, int zout0, int ocount) {
     // slab form: A holds input planes [zin0, zin0 + nzin) (of the n3 global ones), P output planes [zout0, zout0 + ocount) of the
     // m3 global ones (whole array: 0, 0, m3); plane indices below are global
@@ -676,15 +692,15 @@ template <typename T, int BY, int NW> __global__ void __launch_bounds__(32 * NW)
     V* S1 = reinterpret_cast<V*>(smem_raw);  // [NY][HX]
     V* S2 = S1 + NY * HX;                     // [2][BY][HX]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int k1 = blockIdx.x * BX, k2 = blockIdx.y * BY, k3 = (zout0 & ~1) + blockIdx.z * zc;  // BX, BY, zc and k3 are even
-    const int y0 = k2 >> 1, z0 = k3 >> 1;
+    const int k1 = blockIdx.x * BX, k2 = blockIdx.y * BY, k3 = (DO3 ? (zout0 & ~1) : zout0) + blockIdx.z * zc;  // BX, BY, zc (and k3 when DO3) are even
+    const int y0 = k2 >> 1, z0 = DO3 ? k3 >> 1 : k3;  // DO3 == false: dims 1 and 2 only, plane gz of P comes from plane gz of A
     const bool ev1 = !(m1 & 1), ev2 = !(m2 & 1), ev3 = !(m3 & 1);
     const int gx = k1 + 2 * lane, xi = gx >> 1;
     const bool xv0 = gx < m1, xv1 = gx + 1 < m1, xh = xv0 && xi + 1 < n1;
     const bool vst = xv1 && !(m1 & 1) && ((reinterpret_cast<uintptr_t>(P) & (2 * sizeof(T) - 1)) == 0);  // aligned pair stores
     const int nplanes = min(zc, zout0 + ocount - k3);  // output planes of this chunk (those below zout0 are skipped)
     const size_t iplane = (size_t)n2 * (size_t)n1, oplane = (size_t)m2 * (size_t)m1;
-    for (int ip = 0; 2 * (ip - 1) < nplanes; ip++) {
+    for (int ip = 0; DO3 ? 2 * (ip - 1) < nplanes : ip < nplanes; ip++) {
         const int lz = z0 + ip;
         const bool zin = lz < n3 && lz < zin0 + nzin;  // (planes a needed tap lies on are present: checked by the host)
         // ---- stage A: dim-1 prolongation of input plane lz, rows y0 .. y0+NY-1
@@ -717,10 +733,19 @@ template <typename T, int BY, int NW> __global__ void __launch_bounds__(32 * NW)
                     v.x = prolong_at<T>(ev2, gy & 1, b0.x, b1.x);
                     v.y = prolong_at<T>(ev2, gy & 1, b0.y, b1.y);
                 }
-                dst[y * HX] = v;
+                if constexpr (DO3) dst[y * HX] = v;
+                else if (gy < m2 && xv0) {  // dims 1, 2 only: this is the result
+                    T* p = P + ((size_t)(lz - zout0) * (size_t)m2 + gy) * (size_t)m1 + gx;
+                    if (vst) *reinterpret_cast<V*>(p) = v;
+                    else {
+                        p[0] = v.x;
+                        if (xv1) p[1] = v.y;
+                    }
+                }
             }
         }
         __syncthreads();
+        if constexpr (!DO3) continue;
         // ---- stage C: output planes 2(lz-1), 2(lz-1)+1 from slots (ip-1) & 1 (plane lz-1) and ip & 1 (plane lz)
         if (ip >= 1 && xv0) {
             const V* s0 = S2 + (((ip - 1) & 1) * BY) * HX + lane;
@@ -752,14 +777,14 @@ template <typename T, int BY, int NW> __global__ void __launch_bounds__(32 * NW)
         }
     }
 }
-template <typename T, int BY, int NW> int prolong3_march_launch(const T* in, T* out, i64 n1, i64 n2, i64 n3, const i64* m, i64 zin0, i64 nzin, i64 zout0, i64 ocount, cudaStream_t s) {
+template <typename T, int BY, int NW, bool DO3 = true> int prolong3_march_launch(const T* in, T* out, i64 n1, i64 n2, i64 n3, const i64* m, i64 zin0, i64 nzin, i64 zout0, i64 ocount, cudaStream_t s) {
     constexpr int BX = 64, NY = BY / 2 + 1;
     const size_t smem = sizeof(T) * (size_t)(NY * BX + 2 * BY * BX);
-    auto kern = prolong3_march_kernel<T, BY, NW>;
+    auto kern = prolong3_march_kernel<T, BY, NW, DO3>;
     GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const i64 gx = (m[0] + BX - 1) / BX, gy = (m[1] + BY - 1) / BY;
     i64 zc = 64;  // output planes per chunk (even): one extra input plane per chunk
-    const i64 span = zout0 + ocount - (zout0 & ~(i64)1);  // planes from the even chunk origin
+    const i64 span = DO3 ? zout0 + ocount - (zout0 & ~(i64)1) : ocount;  // planes from the (even) chunk origin
     while (zc > 8 && gx * gy * ((span + zc - 1) / zc) < (i64)num_sms() * 4 * 4) zc /= 2;
     dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)((span + zc - 1) / zc));
     kern<<<grid, 32 * NW, smem, s>>>(in, out, (int)n1, (int)n2, (int)n3, (int)m[0], (int)m[1], (int)m[2], (int)zc, (int)zin0, (int)nzin, (int)zout0, (int)ocount);
@@ -800,6 +825,20 @@ template <typename T> int prolong3_impl(const i64* dims, const T* in, const i64*
     count_launch();
     GB_CUDA(cudaGetLastError());
     return GB_OK;
+}
+
+// prolong along dims 1 and 2 only, fused: 2-D arrays (nz = 1) and prolong(A, [m1,m2,n3]) on 3-D arrays
+template <typename T> int prolong12_impl(i64 n1, i64 n2, i64 nz, const T* in, i64 m1, i64 m2, T* out, cudaStream_t s) {
+    const i64 nn[2] = {n1, n2}, mm[2] = {m1, m2};
+    for (int d = 0; d < 2; d++) {
+        const i64 newsz = (mm[d] & 1) ? 2 * nn[d] - 1 : 2 * (nn[d] - 1);
+        if (newsz != mm[d]) return fail(GB_ERR_PROLONG_SIZE, "Cannot prolong a dimension of length " + std::to_string(nn[d]) + " to " + std::to_string(mm[d]));
+        if (mm[d] <= nn[d]) return fail(GB_ERR_UNSUPPORTED, "fused 2-D prolong: both dimensions must grow (use gb_prolong per dimension)");
+        if (mm[d] >= (1ll << 30)) return fail(GB_ERR_UNSUPPORTED, "prolong: extent too large");
+    }
+    if (nz == 0 || nz >= (1ll << 30)) return nz == 0 ? GB_OK : fail(GB_ERR_UNSUPPORTED, "prolong: extent too large");
+    const i64 m[3] = {m1, m2, nz};
+    return prolong3_march_launch<T, 8, 4, false>(in, out, n1, n2, nz, m, 0, nz, 0, nz, s);
 }
 
 // prolong(A, [m1,m2,m3]) (every dimension prolonged) on ONE SLAB of a 3-D array sharded along dim 3: `in` holds coarse
@@ -934,6 +973,16 @@ int restrict_slab_device(int dtype, int ndim, const i64* dims, const void* in, i
                          cudaStream_t s) {
     if (dtype == GB_F64) return restrict_slab_impl<double>(ndim, dims, (const double*)in, dim, scale, L, in_first, out_first, ocount, (double*)out, s);
     if (dtype == GB_F32) return restrict_slab_impl<float>(ndim, dims, (const float*)in, dim, scale, L, in_first, out_first, ocount, (float*)out, s);
+    return fail(GB_ERR_ARG, "bad dtype");
+}
+int restrict12_device(int dtype, i64 L1, i64 L2, i64 nz, const void* in, double scale, void* out, cudaStream_t s) {
+    if (dtype == GB_F64) return restrict12_impl<double>(L1, L2, nz, (const double*)in, scale, (double*)out, s);
+    if (dtype == GB_F32) return restrict12_impl<float>(L1, L2, nz, (const float*)in, scale, (float*)out, s);
+    return fail(GB_ERR_ARG, "bad dtype");
+}
+int prolong12_device(int dtype, i64 n1, i64 n2, i64 nz, const void* in, i64 m1, i64 m2, void* out, cudaStream_t s) {
+    if (dtype == GB_F64) return prolong12_impl<double>(n1, n2, nz, (const double*)in, m1, m2, (double*)out, s);
+    if (dtype == GB_F32) return prolong12_impl<float>(n1, n2, nz, (const float*)in, m1, m2, (float*)out, s);
     return fail(GB_ERR_ARG, "bad dtype");
 }
 int restrict3_slab_device(int dtype, const i64* dims, const void* in, double scale, i64 L3, i64 in_first, i64 out_first, i64 ocount, void* out, cudaStream_t s) {

@@ -205,11 +205,19 @@ function restrict3(A::Array{T,3}, scale::Real = one(T)) where {T<:Union{Float32,
         dtcode(T), dims, A, Float64(scale), R, GB_HOST, C_NULL))
     R
 end
+function restrict12(A::Array{T,2}, scale::Real = one(T)) where {T<:Union{Float32,Float64}}
+    R = Array{T,2}(undef, map(restrict_size, size(A))...); dims = Int64[size(A)...]
+    GC.@preserve A R dims check(ccall((:gb_restrict12, LIB), Cint, (Cint, Cint, Ptr{Int64}, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+        dtcode(T), 2, dims, A, Float64(scale), R, GB_HOST, C_NULL))
+    R
+end
 function restrict(A::Array, flag::Union{Array{Bool},BitArray}, scale::Real = one(eltype(A)))     # mapdim, src/utilities.jl:7-20
     ndims(A) == size(flag, 1) || error("Boolean flag must have as many rows as dimensions of A")
     for j = 1:size(flag, 2)
         if ndims(A) == 3 && eltype(A) <: Union{Float32,Float64} && all(flag[:, j])
             A = restrict3(A, scale)
+        elseif ndims(A) == 2 && eltype(A) <: Union{Float32,Float64} && all(flag[:, j]) && minimum(size(A)) >= 2
+            A = restrict12(A, scale)         # image pyramids: both dimensions in one pass (gb_restrict12)
         else
             for i = 1:size(flag, 1)
                 flag[i, j] && (A = restrict(A, i, scale))
@@ -232,11 +240,19 @@ function prolong3(A::Array{T,3}, target::AbstractVector{<:Integer}) where {T<:Un
         dtcode(T), dims, A, osz, P, GB_HOST, C_NULL))
     P
 end
+function prolong12(A::Array{T,2}, m1::Integer, m2::Integer) where {T<:Union{Float32,Float64}}
+    P = Array{T,2}(undef, prolong_size(size(A, 1), Int(m1)), prolong_size(size(A, 2), Int(m2))); dims = Int64[size(A)...]
+    GC.@preserve A P dims check(ccall((:gb_prolong12, LIB), Cint, (Cint, Cint, Ptr{Int64}, Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+        dtcode(T), 2, dims, A, Int64(m1), Int64(m2), P, GB_HOST, C_NULL))
+    P
+end
 function prolong(A::Array, sz::Array{Int})
     ndims(A) == size(sz, 1) || error("Array of sizes must have as many rows as dimensions of A")
     for j = 1:size(sz, 2)
         if ndims(A) == 3 && eltype(A) <: Union{Float32,Float64}
             A = prolong3(A, sz[:, j])
+        elseif ndims(A) == 2 && eltype(A) <: Union{Float32,Float64} && sz[1, j] > size(A, 1) && sz[2, j] > size(A, 2)
+            A = prolong12(A, sz[1, j], sz[2, j])
         else
             for i = 1:size(sz, 1)
                 sz[i, j] > size(A, i) && (A = prolong(A, i, sz[i, j]))

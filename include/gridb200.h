@@ -213,6 +213,14 @@ int gb_restrict3(int dtype, const int64_t* dims, const void* in, double scale, v
 int gb_prolong3(int dtype, const int64_t* dims, const void* in, const int64_t* out_dims, void* out, int mem,
                 void* stream);
 
+/* restrict / prolong along dims 1 and 2 in ONE pass: a 2-D array (ndim = 2: restrict(A, [true,true], scale),
+ * prolong(A, [m1,m2]) -- image pyramids), or every plane of a 3-D array (ndim = 3: flags [true,true,false]).  Same bits
+ * as the per-dimension calls.  Extents below 2 (restrict) or a dimension that does not grow (prolong): GB_ERR_UNSUPPORTED,
+ * use the per-dimension calls. */
+int gb_restrict12(int dtype, int ndim, const int64_t* dims, const void* in, double scale, void* out, int mem, void* stream);
+int gb_prolong12(int dtype, int ndim, const int64_t* dims, const void* in, int64_t m1, int64_t m2, void* out, int mem,
+                 void* stream);
+
 /* ---- device / pinned memory helpers (device-resident query and output buffers) -------------- */
 int gb_device_alloc(void** ptr, size_t bytes);
 int gb_device_free(void* ptr);

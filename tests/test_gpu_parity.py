@@ -254,6 +254,31 @@ def test_fused_3d_equals_staged(gb, oracle, dtype, shape):
             assert same(gb.prolong(A, tgt, fused=False), refp)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", [(9, 9), (8, 8), (130, 21), (259, 40), (256, 41), (2, 2), (3, 2), (64, 64), (127, 6), (70, 9, 5), (65, 34, 3), (8, 8, 1)])
+def test_fused_dims12_equals_staged(gb, oracle, dtype, shape):
+    """gb_restrict12 / gb_prolong12 (the marching kernels without their dim-3 stage: 2-D arrays -- image pyramids -- and
+    flags [true,true,false] on 3-D arrays) are bit-identical to the per-dimension reference, host and device arrays."""
+    rng = np.random.default_rng(sum(shape) + 1)
+    A = rng.standard_normal(shape).astype(dtype)
+    flags = [True, True] + [False] * (len(shape) - 2)
+    for scale in (1.0, 0.7):
+        ref = oracle.restrict_flags(A, flags, scale)
+        assert same(gb.restrict(A, flags, scale), ref)
+        assert same(gb.restrict(A, flags, scale, fused=False), ref)
+    assert same(gb.jl_to_numpy(gb.restrict(gb.jl_from_numpy(A), flags)), oracle.restrict_flags(A, flags, 1.0))
+    if len(shape) == 2:
+        for tgt in ([2 * s - 1 for s in shape], [2 * (s - 1) for s in shape], [2 * shape[0] - 1, 2 * (shape[1] - 1)]):
+            if min(tgt) < 1 or min(shape) < 2:
+                continue
+            refp = oracle.prolong_sizes(A, tgt)
+            assert same(gb.prolong(A, tgt), refp)
+            assert same(gb.prolong(A, tgt, fused=False), refp)
+            assert same(gb.jl_to_numpy(gb.prolong(gb.jl_from_numpy(A), tgt)), refp)
+        with pytest.raises(gb.ErrorException):
+            gb.prolong(A, [2 * shape[0] + 1, 2 * shape[1] - 1])
+
+
 def test_restrict_prolong_chain_roundtrip(gb, oracle):
     """C5 in miniature: 66^3 -> 34 -> 18 -> 10 and back up the same size list."""
     rng = np.random.default_rng(0)
