@@ -1021,6 +1021,13 @@ def prolong(A, *args, fused=True):
     lib = L.lib()
     for j in range(sz.shape[1]):
         grow = [sz[i, j] > cur.shape[i] for i in range(cur.ndim)]
+        if fused and cur.ndim == 3 and grow == [True, True, False]:  # every plane in one pass (gb_prolong12)
+            m1, m2 = prolong_size(cur.shape[0], int(sz[0, j])), prolong_size(cur.shape[1], int(sz[1, j]))
+            out = cur.empty_like_shape([m1, m2, cur.shape[2]])
+            o = _Arr(out, name="out")
+            L.check(lib.gb_prolong12(cur.dtype, 3, _i64s(cur.shape), cur.ptr, m1, m2, o.ptr, cur.mem, cur.stream()))
+            cur = o
+            continue
         if fused and cur.ndim == 3 and sum(grow) >= 2:
             for i in range(3):
                 if grow[i]:

@@ -277,6 +277,11 @@ def test_fused_dims12_equals_staged(gb, oracle, dtype, shape):
             assert same(gb.jl_to_numpy(gb.prolong(gb.jl_from_numpy(A), tgt)), refp)
         with pytest.raises(gb.ErrorException):
             gb.prolong(A, [2 * shape[0] + 1, 2 * shape[1] - 1])
+    else:  # [m1, m2, n3]: every plane prolonged along dims 1 and 2
+        for tgt in ([2 * shape[0] - 1, 2 * shape[1] - 1, shape[2]], [2 * (shape[0] - 1), 2 * shape[1] - 1, shape[2]]):
+            refp = oracle.prolong_sizes(A, tgt)
+            assert same(gb.prolong(A, tgt), refp)
+            assert same(gb.prolong(A, tgt, fused=False), refp)
 
 
 def test_restrict_prolong_chain_roundtrip(gb, oracle):
