@@ -238,7 +238,10 @@ static bool wants_blocked(const gb_grid* g) {
 static int to_blocked_layout(gb_grid* g, cudaStream_t s) {
     void* fin = nullptr;
     const size_t bytes = (size_t)blocked_elems(g->ndim, g->stored_dims) * esize(g->dtype);
-    GB_CUDA(cudaMalloc(&fin, bytes));
+    if (cudaMalloc(&fin, bytes) != cudaSuccess) {  // no room for the second copy the conversion needs: stay column-major
+        cudaGetLastError();
+        return GB_OK;
+    }
     int rc = blocked_device(g->dtype, g->ndim, g->stored_dims, g->coefs, fin, 1, s);
     cudaError_t e = cudaStreamSynchronize(s);
     if (rc || e != cudaSuccess) { cudaFree(fin); return rc ? rc : cuda_fail(e, "cudaStreamSynchronize"); }
