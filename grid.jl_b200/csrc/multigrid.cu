@@ -387,7 +387,7 @@ template <typename T> __device__ __forceinline__ T restrict_full(bool even, T am
 // aligned 16-byte loads), and shared memory moves pairs (one column per lane: 2.94 instead of 2.63 ms per chain).
 template <typename T, int BY, int NW, int UN, bool DO3> __global__ void __launch_bounds__(32 * NW) restrict3_march_kernel(const T* __restrict__ A, T* __restrict__ R, int L1, int L2, int L3, int n1,
                                                                                                         int n2, int n3, int zc, RCoef<T> c, int zin0, int nzin,
-                                                                                                        int zout0, int ocount) {
+                                                                                                        int zout0, int ocount, int xtiles) {
     // slab form: A holds input planes [zin0, zin0 + nzin) of the L3 global ones, R output planes [zout0, zout0 + ocount)
     // of the n3 global ones (whole array: 0, L3, 0, n3); plane indices below are global.
     // DO3 == false: dims 1 and 2 only (2-D arrays, restrict(A, [true,true,false])): plane gz of R comes from plane gz of A.
@@ -397,7 +397,8 @@ template <typename T, int BY, int NW, int UN, bool DO3> __global__ void __launch
     V* S1 = reinterpret_cast<V*>(smem_raw);  // [IY][HX]
     V* S2 = S1 + IY * HX;                     // [4][BY][HX]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int j1 = blockIdx.x * BX, j2 = blockIdx.y * BY, j3 = zout0 + blockIdx.z * zc;
+    // (x, y) tiles are linearised in blockIdx.x (tall 2-D arrays have more row tiles than gridDim.y allows), plane chunks in blockIdx.y
+    const int j1 = (blockIdx.x % xtiles) * BX, j2 = (blockIdx.x / xtiles) * BY, j3 = zout0 + blockIdx.y * zc;
     const int nzo = min(zc, zout0 + ocount - j3);
     const int y0 = 2 * j2 - 2, z0 = DO3 ? 2 * j3 - 2 : j3;
     const bool ev1 = !(L1 & 1), ev2 = !(L2 & 1), ev3 = !(L3 & 1);
@@ -523,9 +524,11 @@ int restrict3_march_launch(const T* in, T* out, i64 L1, i64 L2, i64 L3, i64 n1, 
     const i64 gx = (n1 + BX - 1) / BX, gy = (n2 + BY - 1) / BY;
     i64 zc = 32;  // (16: 2.63, 32: 2.64, 64: 2.68, 128: 2.80, 256: 3.13 ms per chain)
     while (zc > 4 && gx * gy * ((ocount + zc - 1) / zc) < (i64)num_sms() * 4 * 4) zc /= 2;
-    dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)((ocount + zc - 1) / zc));
+    while ((ocount + zc - 1) / zc > 65535) zc *= 2;
+    if (gx * gy >= (1ll << 31)) return fail(GB_ERR_UNSUPPORTED, "restrict: too many tiles");
+    dim3 grid((unsigned)(gx * gy), (unsigned)((ocount + zc - 1) / zc), 1);
     kern<<<grid, 32 * NW, smem, s>>>(in, out, (int)L1, (int)L2, (int)L3, (int)n1, (int)n2, (int)n3, (int)zc, make_coef<T>(scale), (int)zin0, (int)nzin, (int)zout0,
-                                     (int)ocount);
+                                     (int)ocount, (int)gx);
     count_launch();
     GB_CUDA(cudaGetLastError());
     return GB_OK;
@@ -683,7 +686,7 @@ template <typename T, int BY, int BZ> __global__ void __launch_bounds__(256) pro
 // rows).  A lane owns the output pair x = 2*lane, 2*lane+1 for the whole kernel: both come from the same two
 // inputs, the parities are compile-time, and shared memory and (for even row lengths) global stores move pairs.  Same prolong_at calls in the same order as the brick kernel, hence the same bits.
 template <typename T, int BY, int NW, bool DO3> __global__ void __launch_bounds__(32 * NW) prolong3_march_kernel(const T* __restrict__ A, T* __restrict__ P, int n1, int n2, int n3, int m1, int m2,
-                                                                                               int m3, int zc, int zin0, int nzin, int zout0, int ocount) {
+                                                                                               int m3, int zc, int zin0, int nzin, int zout0, int ocount, int xtiles) {
     // slab form: A holds input planes [zin0, zin0 + nzin) (of the n3 global ones), P output planes [zout0, zout0 + ocount) of the
     // m3 global ones (whole array: 0, 0, m3); plane indices below are global
     constexpr int BX = 64, NY = BY / 2 + 1, HX = BX / 2;  // a lane owns the output pair x = 2*lane, 2*lane + 1 (input column `xi`)
@@ -692,7 +695,7 @@ template <typename T, int BY, int NW, bool DO3> __global__ void __launch_bounds_
     V* S1 = reinterpret_cast<V*>(smem_raw);  // [NY][HX]
     V* S2 = S1 + NY * HX;                     // [2][BY][HX]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int k1 = blockIdx.x * BX, k2 = blockIdx.y * BY, k3 = (DO3 ? (zout0 & ~1) : zout0) + blockIdx.z * zc;  // BX, BY, zc (and k3 when DO3) are even
+    const int k1 = (blockIdx.x % xtiles) * BX, k2 = (blockIdx.x / xtiles) * BY, k3 = (DO3 ? (zout0 & ~1) : zout0) + blockIdx.y * zc;  // BX, BY, zc (and k3 when DO3) are even
     const int y0 = k2 >> 1, z0 = DO3 ? k3 >> 1 : k3;  // DO3 == false: dims 1 and 2 only, plane gz of P comes from plane gz of A
     const bool ev1 = !(m1 & 1), ev2 = !(m2 & 1), ev3 = !(m3 & 1);
     const int gx = k1 + 2 * lane, xi = gx >> 1;
@@ -786,8 +789,11 @@ template <typename T, int BY, int NW, bool DO3 = true> int prolong3_march_launch
     i64 zc = 32;  // output planes per chunk (even): one extra input plane per chunk (16: 2.31, 32: 2.29, 64: 2.34, 128: 2.36, 256: 2.42 ms per chain)
     const i64 span = DO3 ? zout0 + ocount - (zout0 & ~(i64)1) : ocount;  // planes from the (even) chunk origin
     while (zc > 8 && gx * gy * ((span + zc - 1) / zc) < (i64)num_sms() * 4 * 4) zc /= 2;
-    dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)((span + zc - 1) / zc));
-    kern<<<grid, 32 * NW, smem, s>>>(in, out, (int)n1, (int)n2, (int)n3, (int)m[0], (int)m[1], (int)m[2], (int)zc, (int)zin0, (int)nzin, (int)zout0, (int)ocount);
+    while ((span + zc - 1) / zc > 65535) zc *= 2;
+    if (gx * gy >= (1ll << 31)) return fail(GB_ERR_UNSUPPORTED, "prolong: too many tiles");
+    dim3 grid((unsigned)(gx * gy), (unsigned)((span + zc - 1) / zc), 1);
+    kern<<<grid, 32 * NW, smem, s>>>(in, out, (int)n1, (int)n2, (int)n3, (int)m[0], (int)m[1], (int)m[2], (int)zc, (int)zin0, (int)nzin, (int)zout0, (int)ocount,
+                                     (int)gx);
     count_launch();
     GB_CUDA(cudaGetLastError());
     return GB_OK;

@@ -255,7 +255,8 @@ def test_fused_3d_equals_staged(gb, oracle, dtype, shape):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-@pytest.mark.parametrize("shape", [(9, 9), (8, 8), (130, 21), (259, 40), (256, 41), (2, 2), (3, 2), (64, 64), (127, 6), (70, 9, 5), (65, 34, 3), (8, 8, 1)])
+@pytest.mark.parametrize("shape", [(9, 9), (8, 8), (130, 21), (259, 40), (256, 41), (2, 2), (3, 2), (64, 64), (127, 6), (70, 9, 5), (65, 34, 3), (8, 8, 1),
+                                   (4, 600001), (3, 300000)])  # (tall arrays: more row tiles than gridDim.y allows)
 def test_fused_dims12_equals_staged(gb, oracle, dtype, shape):
     """gb_restrict12 / gb_prolong12 (the marching kernels without their dim-3 stage: 2-D arrays -- image pyramids -- and
     flags [true,true,false] on 3-D arrays) are bit-identical to the per-dimension reference, host and device arrays."""
