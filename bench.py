@@ -1,24 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- Gpoints/s of InterpGrid valgrad on B200 (BASELINE.json metric), one JSON line.
 
-Workload (config.workload = "C2"): BASELINE configs[1] -- 3-D InterpCubic BCnan on a 256^3 Float64
-grid (stored 258^3 after the cubic padding) incl. the interp_invert! prefilter at construction,
-1e7 uniform-random queries per GPU, valgrad (value + 3 gradient components).
+Headline workload (config.workload = "C2"): BASELINE configs[1] -- 3-D InterpCubic BCnan on a 256^3
+Float64 grid (stored 258^3 after the cubic padding) incl. the interp_invert! prefilter at
+construction, 1e7 uniform-random queries per GPU, valgrad (value + 3 gradient components).
 
 A "step" is one pass of valgrad over one batch of 1e7 queries.
   value  device-resident: queries / outputs already in HBM; CUDA-event timed on the launch stream.
   e2e    the same step through the C-ABI with HOST buffers (pinned): H2D of the queries and D2H of
-         value+gradient inside the timed region (gb_eval, mem=GB_HOST).
+         value+gradient inside the timed region (gb_eval, mem=GB_HOST).  e2e_pageable repeats it with
+         plain malloc'd numpy buffers (what a Julia Array is).
   roofline  the dominant kernel of the step is eval_brick_kernel<double,3,Cubic,nil,valgrad,...>; its
          average duration is measured live with CUDA events on the launch stream (gb_profile_*),
          algorithmic bytes = 56 B/query (24 in + 32 out) x 1e7 queries per launch ->
          achieved GB/s vs the measured HBM peak.  roofline.step_* gives the same figure for the whole
          step (binning sort + brick evaluation + un-permute), which is what `value` measures.
   contraction  the headline runs the library default, EXACT (the reference's arithmetic order,
-         bit-identical to the oracle); extra.fast repeats the step with GB_FAST (separable FMA,
-         within north_star's 4 ulp of the magnitude scale -- tests/test_gpu_parity.py).
-  cpu_baseline  the C++ restatement of the reference algorithm (oracle, "port") on the host cores,
-         bounded sample.
+         bit-identical to the oracle); extra.other_contraction repeats the step with GB_FAST
+         (separable FMA, within north_star's 4 ulp of the magnitude scale -- tests/test_gpu_parity.py).
+  cpu_baseline  the C++ restatement of the reference algorithm (oracle, "port") on the host cores.
+  extra.configs  (N = 1) the other BASELINE configs on the same box, same timing method: C1 (1e6 and 1e8
+         queries), C2 with tile-sorted queries, C3 (the whole 1e9-query batch in 1e8 slices, and the 8192^2
+         prefilter), C4 (three boundary conditions), C5 (restrict and prolong chains), each with its
+         roofline fraction, ncu DRAM traffic (profiles/traffic.json) and a bitwise parity check of a
+         strided subsample against the oracle.
+  extra.c3_sharded / extra.c5_slab  (N > 1) C3's 1e9 queries split over the ranks, and the C5 chain
+         slab-sharded along dim 3 with the NCCL halo exchange (per-level ms, halo bytes, exchange wait).
 Multi-GPU (torchrun, one process per GPU): the grid is prefiltered on rank 0 and the coefficient
 array broadcast over NCCL; query batches shard with no data-path collective ("weak" scaling: 1e7
 queries per GPU).
@@ -38,6 +45,23 @@ N_GRID = 256
 NQ = 10_000_000
 BYTES_PER_QUERY = 56  # 3*8 coordinates in + (1+3)*8 out
 SEED_GRID, SEED_Q = 2, 12
+METRIC = "valgrad throughput, 3-D InterpCubic BCnan 256^3 Float64"
+
+
+def host_cores():
+    """Host threads this process may use -- NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def c2_config(world, contraction):
+    """One dict for both arms (the driver compares them key by key)."""
+    return {"workload": "C2", "grid": "256^3 f64 (stored 258^3)", "order": "InterpCubic", "bc": "BCnan", "outputs": "valgrad",
+            "queries_per_gpu_per_step": NQ, "query_distribution": "uniform [1,256]^3, splitmix64", "contraction": contraction,
+            "l2": "inputs larger than L2 (240 MB in + 320 MB out + 137 MB grid per step vs 126 MB L2)",
+            "parallelism": f"query-sharded x{world}, coefficients replicated by NCCL broadcast"}
 
 
 def measured_peak():
@@ -46,6 +70,14 @@ def measured_peak():
             return float(json.load(f)["hbm_gbs"]), "measured"
     except Exception:
         return 6650.0, "fallback"
+
+
+def load_traffic():
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 class ClockSampler:
@@ -118,11 +150,11 @@ def run_reference(args):
     from oracle import oracle as O
 
     n = N_GRID
+    threads = host_cores()
     A = O.synth(np.float64, n ** 3, SEED_GRID).reshape((n, n, n), order="F")
     t0 = time.perf_counter()
     co = O.make_coefs(A, "nan", "cubic")
     t_pref = time.perf_counter() - t0
-    threads = O.max_threads()
     sample = int(os.environ.get("GB_REF_SAMPLE", str(NQ)))  # the whole 1e7-query batch: ~2 s per step on 16 cores
     X = 1.0 + O.synth(np.float64, 3 * sample, SEED_Q).reshape(sample, 3) * (n - 1.0)
     for _ in range(max(1, min(args.warmup, 2))):
@@ -133,12 +165,11 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / args.steps
     val = sample / dt / 1e9
     line = {
-        "impl": "reference", "metric": "valgrad throughput, 3-D InterpCubic BCnan 256^3 Float64", "value": val, "unit": "Gpoints/s",
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Gpoints/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2", "grid": "256^3 f64 (stored 258^3)", "order": "InterpCubic", "bc": "BCnan", "outputs": "valgrad",
-                   "queries_per_step": sample, "note": "Julia cannot run in this image, "
-                   "this is the C++ restatement of the reference algorithm (oracle)"},
+        "config": c2_config(args.gpus, "EXACT"),
+        "note": "Julia cannot run in this image: this is the C++ restatement of the reference algorithm (oracle), OpenMP over queries on one host",
         "cpu_baseline": {"value": val, "unit": "Gpoints/s", "cores": threads, "kind": "port", "sample": f"{sample} of 1e7 queries per step, OpenMP over queries",
                          "prefilter_s": t_pref},
         "e2e": {"value": val, "unit": "Gpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -146,6 +177,296 @@ def run_reference(args):
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+# ---- helpers for the per-config section -------------------------------------------------------------------------------
+def _timed(torch, fn, reps):
+    """best / median of `reps` CUDA-event timings after two warm-up calls (the batches are larger than L2)."""
+    fn()
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[0], ts[len(ts) // 2]
+
+
+def _row(workload, units, unit_name, bytes_per_unit, best_ms, med_ms, peak, parity, traffic=None, note=None, **more):
+    gups = units / (med_ms * 1e-3) / 1e9
+    r = {"workload": workload, "ms": med_ms, "ms_best": best_ms, "value": gups, "unit": "G%s/s" % unit_name,
+         "roofline": {"bound": "hbm", "achieved": gups * bytes_per_unit, "peak": peak, "unit": "GB/s", "frac": gups * bytes_per_unit / peak,
+                      "algorithmic_bytes_per_unit": bytes_per_unit, "traffic": traffic},
+         "parity_vs_oracle": parity}
+    if note:
+        r["note"] = note
+    r.update(more)
+    return r
+
+
+def extra_configs(gb, torch, np, O, peak, traffic, reps=5):
+    """C1, C2 (sorted queries), C3, C4, C5 on one GPU; see the module docstring."""
+    rows = []
+    dev = torch.device("cuda", torch.cuda.current_device())
+
+    def sub(t, idx):
+        return t[idx].cpu().numpy()
+
+    # ---- C1 ----------------------------------------------------------------------------------------------------
+    n = 1024
+    A = gb.jl_empty((n, n), torch.float64, dev)
+    gb.synth_uniform(A, 1)
+    G = gb.InterpGrid(A, gb.BCreflect, gb.InterpQuadratic)
+    co = G.coefs
+    for nq in (1_000_000, 100_000_000):
+        X = torch.empty((nq, 2), dtype=torch.float64, device=dev)
+        gb.synth_uniform(X, 11, lo=1.0, hi=float(n))
+        v = torch.empty(nq, dtype=torch.float64, device=dev)
+        best, med = _timed(torch, lambda: gb.getindex_(v, G, X), reps)
+        idx = torch.arange(0, nq, max(1, nq // 50_000), device=dev)
+        ov, _, _, _ = O.evaluate(co, "reflect", "quadratic", sub(X, idx), 1)
+        rows.append(_row("C1 2-D InterpQuadratic BCreflect 1024^2 f64 getindex, %.0e queries" % nq, nq, "points", 24, best, med, peak,
+                         bool(np.array_equal(ov, sub(v, idx), equal_nan=True)), traffic.get("c1_plain_bytes_per_1e8") if nq == 100_000_000 else None))
+        del X, v
+    del G, A
+
+    # ---- C2 with tile-sorted queries (coherent callers: no permutation needed) --------------------------------------
+    n, nq = N_GRID, NQ
+    A = gb.jl_empty((n, n, n), torch.float64, dev)
+    gb.synth_uniform(A, SEED_GRID)
+    G = gb.InterpGrid(A, gb.BCnan, gb.InterpCubic)
+    X = torch.empty((nq, 3), dtype=torch.float64, device=dev)
+    gb.synth_uniform(X, SEED_Q, lo=1.0, hi=float(n))
+    fl = X.floor().to(torch.int64)
+    key = ((fl[:, 2] >> 3) * 4096 + (fl[:, 1] >> 4) * 64 + (fl[:, 0] >> 4))  # 16 x 16 x 8-cell tiles, dim 1 fastest
+    Xs = X[torch.argsort(key)].contiguous()
+    del fl, key, X
+    v = torch.empty(nq, dtype=torch.float64, device=dev)
+    g = torch.empty((nq, 3), dtype=torch.float64, device=dev)
+    co = G.coefs
+    idx = torch.arange(0, nq, 200, device=dev)
+    for fast in (False, True):
+        best, med = _timed(torch, lambda: gb.valgrad_(v, g, G, Xs, fast=fast), reps)
+        par = None
+        if not fast:
+            ov, og, _, _ = O.evaluate(co, "nan", "cubic", sub(Xs, idx), 3)
+            par = bool(np.array_equal(ov, sub(v, idx), equal_nan=True) and np.array_equal(og, sub(g, idx), equal_nan=True))
+        rows.append(_row("C2 3-D InterpCubic BCnan 256^3 f64 valgrad, 1e7 queries pre-sorted by grid tile, %s" % ("FAST" if fast else "EXACT"), nq, "points",
+                         BYTES_PER_QUERY, best, med, peak, par, traffic.get("c2_sorted_%s_bytes_per_step" % ("fast" if fast else "exact"))))
+    del G, A, Xs, v, g
+
+    # ---- C3: the whole 1e9-query batch, 1e8 at a time; and the prefilter of the 8192^2 image --------------------------
+    n, nq, nsl = 8192, 100_000_000, 10
+    A = gb.jl_empty((n, n), torch.float32, dev)
+    gb.synth_uniform(A, 3)
+    G = gb.InterpGrid(A, gb.BCreflect, gb.InterpQuadratic)
+    co = G.coefs
+    X = torch.empty((nq, 2), dtype=torch.float32, device=dev)
+    v = torch.empty(nq, dtype=torch.float32, device=dev)
+    g = torch.empty((nq, 2), dtype=torch.float32, device=dev)
+    h = torch.empty((nq, 2, 2), dtype=torch.float32, device=dev)
+    gb.synth_uniform(X, 14, lo=1.0, hi=float(n))
+    gb.valgradhess_(v, g, h, G, X)
+    torch.cuda.synchronize()
+    tot, par = 0.0, True
+    for k in range(nsl):
+        gb.synth_uniform(X, 14, lo=1.0, hi=float(n), first=k * nq * 2)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        gb.valgradhess_(v, g, h, G, X)
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+        if k in (0, nsl - 1):
+            idx = torch.arange(0, nq, 5000, device=dev)
+            ov, og, oh, _ = O.evaluate(co, "reflect", "quadratic", sub(X, idx), 7)
+            par = par and bool(np.array_equal(ov, sub(v, idx), equal_nan=True) and np.array_equal(og, sub(g, idx), equal_nan=True)
+                               and np.array_equal(oh, sub(h, idx), equal_nan=True))
+    rows.append(_row("C3 2-D InterpQuadratic BCreflect 8192^2 f32 valgradhess, 1e9 queries (10 slices of 1e8)", nq * nsl, "points", 36, tot, tot, peak, par,
+                     traffic.get("c3_plain_blocked_bytes_per_1e8"), note="ms = sum of the 10 slices; traffic is per 1e8-query launch"))
+    del X, v, g, h, G
+    for fast in (False, True):
+        def pf():
+            B = A.clone()
+            gb.interp_invert_(B, gb.BCreflect, gb.InterpQuadratic, fast=fast)
+        try:
+            def cl():
+                A.clone()
+            b0, m0 = _timed(torch, cl, reps)
+            best, med = _timed(torch, pf, reps)
+        except TypeError:
+            continue  # library without the FAST prefilter
+        rows.append(_row("C3 prefilter: interp_invert! of the 8192^2 f32 image, both sweeps, %s" % ("FAST (in-line parallel solver)" if fast else "EXACT (LU order)"),
+                         n * n, "points", 16, max(best - b0, 1e-6), max(med - m0, 1e-6), peak, None,
+                         traffic.get("c3_prefilter_%s_bytes" % ("fast" if fast else "exact")), note="time of the device copy that precedes the in-place solve subtracted"))
+    del A
+
+    # ---- C4 ----------------------------------------------------------------------------------------------------
+    n, nq = 64, 100_000_000
+    A = gb.jl_empty((n,) * 4, torch.float64, dev)
+    gb.synth_uniform(A, 4)
+    rng = gb.FloatRange(-63.0, 2.0, 64, 63.0)  # -1.0 : 2/63 : 1.0
+    X = torch.empty((nq, 4), dtype=torch.float64, device=dev)
+    gb.synth_uniform(X, 15, lo=-1.0 + (-16.0) * 2.0 / 63.0, hi=1.0 + 16.0 * 2.0 / 63.0)  # index coordinates U[1-16, 64+16]
+    v = torch.empty(nq, dtype=torch.float64, device=dev)
+    idx = torch.arange(0, nq, 5000, device=dev)
+    for name, bc in (("periodic", gb.BCperiodic), ("nearest", gb.BCnearest), ("fill", -1.0)):
+        G = gb.InterpGrid(A, bc, gb.InterpLinear)
+        CG = gb.CoordInterpGrid((rng,) * 4, G)
+        best, med = _timed(torch, lambda: gb.getindex_(v, CG, X), reps)
+        ov, _, _, _ = O.evaluate(G.coefs, name, "linear", sub(X, idx), 1, affine=[rng.row()] * 4)
+        rows.append(_row("C4 4-D InterpLinear BC%s 64^4 f64 getindex via CoordInterpGrid, 1e8 queries" % name, nq, "points", 40, best, med, peak,
+                         bool(np.array_equal(ov, sub(v, idx), equal_nan=True)), traffic.get("c4_plain_blocked_%s_bytes_per_1e8" % name)))
+        del G, CG
+    del A, X, v
+
+    # ---- C5 ----------------------------------------------------------------------------------------------------
+    n = 1024
+    A = gb.jl_empty((n, n, n), torch.float64, dev)
+    gb.synth_uniform(A, 5)
+    sizes = [n]
+    while sizes[-1] > 17:
+        sizes.append(gb.restrict_size(sizes[-1]))
+
+    def down():
+        lv = [A]
+        for _ in sizes[1:]:
+            lv.append(gb.restrict(lv[-1], [True, True, True]))
+        return lv
+
+    best_d, med_d = _timed(torch, down, reps)
+    levels = down()
+    coarse = levels[-1]
+
+    def up():
+        cur = coarse
+        for s in reversed(sizes[:-1]):
+            cur = gb.prolong(cur, [s, s, s])
+        return cur
+
+    best_u, med_u = _timed(torch, up, reps)
+    k = sizes.index(129)
+    a129 = gb.jl_to_numpy(levels[k])
+    par = bool(np.array_equal(O.restrict_flags(a129, [True] * 3), gb.jl_to_numpy(levels[k + 1])))
+    par = par and bool(np.array_equal(O.prolong_sizes(gb.jl_to_numpy(levels[k + 1]), [129] * 3), gb.jl_to_numpy(gb.prolong(levels[k + 1], [129] * 3))))
+    bpu = 8.0 * sum(a ** 3 + b ** 3 for a, b in zip(sizes[:-1], sizes[1:])) / n ** 3
+    chain = "->".join(map(str, sizes))
+    rows.append(_row("C5 restrict chain %s f64 (fused 3-D marching kernel)" % chain, n ** 3, "points", bpu, best_d, med_d, peak, par, traffic.get("c5_restrict_chain_bytes"),
+                     note="unit = level-0 point; parity on the 129^3 level (full-size levels: tests/test_gpu_fullsize.py)"))
+    rows.append(_row("C5 prolong chain back up (fused 3-D marching kernel)", n ** 3, "points", bpu, best_u, med_u, peak, par, traffic.get("c5_prolong_chain_bytes")))
+    return rows
+
+
+def c3_sharded(gb, torch, dist, np, O, peak, rank, world, dev):
+    """C3's 1e9 queries split over the ranks (strong scaling): contiguous ranges, coefficients broadcast once."""
+    import grid_jl_b200.dist as D
+
+    n, total, slice_q = 8192, 1_000_000_000, 50_000_000
+    G = None
+    if rank == 0:
+        A = gb.jl_empty((n, n), torch.float32, dev)
+        gb.synth_uniform(A, 3)
+        G = gb.InterpGrid(A, gb.BCreflect, gb.InterpQuadratic)
+        del A
+    t0 = time.perf_counter()
+    G = D.broadcast_grid(G, gb.BCreflect, gb.InterpQuadratic, src=0)
+    torch.cuda.synchronize()
+    t_bcast = time.perf_counter() - t0
+    q0, q1 = D.shard_range(total, rank, world)
+    X = torch.empty((slice_q, 2), dtype=torch.float32, device=dev)
+    v = torch.empty(slice_q, dtype=torch.float32, device=dev)
+    g = torch.empty((slice_q, 2), dtype=torch.float32, device=dev)
+    h = torch.empty((slice_q, 2, 2), dtype=torch.float32, device=dev)
+    gb.synth_uniform(X, 14, lo=1.0, hi=float(n), first=q0 * 2)
+    gb.valgradhess_(v, g, h, G, X)  # warm-up
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms, par = 0.0, True
+    for s0 in range(q0, q1, slice_q):
+        cnt = min(slice_q, q1 - s0)
+        gb.synth_uniform(X[:cnt], 14, lo=1.0, hi=float(n), first=s0 * 2)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        gb.valgradhess_(v[:cnt], g[:cnt], h[:cnt], G, X[:cnt])
+        e1.record()
+        torch.cuda.synchronize()
+        ms += e0.elapsed_time(e1)
+        if s0 == q0 and rank in (0, world - 1):
+            idx = torch.arange(0, cnt, 10_000, device=dev)
+            ov, og, oh, _ = O.evaluate(G.coefs, "reflect", "quadratic", X[idx].cpu().numpy(), 7)
+            par = bool(np.array_equal(ov, v[idx].cpu().numpy(), equal_nan=True) and np.array_equal(oh, h[idx].cpu().numpy(), equal_nan=True))
+    t = torch.tensor([ms, 0.0 if par else 1.0], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t[0].item())
+    val = total / (ms_max * 1e-3) / 1e9
+    return {"workload": "C3 2-D InterpQuadratic BCreflect 8192^2 f32 valgradhess, 1e9 queries sharded over %d GPUs" % world, "scaling": "strong",
+            "ms": ms_max, "value": val, "unit": "Gpoints/s", "queries_per_gpu": q1 - q0, "broadcast_ms": t_bcast * 1e3,
+            "roofline": {"bound": "hbm", "achieved": val * 36 / world, "peak": peak, "unit": "GB/s per GPU", "frac": val * 36 / world / peak},
+            "parity_vs_oracle": float(t[1].item()) == 0.0}
+
+
+def c5_slab(gb, torch, dist, np, O, peak, rank, world, dev, reps=3):
+    """The C5 chain with the arrays slab-sharded along dim 3; one halo exchange per level (NCCL)."""
+    import grid_jl_b200.dist as D
+
+    n = 1024
+    sizes = [n]
+    while sizes[-1] > 17:
+        sizes.append(gb.restrict_size(sizes[-1]))
+    f0, f1 = D.shard_range(n, rank, world)
+    local = gb.jl_empty((n, n, f1 - f0), torch.float64, dev)
+    gb.synth_uniform(local, 5, first=f0 * n * n)  # this rank's planes of the same synthetic array
+    res = {"workload": "C5 restrict / prolong chain %s f64, slab-sharded along dim 3 over %d GPUs" % ("->".join(map(str, sizes)), world), "scaling": "strong"}
+    out = {}
+    for direction in ("restrict", "prolong"):
+        best = None
+        for rep in range(reps + 1):
+            stats = []
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if direction == "restrict":
+                cur, lv = local, [local]
+                for L in sizes[:-1]:
+                    cur = D.slab_restrict3(cur, L, rank, world, stats=stats)
+                    lv.append(cur)
+            else:
+                cur = coarse
+                for c, s in zip(reversed(sizes[1:]), reversed(sizes[:-1])):
+                    cur = D.slab_prolong3(cur, c, (s, s, s), rank, world, stats=stats)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            if rep > 0 and (best is None or ms < best[0]):
+                best = (ms, stats)
+        if direction == "restrict":
+            levels, coarse = lv, lv[-1]
+        t = torch.tensor([best[0]], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        bpu = 8.0 * sum(a ** 3 + b ** 3 for a, b in zip(sizes[:-1], sizes[1:])) / n ** 3
+        val = n ** 3 / (ms * 1e-3) / 1e9
+        out[direction] = {"ms": ms, "value": val, "unit": "Gpoints/s (level-0 points)",
+                          "roofline": {"bound": "hbm", "achieved": val * bpu / world, "peak": peak, "unit": "GB/s per GPU", "frac": val * bpu / world / peak},
+                          "levels_rank0": best[1]}
+    # parity: the 129^3 level gathered on rank 0 against the oracle applied to the gathered 257^3 level
+    k = sizes.index(257)
+    parts = [None] * world
+    dist.all_gather_object(parts, (gb.jl_to_numpy(levels[k]), gb.jl_to_numpy(levels[k + 1])))
+    par = None
+    if rank == 0:
+        fine = np.concatenate([p[0] for p in parts], axis=2)
+        coarse_ref = O.restrict_flags(np.asfortranarray(fine), [True] * 3)
+        par = bool(np.array_equal(coarse_ref, np.concatenate([p[1] for p in parts], axis=2)))
+    res.update(out)
+    res["parity_vs_oracle"] = par
+    return res
 
 
 def main():
@@ -157,6 +478,7 @@ def main():
     ap.add_argument("--fast", action="store_true", help="time the GB_FAST (separable FMA) contraction instead of the bit-exact default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip extra.configs / extra.c3_sharded / extra.c5_slab")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL's version banner, library
     # chatter) is sent to stderr while the benchmark runs; the line itself goes to the saved descriptor.
@@ -182,6 +504,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n = N_GRID
+    peak, how = measured_peak()
+    traffic = load_traffic()
 
     # ---- grid construction: synth samples on device, pad + prefilter on rank 0, broadcast coefs ----
     pref_ms = None
@@ -277,77 +601,105 @@ def main():
         oe[1].record()
         torch.cuda.synchronize()
         oms = oe[0].elapsed_time(oe[1]) / osteps
+        ostages = stage_profile(of)
+        okern = ostages.get("eval_brick", oms)
         other = {"contraction": "FAST" if of else "EXACT", "value": NQ / (oms * 1e-3) / 1e9, "unit": "Gpoints/s", "ms_per_step": oms,
-                 "stages_ms": stage_profile(of)}
+                 "stages_ms": ostages, "roofline_frac_kernel": BYTES_PER_QUERY * NQ / (okern * 1e-3) / 1e9 / peak,
+                 "roofline_frac_step": BYTES_PER_QUERY * NQ / (oms * 1e-3) / 1e9 / peak}
         gb.valgrad_(val, grad, G, X, fast=args.fast)  # leave the headline mode's results in val / grad
         torch.cuda.synchronize()
 
     # ---- end to end through the host-buffer C-ABI call ----------------------------------------------
-    e2e = None
+    e2e = e2e_pageable = None
     if not args.no_e2e:
+        def host_run(Xn, vn, gn, ksteps):
+            for _ in range(2):
+                gb.valgrad_(vn, gn, G, Xn, fast=args.fast)
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(ksteps):
+                gb.valgrad_(vn, gn, G, Xn, fast=args.fast)  # returns when the results are in vn/gn
+            dt = (time.perf_counter() - t0) / ksteps
+            te = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            return float(te.item())
+
         Xh = torch.empty((NQ, 3), dtype=torch.float64).pin_memory()
         Xh.copy_(X)
         vh = torch.empty(NQ, dtype=torch.float64).pin_memory()
         gh = torch.empty((NQ, 3), dtype=torch.float64).pin_memory()
-        Xn, vn, gn = Xh.numpy(), vh.numpy(), gh.numpy()
         ksteps = max(3, min(args.steps, 10))
-        for _ in range(2):
-            gb.valgrad_(vn, gn, G, Xn, fast=args.fast)
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(ksteps):
-            gb.valgrad_(vn, gn, G, Xn, fast=args.fast)  # returns when the results are in vn/gn
-        dt = (time.perf_counter() - t0) / ksteps
-        te = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        dt = float(te.item())
+        dt = host_run(Xh.numpy(), vh.numpy(), gh.numpy(), ksteps)
         assert torch.equal(vh.to(dev), val) or args.fast, "host-path results differ from the device path"
         e2e = {"value": world * NQ / dt / 1e9, "unit": "Gpoints/s", "h2d_bytes_per_step": NQ * 24, "d2h_bytes_per_step": NQ * 32,
                "ms_per_step": dt * 1e3, "steps": ksteps, "host_memory": "pinned"}
+        # the same call with pageable buffers: what a Julia Array (plain malloc) gives unless the caller pins it
+        Xp, vp, gp = np.array(Xh.numpy(), copy=True), np.empty(NQ), np.empty((NQ, 3))
+        del Xh, vh, gh
+        dtp = host_run(Xp, vp, gp, max(2, ksteps // 2))
+        assert np.array_equal(vp, val.cpu().numpy()) or args.fast
+        e2e_pageable = {"value": world * NQ / dtp / 1e9, "unit": "Gpoints/s", "ms_per_step": dtp * 1e3, "host_memory": "pageable (numpy / malloc)",
+                        "h2d_bytes_per_step": NQ * 24, "d2h_bytes_per_step": NQ * 32}
+        del Xp, vp, gp
 
     clk.__exit__()
+
+    # ---- the other BASELINE configs ---------------------------------------------------------------------------
+    from oracle import oracle as O  # the checker (parity flags of the extras, cpu_baseline below)
+
+    extra_rows = sharded = slab = None
+    extra_err = None
+    if not args.no_extra:
+        try:
+            if world == 1:
+                torch.cuda.empty_cache()
+                extra_rows = extra_configs(gb, torch, np, O, peak, traffic)
+            else:
+                torch.cuda.empty_cache()
+                sharded = c3_sharded(gb, torch, dist, np, O, peak, rank, world, dev)
+                torch.cuda.empty_cache()
+                slab = c5_slab(gb, torch, dist, np, O, peak, rank, world, dev)
+        except Exception as e:  # the headline line must survive a failure in the extras; the error is reported in it
+            import traceback
+
+            extra_err = "%s: %s | %s" % (type(e).__name__, e, traceback.format_exc().strip().splitlines()[-3:])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
     # ---- roofline of the dominant kernel of the step ------------------------------------------------------
-    peak, how = measured_peak()
     step_ms = total_ms / args.steps
     kernel_ms = stages.get("eval_brick", step_ms)
     achieved = BYTES_PER_QUERY * NQ / (kernel_ms * 1e-3) / 1e9
     step_achieved = BYTES_PER_QUERY * NQ / (step_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("eval_brick_fast_bytes_per_launch" if args.fast else "eval_brick_exact_bytes_per_launch")
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+    tkey = "fast" if args.fast else "exact"
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic.get("eval_brick_%s_bytes_per_launch" % tkey),
                 "peak_source": how, "kernel": "eval_brick_kernel<double,3,Cubic,BCF_NIL,valgrad,%s>" % ("FAST" if args.fast else "EXACT"),
                 "algorithmic_bytes_per_launch": BYTES_PER_QUERY * NQ, "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / step_ms,
                 "stages_ms": stages, "step_achieved": step_achieved, "step_frac": step_achieved / peak,
+                "step_traffic": traffic.get("c2_step_%s_bytes" % tkey), "step_traffic_by_stage": traffic.get("c2_step_%s_by_stage" % tkey),
+                "traffic_source": traffic.get("source"),
                 "frac_of_nominal_8TBs": achieved / 8000.0,
                 # what actually bounds the EXACT kernel: the FP64 pipe (64 lanes/SM, one mul or add per lane per clock;
-                # ncu sm__pipe_fp64_cycles_active 80 %, profiles/r1_v12_exact_full.txt).  816 unfusable mul/add of the
+                # ncu sm__pipe_fp64_cycles_active 80 %).  816 unfusable mul/add of the
                 # reference's contraction + ~130 for weights / coordinates per query; FAST: 192 FMA + ~75.
-                "fp64_pipe": (lambda ops, clk: {"ops_per_query": ops, "achieved_Tops": ops * NQ / (kernel_ms * 1e-3) / 1e12,
-                                                "peak_Tops": 64 * 148 * clk * 1e6 / 1e12,
-                                                "frac": ops * NQ / (kernel_ms * 1e-3) / (64 * 148 * clk * 1e6)})(
-                                                    267 if args.fast else 945, (clk.max_mhz or 1965)),
+                "fp64_pipe": (lambda ops, clk_: {"ops_per_query": ops, "achieved_Tops": ops * NQ / (kernel_ms * 1e-3) / 1e12,
+                                                 "peak_Tops": 64 * 148 * clk_ * 1e6 / 1e12,
+                                                 "frac": ops * NQ / (kernel_ms * 1e-3) / (64 * 148 * clk_ * 1e6)})(
+                                                     267 if args.fast else 945, (clk.max_mhz or 1965)),
                 "limiter": "FP64 pipe (816 dependent mul/add per query in the reference's order)" if not args.fast else "shared-memory gathers + FP64 pipe"}
 
     # ---- CPU baseline (oracle port) on a bounded sample ---------------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        from oracle import oracle as O
-
         sample = int(os.environ.get("GB_REF_SAMPLE", str(NQ)))  # the whole batch: ~2 s on 16 cores (+ ~1 s single-core subsample)
         co = G.coefs
         Xs = X[:sample].cpu().numpy()
-        threads = O.max_threads()
+        threads = host_cores()
         O.evaluate(co, "nan", "cubic", Xs[: sample // 10], 3, nthreads=threads)
         t0 = time.perf_counter()
         ov, og, _, _ = O.evaluate(co, "nan", "cubic", Xs, 3, nthreads=threads)
@@ -362,18 +714,17 @@ def main():
                "bit_identical_to_gpu": parity if not args.fast else None}
 
     line = {
-        "metric": "valgrad throughput, 3-D InterpCubic BCnan 256^3 Float64", "value": value, "unit": "Gpoints/s", "n_gpus": world,
+        "metric": METRIC, "value": value, "unit": "Gpoints/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2", "grid": "256^3 f64 (stored 258^3)", "order": "InterpCubic", "bc": "BCnan", "outputs": "valgrad",
-                   "queries_per_gpu_per_step": NQ, "query_distribution": "uniform [1,256]^3, splitmix64", "contraction": "FAST" if args.fast else "EXACT",
-                   "l2": "inputs larger than L2 (240 MB in + 320 MB out + 137 MB grid per step vs 126 MB L2)",
-                   "parallelism": f"query-sharded x{world}, coefficients replicated by NCCL broadcast"},
+        "config": c2_config(world, "FAST" if args.fast else "EXACT"),
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary((t_win0, t_win1)),
         "extra": {"prefilter_ms": pref_ms, "prefilter_note": "InterpGrid(A,BCnan,InterpCubic) on device: pad + 3 prefilter sweeps of 258^3 f64",
+                  "prefilter_roofline_frac": (64.0 * (n + 2) ** 3 / (pref_ms * 1e-3) / 1e9 / peak) if pref_ms else None,
                   "step_ms_min": per[0], "step_ms_median": per[len(per) // 2], "step_ms_max": per[-1],
-                  "other_contraction": other,
-                  "with_prefilter_ms_per_step": (ms_per_step + pref_ms) if pref_ms else None},
+                  "other_contraction": other, "e2e_pageable": e2e_pageable,
+                  "with_prefilter_ms_per_step": (ms_per_step + pref_ms) if pref_ms else None,
+                  "configs": extra_rows, "c3_sharded": sharded, "c5_slab": slab, "extra_error": extra_err},
     }
     print(json.dumps(line), flush=True)
     if world > 1:

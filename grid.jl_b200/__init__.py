@@ -12,7 +12,7 @@ from ._lib import (BoundsError, CudaError, DimensionMismatch, ErrorException, Gr
 from .api import *  # noqa: F401,F403
 from .api import (AbstractInterpGrid, BCfill, BCna, BCnan, BCnearest, BCnil, BCperiodic, BCreflect, BoundaryCondition,
                   CoordInterpGrid, FloatRange, InterpBackward, InterpCubic, InterpForward, InterpGrid, InterpGridChannels, InterpIrregular, InterpLinear, InterpNearest, InterpQuadratic,
-                  InterpType, StepRange, UnitRange, frange, getindex_, getindex_batch, interp_invert_, jl_empty,
+                  InterpType, StepRange, UnitRange, filledges_, frange, getindex_, getindex_batch, interp_invert_, jl_empty,
                   jl_from_numpy, jl_to_numpy, launch_count, npoints, PROFILE_STAGES, profile_enable, profile_read, pad1, prolong, prolongb, prolong_size, restrict, restrictb, restrict_extrap,
                   restrict_size, synth_uniform, valgrad, valgrad_, valgrad_batch, valgradhess, valgradhess_,
                   valgradhess_batch, wrap)

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libgridb200.so")
 GB_F32, GB_F64 = 0, 1
 GB_HOST, GB_DEVICE = 0, 1
 GB_OUT_VAL, GB_OUT_GRAD, GB_OUT_HESS = 1, 2, 4
-GB_EXACT, GB_FAST, GB_TILED, GB_PLAIN = 0, 1, 2, 4
+GB_EXACT, GB_FAST, GB_TILED, GB_PLAIN, GB_SORTED = 0, 1, 2, 4, 8
 (GB_OK, GB_ERR_ARG, GB_ERR_INVALID_LOCATION, GB_ERR_UNSUPPORTED, GB_ERR_CUDA, GB_ERR_DIM, GB_ERR_PROLONG_SIZE) = range(7)
 
 vp, i64, i32, f64, u64 = C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_uint64
@@ -42,6 +42,22 @@ SIGNATURES = {
     "gb_grid_coefs_copy": (i32, [vp, vp, vp]),
     "gb_grid_destroy": (i32, [vp]),
     "gb_invert": (i32, [i32, i32, p_i64, vp, i32, i32, i32, p_i32, i32, vp]),
+    "gb_invert_opt": (i32, [i32, i32, p_i64, vp, i32, i32, i32, p_i32, i32, i32, vp]),
+    "gb_grid_create_opt": (i32, [p_vp, i32, i32, p_i64, vp, i32, i32, i32, f64, i32, vp]),
+    "gb_filledges": (i32, [i32, i32, p_i64, vp, f64, i32, vp]),
+    "gb_comm_unique_id": (i32, [vp, C.c_size_t]),
+    "gb_comm_init_rank": (i32, [p_vp, i32, i32, vp, C.c_size_t]),
+    "gb_comm_init_all": (i32, [p_vp, i32, p_i32]),
+    "gb_comm_init_loopback": (i32, [p_vp, i32]),
+    "gb_comm_size": (i32, [vp, p_i32, p_i32, p_i32]),
+    "gb_comm_destroy": (i32, [vp]),
+    "gb_shard_range": (i32, [i64, i32, i32, p_i64, p_i64]),
+    "gb_slab_plan": (i32, [i32, i64, i64, i32, i32, p_i64, p_i64, p_i64, p_i64, p_i64, i32, p_i32]),
+    "gb_grid_replicate": (i32, [vp, i32, p_vp, i32, i32, p_i64, i32, i32, f64]),
+    "gb_eval_sharded": (i32, [vp, p_vp, i32, i64, vp, i32, p_f64, vp, vp, vp, i32, p_i64]),
+    "gb_restrict3_sharded": (i32, [vp, i32, p_i64, p_vp, f64, p_vp, p_vp]),
+    "gb_prolong3_sharded": (i32, [vp, i32, p_i64, p_vp, p_i64, p_vp, p_vp]),
+    "gb_comm_stats": (i32, [vp, p_f64, i32, p_i32]),
     "gb_pad1": (i32, [i32, i32, p_i64, vp, f64, vp, i32, vp]),
     "gb_eval": (i32, [vp, i32, i64, vp, i32, i64, i64, p_f64, vp, vp, vp, i32, i32, p_i64, vp]),
     "gb_eval_soa": (i32, [vp, i32, i64, p_vp, i32, p_f64, vp, vp, vp, i32, i32, p_i64, vp]),

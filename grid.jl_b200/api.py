@@ -415,7 +415,9 @@ class InterpGrid(AbstractInterpGrid):
     A: numpy array or column-major CUDA tensor.  The padded, prefiltered coefficients live on the
     current CUDA device for the lifetime of the object."""
 
-    def __init__(self, A, bc, it, _from_coefs=False):
+    def __init__(self, A, bc, it, _from_coefs=False, fast_prefilter=False):
+        """fast_prefilter: run interp_invert! with the line-parallel GB_FAST solver where it applies (grids with few long
+        lines; a few ulp of max|A| instead of bit-identical coefficients)."""
         lib = L.lib()
         order = _it(it)
         fill = float("nan")
@@ -428,9 +430,16 @@ class InterpGrid(AbstractInterpGrid):
         a = _Arr(A, name="A")
         self.BC, self.IT = bc, it
         self._h = C.c_void_p()
-        fn = lib.gb_grid_create_from_coefs if _from_coefs else lib.gb_grid_create
-        L.check(fn(C.byref(self._h), a.dtype, a.ndim, _i64s(a.shape), a.ptr, a.mem, bcode, order, fill, a.stream()))
+        if _from_coefs:
+            L.check(lib.gb_grid_create_from_coefs(C.byref(self._h), a.dtype, a.ndim, _i64s(a.shape), a.ptr, a.mem, bcode, order, fill, a.stream()))
+        else:
+            L.check(lib.gb_grid_create_opt(C.byref(self._h), a.dtype, a.ndim, _i64s(a.shape), a.ptr, a.mem, bcode, order, fill,
+                                           L.GB_FAST if fast_prefilter else L.GB_EXACT, a.stream()))
         self._lib = lib
+        self._read_info(fill)
+
+    def _read_info(self, fill):
+        lib = self._lib
         dt, nd = C.c_int(), C.c_int()
         ud, sd = (C.c_int64 * 8)(), (C.c_int64 * 8)()
         L.check(lib.gb_grid_info(self._h, C.byref(dt), C.byref(nd), ud, sd, None, None, None))
@@ -441,6 +450,15 @@ class InterpGrid(AbstractInterpGrid):
         self._stored = tuple(sd[i] for i in range(self.ndim))
         self.fillval = fill
         self.affine = None
+
+    @classmethod
+    def _adopt(cls, handle, bc, it, fill=float("nan")):
+        """Wrap an existing gb_grid handle (gb_grid_replicate); the object owns it from now on."""
+        g = cls.__new__(cls)
+        g.BC, g.IT = bc, it
+        g._h, g._lib = handle, L.lib()
+        g._read_info(fill)
+        return g
 
     @classmethod
     def from_coefs(cls, coefs, bc, it, fill=float("nan")):
@@ -504,7 +522,7 @@ class InterpGrid(AbstractInterpGrid):
         return flat.reshape(self._stored[::-1]).permute(*range(self.ndim - 1, -1, -1))
 
     # -- evaluation core --
-    def _eval(self, X, mask, val=None, grad=None, hess=None, fast=False, affine=None, tiled=None):
+    def _eval(self, X, mask, val=None, grad=None, hess=None, fast=False, affine=None, tiled=None, sorted=False):
         N = self.ndim
         q = X if isinstance(X, _Queries) else _Queries(X, N)
         dt = self.dtype_code
@@ -525,7 +543,7 @@ class InterpGrid(AbstractInterpGrid):
             aff = (C.c_double * (4 * N))(*[v for row in affine for v in row])
         bad = C.c_int64(-1)
         pbad = C.byref(bad) if self.BC is BCnil else None
-        flags = (L.GB_FAST if fast else L.GB_EXACT) | (0 if tiled is None else (L.GB_TILED if tiled else L.GB_PLAIN))
+        flags = (L.GB_FAST if fast else L.GB_EXACT) | (0 if tiled is None else (L.GB_TILED if tiled else L.GB_PLAIN)) | (L.GB_SORTED if sorted else 0)
         if q.cols is not None:
             rc = self._lib.gb_eval_soa(self._h, mask, q.nq, q.ptrs, q.xdtype, aff, pv, pg, ph, q.mem, flags, pbad, q.stream())
         else:
@@ -800,39 +818,55 @@ def valgradhess(*args):
 # only changes scheduling (binned shared-memory bricks vs plain global gathers), never results.
 
 
-def getindex_(out, G, X, fast=False, tiled=None):
-    ig = _grid_of(G)
-    ig._eval(X, L.GB_OUT_VAL, val=out, fast=fast, affine=G.affine, tiled=tiled)
+def _irregular_batch(G, X, out=None):
+    """InterpIrregular in the batched entry points: 1-D, value only (src/interp.jl:318-377)."""
+    v = G._eval(X)
+    if out is None:
+        return v
+    if _is_tensor(out):
+        out.copy_(v if _is_tensor(v) else _torch().as_tensor(v))
+    else:
+        out[...] = v.cpu().numpy() if _is_tensor(v) else v
     return out
 
 
-def valgrad_(v, g, G, X, fast=False, tiled=None):
+def getindex_(out, G, X, fast=False, tiled=None, sorted=False):
+    if isinstance(G, InterpIrregular):
+        return _irregular_batch(G, X, out)
     ig = _grid_of(G)
-    ig._eval(X, L.GB_OUT_VAL | L.GB_OUT_GRAD, val=v, grad=g, fast=fast, affine=G.affine, tiled=tiled)
+    ig._eval(X, L.GB_OUT_VAL, val=out, fast=fast, affine=G.affine, tiled=tiled, sorted=sorted)
+    return out
+
+
+def valgrad_(v, g, G, X, fast=False, tiled=None, sorted=False):
+    ig = _grid_of(G)
+    ig._eval(X, L.GB_OUT_VAL | L.GB_OUT_GRAD, val=v, grad=g, fast=fast, affine=G.affine, tiled=tiled, sorted=sorted)
     return v
 
 
-def valgradhess_(v, g, h, G, X, fast=False, tiled=None):
+def valgradhess_(v, g, h, G, X, fast=False, tiled=None, sorted=False):
     if isinstance(G, CoordInterpGrid):
         raise MethodError(L.GB_ERR_UNSUPPORTED, "valgradhess has no method for CoordInterpGrid")
-    G._eval(X, L.GB_OUT_VAL | L.GB_OUT_GRAD | L.GB_OUT_HESS, val=v, grad=g, hess=h, fast=fast, tiled=tiled)
+    G._eval(X, L.GB_OUT_VAL | L.GB_OUT_GRAD | L.GB_OUT_HESS, val=v, grad=g, hess=h, fast=fast, tiled=tiled, sorted=sorted)
     return v
 
 
-def getindex_batch(G, X, fast=False, tiled=None):
-    return _grid_of(G)._eval(X, L.GB_OUT_VAL, fast=fast, affine=G.affine, tiled=tiled)[0]
+def getindex_batch(G, X, fast=False, tiled=None, sorted=False):
+    if isinstance(G, InterpIrregular):
+        return _irregular_batch(G, X)
+    return _grid_of(G)._eval(X, L.GB_OUT_VAL, fast=fast, affine=G.affine, tiled=tiled, sorted=sorted)[0]
 
 
-def valgrad_batch(G, X, fast=False, tiled=None):
-    v, g, _ = _grid_of(G)._eval(X, L.GB_OUT_VAL | L.GB_OUT_GRAD, fast=fast, affine=G.affine, tiled=tiled)
+def valgrad_batch(G, X, fast=False, tiled=None, sorted=False):
+    v, g, _ = _grid_of(G)._eval(X, L.GB_OUT_VAL | L.GB_OUT_GRAD, fast=fast, affine=G.affine, tiled=tiled, sorted=sorted)
     return v, g
 
 
-def valgradhess_batch(G, X, fast=False, tiled=None):
+def valgradhess_batch(G, X, fast=False, tiled=None, sorted=False):
     """h[q] is the symmetric N x N Hessian of query q."""
     if isinstance(G, CoordInterpGrid):
         raise MethodError(L.GB_ERR_UNSUPPORTED, "valgradhess has no method for CoordInterpGrid")
-    return G._eval(X, L.GB_OUT_VAL | L.GB_OUT_GRAD | L.GB_OUT_HESS, fast=fast, tiled=tiled)
+    return G._eval(X, L.GB_OUT_VAL | L.GB_OUT_GRAD | L.GB_OUT_HESS, fast=fast, tiled=tiled, sorted=sorted)
 
 
 # ---- CoordInterpGrid (src/coord.jl:3-69) ----------------------------------------------------------------------
@@ -871,8 +905,18 @@ class CoordInterpGrid(AbstractInterpGrid):
 # ---- prefilter / padding ----------------------------------------------------------------------------------------
 
 
-def interp_invert_(A, bc, it, dimlist=None):
-    """interp_invert!(A, BC, IT[, dimlist]) in place (src/interp.jl:909-953); dimlist is 1-based."""
+def filledges_(A, val):
+    """filledges!(A, val) (src/utilities.jl:22-33): every element on a face of the array is set to val, in place."""
+    a = _Arr(A, writable=True, name="A")
+    L.check(L.lib().gb_filledges(a.dtype, a.ndim, _i64s(a.shape), a.ptr, float(val), a.mem, a.stream()))
+    if a.mem == L.GB_HOST and isinstance(A, np.ndarray) and a.obj is not A:
+        A[...] = a.obj
+    return A
+
+
+def interp_invert_(A, bc, it, dimlist=None, fast=False):
+    """interp_invert!(A, BC, IT[, dimlist]) in place (src/interp.jl:909-953); dimlist is 1-based.
+    fast=True: the line-parallel GB_FAST solver where it applies (same solution to a few ulp of max|A|)."""
     lib = L.lib()
     a = _Arr(A, writable=True, name="A")
     if isinstance(bc, (int, float)) and not isinstance(bc, bool):
@@ -887,7 +931,7 @@ def interp_invert_(A, bc, it, dimlist=None):
             if not 1 <= d <= a.ndim:
                 raise ErrorException(L.GB_ERR_ARG, "dimlist entry out of range")
         dl, n = (C.c_int * len(dimlist))(*[d - 1 for d in dimlist]), len(dimlist)
-    L.check(lib.gb_invert(a.dtype, a.ndim, _i64s(a.shape), a.ptr, a.mem, bcode, _it(it), dl, n, a.stream()))
+    L.check(lib.gb_invert_opt(a.dtype, a.ndim, _i64s(a.shape), a.ptr, a.mem, bcode, _it(it), dl, n, L.GB_FAST if fast else L.GB_EXACT, a.stream()))
     if a.mem == L.GB_HOST and isinstance(A, np.ndarray) and a.obj is not A:
         A[...] = a.obj  # 1-D / already-F-ordered views share memory; this covers harmless copies
     return A
@@ -1141,7 +1185,10 @@ def profile_read():
     ms = (C.c_double * 8)()
     n = C.c_int(0)
     L.check(L.lib().gb_profile_read(ms, 8, C.byref(n)))
-    return {PROFILE_STAGES[i]: float(ms[i]) for i in range(n.value)}
+    out = {PROFILE_STAGES[i]: float(ms[i]) for i in range(n.value)}
+    if n.value:
+        out["grouped"] = float(ms[6])  # 1.0: the batch arrived grouped by tile and was evaluated in place (no permutation)
+    return out
 
 
 def synth_uniform(out, seed, lo=0.0, hi=1.0, first=0):

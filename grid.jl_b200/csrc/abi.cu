@@ -35,16 +35,22 @@ int num_sms() {
     return n;
 }
 
+// Stream-ordered scratch (cudaMallocAsync) comes from the device's default pool.  Keep a bounded amount cached between
+// calls -- staging buffers and sort scratch are reused call after call -- instead of everything forever: PyTorch's
+// allocator (plain cudaMalloc) cannot reuse what this pool holds.  Once per device; GB_POOL_KEEP_MB overrides 2048.
 static void pool_keep_memory() {
-    static std::once_flag once;
-    std::call_once(once, [] {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return;
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) return;
-        unsigned long long keep = ~0ull;  // staging buffers are reused call after call
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    });
+    static std::mutex mu;
+    static bool done[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+    std::lock_guard<std::mutex> lk(mu);
+    if (done[dev]) return;
+    done[dev] = true;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) return;
+    const char* e = getenv("GB_POOL_KEEP_MB");
+    unsigned long long keep = (unsigned long long)(e ? std::max(0.0, atof(e)) : 2048.0) * 1048576ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
 }
 
 static size_t esize(int dtype) { return dtype == GB_F64 ? 8 : 4; }
@@ -64,7 +70,18 @@ struct gb_grid {
     int blocked;  // resident layout: 4^N-element Morton blocks instead of column-major (wants_blocked below)
     int device;
     int shift;
+    cudaEvent_t ready;  // recorded on the creation stream once the coefficients are final: every reader's stream waits for it
 };
+// Order a reader's stream after the grid's construction (device-mode creation returns before its kernels have run, and
+// readers may use other, non-blocking streams).
+static int wait_ready(const gb_grid* g, cudaStream_t s) {
+    if (g->ready) GB_CUDA(cudaStreamWaitEvent(s, g->ready, 0));
+    return GB_OK;
+}
+static void mark_ready(gb_grid* g, cudaStream_t s) {
+    if (!g->ready && cudaEventCreateWithFlags(&g->ready, cudaEventDisableTiming) != cudaSuccess) { g->ready = nullptr; cudaStreamSynchronize(s); return; }
+    if (cudaEventRecord(g->ready, s) != cudaSuccess) cudaStreamSynchronize(s);
+}
 
 static int check_grid_args(int dtype, int ndim, const int64_t* dims, int bc, int order) {
     if (!ok_dtype(dtype)) return fail(GB_ERR_ARG, "dtype must be GB_F32 or GB_F64");
@@ -75,7 +92,7 @@ static int check_grid_args(int dtype, int ndim, const int64_t* dims, int bc, int
     if (order == GB_CUBIC && bc > GB_BC_NA) return fail(GB_ERR_UNSUPPORTED, "InterpCubic supports only BCnil/BCnan/BCna (README.md:146)");
     if (!dims) return fail(GB_ERR_ARG, "dims is NULL");
     for (int d = 0; d < ndim; d++)
-        if (dims[d] < 1 || dims[d] > (1ll << 30)) return fail(GB_ERR_ARG, "every dimension must be in [1, 2^30]");
+        if (dims[d] < 1 || dims[d] >= (1ll << 30) - 2) return fail(GB_ERR_ARG, "every dimension must be in [1, 2^30 - 3] (the reflect fold forms 2*len in 32 bits)");
     double tot = 1;
     for (int d = 0; d < ndim; d++) tot *= (double)(dims[d] + 2);
     if (tot > 2147483648.0) return fail(GB_ERR_ARG, "grids are limited to 2^31 stored elements (32-bit tap offsets)");
@@ -154,11 +171,14 @@ int gb_synth_uniform(int dtype, void* device_out, int64_t n, uint64_t seed, doub
 }
 
 // ---- prefilter ------------------------------------------------------------------------------
-int gb_invert(int dtype, int ndim, const int64_t* dims, void* data, int mem, int bc, int order, const int* dimlist,
-              int ndimlist, void* stream) {
+// interp_invert!(A, BC, IT, dimlist) in place; flags: GB_EXACT (the reference's substitution order) or GB_FAST (line-parallel
+// solver where it applies, see prefilter_fast.cu)
+int gb_invert_opt(int dtype, int ndim, const int64_t* dims, void* data, int mem, int bc, int order, const int* dimlist, int ndimlist, int flags,
+                  void* stream) {
     if (!ok_dtype(dtype)) return fail(GB_ERR_ARG, "bad dtype");
-    if (ndim < 1 || !dims || !data) return fail(GB_ERR_ARG, "bad array arguments");
+    if (ndim < 1 || ndim > MAXG || !dims || !data) return fail(GB_ERR_ARG, "bad array arguments");
     if (bc < GB_BC_NIL || bc > GB_BC_FILL || order < GB_NEAREST || order > GB_CUBIC) return fail(GB_ERR_ARG, "bad bc/order");
+    if (flags & ~GB_FAST) return fail(GB_ERR_ARG, "gb_invert_opt: flags must be GB_EXACT or GB_FAST");
     if (order < GB_QUADRATIC) return GB_OK;
     std::vector<int> all;
     if (!dimlist) {
@@ -166,24 +186,68 @@ int gb_invert(int dtype, int ndim, const int64_t* dims, void* data, int mem, int
         dimlist = all.data();
         ndimlist = ndim;
     }
+    for (int k = 0; k < ndimlist; k++)
+        if (dimlist[k] < 0 || dimlist[k] >= ndim) return fail(GB_ERR_ARG, "dimlist entry out of range");
     i64 total = 1;
     for (int d = 0; d < ndim; d++) total *= dims[d];
+    if (total == 0) return GB_OK;
     cudaStream_t s = (cudaStream_t)stream;
     pool_keep_memory();
-    if (mem == GB_DEVICE) return invert_device(dtype, ndim, (const i64*)dims, data, bc, order, dimlist, ndimlist, s);
-    void* dev = nullptr;
     const size_t bytes = (size_t)total * esize(dtype);
-    GB_CUDA(cudaMallocAsync(&dev, bytes, s));
-    GB_CUDA(cudaMemcpyAsync(dev, data, bytes, cudaMemcpyHostToDevice, s));
-    int rc = invert_device(dtype, ndim, (const i64*)dims, dev, bc, order, dimlist, ndimlist, s);
-    if (rc == GB_OK) {
-        cudaError_t e = cudaMemcpyAsync(data, dev, bytes, cudaMemcpyDeviceToHost, s);
-        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync D2H");
+    const int nflip = (flags & GB_FAST) ? fast_sweep_count(dtype, ndim, (const i64*)dims, bc, order, dimlist, ndimlist) : 0;
+    AsyncBuf dev(s), spare(s);
+    void* work = data;
+    if (mem != GB_DEVICE) {
+        GB_CUDA(dev.alloc(bytes));
+        GB_CUDA(cudaMemcpyAsync(dev.p, data, bytes, cudaMemcpyHostToDevice, s));
+        work = dev.p;
     }
-    cudaFreeAsync(dev, s);
-    cudaError_t e = cudaStreamSynchronize(s);
-    if (rc == GB_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize");
-    return rc;
+    int rc = GB_OK;
+    void* result = work;
+    if (nflip > 0) {
+        GB_CUDA(spare.alloc(bytes));
+        int in_tmp = 0;
+        rc = invert_fast_device(dtype, ndim, (const i64*)dims, work, spare.p, bc, order, dimlist, ndimlist, &in_tmp, s);
+        if (rc) return rc;
+        if (in_tmp) result = spare.p;
+    } else {
+        rc = invert_device(dtype, ndim, (const i64*)dims, work, bc, order, dimlist, ndimlist, s);
+        if (rc) return rc;
+    }
+    if (mem == GB_DEVICE) {
+        if (result != data) GB_CUDA(cudaMemcpyAsync(data, result, bytes, cudaMemcpyDeviceToDevice, s));  // odd number of ping-pong sweeps
+        return GB_OK;
+    }
+    GB_CUDA(cudaMemcpyAsync(data, result, bytes, cudaMemcpyDeviceToHost, s));
+    GB_CUDA(cudaStreamSynchronize(s));
+    return GB_OK;
+}
+int gb_invert(int dtype, int ndim, const int64_t* dims, void* data, int mem, int bc, int order, const int* dimlist,
+              int ndimlist, void* stream) {
+    return gb_invert_opt(dtype, ndim, dims, data, mem, bc, order, dimlist, ndimlist, GB_EXACT, stream);
+}
+
+// filledges!(A, val), src/utilities.jl:22-33
+int gb_filledges(int dtype, int ndim, const int64_t* dims, void* data, double val, int mem, void* stream) {
+    if (!ok_dtype(dtype) || ndim < 1 || ndim > MAXG || !dims || !data) return fail(GB_ERR_ARG, "bad arguments");
+    i64 total = 1;
+    for (int d = 0; d < ndim; d++) {
+        if (dims[d] < 0) return fail(GB_ERR_ARG, "bad dims");
+        total *= dims[d];
+    }
+    if (total == 0) return GB_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    pool_keep_memory();
+    if (mem == GB_DEVICE) return filledges_device(dtype, ndim, (const i64*)dims, data, val, s);
+    const size_t bytes = (size_t)total * esize(dtype);
+    AsyncBuf dev(s);
+    GB_CUDA(dev.alloc(bytes));
+    GB_CUDA(cudaMemcpyAsync(dev.p, data, bytes, cudaMemcpyHostToDevice, s));
+    int rc = filledges_device(dtype, ndim, (const i64*)dims, dev.p, val, s);
+    if (rc) return rc;
+    GB_CUDA(cudaMemcpyAsync(data, dev.p, bytes, cudaMemcpyDeviceToHost, s));
+    GB_CUDA(cudaStreamSynchronize(s));
+    return GB_OK;
 }
 
 int gb_pad1(int dtype, int ndim, const int64_t* dims, const void* in, double fill, void* out, int mem, void* stream) {
@@ -193,27 +257,22 @@ int gb_pad1(int dtype, int ndim, const int64_t* dims, const void* in, double fil
     if (mem == GB_DEVICE) return pad1_device(dtype, ndim, (const i64*)dims, in, fill, out, s);
     i64 it = 1, ot = 1;
     for (int d = 0; d < ndim; d++) { it *= dims[d]; ot *= dims[d] + 2; }
-    void *di = nullptr, *dout = nullptr;
-    GB_CUDA(cudaMallocAsync(&di, it * esize(dtype), s));
-    GB_CUDA(cudaMallocAsync(&dout, ot * esize(dtype), s));
-    GB_CUDA(cudaMemcpyAsync(di, in, it * esize(dtype), cudaMemcpyHostToDevice, s));
-    int rc = pad1_device(dtype, ndim, (const i64*)dims, di, fill, dout, s);
-    if (rc == GB_OK) {
-        cudaError_t e = cudaMemcpyAsync(out, dout, ot * esize(dtype), cudaMemcpyDeviceToHost, s);
-        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync D2H");
-    }
-    cudaFreeAsync(di, s);
-    cudaFreeAsync(dout, s);
-    cudaError_t e = cudaStreamSynchronize(s);
-    if (rc == GB_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize");
-    return rc;
+    AsyncBuf di(s), dout(s);
+    GB_CUDA(di.alloc(it * esize(dtype)));
+    GB_CUDA(dout.alloc(ot * esize(dtype)));
+    GB_CUDA(cudaMemcpyAsync(di.p, in, it * esize(dtype), cudaMemcpyHostToDevice, s));
+    int rc = pad1_device(dtype, ndim, (const i64*)dims, di.p, fill, dout.p, s);
+    if (rc) return rc;
+    GB_CUDA(cudaMemcpyAsync(out, dout.p, ot * esize(dtype), cudaMemcpyDeviceToHost, s));
+    GB_CUDA(cudaStreamSynchronize(s));
+    return GB_OK;
 }
 
 // ---- grid lifetime ----------------------------------------------------------------------------
 static int new_grid(gb_grid** out, int dtype, int ndim, int bc, int order, double fill) {
     gb_grid* g = new gb_grid();
     g->dtype = dtype; g->ndim = ndim; g->bc = bc; g->order = order; g->fill = fill;
-    g->coefs = nullptr; g->total = 0; g->nchan = 1; g->blocked = 0;
+    g->coefs = nullptr; g->total = 0; g->nchan = 1; g->blocked = 0; g->ready = nullptr;
     g->shift = needs_shift(bc, order) ? 1 : 0;
     for (int d = 0; d < MAXG; d++) g->user_dims[d] = g->stored_dims[d] = 1;
     if (cudaGetDevice(&g->device) != cudaSuccess) g->device = 0;
@@ -255,7 +314,7 @@ static int to_blocked_layout(gb_grid* g, cudaStream_t s) {
 // `samples`): copy (or pad by one sample per interpolated dimension, src/interp.jl:58-72), then
 // interp_invert! along the interpolated dimensions only (the README's dimlist = 1:3 usage).
 static int grid_create_impl(gb_grid** out, int dtype, int ndim, const int64_t* dims, int64_t nchan, const void* samples, int mem, int bc,
-                            int order, double fill, void* stream) {
+                            int order, double fill, int flags, void* stream) {
     if (!out || !samples) return fail(GB_ERR_ARG, "NULL argument");
     *out = nullptr;
     int rc = check_grid_args(dtype, ndim, dims, bc, order);
@@ -292,26 +351,48 @@ static int grid_create_impl(gb_grid** out, int dtype, int ndim, const int64_t* d
         delete g;
         return code;
     };
-    if (pad) {
-        if (mem == GB_HOST) {
-            e = cudaMallocAsync(&staged, (size_t)ut * (size_t)nchan * es, s);
-            if (e != cudaSuccess) return cleanup(cuda_fail(e, "cudaMallocAsync"));
-            e = cudaMemcpyAsync(staged, samples, (size_t)ut * (size_t)nchan * es, cudaMemcpyHostToDevice, s);
-            if (e != cudaSuccess) return cleanup(cuda_fail(e, "cudaMemcpyAsync H2D"));
-            src = staged;
-        }
-        for (i64 c = 0; c < nchan; c++) {
-            rc = pad1_device(dtype, ndim, (const i64*)dims, (const char*)src + (size_t)c * ut * es, padval, (char*)g->coefs + (size_t)c * st * es, s);
-            if (rc) return cleanup(rc);
-        }
-    } else {
-        e = cudaMemcpyAsync(g->coefs, samples, (size_t)ut * (size_t)nchan * es, mem == GB_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s);
-        if (e != cudaSuccess) return cleanup(cuda_fail(e, "cudaMemcpyAsync"));
-    }
     std::vector<int> all;
     for (int d = 0; d < ndim; d++) all.push_back(d);
     sd[ndim] = nchan;  // lines of every channel are solved in the same sweeps
-    rc = invert_device(dtype, nchan > 1 ? ndim + 1 : ndim, sd, g->coefs, pf_bc, order, all.data(), ndim, s);
+    const int pf_nd = nchan > 1 ? ndim + 1 : ndim;
+    // GB_FAST prefilter: its sweeps ping-pong between two arrays; start in the spare one when their number is odd, so
+    // that the result lands in g->coefs without a final copy
+    void* spare = nullptr;
+    const int nflip = (flags & GB_FAST) && order >= GB_QUADRATIC ? fast_sweep_count(dtype, pf_nd, sd, pf_bc, order, all.data(), ndim) : 0;
+    if (nflip > 0) {
+        e = cudaMallocAsync(&spare, (size_t)st * (size_t)nchan * es, s);
+        if (e != cudaSuccess) return cleanup(cuda_fail(e, "cudaMallocAsync"));
+    }
+    void* first = (nflip & 1) ? spare : g->coefs;  // where padding / the copy writes
+    auto cleanup2 = [&](int code) {
+        if (spare) cudaFreeAsync(spare, s);
+        return cleanup(code);
+    };
+    if (pad) {
+        if (mem == GB_HOST) {
+            e = cudaMallocAsync(&staged, (size_t)ut * (size_t)nchan * es, s);
+            if (e != cudaSuccess) return cleanup2(cuda_fail(e, "cudaMallocAsync"));
+            e = cudaMemcpyAsync(staged, samples, (size_t)ut * (size_t)nchan * es, cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) return cleanup2(cuda_fail(e, "cudaMemcpyAsync H2D"));
+            src = staged;
+        }
+        for (i64 c = 0; c < nchan; c++) {
+            rc = pad1_device(dtype, ndim, (const i64*)dims, (const char*)src + (size_t)c * ut * es, padval, (char*)first + (size_t)c * st * es, s);
+            if (rc) return cleanup2(rc);
+        }
+    } else {
+        e = cudaMemcpyAsync(first, samples, (size_t)ut * (size_t)nchan * es, mem == GB_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) return cleanup2(cuda_fail(e, "cudaMemcpyAsync"));
+    }
+    if (nflip > 0) {
+        int in_tmp = 0;
+        rc = invert_fast_device(dtype, pf_nd, sd, first, first == spare ? g->coefs : spare, pf_bc, order, all.data(), ndim, &in_tmp, s);
+        if (rc == GB_OK && ((in_tmp != 0) != (first == spare))) rc = fail(GB_ERR_CUDA, "internal: fast prefilter ended in the wrong buffer");
+        cudaFreeAsync(spare, s);
+        spare = nullptr;
+    } else {
+        rc = invert_device(dtype, pf_nd, sd, g->coefs, pf_bc, order, all.data(), ndim, s);
+    }
     if (rc) return cleanup(rc);
     if (nchan > 1) {  // resident layout of multi-valued grids: channel-interleaved (see interleave_device)
         void* fin = nullptr;
@@ -331,6 +412,8 @@ static int grid_create_impl(gb_grid** out, int dtype, int ndim, const int64_t* d
     if (mem == GB_HOST) {
         e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) { staged = nullptr; return cleanup(cuda_fail(e, "cudaStreamSynchronize")); }
+    } else {
+        mark_ready(g, s);
     }
     *out = g;
     return GB_OK;
@@ -372,6 +455,7 @@ static int grid_from_coefs_impl(gb_grid** out, int dtype, int ndim, const int64_
         if (tmp) cudaFreeAsync(tmp, s);
         e = (mem == GB_HOST) ? cudaStreamSynchronize(s) : cudaSuccess;
         if (rc || e != cudaSuccess) { cudaFree(g->coefs); delete g; return rc ? rc : cuda_fail(e, "copy coefs"); }
+        if (mem != GB_HOST) mark_ready(g, s);
         *out = g;
         return GB_OK;
     }
@@ -381,6 +465,8 @@ static int grid_from_coefs_impl(gb_grid** out, int dtype, int ndim, const int64_
     if (wants_blocked(g)) {
         rc = to_blocked_layout(g, s);
         if (rc) { cudaFree(g->coefs); delete g; return rc; }
+    } else if (mem != GB_HOST) {
+        mark_ready(g, s);
     }
     *out = g;
     return GB_OK;
@@ -388,7 +474,12 @@ static int grid_from_coefs_impl(gb_grid** out, int dtype, int ndim, const int64_
 
 int gb_grid_create(gb_grid** out, int dtype, int ndim, const int64_t* dims, const void* samples, int mem, int bc,
                    int order, double fill, void* stream) {
-    return grid_create_impl(out, dtype, ndim, dims, 1, samples, mem, bc, order, fill, stream);
+    return grid_create_impl(out, dtype, ndim, dims, 1, samples, mem, bc, order, fill, GB_EXACT, stream);
+}
+int gb_grid_create_opt(gb_grid** out, int dtype, int ndim, const int64_t* dims, const void* samples, int mem, int bc,
+                       int order, double fill, int flags, void* stream) {
+    if (flags & ~GB_FAST) return fail(GB_ERR_ARG, "gb_grid_create_opt: flags must be GB_EXACT or GB_FAST");
+    return grid_create_impl(out, dtype, ndim, dims, 1, samples, mem, bc, order, fill, flags, stream);
 }
 int gb_grid_create_from_coefs(gb_grid** out, int dtype, int ndim, const int64_t* stored_dims, const void* coefs, int mem,
                               int bc, int order, double fill, void* stream) {
@@ -396,7 +487,7 @@ int gb_grid_create_from_coefs(gb_grid** out, int dtype, int ndim, const int64_t*
 }
 int gb_grid_create_channels(gb_grid** out, int dtype, int ndim, const int64_t* dims, int64_t nchan, const void* samples, int mem,
                             int bc, int order, double fill, void* stream) {
-    return grid_create_impl(out, dtype, ndim, dims, nchan, samples, mem, bc, order, fill, stream);
+    return grid_create_impl(out, dtype, ndim, dims, nchan, samples, mem, bc, order, fill, GB_EXACT, stream);
 }
 int gb_grid_create_from_coefs_channels(gb_grid** out, int dtype, int ndim, const int64_t* stored_dims, int64_t nchan, const void* coefs,
                                        int mem, int bc, int order, double fill, int raw_coords, void* stream) {
@@ -433,6 +524,8 @@ int gb_grid_coefs_copy(const gb_grid* g, void* device_out, void* stream) {
     if (!g || !device_out) return fail(GB_ERR_ARG, "NULL argument");
     cudaStream_t s = (cudaStream_t)stream;
     const size_t bytes = (size_t)g->total * (size_t)g->nchan * esize(g->dtype);
+    int rcw = wait_ready(g, s);
+    if (rcw) return rcw;
     if (g->blocked) return blocked_device(g->dtype, g->ndim, g->stored_dims, g->coefs, device_out, 0, s);
     if (g->nchan > 1) return interleave_device(g->dtype, g->coefs, device_out, g->total, g->nchan, 0, s);
     GB_CUDA(cudaMemcpyAsync(device_out, g->coefs, bytes, cudaMemcpyDeviceToDevice, s));
@@ -451,12 +544,16 @@ int gb_grid_coefs_download(const gb_grid* g, void* host_out) {
         if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy D2H");
         return GB_OK;
     }
-    GB_CUDA(cudaMemcpy(host_out, g->coefs, bytes, cudaMemcpyDeviceToHost));
+    int rcw = wait_ready(g, nullptr);
+    if (rcw) return rcw;
+    GB_CUDA(cudaMemcpyAsync(host_out, g->coefs, bytes, cudaMemcpyDeviceToHost, nullptr));
+    GB_CUDA(cudaStreamSynchronize(nullptr));
     return GB_OK;
 }
 int gb_grid_destroy(gb_grid* g) {
     if (!g) return GB_OK;
     cudaFree(g->coefs);
+    if (g->ready) cudaEventDestroy(g->ready);
     delete g;
     return GB_OK;
 }
@@ -673,6 +770,7 @@ int eval_host(const gb_grid* g, int out_mask, int outmode, i64 nq, const void* c
     for (int i = 0; i < nslot && rc == GB_OK; i++) {
         Slot& sl = slots[i];
         if (!cu(cudaStreamCreateWithFlags(&sl.s, cudaStreamNonBlocking), "cudaStreamCreate")) break;
+        if (g->ready) cu(cudaStreamWaitEvent(sl.s, g->ready, 0), "cudaStreamWaitEvent");  // a grid built on another stream
         cu(cudaMallocAsync(&sl.x, (size_t)chunk * N * xs, sl.s), "cudaMallocAsync");
         if (out_mask & GB_OUT_VAL) cu(cudaMallocAsync(&sl.v, (size_t)chunk * es, sl.s), "cudaMallocAsync");
         if (out_mask & GB_OUT_GRAD) cu(cudaMallocAsync(&sl.gr, (size_t)chunk * N * es, sl.s), "cudaMallocAsync");
@@ -739,6 +837,10 @@ int eval_device(const gb_grid* g, int outmode, i64 nq, const void* const* xp, i6
     call.nq = nq; call.q0 = 0; call.xqs = xqs;
     for (int d = 0; d < g->ndim; d++) call.xp[d] = xp[d];
     call.val = val; call.grad = grad; call.hess = hess;
+    {
+        const int rcw = wait_ready(g, s);
+        if (rcw) return rcw;
+    }
     u64* d_bad = nullptr;
     const bool check = first_invalid && g->bc == GB_BC_NIL;
     if (check) {
@@ -847,6 +949,8 @@ int gb_eval_outer(const gb_grid* g, const int64_t* lens, const void* const* vecs
     DeviceGuard guard(g->device);
     pool_keep_memory();
     cudaStream_t s = (cudaStream_t)stream;
+    rc = wait_ready(g, s);
+    if (rc) return rc;
     const size_t xs = esize(xdtype), es = esize(g->dtype) * (size_t)g->nchan;
     // device copies of the vectors (host mode), the pointer table, lens, the expanded columns
     void* dvec[MAXG] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -1001,20 +1105,15 @@ int gb_prolong_size(int64_t n, int64_t len, int64_t* newlen) {
 
 static int mg_host(int dtype, i64 in_elems, i64 out_elems, const void* in, void* out, cudaStream_t s,
                    int (*run)(void*, const void*, void*, cudaStream_t), void* ctx) {
-    void *di = nullptr, *dout = nullptr;
-    GB_CUDA(cudaMallocAsync(&di, std::max<size_t>(1, in_elems * esize(dtype)), s));
-    GB_CUDA(cudaMallocAsync(&dout, std::max<size_t>(1, out_elems * esize(dtype)), s));
-    GB_CUDA(cudaMemcpyAsync(di, in, in_elems * esize(dtype), cudaMemcpyHostToDevice, s));
-    int rc = run(ctx, di, dout, s);
-    if (rc == GB_OK) {
-        cudaError_t e = cudaMemcpyAsync(out, dout, out_elems * esize(dtype), cudaMemcpyDeviceToHost, s);
-        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync D2H");
-    }
-    cudaFreeAsync(di, s);
-    cudaFreeAsync(dout, s);
-    cudaError_t e = cudaStreamSynchronize(s);
-    if (rc == GB_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize");
-    return rc;
+    AsyncBuf di(s), dout(s);
+    GB_CUDA(di.alloc(in_elems * esize(dtype)));
+    GB_CUDA(dout.alloc(out_elems * esize(dtype)));
+    GB_CUDA(cudaMemcpyAsync(di.p, in, in_elems * esize(dtype), cudaMemcpyHostToDevice, s));
+    int rc = run(ctx, di.p, dout.p, s);
+    if (rc) return rc;
+    GB_CUDA(cudaMemcpyAsync(out, dout.p, out_elems * esize(dtype), cudaMemcpyDeviceToHost, s));
+    GB_CUDA(cudaStreamSynchronize(s));
+    return GB_OK;
 }
 
 int gb_restrict(int dtype, int ndim, const int64_t* dims, const void* in, int dim, double scale, void* out, int mem, void* stream) {

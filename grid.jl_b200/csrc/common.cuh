@@ -41,10 +41,24 @@ int cuda_fail(cudaError_t e, const char* what);
         if (_e != cudaSuccess) return gb::cuda_fail(_e, #expr);    \
     } while (0)
 
+// stream-ordered scratch released on every exit path (cudaFreeAsync on the stream it was allocated on)
+struct AsyncBuf {
+    void* p = nullptr;
+    cudaStream_t s;
+    explicit AsyncBuf(cudaStream_t s_) : s(s_) {}
+    AsyncBuf(const AsyncBuf&) = delete;
+    AsyncBuf& operator=(const AsyncBuf&) = delete;
+    ~AsyncBuf() {
+        if (p) cudaFreeAsync(p, s);
+    }
+    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 1, s); }
+};
+
 extern std::atomic<long long> g_launches;
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int num_sms();
 void prof_mark(int stage_boundary, cudaStream_t s);
+void prof_mode(const unsigned int* nwork, cudaStream_t s);  // records which path (sorted / grouped) the tiled call took
 int prof_enable(int on);
 int prof_read(double* ms, int n, int* nstages);  // eval_tile.cu: records boundary event i (0..6) when profiling is on
 
@@ -77,11 +91,20 @@ template <typename T> __device__ __forceinline__ T exact_div(T a, T d, T rd) {
 // fixed leading tile extents (cells), so that brick strides are compile-time constants; the extent
 // along the LAST dimension is chosen at run time (choose_tile): N=1 -, N=2 64, N=3 16x16, N=4 8x8x8
 __host__ __device__ constexpr int brick_tile(int N, int d) { return N == 2 ? 64 : N == 3 ? 16 : 8; }
-__host__ __device__ constexpr int brick_stride(int N, int L, int d) {
+// extent of the brick along dimension e (tile + L-1 halo cells); the contiguous dimension is padded to a multiple of 16 bytes
+// (esz = element size) so that a brick row is a legal TMA box row (cp.async.bulk.tensor: boxDim[0]*esz % 16 == 0)
+__host__ __device__ constexpr int brick_extent(int N, int L, int e, int esz) {
+    const int f = brick_tile(N, e) + L - 1, q = 16 / esz;
+    return e == 0 ? (f + q - 1) / q * q : f;
+}
+__host__ __device__ constexpr int brick_stride(int N, int L, int d, int esz) {
     int s = 1;
-    for (int e = 0; e < d; e++) s *= brick_tile(N, e) + L - 1;
+    for (int e = 0; e < d; e++) s *= brick_extent(N, L, e, esz);
     return s;
 }
+// the brick (tiled) path is compiled for the neighbourhoods heavy enough for it ever to win (launch_one's heuristic needs
+// >= 256 B of taps per query; GB_TILED on anything else silently takes the plain path -- scheduling only, same results)
+__host__ __device__ constexpr bool brick_compiled(int N, int order) { return (N == 2 || N == 3) && order >= GB_QUADRATIC; }
 
 // ---- evaluation launch interface (eval_inst.cu, one translation unit per (T, N, order)) ---------
 template <int N> struct EvalParams {
@@ -109,8 +132,10 @@ template <int N> struct EvalParams {
     int aos;              // != 0: outputs are records of `aos` words per sorted slot at `val`
     int tile[N];          // cells per tile
     int ntile[N];         // tiles per dimension
-    const u32* work;      // 3 words per work item: tile, first sorted slot, one past the last
-    const u32* nwork;     // device: [0] number of work items, [1] the ticket counter CTAs pull items from
+    const u32* work;      // 4 words per work item: tile, first slot, one past the last, -
+    const u32* nwork;     // device: [0] number of work items, [1] the ticket counter CTAs pull items from, [2] mode: 1 = the batch
+                          // arrived grouped by tile and the items index the CALLER's arrays (no permutation), 0 = sorted slots
+    int use_tma;          // bricks are staged by cp.async.bulk.tensor through the kernel's tensor map (else element-wise cp.async)
 };
 
 // One entry per (dtype, N, order) -- eval_inst.cu; each dispatches on (bc family, output mode, flags).
@@ -145,7 +170,14 @@ int launch_eval_generic(const GenericParams& p, int dtype, cudaStream_t s);
 // ---- prefilter (prefilter.cu) -------------------------------------------------------------------
 int invert_device(int dtype, int ndim, const i64* dims, void* data, int bc, int order, const int* dimlist, int ndl,
                   cudaStream_t s);
+// GB_FAST prefilter (prefilter_fast.cu): sweeps ping-pong between `data` and `tmp` (same size); *in_tmp tells where the
+// result ended up.  Sweeps the fast solver does not take (short lines, many lines, TMA-ineligible pitch) run the exact
+// in-place kernels on the current buffer.
+int invert_fast_device(int dtype, int ndim, const i64* dims, void* data, void* tmp, int bc, int order, const int* dimlist, int ndl, int* in_tmp, cudaStream_t s);
+int fast_sweep_count(int dtype, int ndim, const i64* dims, int bc, int order, const int* dimlist, int ndl);  // sweeps that will flip buffers
+int invert_sweep_exact(int dtype, int ndim, const i64* dims, void* data, int bc, int order, int idim, cudaStream_t s);
 int pad1_device(int dtype, int ndim, const i64* dims, const void* in, double fill, void* out, cudaStream_t s);
+int filledges_device(int dtype, int ndim, const i64* dims, void* data, double val, cudaStream_t s);
 
 // ---- restrict / prolong (multigrid.cu) ------------------------------------------------------------
 int restrict_device(int dtype, int ndim, const i64* dims, const void* in, int dim, double scale, void* out, cudaStream_t s);

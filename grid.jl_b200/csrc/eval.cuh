@@ -20,8 +20,11 @@
 // plus the separable tensor-product path (outer_table_kernel / outer_eval_kernel).
 // Compiled with -fmad=false: plain * and + never fuse.
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only; the encoder is resolved through cudaGetDriverEntryPoint)
+
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -300,7 +303,7 @@ template <typename T, int N, int L, bool GUARD> struct GlobalTaps {
 
 template <typename T, int N, int L> struct BrickTaps {
     const T* b;  // brick + offset of the query's first tap
-    template <int D> __device__ __forceinline__ u32 step(u32 cur, int i) const { return cur + (u32)(i * brick_stride(N, L, D)); }
+    template <int D> __device__ __forceinline__ u32 step(u32 cur, int i) const { return cur + (u32)(i * brick_stride(N, L, D, (int)sizeof(T))); }
     __device__ __forceinline__ T load(u32 j) const { return b[j]; }
 };
 
@@ -825,31 +828,44 @@ __global__ void __launch_bounds__(EVAL_BLOCK, 2) eval_kernel(const EvalParams<N>
 }
 
 // ====================================================================================================
-// Tiled ("brick") evaluation: the batch is counting-sorted by grid tile, then evaluated tile by tile
-// out of shared memory.
+// Tiled ("brick") evaluation: the batch is grouped by grid tile, then evaluated tile by tile out of
+// shared memory.
 //   tile_hist      key of every query (tile of its lowest tap per dimension) + per-CTA histograms in
-//                  shared memory (no global atomics), written bin-major to bh[bin][cta]
+//                  shared memory (no global atomics), written bin-major to bh[bin][cta].  The same pass
+//                  marks RUN STARTS in a bitmap (a query whose key differs from its predecessor's, and every
+//                  2048th query) and counts them.
+//   sorted_decide  (eval_tile.cu) few run starts = the batch arrived grouped by tile (coherent callers: points
+//                  binned once, Morton / tile-sorted streams).  Then the runs themselves are the work items
+//                  (run_items), they index the CALLER's arrays, and nothing is permuted: the brick kernel reads
+//                  the coordinates and writes val / grad / hess in place, coalesced.  The decision is taken on
+//                  the device (nwork[2]); the kernels of the path not taken exit at once, so the host never
+//                  waits for it.
+//   otherwise      a counting sort:
 //   tile_offsets   (eval_tile.cu) per-bin totals, scan, work-item list (a tile's queries split into
 //                  items of <= EVAL_CHUNK), per-(bin,cta) write cursors
 //   tile_scatter   each CTA replays its slice and writes one RECORD per query at its sorted slot:
 //                  the N index coordinates (already in T, affine map and setx shift applied) and the
 //                  query's original index -- (N+1) words of T, a full 32-byte sector for f64 N=3
 //   eval_brick     CTAs pull work items from an atomic counter.  The tile's coefficient brick
-//                  (tile + L-1 halo) is staged with cp.async into one of two shared-memory buffers
-//                  while the previous item is being evaluated; records are read coalesced (the first
+//                  (tile + L-1 halo) is staged into one of two shared-memory buffers while the previous item is
+//                  being evaluated -- by ONE cp.async.bulk.tensor (TMA) per brick, completion on an mbarrier,
+//                  cells past the array zero-filled by the TMA unit; grids whose row pitch is not a multiple of
+//                  16 bytes fall back to element-wise cp.async.  Records are read coalesced (the first
 //                  record of the next item is prefetched across the item boundary); every tap is an
 //                  LDS at a compile-time offset from the query's first tap; outputs go to the
-//                  query's original position.
+//                  query's sorted slot (or, grouped batches, to its own position).
 //   eval_deferred  a query whose taps are not L consecutive cells inside the brick (wrapped /
 //                  repeated taps at the grid boundary, taps past the last sample, invalid location)
 //                  or that met a NaN/Inf coefficient is not evaluated by eval_brick: its slot goes
 //                  to a list and this kernel runs the global-memory path (eval_one) on the list, so
 //                  no boundary condition needs special bricks and results are bit-identical to plain.
+//   unpermute      sorted slots -> the caller's order and arrays
 constexpr int BRICK_BLOCK = 256;
 constexpr u32 EVAL_CHUNK = 2048;  // queries per work item
 constexpr int SORT_BLOCK = 256;
 constexpr int SORT_UNROLL = 4;    // queries in flight per thread in the two sort passes
 constexpr int PASS1_UNROLL = 4;   // records in flight per thread in the brick kernel's locate pass
+constexpr i64 SORT_ITER = (i64)SORT_BLOCK * SORT_UNROLL;  // queries a sort CTA handles per iteration; per-CTA slices are multiples of it
 
 template <typename T> __device__ __forceinline__ T bits_to(u32 q);
 template <> __device__ __forceinline__ double bits_to<double>(u32 q) { return __longlong_as_double((long long)q); }
@@ -894,6 +910,16 @@ template <typename T, int N> __device__ __forceinline__ void load_record(const T
         q = bits_of(__ldg(r + N));
     }
 }
+// One query of a work item.  DIRECT (grouped batches): slot j IS the query's index in the caller's batch, the
+// coordinates come from the caller's array; otherwise from the sorted record.
+template <typename T, int N, bool DIRECT> __device__ __forceinline__ void fetch_query(const EvalParams<N>& p, const T* __restrict__ rec, u32 j, T (&x)[N], u32& q) {
+    if constexpr (DIRECT) {
+        load_index_coords<T, N>(p, (i64)j, x);
+        q = j;
+    } else {
+        load_record<T, N>(rec, j, x, q);
+    }
+}
 
 // sort key of a query: the tile of its lowest tap per dimension (a locality hint only -- queries whose taps
 // leave the brick are deferred); invalid locations go to the extra last bin
@@ -915,10 +941,43 @@ __device__ __forceinline__ u32 tile_key(const EvalParams<N>& p, const T (&x)[N],
     return valid ? key : (u32)ntot;
 }
 
+// Run starts of one iteration of a sort CTA (thread t holds the keys of queries qb + u*SORT_BLOCK, u < SORT_UNROLL;
+// inactive slots carry key 0xffffffff).  A query starts a run when its key differs from its predecessor's or its index is
+// a multiple of EVAL_CHUNK (items are at most that long).  The 32 queries of a warp and slot u are one bitmap word.
+// All threads of the CTA call together; returns the number of run starts this WARP marked (lane 0 only).
+struct RunMarkSmem { u32 edge[SORT_UNROLL][SORT_BLOCK / 32]; u32 prev; };
+__device__ __forceinline__ u32 mark_runs(const u32 (&key)[SORT_UNROLL], i64 qb, i64 q1, RunMarkSmem& sm, u32* __restrict__ bitmap) {
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int u = 0; u < SORT_UNROLL; u++)
+        if (lane == 31) sm.edge[u][warp] = key[u];
+    __syncthreads();
+    u32 nb = 0;
+#pragma unroll
+    for (int u = 0; u < SORT_UNROLL; u++) {
+        u32 prev = __shfl_up_sync(0xffffffffu, key[u], 1);
+        if (lane == 0) prev = warp > 0 ? sm.edge[u][warp - 1] : (u > 0 ? sm.edge[u - 1][SORT_BLOCK / 32 - 1] : sm.prev);
+        const i64 q = qb + (i64)u * SORT_BLOCK;
+        const bool brk = q < q1 && (prev != key[u] || (q & (i64)(EVAL_CHUNK - 1)) == 0);
+        const u32 word = __ballot_sync(0xffffffffu, brk);
+        if (lane == 0 && q < q1) {
+            bitmap[q >> 5] = word;
+            nb += (u32)__popc(word);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == SORT_BLOCK - 1) sm.prev = key[SORT_UNROLL - 1];
+    return nb;
+}
+
 template <typename T, int N, int ORDER, int BCF>
-__global__ void __launch_bounds__(SORT_BLOCK) tile_hist_kernel(const EvalParams<N> p, u32* __restrict__ bh, u32 nbins, i64 per_cta) {
+__global__ void __launch_bounds__(SORT_BLOCK) tile_hist_kernel(const EvalParams<N> p, u32* __restrict__ bh, u32 nbins, i64 per_cta, u32* __restrict__ bitmap,
+                                                               u32* __restrict__ runcnt) {
     extern __shared__ u32 s_hist[];
+    __shared__ RunMarkSmem s_rm;
+    __shared__ u32 s_nb;
     for (u32 b = threadIdx.x; b < nbins; b += SORT_BLOCK) s_hist[b] = 0;
+    if (threadIdx.x == 0) { s_rm.prev = 0xfffffffeu; s_nb = 0; }  // no predecessor: the CTA's first query starts a run
     __syncthreads();
     int ntot = 1;
 #pragma unroll
@@ -928,7 +987,9 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_hist_kernel(const EvalParams<
     for (int d = 0; d < N; d++) shift[d] = __ffs(p.tile[d]) - 1;
     const i64 q0 = (i64)blockIdx.x * per_cta;
     const i64 q1 = q0 + per_cta < p.nq ? q0 + per_cta : p.nq;
-    for (i64 qb = q0 + threadIdx.x; qb < q1; qb += SORT_BLOCK * SORT_UNROLL) {
+    u32 nb = 0;
+    for (i64 qb0 = q0; qb0 < q1; qb0 += SORT_ITER) {  // (uniform trip count: mark_runs is a CTA-wide call)
+        const i64 qb = qb0 + threadIdx.x;
         double raw[SORT_UNROLL][N];
 #pragma unroll
         for (int u = 0; u < SORT_UNROLL; u++) {
@@ -938,25 +999,90 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_hist_kernel(const EvalParams<
                 for (int d = 0; d < N; d++) raw[u][d] = load_raw<N>(p, d, q);
             }
         }
+        u32 key[SORT_UNROLL];
 #pragma unroll
         for (int u = 0; u < SORT_UNROLL; u++) {
             const i64 q = qb + u * SORT_BLOCK;
+            key[u] = 0xffffffffu;
             if (q < q1) {
                 T x[N];
 #pragma unroll
                 for (int d = 0; d < N; d++) x[d] = index_coord<T, N>(p, d, raw[u][d]);
-                atomicAdd(s_hist + tile_key<T, N, ORDER, BCF>(p, x, shift, ntot), 1u);
+                key[u] = tile_key<T, N, ORDER, BCF>(p, x, shift, ntot);
+                atomicAdd(s_hist + key[u], 1u);
             }
         }
+        nb += mark_runs(key, qb, q1, s_rm, bitmap);
     }
+    if (nb) atomicAdd(&s_nb, nb);
     __syncthreads();
     for (u32 b = threadIdx.x; b < nbins; b += SORT_BLOCK) bh[(size_t)b * gridDim.x + blockIdx.x] = s_hist[b];
+    if (threadIdx.x == 0) runcnt[blockIdx.x] = s_nb;
+}
+
+// Grouped batches: the runs marked in the bitmap become the work items {tile, first query, one past the last, -}.
+// Same CTA partition as tile_hist (per_cta is a multiple of SORT_ITER, so a CTA owns whole bitmap words); base[cta] =
+// number of runs in the CTAs before it (sorted_decide).
+template <typename T, int N, int ORDER, int BCF>
+__global__ void __launch_bounds__(SORT_BLOCK) run_items_kernel(const EvalParams<N> p, const u32* __restrict__ bitmap, const u32* __restrict__ base,
+                                                               u32* __restrict__ work, const u32* __restrict__ nwork, i64 per_cta) {
+    if (nwork[2] == 0) return;
+    __shared__ u32 s_w[SORT_BLOCK / 32], s_carry;
+    int ntot = 1, shift[N];
+#pragma unroll
+    for (int d = 0; d < N; d++) { ntot *= p.ntile[d]; shift[d] = __ffs(p.tile[d]) - 1; }
+    const i64 q0 = (i64)blockIdx.x * per_cta;
+    const i64 q1 = q0 + per_cta < p.nq ? q0 + per_cta : p.nq;
+    if (q0 >= q1) return;
+    const i64 w0 = q0 >> 5, w1 = (q1 + 31) >> 5, wall = (p.nq + 31) >> 5;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = base[blockIdx.x];
+    __syncthreads();
+    for (i64 wb = w0; wb < w1; wb += SORT_BLOCK) {
+        const i64 w = wb + threadIdx.x;
+        const u32 bits = w < w1 ? bitmap[w] : 0u;
+        const u32 cnt = (u32)__popc(bits);
+        u32 incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += t;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        u32 before = s_carry;
+        for (u32 k = 0; k < warp; k++) before += s_w[k];
+        u32 rank = before + incl - cnt;
+        u32 rest = bits;
+        while (rest) {
+            const int b = __ffs(rest) - 1;
+            rest &= rest - 1;
+            const i64 q = (w << 5) + b;
+            // end of the run: the next marked query (at most EVAL_CHUNK ahead), else the end of the batch
+            i64 e = p.nq;
+            if (rest) e = (w << 5) + (__ffs(rest) - 1);
+            else {
+                for (i64 v = w + 1; v < wall; v++) {
+                    const u32 nb = bitmap[v];
+                    if (nb) { e = (v << 5) + (__ffs(nb) - 1); break; }
+                }
+            }
+            T x[N];
+            load_index_coords<T, N>(p, q, x);
+            reinterpret_cast<uint4*>(work)[rank] = make_uint4(tile_key<T, N, ORDER, BCF>(p, x, shift, ntot), (u32)q, (u32)e, 0u);
+            rank++;
+        }
+        __syncthreads();
+        if (threadIdx.x == SORT_BLOCK - 1) s_carry = before + incl;
+        __syncthreads();
+    }
 }
 
 // (the key is recomputed rather than carried over from tile_hist: this kernel waits on memory, the arithmetic is free)
 template <typename T, int N, int ORDER, int BCF>
 __global__ void __launch_bounds__(SORT_BLOCK) tile_scatter_kernel(const EvalParams<N> p, const u32* __restrict__ boff, T* __restrict__ rec,
                                                                   u32* __restrict__ inv, u32 nbins, i64 per_cta) {
+    if (p.nwork[2] != 0) return;  // grouped batch: nothing to permute
     extern __shared__ u32 s_cur[];
     for (u32 b = threadIdx.x; b < nbins; b += SORT_BLOCK) s_cur[b] = boff[(size_t)b * gridDim.x + blockIdx.x];
     __syncthreads();
@@ -965,7 +1091,7 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_scatter_kernel(const EvalPara
     for (int d = 0; d < N; d++) { ntot *= p.ntile[d]; shift[d] = __ffs(p.tile[d]) - 1; }
     const i64 q0 = (i64)blockIdx.x * per_cta;
     const i64 q1 = q0 + per_cta < p.nq ? q0 + per_cta : p.nq;
-    for (i64 qb = q0 + threadIdx.x; qb < q1; qb += SORT_BLOCK * SORT_UNROLL) {
+    for (i64 qb = q0 + threadIdx.x; qb < q1; qb += SORT_ITER) {
         double raw[SORT_UNROLL][N];
 #pragma unroll
         for (int u = 0; u < SORT_UNROLL; u++) {
@@ -994,17 +1120,26 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_scatter_kernel(const EvalPara
 // 512^3 f64: 7.1e4 tiles): one histogram / cursor array in global memory, updated with warp-aggregated atomics
 // (lanes of a warp that hit the same tile share one atomic, so a clustered batch does not serialise on one
 // address).  The order of the records inside a tile then depends on scheduling; results do not (every query is
-// evaluated on its own and returned to its own position).
+// evaluated on its own and returned to its own position).  The counting pass marks the run starts like tile_hist.
 template <typename T, int N, int ORDER, int BCF, bool SCATTER>
 __global__ void __launch_bounds__(SORT_BLOCK) tile_sort_global_kernel(const EvalParams<N> p, u32* __restrict__ bins, T* __restrict__ rec, u32* __restrict__ inv,
-                                                                      i64 per_cta) {
+                                                                      i64 per_cta, u32* __restrict__ bitmap, u32* __restrict__ runcnt) {
+    __shared__ RunMarkSmem s_rm;
+    __shared__ u32 s_nb;
+    if constexpr (SCATTER) {
+        if (p.nwork[2] != 0) return;
+    } else {
+        if (threadIdx.x == 0) { s_rm.prev = 0xfffffffeu; s_nb = 0; }
+        __syncthreads();
+    }
     int ntot = 1, shift[N];
 #pragma unroll
     for (int d = 0; d < N; d++) { ntot *= p.ntile[d]; shift[d] = __ffs(p.tile[d]) - 1; }
     const i64 q0 = (i64)blockIdx.x * per_cta;
     const i64 q1 = q0 + per_cta < p.nq ? q0 + per_cta : p.nq;
     const u32 lane = threadIdx.x & 31;
-    for (i64 qb0 = q0; qb0 < q1; qb0 += SORT_BLOCK * SORT_UNROLL) {  // (uniform trip count: the warp votes below need every lane)
+    u32 nb = 0;
+    for (i64 qb0 = q0; qb0 < q1; qb0 += SORT_ITER) {  // (uniform trip count: the warp votes below need every lane)
         const i64 qb = qb0 + threadIdx.x;
         double raw[SORT_UNROLL][N];
 #pragma unroll
@@ -1015,6 +1150,7 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_sort_global_kernel(const Eval
                 for (int d = 0; d < N; d++) raw[u][d] = load_raw<N>(p, d, q);
             }
         }
+        u32 keys[SORT_UNROLL];
 #pragma unroll
         for (int u = 0; u < SORT_UNROLL; u++) {
             const i64 q = qb + u * SORT_BLOCK;
@@ -1026,6 +1162,7 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_sort_global_kernel(const Eval
                 for (int d = 0; d < N; d++) x[d] = index_coord<T, N>(p, d, raw[u][d]);
                 key = tile_key<T, N, ORDER, BCF>(p, x, shift, ntot);
             }
+            keys[u] = key;
             const u32 peers = __match_any_sync(0xffffffffu, key);
             const u32 leader = __ffs(peers) - 1;
             u32 base = 0;
@@ -1039,11 +1176,53 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_sort_global_kernel(const Eval
                 }
             }
         }
+        if constexpr (!SCATTER) nb += mark_runs(keys, qb, q1, s_rm, bitmap);
+    }
+    if constexpr (!SCATTER) {
+        if (nb) atomicAdd(&s_nb, nb);
+        __syncthreads();
+        if (threadIdx.x == 0) runcnt[blockIdx.x] = s_nb;
     }
 }
 
-// ---- cp.async (Ampere-style async copies are the right granule here: brick rows are short and
-// arbitrarily aligned, so elements travel one by one; zero-fill handles cells past the array) ---------
+// ---- brick staging --------------------------------------------------------------------------------------------------
+// TMA: one cp.async.bulk.tensor per brick, issued by one thread; the box is the whole brick (its contiguous extent
+// padded to 16 bytes, brick_extent), cells past the array are zero-filled by the TMA unit, completion is counted in
+// bytes on an mbarrier.  Fallback for grids whose row pitch is not a multiple of 16 bytes (TMA's stride rule):
+// Ampere-style element-wise cp.async with zero-fill.
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((u32)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((u32)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+    const u32 a = (u32)__cvta_generic_to_shared(bar);
+    u32 done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+template <int N> __device__ __forceinline__ void tma_load_brick(const CUtensorMap* tmap, void* dst, u64* bar, const int (&lo)[N]) {
+    const u32 d = (u32)__cvta_generic_to_shared(dst), b = (u32)__cvta_generic_to_shared(bar);
+    if constexpr (N == 2) {
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(d), "l"(tmap), "r"(b),
+                     "r"(lo[0]), "r"(lo[1])
+                     : "memory");
+    } else {
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(d), "l"(tmap),
+                     "r"(b), "r"(lo[0]), "r"(lo[1]), "r"(lo[2])
+                     : "memory");
+    }
+}
 template <int BYTES> __device__ __forceinline__ void cp_async_zfill(u32 saddr, const void* g, bool pred) {
     const int sz = pred ? BYTES : 0;
     asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(saddr), "l"(g), "n"(BYTES), "r"(sz) : "memory");
@@ -1062,6 +1241,7 @@ template <int N, int L> __device__ __forceinline__ void brick_geo(const EvalPara
         clip[d] = full < left ? full : left;
     }
 }
+// element-wise staging (vol = padded brick volume; padding cells are zero-filled like cells past the array)
 template <typename T, int N, int L> __device__ __forceinline__ void brick_fill(const EvalParams<N>& p, const T* __restrict__ A, T* brick, u32 tile, int vol) {
     int lo[N], clip[N];
     brick_geo<N, L>(p, tile, lo, clip);
@@ -1073,7 +1253,7 @@ template <typename T, int N, int L> __device__ __forceinline__ void brick_fill(c
         bool inside = true;
 #pragma unroll
         for (int d = 0; d < N - 1; d++) {
-            const int F = brick_tile(N, d) + L - 1;  // a constant after unrolling
+            const int F = brick_extent(N, L, d, (int)sizeof(T));  // a constant after unrolling
             const int rd = r % F;
             r /= F;
             inside = inside && rd < clip[d];
@@ -1082,6 +1262,20 @@ template <typename T, int N, int L> __device__ __forceinline__ void brick_fill(c
         inside = inside && r < clip[N - 1];
         g += (u32)(lo[N - 1] + r) * (u32)p.stride[N - 1];
         cp_async_zfill<(int)sizeof(T)>(sbase + (u32)e * (u32)sizeof(T), inside ? (const void*)(A + g) : (const void*)A, inside);
+    }
+}
+// stage the brick of `tile` into `dst` (either mechanism); every thread calls
+template <typename T, int N, int L>
+__device__ __forceinline__ void stage_brick(const EvalParams<N>& p, const CUtensorMap* tmap, const T* __restrict__ A, T* dst, u64* bar, u32 tile, int vol) {
+    if (p.use_tma) {
+        if (threadIdx.x == 0) {
+            int lo[N], clip[N];
+            brick_geo<N, L>(p, tile, lo, clip);
+            mbar_expect_tx(bar, (u32)vol * (u32)sizeof(T));
+            tma_load_brick<N>(tmap, dst, bar, lo);
+        }
+    } else {
+        brick_fill<T, N, L>(p, A, dst, tile, vol);
     }
 }
 
@@ -1113,11 +1307,11 @@ __device__ __forceinline__ u32 brick_locate(const EvalParams<N>& p, const T (&x)
         ok = ok && rel >= 0 && rel + L <= clip[d];
 #pragma unroll
         for (int i = 1; i < L; i++) ok = ok && c[d][i] == c[d][0] + i;
-        boff += (u32)rel * (u32)brick_stride(N, L, d);
+        boff += (u32)rel * (u32)brick_stride(N, L, d, (int)sizeof(T));
     }
     return ok ? boff : BRICK_DEFER;
 }
-// one located query out of the brick: weights, contraction, outputs to sorted slot j
+// one located query out of the brick: weights, contraction, outputs to slot j
 template <typename T, int N, int ORDER, int BCF, int OUTMODE, bool FAST>
 __device__ __forceinline__ void brick_eval_one(const EvalParams<N>& p, const T (&dx)[N], const i64 q, const u32 j, const T* brick, const u32 boff,
                                                u32* __restrict__ defer) {
@@ -1137,15 +1331,16 @@ __device__ __forceinline__ void brick_eval_one(const EvalParams<N>& p, const T (
     store_outputs<T, N, OUTMODE>(p, (i64)j, q, true, acc);
 }
 
-// the deferred queries: plain evaluation (eval_one) of the records whose slots are listed
-template <typename T, int N, int ORDER, int BCF, int OUTMODE, bool FAST>
+// the deferred queries: plain evaluation (eval_one) of the slots listed
+template <typename T, int N, int ORDER, int BCF, int OUTMODE, bool FAST, bool DIRECT>
 __global__ void __launch_bounds__(EVAL_BLOCK, 2) eval_deferred_kernel(const EvalParams<N> p, const T* __restrict__ rec, const u32* __restrict__ defer) {
+    if ((p.nwork[2] != 0) != DIRECT) return;
     const u32 n = defer[0];
     for (u32 i = blockIdx.x * EVAL_BLOCK + threadIdx.x; i < n; i += gridDim.x * EVAL_BLOCK) {
         T x[N];
         u32 q;
         const u32 j = defer[1 + i];
-        load_record<T, N>(rec, j, x, q);
+        fetch_query<T, N, DIRECT>(p, rec, j, x, q);
         eval_one<T, N, ORDER, BCF, OUTMODE, FAST>(p, x, (i64)j, (i64)q);
     }
 }
@@ -1159,21 +1354,24 @@ __global__ void __launch_bounds__(EVAL_BLOCK, 2) eval_deferred_kernel(const Eval
 // over the item with shared-memory counters); class c is served by the 16 threads t = c (mod 16).
 // Classes are never equally full: each thread runs T = ceil(n/256) rounds, and a thread whose class
 // runs dry pulls from the overflow of fuller classes (those few loads may conflict).
-template <typename T, int N, int ORDER, int BCF, int OUTMODE, bool FAST>
-__global__ void __launch_bounds__(BRICK_BLOCK, 2) eval_brick_kernel(const EvalParams<N> p, const T* __restrict__ rec, u32* __restrict__ defer) {
+template <typename T, int N, int ORDER, int BCF, int OUTMODE, bool FAST, bool DIRECT>
+__global__ void __launch_bounds__(BRICK_BLOCK, 2)
+    eval_brick_kernel(const EvalParams<N> p, const T* __restrict__ rec, u32* __restrict__ defer, const __grid_constant__ CUtensorMap tmap) {
     constexpr int L = ORDER + 1;
     // Bank-class binning pays where the shared-memory pipe is the limiter (FAST: 64 loads per ~270
     // FP64 operations); EXACT is bound by the FP64 pipe (816 dependent multiply/add per query) and
     // keeps the direct schedule, which has fewer barriers per item.
     constexpr bool BINNED = FAST;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if ((p.nwork[2] != 0) != DIRECT) return;  // the other variant of this kernel serves this batch (sorted_decide)
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) u64 s_bar[2];
     __shared__ u32 s_it[2];
     __shared__ u32 s_cnt[2][16], s_cur[2][16], s_opull[2], s_off[17], s_ooff[17];  // counters: one set per item parity
     __shared__ unsigned short s_boff[BINNED ? EVAL_CHUNK : 1], s_idx[BINNED ? EVAL_CHUNK : 1];  // bank-class lists (FAST only)
     T* bricks = reinterpret_cast<T*>(smem_raw);
     const T* __restrict__ A = (const T*)p.coefs;
-    const int vol = brick_stride(N, L, N - 1) * (p.tile[N - 1] + L - 1);
-    const int volp = (vol + 3) & ~3;
+    const int vol = brick_stride(N, L, N - 1, (int)sizeof(T)) * (p.tile[N - 1] + L - 1);
+    const int volp = (vol + 31) & ~31;  // buffers stay 128-byte aligned (TMA destination)
     u32 ntot = 1;
 #pragma unroll
     for (int d = 0; d < N; d++) ntot *= (u32)p.ntile[d];
@@ -1181,12 +1379,16 @@ __global__ void __launch_bounds__(BRICK_BLOCK, 2) eval_brick_kernel(const EvalPa
     u32* ctr = const_cast<u32*>(p.nwork) + 1;
     const u32* __restrict__ work = p.work;
     const u32 tid = threadIdx.x;
+    const bool tma = p.use_tma != 0;
     // items differ in cost: CTAs pull them from a shared counter, one item ahead of the one being
     // staged (thread 0 keeps the next ticket in a register, so the atomic's latency is hidden)
     u32 pend = 0;
     if (tid == 0) {
         s_it[0] = atomicAdd(ctr, 1u);
         pend = atomicAdd(ctr, 1u);
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 16) { s_cnt[0][tid] = 0; s_cur[0][tid] = 0; }
     if (tid == 16) s_opull[0] = 0;
@@ -1195,10 +1397,11 @@ __global__ void __launch_bounds__(BRICK_BLOCK, 2) eval_brick_kernel(const EvalPa
     u32 tile_c = 0, beg_c = 0, end_c = 0;
     if (cur < nwork) {
         { const uint4 it = reinterpret_cast<const uint4*>(work)[cur]; tile_c = it.x; beg_c = it.y; end_c = it.z; }
-        if (tile_c < ntot) brick_fill<T, N, L>(p, A, bricks, tile_c, vol);
+        if (tile_c < ntot) stage_brick<T, N, L>(p, &tmap, A, bricks, &s_bar[0], tile_c, vol);
     }
     cp_async_commit();
-    T xn[N];  // direct mode: the prefetched record
+    u32 phase[2] = {0, 0};  // mbarrier parity of each buffer's next completion (TMA)
+    T xn[N];  // direct schedule: the prefetched query
     u32 qn = 0;
 #pragma unroll
     for (int d = 0; d < N; d++) xn[d] = (T)0;
@@ -1215,21 +1418,29 @@ __global__ void __launch_bounds__(BRICK_BLOCK, 2) eval_brick_kernel(const EvalPa
         u32 tile_n = 0, beg_n = 0, end_n = 0;
         if (nxt < nwork) {
             { const uint4 it = reinterpret_cast<const uint4*>(work)[nxt]; tile_n = it.x; beg_n = it.y; end_n = it.z; }
-            if (tile_n < ntot) brick_fill<T, N, L>(p, A, bricks + (size_t)(par ^ 1) * volp, tile_n, vol);
+            if (tile_n < ntot) stage_brick<T, N, L>(p, &tmap, A, bricks + (size_t)(par ^ 1) * volp, &s_bar[par ^ 1], tile_n, vol);
         }
         cp_async_commit();
         int lo[N], clip[N];
         const bool have = tile_c < ntot;  // the last bin holds invalid queries: no brick
         brick_geo<N, L>(p, have ? tile_c : 0u, lo, clip);
         const u32 n = end_c - beg_c;
+        // the brick of item k has landed: this thread's cp.async groups / the buffer's mbarrier phase
+        auto brick_ready = [&]() {
+            if (tma) {
+                if (have) { mbar_wait(&s_bar[par], phase[par]); phase[par] ^= 1u; }
+            } else {
+                cp_async_wait<1>();
+            }
+        };
         if constexpr (BINNED) {
-            // ---- pass 1 over the item's records: locate, count the bank classes (the brick is not needed yet)
+            // ---- pass 1 over the item's queries: locate, count the bank classes (the brick is not needed yet)
             for (u32 r0 = tid; r0 < n; r0 += BRICK_BLOCK * PASS1_UNROLL) {
                 T x[PASS1_UNROLL][N];
                 u32 q;
 #pragma unroll
                 for (int u = 0; u < PASS1_UNROLL; u++)  // the loads of PASS1_UNROLL records in flight together
-                    if (r0 + u * BRICK_BLOCK < n) load_record<T, N>(rec, beg_c + r0 + u * BRICK_BLOCK, x[u], q);
+                    if (r0 + u * BRICK_BLOCK < n) fetch_query<T, N, DIRECT>(p, rec, beg_c + r0 + u * BRICK_BLOCK, x[u], q);
 #pragma unroll
                 for (int u = 0; u < PASS1_UNROLL; u++) {
                     const u32 r = r0 + u * BRICK_BLOCK;
@@ -1271,8 +1482,8 @@ __global__ void __launch_bounds__(BRICK_BLOCK, 2) eval_brick_kernel(const EvalPa
                     s_idx[s_off[cl] + atomicAdd(&s_cur[par][cl], 1u)] = (unsigned short)r;
                 }
             }
-            cp_async_wait<1>();  // this thread's copies for item k have landed ...
-            __syncthreads();     // ... and everybody else's; the index list is complete
+            brick_ready();
+            __syncthreads();     // everybody's copies have landed; the index list is complete
             // ---- evaluation: T rounds, thread t serves class t mod 16
             const T* brick = bricks + (size_t)par * volp;
             const u32 cls = tid & 15u, rank = tid >> 4;
@@ -1295,30 +1506,30 @@ __global__ void __launch_bounds__(BRICK_BLOCK, 2) eval_brick_kernel(const EvalPa
             };
             u32 rn = 0;
             bool more = next_record(0, rn);
-            if (more) load_record<T, N>(rec, beg_c + rn, xn, qn);
+            if (more) fetch_query<T, N, DIRECT>(p, rec, beg_c + rn, xn, qn);
             for (u32 i = 0; more; i++) {
                 T x[N];
 #pragma unroll
                 for (int d = 0; d < N; d++) x[d] = xn[d];
                 const u32 q = qn, r = rn;
                 more = next_record(i + 1, rn);
-                if (more) load_record<T, N>(rec, beg_c + rn, xn, qn);  // in flight during this round's evaluation
+                if (more) fetch_query<T, N, DIRECT>(p, rec, beg_c + rn, xn, qn);  // in flight during this round's evaluation
                 int cc[N][L];
                 T dx[N];
                 query_taps<T, N, ORDER, BCF>(p, x, cc, dx);
                 brick_eval_one<T, N, ORDER, BCF, OUTMODE, FAST>(p, dx, (i64)q, beg_c + r, brick, (u32)s_boff[r], defer);
             }
         } else {
-            // ---- direct: thread t takes records t, t+256, ... of the item; the next record is in flight
+            // ---- direct: thread t takes queries t, t+256, ... of the item; the next one is in flight
             // while the current one is evaluated (across the item boundary too)
-            cp_async_wait<1>();  // this thread's copies for item k have landed ...
-            __syncthreads();     // ... and everybody else's
+            brick_ready();
+            __syncthreads();     // ... and everybody else's copies
             const T* brick = bricks + (size_t)par * volp;
             const bool next_has = nxt < nwork && beg_n + tid < end_n;
             u32 j = beg_c + tid;
-            if (k == 0 && j < end_c) load_record<T, N>(rec, j, xn, qn);
+            if (k == 0 && j < end_c) fetch_query<T, N, DIRECT>(p, rec, j, xn, qn);
             if (j >= end_c) {
-                if (next_has) load_record<T, N>(rec, beg_n + tid, xn, qn);
+                if (next_has) fetch_query<T, N, DIRECT>(p, rec, beg_n + tid, xn, qn);
             } else {
                 while (true) {
                     T x[N];
@@ -1327,8 +1538,8 @@ __global__ void __launch_bounds__(BRICK_BLOCK, 2) eval_brick_kernel(const EvalPa
                     const u32 q = qn, jc = j;
                     j += BRICK_BLOCK;
                     const bool more = j < end_c;
-                    if (more) load_record<T, N>(rec, j, xn, qn);
-                    else if (next_has) load_record<T, N>(rec, beg_n + tid, xn, qn);
+                    if (more) fetch_query<T, N, DIRECT>(p, rec, j, xn, qn);
+                    else if (next_has) fetch_query<T, N, DIRECT>(p, rec, beg_n + tid, xn, qn);
                     T dx[N];
                     const u32 boff = brick_locate<T, N, ORDER, BCF>(p, x, lo, clip, have, dx);
                     if (boff == BRICK_DEFER) defer_slot(defer, jc);  // global-memory path, later
@@ -1346,7 +1557,8 @@ __global__ void __launch_bounds__(BRICK_BLOCK, 2) eval_brick_kernel(const EvalPa
 // f64 valgrad in 3-D) and writes the caller's val / grad / hess arrays coalesced.
 template <typename T, int N, int OUTMODE>
 __global__ void __launch_bounds__(256) unpermute_kernel(const T* __restrict__ osorted, const u32* __restrict__ inv, T* __restrict__ val, T* __restrict__ grad,
-                                                        T* __restrict__ hess, i64 nq) {
+                                                        T* __restrict__ hess, i64 nq, const u32* __restrict__ nwork) {
+    if (nwork[2] != 0) return;  // grouped batch: the outputs were written in place
     constexpr int W = out_words<N>(OUTMODE);
     for (i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (i64)gridDim.x * blockDim.x) {
         const T* src = osorted + (size_t)inv[q] * W;
@@ -1379,8 +1591,11 @@ __global__ void __launch_bounds__(256) unpermute_kernel(const T* __restrict__ os
 // eval_tile.cu
 int tile_offsets(const u32* bh, u32 nbins, u32 nctas, u32* hist, u32* offs, u32* boff, u32* work, u32* nwork, u32 chunk, cudaStream_t s);
 int tile_offsets_global(const u32* hist, u32 nbins, u32* offs, u32* cursor, u32* work, u32* nwork, u32 chunk, cudaStream_t s);
+int sorted_decide(const u32* runcnt, u32 nctas, i64 nq, u32 min_run, u32 max_items, u32* base, u32* nwork, cudaStream_t s);
 bool choose_tile(int N, int L, size_t esz, const int* len, i64 nq, bool forced, int* tile, int* ntile);
 u32 sort_smem_bins();  // 12000: per-CTA histograms live in shared memory (<= 48 KB); more tiles: tile_sort_global_kernel
+u32 sorted_min_run(bool hinted);  // average run length (queries) from which a batch counts as grouped by tile
+int make_brick_tensor_map(CUtensorMap* m, int dtype, int N, const void* base, const int* len, const i64* stride, const int* box);
 // Larger batches are evaluated in slices: bounds the record scratch, and keeps the randomly written regions -- the
 // slice's records and its outputs -- from outgrowing L2 by too much: the two permutations of a 4e7-query batch
 // cost 3.13 ms in one piece, 4 x 0.55 ms in four (256^3 f64: 6.11 -> 5.41 ms).  Slices must stay large against the
@@ -1399,28 +1614,35 @@ inline i64 tiled_max_batch(i64 ntiles = -1) {
 }
 
 template <typename T, int N, int ORDER, int BCF, int OUTMODE, bool FAST>
-int launch_tiled(const EvalParams<N>& p_in, cudaStream_t s) {
+int launch_tiled(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     constexpr int L = ORDER + 1;
-    auto kern = eval_brick_kernel<T, N, ORDER, BCF, OUTMODE, FAST>;
+    auto kern = eval_brick_kernel<T, N, ORDER, BCF, OUTMODE, FAST, false>;
+    auto kern_direct = eval_brick_kernel<T, N, ORDER, BCF, OUTMODE, FAST, true>;
     EvalParams<N> p = p_in;
     u32 nbins = 1;
-    size_t vol = 1;
-    for (int d = 0; d < N; d++) { nbins *= (u32)p.ntile[d]; vol *= (size_t)(p.tile[d] + L - 1); }
+    for (int d = 0; d < N; d++) nbins *= (u32)p.ntile[d];
     nbins += 1;  // + the bin of invalid queries
-    const size_t smem = 2 * ((vol + 3) & ~(size_t)3) * sizeof(T);
+    int box[N];
+    for (int d = 0; d < N; d++) box[d] = d < N - 1 ? brick_extent(N, L, d, (int)sizeof(T)) : p.tile[d] + L - 1;
+    size_t vol = 1;
+    for (int d = 0; d < N; d++) vol *= (size_t)box[d];
+    const size_t smem = 2 * ((vol + 31) & ~(size_t)31) * sizeof(T);
     const u32 nctas = (u32)std::max<i64>(1, std::min<i64>((i64)num_sms() * 2, (p.nq + 4095) / 4096));
-    const i64 per_cta = (p.nq + nctas - 1) / nctas;
-    const size_t max_items = (size_t)nbins + (size_t)(p.nq / EVAL_CHUNK) + 2;
+    const i64 per_cta = ((p.nq + nctas - 1) / nctas + SORT_ITER - 1) / SORT_ITER * SORT_ITER;  // whole bitmap words per CTA
+    const u32 min_run = sorted_min_run((flags & GB_SORTED) != 0);
+    const size_t max_items = (size_t)nbins + (size_t)(p.nq / EVAL_CHUNK) + (min_run ? (size_t)(p.nq / min_run) : 0) + nctas + 2;
     const size_t pitch = ((size_t)p.nq + 15) & ~(size_t)15;
-    // one scratch allocation: records | sorted outputs | inv | deferred-slot list (`keys`) | work | bh | boff | hist | offs | nwork
+    // one scratch allocation: records | sorted outputs | inv | deferred-slot list (`keys`) | work | bh | boff | hist | offs | bitmap | runcnt | runbase | nwork
     constexpr int W = out_words<N>(OUTMODE);
     const bool global_bins = nbins > sort_smem_bins();
     const size_t nbc = global_bins ? 16 : (size_t)nbins * nctas;
     const size_t rec_bytes = (pitch * (N + 1) * sizeof(T) + 31) & ~(size_t)31;
     const size_t out_bytes = (pitch * W * sizeof(T) + 31) & ~(size_t)31;
-    const size_t words = (pitch + 16) + 2 * nbc + 2 * (size_t)(nbins + 4) + 4 + 4 * max_items;
-    unsigned char* scratch = nullptr;
-    GB_CUDA(cudaMallocAsync((void**)&scratch, rec_bytes + out_bytes + (pitch + words) * sizeof(u32), s));
+    const size_t bm_words = ((size_t)per_cta * nctas + 31) / 32 + 4;
+    const size_t words = (pitch + 16) + 2 * nbc + 2 * (size_t)(nbins + 4) + bm_words + 2 * (size_t)(nctas + 4) + 8 + 4 * max_items;
+    AsyncBuf guard(s);  // released on every exit path
+    GB_CUDA(guard.alloc(rec_bytes + out_bytes + (pitch + words) * sizeof(u32)));
+    unsigned char* scratch = (unsigned char*)guard.p;
     T* rec = reinterpret_cast<T*>(scratch);
     T* osorted = reinterpret_cast<T*>(scratch + rec_bytes);
     u32* inv = reinterpret_cast<u32*>(scratch + rec_bytes + out_bytes);
@@ -1430,63 +1652,84 @@ int launch_tiled(const EvalParams<N>& p_in, cudaStream_t s) {
     u32* boff = bh + nbc;
     u32* hist = boff + nbc;
     u32* offs = hist + (nbins + 4);
-    u32* nwork = offs + (nbins + 4);
+    u32* bitmap = offs + (nbins + 4);
+    u32* runcnt = bitmap + bm_words;
+    u32* runbase = runcnt + (nctas + 4);
+    u32* nwork = runbase + (nctas + 4);
     const size_t hsmem = (size_t)nbins * sizeof(u32);
+    // brick staging: TMA when the array obeys its stride rule (every stride but the first a multiple of 16 bytes)
+    CUtensorMap tmap;
+    std::memset(&tmap, 0, sizeof(tmap));
+    static const bool tma_off = [] { const char* e = getenv("GB_NO_TMA"); return e && *e && *e != '0'; }();
+    p.use_tma = 0;
+    if (!tma_off && make_brick_tensor_map(&tmap, dtype_of<T>::value, N, p.coefs, p.len, p.stride, box) == GB_OK) p.use_tma = 1;
+    p.work = work;
+    p.nwork = nwork;
+    GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per device, cheap
+    GB_CUDA(cudaFuncSetAttribute(kern_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int bt = 0;
+    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt, kern, BRICK_BLOCK, smem));
+    if (bt < 1) return fail(GB_ERR_CUDA, "tiled evaluation: brick does not fit in shared memory");
     prof_mark(0, s);
     int rc;
     if (global_bins) {  // hist doubles as the write cursors after the scan
         GB_CUDA(cudaMemsetAsync(hist, 0, (size_t)nbins * sizeof(u32), s));
-        tile_sort_global_kernel<T, N, ORDER, BCF, false><<<nctas, SORT_BLOCK, 0, s>>>(p, hist, rec, inv, per_cta);
+        tile_sort_global_kernel<T, N, ORDER, BCF, false><<<nctas, SORT_BLOCK, 0, s>>>(p, hist, rec, inv, per_cta, bitmap, runcnt);
         count_launch();
+        rc = sorted_decide(runcnt, nctas, p.nq, min_run, (u32)max_items, runbase, nwork, s);
+        if (rc) return rc;
         prof_mark(1, s);
         rc = tile_offsets_global(hist, nbins, offs, hist, work, nwork, EVAL_CHUNK, s);
-        if (rc) { cudaFreeAsync(scratch, s); return rc; }
+        if (rc) return rc;
         prof_mark(2, s);
-        tile_sort_global_kernel<T, N, ORDER, BCF, true><<<nctas, SORT_BLOCK, 0, s>>>(p, hist, rec, inv, per_cta);
+        tile_sort_global_kernel<T, N, ORDER, BCF, true><<<nctas, SORT_BLOCK, 0, s>>>(p, hist, rec, inv, per_cta, bitmap, runcnt);
         count_launch();
     } else {
-        tile_hist_kernel<T, N, ORDER, BCF><<<nctas, SORT_BLOCK, hsmem, s>>>(p, bh, nbins, per_cta);
+        tile_hist_kernel<T, N, ORDER, BCF><<<nctas, SORT_BLOCK, hsmem, s>>>(p, bh, nbins, per_cta, bitmap, runcnt);
         count_launch();
+        rc = sorted_decide(runcnt, nctas, p.nq, min_run, (u32)max_items, runbase, nwork, s);
+        if (rc) return rc;
         prof_mark(1, s);
         rc = tile_offsets(bh, nbins, nctas, hist, offs, boff, work, nwork, EVAL_CHUNK, s);
-        if (rc) { cudaFreeAsync(scratch, s); return rc; }
+        if (rc) return rc;
         prof_mark(2, s);
         tile_scatter_kernel<T, N, ORDER, BCF><<<nctas, SORT_BLOCK, hsmem, s>>>(p, boff, rec, inv, nbins, per_cta);
         count_launch();
     }
+    run_items_kernel<T, N, ORDER, BCF><<<nctas, SORT_BLOCK, 0, s>>>(p, bitmap, runbase, work, nwork, per_cta);
+    count_launch();
     GB_CUDA(cudaGetLastError());
-    GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per device, cheap
-    int bt = 0;
-    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt, kern, BRICK_BLOCK, smem));
-    if (bt < 1) { cudaFreeAsync(scratch, s); return fail(GB_ERR_CUDA, "tiled evaluation: brick does not fit in shared memory"); }
-    p.work = work;
-    p.nwork = nwork;
     const i64 grid = std::min<i64>((i64)max_items, (i64)num_sms() * bt);
     // the deferred-slot list (count first)
     u32* defer = keys;
     GB_CUDA(cudaMemsetAsync(defer, 0, sizeof(u32), s));
-    p.aos = W;  // both kernels write one output record per sorted slot ...
+    EvalParams<N> pd = p;  // grouped batch: slots are the caller's indices, outputs go straight to the caller's arrays
+    pd.aos = 0;
+    p.aos = W;  // sorted batch: both kernels write one output record per sorted slot ...
     p.val = osorted;
     p.grad = nullptr;
     p.hess = nullptr;
     prof_mark(3, s);
-    kern<<<(int)grid, BRICK_BLOCK, smem, s>>>(p, rec, defer);
+    kern<<<(int)grid, BRICK_BLOCK, smem, s>>>(p, rec, defer, tmap);
+    kern_direct<<<(int)grid, BRICK_BLOCK, smem, s>>>(pd, rec, defer, tmap);
     prof_mark(4, s);
-    eval_deferred_kernel<T, N, ORDER, BCF, OUTMODE, FAST><<<num_sms() * 2, EVAL_BLOCK, 0, s>>>(p, rec, defer);
+    eval_deferred_kernel<T, N, ORDER, BCF, OUTMODE, FAST, false><<<num_sms() * 2, EVAL_BLOCK, 0, s>>>(p, rec, defer);
+    eval_deferred_kernel<T, N, ORDER, BCF, OUTMODE, FAST, true><<<num_sms() * 2, EVAL_BLOCK, 0, s>>>(pd, rec, defer);
     prof_mark(5, s);
     // ... and the records go back to the caller's order and arrays
     const int ugrid = (int)std::min<i64>((p.nq + 255) / 256, (i64)num_sms() * 32);
-    unpermute_kernel<T, N, OUTMODE><<<ugrid, 256, 0, s>>>(osorted, inv, (T*)p_in.val, (T*)p_in.grad, (T*)p_in.hess, p.nq);
+    unpermute_kernel<T, N, OUTMODE><<<ugrid, 256, 0, s>>>(osorted, inv, (T*)p_in.val, (T*)p_in.grad, (T*)p_in.hess, p.nq, nwork);
+    prof_mode(nwork, s);
     prof_mark(6, s);
-    count_launch(3);
+    count_launch(5);
     GB_CUDA(cudaGetLastError());
-    GB_CUDA(cudaFreeAsync(scratch, s));
     return GB_OK;
 }
 
 template <typename T, int N, int ORDER, int BCF, int OUTMODE, bool FAST>
 int launch_one(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     constexpr int L = ORDER + 1;
+    constexpr bool BRICK = brick_compiled(N, ORDER);
     auto kern = eval_kernel<T, N, ORDER, BCF, OUTMODE, FAST>;
     EvalParams<N> p = p_in;
     const size_t grid_bytes = (size_t)p.total * sizeof(T);
@@ -1499,9 +1742,10 @@ int launch_one(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     size_t tap_bytes = sizeof(T);
     for (int d = 0; d < N; d++) tap_bytes *= (size_t)L;
     if (!(flags & (GB_TILED | GB_PLAIN))) tiled = N >= 2 && tap_bytes >= 256 && p.nq >= (1ll << 20) && grid_bytes >= (48u << 20);
-    if (p.nchan > 1 || p.blocked) tiled = false;  // multi-valued / blocked grids: plain path
+    if (p.nchan > 1 || p.blocked || !BRICK) tiled = false;  // multi-valued / blocked grids, light neighbourhoods: plain path
     if (tiled) tiled = choose_tile(N, L, sizeof(T), p.len, std::min<i64>(p.nq, tiled_max_batch()), forced, p.tile, p.ntile);
     p.aos = 0;
+    p.use_tma = 0;
     if (!tiled) {
         static int blocks_plain = 0;  // benign race: every thread computes the same value
         if (blocks_plain == 0) {
@@ -1519,22 +1763,24 @@ int launch_one(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
         GB_CUDA(cudaGetLastError());
         return GB_OK;
     }
-    // equal slices of at most tiled_max_batch() queries, one after the other on the stream
-    i64 ntiles = 1;
-    for (int d = 0; d < N; d++) ntiles *= p.ntile[d];
-    const i64 limit = tiled_max_batch(ntiles), nslices = (p_in.nq + limit - 1) / limit;
-    const i64 slice = std::min<i64>(limit, (((p_in.nq + nslices - 1) / nslices) + 255) & ~(i64)255);
-    const size_t xs = p.xdtype == GB_F64 ? 8 : 4;
-    for (i64 q0 = 0; q0 < p_in.nq; q0 += slice) {
-        EvalParams<N> sp = p;
-        sp.nq = std::min<i64>(slice, p_in.nq - q0);
-        sp.q0 = p_in.q0 + q0;
-        for (int d = 0; d < N; d++) sp.xp[d] = (const char*)p.xp[d] + (size_t)q0 * (size_t)p.xqs * xs;
-        if (p.val) sp.val = (T*)p.val + q0;
-        if (p.grad) sp.grad = (T*)p.grad + q0 * N;
-        if (p.hess) sp.hess = (T*)p.hess + q0 * N * N;
-        const int rc = launch_tiled<T, N, ORDER, BCF, OUTMODE, FAST>(sp, s);
-        if (rc) return rc;
+    if constexpr (BRICK) {
+        // equal slices of at most tiled_max_batch() queries, one after the other on the stream
+        i64 ntiles = 1;
+        for (int d = 0; d < N; d++) ntiles *= p.ntile[d];
+        const i64 limit = tiled_max_batch(ntiles), nslices = (p_in.nq + limit - 1) / limit;
+        const i64 slice = std::min<i64>(limit, (((p_in.nq + nslices - 1) / nslices) + 255) & ~(i64)255);
+        const size_t xs = p.xdtype == GB_F64 ? 8 : 4;
+        for (i64 q0 = 0; q0 < p_in.nq; q0 += slice) {
+            EvalParams<N> sp = p;
+            sp.nq = std::min<i64>(slice, p_in.nq - q0);
+            sp.q0 = p_in.q0 + q0;
+            for (int d = 0; d < N; d++) sp.xp[d] = (const char*)p.xp[d] + (size_t)q0 * (size_t)p.xqs * xs;
+            if (p.val) sp.val = (T*)p.val + q0;
+            if (p.grad) sp.grad = (T*)p.grad + q0 * N;
+            if (p.hess) sp.hess = (T*)p.hess + q0 * N * N;
+            const int rc = launch_tiled<T, N, ORDER, BCF, OUTMODE, FAST>(sp, flags, s);
+            if (rc) return rc;
+        }
     }
     return GB_OK;
 }
@@ -1637,8 +1883,9 @@ int launch_outer_bc(const EvalParams<N>& p, const i64* lens, int flags, void* ou
     if (nq == 0) return GB_OK;
     // one scratch block: taps (int) | weights (T) | flags
     const size_t tap_b = ((size_t)rows * L * sizeof(int) + 15) & ~(size_t)15, w_b = ((size_t)rows * L * sizeof(T) + 15) & ~(size_t)15;
-    unsigned char* blk = nullptr;
-    GB_CUDA(cudaMallocAsync((void**)&blk, tap_b + w_b + (size_t)rows + 16, s));
+    AsyncBuf scratch(s);
+    GB_CUDA(scratch.alloc(tap_b + w_b + (size_t)rows + 16));
+    unsigned char* blk = (unsigned char*)scratch.p;
     int* tap = reinterpret_cast<int*>(blk);
     T* w = reinterpret_cast<T*>(blk + tap_b);
     unsigned char* flg = blk + tap_b + w_b;
@@ -1656,7 +1903,6 @@ int launch_outer_bc(const EvalParams<N>& p, const i64* lens, int flags, void* ou
     else outer_eval_kernel<T, N, ORDER, BCF, false><<<grid, 256, 0, s>>>(p, t, (T*)out, nq);
     count_launch(N + 1);
     GB_CUDA(cudaGetLastError());
-    GB_CUDA(cudaFreeAsync(blk, s));
     return GB_OK;
 }
 template <typename T, int N, int ORDER> int launch_outer_order(const EvalParams<N>& p, int bcf, const i64* lens, int flags, void* out, cudaStream_t s) {

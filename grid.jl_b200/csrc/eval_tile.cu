@@ -6,6 +6,8 @@
 #include <cstring>
 #include <mutex>
 
+#include <cuda.h>  // CUtensorMap / cuTensorMapEncodeTiled types (the entry point is resolved at run time)
+
 #include "common.cuh"
 
 namespace gb {
@@ -17,7 +19,14 @@ std::atomic<int> g_prof_on{0};
 std::mutex g_prof_mu;
 cudaEvent_t g_prof_ev[PROF_NB];
 bool g_prof_init = false, g_prof_have = false;
+u32* g_prof_mode = nullptr;  // pinned: nwork[2] of the last profiled tiled call (1 = grouped batch, evaluated in place)
 }  // namespace
+void prof_mode(const u32* nwork, cudaStream_t s) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_prof_mode && cudaHostAlloc((void**)&g_prof_mode, sizeof(u32), cudaHostAllocDefault) != cudaSuccess) { g_prof_mode = nullptr; return; }
+    cudaMemcpyAsync(g_prof_mode, nwork + 2, sizeof(u32), cudaMemcpyDeviceToHost, s);
+}
 void prof_mark(int i, cudaStream_t s) {
     if (!g_prof_on.load(std::memory_order_relaxed) || i < 0 || i >= PROF_NB) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -45,6 +54,7 @@ int prof_read(double* ms, int n, int* nstages) {
         GB_CUDA(cudaEventElapsedTime(&t, g_prof_ev[k], g_prof_ev[k + 1]));
         ms[k] = (double)t;
     }
+    if (PROF_NB - 1 < n) ms[PROF_NB - 1] = g_prof_mode ? (double)*g_prof_mode : 0.0;  // [6]: 1 = the batch was grouped by tile and evaluated in place
     if (nstages) *nstages = PROF_NB - 1;
     return GB_OK;
 }
@@ -55,6 +65,7 @@ int prof_read(double* ms, int n, int* nstages) {
 constexpr int SCAN_PER = 12;  // bins per thread and segment (1024 * 12 >= sort_smem_bins(): one segment for the shared-memory sort)
 __global__ void __launch_bounds__(1024) tile_scan_kernel(const u32* __restrict__ hist, u32 nbins, u32* __restrict__ offs, u32* __restrict__ work,
                                                          u32* __restrict__ nwork, u32 chunk) {
+    if (nwork[2] != 0) return;  // grouped batch (sorted_decide): the runs are the work items
     __shared__ u32 s_wc[32], s_wi[32], s_base[2];
     const u32 t = threadIdx.x, lane = t & 31, warp = t >> 5;
     if (t == 0) { s_base[0] = 0; s_base[1] = 0; }
@@ -116,7 +127,8 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const u32* __restrict__
 }
 
 // hist[b] = sum over CTAs of bh[b][cta]; one warp per bin.
-__global__ void __launch_bounds__(256) bin_totals_kernel(const u32* __restrict__ bh, u32 nbins, u32 nctas, u32* __restrict__ hist) {
+__global__ void __launch_bounds__(256) bin_totals_kernel(const u32* __restrict__ bh, u32 nbins, u32 nctas, u32* __restrict__ hist, const u32* __restrict__ nwork) {
+    if (nwork[2] != 0) return;
     const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= nbins) return;
     u32 sum = 0;
@@ -127,7 +139,9 @@ __global__ void __launch_bounds__(256) bin_totals_kernel(const u32* __restrict__
 }
 
 // boff[b][cta] = offs[b] + (queries of bin b owned by CTAs < cta); one warp per bin.
-__global__ void __launch_bounds__(256) bin_cursors_kernel(const u32* __restrict__ bh, u32 nbins, u32 nctas, const u32* __restrict__ offs, u32* __restrict__ boff) {
+__global__ void __launch_bounds__(256) bin_cursors_kernel(const u32* __restrict__ bh, u32 nbins, u32 nctas, const u32* __restrict__ offs, u32* __restrict__ boff,
+                                                          const u32* __restrict__ nwork) {
+    if (nwork[2] != 0) return;
     const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= nbins) return;
     u32 carry = offs[warp];
@@ -147,9 +161,9 @@ __global__ void __launch_bounds__(256) bin_cursors_kernel(const u32* __restrict_
 
 int tile_offsets(const u32* bh, u32 nbins, u32 nctas, u32* hist, u32* offs, u32* boff, u32* work, u32* nwork, u32 chunk, cudaStream_t s) {
     const u32 wgrid = (nbins * 32 + 255) / 256;
-    bin_totals_kernel<<<wgrid, 256, 0, s>>>(bh, nbins, nctas, hist);
+    bin_totals_kernel<<<wgrid, 256, 0, s>>>(bh, nbins, nctas, hist, nwork);
     tile_scan_kernel<<<1, 1024, 0, s>>>(hist, nbins, offs, work, nwork, chunk);
-    bin_cursors_kernel<<<wgrid, 256, 0, s>>>(bh, nbins, nctas, offs, boff);
+    bin_cursors_kernel<<<wgrid, 256, 0, s>>>(bh, nbins, nctas, offs, boff, nwork);
     count_launch(3);
     GB_CUDA(cudaGetLastError());
     return GB_OK;
@@ -163,6 +177,93 @@ int tile_offsets_global(const u32* hist, u32 nbins, u32* offs, u32* cursor, u32*
     GB_CUDA(cudaGetLastError());
     GB_CUDA(cudaMemcpyAsync(cursor, offs, (size_t)nbins * sizeof(u32), cudaMemcpyDeviceToDevice, s));
     return GB_OK;
+}
+
+// ---- grouped ("sorted") batches ------------------------------------------------------------------------------------
+// runcnt[cta] = run starts the sort CTAs marked (eval.cuh: mark_runs).  Few runs = the batch arrived grouped by tile:
+// nwork[2] = 1, nwork[0] = number of runs (the work items, built by run_items_kernel from base[cta] = runs before CTA
+// cta), nwork[1] = 0 (ticket counter).  Otherwise nwork[2] = 0 and the counting sort proceeds.  One CTA.
+__global__ void __launch_bounds__(1024) sorted_decide_kernel(const u32* __restrict__ runcnt, u32 nctas, u32 limit, u32* __restrict__ base, u32* __restrict__ nwork) {
+    __shared__ u32 s_w[32];
+    const u32 t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const u32 c = t < nctas ? runcnt[t] : 0u;
+    u32 incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 a = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += a;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        u32 w = s_w[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 a = __shfl_up_sync(0xffffffffu, w, o);
+            if ((int)lane >= o) w += a;
+        }
+        s_w[lane] = w;
+    }
+    __syncthreads();
+    const u32 before = (warp ? s_w[warp - 1] : 0u) + incl - c;
+    if (t < nctas) base[t] = before;
+    if (t == 0) {
+        const u32 total = s_w[31];
+        const u32 grouped = (limit != 0 && total <= limit) ? 1u : 0u;
+        nwork[2] = grouped;
+        if (grouped) { nwork[0] = total; nwork[1] = 0; }
+    }
+}
+// min_run: average run length from which the batch counts as grouped (0: never)
+int sorted_decide(const u32* runcnt, u32 nctas, i64 nq, u32 min_run, u32 max_items, u32* base, u32* nwork, cudaStream_t s) {
+    if (nctas > 1024) return fail(GB_ERR_CUDA, "sorted_decide: too many sort CTAs");
+    u32 limit = 0;
+    if (min_run) {  // run starts include the forced ones (every EVAL_CHUNK-th query, each CTA's first)
+        const i64 l = nq / min_run + nq / 2048 + nctas;
+        limit = (u32)std::min<i64>(l, (i64)max_items - 2);
+    }
+    sorted_decide_kernel<<<1, 1024, 0, s>>>(runcnt, nctas, limit, base, nwork);
+    count_launch();
+    GB_CUDA(cudaGetLastError());
+    return GB_OK;
+}
+// GB_SORTED_MIN_RUN: average run length (queries per visit of a tile) from which a batch is evaluated in place;
+// default 256 (32 when the caller passed GB_SORTED); 0 disables the detection.
+u32 sorted_min_run(bool hinted) {
+    static const long env = [] { const char* e = getenv("GB_SORTED_MIN_RUN"); return e ? atol(e) : -1L; }();
+    if (env >= 0) return (u32)env;
+    return hinted ? 32u : 256u;
+}
+
+// Tensor map of the coefficient array for the brick kernel's TMA loads: rank N, box = the brick.  Fails (-> cp.async
+// staging) when the array breaks TMA's rules: strides of dims >= 1 must be multiples of 16 bytes, box extents <= 256.
+int make_brick_tensor_map(CUtensorMap* m, int dtype, int N, const void* base, const int* len, const i64* stride, const int* box) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                 CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess) fn = nullptr;
+        return (EncodeFn)fn;
+    }();
+    if (!encode || N < 2 || N > 3) return GB_ERR_UNSUPPORTED;
+    const size_t es = dtype == GB_F64 ? 8 : 4;
+    if (((uintptr_t)base & 15) != 0) return GB_ERR_UNSUPPORTED;
+    cuuint64_t gdim[3], gstr[2];
+    cuuint32_t bdim[3], estr[3] = {1, 1, 1};
+    for (int d = 0; d < N; d++) {
+        gdim[d] = (cuuint64_t)len[d];
+        if (box[d] < 1 || box[d] > 256) return GB_ERR_UNSUPPORTED;
+        bdim[d] = (cuuint32_t)box[d];
+        if (d >= 1) {
+            gstr[d - 1] = (cuuint64_t)stride[d] * es;
+            if (gstr[d - 1] % 16 != 0) return GB_ERR_UNSUPPORTED;
+        }
+    }
+    if ((box[0] * es) % 16 != 0) return GB_ERR_UNSUPPORTED;
+    const CUresult r = encode(m, dtype == GB_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)N, const_cast<void*>(base), gdim, gstr,
+                              bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? GB_OK : GB_ERR_UNSUPPORTED;
 }
 
 // Tile shape.  The leading extents are fixed (brick_tile); the extent along the last dimension is
@@ -194,7 +295,7 @@ bool choose_tile(int N, int L, size_t esz, const int* len, i64 nq, bool forced, 
     for (int d = 0; d < N - 1; d++) {
         tile[d] = brick_tile(N, d);
         ntile[d] = (len[d] + tile[d] - 1) / tile[d];
-        lead *= (size_t)(tile[d] + L - 1);
+        lead *= (size_t)brick_extent(N, L, d, (int)esz);
         nt *= (unsigned long long)ntile[d];
     }
     const int last = len[N - 1];

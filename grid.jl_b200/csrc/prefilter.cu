@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -475,88 +476,143 @@ template <typename T> struct HostSys {
     }
 };
 
+// ---- factorisation cache ---------------------------------------------------------------------------------------------
+// The factors of a sweep depend on (element type, bc family, order, n) only: computed and uploaded once per device, then
+// reused by every later sweep of that shape (InterpGrid(...) on 258^3 spends more time here than in its kernels otherwise).
+template <typename T> struct CachedSys {
+    LineSys<T> sys;
+    int woodbury = 0;
+};
+template <typename T> int get_line_sys(int bc, int order, i64 n, CachedSys<T>& out) {
+    struct Key {
+        int dev, fam, order;
+        i64 n;
+        bool operator==(const Key& o) const { return dev == o.dev && fam == o.fam && order == o.order && n == o.n; }
+    };
+    static std::mutex mu;
+    static std::vector<std::pair<Key, CachedSys<T>>> cache;
+    int dev = 0;
+    GB_CUDA(cudaGetDevice(&dev));
+    const Key key{dev, bc_family(bc), order, n};
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& e : cache)
+        if (e.first == key) { out = e.second; return GB_OK; }
+    HostSys<T> hs;
+    int rc = hs.setup(bc, order, n);
+    if (rc) return rc;
+    // one device blob: dl | d | du | du2 | rd | swap
+    const size_t nT = (size_t)(5 * n);
+    const size_t bytes = nT * sizeof(T) + (size_t)n * sizeof(int);
+    std::vector<unsigned char> blob(bytes, 0);
+    T* hb = reinterpret_cast<T*>(blob.data());
+    std::copy(hs.dl.begin(), hs.dl.end(), hb);
+    std::copy(hs.d.begin(), hs.d.end(), hb + n);
+    std::copy(hs.du.begin(), hs.du.end(), hb + 2 * n);
+    std::copy(hs.du2.begin(), hs.du2.end(), hb + 3 * n);
+    for (i64 i = 0; i < n; i++) hb[4 * n + i] = (T)1 / hs.d[i];  // correctly rounded reciprocals of the pivots
+    int* hsw = reinterpret_cast<int*>(blob.data() + nT * sizeof(T));
+    std::copy(hs.swap.begin(), hs.swap.end(), hsw);
+    unsigned char* dblob = nullptr;
+    GB_CUDA(cudaMalloc((void**)&dblob, bytes));
+    cudaError_t e = cudaMemcpy(dblob, blob.data(), bytes, cudaMemcpyHostToDevice);  // synchronous: valid for every stream afterwards
+    if (e != cudaSuccess) { cudaFree(dblob); return cuda_fail(e, "cudaMemcpy (prefilter factors)"); }
+    CachedSys<T> cs;
+    LineSys<T>& sys = cs.sys;
+    T* db = reinterpret_cast<T*>(dblob);
+    sys.dl = db; sys.d = db + n; sys.du = db + 2 * n; sys.du2 = db + 3 * n; sys.rd = db + 4 * n;
+    sys.swap = reinterpret_cast<const int*>(dblob + nT * sizeof(T));
+    sys.woodbury = hs.woodbury ? 1 : 0;
+    cs.woodbury = sys.woodbury;
+    sys.vcol0 = (int)hs.vcol[0]; sys.vcol1 = (int)hs.vcol[1];
+    for (int i = 0; i < 4; i++) sys.cp[i] = hs.cp[i];
+    {  // stationary interior: longest runs of bit-identical factors (forward steps end before n-2: sparse_step's k1 row)
+        auto same = [](T a, T b) { return std::memcmp(&a, &b, sizeof(T)) == 0; };
+        auto longest = [&](i64 lo, i64 hi, auto eq, i64& r0, i64& r1) {
+            r0 = r1 = 0;
+            for (i64 i = lo; i < hi;) {
+                i64 j = i + 1;
+                while (j < hi && eq(i, j)) j++;
+                if (j - i > r1 - r0) { r0 = i; r1 = j; }
+                i = j;
+            }
+        };
+        longest(0, n - 2, [&](i64 i, i64 j) { return !hs.swap[i] && !hs.swap[j] && same(hs.dl[i], hs.dl[j]); }, sys.f0, sys.f1);
+        if (sys.f1 - sys.f0 < 2 || hs.swap[sys.f0]) sys.f0 = sys.f1 = 0;
+        longest(0, n - 2, [&](i64 i, i64 j) { return same(hs.du[i], hs.du[j]) && same(hs.du2[i], hs.du2[j]) && same(hs.d[i], hs.d[j]); }, sys.b0, sys.b1);
+        if (sys.b1 - sys.b0 < 2) sys.b0 = sys.b1 = 0;
+        sys.cdl = n > 1 ? hs.dl[sys.f0] : (T)0;
+        sys.cdu = n > 2 ? hs.du[sys.b0] : (T)0;
+        sys.cdu2 = n > 2 ? hs.du2[sys.b0] : (T)0;
+        sys.cd = hs.d[sys.b0];
+        sys.crd = (T)1 / hs.d[sys.b0];
+    }
+    if (cache.size() >= 256) {  // bounded: forget the oldest shape
+        cudaFree(const_cast<T*>(cache.front().second.sys.dl));
+        cache.erase(cache.begin());
+    }
+    cache.emplace_back(key, cs);
+    out = cs;
+    return GB_OK;
+}
+
+// one exact sweep (the reference's LU / Woodbury substitution order) along dimension idim, in place
+template <typename T> int sweep_exact(T* A, int ndim, const i64* dims, int bc, int order, int idim, cudaStream_t s) {
+    if (idim < 0 || idim >= ndim) return fail(GB_ERR_ARG, "dimlist entry out of range");
+    i64 total = 1, str = 1;
+    for (int d = 0; d < ndim; d++) {
+        if (d == idim) str = total;
+        total *= dims[d];
+    }
+    if (total == 0) return GB_OK;
+    const i64 n = dims[idim], nlines = total / n;
+    CachedSys<T> cs;
+    int rc = get_line_sys<T>(bc, order, n, cs);
+    if (rc) return rc;
+    const LineSys<T>& sys = cs.sys;
+    // Woodbury: checkpoints of the second solve's RHS in shared memory when they fit, else an array-sized scratch
+    const size_t ck_bytes = cs.woodbury && n >= 3 ? (size_t)((n - 2 + PF_U - 1) / PF_U) * 128 * sizeof(T) : 0;
+    const int use_ck = cs.woodbury && ck_bytes > 0 && ck_bytes <= 64 * 1024;
+    const size_t dyn = use_ck ? ck_bytes : 0;
+    AsyncBuf tmp(s);
+    if (cs.woodbury && !use_ck) GB_CUDA(tmp.alloc((size_t)total * sizeof(T)));
+    if (str == 1 && nlines >= 32) {
+        const i64 grid = (nlines + 32 * PF_WARPS - 1) / (32 * PF_WARPS);
+        auto kern = line_solve_tile<T, 8>;  // 8: measured faster than 16
+        if (dyn) GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        kern<<<(unsigned)grid, 32 * PF_WARPS, dyn, s>>>(A, (T*)tmp.p, n, nlines, sys, use_ck);
+    } else {
+        const i64 grid = (nlines + 127) / 128;
+        auto kern = line_solve_global<T>;
+        if (dyn) GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        kern<<<(unsigned)grid, 128, dyn, s>>>(A, (T*)tmp.p, n, str, str, nlines, sys, use_ck);
+    }
+    count_launch();
+    GB_CUDA(cudaGetLastError());
+    return GB_OK;
+}
+
 template <typename T> int invert_impl(T* A, int ndim, const i64* dims, int bc, int order, const int* dimlist, int ndl, cudaStream_t s) {
     if (order < GB_QUADRATIC) return GB_OK;  // src/interp.jl:909-912
-    i64 total = 1;
-    std::vector<i64> strides(ndim);
-    for (int d = 0; d < ndim; d++) { strides[d] = total; total *= dims[d]; }
-    if (total == 0) return GB_OK;
-    T* tmp = nullptr;
-    int rc = GB_OK;
-    for (int k = 0; k < ndl && rc == GB_OK; k++) {
-        const int idim = dimlist[k];
-        if (idim < 0 || idim >= ndim) { rc = fail(GB_ERR_ARG, "dimlist entry out of range"); break; }
-        const i64 n = dims[idim], str = strides[idim], nlines = total / n;
-        HostSys<T> hs;
-        rc = hs.setup(bc, order, n);
-        if (rc) break;
-        // one device blob: dl | d | du | du2 | rd | swap
-        const size_t nT = (size_t)(5 * n);
-        const size_t bytes = nT * sizeof(T) + (size_t)n * sizeof(int);
-        std::vector<unsigned char> blob(bytes, 0);
-        T* hb = reinterpret_cast<T*>(blob.data());
-        std::copy(hs.dl.begin(), hs.dl.end(), hb);
-        std::copy(hs.d.begin(), hs.d.end(), hb + n);
-        std::copy(hs.du.begin(), hs.du.end(), hb + 2 * n);
-        std::copy(hs.du2.begin(), hs.du2.end(), hb + 3 * n);
-        for (i64 i = 0; i < n; i++) hb[4 * n + i] = (T)1 / hs.d[i];  // correctly rounded reciprocals of the pivots
-        int* hsw = reinterpret_cast<int*>(blob.data() + nT * sizeof(T));
-        std::copy(hs.swap.begin(), hs.swap.end(), hsw);
-        unsigned char* dblob = nullptr;
-        GB_CUDA(cudaMallocAsync((void**)&dblob, bytes, s));
-        // blob is pageable: cudaMemcpyAsync stages it before returning, so the vector may die.
-        GB_CUDA(cudaMemcpyAsync(dblob, blob.data(), bytes, cudaMemcpyHostToDevice, s));
-        LineSys<T> sys;
-        T* db = reinterpret_cast<T*>(dblob);
-        sys.dl = db; sys.d = db + n; sys.du = db + 2 * n; sys.du2 = db + 3 * n; sys.rd = db + 4 * n;
-        sys.swap = reinterpret_cast<const int*>(dblob + nT * sizeof(T));
-        sys.woodbury = hs.woodbury ? 1 : 0;
-        sys.vcol0 = (int)hs.vcol[0]; sys.vcol1 = (int)hs.vcol[1];
-        for (int i = 0; i < 4; i++) sys.cp[i] = hs.cp[i];
-        {  // stationary interior: longest runs of bit-identical factors (forward steps end before n-2: sparse_step's k1 row)
-            auto same = [](T a, T b) { return std::memcmp(&a, &b, sizeof(T)) == 0; };
-            auto longest = [&](i64 lo, i64 hi, auto eq, i64& r0, i64& r1) {
-                r0 = r1 = 0;
-                for (i64 i = lo; i < hi;) {
-                    i64 j = i + 1;
-                    while (j < hi && eq(i, j)) j++;
-                    if (j - i > r1 - r0) { r0 = i; r1 = j; }
-                    i = j;
-                }
-            };
-            longest(0, n - 2, [&](i64 i, i64 j) { return !hs.swap[i] && !hs.swap[j] && same(hs.dl[i], hs.dl[j]); }, sys.f0, sys.f1);
-            if (sys.f1 - sys.f0 < 2 || hs.swap[sys.f0]) sys.f0 = sys.f1 = 0;
-            longest(0, n - 2, [&](i64 i, i64 j) { return same(hs.du[i], hs.du[j]) && same(hs.du2[i], hs.du2[j]) && same(hs.d[i], hs.d[j]); }, sys.b0, sys.b1);
-            if (sys.b1 - sys.b0 < 2) sys.b0 = sys.b1 = 0;
-            sys.cdl = n > 1 ? hs.dl[sys.f0] : (T)0;
-            sys.cdu = n > 2 ? hs.du[sys.b0] : (T)0;
-            sys.cdu2 = n > 2 ? hs.du2[sys.b0] : (T)0;
-            sys.cd = hs.d[sys.b0];
-            sys.crd = (T)1 / hs.d[sys.b0];
-        }
-
-        // Woodbury: checkpoints of the second solve's RHS in shared memory when they fit, else an array-sized scratch
-        const size_t ck_bytes = hs.woodbury && n >= 3 ? (size_t)((n - 2 + PF_U - 1) / PF_U) * 128 * sizeof(T) : 0;
-        const int use_ck = hs.woodbury && ck_bytes > 0 && ck_bytes <= 64 * 1024;
-        const size_t dyn = use_ck ? ck_bytes : 0;
-        if (hs.woodbury && !use_ck && !tmp) GB_CUDA(cudaMallocAsync((void**)&tmp, (size_t)total * sizeof(T), s));
-        if (str == 1 && nlines >= 32) {
-            const i64 grid = (nlines + 32 * PF_WARPS - 1) / (32 * PF_WARPS);
-            auto kern = line_solve_tile<T, 8>;  // 8: measured faster than 16
-            if (dyn) GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-            kern<<<(unsigned)grid, 32 * PF_WARPS, dyn, s>>>(A, use_ck ? nullptr : tmp, n, nlines, sys, use_ck);
-        } else {
-            const i64 grid = (nlines + 127) / 128;
-            auto kern = line_solve_global<T>;
-            if (dyn) GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-            kern<<<(unsigned)grid, 128, dyn, s>>>(A, use_ck ? nullptr : tmp, n, str, str, nlines, sys, use_ck);
-        }
-        count_launch();
-        GB_CUDA(cudaGetLastError());
-        GB_CUDA(cudaFreeAsync(dblob, s));
+    for (int k = 0; k < ndl; k++) {
+        const int rc = sweep_exact<T>(A, ndim, dims, bc, order, dimlist[k], s);
+        if (rc) return rc;
     }
-    if (tmp) GB_CUDA(cudaFreeAsync(tmp, s));
-    return rc;
+    return GB_OK;
+}
+
+// filledges!(A, val) (src/utilities.jl:22-33): one thread per element, only edge elements are written
+struct EdgeDims { i64 d[MAXG]; int n; };
+template <typename T> __global__ void __launch_bounds__(256) filledges_kernel(T* __restrict__ A, i64 total, EdgeDims e, T val) {
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (i64)gridDim.x * blockDim.x) {
+        i64 rem = k;
+        bool edge = false;
+        for (int d = 0; d < e.n; d++) {
+            const i64 c = rem % e.d[d];
+            rem /= e.d[d];
+            edge = edge || c == 0 || c == e.d[d] - 1;
+        }
+        if (edge) A[k] = val;
+    }
 }
 
 template <typename T, int N> struct PadParams { i64 od[N]; i64 id[N]; };
@@ -614,6 +670,27 @@ int invert_device(int dtype, int ndim, const i64* dims, void* data, int bc, int 
     if (dtype == GB_F64) return invert_impl<double>((double*)data, ndim, dims, bc, order, dimlist, ndl, s);
     if (dtype == GB_F32) return invert_impl<float>((float*)data, ndim, dims, bc, order, dimlist, ndl, s);
     return fail(GB_ERR_ARG, "bad dtype");
+}
+int invert_sweep_exact(int dtype, int ndim, const i64* dims, void* data, int bc, int order, int idim, cudaStream_t s) {
+    if (order < GB_QUADRATIC) return GB_OK;
+    if (dtype == GB_F64) return sweep_exact<double>((double*)data, ndim, dims, bc, order, idim, s);
+    if (dtype == GB_F32) return sweep_exact<float>((float*)data, ndim, dims, bc, order, idim, s);
+    return fail(GB_ERR_ARG, "bad dtype");
+}
+int filledges_device(int dtype, int ndim, const i64* dims, void* data, double val, cudaStream_t s) {
+    if (ndim < 1 || ndim > MAXG) return fail(GB_ERR_UNSUPPORTED, "filledges: ndim must be 1..8");
+    EdgeDims e;
+    e.n = ndim;
+    i64 total = 1;
+    for (int d = 0; d < ndim; d++) { e.d[d] = dims[d]; total *= dims[d]; }
+    if (total <= 0) return GB_OK;
+    const int grid = (int)std::max<i64>(1, std::min<i64>((total + 255) / 256, (i64)num_sms() * 32));
+    if (dtype == GB_F64) filledges_kernel<double><<<grid, 256, 0, s>>>((double*)data, total, e, val);
+    else if (dtype == GB_F32) filledges_kernel<float><<<grid, 256, 0, s>>>((float*)data, total, e, (float)val);
+    else return fail(GB_ERR_ARG, "bad dtype");
+    count_launch();
+    GB_CUDA(cudaGetLastError());
+    return GB_OK;
 }
 int pad1_device(int dtype, int ndim, const i64* dims, const void* in, double fill, void* out, cudaStream_t s) {
     if (dtype == GB_F64) return pad1_impl<double>(ndim, dims, (const double*)in, fill, (double*)out, s);

@@ -15,7 +15,8 @@ export BoundaryCondition, BCnil, BCnan, BCna, BCreflect, BCperiodic, BCnearest, 
        AbstractInterpGrid, InterpGrid, CoordInterpGrid,
        valgrad, valgradhess, getindex!, valgrad!, valgradhess!,
        interp_invert!, pad1, restrict, prolong, restrict_size, prolong_size,
-       restrictb, restrict_extrap, prolongb, interp_channels!, InterpIrregular, InterpForward, InterpBackward
+       restrictb, restrict_extrap, prolongb, interp_channels!, InterpIrregular, InterpForward, InterpBackward,
+       filledges!, pin!, unpin!, GridComm, replicate, getindex_sharded!, valgrad_sharded!, restrict3_sharded, prolong3_sharded
 
 const LIB = get(ENV, "GRIDB200_LIB", joinpath(@__DIR__, "..", "libgridb200.so"))
 
@@ -39,6 +40,7 @@ itcode(::Type{InterpNearest}) = 0; itcode(::Type{InterpLinear}) = 1; itcode(::Ty
 dtcode(::Type{Float32}) = 0; dtcode(::Type{Float64}) = 1
 const GB_HOST, GB_DEVICE = 0, 1
 const OUT_VAL, OUT_GRAD, OUT_HESS = 1, 2, 4
+const GB_FAST, GB_TILED, GB_PLAIN, GB_SORTED = 1, 2, 4, 8     # gb_eval flags (include/gridb200.h)
 
 lasterror() = unsafe_string(ccall((:gb_last_error, LIB), Cstring, ()))
 function check(rc::Cint, bad::Int64 = -1)
@@ -149,8 +151,50 @@ struct CoordInterpGrid{T,N,BC,IT,R} <: AbstractInterpGrid{T,N,BC,IT}
     grid::InterpGrid{T,N,BC,IT}
     affine::Matrix{Float64}      # 4 x N: kind, start, step, divisor  (coordlookup :30-32)
 end
-# Julia >= 1.0 ranges: StepRangeLen(ref, step, len, offset) plays FloatRange's role
-_row(r::StepRangeLen) = Float64[0, Float64(first(r)), Float64(step(r)), 1]
+# Julia >= 1.0 float ranges are StepRangeLen; the reference's are Julia 0.4 FloatRange(start, step, len, divisor) with
+# INTEGER-valued start / step after the "lifting" of colon(start, step, stop) (base/range.jl of 0.4), and coordlookup
+# computes (divisor*x - start)/step + 1 (src/coord.jl:30): -1.0:0.1:1.0 is FloatRange(-10, 1, 21, 10), i.e.
+# (10x + 10)/1 + 1 -- NOT (x + 1)/0.1 + 1.  The lifting is reproduced here so that index coordinates carry the same bits.
+function _rat(x::Float64)                              # Base.rat of Julia 0.4: continued-fraction rational of a float
+    y = x; a = d = 1; b = c = 0
+    m = 16777216.0                                     # maxintfloat(Float32)
+    while abs(y) <= m
+        f = trunc(Int, y); y -= f
+        a, c = f * a + c, a
+        b, d = f * b + d, b
+        max(abs(a), abs(b)) > 16777216 && return c, d
+        (b != 0 && Float64(a) / Float64(b) == x) && break
+        y == 0 && break
+        y = inv(y)
+    end
+    return a, b
+end
+function _lift(start::Float64, step::Float64, stop::Float64)   # -> (start, step, len, divisor) of the FloatRange
+    step == 0 && error("range step cannot be zero")
+    start == stop && return (start, step, 1, 1.0)
+    (0 < step) != (start < stop) && return (start, step, 0, 1.0)
+    r = (stop - start) / step
+    n = round(r)
+    lo = prevfloat((prevfloat(stop) - nextfloat(start)) / n)
+    hi = nextfloat((nextfloat(stop) - prevfloat(start)) / n)
+    if lo <= step <= hi
+        a0, b = _rat(start); a = Float64(a0)
+        if b != 0 && a / Float64(b) == start
+            c0, d = _rat(step); c = Float64(c0)
+            if d != 0 && c / Float64(d) == step
+                e = lcm(b, d)
+                a *= div(e, b); c *= div(e, d)
+                (a + n * c) / Float64(e) == stop && return (a, c, Int(n) + 1, Float64(e))
+            end
+        end
+    end
+    return (start, step, floor(Int, r) + 1, 1.0)
+end
+function _row(r::StepRangeLen)
+    a, c, len, e = _lift(Float64(first(r)), Float64(step(r)), Float64(last(r)))
+    len == length(r) || return Float64[0, Float64(first(r)), Float64(step(r)), 1]   # not a colon-built range: plain affine map
+    Float64[0, a, c, e]
+end
 _row(r::StepRange{<:Integer}) = Float64[1, first(r), step(r), 1]
 _row(r::UnitRange{<:Integer}) = Float64[2, first(r), 1, 1]
 function CoordInterpGrid(coord::NTuple{N,AbstractRange}, grid::InterpGrid{T,N,BC,IT}) where {T,N,BC,IT}
@@ -170,13 +214,25 @@ function valgrad(C::CoordInterpGrid{T,N}, x::Real...) where {T,N}
 end
 
 # ---- prefilter / padding ----------------------------------------------------------------------------
-function interp_invert!(A::Array{T,N}, ::Type{BC}, ::Type{IT}, dimlist = 1:N) where {T<:Union{Float32,Float64},N,BC<:BoundaryCondition,IT<:InterpType}
+# fast = true: the line-parallel GB_FAST solver where it applies (few long lines); a few ulp of max|A| instead of bit-identical
+function interp_invert!(A::Array{T,N}, ::Type{BC}, ::Type{IT}, dimlist = 1:N; fast::Bool = false) where {T<:Union{Float32,Float64},N,BC<:BoundaryCondition,IT<:InterpType}
     dims = Int64[size(A)...]; dl = Cint[d - 1 for d in dimlist]
-    GC.@preserve A dims dl check(ccall((:gb_invert, LIB), Cint,
-        (Cint, Cint, Ptr{Int64}, Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cint}, Cint, Ptr{Cvoid}),
-        dtcode(T), N, dims, A, GB_HOST, bccode(BC), itcode(IT), dl, length(dl), C_NULL))
+    GC.@preserve A dims dl check(ccall((:gb_invert_opt, LIB), Cint,
+        (Cint, Cint, Ptr{Int64}, Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cint}, Cint, Cint, Ptr{Cvoid}),
+        dtcode(T), N, dims, A, GB_HOST, bccode(BC), itcode(IT), dl, length(dl), fast ? GB_FAST : 0, C_NULL))
     A
 end
+# filledges!(A, val), src/utilities.jl:22-33
+function filledges!(A::Array{T,N}, val) where {T<:Union{Float32,Float64},N}
+    dims = Int64[size(A)...]
+    GC.@preserve A dims check(ccall((:gb_filledges, LIB), Cint, (Cint, Cint, Ptr{Int64}, Ptr{Cvoid}, Cdouble, Cint, Ptr{Cvoid}),
+        dtcode(T), N, dims, A, Float64(val), GB_HOST, C_NULL))
+    A
+end
+# A Julia Array is pageable memory: host-buffer calls copy through the driver's staging buffers (about half the PCIe rate).
+# Arrays that are passed again and again (query batches, output buffers of an optimisation loop) can be page-locked once:
+pin!(A::Array) = (check(ccall((:gb_host_register, LIB), Cint, (Ptr{Cvoid}, Csize_t), A, sizeof(A))); A)
+unpin!(A::Array) = (check(ccall((:gb_host_unregister, LIB), Cint, (Ptr{Cvoid},), A)); A)
 function pad1(A::Array{T,N}, f::Number) where {T<:Union{Float32,Float64},N}
     out = Array{T,N}(undef, (size(A) .+ 2)...); dims = Int64[size(A)...]
     GC.@preserve A out dims check(ccall((:gb_pad1, LIB), Cint, (Cint, Cint, Ptr{Int64}, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
@@ -338,5 +394,55 @@ function getindex!(out::Vector{T}, G::InterpIrregular{T,BC,IT}, x::Vector{T}) wh
     out
 end
 Base.getindex(G::InterpIrregular{T}, x::Real) where {T} = getindex!(Vector{T}(undef, 1), G, T[x])[1]
+
+# ---- multi-GPU: one Julia process drives every GPU of the box (gb_comm_init_all; SURVEY 8b/8e) -------------------------
+# Point evaluation: the coefficients are replicated once (one ncclBroadcast), a host batch is split into contiguous ranges
+# over the devices.  restrict / prolong of a 3-D array: slabs along dim 3, one halo exchange per level
+# (src/restrict_prolong.jl:181-185, 87-100 spread over the devices; bit-identical to the single-device result).
+mutable struct GridComm
+    handle::Ptr{Cvoid}
+    ndev::Int
+end
+function GridComm(ndev::Integer)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:gb_comm_init_all, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint, Ptr{Cint}), h, ndev, C_NULL))
+    c = GridComm(h[], ndev)
+    finalizer(x -> ccall((:gb_comm_destroy, LIB), Cint, (Ptr{Cvoid},), x.handle), c)
+    c
+end
+# replicate(comm, G): G lives on device 0; returns one handle per device (the first is G's own)
+function replicate(c::GridComm, G::InterpGrid{T,N,BC,IT}) where {T,N,BC,IT}
+    hs = fill(C_NULL, c.ndev); hs[1] = G.handle
+    stored = Vector{Int64}(undef, 8); dt = Ref{Cint}(0); nd = Ref{Cint}(0)
+    check(ccall((:gb_grid_info, LIB), Cint, (Ptr{Cvoid}, Ref{Cint}, Ref{Cint}, Ptr{Int64}, Ptr{Int64}, Ptr{Cint}, Ptr{Cint}, Ptr{Cdouble}),
+                G.handle, dt, nd, C_NULL, stored, C_NULL, C_NULL, C_NULL))
+    check(ccall((:gb_grid_replicate, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Ptr{Cvoid}}, Cint, Cint, Ptr{Int64}, Cint, Cint, Cdouble),
+                c.handle, 0, hs, dtcode(T), N, stored, bccode(BC), itcode(IT), Float64(G.fillval)))
+    hs      # hs[2:end] are owned by the caller: gb_grid_destroy them when done
+end
+function _eval_sharded!(c::GridComm, hs::Vector{Ptr{Cvoid}}, mask::Int, X::Matrix{Float64}, v, g, h)
+    bad = Ref{Int64}(-1)
+    rc = GC.@preserve X v g h hs ccall((:gb_eval_sharded, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Cint, Int64, Ptr{Cvoid}, Cint, Ptr{Cdouble}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ref{Int64}),
+        c.handle, hs, mask, size(X, 2), X, 1, C_NULL, v === nothing ? C_NULL : pointer(v), g === nothing ? C_NULL : pointer(g),
+        h === nothing ? C_NULL : pointer(h), 0, bad)
+    check(rc, bad[])
+end
+getindex_sharded!(out::Vector, c::GridComm, hs::Vector{Ptr{Cvoid}}, X::Matrix{Float64}) = (_eval_sharded!(c, hs, OUT_VAL, X, out, nothing, nothing); out)
+valgrad_sharded!(v::Vector, g::Matrix, c::GridComm, hs::Vector{Ptr{Cvoid}}, X::Matrix{Float64}) = (_eval_sharded!(c, hs, OUT_VAL | OUT_GRAD, X, v, g, nothing); v)
+# slabs[i]: device pointer (gb_device_alloc) to planes gb_shard_range(size3, i-1, ndev) of the global array on device i-1;
+# the outputs are device pointers the caller allocated for planes gb_shard_range(restrict_size(size3), i-1, ndev)
+function restrict3_sharded(c::GridComm, ::Type{T}, gdims::NTuple{3,Int}, slabs::Vector{Ptr{Cvoid}}, outs::Vector{Ptr{Cvoid}}, scale::Real = 1.0) where {T<:Union{Float32,Float64}}
+    dims = Int64[gdims...]
+    check(ccall((:gb_restrict3_sharded, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Int64}, Ptr{Ptr{Cvoid}}, Cdouble, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}),
+                c.handle, dtcode(T), dims, slabs, Float64(scale), outs, C_NULL))
+    outs
+end
+function prolong3_sharded(c::GridComm, ::Type{T}, gdims::NTuple{3,Int}, target::NTuple{3,Int}, slabs::Vector{Ptr{Cvoid}}, outs::Vector{Ptr{Cvoid}}) where {T<:Union{Float32,Float64}}
+    dims = Int64[gdims...]; odims = Int64[target...]
+    check(ccall((:gb_prolong3_sharded, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Int64}, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}),
+                c.handle, dtcode(T), dims, slabs, odims, outs, C_NULL))
+    outs
+end
 
 end # module

@@ -65,8 +65,17 @@ enum {
        gathers straight from global memory ("plain").  Callers whose queries are spatially coherent
        (lattices, image warps, points pre-sorted by cell) should pass GB_PLAIN: measured 1.6-2.3x
        faster than the default on such batches (profiles/README.md). */
-    GB_TILED = 2, /* force the binned shared-memory path */
-    GB_PLAIN = 4  /* force the plain path */
+    GB_TILED = 2, /* force the binned shared-memory path (compiled for 2-D / 3-D Quadratic and Cubic; ignored elsewhere) */
+    GB_PLAIN = 4, /* force the plain path */
+    /* Hint: the batch is grouped by location (sorted by grid tile, Morton order, binned once and evaluated many times).
+       The tiled path detects such batches by itself -- the binning pass counts how often consecutive queries change
+       tile -- and then evaluates them IN PLACE: no permutation of the queries, no un-permutation of the results.
+       The hint only lowers the detection threshold (average run of 32 instead of 256 queries per tile visit;
+       GB_SORTED_MIN_RUN overrides both).  Results are bit-identical in every case. */
+    GB_SORTED = 8,
+    /* gb_invert_opt / gb_grid_create_opt with GB_FAST: the prefilter runs as a line-parallel solver (one line per
+       warp, parallel cyclic reduction of the interior recurrences) instead of the reference's sequential LU sweep;
+       same solution to a few ulp of max|f| instead of bit for bit. */
 };
 
 int gb_version(void);
@@ -78,9 +87,11 @@ int64_t gb_launch_count(void);
 /* Stage timing of the tiled evaluation (measurement aid for bench.py's roofline line; no reference
    counterpart).  gb_profile_enable(1) makes every tiled gb_eval* call record CUDA events on its
    launch stream around its stages; gb_profile_read waits for the last such call and returns the
-   stage durations in milliseconds: ms[0] tile_hist, [1] tile_offsets (3 small kernels),
-   [2] tile_scatter, [3] eval_brick, [4] eval_deferred, [5] unpermute.  n = capacity of ms;
-   *nstages = 6, or 0 when no tiled call ran since profiling was enabled. */
+   stage durations in milliseconds: ms[0] tile_hist (+ the grouped-batch decision), [1] tile_offsets (3 small
+   kernels), [2] tile_scatter, [3] eval_brick, [4] eval_deferred, [5] unpermute (stages of the path not taken --
+   sorted vs grouped batches, see GB_SORTED -- cost an empty launch each).  n = capacity of ms;
+   *nstages = 6, or 0 when no tiled call ran since profiling was enabled.  With n >= 7, ms[6] = 1.0 when the call
+   found the batch grouped by tile and evaluated it in place, else 0.0. */
 int gb_profile_enable(int on);
 int gb_profile_read(double* ms, int n, int* nstages);
 
@@ -130,6 +141,19 @@ int gb_grid_destroy(gb_grid* g);
  * a no-op for Nearest/Linear (:909-912). */
 int gb_invert(int dtype, int ndim, const int64_t* dims, void* data, int mem, int bc, int order,
               const int* dimlist, int ndimlist, void* stream);
+/* The same with flags: GB_EXACT (= gb_invert: the reference's LU / Woodbury operation order, bit-identical to the
+ * oracle) or GB_FAST (line-parallel solver: every line is solved by a whole warp -- the tridiagonal system's two
+ * one-term recurrences are evaluated by warp-level scans, the boundary rows / Woodbury corners by a rank-2
+ * correction -- so grids with few long lines, e.g. an 8192 x 8192 image, fill the machine; agrees with the exact
+ * solve to a few ulp of max|f|, the tolerance north_star states). */
+int gb_invert_opt(int dtype, int ndim, const int64_t* dims, void* data, int mem, int bc, int order,
+                  const int* dimlist, int ndimlist, int flags, void* stream);
+/* gb_grid_create with flags for the prefilter (GB_EXACT / GB_FAST as in gb_invert_opt). */
+int gb_grid_create_opt(gb_grid** out, int dtype, int ndim, const int64_t* dims, const void* samples, int mem,
+                       int bc, int order, double fill, int flags, void* stream);
+/* filledges!(A, val) (src/utilities.jl:22-33): every element with an index equal to 1 or size(A, d) in some
+ * dimension d is set to val, in place. */
+int gb_filledges(int dtype, int ndim, const int64_t* dims, void* data, double val, int mem, void* stream);
 /* pad1(A, f, 1:N) (src/interp.jl:1305-1310): out has dims+2 */
 int gb_pad1(int dtype, int ndim, const int64_t* dims, const void* in, double fill, void* out, int mem, void* stream);
 
@@ -220,6 +244,62 @@ int gb_prolong3(int dtype, const int64_t* dims, const void* in, const int64_t* o
 int gb_restrict12(int dtype, int ndim, const int64_t* dims, const void* in, double scale, void* out, int mem, void* stream);
 int gb_prolong12(int dtype, int ndim, const int64_t* dims, const void* in, int64_t m1, int64_t m2, void* out, int mem,
                  void* stream);
+
+/* ---- multi-GPU (SURVEY.md 8b "*_init(ndev, dev_ids) / *_shutdown", 8e) ---------------------------------------
+ * The reference is single-process and single-threaded; these entry points have no reference counterpart beyond the
+ * functions whose work they spread: getindex / valgrad / valgradhess batches (src/interp.jl:142-270) shard by query
+ * range over replicated coefficients, restrict(A, [true,true,true]) / prolong(A, sizes)
+ * (src/restrict_prolong.jl:181-185, 87-100) shard by slabs along dim 3 with one halo exchange per call.
+ *
+ * A communicator owns one or more LOCAL ranks (a device, an NCCL communicator, a communication stream):
+ *   gb_comm_init_all       one process drives `ndev` GPUs (ncclCommInitAll; dev_ids NULL = 0..ndev-1): a Julia host
+ *                          reaches the whole box with one ccall per operation;
+ *   gb_comm_init_rank      one process per GPU: rank 0 calls gb_comm_unique_id and ships the 128 bytes through the
+ *                          launcher's channel (torch.distributed, MPI, a file); every process passes its rank; the
+ *                          calling thread's current device becomes the rank's device;
+ *   gb_comm_init_loopback  `nranks` virtual ranks on the current device, halo transfers are device copies: the whole
+ *                          sharded path on a one-GPU box (tests; no NCCL involved).
+ * NCCL is bound at run time (libnccl.so.2 as already loaded in the process, else from the loader path; GB_NCCL_LIB
+ * overrides); without it these calls return GB_ERR_UNSUPPORTED and everything else works.
+ * Per-rank array arguments (`grids`, `in_slabs`, `out_slabs`, `streams`) have one entry per LOCAL rank, in rank order. */
+typedef struct gb_comm gb_comm;
+int gb_comm_unique_id(void* id, size_t bytes /* >= 128 */);
+int gb_comm_init_rank(gb_comm** out, int nranks, int rank, const void* id, size_t bytes);
+int gb_comm_init_all(gb_comm** out, int ndev, const int* dev_ids);
+int gb_comm_init_loopback(gb_comm** out, int nranks);
+int gb_comm_size(const gb_comm* c, int* nranks, int* nlocal, int* first_rank);
+int gb_comm_destroy(gb_comm* c);
+/* Host-only geometry (no GPU needed): rank r of n owns the contiguous, balanced range [lo, hi). */
+int gb_shard_range(int64_t n, int rank, int nranks, int64_t* lo, int64_t* hi);
+/* One level of slab-sharded restrict (kind 0: n_in = fine extent along dim 3, n_out = restrict_size(n_in)) or prolong
+ * (kind 1: n_in coarse, n_out fine): own[2] = input planes rank holds, out[2] = output planes it produces, need[2] =
+ * INCLUSIVE input range those outputs read (need[1] < need[0]: none), ext[2] = planes held after the exchange;
+ * transfers = rows (src, dst, first_plane, count) of the WHOLE exchange (identical on every rank), at most max_transfers
+ * rows written, *ntransfers = their number.  Any out pointer may be NULL. */
+int gb_slab_plan(int kind, int64_t n_in, int64_t n_out, int rank, int nranks, int64_t* own, int64_t* out, int64_t* need,
+                 int64_t* ext, int64_t* transfers, int max_transfers, int* ntransfers);
+/* One ncclBroadcast of the stored coefficient array from `src_rank` to every rank.  grids[i]: the source rank's
+ * entry is its grid (any resident layout); every other local entry receives a new handle (gb_grid_destroy it).
+ * Every rank passes the same dtype / stored_dims / bc / order / fill (gb_grid_info of the source). */
+int gb_grid_replicate(gb_comm* c, int src_rank, gb_grid** grids, int dtype, int ndim, const int64_t* stored_dims, int bc,
+                      int order, double fill);
+/* gb_eval on a HOST batch (N x nq layout: x_qstride = N, x_dstride = 1) split into contiguous ranges over the LOCAL
+ * devices, each running the pipelined host-buffer path concurrently; *first_invalid is the smallest offending index. */
+int gb_eval_sharded(gb_comm* c, gb_grid* const* grids, int out_mask, int64_t nq, const void* x, int xdtype,
+                    const double* affine, void* val, void* grad, void* hess, int flags, int64_t* first_invalid);
+/* restrict(A, [true,true,true], scale) / prolong(A, out_dims) of a 3-D array sharded by slabs along dim 3: local rank i
+ * (global rank r) passes DEVICE planes gb_shard_range(global_dims[2], r) in in_slabs[i] and receives planes
+ * gb_shard_range(out extent along dim 3, r) in out_slabs[i].  Interior planes are computed while the halo planes
+ * travel (grouped ncclSend/ncclRecv on the communication stream); boundary planes follow.  Bit-identical to the
+ * unsharded gb_restrict3 / gb_prolong3.  streams: NULL (library streams; the call returns when the results are in
+ * place) or one cudaStream_t per local rank (work is enqueued; later work on that stream is ordered after it). */
+int gb_restrict3_sharded(gb_comm* c, int dtype, const int64_t* global_dims, const void* const* in_slabs, double scale,
+                         void* const* out_slabs, void* const* streams);
+int gb_prolong3_sharded(gb_comm* c, int dtype, const int64_t* global_dims, const void* const* in_slabs,
+                        const int64_t* out_dims, void* const* out_slabs, void* const* streams);
+/* Timing of the last sharded restrict / prolong call, 4 doubles per local rank: total ms, interior-kernel ms, time the
+ * halo landed after the interior kernel had finished (ms; 0 = fully hidden), halo bytes received.  Waits for the call. */
+int gb_comm_stats(gb_comm* c, double* out, int n, int* nout);
 
 /* ---- device / pinned memory helpers (device-resident query and output buffers) -------------- */
 int gb_device_alloc(void** ptr, size_t bytes);

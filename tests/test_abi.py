@@ -115,3 +115,37 @@ def test_argument_validation_without_gpu(gb):
     with pytest.raises(gb.ErrorException):
         gb.pad1(np.zeros(3), gb.BCfill)  # src/interp.jl:1304
     assert gb.npoints(gb.InterpCubic) == 4 and gb.npoints(gb.InterpNearest) == 1
+
+
+def _build_abi_smoke(tmp_path):
+    import shutil
+    import subprocess
+
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    exe = str(tmp_path / "abi_smoke")
+    pkg = os.path.join(ROOT, "grid.jl_b200")
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Werror", "-O1", "-o", exe, os.path.join(ROOT, "tests", "native", "abi_smoke.c"), "-L", pkg,
+                           "-l:libgridb200.so", "-Wl,-rpath," + pkg, "-lm"])
+    return exe
+
+
+def test_c_caller_prototypes(gb, tmp_path):
+    """tests/native/abi_smoke.c: a plain-C caller with the Julia binding's argument types compiles against the header with
+    -Werror, links against the library and runs its host-only part."""
+    import subprocess
+
+    exe = _build_abi_smoke(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "gridb200 10100" in out.stdout
+
+
+@pytest.mark.gpu
+def test_c_caller_runs_the_readme_example(gb, tmp_path):
+    """the same program end to end on the GPU: gb_grid_create -> gb_eval -> gb_grid_destroy, README values bit for bit"""
+    import subprocess
+
+    exe = _build_abi_smoke(tmp_path)
+    out = subprocess.run([exe, "run"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "abi smoke ok" in out.stdout, out.stdout + out.stderr

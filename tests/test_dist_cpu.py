@@ -201,3 +201,21 @@ def test_shard_range_and_plan_cover():
             if L // w >= 8:
                 plan = D.SlabPlan("restrict", L, n, w)
                 assert all(c <= 3 for (_, _, _, c) in plan.transfers)
+
+
+def test_c_plan_matches_python_plan():
+    """gb_slab_plan / gb_shard_range (host-only C ABI, csrc/comm.cu) against the Python plan the gloo tests exercise."""
+    import grid_jl_b200  # noqa: F401
+    import grid_jl_b200.dist as D
+
+    for L in (5, 8, 16, 17, 64, 65, 1024, 513, 33):
+        for w in (1, 2, 3, 4, 8, 16):
+            n = D.restrict_size(L)
+            for kind, n_in, n_out in (("restrict", L, n), ("prolong", n, L)):
+                plan = D.SlabPlan(kind, n_in, n_out, w)
+                for r in range(w):
+                    own, out, need, ext, tr = D.c_slab_plan(kind, n_in, n_out, r, w)
+                    assert own == plan.own[r] and out == plan.out[r] and ext == plan.ext_range(r)
+                    if plan.need[r][1] >= plan.need[r][0]:
+                        assert need == plan.need[r]
+                    assert sorted(tr) == sorted(plan.transfers)

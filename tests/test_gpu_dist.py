@@ -1,6 +1,10 @@
-"""Multi-GPU tests (need >= 2 CUDA devices; skipped otherwise): NCCL broadcast of the coefficients,
-query sharding and the slab-sharded restrict/prolong with a real halo exchange.  Launched in-process
-with torch.multiprocessing, one process per GPU."""
+"""Multi-GPU tests with real NCCL traffic (need >= 2 CUDA devices; skipped otherwise -- the same code paths run on one
+GPU with virtual ranks in test_gpu_round2.py::test_comm_loopback_*):
+  * one process per GPU (torch.multiprocessing): gb_comm_init_rank through torch.distributed, gb_grid_replicate
+    (ncclBroadcast of the coefficients), query sharding, gb_restrict3_sharded / gb_prolong3_sharded (grouped
+    ncclSend/ncclRecv halo exchange overlapped with the interior planes);
+  * one process driving every GPU (gb_comm_init_all): the same through the single-process entry points, plus
+    gb_eval_sharded on host buffers."""
 import os
 import socket
 import sys
@@ -83,3 +87,52 @@ def test_multi_gpu_broadcast_shard_and_halo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(all(t) for t in res), res
+
+
+def test_single_process_all_devices():
+    """gb_comm_init_all: what a Julia host uses -- one process, every GPU of the box."""
+    import ctypes as C
+
+    import torch
+
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    ndev = min(ndev, 8)
+    sys.path.insert(0, ROOT)
+    import grid_jl_b200 as gb
+    import grid_jl_b200.dist as D
+    from oracle import oracle as O
+
+    shape = (48, 40, 70)
+    A = O.synth(np.float64, int(np.prod(shape)), seed=4).reshape(shape, order="F")
+    ref = O.restrict_flags(A, [True, True, True])
+    refp = O.prolong_sizes(ref, list(shape))
+    comm = D.Comm.all_devices(ndev)
+    try:
+        L3, n3 = shape[2], D.restrict_size(shape[2])
+        fine = [gb.jl_from_numpy(np.asfortranarray(A[:, :, slice(*D.shard_range(L3, r, ndev))]), device="cuda:%d" % r) for r in range(ndev)]
+        coarse = comm.restrict3(fine, shape, 1.0, use_streams=False)
+        for r in range(ndev):
+            k0, k1 = D.shard_range(n3, r, ndev)
+            assert np.array_equal(gb.jl_to_numpy(coarse[r]), ref[:, :, k0:k1])
+        up = comm.prolong3(coarse, ref.shape, shape, use_streams=False)
+        for r in range(ndev):
+            f0, f1 = D.shard_range(L3, r, ndev)
+            assert np.array_equal(gb.jl_to_numpy(up[r]), refp[:, :, f0:f1])
+        assert sum(s["halo_bytes"] for s in comm.stats()) > 0
+        # replicate + host batch split over the devices
+        co = O.make_coefs(A, "nan", "cubic")
+        with torch.cuda.device(0):
+            g0 = gb.InterpGrid(gb.jl_from_numpy(A, device="cuda:0"), gb.BCnan, gb.InterpCubic)
+        grids = comm.replicate([g0] + [None] * (ndev - 1), 0, (g0.stored_shape, np.float64, gb.BCnan, gb.InterpCubic, float("nan")))
+        assert all(np.array_equal(g.coefs, co) for g in grids)
+        X = 1.0 + O.synth(np.float64, 3 * 300_000, seed=6).reshape(300_000, 3) * (np.array(shape) - 1.0)
+        ov, og, _, _ = O.evaluate(co, "nan", "cubic", X, 3)
+        v, gr = np.empty(len(X)), np.empty((len(X), 3))
+        L = gb._lib
+        hs = (C.c_void_p * ndev)(*[g._h.value for g in grids])
+        L.check(L.lib().gb_eval_sharded(comm._h, hs, 3, len(X), X.ctypes.data, L.GB_F64, None, v.ctypes.data, gr.ctypes.data, None, 0, None))
+        assert np.array_equal(v, ov) and np.array_equal(gr, og)
+    finally:
+        comm.close()

@@ -1,0 +1,306 @@
+"""GPU tests of the round-2 paths, through the C ABI, against the CPU oracle:
+grouped ("sorted") batches evaluated in place, TMA brick staging vs the cp.async fallback, the GB_FAST prefilter
+(kernels of prefilter_fast.cu), filledges!, stream ordering of device-built grids, and the multi-GPU entry points
+(gb_comm_*) on virtual ranks of one GPU."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EPS64, EPS32 = 2.220446049250313e-16, 1.1920929e-07
+
+
+def same(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return a.shape == b.shape and a.dtype == b.dtype and np.array_equal(a, b, equal_nan=True)
+
+
+def tile_key(X, shape):
+    """a spatial key that groups queries by (16 x 16 x 8)-cell blocks (2-D: 64 x 32), dim 1 fastest"""
+    fl = np.floor(X).astype(np.int64)
+    if X.shape[1] == 3:
+        return ((fl[:, 2] >> 3) * 4096 + (fl[:, 1] >> 4)) * 4096 + (fl[:, 0] >> 4)
+    return (fl[:, 1] >> 5) * 65536 + (fl[:, 0] >> 6)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("bc,order,shape", [("nan", "cubic", (70, 66, 50)), ("reflect", "quadratic", (300, 200)), ("nan", "quadratic", (64, 40, 33)),
+                                            ("periodic", "cubic" if False else "quadratic", (48, 40, 36))])
+def test_grouped_batches_evaluate_in_place(gb, oracle, dtype, bc, order, shape):
+    """Queries pre-sorted by tile: the tiled path detects it (profile: grouped == 1), skips both permutations, and the
+    results are bit-identical to the oracle; the same queries shuffled take the counting sort (grouped == 0)."""
+    import torch
+
+    BC = dict(nan=gb.BCnan, reflect=gb.BCreflect, periodic=gb.BCperiodic)[bc]
+    IT = dict(cubic=gb.InterpCubic, quadratic=gb.InterpQuadratic)[order]
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal(shape).astype(dtype)
+    g = gb.InterpGrid(A, BC, IT)
+    co = oracle.make_coefs(A, bc, order)
+    nq = 400_000
+    X = (1.0 + rng.random((nq, len(shape))) * (np.array(shape) - 1.0)).astype(dtype)
+    X[::1000] = -3.0  # a few invalid / wrapped locations inside the runs
+    Xs = np.ascontiguousarray(X[np.argsort(tile_key(X, shape), kind="stable")])
+    mask = 7
+    ov, og, oh, _ = oracle.evaluate(co, bc, order, Xs, mask, raise_invalid=False)
+    gb.profile_enable(True)
+    try:
+        for fast in (False, True):
+            v, gr, h = g._eval(torch.from_numpy(Xs).cuda(), mask, tiled=True, fast=fast)
+            st = gb.profile_read()
+            assert st["grouped"] == 1.0, st
+            if not fast:
+                assert same(v.cpu().numpy(), ov) and same(gr.cpu().numpy(), og) and same(h.cpu().numpy(), oh)
+            else:
+                vp, gp, hp = g._eval(torch.from_numpy(Xs).cuda(), mask, tiled=False, fast=True)
+                assert torch.equal(v, vp) or bool(((v == vp) | (v.isnan() & vp.isnan())).all())
+        v, gr, h = g._eval(torch.from_numpy(X).cuda(), mask, tiled=True)
+        assert gb.profile_read()["grouped"] == 0.0
+        ou, ogu, ohu, _ = oracle.evaluate(co, bc, order, X, mask, raise_invalid=False)
+        assert same(v.cpu().numpy(), ou) and same(gr.cpu().numpy(), ogu) and same(h.cpu().numpy(), ohu)
+        # short runs (sorted by cell in raster order): with the GB_SORTED hint still in place, without it sorted
+        Xc = np.ascontiguousarray(X[np.lexsort(tuple(np.floor(X[:, d]) for d in range(len(shape))))])
+        oc, _, _, _ = oracle.evaluate(co, bc, order, Xc, 1, raise_invalid=False)
+        for hint in (False, True):
+            vc, _, _ = g._eval(torch.from_numpy(Xc).cuda(), 1, tiled=True, sorted=hint)
+            assert same(vc.cpu().numpy(), oc)
+    finally:
+        gb.profile_enable(False)
+
+
+def test_grouped_detection_corner_cases(gb, oracle):
+    """one run only; runs longer than a work item; a batch that is not a multiple of anything; BCnil's first invalid
+    index in a grouped batch"""
+    import torch
+
+    rng = np.random.default_rng(9)
+    A = rng.standard_normal((40, 40, 40))
+    g = gb.InterpGrid(A, gb.BCnan, gb.InterpCubic)
+    co = oracle.make_coefs(A, "nan", "cubic")
+    gb.profile_enable(True)
+    try:
+        for nq in (1, 31, 2049, 70_001):
+            X = 5.0 + rng.random((nq, 3)) * 3.0  # all in one tile
+            v, gr, _ = g._eval(torch.from_numpy(X).cuda(), 3, tiled=True)
+            assert gb.profile_read()["grouped"] == 1.0
+            ov, og, _, _ = oracle.evaluate(co, "nan", "cubic", X, 3)
+            assert same(v.cpu().numpy(), ov) and same(gr.cpu().numpy(), og)
+    finally:
+        gb.profile_enable(False)
+    gn = gb.InterpGrid(A, gb.BCnil, gb.InterpCubic)
+    X = 5.0 + rng.random((5000, 3)) * 3.0
+    X[3210, 1] = 77.0
+    with pytest.raises(gb.ErrorException) as ei:
+        gn._eval(torch.from_numpy(X).cuda(), 3, tiled=True)
+    assert "query 3210" in str(ei.value)
+
+
+def test_tma_and_cp_async_staging_agree(gb, oracle):
+    """Bricks staged by TMA (row pitch a multiple of 16 bytes) and by the element-wise fallback (odd pitches; GB_NO_TMA=1
+    in a child process) give the oracle's bits."""
+    import torch
+
+    rng = np.random.default_rng(21)
+    for dtype, shapes in ((np.float64, [(66, 41, 37), (67, 41, 37), (130, 90)]), (np.float32, [(68, 33, 30), (66, 33, 30), (131, 77)])):
+        for shape in shapes:
+            A = rng.standard_normal(shape).astype(dtype)
+            bc, order = ("nan", "cubic") if len(shape) == 3 else ("reflect", "quadratic")
+            g = gb.InterpGrid(A, gb.BCnan if bc == "nan" else gb.BCreflect, gb.InterpCubic if order == "cubic" else gb.InterpQuadratic)
+            co = oracle.make_coefs(A, bc, order)
+            X = (0.5 + rng.random((120_000, len(shape))) * (np.array(shape))).astype(dtype)
+            ov, og, _, _ = oracle.evaluate(co, bc, order, X, 3, raise_invalid=False)
+            v, gr, _ = g._eval(torch.from_numpy(X).cuda(), 3, tiled=True)
+            assert same(v.cpu().numpy(), ov) and same(gr.cpu().numpy(), og), (dtype, shape)
+    code = r"""
+import sys; sys.path.insert(0, %r)
+import numpy as np, torch
+import grid_jl_b200 as gb
+from oracle import oracle as O
+rng = np.random.default_rng(22)
+A = rng.standard_normal((66, 41, 37))
+g = gb.InterpGrid(A, gb.BCnan, gb.InterpCubic)
+co = O.make_coefs(A, "nan", "cubic")
+X = 0.5 + rng.random((100000, 3)) * np.array(A.shape)
+ov, og, _, _ = O.evaluate(co, "nan", "cubic", X, 3, raise_invalid=False)
+v, gr, _ = g._eval(torch.from_numpy(X).cuda(), 3, tiled=True)
+assert np.array_equal(v.cpu().numpy(), ov, equal_nan=True) and np.array_equal(gr.cpu().numpy(), og, equal_nan=True)
+print("ok")
+""" % ROOT
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, GB_NO_TMA="1"), capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("bc,order", [("nan", "quadratic"), ("reflect", "quadratic"), ("periodic", "quadratic"), ("nearest", "quadratic"), ("nan", "cubic")])
+def test_fast_prefilter_kernels(gb, oracle, dtype, bc, order):
+    """interp_invert!(..., fast=True): TMA-tiled dim-1 sweeps, strided sweeps, dense end rows, ping-pong buffers, and the
+    sweeps that fall back to the exact kernel -- against the oracle's exact solve: <= 6 ulp of max|A| per sweep chain
+    (Float64; the oracle's own rounding included), <= 1e-5 relative (Float32)."""
+    import torch
+
+    BC = dict(nan=gb.BCnan, reflect=gb.BCreflect, periodic=gb.BCperiodic, nearest=gb.BCnearest)[bc]
+    IT = gb.InterpCubic if order == "cubic" else gb.InterpQuadratic
+    rng = np.random.default_rng(31)
+    eps = EPS64 if dtype == np.float64 else EPS32
+    for shape in [(1024, 640), (512, 300), (300, 512), (4096,), (260, 40, 288), (8192, 96), (1000, 33)]:
+        A = np.asfortranarray(rng.standard_normal(shape).astype(dtype))
+        ref = oracle.invert(A, bc, order)
+        tol = (6 * len(shape) * eps if dtype == np.float64 else 1e-5) * float(np.abs(ref).max())
+        for dev in (True, False):
+            B = gb.jl_from_numpy(A) if dev else A.copy(order="F")
+            gb.interp_invert_(B, BC, IT, fast=True)
+            got = gb.jl_to_numpy(B) if dev else B
+            assert np.abs(got.astype(np.float64) - ref.astype(np.float64)).max() <= tol, (shape, dev)
+        # a dimlist subset (odd number of flipping sweeps in place) and exactness of the default mode next to it
+        if len(shape) >= 2:
+            B = gb.jl_from_numpy(A)
+            gb.interp_invert_(B, BC, IT, dimlist=[1], fast=True)
+            r1 = oracle.invert(A, bc, order, dimlist=[0])
+            assert np.abs(gb.jl_to_numpy(B).astype(np.float64) - r1.astype(np.float64)).max() <= tol
+        B = gb.jl_from_numpy(A)
+        gb.interp_invert_(B, BC, IT)
+        assert same(gb.jl_to_numpy(B), ref)
+
+
+def test_fast_prefilter_grid_construction(gb, oracle):
+    """InterpGrid(..., fast_prefilter=True) on an image-like grid: coefficients within tolerance of the oracle's, on-grid
+    reproduction (test/grid.jl:50-98), and evaluation identical to a grid adopted from those same coefficients."""
+    import torch
+
+    rng = np.random.default_rng(33)
+    for dtype, bc, order, shape in ((np.float32, "reflect", "quadratic", (2048, 1024)), (np.float64, "nan", "cubic", (700, 300)), (np.float64, -2.5, "quadratic", (600, 512))):
+        A = np.asfortranarray(rng.standard_normal(shape).astype(dtype))
+        BC = bc if not isinstance(bc, str) else dict(nan=gb.BCnan, reflect=gb.BCreflect)[bc]
+        IT = gb.InterpCubic if order == "cubic" else gb.InterpQuadratic
+        g = gb.InterpGrid(gb.jl_from_numpy(A), BC, IT, fast_prefilter=True)
+        co = oracle.make_coefs(A, "fill" if not isinstance(bc, str) else bc, order, bc if not isinstance(bc, str) else None)
+        eps = EPS64 if dtype == np.float64 else EPS32
+        assert np.abs(g.coefs.astype(np.float64) - co.astype(np.float64)).max() <= 16 * eps * float(np.abs(co).max())
+        idx = np.stack([rng.integers(1, n + 1, 20000) for n in shape], axis=1).astype(np.float64)
+        v = gb.getindex_batch(g, idx)
+        a = A[tuple((idx[:, d] - 1).astype(int) for d in range(2))]
+        assert np.abs(v - a).max() < (1e-12 if dtype == np.float64 else 2e-5)
+        g2 = gb.InterpGrid.from_coefs(g.coefs, BC if isinstance(bc, str) else gb.BCfill, IT)
+        X = 1.0 + rng.random((50000, 2)) * (np.array(shape) - 1.0)
+        assert same(gb.getindex_batch(g, X), gb.getindex_batch(g2, X))
+
+
+def test_filledges(gb):
+    """filledges!(A, val), src/utilities.jl:22-33"""
+    rng = np.random.default_rng(41)
+    for shape in [(7,), (5, 6), (4, 5, 6), (3, 4, 2, 5), (1, 9), (2, 2, 2)]:
+        for dtype in (np.float64, np.float32):
+            A = np.asfortranarray(rng.standard_normal(shape).astype(dtype))
+            ref = A.copy(order="F")
+            for d in range(A.ndim):
+                sl = [slice(None)] * A.ndim
+                sl[d] = [0, shape[d] - 1]
+                ref[tuple(sl)] = -7.25
+            B = A.copy(order="F")
+            gb.filledges_(B, -7.25)
+            assert same(B, ref)
+            D = gb.jl_from_numpy(A)
+            gb.filledges_(D, -7.25)
+            assert same(gb.jl_to_numpy(D), ref)
+
+
+def test_device_built_grid_is_ordered_before_host_queries(gb, oracle):
+    """A grid built from a device tensor on a non-default stream, then queried through the HOST path right away (other
+    streams inside the library): the readers wait for the construction (abi.cu eval_host)."""
+    import torch
+
+    n = 200
+    A = oracle.synth(np.float64, n ** 3, 8).reshape((n, n, n), order="F")
+    co = oracle.make_coefs(A, "nan", "cubic")
+    X = 1.0 + oracle.synth(np.float64, 3 * 5000, 18).reshape(5000, 3) * (n - 1.0)
+    ov, og, _, _ = oracle.evaluate(co, "nan", "cubic", X, 3)
+    Ad = gb.jl_from_numpy(A)
+    st = torch.cuda.Stream()
+    for _ in range(3):
+        with torch.cuda.stream(st):
+            big = torch.empty(1 << 27, device="cuda").normal_()  # keep the stream busy ahead of the construction
+            g = gb.InterpGrid(Ad, gb.BCnan, gb.InterpCubic)
+        v, gr = gb.valgrad_batch(g, X)  # numpy queries: host path, library streams
+        assert same(v, ov) and same(gr, og)
+        assert gb.valgrad(g, *X[7])[0] == ov[7]
+        assert same(g.coefs, co)
+        del big, g
+    torch.cuda.synchronize()
+
+
+def test_interp_irregular_batched_entry_points(gb):
+    rng = np.random.default_rng(43)
+    knots = np.sort(rng.random(50)) * 10
+    vals = rng.standard_normal(50)
+    G = gb.InterpIrregular(knots, vals, gb.BCnan, gb.InterpLinear)
+    x = rng.random(1000) * 10
+    assert same(gb.getindex_batch(G, x), G[x])
+    out = np.empty(1000)
+    gb.getindex_(out, G, x)
+    assert same(out, G[x])
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape,world", [((40, 36, 50), 2), ((33, 20, 64), 3), ((20, 18, 129), 5), ((12, 10, 17), 8), ((9, 8, 20), 4), ((66, 40, 128), 8)])
+def test_comm_loopback_sharded_multigrid(gb, oracle, dtype, shape, world):
+    """gb_restrict3_sharded / gb_prolong3_sharded on `world` virtual ranks of one GPU (gb_comm_init_loopback): plan, halo
+    planes, interior / boundary split and the slab kernels -- assembled slabs equal the unsharded oracle result bitwise."""
+    import torch
+
+    import grid_jl_b200.dist as D
+
+    A = oracle.synth(dtype, int(np.prod(shape)), seed=51).reshape(shape, order="F")
+    ref = oracle.restrict_flags(A, [True, True, True])
+    refp = oracle.prolong_sizes(ref, list(shape))
+    comm = D.Comm.loopback(world)
+    try:
+        assert (comm.nranks, comm.nlocal, comm.first_rank) == (world, world, 0)
+        L3, n3 = shape[2], D.restrict_size(shape[2])
+        fine = [gb.jl_from_numpy(np.asfortranarray(A[:, :, slice(*D.shard_range(L3, r, world))])) for r in range(world)]
+        for use_streams in (True, False):
+            coarse = comm.restrict3(fine, shape, 1.0, use_streams=use_streams)
+            torch.cuda.synchronize()
+            for r in range(world):
+                k0, k1 = D.shard_range(n3, r, world)
+                assert same(gb.jl_to_numpy(coarse[r]), np.asfortranarray(ref[:, :, k0:k1])), ("restrict", r)
+            st = comm.stats()
+            assert len(st) == world and all(s["total_ms"] >= 0 for s in st)
+            up = comm.prolong3(coarse, ref.shape, shape, use_streams=use_streams)
+            torch.cuda.synchronize()
+            for r in range(world):
+                f0, f1 = D.shard_range(L3, r, world)
+                assert same(gb.jl_to_numpy(up[r]), np.asfortranarray(refp[:, :, f0:f1])), ("prolong", r)
+        halo = sum(s["halo_bytes"] for s in comm.stats())
+        assert (halo > 0) == (world > 1)
+    finally:
+        comm.close()
+
+
+def test_comm_loopback_replicate_and_sharded_eval(gb, oracle):
+    import ctypes as C
+
+    import grid_jl_b200.dist as D
+
+    rng = np.random.default_rng(61)
+    A = rng.standard_normal((30, 28, 26))
+    co = oracle.make_coefs(A, "nan", "cubic")
+    comm = D.Comm.loopback(3)
+    try:
+        g0 = gb.InterpGrid(A, gb.BCnan, gb.InterpCubic)
+        grids = comm.replicate([None, g0, None], 1, (g0.stored_shape, np.float64, gb.BCnan, gb.InterpCubic, float("nan")))
+        assert grids[1] is g0 and all(same(g.coefs, co) for g in grids)
+        X = 1.0 + rng.random((100_001, 3)) * (np.array(A.shape) - 1.0)
+        X[77_777, 2] = 99.0
+        ov, og, _, _ = oracle.evaluate(co, "nan", "cubic", X, 3, raise_invalid=False)
+        v, gr = np.empty(len(X)), np.empty((len(X), 3))
+        L = gb._lib
+        hs = (C.c_void_p * 3)(*[g._h.value for g in grids])
+        bad = C.c_int64(-5)
+        L.check(L.lib().gb_eval_sharded(comm._h, hs, 3, len(X), X.ctypes.data, L.GB_F64, None, v.ctypes.data, gr.ctypes.data, None, 0, C.byref(bad)))
+        assert same(v, ov) and same(gr, og) and bad.value == -1  # BCnan: NaN, no error
+    finally:
+        comm.close()

@@ -384,6 +384,23 @@ def test_prefilter_vs_dense(oracle, bc, order, n):
     assert np.max(np.abs(M @ c - f)) < 64 * eps * np.max(np.abs(f))
 
 
+@pytest.mark.parametrize("bc,order", [("nan", "quadratic"), ("reflect", "quadratic"), ("periodic", "quadratic"), ("nearest", "quadratic"), ("nan", "cubic")])
+def test_prefilter_vs_long_double_witness(oracle, bc, order):
+    """Second witness for the prefilter's last bits (parity-unpinned by the reference's own tests): the oracle's
+    LU + Woodbury restatement against a dense long-double Gaussian elimination of the same matrix at n = 258 (the C2 line
+    length) -- within 4 ulp of max|f| for every system, Float64; within 4 Float32 ulp for Float32."""
+    from test_fast_prefilter_host import dense_matrix, solve_longdouble
+
+    n = 258
+    for dt, e in ((np.float64, eps), (np.float32, 1.1920929e-07)):
+        for seed in range(3):
+            f = np.random.default_rng(seed).standard_normal(n).astype(dt)
+            c = oracle.invert(f, bc, order)
+            truth = solve_longdouble(dense_matrix(bc, order, n, dt), f)
+            err = float(np.abs(c.astype(np.longdouble) - truth).max())
+            assert err <= 4 * e * float(np.abs(f).max()), (bc, order, dt, err / (e * float(np.abs(f).max())))
+
+
 def test_prefilter_lu_matches_lapack_gttrf(oracle):
     """The dgttrf transliteration (Julia Base lufact!(::Tridiagonal)) against LAPACK itself."""
     from scipy.linalg import lapack
