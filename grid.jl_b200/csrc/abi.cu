@@ -54,6 +54,15 @@ static void pool_keep_memory() {
 }
 
 static size_t esize(int dtype) { return dtype == GB_F64 ? 8 : 4; }
+
+// Coefficient arrays come from the stream-ordered pool (a cudaMalloc / cudaFree pair of 137 MB costs ~0.4 ms, more than
+// half the kernels of InterpGrid(...) on 258^3); the pool keeps the memory of a destroyed grid for the next one.
+static cudaError_t coefs_alloc(void** p, size_t bytes, cudaStream_t s) { return cudaMallocAsync(p, bytes ? bytes : 1, s); }
+static void coefs_free(void* p) {
+    if (!p) return;
+    cudaDeviceSynchronize();  // (what cudaFree did implicitly: no stream may still be reading the grid)
+    cudaFreeAsync(p, nullptr);
+}
 static bool ok_dtype(int d) { return d == GB_F32 || d == GB_F64; }
 
 }  // namespace gb
@@ -297,14 +306,14 @@ static bool wants_blocked(const gb_grid* g) {
 static int to_blocked_layout(gb_grid* g, cudaStream_t s) {
     void* fin = nullptr;
     const size_t bytes = (size_t)blocked_elems(g->ndim, g->stored_dims) * esize(g->dtype);
-    if (cudaMalloc(&fin, bytes) != cudaSuccess) {  // no room for the second copy the conversion needs: stay column-major
+    if (coefs_alloc(&fin, bytes, s) != cudaSuccess) {  // no room for the second copy the conversion needs: stay column-major
         cudaGetLastError();
         return GB_OK;
     }
     int rc = blocked_device(g->dtype, g->ndim, g->stored_dims, g->coefs, fin, 1, s);
     cudaError_t e = cudaStreamSynchronize(s);
-    if (rc || e != cudaSuccess) { cudaFree(fin); return rc ? rc : cuda_fail(e, "cudaStreamSynchronize"); }
-    cudaFree(g->coefs);
+    if (rc || e != cudaSuccess) { coefs_free(fin); return rc ? rc : cuda_fail(e, "cudaStreamSynchronize"); }
+    coefs_free(g->coefs);
     g->coefs = fin;
     g->blocked = 1;
     return GB_OK;
@@ -340,14 +349,14 @@ static int grid_create_impl(gb_grid** out, int dtype, int ndim, const int64_t* d
     g->total = st;
     g->nchan = nchan;
     const size_t es = esize(dtype);
-    cudaError_t e = cudaMalloc(&g->coefs, (size_t)st * (size_t)nchan * es);
+    cudaError_t e = coefs_alloc(&g->coefs, (size_t)st * (size_t)nchan * es, s);
     if (e != cudaSuccess) { delete g; return cuda_fail(e, "cudaMalloc(coefs)"); }
     void* staged = nullptr;
     const void* src = samples;
     auto cleanup = [&](int code) {
         if (staged) cudaFreeAsync(staged, s);
         cudaStreamSynchronize(s);
-        cudaFree(g->coefs);
+        coefs_free(g->coefs);
         delete g;
         return code;
     };
@@ -396,12 +405,12 @@ static int grid_create_impl(gb_grid** out, int dtype, int ndim, const int64_t* d
     if (rc) return cleanup(rc);
     if (nchan > 1) {  // resident layout of multi-valued grids: channel-interleaved (see interleave_device)
         void* fin = nullptr;
-        e = cudaMalloc(&fin, (size_t)st * (size_t)nchan * es);
+        e = coefs_alloc(&fin, (size_t)st * (size_t)nchan * es, s);
         if (e != cudaSuccess) return cleanup(cuda_fail(e, "cudaMalloc(coefs)"));
         rc = interleave_device(dtype, g->coefs, fin, st, nchan, 1, s);
-        if (rc) { cudaFree(fin); return cleanup(rc); }
+        if (rc) { coefs_free(fin); return cleanup(rc); }
         cudaStreamSynchronize(s);
-        cudaFree(g->coefs);
+        coefs_free(g->coefs);
         g->coefs = fin;
     }
     if (wants_blocked(g)) {
@@ -440,7 +449,7 @@ static int grid_from_coefs_impl(gb_grid** out, int dtype, int ndim, const int64_
     g->nchan = nchan;
     cudaStream_t s = (cudaStream_t)stream;
     const size_t bytes = (size_t)st * (size_t)nchan * esize(dtype);
-    cudaError_t e = cudaMalloc(&g->coefs, bytes);
+    cudaError_t e = coefs_alloc(&g->coefs, bytes, s);
     if (e != cudaSuccess) { delete g; return cuda_fail(e, "cudaMalloc(coefs)"); }
     if (nchan > 1) {  // adopt channel-last coefficients into the channel-interleaved resident layout
         void* tmp = nullptr;
@@ -448,23 +457,23 @@ static int grid_from_coefs_impl(gb_grid** out, int dtype, int ndim, const int64_
         if (mem == GB_HOST) {
             e = cudaMallocAsync(&tmp, bytes, s);
             if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, coefs, bytes, cudaMemcpyHostToDevice, s);
-            if (e != cudaSuccess) { if (tmp) cudaFreeAsync(tmp, s); cudaFree(g->coefs); delete g; return cuda_fail(e, "copy coefs"); }
+            if (e != cudaSuccess) { if (tmp) cudaFreeAsync(tmp, s); coefs_free(g->coefs); delete g; return cuda_fail(e, "copy coefs"); }
             src = tmp;
         }
         rc = interleave_device(dtype, src, g->coefs, st, nchan, 1, s);
         if (tmp) cudaFreeAsync(tmp, s);
         e = (mem == GB_HOST) ? cudaStreamSynchronize(s) : cudaSuccess;
-        if (rc || e != cudaSuccess) { cudaFree(g->coefs); delete g; return rc ? rc : cuda_fail(e, "copy coefs"); }
+        if (rc || e != cudaSuccess) { coefs_free(g->coefs); delete g; return rc ? rc : cuda_fail(e, "copy coefs"); }
         if (mem != GB_HOST) mark_ready(g, s);
         *out = g;
         return GB_OK;
     }
     e = cudaMemcpyAsync(g->coefs, coefs, bytes, mem == GB_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s);
     if (e == cudaSuccess && mem == GB_HOST) e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) { cudaFree(g->coefs); delete g; return cuda_fail(e, "copy coefs"); }
+    if (e != cudaSuccess) { coefs_free(g->coefs); delete g; return cuda_fail(e, "copy coefs"); }
     if (wants_blocked(g)) {
         rc = to_blocked_layout(g, s);
-        if (rc) { cudaFree(g->coefs); delete g; return rc; }
+        if (rc) { coefs_free(g->coefs); delete g; return rc; }
     } else if (mem != GB_HOST) {
         mark_ready(g, s);
     }
@@ -552,7 +561,7 @@ int gb_grid_coefs_download(const gb_grid* g, void* host_out) {
 }
 int gb_grid_destroy(gb_grid* g) {
     if (!g) return GB_OK;
-    cudaFree(g->coefs);
+    coefs_free(g->coefs);
     if (g->ready) cudaEventDestroy(g->ready);
     delete g;
     return GB_OK;

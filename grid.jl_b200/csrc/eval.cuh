@@ -831,15 +831,17 @@ __global__ void __launch_bounds__(EVAL_BLOCK, 2) eval_kernel(const EvalParams<N>
 // Tiled ("brick") evaluation: the batch is grouped by grid tile, then evaluated tile by tile out of
 // shared memory.
 //   tile_hist      key of every query (tile of its lowest tap per dimension) + per-CTA histograms in
-//                  shared memory (no global atomics), written bin-major to bh[bin][cta].  The same pass
-//                  marks RUN STARTS in a bitmap (a query whose key differs from its predecessor's, and every
-//                  2048th query) and counts them.
-//   sorted_decide  (eval_tile.cu) few run starts = the batch arrived grouped by tile (coherent callers: points
-//                  binned once, Morton / tile-sorted streams).  Then the runs themselves are the work items
-//                  (run_items), they index the CALLER's arrays, and nothing is permuted: the brick kernel reads
-//                  the coordinates and writes val / grad / hess in place, coalesced.  The decision is taken on
-//                  the device (nwork[2]); the kernels of the path not taken exit at once, so the host never
-//                  waits for it.
+//                  shared memory (no global atomics), written bin-major to bh[bin][cta].  The same pass asks
+//                  whether the batch, in the order it ARRIVED, already consists of chunks that each fit one brick:
+//                  bounding boxes of the first taps of 32 consecutive queries (warp reductions), merged up a binary
+//                  tree to chunks of 128 ... 1024 queries (group_iteration).
+//   sorted_decide  (eval_tile.cu) nearly all queries in fitting chunks = the batch is spatially grouped (sorted by
+//                  tile or cell block, Morton / Hilbert order, a lattice walked block by block, points binned once
+//                  and evaluated many times).  Then the chunks themselves are the work items (run_items), each with
+//                  the brick whose corner is its box's corner; they index the CALLER's arrays, and nothing is
+//                  permuted: the brick kernel reads the coordinates and writes val / grad / hess in place,
+//                  coalesced.  The decision is taken on the device (nwork[2]); the kernels of the path not taken
+//                  exit at once, so the host never waits for it.
 //   otherwise      a counting sort:
 //   tile_offsets   (eval_tile.cu) per-bin totals, scan, work-item list (a tile's queries split into
 //                  items of <= EVAL_CHUNK), per-(bin,cta) write cursors
@@ -922,12 +924,13 @@ template <typename T, int N, bool DIRECT> __device__ __forceinline__ void fetch_
 }
 
 // sort key of a query: the tile of its lowest tap per dimension (a locality hint only -- queries whose taps
-// leave the brick are deferred); invalid locations go to the extra last bin
+// leave the brick are deferred); invalid locations go to the extra last bin.  first[] receives the coordinate of the
+// query's FIRST tap per dimension (clamped into the array), the corner the grouped-batch boxes are built from.
 template <typename T, int N, int ORDER, int BCF>
-__device__ __forceinline__ u32 tile_key(const EvalParams<N>& p, const T (&x)[N], const int (&shift)[N], int ntot) {
+__device__ __forceinline__ u32 tile_key(const EvalParams<N>& p, const T (&x)[N], const int (&shift)[N], int ntot, int (&first)[N], bool& valid) {
     int c[N][ORDER + 1];
     T dx[N];
-    const bool valid = query_taps<T, N, ORDER, BCF>(p, x, c, dx);
+    valid = query_taps<T, N, ORDER, BCF>(p, x, c, dx);
     u32 key = 0, mul = 1;
 #pragma unroll
     for (int d = 0; d < N; d++) {
@@ -937,47 +940,104 @@ __device__ __forceinline__ u32 tile_key(const EvalParams<N>& p, const T (&x)[N],
         lo = lo < 0 ? 0 : (lo >= p.len[d] ? p.len[d] - 1 : lo);
         key += (u32)(lo >> shift[d]) * mul;
         mul *= (u32)p.ntile[d];
+        const int f = c[d][0];
+        first[d] = f < 0 ? 0 : (f >= p.len[d] ? p.len[d] - 1 : f);
     }
     return valid ? key : (u32)ntot;
 }
+template <typename T, int N, int ORDER, int BCF>
+__device__ __forceinline__ u32 tile_key(const EvalParams<N>& p, const T (&x)[N], const int (&shift)[N], int ntot) {
+    int first[N];
+    bool valid;
+    return tile_key<T, N, ORDER, BCF>(p, x, shift, ntot, first, valid);
+}
 
-// Run starts of one iteration of a sort CTA (thread t holds the keys of queries qb + u*SORT_BLOCK, u < SORT_UNROLL;
-// inactive slots carry key 0xffffffff).  A query starts a run when its key differs from its predecessor's or its index is
-// a multiple of EVAL_CHUNK (items are at most that long).  The 32 queries of a warp and slot u are one bitmap word.
-// All threads of the CTA call together; returns the number of run starts this WARP marked (lane 0 only).
-struct RunMarkSmem { u32 edge[SORT_UNROLL][SORT_BLOCK / 32]; u32 prev; };
-__device__ __forceinline__ u32 mark_runs(const u32 (&key)[SORT_UNROLL], i64 qb, i64 q1, RunMarkSmem& sm, u32* __restrict__ bitmap) {
+// ---- grouped batches: does the batch, AS IT ARRIVED, consist of chunks that fit a brick? ------------------------------
+// One iteration of a sort CTA covers SORT_ITER = 1024 consecutive queries = 32 leaves of 32 (warp w, slot u: leaf u*8 + w).
+// Per leaf the bounding box of the queries' first taps (warp reductions), then a binary tree over the 32 leaves (one
+// warp): a node FITS when its box is at most one tile wide in every dimension -- then every query in it finds its
+// whole neighbourhood in the brick whose corner is the box's corner.  The maximal fitting nodes of >= GROUP_MIN queries
+// are the work items of a grouped batch; a GROUP_MIN-node that does not fit becomes an item without a brick (its queries
+// take the global-memory path).  Recorded per iteration: the fit flags of the nodes of 64 / 128 / 256 / 512 / 1024
+// queries (16 + 8 + 4 + 2 + 1 = 31 bits) and the box corners of the sixteen 64-query nodes; per CTA: items, and queries
+// left without a brick.
+// (staging a 32 KB brick costs about as much as evaluating 90 queries out of it, the global-memory path about 3x a brick
+// evaluation per query: break-even near 40 queries)
+constexpr int GROUP_MIN = 64;                           // smallest chunk worth a brick of its own
+constexpr int GROUP_NODES = (int)(SORT_ITER / GROUP_MIN);  // 16 nodes of GROUP_MIN queries per iteration
+struct GroupSmem { int bb[32][2 * MAXD]; };
+// every thread of the CTA calls; first[u][d] / ok[u] describe the thread's query of slot u (ok false: not a query or an
+// invalid location).  Returns (warp 0 only) the iteration's 31 fit flags; corners[] (16 x uint2) is written.
+template <int N>
+__device__ __forceinline__ u32 group_iteration(const EvalParams<N>& p, const int (&first)[SORT_UNROLL][N], const bool (&ok)[SORT_UNROLL], GroupSmem& sm,
+                                               uint2* __restrict__ corners) {
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int u = 0; u < SORT_UNROLL; u++)
-        if (lane == 31) sm.edge[u][warp] = key[u];
-    __syncthreads();
-    u32 nb = 0;
-#pragma unroll
     for (int u = 0; u < SORT_UNROLL; u++) {
-        u32 prev = __shfl_up_sync(0xffffffffu, key[u], 1);
-        if (lane == 0) prev = warp > 0 ? sm.edge[u][warp - 1] : (u > 0 ? sm.edge[u - 1][SORT_BLOCK / 32 - 1] : sm.prev);
-        const i64 q = qb + (i64)u * SORT_BLOCK;
-        const bool brk = q < q1 && (prev != key[u] || (q & (i64)(EVAL_CHUNK - 1)) == 0);
-        const u32 word = __ballot_sync(0xffffffffu, brk);
-        if (lane == 0 && q < q1) {
-            bitmap[q >> 5] = word;
-            nb += (u32)__popc(word);
+#pragma unroll
+        for (int d = 0; d < N; d++) {
+            const int mn = __reduce_min_sync(0xffffffffu, ok[u] ? first[u][d] : 0x7fffffff);
+            const int mx = __reduce_max_sync(0xffffffffu, ok[u] ? first[u][d] : -1);
+            if (lane == 0) { sm.bb[u * (SORT_BLOCK / 32) + warp][2 * d] = mn; sm.bb[u * (SORT_BLOCK / 32) + warp][2 * d + 1] = mx; }
         }
     }
     __syncthreads();
-    if (threadIdx.x == SORT_BLOCK - 1) sm.prev = key[SORT_UNROLL - 1];
-    return nb;
+    u32 flags = 0;
+    if (warp == 0) {
+        int mn[N], mx[N];
+#pragma unroll
+        for (int d = 0; d < N; d++) { mn[d] = sm.bb[lane][2 * d]; mx[d] = sm.bb[lane][2 * d + 1]; }
+        int bit = 0;
+#pragma unroll
+        for (int lvl = 1; lvl <= 5; lvl++) {  // nodes of 64, 128, ..., 1024 queries
+            bool fit = true;
+#pragma unroll
+            for (int d = 0; d < N; d++) {
+                mn[d] = min(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], 1 << (lvl - 1)));
+                mx[d] = max(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], 1 << (lvl - 1)));
+                fit = fit && (mx[d] < mn[d] || mx[d] - mn[d] < p.tile[d]);  // (an empty box fits)
+            }
+            const u32 votes = __ballot_sync(0xffffffffu, fit);
+            const int nn = 32 >> lvl;  // nodes at this level: 16, 8, 4, 2, 1
+            for (int j = 0; j < nn; j++) flags |= ((votes >> (j << lvl)) & 1u) << (bit + j);
+            bit += nn;
+            if (lvl == 1 && (lane & 1) == 0) {  // corner of the 64-query node lane/2
+                uint2 c;  // (no valid query in the node: mn == INT_MAX everywhere, kept as the largest corner)
+                c.x = (u32)mn[0];
+                c.y = 0x7fffffffu;
+                if constexpr (N == 2) c.y = (u32)mn[1];
+                if constexpr (N >= 3) c.y = ((u32)mn[1] & 0xffffu) | (((u32)mn[2] & 0xffffu) << 16);
+                corners[lane >> 1] = c;
+            }
+        }
+    }
+    __syncthreads();
+    return flags;
+}
+// the items an iteration's flags stand for: calls emit(first 128-node, nodes, has_brick) in query order; returns their number
+template <typename F> __device__ __forceinline__ int group_items(u32 flags, F emit) {
+    const u32 f1 = flags & 0xffffu, f2 = (flags >> 16) & 0xffu, f3 = (flags >> 24) & 0xfu, f4 = (flags >> 28) & 3u, f5 = (flags >> 30) & 1u;
+    if (f5) { emit(0, 16, true); return 1; }
+    int n = 0;
+    for (int h = 0; h < 2; h++) {
+        if ((f4 >> h) & 1u) { emit(8 * h, 8, true); n++; continue; }
+        for (int q = 2 * h; q < 2 * h + 2; q++) {
+            if ((f3 >> q) & 1u) { emit(4 * q, 4, true); n++; continue; }
+            for (int e = 2 * q; e < 2 * q + 2; e++) {
+                if ((f2 >> e) & 1u) { emit(2 * e, 2, true); n++; continue; }
+                for (int g = 2 * e; g < 2 * e + 2; g++) { emit(g, 1, ((f1 >> g) & 1u) != 0); n++; }
+            }
+        }
+    }
+    return n;
 }
 
 template <typename T, int N, int ORDER, int BCF>
-__global__ void __launch_bounds__(SORT_BLOCK) tile_hist_kernel(const EvalParams<N> p, u32* __restrict__ bh, u32 nbins, i64 per_cta, u32* __restrict__ bitmap,
-                                                               u32* __restrict__ runcnt) {
+__global__ void __launch_bounds__(SORT_BLOCK) tile_hist_kernel(const EvalParams<N> p, u32* __restrict__ bh, u32 nbins, i64 per_cta, u32* __restrict__ gflags,
+                                                               uint2* __restrict__ gcorner, u32* __restrict__ runcnt) {
     extern __shared__ u32 s_hist[];
-    __shared__ RunMarkSmem s_rm;
-    __shared__ u32 s_nb;
+    __shared__ GroupSmem s_grp;
     for (u32 b = threadIdx.x; b < nbins; b += SORT_BLOCK) s_hist[b] = 0;
-    if (threadIdx.x == 0) { s_rm.prev = 0xfffffffeu; s_nb = 0; }  // no predecessor: the CTA's first query starts a run
     __syncthreads();
     int ntot = 1;
 #pragma unroll
@@ -987,8 +1047,8 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_hist_kernel(const EvalParams<
     for (int d = 0; d < N; d++) shift[d] = __ffs(p.tile[d]) - 1;
     const i64 q0 = (i64)blockIdx.x * per_cta;
     const i64 q1 = q0 + per_cta < p.nq ? q0 + per_cta : p.nq;
-    u32 nb = 0;
-    for (i64 qb0 = q0; qb0 < q1; qb0 += SORT_ITER) {  // (uniform trip count: mark_runs is a CTA-wide call)
+    u32 nitems = 0, nbad = 0;  // thread 0: items of this CTA's range, queries in items without a brick
+    for (i64 qb0 = q0; qb0 < q1; qb0 += SORT_ITER) {  // (uniform trip count: group_iteration is a CTA-wide call)
         const i64 qb = qb0 + threadIdx.x;
         double raw[SORT_UNROLL][N];
 #pragma unroll
@@ -999,49 +1059,69 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_hist_kernel(const EvalParams<
                 for (int d = 0; d < N; d++) raw[u][d] = load_raw<N>(p, d, q);
             }
         }
-        u32 key[SORT_UNROLL];
+        int first[SORT_UNROLL][N];
+        bool ok[SORT_UNROLL];
 #pragma unroll
         for (int u = 0; u < SORT_UNROLL; u++) {
             const i64 q = qb + u * SORT_BLOCK;
-            key[u] = 0xffffffffu;
+            ok[u] = false;
+#pragma unroll
+            for (int d = 0; d < N; d++) first[u][d] = 0;
             if (q < q1) {
                 T x[N];
 #pragma unroll
                 for (int d = 0; d < N; d++) x[d] = index_coord<T, N>(p, d, raw[u][d]);
-                key[u] = tile_key<T, N, ORDER, BCF>(p, x, shift, ntot);
-                atomicAdd(s_hist + key[u], 1u);
+                atomicAdd(s_hist + tile_key<T, N, ORDER, BCF>(p, x, shift, ntot, first[u], ok[u]), 1u);
             }
         }
-        nb += mark_runs(key, qb, q1, s_rm, bitmap);
+        const i64 it = qb0 / SORT_ITER;
+        const u32 flags = group_iteration<N>(p, first, ok, s_grp, gcorner + it * GROUP_NODES);
+        if (threadIdx.x == 0) {
+            gflags[it] = flags;
+            const i64 left = q1 - qb0;
+            nitems += (u32)group_items(flags, [&](int e, int n, bool brick) {
+                if (!brick) nbad += (u32)max((i64)0, min((i64)GROUP_MIN, left - (i64)e * GROUP_MIN));
+            });
+        }
     }
-    if (nb) atomicAdd(&s_nb, nb);
     __syncthreads();
     for (u32 b = threadIdx.x; b < nbins; b += SORT_BLOCK) bh[(size_t)b * gridDim.x + blockIdx.x] = s_hist[b];
-    if (threadIdx.x == 0) runcnt[blockIdx.x] = s_nb;
+    if (threadIdx.x == 0) { runcnt[2 * blockIdx.x] = nitems; runcnt[2 * blockIdx.x + 1] = nbad; }
 }
 
-// Grouped batches: the runs marked in the bitmap become the work items {tile, first query, one past the last, -}.
-// Same CTA partition as tile_hist (per_cta is a multiple of SORT_ITER, so a CTA owns whole bitmap words); base[cta] =
-// number of runs in the CTAs before it (sorted_decide).
-template <typename T, int N, int ORDER, int BCF>
-__global__ void __launch_bounds__(SORT_BLOCK) run_items_kernel(const EvalParams<N> p, const u32* __restrict__ bitmap, const u32* __restrict__ base,
-                                                               u32* __restrict__ work, const u32* __restrict__ nwork, i64 per_cta) {
+// work item {corner dim 1, first slot, one past the last, corner dims 2, 3 | no-brick flag}
+__device__ __forceinline__ uint4 make_item(const int* lo, int N, u32 beg, u32 end, bool brick) {
+    u32 w = brick ? 0u : 0x80000000u;
+    if (N == 2) w |= (u32)lo[1] & 0x7fffffffu;
+    if (N >= 3) w |= ((u32)lo[1] & 0x7fffu) | (((u32)lo[2] & 0x7fffu) << 15);
+    return make_uint4((u32)lo[0], beg, end, w);
+}
+template <int N> __device__ __forceinline__ bool item_corner(const uint4 it, int (&lo)[N]) {
+    lo[0] = (int)it.x;
+    if constexpr (N == 2) lo[1] = (int)(it.w & 0x7fffffffu);
+    if constexpr (N >= 3) { lo[1] = (int)(it.w & 0x7fffu); lo[2] = (int)((it.w >> 15) & 0x7fffu); }
+    return (it.w & 0x80000000u) == 0;  // has a brick
+}
+
+// Grouped batches: the fitting chunks recorded by the binning pass become the work items; slots are the caller's indices.
+// Same CTA partition as tile_hist; base[cta] = number of items in the CTAs before it (sorted_decide).  One thread per
+// iteration.
+template <int N>
+__global__ void __launch_bounds__(SORT_BLOCK) run_items_kernel(const EvalParams<N> p, const u32* __restrict__ gflags, const uint2* __restrict__ gcorner,
+                                                               const u32* __restrict__ base, u32* __restrict__ work, const u32* __restrict__ nwork, i64 per_cta) {
     if (nwork[2] == 0) return;
     __shared__ u32 s_w[SORT_BLOCK / 32], s_carry;
-    int ntot = 1, shift[N];
-#pragma unroll
-    for (int d = 0; d < N; d++) { ntot *= p.ntile[d]; shift[d] = __ffs(p.tile[d]) - 1; }
     const i64 q0 = (i64)blockIdx.x * per_cta;
     const i64 q1 = q0 + per_cta < p.nq ? q0 + per_cta : p.nq;
     if (q0 >= q1) return;
-    const i64 w0 = q0 >> 5, w1 = (q1 + 31) >> 5, wall = (p.nq + 31) >> 5;
+    const i64 it0 = q0 / SORT_ITER, it1 = (q1 + SORT_ITER - 1) / SORT_ITER;
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_carry = base[blockIdx.x];
     __syncthreads();
-    for (i64 wb = w0; wb < w1; wb += SORT_BLOCK) {
-        const i64 w = wb + threadIdx.x;
-        const u32 bits = w < w1 ? bitmap[w] : 0u;
-        const u32 cnt = (u32)__popc(bits);
+    for (i64 ib = it0; ib < it1; ib += SORT_BLOCK) {
+        const i64 it = ib + threadIdx.x;
+        const u32 flags = it < it1 ? gflags[it] : 0u;
+        const u32 cnt = it < it1 ? (u32)group_items(flags, [](int, int, bool) {}) : 0u;
         u32 incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -1053,24 +1133,25 @@ __global__ void __launch_bounds__(SORT_BLOCK) run_items_kernel(const EvalParams<
         u32 before = s_carry;
         for (u32 k = 0; k < warp; k++) before += s_w[k];
         u32 rank = before + incl - cnt;
-        u32 rest = bits;
-        while (rest) {
-            const int b = __ffs(rest) - 1;
-            rest &= rest - 1;
-            const i64 q = (w << 5) + b;
-            // end of the run: the next marked query (at most EVAL_CHUNK ahead), else the end of the batch
-            i64 e = p.nq;
-            if (rest) e = (w << 5) + (__ffs(rest) - 1);
-            else {
-                for (i64 v = w + 1; v < wall; v++) {
-                    const u32 nb = bitmap[v];
-                    if (nb) { e = (v << 5) + (__ffs(nb) - 1); break; }
+        if (it < it1) {
+            const i64 qb = it * SORT_ITER;
+            group_items(flags, [&](int e, int n, bool brick_in) {
+                bool brick = brick_in;
+                int lo[3] = {0x7fffffff, 0x7fffffff, 0xffff};
+                for (int k = e; k < e + n; k++) {  // (nodes without a valid query carry the largest corner)
+                    const uint2 c = gcorner[it * GROUP_NODES + k];
+                    lo[0] = min(lo[0], (int)c.x);
+                    lo[1] = min(lo[1], (int)(N >= 3 ? (c.y & 0xffffu) : (c.y & 0x7fffffffu)));
+                    lo[2] = min(lo[2], (int)(c.y >> 16));
                 }
-            }
-            T x[N];
-            load_index_coords<T, N>(p, q, x);
-            reinterpret_cast<uint4*>(work)[rank] = make_uint4(tile_key<T, N, ORDER, BCF>(p, x, shift, ntot), (u32)q, (u32)e, 0u);
-            rank++;
+                if (lo[0] == 0x7fffffff) { lo[0] = lo[1] = lo[2] = 0; brick = false; }  // nothing valid in the chunk
+                if (N >= 3 && lo[1] > 0x7fff) lo[1] = 0;
+                if (N >= 3 && lo[2] > 0x7fff) lo[2] = 0;
+                const i64 b = qb + (i64)e * GROUP_MIN, en = min(q1, b + (i64)n * GROUP_MIN);
+                if (b < en) reinterpret_cast<uint4*>(work)[rank] = make_item(lo, N, (u32)b, (u32)en, brick);
+                else reinterpret_cast<uint4*>(work)[rank] = make_item(lo, N, (u32)q1, (u32)q1, false);  // (past the end of the batch: empty)
+                rank++;
+            });
         }
         __syncthreads();
         if (threadIdx.x == SORT_BLOCK - 1) s_carry = before + incl;
@@ -1123,14 +1204,10 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_scatter_kernel(const EvalPara
 // evaluated on its own and returned to its own position).  The counting pass marks the run starts like tile_hist.
 template <typename T, int N, int ORDER, int BCF, bool SCATTER>
 __global__ void __launch_bounds__(SORT_BLOCK) tile_sort_global_kernel(const EvalParams<N> p, u32* __restrict__ bins, T* __restrict__ rec, u32* __restrict__ inv,
-                                                                      i64 per_cta, u32* __restrict__ bitmap, u32* __restrict__ runcnt) {
-    __shared__ RunMarkSmem s_rm;
-    __shared__ u32 s_nb;
+                                                                      i64 per_cta, u32* __restrict__ gflags, uint2* __restrict__ gcorner, u32* __restrict__ runcnt) {
+    __shared__ GroupSmem s_grp;
     if constexpr (SCATTER) {
         if (p.nwork[2] != 0) return;
-    } else {
-        if (threadIdx.x == 0) { s_rm.prev = 0xfffffffeu; s_nb = 0; }
-        __syncthreads();
     }
     int ntot = 1, shift[N];
 #pragma unroll
@@ -1138,7 +1215,7 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_sort_global_kernel(const Eval
     const i64 q0 = (i64)blockIdx.x * per_cta;
     const i64 q1 = q0 + per_cta < p.nq ? q0 + per_cta : p.nq;
     const u32 lane = threadIdx.x & 31;
-    u32 nb = 0;
+    u32 nitems = 0, nbad = 0;
     for (i64 qb0 = q0; qb0 < q1; qb0 += SORT_ITER) {  // (uniform trip count: the warp votes below need every lane)
         const i64 qb = qb0 + threadIdx.x;
         double raw[SORT_UNROLL][N];
@@ -1150,19 +1227,22 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_sort_global_kernel(const Eval
                 for (int d = 0; d < N; d++) raw[u][d] = load_raw<N>(p, d, q);
             }
         }
-        u32 keys[SORT_UNROLL];
+        int first[SORT_UNROLL][N];
+        bool ok[SORT_UNROLL];
 #pragma unroll
         for (int u = 0; u < SORT_UNROLL; u++) {
             const i64 q = qb + u * SORT_BLOCK;
             const bool act = q < q1;
             T x[N];
             u32 key = 0xffffffffu;
+            ok[u] = false;
+#pragma unroll
+            for (int d = 0; d < N; d++) first[u][d] = 0;
             if (act) {
 #pragma unroll
                 for (int d = 0; d < N; d++) x[d] = index_coord<T, N>(p, d, raw[u][d]);
-                key = tile_key<T, N, ORDER, BCF>(p, x, shift, ntot);
+                key = tile_key<T, N, ORDER, BCF>(p, x, shift, ntot, first[u], ok[u]);
             }
-            keys[u] = key;
             const u32 peers = __match_any_sync(0xffffffffu, key);
             const u32 leader = __ffs(peers) - 1;
             u32 base = 0;
@@ -1176,12 +1256,20 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_sort_global_kernel(const Eval
                 }
             }
         }
-        if constexpr (!SCATTER) nb += mark_runs(keys, qb, q1, s_rm, bitmap);
+        if constexpr (!SCATTER) {
+            const i64 it = qb0 / SORT_ITER;
+            const u32 flags = group_iteration<N>(p, first, ok, s_grp, gcorner + it * GROUP_NODES);
+            if (threadIdx.x == 0) {
+                gflags[it] = flags;
+                const i64 left = q1 - qb0;
+                nitems += (u32)group_items(flags, [&](int e, int n, bool brick) {
+                    if (!brick) nbad += (u32)max((i64)0, min((i64)GROUP_MIN, left - (i64)e * GROUP_MIN));
+                });
+            }
+        }
     }
     if constexpr (!SCATTER) {
-        if (nb) atomicAdd(&s_nb, nb);
-        __syncthreads();
-        if (threadIdx.x == 0) runcnt[blockIdx.x] = s_nb;
+        if (threadIdx.x == 0) { runcnt[2 * blockIdx.x] = nitems; runcnt[2 * blockIdx.x + 1] = nbad; }
     }
 }
 
@@ -1230,21 +1318,18 @@ template <int BYTES> __device__ __forceinline__ void cp_async_zfill(u32 saddr, c
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int KEEP> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(KEEP) : "memory"); }
 
-template <int N, int L> __device__ __forceinline__ void brick_geo(const EvalParams<N>& p, u32 tile, int (&lo)[N], int (&clip)[N]) {
-    u32 rem = tile;
+// clip[d]: cells of the brick along d that exist (the brick may stick out of the array)
+template <int N, int L> __device__ __forceinline__ void brick_clip(const EvalParams<N>& p, const int (&lo)[N], int (&clip)[N]) {
 #pragma unroll
     for (int d = 0; d < N; d++) {
-        const int t = rem % (u32)p.ntile[d];
-        rem /= (u32)p.ntile[d];
-        lo[d] = t * p.tile[d];
         const int full = p.tile[d] + L - 1, left = p.len[d] - lo[d];
         clip[d] = full < left ? full : left;
     }
 }
 // element-wise staging (vol = padded brick volume; padding cells are zero-filled like cells past the array)
-template <typename T, int N, int L> __device__ __forceinline__ void brick_fill(const EvalParams<N>& p, const T* __restrict__ A, T* brick, u32 tile, int vol) {
-    int lo[N], clip[N];
-    brick_geo<N, L>(p, tile, lo, clip);
+template <typename T, int N, int L> __device__ __forceinline__ void brick_fill(const EvalParams<N>& p, const T* __restrict__ A, T* brick, const int (&lo)[N], int vol) {
+    int clip[N];
+    brick_clip<N, L>(p, lo, clip);
     const u32 sbase = (u32)__cvta_generic_to_shared(brick);
 #pragma unroll 4
     for (int e = threadIdx.x; e < vol; e += BRICK_BLOCK) {
@@ -1266,16 +1351,14 @@ template <typename T, int N, int L> __device__ __forceinline__ void brick_fill(c
 }
 // stage the brick of `tile` into `dst` (either mechanism); every thread calls
 template <typename T, int N, int L>
-__device__ __forceinline__ void stage_brick(const EvalParams<N>& p, const CUtensorMap* tmap, const T* __restrict__ A, T* dst, u64* bar, u32 tile, int vol) {
+__device__ __forceinline__ void stage_brick(const EvalParams<N>& p, const CUtensorMap* tmap, const T* __restrict__ A, T* dst, u64* bar, const int (&lo)[N], int vol) {
     if (p.use_tma) {
         if (threadIdx.x == 0) {
-            int lo[N], clip[N];
-            brick_geo<N, L>(p, tile, lo, clip);
             mbar_expect_tx(bar, (u32)vol * (u32)sizeof(T));
             tma_load_brick<N>(tmap, dst, bar, lo);
         }
     } else {
-        brick_fill<T, N, L>(p, A, dst, tile, vol);
+        brick_fill<T, N, L>(p, A, dst, lo, vol);
     }
 }
 
@@ -1372,9 +1455,6 @@ __global__ void __launch_bounds__(BRICK_BLOCK, 2)
     const T* __restrict__ A = (const T*)p.coefs;
     const int vol = brick_stride(N, L, N - 1, (int)sizeof(T)) * (p.tile[N - 1] + L - 1);
     const int volp = (vol + 31) & ~31;  // buffers stay 128-byte aligned (TMA destination)
-    u32 ntot = 1;
-#pragma unroll
-    for (int d = 0; d < N; d++) ntot *= (u32)p.ntile[d];
     const u32 nwork = p.nwork[0];
     u32* ctr = const_cast<u32*>(p.nwork) + 1;
     const u32* __restrict__ work = p.work;
@@ -1394,10 +1474,16 @@ __global__ void __launch_bounds__(BRICK_BLOCK, 2)
     if (tid == 16) s_opull[0] = 0;
     __syncthreads();
     u32 cur = s_it[0];
-    u32 tile_c = 0, beg_c = 0, end_c = 0;
+    u32 beg_c = 0, end_c = 0;
+    int lo_c[N];
+    bool have_c = false;
+#pragma unroll
+    for (int d = 0; d < N; d++) lo_c[d] = 0;
     if (cur < nwork) {
-        { const uint4 it = reinterpret_cast<const uint4*>(work)[cur]; tile_c = it.x; beg_c = it.y; end_c = it.z; }
-        if (tile_c < ntot) stage_brick<T, N, L>(p, &tmap, A, bricks, &s_bar[0], tile_c, vol);
+        const uint4 it = reinterpret_cast<const uint4*>(work)[cur];
+        beg_c = it.y; end_c = it.z;
+        have_c = item_corner<N>(it, lo_c);
+        if (have_c) stage_brick<T, N, L>(p, &tmap, A, bricks, &s_bar[0], lo_c, vol);
     }
     cp_async_commit();
     u32 phase[2] = {0, 0};  // mbarrier parity of each buffer's next completion (TMA)
@@ -1415,15 +1501,23 @@ __global__ void __launch_bounds__(BRICK_BLOCK, 2)
         if (tid < 16) { s_cnt[par ^ 1][tid] = 0; s_cur[par ^ 1][tid] = 0; }  // the next item's counters (idle since item k-1)
         if (tid == 16) s_opull[par ^ 1] = 0;
         const u32 nxt = s_it[par ^ 1];
-        u32 tile_n = 0, beg_n = 0, end_n = 0;
+        u32 beg_n = 0, end_n = 0;
+        int lo_n[N];
+        bool have_n = false;
+#pragma unroll
+        for (int d = 0; d < N; d++) lo_n[d] = 0;
         if (nxt < nwork) {
-            { const uint4 it = reinterpret_cast<const uint4*>(work)[nxt]; tile_n = it.x; beg_n = it.y; end_n = it.z; }
-            if (tile_n < ntot) stage_brick<T, N, L>(p, &tmap, A, bricks + (size_t)(par ^ 1) * volp, &s_bar[par ^ 1], tile_n, vol);
+            const uint4 it = reinterpret_cast<const uint4*>(work)[nxt];
+            beg_n = it.y; end_n = it.z;
+            have_n = item_corner<N>(it, lo_n);
+            if (have_n) stage_brick<T, N, L>(p, &tmap, A, bricks + (size_t)(par ^ 1) * volp, &s_bar[par ^ 1], lo_n, vol);
         }
         cp_async_commit();
         int lo[N], clip[N];
-        const bool have = tile_c < ntot;  // the last bin holds invalid queries: no brick
-        brick_geo<N, L>(p, have ? tile_c : 0u, lo, clip);
+        const bool have = have_c;  // items without a brick (invalid locations, chunks that do not fit one): every query is deferred
+#pragma unroll
+        for (int d = 0; d < N; d++) lo[d] = lo_c[d];
+        brick_clip<N, L>(p, lo, clip);
         const u32 n = end_c - beg_c;
         // the brick of item k has landed: this thread's cp.async groups / the buffer's mbarrier phase
         auto brick_ready = [&]() {
@@ -1548,7 +1642,9 @@ __global__ void __launch_bounds__(BRICK_BLOCK, 2)
                 }
             }
         }
-        cur = nxt; tile_c = tile_n; beg_c = beg_n; end_c = end_n;
+        cur = nxt; have_c = have_n; beg_c = beg_n; end_c = end_n;
+#pragma unroll
+        for (int d = 0; d < N; d++) lo_c[d] = lo_n[d];
     }
     cp_async_wait<0>();
 }
@@ -1589,12 +1685,13 @@ __global__ void __launch_bounds__(256) unpermute_kernel(const T* __restrict__ os
 }
 
 // eval_tile.cu
-int tile_offsets(const u32* bh, u32 nbins, u32 nctas, u32* hist, u32* offs, u32* boff, u32* work, u32* nwork, u32 chunk, cudaStream_t s);
-int tile_offsets_global(const u32* hist, u32 nbins, u32* offs, u32* cursor, u32* work, u32* nwork, u32 chunk, cudaStream_t s);
-int sorted_decide(const u32* runcnt, u32 nctas, i64 nq, u32 min_run, u32 max_items, u32* base, u32* nwork, cudaStream_t s);
+struct TileGeo { int N, tile[MAXD], ntile[MAXD]; };  // for the scan's work items (tile index -> brick corner)
+int tile_offsets(const u32* bh, u32 nbins, u32 nctas, u32* hist, u32* offs, u32* boff, u32* work, u32* nwork, u32 chunk, const TileGeo& geo, cudaStream_t s);
+int tile_offsets_global(const u32* hist, u32 nbins, u32* offs, u32* cursor, u32* work, u32* nwork, u32 chunk, const TileGeo& geo, cudaStream_t s);
+int sorted_decide(const u32* runcnt, u32 nctas, i64 nq, u32 bad_percent, u32 max_items, u32* base, u32* nwork, cudaStream_t s);
 bool choose_tile(int N, int L, size_t esz, const int* len, i64 nq, bool forced, int* tile, int* ntile);
 u32 sort_smem_bins();  // 12000: per-CTA histograms live in shared memory (<= 48 KB); more tiles: tile_sort_global_kernel
-u32 sorted_min_run(bool hinted);  // average run length (queries) from which a batch counts as grouped by tile
+u32 grouped_bad_percent(bool hinted);  // share of queries (percent) that may lack a brick for a batch to be evaluated in place; 0: never
 int make_brick_tensor_map(CUtensorMap* m, int dtype, int N, const void* base, const int* len, const i64* stride, const int* box);
 // Larger batches are evaluated in slices: bounds the record scratch, and keeps the randomly written regions -- the
 // slice's records and its outputs -- from outgrowing L2 by too much: the two permutations of a 4e7-query batch
@@ -1628,18 +1725,18 @@ int launch_tiled(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     for (int d = 0; d < N; d++) vol *= (size_t)box[d];
     const size_t smem = 2 * ((vol + 31) & ~(size_t)31) * sizeof(T);
     const u32 nctas = (u32)std::max<i64>(1, std::min<i64>((i64)num_sms() * 2, (p.nq + 4095) / 4096));
-    const i64 per_cta = ((p.nq + nctas - 1) / nctas + SORT_ITER - 1) / SORT_ITER * SORT_ITER;  // whole bitmap words per CTA
-    const u32 min_run = sorted_min_run((flags & GB_SORTED) != 0);
-    const size_t max_items = (size_t)nbins + (size_t)(p.nq / EVAL_CHUNK) + (min_run ? (size_t)(p.nq / min_run) : 0) + nctas + 2;
+    const i64 per_cta = ((p.nq + nctas - 1) / nctas + SORT_ITER - 1) / SORT_ITER * SORT_ITER;  // whole iterations per CTA
+    const u32 bad_percent = grouped_bad_percent((flags & GB_SORTED) != 0);
+    const size_t niter = (size_t)(per_cta / SORT_ITER) * nctas;
+    const size_t max_items = (size_t)nbins + (size_t)(p.nq / EVAL_CHUNK) + niter * GROUP_NODES + nctas + 2;
     const size_t pitch = ((size_t)p.nq + 15) & ~(size_t)15;
-    // one scratch allocation: records | sorted outputs | inv | deferred-slot list (`keys`) | work | bh | boff | hist | offs | bitmap | runcnt | runbase | nwork
+    // one scratch allocation: records | sorted outputs | inv | deferred-slot list (`keys`) | work | group corners | bh | boff | hist | offs | group flags | runcnt | runbase | nwork
     constexpr int W = out_words<N>(OUTMODE);
     const bool global_bins = nbins > sort_smem_bins();
     const size_t nbc = global_bins ? 16 : (size_t)nbins * nctas;
     const size_t rec_bytes = (pitch * (N + 1) * sizeof(T) + 31) & ~(size_t)31;
     const size_t out_bytes = (pitch * W * sizeof(T) + 31) & ~(size_t)31;
-    const size_t bm_words = ((size_t)per_cta * nctas + 31) / 32 + 4;
-    const size_t words = (pitch + 16) + 2 * nbc + 2 * (size_t)(nbins + 4) + bm_words + 2 * (size_t)(nctas + 4) + 8 + 4 * max_items;
+    const size_t words = (pitch + 16) + 4 * max_items + 2 * niter * GROUP_NODES + 2 * nbc + 2 * (size_t)(nbins + 4) + (niter + 4) + 3 * (size_t)(nctas + 4) + 8;
     AsyncBuf guard(s);  // released on every exit path
     GB_CUDA(guard.alloc(rec_bytes + out_bytes + (pitch + words) * sizeof(u32)));
     unsigned char* scratch = (unsigned char*)guard.p;
@@ -1647,15 +1744,19 @@ int launch_tiled(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     T* osorted = reinterpret_cast<T*>(scratch + rec_bytes);
     u32* inv = reinterpret_cast<u32*>(scratch + rec_bytes + out_bytes);
     u32* keys = inv + pitch;
-    u32* work = keys + pitch + 16;  // (16-byte aligned: items are uint4 {tile, first slot, end slot, -})
-    u32* bh = work + 4 * max_items;
+    u32* work = keys + pitch + 16;  // (16-byte aligned: items are uint4, see make_item)
+    uint2* gcorner = reinterpret_cast<uint2*>(work + 4 * max_items);
+    u32* bh = reinterpret_cast<u32*>(gcorner + niter * GROUP_NODES);
     u32* boff = bh + nbc;
     u32* hist = boff + nbc;
     u32* offs = hist + (nbins + 4);
-    u32* bitmap = offs + (nbins + 4);
-    u32* runcnt = bitmap + bm_words;
-    u32* runbase = runcnt + (nctas + 4);
+    u32* gflags = offs + (nbins + 4);
+    u32* runcnt = gflags + (niter + 4);
+    u32* runbase = runcnt + 2 * (nctas + 4);
     u32* nwork = runbase + (nctas + 4);
+    TileGeo geo;
+    geo.N = N;
+    for (int d = 0; d < MAXD; d++) { geo.tile[d] = d < N ? p.tile[d] : 1; geo.ntile[d] = d < N ? p.ntile[d] : 1; }
     const size_t hsmem = (size_t)nbins * sizeof(u32);
     // brick staging: TMA when the array obeys its stride rule (every stride but the first a multiple of 16 bytes)
     CUtensorMap tmap;
@@ -1674,29 +1775,29 @@ int launch_tiled(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     int rc;
     if (global_bins) {  // hist doubles as the write cursors after the scan
         GB_CUDA(cudaMemsetAsync(hist, 0, (size_t)nbins * sizeof(u32), s));
-        tile_sort_global_kernel<T, N, ORDER, BCF, false><<<nctas, SORT_BLOCK, 0, s>>>(p, hist, rec, inv, per_cta, bitmap, runcnt);
+        tile_sort_global_kernel<T, N, ORDER, BCF, false><<<nctas, SORT_BLOCK, 0, s>>>(p, hist, rec, inv, per_cta, gflags, gcorner, runcnt);
         count_launch();
-        rc = sorted_decide(runcnt, nctas, p.nq, min_run, (u32)max_items, runbase, nwork, s);
+        rc = sorted_decide(runcnt, nctas, p.nq, bad_percent, (u32)max_items, runbase, nwork, s);
         if (rc) return rc;
         prof_mark(1, s);
-        rc = tile_offsets_global(hist, nbins, offs, hist, work, nwork, EVAL_CHUNK, s);
+        rc = tile_offsets_global(hist, nbins, offs, hist, work, nwork, EVAL_CHUNK, geo, s);
         if (rc) return rc;
         prof_mark(2, s);
-        tile_sort_global_kernel<T, N, ORDER, BCF, true><<<nctas, SORT_BLOCK, 0, s>>>(p, hist, rec, inv, per_cta, bitmap, runcnt);
+        tile_sort_global_kernel<T, N, ORDER, BCF, true><<<nctas, SORT_BLOCK, 0, s>>>(p, hist, rec, inv, per_cta, gflags, gcorner, runcnt);
         count_launch();
     } else {
-        tile_hist_kernel<T, N, ORDER, BCF><<<nctas, SORT_BLOCK, hsmem, s>>>(p, bh, nbins, per_cta, bitmap, runcnt);
+        tile_hist_kernel<T, N, ORDER, BCF><<<nctas, SORT_BLOCK, hsmem, s>>>(p, bh, nbins, per_cta, gflags, gcorner, runcnt);
         count_launch();
-        rc = sorted_decide(runcnt, nctas, p.nq, min_run, (u32)max_items, runbase, nwork, s);
+        rc = sorted_decide(runcnt, nctas, p.nq, bad_percent, (u32)max_items, runbase, nwork, s);
         if (rc) return rc;
         prof_mark(1, s);
-        rc = tile_offsets(bh, nbins, nctas, hist, offs, boff, work, nwork, EVAL_CHUNK, s);
+        rc = tile_offsets(bh, nbins, nctas, hist, offs, boff, work, nwork, EVAL_CHUNK, geo, s);
         if (rc) return rc;
         prof_mark(2, s);
         tile_scatter_kernel<T, N, ORDER, BCF><<<nctas, SORT_BLOCK, hsmem, s>>>(p, boff, rec, inv, nbins, per_cta);
         count_launch();
     }
-    run_items_kernel<T, N, ORDER, BCF><<<nctas, SORT_BLOCK, 0, s>>>(p, bitmap, runbase, work, nwork, per_cta);
+    run_items_kernel<N><<<nctas, SORT_BLOCK, 0, s>>>(p, gflags, gcorner, runbase, work, nwork, per_cta);
     count_launch();
     GB_CUDA(cudaGetLastError());
     const i64 grid = std::min<i64>((i64)max_items, (i64)num_sms() * bt);
@@ -1743,6 +1844,7 @@ int launch_one(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     for (int d = 0; d < N; d++) tap_bytes *= (size_t)L;
     if (!(flags & (GB_TILED | GB_PLAIN))) tiled = N >= 2 && tap_bytes >= 256 && p.nq >= (1ll << 20) && grid_bytes >= (48u << 20);
     if (p.nchan > 1 || p.blocked || !BRICK) tiled = false;  // multi-valued / blocked grids, light neighbourhoods: plain path
+    if (N == 3 && (p.len[1] > 0x7fff || p.len[2] > 0x7fff)) tiled = false;  // (work items pack the brick corner: make_item)
     if (tiled) tiled = choose_tile(N, L, sizeof(T), p.len, std::min<i64>(p.nq, tiled_max_batch()), forced, p.tile, p.ntile);
     p.aos = 0;
     p.use_tma = 0;

@@ -63,8 +63,22 @@ int prof_read(double* ms, int n, int* nstages) {
 // registers: one pass over global memory); warp-shuffle scans of (queries per slice) and (work items per
 // slice), then a 32-entry scan of the warp totals, give every thread its starting offsets.
 constexpr int SCAN_PER = 12;  // bins per thread and segment (1024 * 12 >= sort_smem_bins(): one segment for the shared-memory sort)
+struct TileGeo { int N, tile[MAXD], ntile[MAXD]; };
+// work item of tile `bin`: {corner dim 1, first slot, one past the last, corner dims 2, 3 | no-brick flag} (eval.cuh: make_item)
+__device__ __forceinline__ uint4 tile_item(const TileGeo& g, u32 bin, u32 ntot, u32 beg, u32 end) {
+    if (bin >= ntot) return make_uint4(0u, beg, end, 0x80000000u);  // the bin of invalid locations: no brick
+    u32 rem = bin, lo[MAXD] = {0, 0, 0, 0};
+    for (int d = 0; d < g.N; d++) {
+        lo[d] = (rem % (u32)g.ntile[d]) * (u32)g.tile[d];
+        rem /= (u32)g.ntile[d];
+    }
+    u32 w = 0;
+    if (g.N == 2) w = lo[1] & 0x7fffffffu;
+    if (g.N >= 3) w = (lo[1] & 0x7fffu) | ((lo[2] & 0x7fffu) << 15);
+    return make_uint4(lo[0], beg, end, w);
+}
 __global__ void __launch_bounds__(1024) tile_scan_kernel(const u32* __restrict__ hist, u32 nbins, u32* __restrict__ offs, u32* __restrict__ work,
-                                                         u32* __restrict__ nwork, u32 chunk) {
+                                                         u32* __restrict__ nwork, u32 chunk, const TileGeo geo) {
     if (nwork[2] != 0) return;  // grouped batch (sorted_decide): the runs are the work items
     __shared__ u32 s_wc[32], s_wi[32], s_base[2];
     const u32 t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -113,7 +127,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const u32* __restrict__
                 const u32 n = (h[k] + chunk - 1) / chunk;            // items of this bin ...
                 const u32 sz = n ? (h[k] + n - 1) / n : 0;           // ... of equal size
                 for (u32 j = 0; j < n; j++) {
-                    reinterpret_cast<uint4*>(work)[w] = make_uint4(seg + b, o + j * sz, o + min((j + 1) * sz, h[k]), 0u);
+                    reinterpret_cast<uint4*>(work)[w] = tile_item(geo, seg + b, nbins - 1, o + j * sz, o + min((j + 1) * sz, h[k]));
                     w++;
                 }
                 o += h[k];
@@ -159,10 +173,10 @@ __global__ void __launch_bounds__(256) bin_cursors_kernel(const u32* __restrict_
     }
 }
 
-int tile_offsets(const u32* bh, u32 nbins, u32 nctas, u32* hist, u32* offs, u32* boff, u32* work, u32* nwork, u32 chunk, cudaStream_t s) {
+int tile_offsets(const u32* bh, u32 nbins, u32 nctas, u32* hist, u32* offs, u32* boff, u32* work, u32* nwork, u32 chunk, const TileGeo& geo, cudaStream_t s) {
     const u32 wgrid = (nbins * 32 + 255) / 256;
     bin_totals_kernel<<<wgrid, 256, 0, s>>>(bh, nbins, nctas, hist, nwork);
-    tile_scan_kernel<<<1, 1024, 0, s>>>(hist, nbins, offs, work, nwork, chunk);
+    tile_scan_kernel<<<1, 1024, 0, s>>>(hist, nbins, offs, work, nwork, chunk, geo);
     bin_cursors_kernel<<<wgrid, 256, 0, s>>>(bh, nbins, nctas, offs, boff, nwork);
     count_launch(3);
     GB_CUDA(cudaGetLastError());
@@ -171,68 +185,74 @@ int tile_offsets(const u32* bh, u32 nbins, u32 nctas, u32* hist, u32* offs, u32*
 
 // global-histogram sort (tile_sort_global_kernel): hist holds the totals already; after the scan the write cursors
 // are the bin offsets themselves (cursor may alias hist)
-int tile_offsets_global(const u32* hist, u32 nbins, u32* offs, u32* cursor, u32* work, u32* nwork, u32 chunk, cudaStream_t s) {
-    tile_scan_kernel<<<1, 1024, 0, s>>>(hist, nbins, offs, work, nwork, chunk);
+int tile_offsets_global(const u32* hist, u32 nbins, u32* offs, u32* cursor, u32* work, u32* nwork, u32 chunk, const TileGeo& geo, cudaStream_t s) {
+    tile_scan_kernel<<<1, 1024, 0, s>>>(hist, nbins, offs, work, nwork, chunk, geo);
     count_launch();
     GB_CUDA(cudaGetLastError());
     GB_CUDA(cudaMemcpyAsync(cursor, offs, (size_t)nbins * sizeof(u32), cudaMemcpyDeviceToDevice, s));
     return GB_OK;
 }
 
-// ---- grouped ("sorted") batches ------------------------------------------------------------------------------------
-// runcnt[cta] = run starts the sort CTAs marked (eval.cuh: mark_runs).  Few runs = the batch arrived grouped by tile:
-// nwork[2] = 1, nwork[0] = number of runs (the work items, built by run_items_kernel from base[cta] = runs before CTA
+// ---- grouped batches ---------------------------------------------------------------------------------------------
+// runcnt[2 cta] = work items the binning pass found for a grouped evaluation of the CTA's range (eval.cuh:
+// group_iteration), runcnt[2 cta + 1] = queries of that range left without a brick.  Few of the latter = the batch
+// arrived in an order whose chunks each fit a brick (sorted by tile or cell block, Morton / Hilbert order, a lattice walked
+// block by block): nwork[2] = 1, nwork[0] = number of items (built by run_items_kernel from base[cta] = items before CTA
 // cta), nwork[1] = 0 (ticket counter).  Otherwise nwork[2] = 0 and the counting sort proceeds.  One CTA.
-__global__ void __launch_bounds__(1024) sorted_decide_kernel(const u32* __restrict__ runcnt, u32 nctas, u32 limit, u32* __restrict__ base, u32* __restrict__ nwork) {
-    __shared__ u32 s_w[32];
+__global__ void __launch_bounds__(1024) sorted_decide_kernel(const u32* __restrict__ runcnt, u32 nctas, u32 max_bad, u32 max_items, u32* __restrict__ base,
+                                                            u32* __restrict__ nwork) {
+    __shared__ u32 s_w[32], s_b[32];
     const u32 t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const u32 c = t < nctas ? runcnt[t] : 0u;
+    const u32 c = t < nctas ? runcnt[2 * t] : 0u;
+    u32 bad = t < nctas ? runcnt[2 * t + 1] : 0u;
     u32 incl = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const u32 a = __shfl_up_sync(0xffffffffu, incl, o);
         if ((int)lane >= o) incl += a;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
     if (lane == 31) s_w[warp] = incl;
+    if (lane == 0) s_b[warp] = bad;
     __syncthreads();
     if (warp == 0) {
-        u32 w = s_w[lane];
+        u32 w = s_w[lane], bb = s_b[lane];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const u32 a = __shfl_up_sync(0xffffffffu, w, o);
             if ((int)lane >= o) w += a;
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bb += __shfl_xor_sync(0xffffffffu, bb, o);
         s_w[lane] = w;
+        if (lane == 0) s_b[0] = bb;
     }
     __syncthreads();
     const u32 before = (warp ? s_w[warp - 1] : 0u) + incl - c;
     if (t < nctas) base[t] = before;
     if (t == 0) {
         const u32 total = s_w[31];
-        const u32 grouped = (limit != 0 && total <= limit) ? 1u : 0u;
+        const u32 grouped = (max_items != 0 && total <= max_items && s_b[0] <= max_bad) ? 1u : 0u;
         nwork[2] = grouped;
         if (grouped) { nwork[0] = total; nwork[1] = 0; }
     }
 }
-// min_run: average run length from which the batch counts as grouped (0: never)
-int sorted_decide(const u32* runcnt, u32 nctas, i64 nq, u32 min_run, u32 max_items, u32* base, u32* nwork, cudaStream_t s) {
+int sorted_decide(const u32* runcnt, u32 nctas, i64 nq, u32 bad_percent, u32 max_items, u32* base, u32* nwork, cudaStream_t s) {
     if (nctas > 1024) return fail(GB_ERR_CUDA, "sorted_decide: too many sort CTAs");
-    u32 limit = 0;
-    if (min_run) {  // run starts include the forced ones (every EVAL_CHUNK-th query, each CTA's first)
-        const i64 l = nq / min_run + nq / 2048 + nctas;
-        limit = (u32)std::min<i64>(l, (i64)max_items - 2);
-    }
-    sorted_decide_kernel<<<1, 1024, 0, s>>>(runcnt, nctas, limit, base, nwork);
+    const u32 max_bad = (u32)std::min<i64>((i64)0x7fffffff, nq * (i64)bad_percent / 100);
+    sorted_decide_kernel<<<1, 1024, 0, s>>>(runcnt, nctas, max_bad, bad_percent ? max_items - 2 : 0u, base, nwork);
     count_launch();
     GB_CUDA(cudaGetLastError());
     return GB_OK;
 }
-// GB_SORTED_MIN_RUN: average run length (queries per visit of a tile) from which a batch is evaluated in place;
-// default 256 (32 when the caller passed GB_SORTED); 0 disables the detection.
-u32 sorted_min_run(bool hinted) {
-    static const long env = [] { const char* e = getenv("GB_SORTED_MIN_RUN"); return e ? atol(e) : -1L; }();
-    if (env >= 0) return (u32)env;
-    return hinted ? 32u : 256u;
+// GB_GROUPED_BAD_PERCENT: share of the queries that may sit in chunks too scattered for a brick (they take the
+// global-memory path) for the batch still to be evaluated in place; default 12 (30 when the caller passed GB_SORTED);
+// 0 disables the detection.
+u32 grouped_bad_percent(bool hinted) {
+    static const long env = [] { const char* e = getenv("GB_GROUPED_BAD_PERCENT"); return e ? atol(e) : -1L; }();
+    if (env >= 0) return (u32)std::min(100L, env);
+    return hinted ? 30u : 12u;
 }
 
 // Tensor map of the coefficient array for the brick kernel's TMA loads: rank N, box = the brick.  Fails (-> cp.async

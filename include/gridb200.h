@@ -67,11 +67,12 @@ enum {
        faster than the default on such batches (profiles/README.md). */
     GB_TILED = 2, /* force the binned shared-memory path (compiled for 2-D / 3-D Quadratic and Cubic; ignored elsewhere) */
     GB_PLAIN = 4, /* force the plain path */
-    /* Hint: the batch is grouped by location (sorted by grid tile, Morton order, binned once and evaluated many times).
-       The tiled path detects such batches by itself -- the binning pass counts how often consecutive queries change
-       tile -- and then evaluates them IN PLACE: no permutation of the queries, no un-permutation of the results.
-       The hint only lowers the detection threshold (average run of 32 instead of 256 queries per tile visit;
-       GB_SORTED_MIN_RUN overrides both).  Results are bit-identical in every case. */
+    /* Hint: the batch is spatially grouped (sorted by tile or cell block, Morton / Hilbert order, a lattice walked block
+       by block, points binned once and evaluated many times).  The tiled path detects such batches by itself -- its
+       binning pass checks whether chunks of 128-1024 consecutive queries each fit one shared-memory brick -- and then
+       evaluates them IN PLACE: no permutation of the queries, no un-permutation of the results.  The hint only
+       raises the share of stray queries tolerated (30 % instead of 12 %; GB_GROUPED_BAD_PERCENT overrides both, 0
+       disables the detection).  Results are bit-identical in every case. */
     GB_SORTED = 8,
     /* gb_invert_opt / gb_grid_create_opt with GB_FAST: the prefilter runs as a line-parallel solver (one line per
        warp, parallel cyclic reduction of the interior recurrences) instead of the reference's sequential LU sweep;

@@ -34,7 +34,7 @@ int main(int argc, char** argv) {
 
     /* README.md:36-68: y = 8.1 (x - 2.3)^2 + 1.6 on x = 1..5, InterpGrid(y, BCnil, InterpQuadratic) */
     double y[5];
-    for (int i = 0; i < 5; i++) y[i] = 8.1 * (i + 1 - 2.3) * (i + 1 - 2.3) + 1.6;
+    for (int i = 0; i < 5; i++) y[i] = 8.1 * ((i + 1 - 2.3) * (i + 1 - 2.3)) + 1.6; /* a*(x-c).^2+o */
     const int64_t dims[1] = {5};
     gb_grid* g = NULL;
     int rc = p_create(&g, GB_F64, 1, dims, y, GB_HOST, GB_BC_NIL, GB_QUADRATIC, NAN, NULL);
