@@ -91,11 +91,13 @@ template <typename T> __device__ __forceinline__ T exact_div(T a, T d, T rd) {
 // fixed leading tile extents (cells), so that brick strides are compile-time constants; the extent
 // along the LAST dimension is chosen at run time (choose_tile): N=1 -, N=2 64, N=3 16x16, N=4 8x8x8
 __host__ __device__ constexpr int brick_tile(int N, int d) { return N == 2 ? 64 : N == 3 ? 16 : 8; }
-// extent of the brick along dimension e (tile + L-1 halo cells); the contiguous dimension is padded to a multiple of 16 bytes
-// (esz = element size) so that a brick row is a legal TMA box row (cp.async.bulk.tensor: boxDim[0]*esz % 16 == 0)
+// extent of the brick along dimension e (tile + L-1 halo cells).  TMA (cp.async.bulk.tensor) wants every box row to start on a
+// 16-byte boundary and to be a multiple of 16 bytes long (esz = element size, q = 16/esz elements): the contiguous dimension
+// therefore carries q-1 spare cells -- a brick whose corner had to be aligned DOWN still holds a full tile -- and is rounded
+// up to a multiple of q.
 __host__ __device__ constexpr int brick_extent(int N, int L, int e, int esz) {
     const int f = brick_tile(N, e) + L - 1, q = 16 / esz;
-    return e == 0 ? (f + q - 1) / q * q : f;
+    return e == 0 ? (f + (q - 1) + q - 1) / q * q : f;
 }
 __host__ __device__ constexpr int brick_stride(int N, int L, int d, int esz) {
     int s = 1;

@@ -940,7 +940,9 @@ __device__ __forceinline__ u32 tile_key(const EvalParams<N>& p, const T (&x)[N],
         lo = lo < 0 ? 0 : (lo >= p.len[d] ? p.len[d] - 1 : lo);
         key += (u32)(lo >> shift[d]) * mul;
         mul *= (u32)p.ntile[d];
-        const int f = c[d][0];
+        // (taken from the second tap where there is one: at a wrapping boundary the first tap sits at the far end of the array,
+        // which would tear the chunk's box apart; such a query is deferred by brick_locate whatever its chunk's brick is)
+        const int f = ORDER >= 2 ? c[d][1] - 1 : c[d][0];
         first[d] = f < 0 ? 0 : (f >= p.len[d] ? p.len[d] - 1 : f);
     }
     return valid ? key : (u32)ntot;
@@ -954,90 +956,134 @@ __device__ __forceinline__ u32 tile_key(const EvalParams<N>& p, const T (&x)[N],
 
 // ---- grouped batches: does the batch, AS IT ARRIVED, consist of chunks that fit a brick? ------------------------------
 // One iteration of a sort CTA covers SORT_ITER = 1024 consecutive queries = 32 leaves of 32 (warp w, slot u: leaf u*8 + w).
-// Per leaf the bounding box of the queries' first taps (warp reductions), then a binary tree over the 32 leaves (one
-// warp): a node FITS when its box is at most one tile wide in every dimension -- then every query in it finds its
-// whole neighbourhood in the brick whose corner is the box's corner.  The maximal fitting nodes of >= GROUP_MIN queries
-// are the work items of a grouped batch; a GROUP_MIN-node that does not fit becomes an item without a brick (its queries
-// take the global-memory path).  Recorded per iteration: the fit flags of the nodes of 64 / 128 / 256 / 512 / 1024
-// queries (16 + 8 + 4 + 2 + 1 = 31 bits) and the box corners of the sixteen 64-query nodes; per CTA: items, and queries
-// left without a brick.
+// Per leaf the bounding box of the queries' first taps (warp reductions; a leaf whose own box exceeds a tile is "stray").
+// Thread 0 then walks the 32 leaves greedily: a chunk grows leaf by leaf while its box still fits one brick -- at most one
+// tile wide in every dimension, so that every query in it finds its whole neighbourhood in the brick whose corner is the
+// box's corner -- and is cut where it would not.  Chunks of >= GROUP_MIN queries are the work items of a grouped
+// batch; shorter chunks and runs of stray leaves become items WITHOUT a brick (their queries take the global-memory
+// path).  Recorded per iteration: a bit per leaf where an item starts, a bit whether that item has a brick, and the
+// items' brick corners; per CTA: items, and queries left without a brick.
+// Uniformly random batches pay two reductions per leaf and one barrier: no leaf fits, the walk is skipped; a CTA whose
+// first iterations are mostly stray stops looking altogether.
 // (staging a 32 KB brick costs about as much as evaluating 90 queries out of it, the global-memory path about 3x a brick
 // evaluation per query: break-even near 40 queries)
-constexpr int GROUP_MIN = 64;                           // smallest chunk worth a brick of its own
-constexpr int GROUP_NODES = (int)(SORT_ITER / GROUP_MIN);  // 16 nodes of GROUP_MIN queries per iteration
-struct GroupSmem { int bb[32][2 * MAXD]; };
-// every thread of the CTA calls; first[u][d] / ok[u] describe the thread's query of slot u (ok false: not a query or an
-// invalid location).  Returns (warp 0 only) the iteration's 31 fit flags; corners[] (16 x uint2) is written.
+constexpr int GROUP_MIN = 64;    // smallest chunk worth a brick of its own
+constexpr int GROUP_LEAVES = 32;  // leaves (and at most that many items) per iteration
+constexpr int GROUP_STRAY = 0x7ffffff0;
+struct GroupSmem { int bb[GROUP_LEAVES][2 * MAXD]; int dead; };
+struct GroupGeo { int cap0, amask; };  // dim 1: the corner is aligned down to 16 bytes (amask = 16/sizeof(T) - 1), first taps fit up to cap0 cells past it
+struct GroupOut { u32 start, brick, nitems, nbad; };  // thread 0 only
+
+template <int N> __device__ __forceinline__ bool box_fits(const EvalParams<N>& p, const GroupGeo& gg, const int (&mn)[N], const int (&mx)[N]) {
+    bool fit = mx[0] < mn[0] || mx[0] - (mn[0] & ~gg.amask) <= gg.cap0;  // (an empty box fits)
+#pragma unroll
+    for (int d = 1; d < N; d++) fit = fit && (mx[d] < mn[d] || mx[d] - mn[d] < p.tile[d]);
+    return fit;
+}
+// Every thread of the CTA calls; first[u][d] / ok[u] describe the thread's query of slot u (ok false: not a query or an
+// invalid location); `left` = queries from the iteration's first one to the end of the CTA's range.  corners[] receives
+// the brick corner of the k-th item of the iteration.  The caller closes the iteration with a CTA barrier.
 template <int N>
-__device__ __forceinline__ u32 group_iteration(const EvalParams<N>& p, const int (&first)[SORT_UNROLL][N], const bool (&ok)[SORT_UNROLL], GroupSmem& sm,
-                                               uint2* __restrict__ corners) {
+__device__ __forceinline__ GroupOut group_iteration(const EvalParams<N>& p, const int (&first)[SORT_UNROLL][N], const bool (&ok)[SORT_UNROLL], GroupSmem& sm,
+                                                    uint2* __restrict__ corners, const GroupGeo gg, const i64 left, const bool dead) {
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    GroupOut out{1u, 0u, 1u, (u32)min((i64)SORT_ITER, left)};  // nothing fits: one item without a brick
+    if (dead) return out;  // (CTA-uniform; no barrier: the sort loop runs free again)
+    bool anyfit = false;
+    {
 #pragma unroll
-    for (int u = 0; u < SORT_UNROLL; u++) {
-#pragma unroll
-        for (int d = 0; d < N; d++) {
-            const int mn = __reduce_min_sync(0xffffffffu, ok[u] ? first[u][d] : 0x7fffffff);
-            const int mx = __reduce_max_sync(0xffffffffu, ok[u] ? first[u][d] : -1);
-            if (lane == 0) { sm.bb[u * (SORT_BLOCK / 32) + warp][2 * d] = mn; sm.bb[u * (SORT_BLOCK / 32) + warp][2 * d + 1] = mx; }
-        }
-    }
-    __syncthreads();
-    u32 flags = 0;
-    if (warp == 0) {
-        int mn[N], mx[N];
-#pragma unroll
-        for (int d = 0; d < N; d++) { mn[d] = sm.bb[lane][2 * d]; mx[d] = sm.bb[lane][2 * d + 1]; }
-        int bit = 0;
-#pragma unroll
-        for (int lvl = 1; lvl <= 5; lvl++) {  // nodes of 64, 128, ..., 1024 queries
+        for (int u = 0; u < SORT_UNROLL; u++) {
+            int mn[N], mx[N];
             bool fit = true;
 #pragma unroll
-            for (int d = 0; d < N; d++) {
-                mn[d] = min(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], 1 << (lvl - 1)));
-                mx[d] = max(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], 1 << (lvl - 1)));
-                fit = fit && (mx[d] < mn[d] || mx[d] - mn[d] < p.tile[d]);  // (an empty box fits)
+            for (int d = N - 1; d >= 0; d--) {  // slowest dimension first: a scattered leaf fails at once
+                mn[d] = 0; mx[d] = GROUP_STRAY;
+                if (fit) {
+                    mn[d] = __reduce_min_sync(0xffffffffu, ok[u] ? first[u][d] : 0x7fffffff);
+                    mx[d] = __reduce_max_sync(0xffffffffu, ok[u] ? first[u][d] : -1);
+                    if (d == 0) fit = mx[0] < mn[0] || mx[0] - (mn[0] & ~gg.amask) <= gg.cap0;
+                    else fit = mx[d] < mn[d] || mx[d] - mn[d] < p.tile[d];
+                }
             }
-            const u32 votes = __ballot_sync(0xffffffffu, fit);
-            const int nn = 32 >> lvl;  // nodes at this level: 16, 8, 4, 2, 1
-            for (int j = 0; j < nn; j++) flags |= ((votes >> (j << lvl)) & 1u) << (bit + j);
-            bit += nn;
-            if (lvl == 1 && (lane & 1) == 0) {  // corner of the 64-query node lane/2
-                uint2 c;  // (no valid query in the node: mn == INT_MAX everywhere, kept as the largest corner)
-                c.x = (u32)mn[0];
-                c.y = 0x7fffffffu;
-                if constexpr (N == 2) c.y = (u32)mn[1];
-                if constexpr (N >= 3) c.y = ((u32)mn[1] & 0xffffu) | (((u32)mn[2] & 0xffffu) << 16);
-                corners[lane >> 1] = c;
+            anyfit = anyfit || fit;
+            if (lane == 0) {
+                int* bb = sm.bb[u * (SORT_BLOCK / 32) + warp];
+#pragma unroll
+                for (int d = 0; d < N; d++) { bb[2 * d] = fit ? mn[d] : 0; bb[2 * d + 1] = fit ? mx[d] : GROUP_STRAY; }
             }
         }
     }
-    __syncthreads();
-    return flags;
+    const int some = __syncthreads_or(anyfit ? 1 : 0);
+    if (some && threadIdx.x == 0) {  // the greedy walk over the leaves
+        out = GroupOut{0u, 0u, 0u, 0u};
+        int cmn[N], cmx[N], cstart = 0;
+        bool cstray;
+        auto take = [&](int l) {
+#pragma unroll
+            for (int d = 0; d < N; d++) { cmn[d] = sm.bb[l][2 * d]; cmx[d] = sm.bb[l][2 * d + 1]; }
+            cstray = cmx[0] == GROUP_STRAY;
+            cstart = l;
+        };
+        auto emit = [&](int end) {
+            const bool brick = !cstray && (end - cstart) * 32 >= GROUP_MIN && cmx[0] >= cmn[0];
+            out.start |= 1u << cstart;
+            if (brick) {
+                out.brick |= 1u << cstart;
+                uint2 c;
+                c.x = (u32)(cmn[0] & ~gg.amask);
+                c.y = 0;
+                if constexpr (N == 2) c.y = (u32)cmn[1];
+                if constexpr (N >= 3) c.y = ((u32)cmn[1] & 0xffffu) | (((u32)cmn[2] & 0xffffu) << 16);
+                corners[out.nitems] = c;
+            } else {
+                out.nbad += (u32)max((i64)0, min((i64)(end - cstart) * 32, left - (i64)cstart * 32));
+            }
+            out.nitems++;
+        };
+        take(0);
+        for (int l = 1; l < GROUP_LEAVES; l++) {
+            int mn[N], mx[N];
+#pragma unroll
+            for (int d = 0; d < N; d++) { mn[d] = sm.bb[l][2 * d]; mx[d] = sm.bb[l][2 * d + 1]; }
+            const bool stray = mx[0] == GROUP_STRAY;
+            if (stray && cstray) continue;  // a run of stray leaves is one item
+            if (!stray && !cstray) {
+                int un[N], ux[N];
+#pragma unroll
+                for (int d = 0; d < N; d++) { un[d] = min(cmn[d], mn[d]); ux[d] = max(cmx[d], mx[d]); }
+                if (box_fits<N>(p, gg, un, ux)) {
+#pragma unroll
+                    for (int d = 0; d < N; d++) { cmn[d] = un[d]; cmx[d] = ux[d]; }
+                    continue;
+                }
+            }
+            emit(l);
+            take(l);
+        }
+        emit(GROUP_LEAVES);
+    }
+    return out;
 }
-// the items an iteration's flags stand for: calls emit(first 128-node, nodes, has_brick) in query order; returns their number
-template <typename F> __device__ __forceinline__ int group_items(u32 flags, F emit) {
-    const u32 f1 = flags & 0xffffu, f2 = (flags >> 16) & 0xffu, f3 = (flags >> 24) & 0xfu, f4 = (flags >> 28) & 3u, f5 = (flags >> 30) & 1u;
-    if (f5) { emit(0, 16, true); return 1; }
-    int n = 0;
-    for (int h = 0; h < 2; h++) {
-        if ((f4 >> h) & 1u) { emit(8 * h, 8, true); n++; continue; }
-        for (int q = 2 * h; q < 2 * h + 2; q++) {
-            if ((f3 >> q) & 1u) { emit(4 * q, 4, true); n++; continue; }
-            for (int e = 2 * q; e < 2 * q + 2; e++) {
-                if ((f2 >> e) & 1u) { emit(2 * e, 2, true); n++; continue; }
-                for (int g = 2 * e; g < 2 * e + 2; g++) { emit(g, 1, ((f1 >> g) & 1u) != 0); n++; }
-            }
-        }
+// the items of one iteration in query order: calls emit(k, first leaf, one past the last leaf, has_brick)
+template <typename F> __device__ __forceinline__ void group_items(u32 start, u32 brick, F emit) {
+    int k = 0;
+    u32 rest = start;
+    while (rest) {
+        const int l = __ffs(rest) - 1;
+        rest &= rest - 1;
+        const int e = rest ? __ffs(rest) - 1 : GROUP_LEAVES;
+        emit(k, l, e, ((brick >> l) & 1u) != 0);
+        k++;
     }
-    return n;
 }
 
 template <typename T, int N, int ORDER, int BCF>
-__global__ void __launch_bounds__(SORT_BLOCK) tile_hist_kernel(const EvalParams<N> p, u32* __restrict__ bh, u32 nbins, i64 per_cta, u32* __restrict__ gflags,
+__global__ void __launch_bounds__(SORT_BLOCK) tile_hist_kernel(const EvalParams<N> p, u32* __restrict__ bh, u32 nbins, i64 per_cta, uint2* __restrict__ gflags,
                                                                uint2* __restrict__ gcorner, u32* __restrict__ runcnt) {
     extern __shared__ u32 s_hist[];
     __shared__ GroupSmem s_grp;
     for (u32 b = threadIdx.x; b < nbins; b += SORT_BLOCK) s_hist[b] = 0;
+    if (threadIdx.x == 0) s_grp.dead = 0;
     __syncthreads();
     int ntot = 1;
 #pragma unroll
@@ -1045,9 +1091,11 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_hist_kernel(const EvalParams<
     int shift[N];  // tile extents are powers of two (choose_tile)
 #pragma unroll
     for (int d = 0; d < N; d++) shift[d] = __ffs(p.tile[d]) - 1;
+    const GroupGeo gg{brick_extent(N, ORDER + 1, 0, (int)sizeof(T)) - (ORDER + 1), 16 / (int)sizeof(T) - 1};
     const i64 q0 = (i64)blockIdx.x * per_cta;
     const i64 q1 = q0 + per_cta < p.nq ? q0 + per_cta : p.nq;
     u32 nitems = 0, nbad = 0;  // thread 0: items of this CTA's range, queries in items without a brick
+    bool dead = false;         // CTA-uniform: this range is not grouped, stop looking
     for (i64 qb0 = q0; qb0 < q1; qb0 += SORT_ITER) {  // (uniform trip count: group_iteration is a CTA-wide call)
         const i64 qb = qb0 + threadIdx.x;
         double raw[SORT_UNROLL][N];
@@ -1075,26 +1123,29 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_hist_kernel(const EvalParams<
             }
         }
         const i64 it = qb0 / SORT_ITER;
-        const u32 flags = group_iteration<N>(p, first, ok, s_grp, gcorner + it * GROUP_NODES);
+        const GroupOut go = group_iteration<N>(p, first, ok, s_grp, gcorner + it * GROUP_LEAVES, gg, q1 - qb0, dead);
         if (threadIdx.x == 0) {
-            gflags[it] = flags;
-            const i64 left = q1 - qb0;
-            nitems += (u32)group_items(flags, [&](int e, int n, bool brick) {
-                if (!brick) nbad += (u32)max((i64)0, min((i64)GROUP_MIN, left - (i64)e * GROUP_MIN));
-            });
+            gflags[it] = make_uint2(go.start, go.brick);
+            nitems += go.nitems;
+            nbad += go.nbad;
+            // mostly stray after the first iterations: this is not a grouped batch, stop looking (everything left counts as stray)
+            if (!dead && qb0 - q0 >= 3 * SORT_ITER && (i64)nbad * 2 > qb0 + SORT_ITER - q0) s_grp.dead = 1;
+        }
+        if (!dead) {
+            __syncthreads();
+            dead = s_grp.dead != 0;
         }
     }
-    __syncthreads();
     for (u32 b = threadIdx.x; b < nbins; b += SORT_BLOCK) bh[(size_t)b * gridDim.x + blockIdx.x] = s_hist[b];
     if (threadIdx.x == 0) { runcnt[2 * blockIdx.x] = nitems; runcnt[2 * blockIdx.x + 1] = nbad; }
 }
 
 // work item {corner dim 1, first slot, one past the last, corner dims 2, 3 | no-brick flag}
-__device__ __forceinline__ uint4 make_item(const int* lo, int N, u32 beg, u32 end, bool brick) {
+__device__ __forceinline__ uint4 make_item(const uint2 corner, int N, u32 beg, u32 end, bool brick) {
     u32 w = brick ? 0u : 0x80000000u;
-    if (N == 2) w |= (u32)lo[1] & 0x7fffffffu;
-    if (N >= 3) w |= ((u32)lo[1] & 0x7fffu) | (((u32)lo[2] & 0x7fffu) << 15);
-    return make_uint4((u32)lo[0], beg, end, w);
+    if (N == 2) w |= corner.y & 0x7fffffffu;
+    if (N >= 3) w |= (corner.y & 0x7fffu) | (((corner.y >> 16) & 0x7fffu) << 15);
+    return make_uint4(brick ? corner.x : 0u, beg, end, brick ? w : 0x80000000u);
 }
 template <int N> __device__ __forceinline__ bool item_corner(const uint4 it, int (&lo)[N]) {
     lo[0] = (int)it.x;
@@ -1103,11 +1154,11 @@ template <int N> __device__ __forceinline__ bool item_corner(const uint4 it, int
     return (it.w & 0x80000000u) == 0;  // has a brick
 }
 
-// Grouped batches: the fitting chunks recorded by the binning pass become the work items; slots are the caller's indices.
+// Grouped batches: the chunks recorded by the binning pass become the work items; slots are the caller's indices.
 // Same CTA partition as tile_hist; base[cta] = number of items in the CTAs before it (sorted_decide).  One thread per
 // iteration.
 template <int N>
-__global__ void __launch_bounds__(SORT_BLOCK) run_items_kernel(const EvalParams<N> p, const u32* __restrict__ gflags, const uint2* __restrict__ gcorner,
+__global__ void __launch_bounds__(SORT_BLOCK) run_items_kernel(const EvalParams<N> p, const uint2* __restrict__ gflags, const uint2* __restrict__ gcorner,
                                                                const u32* __restrict__ base, u32* __restrict__ work, const u32* __restrict__ nwork, i64 per_cta) {
     if (nwork[2] == 0) return;
     __shared__ u32 s_w[SORT_BLOCK / 32], s_carry;
@@ -1120,8 +1171,8 @@ __global__ void __launch_bounds__(SORT_BLOCK) run_items_kernel(const EvalParams<
     __syncthreads();
     for (i64 ib = it0; ib < it1; ib += SORT_BLOCK) {
         const i64 it = ib + threadIdx.x;
-        const u32 flags = it < it1 ? gflags[it] : 0u;
-        const u32 cnt = it < it1 ? (u32)group_items(flags, [](int, int, bool) {}) : 0u;
+        const uint2 fl = it < it1 ? gflags[it] : make_uint2(0u, 0u);
+        const u32 cnt = (u32)__popc(fl.x);
         u32 incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -1132,25 +1183,13 @@ __global__ void __launch_bounds__(SORT_BLOCK) run_items_kernel(const EvalParams<
         __syncthreads();
         u32 before = s_carry;
         for (u32 k = 0; k < warp; k++) before += s_w[k];
-        u32 rank = before + incl - cnt;
+        const u32 rank = before + incl - cnt;
         if (it < it1) {
             const i64 qb = it * SORT_ITER;
-            group_items(flags, [&](int e, int n, bool brick_in) {
-                bool brick = brick_in;
-                int lo[3] = {0x7fffffff, 0x7fffffff, 0xffff};
-                for (int k = e; k < e + n; k++) {  // (nodes without a valid query carry the largest corner)
-                    const uint2 c = gcorner[it * GROUP_NODES + k];
-                    lo[0] = min(lo[0], (int)c.x);
-                    lo[1] = min(lo[1], (int)(N >= 3 ? (c.y & 0xffffu) : (c.y & 0x7fffffffu)));
-                    lo[2] = min(lo[2], (int)(c.y >> 16));
-                }
-                if (lo[0] == 0x7fffffff) { lo[0] = lo[1] = lo[2] = 0; brick = false; }  // nothing valid in the chunk
-                if (N >= 3 && lo[1] > 0x7fff) lo[1] = 0;
-                if (N >= 3 && lo[2] > 0x7fff) lo[2] = 0;
-                const i64 b = qb + (i64)e * GROUP_MIN, en = min(q1, b + (i64)n * GROUP_MIN);
-                if (b < en) reinterpret_cast<uint4*>(work)[rank] = make_item(lo, N, (u32)b, (u32)en, brick);
-                else reinterpret_cast<uint4*>(work)[rank] = make_item(lo, N, (u32)q1, (u32)q1, false);  // (past the end of the batch: empty)
-                rank++;
+            group_items(fl.x, fl.y, [&](int k, int l, int e, bool brick) {
+                const i64 b = min(q1, qb + (i64)l * 32), en = min(q1, qb + (i64)e * 32);
+                const uint2 c = brick ? gcorner[it * GROUP_LEAVES + k] : make_uint2(0u, 0u);
+                reinterpret_cast<uint4*>(work)[rank + k] = make_item(c, N, (u32)b, (u32)en, brick && b < en);
             });
         }
         __syncthreads();
@@ -1204,11 +1243,15 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_scatter_kernel(const EvalPara
 // evaluated on its own and returned to its own position).  The counting pass marks the run starts like tile_hist.
 template <typename T, int N, int ORDER, int BCF, bool SCATTER>
 __global__ void __launch_bounds__(SORT_BLOCK) tile_sort_global_kernel(const EvalParams<N> p, u32* __restrict__ bins, T* __restrict__ rec, u32* __restrict__ inv,
-                                                                      i64 per_cta, u32* __restrict__ gflags, uint2* __restrict__ gcorner, u32* __restrict__ runcnt) {
+                                                                      i64 per_cta, uint2* __restrict__ gflags, uint2* __restrict__ gcorner, u32* __restrict__ runcnt) {
     __shared__ GroupSmem s_grp;
     if constexpr (SCATTER) {
         if (p.nwork[2] != 0) return;
+    } else {
+        if (threadIdx.x == 0) s_grp.dead = 0;
+        __syncthreads();
     }
+    const GroupGeo gg{brick_extent(N, ORDER + 1, 0, (int)sizeof(T)) - (ORDER + 1), 16 / (int)sizeof(T) - 1};
     int ntot = 1, shift[N];
 #pragma unroll
     for (int d = 0; d < N; d++) { ntot *= p.ntile[d]; shift[d] = __ffs(p.tile[d]) - 1; }
@@ -1216,6 +1259,7 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_sort_global_kernel(const Eval
     const i64 q1 = q0 + per_cta < p.nq ? q0 + per_cta : p.nq;
     const u32 lane = threadIdx.x & 31;
     u32 nitems = 0, nbad = 0;
+    bool dead = false;
     for (i64 qb0 = q0; qb0 < q1; qb0 += SORT_ITER) {  // (uniform trip count: the warp votes below need every lane)
         const i64 qb = qb0 + threadIdx.x;
         double raw[SORT_UNROLL][N];
@@ -1258,13 +1302,16 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_sort_global_kernel(const Eval
         }
         if constexpr (!SCATTER) {
             const i64 it = qb0 / SORT_ITER;
-            const u32 flags = group_iteration<N>(p, first, ok, s_grp, gcorner + it * GROUP_NODES);
+            const GroupOut go = group_iteration<N>(p, first, ok, s_grp, gcorner + it * GROUP_LEAVES, gg, q1 - qb0, dead);
             if (threadIdx.x == 0) {
-                gflags[it] = flags;
-                const i64 left = q1 - qb0;
-                nitems += (u32)group_items(flags, [&](int e, int n, bool brick) {
-                    if (!brick) nbad += (u32)max((i64)0, min((i64)GROUP_MIN, left - (i64)e * GROUP_MIN));
-                });
+                gflags[it] = make_uint2(go.start, go.brick);
+                nitems += go.nitems;
+                nbad += go.nbad;
+                if (!dead && qb0 - q0 >= 3 * SORT_ITER && (i64)nbad * 2 > qb0 + SORT_ITER - q0) s_grp.dead = 1;
+            }
+            if (!dead) {
+                __syncthreads();
+                dead = s_grp.dead != 0;
             }
         }
     }
@@ -1319,17 +1366,17 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int KEEP> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(KEEP) : "memory"); }
 
 // clip[d]: cells of the brick along d that exist (the brick may stick out of the array)
-template <int N, int L> __device__ __forceinline__ void brick_clip(const EvalParams<N>& p, const int (&lo)[N], int (&clip)[N]) {
+template <typename T, int N, int L> __device__ __forceinline__ void brick_clip(const EvalParams<N>& p, const int (&lo)[N], int (&clip)[N]) {
 #pragma unroll
     for (int d = 0; d < N; d++) {
-        const int full = p.tile[d] + L - 1, left = p.len[d] - lo[d];
+        const int full = d == 0 ? brick_extent(N, L, 0, (int)sizeof(T)) : p.tile[d] + L - 1, left = p.len[d] - lo[d];
         clip[d] = full < left ? full : left;
     }
 }
 // element-wise staging (vol = padded brick volume; padding cells are zero-filled like cells past the array)
 template <typename T, int N, int L> __device__ __forceinline__ void brick_fill(const EvalParams<N>& p, const T* __restrict__ A, T* brick, const int (&lo)[N], int vol) {
     int clip[N];
-    brick_clip<N, L>(p, lo, clip);
+    brick_clip<T, N, L>(p, lo, clip);
     const u32 sbase = (u32)__cvta_generic_to_shared(brick);
 #pragma unroll 4
     for (int e = threadIdx.x; e < vol; e += BRICK_BLOCK) {
@@ -1517,7 +1564,7 @@ __global__ void __launch_bounds__(BRICK_BLOCK, 2)
         const bool have = have_c;  // items without a brick (invalid locations, chunks that do not fit one): every query is deferred
 #pragma unroll
         for (int d = 0; d < N; d++) lo[d] = lo_c[d];
-        brick_clip<N, L>(p, lo, clip);
+        brick_clip<T, N, L>(p, lo, clip);
         const u32 n = end_c - beg_c;
         // the brick of item k has landed: this thread's cp.async groups / the buffer's mbarrier phase
         auto brick_ready = [&]() {
@@ -1728,7 +1775,7 @@ int launch_tiled(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     const i64 per_cta = ((p.nq + nctas - 1) / nctas + SORT_ITER - 1) / SORT_ITER * SORT_ITER;  // whole iterations per CTA
     const u32 bad_percent = grouped_bad_percent((flags & GB_SORTED) != 0);
     const size_t niter = (size_t)(per_cta / SORT_ITER) * nctas;
-    const size_t max_items = (size_t)nbins + (size_t)(p.nq / EVAL_CHUNK) + niter * GROUP_NODES + nctas + 2;
+    const size_t max_items = (size_t)nbins + (size_t)(p.nq / EVAL_CHUNK) + niter * GROUP_LEAVES + nctas + 2;
     const size_t pitch = ((size_t)p.nq + 15) & ~(size_t)15;
     // one scratch allocation: records | sorted outputs | inv | deferred-slot list (`keys`) | work | group corners | bh | boff | hist | offs | group flags | runcnt | runbase | nwork
     constexpr int W = out_words<N>(OUTMODE);
@@ -1736,7 +1783,7 @@ int launch_tiled(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     const size_t nbc = global_bins ? 16 : (size_t)nbins * nctas;
     const size_t rec_bytes = (pitch * (N + 1) * sizeof(T) + 31) & ~(size_t)31;
     const size_t out_bytes = (pitch * W * sizeof(T) + 31) & ~(size_t)31;
-    const size_t words = (pitch + 16) + 4 * max_items + 2 * niter * GROUP_NODES + 2 * nbc + 2 * (size_t)(nbins + 4) + (niter + 4) + 3 * (size_t)(nctas + 4) + 8;
+    const size_t words = (pitch + 16) + 4 * max_items + 2 * niter * GROUP_LEAVES + 2 * (niter + 4) + 2 * nbc + 2 * (size_t)(nbins + 4) + 3 * (size_t)(nctas + 4) + 8;
     AsyncBuf guard(s);  // released on every exit path
     GB_CUDA(guard.alloc(rec_bytes + out_bytes + (pitch + words) * sizeof(u32)));
     unsigned char* scratch = (unsigned char*)guard.p;
@@ -1746,12 +1793,12 @@ int launch_tiled(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     u32* keys = inv + pitch;
     u32* work = keys + pitch + 16;  // (16-byte aligned: items are uint4, see make_item)
     uint2* gcorner = reinterpret_cast<uint2*>(work + 4 * max_items);
-    u32* bh = reinterpret_cast<u32*>(gcorner + niter * GROUP_NODES);
+    uint2* gflags = gcorner + niter * GROUP_LEAVES;
+    u32* bh = reinterpret_cast<u32*>(gflags + (niter + 4));
     u32* boff = bh + nbc;
     u32* hist = boff + nbc;
     u32* offs = hist + (nbins + 4);
-    u32* gflags = offs + (nbins + 4);
-    u32* runcnt = gflags + (niter + 4);
+    u32* runcnt = offs + (nbins + 4);
     u32* runbase = runcnt + 2 * (nctas + 4);
     u32* nwork = runbase + (nctas + 4);
     TileGeo geo;

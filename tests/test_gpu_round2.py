@@ -20,11 +20,12 @@ def same(a, b):
 
 
 def tile_key(X, shape):
-    """a spatial key that groups queries by (16 x 16 x 8)-cell blocks (2-D: 64 x 32), dim 1 fastest"""
+    """a spatial key that groups queries by blocks of 8 x 8 x 4 cells (2-D: 32 x 16), dim 1 fastest: any block whose
+    first taps span at most one brick tile (16 x 16 x 8 cells in 3-D, 64 x 64 in 2-D) will do"""
     fl = np.floor(X).astype(np.int64)
     if X.shape[1] == 3:
-        return ((fl[:, 2] >> 3) * 4096 + (fl[:, 1] >> 4)) * 4096 + (fl[:, 0] >> 4)
-    return (fl[:, 1] >> 5) * 65536 + (fl[:, 0] >> 6)
+        return ((fl[:, 2] >> 2) * 4096 + (fl[:, 1] >> 3)) * 4096 + (fl[:, 0] >> 3)
+    return (fl[:, 1] >> 4) * 65536 + (fl[:, 0] >> 5)
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
