@@ -235,7 +235,7 @@ def extra_configs(gb, torch, np, O, peak, traffic, reps=5):
         del X, v
     del G, A
 
-    # ---- C2 with tile-sorted queries (coherent callers: no permutation needed) --------------------------------------
+    # ---- C2 with block-sorted queries (coherent callers: evaluated in place, no permutation) --------------------------------------
     n, nq = N_GRID, NQ
     A = gb.jl_empty((n, n, n), torch.float64, dev)
     gb.synth_uniform(A, SEED_GRID)
@@ -256,7 +256,7 @@ def extra_configs(gb, torch, np, O, peak, traffic, reps=5):
         if not fast:
             ov, og, _, _ = O.evaluate(co, "nan", "cubic", sub(Xs, idx), 3)
             par = bool(np.array_equal(ov, sub(v, idx), equal_nan=True) and np.array_equal(og, sub(g, idx), equal_nan=True))
-        rows.append(_row("C2 3-D InterpCubic BCnan 256^3 f64 valgrad, 1e7 queries pre-sorted by grid tile, %s" % ("FAST" if fast else "EXACT"), nq, "points",
+        rows.append(_row("C2 3-D InterpCubic BCnan 256^3 f64 valgrad, 1e7 queries sorted by 16x16x8-cell block (coherent: the probe hands them to the plain kernel), %s" % ("FAST" if fast else "EXACT"), nq, "points",
                          BYTES_PER_QUERY, best, med, peak, par, traffic.get("c2_sorted_%s_bytes_per_step" % ("fast" if fast else "exact"))))
     del G, A, Xs, v, g
 

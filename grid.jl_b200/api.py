@@ -1187,7 +1187,7 @@ def profile_read():
     L.check(L.lib().gb_profile_read(ms, 8, C.byref(n)))
     out = {PROFILE_STAGES[i]: float(ms[i]) for i in range(n.value)}
     if n.value:
-        out["grouped"] = float(ms[6])  # 1.0: the batch arrived grouped by tile and was evaluated in place (no permutation)
+        out["coherent"] = float(ms[6])  # 1.0: the batch arrived spatially coherent and was evaluated in place by the plain kernel
     return out
 
 

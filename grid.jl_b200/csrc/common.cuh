@@ -58,7 +58,7 @@ extern std::atomic<long long> g_launches;
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int num_sms();
 void prof_mark(int stage_boundary, cudaStream_t s);
-void prof_mode(const unsigned int* nwork, cudaStream_t s);  // records which path (sorted / grouped) the tiled call took
+void prof_mode(const unsigned int* nwork, cudaStream_t s);  // records which path (bins / plain for a coherent batch) the tiled call took
 int prof_enable(int on);
 int prof_read(double* ms, int n, int* nstages);  // eval_tile.cu: records boundary event i (0..6) when profiling is on
 
@@ -91,13 +91,12 @@ template <typename T> __device__ __forceinline__ T exact_div(T a, T d, T rd) {
 // fixed leading tile extents (cells), so that brick strides are compile-time constants; the extent
 // along the LAST dimension is chosen at run time (choose_tile): N=1 -, N=2 64, N=3 16x16, N=4 8x8x8
 __host__ __device__ constexpr int brick_tile(int N, int d) { return N == 2 ? 64 : N == 3 ? 16 : 8; }
-// extent of the brick along dimension e (tile + L-1 halo cells).  TMA (cp.async.bulk.tensor) wants every box row to start on a
-// 16-byte boundary and to be a multiple of 16 bytes long (esz = element size, q = 16/esz elements): the contiguous dimension
-// therefore carries q-1 spare cells -- a brick whose corner had to be aligned DOWN still holds a full tile -- and is rounded
-// up to a multiple of q.
+// extent of the brick along dimension e (tile + L-1 halo cells); the contiguous dimension is padded to a multiple of 16 bytes
+// (esz = element size) so that a brick row is a legal TMA box row (cp.async.bulk.tensor: boxDim[0]*esz % 16 == 0; the box must
+// also START on a 16-byte boundary -- an odd corner raises "illegal instruction" -- which tile-aligned corners do)
 __host__ __device__ constexpr int brick_extent(int N, int L, int e, int esz) {
     const int f = brick_tile(N, e) + L - 1, q = 16 / esz;
-    return e == 0 ? (f + (q - 1) + q - 1) / q * q : f;
+    return e == 0 ? (f + q - 1) / q * q : f;
 }
 __host__ __device__ constexpr int brick_stride(int N, int L, int d, int esz) {
     int s = 1;
@@ -135,8 +134,8 @@ template <int N> struct EvalParams {
     int tile[N];          // cells per tile
     int ntile[N];         // tiles per dimension
     const u32* work;      // 4 words per work item: tile, first slot, one past the last, -
-    const u32* nwork;     // device: [0] number of work items, [1] the ticket counter CTAs pull items from, [2] mode: 1 = the batch
-                          // arrived grouped by tile and the items index the CALLER's arrays (no permutation), 0 = sorted slots
+    const u32* nwork;     // device: [0] number of work items, [1] the ticket counter CTAs pull items from, [2] 1 = the batch arrived
+                          // spatially coherent: the binning kernels exit and the plain kernel evaluates it in place
     int use_tma;          // bricks are staged by cp.async.bulk.tensor through the kernel's tensor map (else element-wise cp.async)
 };
 

@@ -804,8 +804,11 @@ __device__ __forceinline__ void eval_one(const EvalParams<N>& p, const T (&x)[N]
 // while the current one is evaluated.
 constexpr int EVAL_BLOCK = 256;
 
+// `only_if` (may be NULL): device flag of the tiled launcher -- the kernel runs only when *only_if != 0 (the batch was found
+// coherent, coherence_probe_kernel) and exits at once otherwise.
 template <typename T, int N, int ORDER, int BCF, int OUTMODE, bool FAST>
-__global__ void __launch_bounds__(EVAL_BLOCK, 2) eval_kernel(const EvalParams<N> p) {
+__global__ void __launch_bounds__(EVAL_BLOCK, 2) eval_kernel(const EvalParams<N> p, const u32* __restrict__ only_if) {
+    if (only_if && *only_if == 0) return;
     const i64 step = (i64)gridDim.x * EVAL_BLOCK;
     i64 q = (i64)blockIdx.x * EVAL_BLOCK + threadIdx.x;
     double raw_n[N];
@@ -828,21 +831,15 @@ __global__ void __launch_bounds__(EVAL_BLOCK, 2) eval_kernel(const EvalParams<N>
 }
 
 // ====================================================================================================
-// Tiled ("brick") evaluation: the batch is grouped by grid tile, then evaluated tile by tile out of
+// Tiled ("brick") evaluation: the batch is sorted by grid tile, then evaluated tile by tile out of
 // shared memory.
-//   tile_hist      key of every query (tile of its lowest tap per dimension) + per-CTA histograms in
-//                  shared memory (no global atomics), written bin-major to bh[bin][cta].  The same pass asks
-//                  whether the batch, in the order it ARRIVED, already consists of chunks that each fit one brick:
-//                  bounding boxes of the first taps of 32 consecutive queries (warp reductions), merged up a binary
-//                  tree to chunks of 128 ... 1024 queries (group_iteration).
-//   sorted_decide  (eval_tile.cu) nearly all queries in fitting chunks = the batch is spatially grouped (sorted by
-//                  tile or cell block, Morton / Hilbert order, a lattice walked block by block, points binned once
-//                  and evaluated many times).  Then the chunks themselves are the work items (run_items), each with
-//                  the brick whose corner is its box's corner; they index the CALLER's arrays, and nothing is
-//                  permuted: the brick kernel reads the coordinates and writes val / grad / hess in place,
-//                  coalesced.  The decision is taken on the device (nwork[2]); the kernels of the path not taken
-//                  exit at once, so the host never waits for it.
+//   coherence_probe  looks at a sample of the batch in the order it ARRIVED: spatially coherent batches (lattices in raster
+//                  order, points sorted by cell / tile / Morton code) skip everything below -- the kernels exit at
+//                  once -- and are evaluated in place by the plain kernel, whose gathers then hit L1 / L2; decided on
+//                  the device, the host never waits (nwork[2])
 //   otherwise      a counting sort:
+//   tile_hist      key of every query (tile of its lowest tap per dimension) + per-CTA histograms in
+//                  shared memory (no global atomics), written bin-major to bh[bin][cta]
 //   tile_offsets   (eval_tile.cu) per-bin totals, scan, work-item list (a tile's queries split into
 //                  items of <= EVAL_CHUNK), per-(bin,cta) write cursors
 //   tile_scatter   each CTA replays its slice and writes one RECORD per query at its sorted slot:
@@ -855,7 +852,7 @@ __global__ void __launch_bounds__(EVAL_BLOCK, 2) eval_kernel(const EvalParams<N>
 //                  16 bytes fall back to element-wise cp.async.  Records are read coalesced (the first
 //                  record of the next item is prefetched across the item boundary); every tap is an
 //                  LDS at a compile-time offset from the query's first tap; outputs go to the
-//                  query's sorted slot (or, grouped batches, to its own position).
+//                  query's sorted slot.
 //   eval_deferred  a query whose taps are not L consecutive cells inside the brick (wrapped /
 //                  repeated taps at the grid boundary, taps past the last sample, invalid location)
 //                  or that met a NaN/Inf coefficient is not evaluated by eval_brick: its slot goes
@@ -912,20 +909,9 @@ template <typename T, int N> __device__ __forceinline__ void load_record(const T
         q = bits_of(__ldg(r + N));
     }
 }
-// One query of a work item.  DIRECT (grouped batches): slot j IS the query's index in the caller's batch, the
-// coordinates come from the caller's array; otherwise from the sorted record.
-template <typename T, int N, bool DIRECT> __device__ __forceinline__ void fetch_query(const EvalParams<N>& p, const T* __restrict__ rec, u32 j, T (&x)[N], u32& q) {
-    if constexpr (DIRECT) {
-        load_index_coords<T, N>(p, (i64)j, x);
-        q = j;
-    } else {
-        load_record<T, N>(rec, j, x, q);
-    }
-}
-
 // sort key of a query: the tile of its lowest tap per dimension (a locality hint only -- queries whose taps
 // leave the brick are deferred); invalid locations go to the extra last bin.  first[] receives the coordinate of the
-// query's FIRST tap per dimension (clamped into the array), the corner the grouped-batch boxes are built from.
+// query's FIRST tap per dimension (clamped into the array), what the coherence probe builds its bounding boxes from.
 template <typename T, int N, int ORDER, int BCF>
 __device__ __forceinline__ u32 tile_key(const EvalParams<N>& p, const T (&x)[N], const int (&shift)[N], int ntot, int (&first)[N], bool& valid) {
     int c[N][ORDER + 1];
@@ -954,136 +940,79 @@ __device__ __forceinline__ u32 tile_key(const EvalParams<N>& p, const T (&x)[N],
     return tile_key<T, N, ORDER, BCF>(p, x, shift, ntot, first, valid);
 }
 
-// ---- grouped batches: does the batch, AS IT ARRIVED, consist of chunks that fit a brick? ------------------------------
-// One iteration of a sort CTA covers SORT_ITER = 1024 consecutive queries = 32 leaves of 32 (warp w, slot u: leaf u*8 + w).
-// Per leaf the bounding box of the queries' first taps (warp reductions; a leaf whose own box exceeds a tile is "stray").
-// Thread 0 then walks the 32 leaves greedily: a chunk grows leaf by leaf while its box still fits one brick -- at most one
-// tile wide in every dimension, so that every query in it finds its whole neighbourhood in the brick whose corner is the
-// box's corner -- and is cut where it would not.  Chunks of >= GROUP_MIN queries are the work items of a grouped
-// batch; shorter chunks and runs of stray leaves become items WITHOUT a brick (their queries take the global-memory
-// path).  Recorded per iteration: a bit per leaf where an item starts, a bit whether that item has a brick, and the
-// items' brick corners; per CTA: items, and queries left without a brick.
-// Uniformly random batches pay two reductions per leaf and one barrier: no leaf fits, the walk is skipped; a CTA whose
-// first iterations are mostly stray stops looking altogether.
-// (staging a 32 KB brick costs about as much as evaluating 90 queries out of it, the global-memory path about 3x a brick
-// evaluation per query: break-even near 40 queries)
-constexpr int GROUP_MIN = 64;    // smallest chunk worth a brick of its own
-constexpr int GROUP_LEAVES = 32;  // leaves (and at most that many items) per iteration
-constexpr int GROUP_STRAY = 0x7ffffff0;
-struct GroupSmem { int bb[GROUP_LEAVES][2 * MAXD]; int dead; };
-struct GroupGeo { int cap0, amask; };  // dim 1: the corner is aligned down to 16 bytes (amask = 16/sizeof(T) - 1), first taps fit up to cap0 cells past it
-struct GroupOut { u32 start, brick, nitems, nbad; };  // thread 0 only
-
-template <int N> __device__ __forceinline__ bool box_fits(const EvalParams<N>& p, const GroupGeo& gg, const int (&mn)[N], const int (&mx)[N]) {
-    bool fit = mx[0] < mn[0] || mx[0] - (mn[0] & ~gg.amask) <= gg.cap0;  // (an empty box fits)
+// ---- coherent batches ------------------------------------------------------------------------------------------------
+// Binning pays for batches whose consecutive queries are far apart (uniformly random: every warp of the plain path drags
+// 32 x 16 tap rows through L2).  A batch that arrives spatially coherent -- a lattice walked in raster order, points sorted by
+// cell / tile / Morton code, an image warp -- is served faster by the plain path, whose tap rows then hit L1 / L2
+// (measured on C2, profiles/README.md: 0.62-1.0 ms against 0.9-1.15 ms through the bins).  The probe looks at a sample
+// of the batch AS IT ARRIVED -- per sort CTA four groups of 256 consecutive queries, i.e. 32 leaves of 32 consecutive
+// queries -- and calls a leaf coherent when the bounding box of its queries' first taps holds at most `vmax` cells (four brick
+// tiles).  Nearly all leaves coherent: nwork[2] = 1, the binning kernels exit at once and the plain kernel evaluates the
+// batch in place; else nwork[2] = 0 and the plain kernel exits.  Decided on the device: the host never waits.
+// nwork[3] coherent leaves, nwork[4] leaves, nwork[5] CTAs done (all zeroed by the launcher).
+template <typename T, int N, int ORDER, int BCF>
+__global__ void __launch_bounds__(SORT_BLOCK) coherence_probe_kernel(const EvalParams<N> p, u32* __restrict__ nwork, i64 per_cta, u32 vmax, u32 need_percent) {
+    __shared__ u32 s_last;
+    const i64 q0 = (i64)blockIdx.x * per_cta;
+    const i64 q1 = q0 + per_cta < p.nq ? q0 + per_cta : p.nq;
+    const u32 lane = threadIdx.x & 31;
+    int shift[N];
 #pragma unroll
-    for (int d = 1; d < N; d++) fit = fit && (mx[d] < mn[d] || mx[d] - mn[d] < p.tile[d]);
-    return fit;
-}
-// Every thread of the CTA calls; first[u][d] / ok[u] describe the thread's query of slot u (ok false: not a query or an
-// invalid location); `left` = queries from the iteration's first one to the end of the CTA's range.  corners[] receives
-// the brick corner of the k-th item of the iteration.  The caller closes the iteration with a CTA barrier.
-template <int N>
-__device__ __forceinline__ GroupOut group_iteration(const EvalParams<N>& p, const int (&first)[SORT_UNROLL][N], const bool (&ok)[SORT_UNROLL], GroupSmem& sm,
-                                                    uint2* __restrict__ corners, const GroupGeo gg, const i64 left, const bool dead) {
-    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    GroupOut out{1u, 0u, 1u, (u32)min((i64)SORT_ITER, left)};  // nothing fits: one item without a brick
-    if (dead) return out;  // (CTA-uniform; no barrier: the sort loop runs free again)
-    bool anyfit = false;
-    {
+    for (int d = 0; d < N; d++) shift[d] = 0;
+    u32 good = 0, seen = 0;
+    if (q0 < q1) {
+        const i64 stride = ((q1 - q0) / SORT_UNROLL) & ~(i64)(SORT_BLOCK - 1);  // (groups start on multiples of 256 past q0)
+        double raw[SORT_UNROLL][N];
 #pragma unroll
         for (int u = 0; u < SORT_UNROLL; u++) {
-            int mn[N], mx[N];
-            bool fit = true;
+            const i64 q = q0 + u * stride + threadIdx.x;
+            if (q < q1 && (u == 0 || stride > 0)) {
 #pragma unroll
-            for (int d = N - 1; d >= 0; d--) {  // slowest dimension first: a scattered leaf fails at once
-                mn[d] = 0; mx[d] = GROUP_STRAY;
-                if (fit) {
-                    mn[d] = __reduce_min_sync(0xffffffffu, ok[u] ? first[u][d] : 0x7fffffff);
-                    mx[d] = __reduce_max_sync(0xffffffffu, ok[u] ? first[u][d] : -1);
-                    if (d == 0) fit = mx[0] < mn[0] || mx[0] - (mn[0] & ~gg.amask) <= gg.cap0;
-                    else fit = mx[d] < mn[d] || mx[d] - mn[d] < p.tile[d];
-                }
-            }
-            anyfit = anyfit || fit;
-            if (lane == 0) {
-                int* bb = sm.bb[u * (SORT_BLOCK / 32) + warp];
-#pragma unroll
-                for (int d = 0; d < N; d++) { bb[2 * d] = fit ? mn[d] : 0; bb[2 * d + 1] = fit ? mx[d] : GROUP_STRAY; }
+                for (int d = 0; d < N; d++) raw[u][d] = load_raw<N>(p, d, q);
             }
         }
-    }
-    const int some = __syncthreads_or(anyfit ? 1 : 0);
-    if (some && threadIdx.x == 0) {  // the greedy walk over the leaves
-        out = GroupOut{0u, 0u, 0u, 0u};
-        int cmn[N], cmx[N], cstart = 0;
-        bool cstray;
-        auto take = [&](int l) {
 #pragma unroll
-            for (int d = 0; d < N; d++) { cmn[d] = sm.bb[l][2 * d]; cmx[d] = sm.bb[l][2 * d + 1]; }
-            cstray = cmx[0] == GROUP_STRAY;
-            cstart = l;
-        };
-        auto emit = [&](int end) {
-            const bool brick = !cstray && (end - cstart) * 32 >= GROUP_MIN && cmx[0] >= cmn[0];
-            out.start |= 1u << cstart;
-            if (brick) {
-                out.brick |= 1u << cstart;
-                uint2 c;
-                c.x = (u32)(cmn[0] & ~gg.amask);
-                c.y = 0;
-                if constexpr (N == 2) c.y = (u32)cmn[1];
-                if constexpr (N >= 3) c.y = ((u32)cmn[1] & 0xffffu) | (((u32)cmn[2] & 0xffffu) << 16);
-                corners[out.nitems] = c;
-            } else {
-                out.nbad += (u32)max((i64)0, min((i64)(end - cstart) * 32, left - (i64)cstart * 32));
+        for (int u = 0; u < SORT_UNROLL; u++) {
+            const i64 q = q0 + u * stride + threadIdx.x;
+            const bool act = q < q1 && (u == 0 || stride > 0);
+            int first[N];
+            bool ok = false;
+#pragma unroll
+            for (int d = 0; d < N; d++) first[d] = 0;
+            if (act) {
+                T x[N];
+#pragma unroll
+                for (int d = 0; d < N; d++) x[d] = index_coord<T, N>(p, d, raw[u][d]);
+                tile_key<T, N, ORDER, BCF>(p, x, shift, 0, first, ok);
             }
-            out.nitems++;
-        };
-        take(0);
-        for (int l = 1; l < GROUP_LEAVES; l++) {
-            int mn[N], mx[N];
+            if (!__any_sync(0xffffffffu, act)) continue;
+            double vol = 1.0;
 #pragma unroll
-            for (int d = 0; d < N; d++) { mn[d] = sm.bb[l][2 * d]; mx[d] = sm.bb[l][2 * d + 1]; }
-            const bool stray = mx[0] == GROUP_STRAY;
-            if (stray && cstray) continue;  // a run of stray leaves is one item
-            if (!stray && !cstray) {
-                int un[N], ux[N];
-#pragma unroll
-                for (int d = 0; d < N; d++) { un[d] = min(cmn[d], mn[d]); ux[d] = max(cmx[d], mx[d]); }
-                if (box_fits<N>(p, gg, un, ux)) {
-#pragma unroll
-                    for (int d = 0; d < N; d++) { cmn[d] = un[d]; cmx[d] = ux[d]; }
-                    continue;
-                }
+            for (int d = 0; d < N; d++) {
+                const int mn = __reduce_min_sync(0xffffffffu, ok ? first[d] : 0x7fffffff);
+                const int mx = __reduce_max_sync(0xffffffffu, ok ? first[d] : -1);
+                vol *= mx >= mn ? (double)(mx - mn + 1) : 1.0;
             }
-            emit(l);
-            take(l);
+            seen++;
+            good += vol <= (double)vmax ? 1u : 0u;
         }
-        emit(GROUP_LEAVES);
     }
-    return out;
-}
-// the items of one iteration in query order: calls emit(k, first leaf, one past the last leaf, has_brick)
-template <typename F> __device__ __forceinline__ void group_items(u32 start, u32 brick, F emit) {
-    int k = 0;
-    u32 rest = start;
-    while (rest) {
-        const int l = __ffs(rest) - 1;
-        rest &= rest - 1;
-        const int e = rest ? __ffs(rest) - 1 : GROUP_LEAVES;
-        emit(k, l, e, ((brick >> l) & 1u) != 0);
-        k++;
+    if (lane == 0 && seen) { atomicAdd(nwork + 3, good); atomicAdd(nwork + 4, seen); }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(nwork + 5, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {  // every CTA has reported
+        const u32 g = atomicAdd(nwork + 3, 0u), n = atomicAdd(nwork + 4, 0u);
+        nwork[2] = (n > 0 && (unsigned long long)g * 100ull >= (unsigned long long)n * need_percent) ? 1u : 0u;
     }
 }
 
 template <typename T, int N, int ORDER, int BCF>
-__global__ void __launch_bounds__(SORT_BLOCK) tile_hist_kernel(const EvalParams<N> p, u32* __restrict__ bh, u32 nbins, i64 per_cta, uint2* __restrict__ gflags,
-                                                               uint2* __restrict__ gcorner, u32* __restrict__ runcnt) {
+__global__ void __launch_bounds__(SORT_BLOCK) tile_hist_kernel(const EvalParams<N> p, u32* __restrict__ bh, u32 nbins, i64 per_cta) {
+    if (p.nwork[2] != 0) return;  // coherent batch (coherence_probe_kernel): the plain kernel takes it
     extern __shared__ u32 s_hist[];
-    __shared__ GroupSmem s_grp;
     for (u32 b = threadIdx.x; b < nbins; b += SORT_BLOCK) s_hist[b] = 0;
-    if (threadIdx.x == 0) s_grp.dead = 0;
     __syncthreads();
     int ntot = 1;
 #pragma unroll
@@ -1091,13 +1020,9 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_hist_kernel(const EvalParams<
     int shift[N];  // tile extents are powers of two (choose_tile)
 #pragma unroll
     for (int d = 0; d < N; d++) shift[d] = __ffs(p.tile[d]) - 1;
-    const GroupGeo gg{brick_extent(N, ORDER + 1, 0, (int)sizeof(T)) - (ORDER + 1), 16 / (int)sizeof(T) - 1};
     const i64 q0 = (i64)blockIdx.x * per_cta;
     const i64 q1 = q0 + per_cta < p.nq ? q0 + per_cta : p.nq;
-    u32 nitems = 0, nbad = 0;  // thread 0: items of this CTA's range, queries in items without a brick
-    bool dead = false;         // CTA-uniform: this range is not grouped, stop looking
-    for (i64 qb0 = q0; qb0 < q1; qb0 += SORT_ITER) {  // (uniform trip count: group_iteration is a CTA-wide call)
-        const i64 qb = qb0 + threadIdx.x;
+    for (i64 qb = q0 + threadIdx.x; qb < q1; qb += SORT_ITER) {
         double raw[SORT_UNROLL][N];
 #pragma unroll
         for (int u = 0; u < SORT_UNROLL; u++) {
@@ -1107,46 +1032,22 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_hist_kernel(const EvalParams<
                 for (int d = 0; d < N; d++) raw[u][d] = load_raw<N>(p, d, q);
             }
         }
-        int first[SORT_UNROLL][N];
-        bool ok[SORT_UNROLL];
 #pragma unroll
         for (int u = 0; u < SORT_UNROLL; u++) {
             const i64 q = qb + u * SORT_BLOCK;
-            ok[u] = false;
-#pragma unroll
-            for (int d = 0; d < N; d++) first[u][d] = 0;
             if (q < q1) {
                 T x[N];
 #pragma unroll
                 for (int d = 0; d < N; d++) x[d] = index_coord<T, N>(p, d, raw[u][d]);
-                atomicAdd(s_hist + tile_key<T, N, ORDER, BCF>(p, x, shift, ntot, first[u], ok[u]), 1u);
+                atomicAdd(s_hist + tile_key<T, N, ORDER, BCF>(p, x, shift, ntot), 1u);
             }
         }
-        const i64 it = qb0 / SORT_ITER;
-        const GroupOut go = group_iteration<N>(p, first, ok, s_grp, gcorner + it * GROUP_LEAVES, gg, q1 - qb0, dead);
-        if (threadIdx.x == 0) {
-            gflags[it] = make_uint2(go.start, go.brick);
-            nitems += go.nitems;
-            nbad += go.nbad;
-            // mostly stray after the first iterations: this is not a grouped batch, stop looking (everything left counts as stray)
-            if (!dead && qb0 - q0 >= 3 * SORT_ITER && (i64)nbad * 2 > qb0 + SORT_ITER - q0) s_grp.dead = 1;
-        }
-        if (!dead) {
-            __syncthreads();
-            dead = s_grp.dead != 0;
-        }
     }
+    __syncthreads();
     for (u32 b = threadIdx.x; b < nbins; b += SORT_BLOCK) bh[(size_t)b * gridDim.x + blockIdx.x] = s_hist[b];
-    if (threadIdx.x == 0) { runcnt[2 * blockIdx.x] = nitems; runcnt[2 * blockIdx.x + 1] = nbad; }
 }
 
-// work item {corner dim 1, first slot, one past the last, corner dims 2, 3 | no-brick flag}
-__device__ __forceinline__ uint4 make_item(const uint2 corner, int N, u32 beg, u32 end, bool brick) {
-    u32 w = brick ? 0u : 0x80000000u;
-    if (N == 2) w |= corner.y & 0x7fffffffu;
-    if (N >= 3) w |= (corner.y & 0x7fffu) | (((corner.y >> 16) & 0x7fffu) << 15);
-    return make_uint4(brick ? corner.x : 0u, beg, end, brick ? w : 0x80000000u);
-}
+// work item {brick corner dim 1, first slot, one past the last, corner dims 2, 3 | no-brick flag} (written by tile_scan_kernel)
 template <int N> __device__ __forceinline__ bool item_corner(const uint4 it, int (&lo)[N]) {
     lo[0] = (int)it.x;
     if constexpr (N == 2) lo[1] = (int)(it.w & 0x7fffffffu);
@@ -1154,55 +1055,11 @@ template <int N> __device__ __forceinline__ bool item_corner(const uint4 it, int
     return (it.w & 0x80000000u) == 0;  // has a brick
 }
 
-// Grouped batches: the chunks recorded by the binning pass become the work items; slots are the caller's indices.
-// Same CTA partition as tile_hist; base[cta] = number of items in the CTAs before it (sorted_decide).  One thread per
-// iteration.
-template <int N>
-__global__ void __launch_bounds__(SORT_BLOCK) run_items_kernel(const EvalParams<N> p, const uint2* __restrict__ gflags, const uint2* __restrict__ gcorner,
-                                                               const u32* __restrict__ base, u32* __restrict__ work, const u32* __restrict__ nwork, i64 per_cta) {
-    if (nwork[2] == 0) return;
-    __shared__ u32 s_w[SORT_BLOCK / 32], s_carry;
-    const i64 q0 = (i64)blockIdx.x * per_cta;
-    const i64 q1 = q0 + per_cta < p.nq ? q0 + per_cta : p.nq;
-    if (q0 >= q1) return;
-    const i64 it0 = q0 / SORT_ITER, it1 = (q1 + SORT_ITER - 1) / SORT_ITER;
-    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_carry = base[blockIdx.x];
-    __syncthreads();
-    for (i64 ib = it0; ib < it1; ib += SORT_BLOCK) {
-        const i64 it = ib + threadIdx.x;
-        const uint2 fl = it < it1 ? gflags[it] : make_uint2(0u, 0u);
-        const u32 cnt = (u32)__popc(fl.x);
-        u32 incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((int)lane >= o) incl += t;
-        }
-        if (lane == 31) s_w[warp] = incl;
-        __syncthreads();
-        u32 before = s_carry;
-        for (u32 k = 0; k < warp; k++) before += s_w[k];
-        const u32 rank = before + incl - cnt;
-        if (it < it1) {
-            const i64 qb = it * SORT_ITER;
-            group_items(fl.x, fl.y, [&](int k, int l, int e, bool brick) {
-                const i64 b = min(q1, qb + (i64)l * 32), en = min(q1, qb + (i64)e * 32);
-                const uint2 c = brick ? gcorner[it * GROUP_LEAVES + k] : make_uint2(0u, 0u);
-                reinterpret_cast<uint4*>(work)[rank + k] = make_item(c, N, (u32)b, (u32)en, brick && b < en);
-            });
-        }
-        __syncthreads();
-        if (threadIdx.x == SORT_BLOCK - 1) s_carry = before + incl;
-        __syncthreads();
-    }
-}
-
 // (the key is recomputed rather than carried over from tile_hist: this kernel waits on memory, the arithmetic is free)
 template <typename T, int N, int ORDER, int BCF>
 __global__ void __launch_bounds__(SORT_BLOCK) tile_scatter_kernel(const EvalParams<N> p, const u32* __restrict__ boff, T* __restrict__ rec,
                                                                   u32* __restrict__ inv, u32 nbins, i64 per_cta) {
-    if (p.nwork[2] != 0) return;  // grouped batch: nothing to permute
+    if (p.nwork[2] != 0) return;  // coherent batch: the plain kernel takes it
     extern __shared__ u32 s_cur[];
     for (u32 b = threadIdx.x; b < nbins; b += SORT_BLOCK) s_cur[b] = boff[(size_t)b * gridDim.x + blockIdx.x];
     __syncthreads();
@@ -1243,23 +1100,14 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_scatter_kernel(const EvalPara
 // evaluated on its own and returned to its own position).  The counting pass marks the run starts like tile_hist.
 template <typename T, int N, int ORDER, int BCF, bool SCATTER>
 __global__ void __launch_bounds__(SORT_BLOCK) tile_sort_global_kernel(const EvalParams<N> p, u32* __restrict__ bins, T* __restrict__ rec, u32* __restrict__ inv,
-                                                                      i64 per_cta, uint2* __restrict__ gflags, uint2* __restrict__ gcorner, u32* __restrict__ runcnt) {
-    __shared__ GroupSmem s_grp;
-    if constexpr (SCATTER) {
-        if (p.nwork[2] != 0) return;
-    } else {
-        if (threadIdx.x == 0) s_grp.dead = 0;
-        __syncthreads();
-    }
-    const GroupGeo gg{brick_extent(N, ORDER + 1, 0, (int)sizeof(T)) - (ORDER + 1), 16 / (int)sizeof(T) - 1};
+                                                                      i64 per_cta) {
+    if (p.nwork[2] != 0) return;  // coherent batch: the plain kernel takes it
     int ntot = 1, shift[N];
 #pragma unroll
     for (int d = 0; d < N; d++) { ntot *= p.ntile[d]; shift[d] = __ffs(p.tile[d]) - 1; }
     const i64 q0 = (i64)blockIdx.x * per_cta;
     const i64 q1 = q0 + per_cta < p.nq ? q0 + per_cta : p.nq;
     const u32 lane = threadIdx.x & 31;
-    u32 nitems = 0, nbad = 0;
-    bool dead = false;
     for (i64 qb0 = q0; qb0 < q1; qb0 += SORT_ITER) {  // (uniform trip count: the warp votes below need every lane)
         const i64 qb = qb0 + threadIdx.x;
         double raw[SORT_UNROLL][N];
@@ -1271,21 +1119,16 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_sort_global_kernel(const Eval
                 for (int d = 0; d < N; d++) raw[u][d] = load_raw<N>(p, d, q);
             }
         }
-        int first[SORT_UNROLL][N];
-        bool ok[SORT_UNROLL];
 #pragma unroll
         for (int u = 0; u < SORT_UNROLL; u++) {
             const i64 q = qb + u * SORT_BLOCK;
             const bool act = q < q1;
             T x[N];
             u32 key = 0xffffffffu;
-            ok[u] = false;
-#pragma unroll
-            for (int d = 0; d < N; d++) first[u][d] = 0;
             if (act) {
 #pragma unroll
                 for (int d = 0; d < N; d++) x[d] = index_coord<T, N>(p, d, raw[u][d]);
-                key = tile_key<T, N, ORDER, BCF>(p, x, shift, ntot, first[u], ok[u]);
+                key = tile_key<T, N, ORDER, BCF>(p, x, shift, ntot);
             }
             const u32 peers = __match_any_sync(0xffffffffu, key);
             const u32 leader = __ffs(peers) - 1;
@@ -1300,23 +1143,6 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_sort_global_kernel(const Eval
                 }
             }
         }
-        if constexpr (!SCATTER) {
-            const i64 it = qb0 / SORT_ITER;
-            const GroupOut go = group_iteration<N>(p, first, ok, s_grp, gcorner + it * GROUP_LEAVES, gg, q1 - qb0, dead);
-            if (threadIdx.x == 0) {
-                gflags[it] = make_uint2(go.start, go.brick);
-                nitems += go.nitems;
-                nbad += go.nbad;
-                if (!dead && qb0 - q0 >= 3 * SORT_ITER && (i64)nbad * 2 > qb0 + SORT_ITER - q0) s_grp.dead = 1;
-            }
-            if (!dead) {
-                __syncthreads();
-                dead = s_grp.dead != 0;
-            }
-        }
-    }
-    if constexpr (!SCATTER) {
-        if (threadIdx.x == 0) { runcnt[2 * blockIdx.x] = nitems; runcnt[2 * blockIdx.x + 1] = nbad; }
     }
 }
 
@@ -1369,7 +1195,7 @@ template <int KEEP> __device__ __forceinline__ void cp_async_wait() { asm volati
 template <typename T, int N, int L> __device__ __forceinline__ void brick_clip(const EvalParams<N>& p, const int (&lo)[N], int (&clip)[N]) {
 #pragma unroll
     for (int d = 0; d < N; d++) {
-        const int full = d == 0 ? brick_extent(N, L, 0, (int)sizeof(T)) : p.tile[d] + L - 1, left = p.len[d] - lo[d];
+        const int full = p.tile[d] + L - 1, left = p.len[d] - lo[d];
         clip[d] = full < left ? full : left;
     }
 }
@@ -1462,15 +1288,15 @@ __device__ __forceinline__ void brick_eval_one(const EvalParams<N>& p, const T (
 }
 
 // the deferred queries: plain evaluation (eval_one) of the slots listed
-template <typename T, int N, int ORDER, int BCF, int OUTMODE, bool FAST, bool DIRECT>
+template <typename T, int N, int ORDER, int BCF, int OUTMODE, bool FAST>
 __global__ void __launch_bounds__(EVAL_BLOCK, 2) eval_deferred_kernel(const EvalParams<N> p, const T* __restrict__ rec, const u32* __restrict__ defer) {
-    if ((p.nwork[2] != 0) != DIRECT) return;
+    if (p.nwork[2] != 0) return;  // coherent batch: the plain kernel took it
     const u32 n = defer[0];
     for (u32 i = blockIdx.x * EVAL_BLOCK + threadIdx.x; i < n; i += gridDim.x * EVAL_BLOCK) {
         T x[N];
         u32 q;
         const u32 j = defer[1 + i];
-        fetch_query<T, N, DIRECT>(p, rec, j, x, q);
+        load_record<T, N>(rec, j, x, q);
         eval_one<T, N, ORDER, BCF, OUTMODE, FAST>(p, x, (i64)j, (i64)q);
     }
 }
@@ -1484,7 +1310,7 @@ __global__ void __launch_bounds__(EVAL_BLOCK, 2) eval_deferred_kernel(const Eval
 // over the item with shared-memory counters); class c is served by the 16 threads t = c (mod 16).
 // Classes are never equally full: each thread runs T = ceil(n/256) rounds, and a thread whose class
 // runs dry pulls from the overflow of fuller classes (those few loads may conflict).
-template <typename T, int N, int ORDER, int BCF, int OUTMODE, bool FAST, bool DIRECT>
+template <typename T, int N, int ORDER, int BCF, int OUTMODE, bool FAST>
 __global__ void __launch_bounds__(BRICK_BLOCK, 2)
     eval_brick_kernel(const EvalParams<N> p, const T* __restrict__ rec, u32* __restrict__ defer, const __grid_constant__ CUtensorMap tmap) {
     constexpr int L = ORDER + 1;
@@ -1492,7 +1318,7 @@ __global__ void __launch_bounds__(BRICK_BLOCK, 2)
     // FP64 operations); EXACT is bound by the FP64 pipe (816 dependent multiply/add per query) and
     // keeps the direct schedule, which has fewer barriers per item.
     constexpr bool BINNED = FAST;
-    if ((p.nwork[2] != 0) != DIRECT) return;  // the other variant of this kernel serves this batch (sorted_decide)
+    if (p.nwork[2] != 0) return;  // coherent batch (coherence_probe_kernel): the plain kernel takes it
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) u64 s_bar[2];
     __shared__ u32 s_it[2];
@@ -1581,7 +1407,7 @@ __global__ void __launch_bounds__(BRICK_BLOCK, 2)
                 u32 q;
 #pragma unroll
                 for (int u = 0; u < PASS1_UNROLL; u++)  // the loads of PASS1_UNROLL records in flight together
-                    if (r0 + u * BRICK_BLOCK < n) fetch_query<T, N, DIRECT>(p, rec, beg_c + r0 + u * BRICK_BLOCK, x[u], q);
+                    if (r0 + u * BRICK_BLOCK < n) load_record<T, N>(rec, beg_c + r0 + u * BRICK_BLOCK, x[u], q);
 #pragma unroll
                 for (int u = 0; u < PASS1_UNROLL; u++) {
                     const u32 r = r0 + u * BRICK_BLOCK;
@@ -1647,14 +1473,14 @@ __global__ void __launch_bounds__(BRICK_BLOCK, 2)
             };
             u32 rn = 0;
             bool more = next_record(0, rn);
-            if (more) fetch_query<T, N, DIRECT>(p, rec, beg_c + rn, xn, qn);
+            if (more) load_record<T, N>(rec, beg_c + rn, xn, qn);
             for (u32 i = 0; more; i++) {
                 T x[N];
 #pragma unroll
                 for (int d = 0; d < N; d++) x[d] = xn[d];
                 const u32 q = qn, r = rn;
                 more = next_record(i + 1, rn);
-                if (more) fetch_query<T, N, DIRECT>(p, rec, beg_c + rn, xn, qn);  // in flight during this round's evaluation
+                if (more) load_record<T, N>(rec, beg_c + rn, xn, qn);  // in flight during this round's evaluation
                 int cc[N][L];
                 T dx[N];
                 query_taps<T, N, ORDER, BCF>(p, x, cc, dx);
@@ -1668,9 +1494,9 @@ __global__ void __launch_bounds__(BRICK_BLOCK, 2)
             const T* brick = bricks + (size_t)par * volp;
             const bool next_has = nxt < nwork && beg_n + tid < end_n;
             u32 j = beg_c + tid;
-            if (k == 0 && j < end_c) fetch_query<T, N, DIRECT>(p, rec, j, xn, qn);
+            if (k == 0 && j < end_c) load_record<T, N>(rec, j, xn, qn);
             if (j >= end_c) {
-                if (next_has) fetch_query<T, N, DIRECT>(p, rec, beg_n + tid, xn, qn);
+                if (next_has) load_record<T, N>(rec, beg_n + tid, xn, qn);
             } else {
                 while (true) {
                     T x[N];
@@ -1679,8 +1505,8 @@ __global__ void __launch_bounds__(BRICK_BLOCK, 2)
                     const u32 q = qn, jc = j;
                     j += BRICK_BLOCK;
                     const bool more = j < end_c;
-                    if (more) fetch_query<T, N, DIRECT>(p, rec, j, xn, qn);
-                    else if (next_has) fetch_query<T, N, DIRECT>(p, rec, beg_n + tid, xn, qn);
+                    if (more) load_record<T, N>(rec, j, xn, qn);
+                    else if (next_has) load_record<T, N>(rec, beg_n + tid, xn, qn);
                     T dx[N];
                     const u32 boff = brick_locate<T, N, ORDER, BCF>(p, x, lo, clip, have, dx);
                     if (boff == BRICK_DEFER) defer_slot(defer, jc);  // global-memory path, later
@@ -1701,7 +1527,7 @@ __global__ void __launch_bounds__(BRICK_BLOCK, 2)
 template <typename T, int N, int OUTMODE>
 __global__ void __launch_bounds__(256) unpermute_kernel(const T* __restrict__ osorted, const u32* __restrict__ inv, T* __restrict__ val, T* __restrict__ grad,
                                                         T* __restrict__ hess, i64 nq, const u32* __restrict__ nwork) {
-    if (nwork[2] != 0) return;  // grouped batch: the outputs were written in place
+    if (nwork[2] != 0) return;  // coherent batch: the plain kernel wrote the outputs in place
     constexpr int W = out_words<N>(OUTMODE);
     for (i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (i64)gridDim.x * blockDim.x) {
         const T* src = osorted + (size_t)inv[q] * W;
@@ -1735,10 +1561,9 @@ __global__ void __launch_bounds__(256) unpermute_kernel(const T* __restrict__ os
 struct TileGeo { int N, tile[MAXD], ntile[MAXD]; };  // for the scan's work items (tile index -> brick corner)
 int tile_offsets(const u32* bh, u32 nbins, u32 nctas, u32* hist, u32* offs, u32* boff, u32* work, u32* nwork, u32 chunk, const TileGeo& geo, cudaStream_t s);
 int tile_offsets_global(const u32* hist, u32 nbins, u32* offs, u32* cursor, u32* work, u32* nwork, u32 chunk, const TileGeo& geo, cudaStream_t s);
-int sorted_decide(const u32* runcnt, u32 nctas, i64 nq, u32 bad_percent, u32 max_items, u32* base, u32* nwork, cudaStream_t s);
 bool choose_tile(int N, int L, size_t esz, const int* len, i64 nq, bool forced, int* tile, int* ntile);
 u32 sort_smem_bins();  // 12000: per-CTA histograms live in shared memory (<= 48 KB); more tiles: tile_sort_global_kernel
-u32 grouped_bad_percent(bool hinted);  // share of queries (percent) that may lack a brick for a batch to be evaluated in place; 0: never
+u32 coherent_need_percent(bool hinted);  // share (percent) of the probed leaves that must be coherent for the plain path to take the batch; > 100: never
 int make_brick_tensor_map(CUtensorMap* m, int dtype, int N, const void* base, const int* len, const i64* stride, const int* box);
 // Larger batches are evaluated in slices: bounds the record scratch, and keeps the randomly written regions -- the
 // slice's records and its outputs -- from outgrowing L2 by too much: the two permutations of a 4e7-query batch
@@ -1757,11 +1582,25 @@ inline i64 tiled_max_batch(i64 ntiles = -1) {
     return std::max<i64>((i64)1 << 24, std::min<i64>((i64)1 << 26, ntiles * 1024));
 }
 
+// plain launch geometry, shared by launch_one and the coherent branch of launch_tiled
+template <typename T, int N, int ORDER, int BCF, int OUTMODE, bool FAST> int plain_grid(i64 nq, int* grid) {
+    static int blocks_plain = 0;  // benign race: every thread computes the same value
+    if (blocks_plain == 0) {
+        int b = 0;
+        GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, eval_kernel<T, N, ORDER, BCF, OUTMODE, FAST>, EVAL_BLOCK, 0));
+        blocks_plain = b > 0 ? b : 1;
+    }
+    const i64 need = (nq + EVAL_BLOCK - 1) / EVAL_BLOCK;
+    // one resident wave for small batches (measured: 1e6 queries 43 vs 52 us), a few waves otherwise; CTAs stride over the blocks
+    const i64 cap = (i64)num_sms() * blocks_plain * (nq < (1ll << 22) ? 1 : 4);
+    *grid = (int)(need < cap ? (need > 0 ? need : 1) : cap);
+    return GB_OK;
+}
+
 template <typename T, int N, int ORDER, int BCF, int OUTMODE, bool FAST>
 int launch_tiled(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     constexpr int L = ORDER + 1;
-    auto kern = eval_brick_kernel<T, N, ORDER, BCF, OUTMODE, FAST, false>;
-    auto kern_direct = eval_brick_kernel<T, N, ORDER, BCF, OUTMODE, FAST, true>;
+    auto kern = eval_brick_kernel<T, N, ORDER, BCF, OUTMODE, FAST>;
     EvalParams<N> p = p_in;
     u32 nbins = 1;
     for (int d = 0; d < N; d++) nbins *= (u32)p.ntile[d];
@@ -1772,18 +1611,16 @@ int launch_tiled(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     for (int d = 0; d < N; d++) vol *= (size_t)box[d];
     const size_t smem = 2 * ((vol + 31) & ~(size_t)31) * sizeof(T);
     const u32 nctas = (u32)std::max<i64>(1, std::min<i64>((i64)num_sms() * 2, (p.nq + 4095) / 4096));
-    const i64 per_cta = ((p.nq + nctas - 1) / nctas + SORT_ITER - 1) / SORT_ITER * SORT_ITER;  // whole iterations per CTA
-    const u32 bad_percent = grouped_bad_percent((flags & GB_SORTED) != 0);
-    const size_t niter = (size_t)(per_cta / SORT_ITER) * nctas;
-    const size_t max_items = (size_t)nbins + (size_t)(p.nq / EVAL_CHUNK) + niter * GROUP_LEAVES + nctas + 2;
+    const i64 per_cta = ((p.nq + nctas - 1) / nctas + SORT_BLOCK - 1) / SORT_BLOCK * SORT_BLOCK;
+    const size_t max_items = (size_t)nbins + (size_t)(p.nq / EVAL_CHUNK) + 2;
     const size_t pitch = ((size_t)p.nq + 15) & ~(size_t)15;
-    // one scratch allocation: records | sorted outputs | inv | deferred-slot list (`keys`) | work | group corners | bh | boff | hist | offs | group flags | runcnt | runbase | nwork
+    // one scratch allocation: records | sorted outputs | inv | deferred-slot list (`keys`) | work | bh | boff | hist | offs | nwork
     constexpr int W = out_words<N>(OUTMODE);
     const bool global_bins = nbins > sort_smem_bins();
     const size_t nbc = global_bins ? 16 : (size_t)nbins * nctas;
     const size_t rec_bytes = (pitch * (N + 1) * sizeof(T) + 31) & ~(size_t)31;
     const size_t out_bytes = (pitch * W * sizeof(T) + 31) & ~(size_t)31;
-    const size_t words = (pitch + 16) + 4 * max_items + 2 * niter * GROUP_LEAVES + 2 * (niter + 4) + 2 * nbc + 2 * (size_t)(nbins + 4) + 3 * (size_t)(nctas + 4) + 8;
+    const size_t words = (pitch + 16) + 4 * max_items + 2 * nbc + 2 * (size_t)(nbins + 4) + 8;
     AsyncBuf guard(s);  // released on every exit path
     GB_CUDA(guard.alloc(rec_bytes + out_bytes + (pitch + words) * sizeof(u32)));
     unsigned char* scratch = (unsigned char*)guard.p;
@@ -1791,16 +1628,12 @@ int launch_tiled(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     T* osorted = reinterpret_cast<T*>(scratch + rec_bytes);
     u32* inv = reinterpret_cast<u32*>(scratch + rec_bytes + out_bytes);
     u32* keys = inv + pitch;
-    u32* work = keys + pitch + 16;  // (16-byte aligned: items are uint4, see make_item)
-    uint2* gcorner = reinterpret_cast<uint2*>(work + 4 * max_items);
-    uint2* gflags = gcorner + niter * GROUP_LEAVES;
-    u32* bh = reinterpret_cast<u32*>(gflags + (niter + 4));
+    u32* work = keys + pitch + 16;  // (16-byte aligned: items are uint4, see tile_item)
+    u32* bh = work + 4 * max_items;
     u32* boff = bh + nbc;
     u32* hist = boff + nbc;
     u32* offs = hist + (nbins + 4);
-    u32* runcnt = offs + (nbins + 4);
-    u32* runbase = runcnt + 2 * (nctas + 4);
-    u32* nwork = runbase + (nctas + 4);
+    u32* nwork = offs + (nbins + 4);  // [0] items, [1] ticket counter, [2] coherent flag, [3..5] the probe's counters
     TileGeo geo;
     geo.N = N;
     for (int d = 0; d < MAXD; d++) { geo.tile[d] = d < N ? p.tile[d] : 1; geo.ntile[d] = d < N ? p.ntile[d] : 1; }
@@ -1814,29 +1647,35 @@ int launch_tiled(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     p.work = work;
     p.nwork = nwork;
     GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per device, cheap
-    GB_CUDA(cudaFuncSetAttribute(kern_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int bt = 0;
     GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt, kern, BRICK_BLOCK, smem));
     if (bt < 1) return fail(GB_ERR_CUDA, "tiled evaluation: brick does not fit in shared memory");
+    // Is the batch coherent as it arrived?  Then the plain kernel at the end takes it and everything in between exits at once.
+    // (GB_TILED alone forces the bins: no probe.)
+    const u32 need = coherent_need_percent((flags & GB_SORTED) != 0);
+    const bool probe = (!(flags & GB_TILED) || (flags & GB_SORTED)) && need > 0 && need <= 100;  // (GB_TILED | GB_SORTED: forced onto this path, probe on)
     prof_mark(0, s);
+    GB_CUDA(cudaMemsetAsync(nwork, 0, 8 * sizeof(u32), s));
+    if (probe) {
+        u32 vmax = 4;
+        for (int d = 0; d < N; d++) vmax *= (u32)p.tile[d];
+        coherence_probe_kernel<T, N, ORDER, BCF><<<nctas, SORT_BLOCK, 0, s>>>(p, nwork, per_cta, vmax, need);
+        count_launch();
+    }
     int rc;
     if (global_bins) {  // hist doubles as the write cursors after the scan
         GB_CUDA(cudaMemsetAsync(hist, 0, (size_t)nbins * sizeof(u32), s));
-        tile_sort_global_kernel<T, N, ORDER, BCF, false><<<nctas, SORT_BLOCK, 0, s>>>(p, hist, rec, inv, per_cta, gflags, gcorner, runcnt);
+        tile_sort_global_kernel<T, N, ORDER, BCF, false><<<nctas, SORT_BLOCK, 0, s>>>(p, hist, rec, inv, per_cta);
         count_launch();
-        rc = sorted_decide(runcnt, nctas, p.nq, bad_percent, (u32)max_items, runbase, nwork, s);
-        if (rc) return rc;
         prof_mark(1, s);
         rc = tile_offsets_global(hist, nbins, offs, hist, work, nwork, EVAL_CHUNK, geo, s);
         if (rc) return rc;
         prof_mark(2, s);
-        tile_sort_global_kernel<T, N, ORDER, BCF, true><<<nctas, SORT_BLOCK, 0, s>>>(p, hist, rec, inv, per_cta, gflags, gcorner, runcnt);
+        tile_sort_global_kernel<T, N, ORDER, BCF, true><<<nctas, SORT_BLOCK, 0, s>>>(p, hist, rec, inv, per_cta);
         count_launch();
     } else {
-        tile_hist_kernel<T, N, ORDER, BCF><<<nctas, SORT_BLOCK, hsmem, s>>>(p, bh, nbins, per_cta, gflags, gcorner, runcnt);
+        tile_hist_kernel<T, N, ORDER, BCF><<<nctas, SORT_BLOCK, hsmem, s>>>(p, bh, nbins, per_cta);
         count_launch();
-        rc = sorted_decide(runcnt, nctas, p.nq, bad_percent, (u32)max_items, runbase, nwork, s);
-        if (rc) return rc;
         prof_mark(1, s);
         rc = tile_offsets(bh, nbins, nctas, hist, offs, boff, work, nwork, EVAL_CHUNK, geo, s);
         if (rc) return rc;
@@ -1844,32 +1683,35 @@ int launch_tiled(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
         tile_scatter_kernel<T, N, ORDER, BCF><<<nctas, SORT_BLOCK, hsmem, s>>>(p, boff, rec, inv, nbins, per_cta);
         count_launch();
     }
-    run_items_kernel<N><<<nctas, SORT_BLOCK, 0, s>>>(p, gflags, gcorner, runbase, work, nwork, per_cta);
-    count_launch();
     GB_CUDA(cudaGetLastError());
     const i64 grid = std::min<i64>((i64)max_items, (i64)num_sms() * bt);
     // the deferred-slot list (count first)
     u32* defer = keys;
     GB_CUDA(cudaMemsetAsync(defer, 0, sizeof(u32), s));
-    EvalParams<N> pd = p;  // grouped batch: slots are the caller's indices, outputs go straight to the caller's arrays
-    pd.aos = 0;
-    p.aos = W;  // sorted batch: both kernels write one output record per sorted slot ...
+    EvalParams<N> pp = p;  // the plain kernel's view: the caller's order and arrays
+    pp.aos = 0;
+    p.aos = W;  // both brick-path kernels write one output record per sorted slot ...
     p.val = osorted;
     p.grad = nullptr;
     p.hess = nullptr;
     prof_mark(3, s);
     kern<<<(int)grid, BRICK_BLOCK, smem, s>>>(p, rec, defer, tmap);
-    kern_direct<<<(int)grid, BRICK_BLOCK, smem, s>>>(pd, rec, defer, tmap);
     prof_mark(4, s);
-    eval_deferred_kernel<T, N, ORDER, BCF, OUTMODE, FAST, false><<<num_sms() * 2, EVAL_BLOCK, 0, s>>>(p, rec, defer);
-    eval_deferred_kernel<T, N, ORDER, BCF, OUTMODE, FAST, true><<<num_sms() * 2, EVAL_BLOCK, 0, s>>>(pd, rec, defer);
+    eval_deferred_kernel<T, N, ORDER, BCF, OUTMODE, FAST><<<num_sms() * 2, EVAL_BLOCK, 0, s>>>(p, rec, defer);
     prof_mark(5, s);
     // ... and the records go back to the caller's order and arrays
     const int ugrid = (int)std::min<i64>((p.nq + 255) / 256, (i64)num_sms() * 32);
     unpermute_kernel<T, N, OUTMODE><<<ugrid, 256, 0, s>>>(osorted, inv, (T*)p_in.val, (T*)p_in.grad, (T*)p_in.hess, p.nq, nwork);
+    count_launch(3);
+    if (probe) {  // coherent batch: evaluated in place by the plain kernel (exits at once otherwise)
+        int pgrid = 1;
+        rc = plain_grid<T, N, ORDER, BCF, OUTMODE, FAST>(p.nq, &pgrid);
+        if (rc) return rc;
+        eval_kernel<T, N, ORDER, BCF, OUTMODE, FAST><<<pgrid, EVAL_BLOCK, 0, s>>>(pp, nwork + 2);
+        count_launch();
+    }
     prof_mode(nwork, s);
     prof_mark(6, s);
-    count_launch(5);
     GB_CUDA(cudaGetLastError());
     return GB_OK;
 }
@@ -1896,18 +1738,11 @@ int launch_one(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     p.aos = 0;
     p.use_tma = 0;
     if (!tiled) {
-        static int blocks_plain = 0;  // benign race: every thread computes the same value
-        if (blocks_plain == 0) {
-            int b = 0;
-            GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, EVAL_BLOCK, 0));
-            blocks_plain = b > 0 ? b : 1;
-        }
         for (int d = 0; d < N; d++) { p.tile[d] = 1; p.ntile[d] = 1; }
-        const i64 need = (p.nq + EVAL_BLOCK - 1) / EVAL_BLOCK;
-        // one resident wave for small batches (measured: 1e6 queries 43 vs 52 us), a few waves otherwise; CTAs stride over the blocks
-        const i64 cap = (i64)num_sms() * blocks_plain * (p.nq < (1ll << 22) ? 1 : 4);
-        const int grid = (int)(need < cap ? (need > 0 ? need : 1) : cap);
-        kern<<<grid, EVAL_BLOCK, 0, s>>>(p);
+        int grid = 1;
+        const int rc = plain_grid<T, N, ORDER, BCF, OUTMODE, FAST>(p.nq, &grid);
+        if (rc) return rc;
+        kern<<<grid, EVAL_BLOCK, 0, s>>>(p, nullptr);
         count_launch();
         GB_CUDA(cudaGetLastError());
         return GB_OK;

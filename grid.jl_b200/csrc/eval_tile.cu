@@ -19,7 +19,7 @@ std::atomic<int> g_prof_on{0};
 std::mutex g_prof_mu;
 cudaEvent_t g_prof_ev[PROF_NB];
 bool g_prof_init = false, g_prof_have = false;
-u32* g_prof_mode = nullptr;  // pinned: nwork[2] of the last profiled tiled call (1 = grouped batch, evaluated in place)
+u32* g_prof_mode = nullptr;  // pinned: nwork[2] of the last profiled tiled call (1 = coherent batch, evaluated in place by the plain kernel)
 }  // namespace
 void prof_mode(const u32* nwork, cudaStream_t s) {
     if (!g_prof_on.load(std::memory_order_relaxed)) return;
@@ -54,7 +54,7 @@ int prof_read(double* ms, int n, int* nstages) {
         GB_CUDA(cudaEventElapsedTime(&t, g_prof_ev[k], g_prof_ev[k + 1]));
         ms[k] = (double)t;
     }
-    if (PROF_NB - 1 < n) ms[PROF_NB - 1] = g_prof_mode ? (double)*g_prof_mode : 0.0;  // [6]: 1 = the batch was grouped by tile and evaluated in place
+    if (PROF_NB - 1 < n) ms[PROF_NB - 1] = g_prof_mode ? (double)*g_prof_mode : 0.0;  // [6]: 1 = the batch arrived coherent and the plain kernel evaluated it in place
     if (nstages) *nstages = PROF_NB - 1;
     return GB_OK;
 }
@@ -79,7 +79,7 @@ __device__ __forceinline__ uint4 tile_item(const TileGeo& g, u32 bin, u32 ntot, 
 }
 __global__ void __launch_bounds__(1024) tile_scan_kernel(const u32* __restrict__ hist, u32 nbins, u32* __restrict__ offs, u32* __restrict__ work,
                                                          u32* __restrict__ nwork, u32 chunk, const TileGeo geo) {
-    if (nwork[2] != 0) return;  // grouped batch (sorted_decide): the runs are the work items
+    if (nwork[2] != 0) return;  // coherent batch (coherence_probe_kernel): the plain kernel takes it
     __shared__ u32 s_wc[32], s_wi[32], s_base[2];
     const u32 t = threadIdx.x, lane = t & 31, warp = t >> 5;
     if (t == 0) { s_base[0] = 0; s_base[1] = 0; }
@@ -193,66 +193,13 @@ int tile_offsets_global(const u32* hist, u32 nbins, u32* offs, u32* cursor, u32*
     return GB_OK;
 }
 
-// ---- grouped batches ---------------------------------------------------------------------------------------------
-// runcnt[2 cta] = work items the binning pass found for a grouped evaluation of the CTA's range (eval.cuh:
-// group_iteration), runcnt[2 cta + 1] = queries of that range left without a brick.  Few of the latter = the batch
-// arrived in an order whose chunks each fit a brick (sorted by tile or cell block, Morton / Hilbert order, a lattice walked
-// block by block): nwork[2] = 1, nwork[0] = number of items (built by run_items_kernel from base[cta] = items before CTA
-// cta), nwork[1] = 0 (ticket counter).  Otherwise nwork[2] = 0 and the counting sort proceeds.  One CTA.
-__global__ void __launch_bounds__(1024) sorted_decide_kernel(const u32* __restrict__ runcnt, u32 nctas, u32 max_bad, u32 max_items, u32* __restrict__ base,
-                                                            u32* __restrict__ nwork) {
-    __shared__ u32 s_w[32], s_b[32];
-    const u32 t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const u32 c = t < nctas ? runcnt[2 * t] : 0u;
-    u32 bad = t < nctas ? runcnt[2 * t + 1] : 0u;
-    u32 incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const u32 a = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((int)lane >= o) incl += a;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
-    if (lane == 31) s_w[warp] = incl;
-    if (lane == 0) s_b[warp] = bad;
-    __syncthreads();
-    if (warp == 0) {
-        u32 w = s_w[lane], bb = s_b[lane];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const u32 a = __shfl_up_sync(0xffffffffu, w, o);
-            if ((int)lane >= o) w += a;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) bb += __shfl_xor_sync(0xffffffffu, bb, o);
-        s_w[lane] = w;
-        if (lane == 0) s_b[0] = bb;
-    }
-    __syncthreads();
-    const u32 before = (warp ? s_w[warp - 1] : 0u) + incl - c;
-    if (t < nctas) base[t] = before;
-    if (t == 0) {
-        const u32 total = s_w[31];
-        const u32 grouped = (max_items != 0 && total <= max_items && s_b[0] <= max_bad) ? 1u : 0u;
-        nwork[2] = grouped;
-        if (grouped) { nwork[0] = total; nwork[1] = 0; }
-    }
-}
-int sorted_decide(const u32* runcnt, u32 nctas, i64 nq, u32 bad_percent, u32 max_items, u32* base, u32* nwork, cudaStream_t s) {
-    if (nctas > 1024) return fail(GB_ERR_CUDA, "sorted_decide: too many sort CTAs");
-    const u32 max_bad = (u32)std::min<i64>((i64)0x7fffffff, nq * (i64)bad_percent / 100);
-    sorted_decide_kernel<<<1, 1024, 0, s>>>(runcnt, nctas, max_bad, bad_percent ? max_items - 2 : 0u, base, nwork);
-    count_launch();
-    GB_CUDA(cudaGetLastError());
-    return GB_OK;
-}
-// GB_GROUPED_BAD_PERCENT: share of the queries that may sit in chunks too scattered for a brick (they take the
-// global-memory path) for the batch still to be evaluated in place; default 12 (30 when the caller passed GB_SORTED);
-// 0 disables the detection.
-u32 grouped_bad_percent(bool hinted) {
-    static const long env = [] { const char* e = getenv("GB_GROUPED_BAD_PERCENT"); return e ? atol(e) : -1L; }();
-    if (env >= 0) return (u32)std::min(100L, env);
-    return hinted ? 30u : 12u;
+// GB_COHERENT_PERCENT: share of the probed 32-query leaves that must be spatially coherent for a batch on the tiled path
+// to be handed to the plain kernel instead (eval.cuh: coherence_probe_kernel); default 88 (70 when the caller passed
+// GB_SORTED); values above 100 disable the probe.
+u32 coherent_need_percent(bool hinted) {
+    static const long env = [] { const char* e = getenv("GB_COHERENT_PERCENT"); return e ? atol(e) : -1L; }();
+    if (env >= 0) return (u32)env;
+    return hinted ? 70u : 88u;
 }
 
 // Tensor map of the coefficient array for the brick kernel's TMA loads: rank N, box = the brick.  Fails (-> cp.async

@@ -67,12 +67,11 @@ enum {
        faster than the default on such batches (profiles/README.md). */
     GB_TILED = 2, /* force the binned shared-memory path (compiled for 2-D / 3-D Quadratic and Cubic; ignored elsewhere) */
     GB_PLAIN = 4, /* force the plain path */
-    /* Hint: the batch is spatially grouped (sorted by tile or cell block, Morton / Hilbert order, a lattice walked block
-       by block, points binned once and evaluated many times).  The tiled path detects such batches by itself -- its
-       binning pass checks whether chunks of 128-1024 consecutive queries each fit one shared-memory brick -- and then
-       evaluates them IN PLACE: no permutation of the queries, no un-permutation of the results.  The hint only
-       raises the share of stray queries tolerated (30 % instead of 12 %; GB_GROUPED_BAD_PERCENT overrides both, 0
-       disables the detection).  Results are bit-identical in every case. */
+    /* Hint: the batch is spatially coherent (a lattice in raster order, points sorted by cell, tile or Morton code).  The
+       tiled path probes a sample of every batch by itself -- bounding boxes of the first taps of 32 consecutive queries --
+       and hands coherent batches to the plain kernel, which then beats the bins (its gathers hit L1 / L2); the hint
+       only lowers the share of coherent leaves required (70 % instead of 88 %; GB_COHERENT_PERCENT overrides both,
+       > 100 disables the probe; GB_TILED skips it).  Results are bit-identical in every case. */
     GB_SORTED = 8,
     /* gb_invert_opt / gb_grid_create_opt with GB_FAST: the prefilter runs as a line-parallel solver (one line per
        warp, parallel cyclic reduction of the interior recurrences) instead of the reference's sequential LU sweep;
@@ -88,11 +87,11 @@ int64_t gb_launch_count(void);
 /* Stage timing of the tiled evaluation (measurement aid for bench.py's roofline line; no reference
    counterpart).  gb_profile_enable(1) makes every tiled gb_eval* call record CUDA events on its
    launch stream around its stages; gb_profile_read waits for the last such call and returns the
-   stage durations in milliseconds: ms[0] tile_hist (+ the grouped-batch decision), [1] tile_offsets (3 small
-   kernels), [2] tile_scatter, [3] eval_brick, [4] eval_deferred, [5] unpermute (stages of the path not taken --
-   sorted vs grouped batches, see GB_SORTED -- cost an empty launch each).  n = capacity of ms;
+   stage durations in milliseconds: ms[0] tile_hist (+ the coherence probe), [1] tile_offsets (3 small
+   kernels), [2] tile_scatter, [3] eval_brick, [4] eval_deferred, [5] unpermute (+ the plain kernel, which does all the
+   work of a coherent batch while the other stages exit at once, see GB_SORTED).  n = capacity of ms;
    *nstages = 6, or 0 when no tiled call ran since profiling was enabled.  With n >= 7, ms[6] = 1.0 when the call
-   found the batch grouped by tile and evaluated it in place, else 0.0. */
+   found the batch coherent and evaluated it in place on the plain path, else 0.0. */
 int gb_profile_enable(int on);
 int gb_profile_read(double* ms, int n, int* nstages);
 

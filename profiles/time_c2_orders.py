@@ -1,5 +1,5 @@
 """C2 (256^3 f64 cubic valgrad, 1e7 queries) under different ORDERS of the same query set: stage times of the tiled path
-(gb_profile_*), whether the batch was found grouped (evaluated in place), and the plain path next to it."""
+(gb_profile_*), whether the probe found the batch coherent (plain kernel, in place), and the plain path next to it."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -37,5 +37,5 @@ for name, key in orders.items():
         t = timed(lambda: gb.valgrad_(v, g, G, Xs, fast=fast))
         tp = timed(lambda: gb.valgrad_(v, g, G, Xs, fast=fast, tiled=False))
         gb.profile_enable(True); gb.valgrad_(v, g, G, Xs, fast=fast); st = gb.profile_read(); gb.profile_enable(False)
-        print("%-30s %-5s tiled %.3f ms  plain %.3f ms  grouped %d  stages %s" % (name, "FAST" if fast else "EXACT", t, tp, st.get("grouped", -1),
-              " ".join("%s %.3f" % (k[:6], x) for k, x in st.items() if k != "grouped")), flush=True)
+        print("%-30s %-5s tiled %.3f ms  plain %.3f ms  coherent %d  stages %s" % (name, "FAST" if fast else "EXACT", t, tp, st.get("coherent", -1),
+              " ".join("%s %.3f" % (k[:6], x) for k, x in st.items() if k != "coherent")), flush=True)

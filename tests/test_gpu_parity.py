@@ -892,7 +892,7 @@ def test_stage_profiler(gb):
         assert gb.profile_read() == {}
         g._eval(X, 3, tiled=True)
         st = gb.profile_read()
-        assert tuple(st) == gb.PROFILE_STAGES + ("grouped",) and all(st[k] > 0 for k in gb.PROFILE_STAGES)
-        assert st["grouped"] == 0.0  # random queries: the counting-sort path
+        assert tuple(st) == gb.PROFILE_STAGES + ("coherent",) and all(st[k] > 0 for k in gb.PROFILE_STAGES)
+        assert st["coherent"] == 0.0  # GB_TILED alone: the bins, no coherence probe
     finally:
         gb.profile_enable(False)

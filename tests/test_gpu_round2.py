@@ -30,10 +30,11 @@ def tile_key(X, shape):
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("bc,order,shape", [("nan", "cubic", (70, 66, 50)), ("reflect", "quadratic", (300, 200)), ("nan", "quadratic", (64, 40, 33)),
-                                            ("periodic", "cubic" if False else "quadratic", (48, 40, 36))])
-def test_grouped_batches_evaluate_in_place(gb, oracle, dtype, bc, order, shape):
-    """Queries pre-sorted by tile: the tiled path detects it (profile: grouped == 1), skips both permutations, and the
-    results are bit-identical to the oracle; the same queries shuffled take the counting sort (grouped == 0)."""
+                                            ("periodic", "quadratic", (48, 40, 36))])
+def test_coherent_batches_take_the_plain_kernel(gb, oracle, dtype, bc, order, shape):
+    """The tiled path probes the batch as it arrived: spatially coherent orders (sorted by block, by cell in raster order) are
+    evaluated in place by the plain kernel (profile: coherent == 1), shuffled ones go through the bins (coherent == 0);
+    the oracle's bits either way."""
     import torch
 
     BC = dict(nan=gb.BCnan, reflect=gb.BCreflect, periodic=gb.BCperiodic)[bc]
@@ -44,38 +45,31 @@ def test_grouped_batches_evaluate_in_place(gb, oracle, dtype, bc, order, shape):
     co = oracle.make_coefs(A, bc, order)
     nq = 400_000
     X = (1.0 + rng.random((nq, len(shape))) * (np.array(shape) - 1.0)).astype(dtype)
-    X[::1000] = -3.0  # a few invalid / wrapped locations inside the runs
-    Xs = np.ascontiguousarray(X[np.argsort(tile_key(X, shape), kind="stable")])
+    X[::1000] = -3.0  # a few invalid / wrapped locations
     mask = 7
-    ov, og, oh, _ = oracle.evaluate(co, bc, order, Xs, mask, raise_invalid=False)
+    orders = {"blocks": np.argsort(tile_key(X, shape), kind="stable"),
+              "raster": np.lexsort(tuple(np.floor(X[:, d]) for d in range(len(shape)))),
+              "random": np.arange(nq)}
     gb.profile_enable(True)
     try:
-        for fast in (False, True):
-            v, gr, h = g._eval(torch.from_numpy(Xs).cuda(), mask, tiled=True, fast=fast)
-            st = gb.profile_read()
-            assert st["grouped"] == 1.0, st
-            if not fast:
-                assert same(v.cpu().numpy(), ov) and same(gr.cpu().numpy(), og) and same(h.cpu().numpy(), oh)
-            else:
-                vp, gp, hp = g._eval(torch.from_numpy(Xs).cuda(), mask, tiled=False, fast=True)
-                assert torch.equal(v, vp) or bool(((v == vp) | (v.isnan() & vp.isnan())).all())
-        v, gr, h = g._eval(torch.from_numpy(X).cuda(), mask, tiled=True)
-        assert gb.profile_read()["grouped"] == 0.0
-        ou, ogu, ohu, _ = oracle.evaluate(co, bc, order, X, mask, raise_invalid=False)
-        assert same(v.cpu().numpy(), ou) and same(gr.cpu().numpy(), ogu) and same(h.cpu().numpy(), ohu)
-        # short runs (sorted by cell in raster order): with the GB_SORTED hint still in place, without it sorted
-        Xc = np.ascontiguousarray(X[np.lexsort(tuple(np.floor(X[:, d]) for d in range(len(shape))))])
-        oc, _, _, _ = oracle.evaluate(co, bc, order, Xc, 1, raise_invalid=False)
-        for hint in (False, True):
-            vc, _, _ = g._eval(torch.from_numpy(Xc).cuda(), 1, tiled=True, sorted=hint)
-            assert same(vc.cpu().numpy(), oc)
+        for name, perm in orders.items():
+            Xs = np.ascontiguousarray(X[perm])
+            ov, og, oh, _ = oracle.evaluate(co, bc, order, Xs, mask, raise_invalid=False)
+            for fast in (False, True):
+                v, gr, h = g._eval(torch.from_numpy(Xs).cuda(), mask, tiled=True, sorted=True, fast=fast)  # forced onto the tiled path, probe on
+                st = gb.profile_read()
+                assert st["coherent"] == (0.0 if name == "random" else 1.0), (name, st)
+                if not fast:
+                    assert same(v.cpu().numpy(), ov) and same(gr.cpu().numpy(), og) and same(h.cpu().numpy(), oh), name
+        v, gr, h = g._eval(torch.from_numpy(np.ascontiguousarray(X[orders["blocks"]])).cuda(), mask, tiled=True)  # GB_TILED alone: the bins, no probe
+        assert gb.profile_read()["coherent"] == 0.0
     finally:
         gb.profile_enable(False)
 
 
-def test_grouped_detection_corner_cases(gb, oracle):
-    """one run only; runs longer than a work item; a batch that is not a multiple of anything; BCnil's first invalid
-    index in a grouped batch"""
+def test_coherence_probe_corner_cases(gb, oracle):
+    """tiny batches, batches that are not a multiple of anything, every query invalid, BCnil's first invalid index on the
+    coherent route"""
     import torch
 
     rng = np.random.default_rng(9)
@@ -85,18 +79,21 @@ def test_grouped_detection_corner_cases(gb, oracle):
     gb.profile_enable(True)
     try:
         for nq in (1, 31, 2049, 70_001):
-            X = 5.0 + rng.random((nq, 3)) * 3.0  # all in one tile
-            v, gr, _ = g._eval(torch.from_numpy(X).cuda(), 3, tiled=True)
-            assert gb.profile_read()["grouped"] == 1.0
+            X = 5.0 + rng.random((nq, 3)) * 3.0  # all in one cell block
+            v, gr, _ = g._eval(torch.from_numpy(X).cuda(), 3, tiled=True, sorted=True)
+            assert gb.profile_read()["coherent"] == 1.0
             ov, og, _, _ = oracle.evaluate(co, "nan", "cubic", X, 3)
             assert same(v.cpu().numpy(), ov) and same(gr.cpu().numpy(), og)
+        X = np.full((5000, 3), -7.0)
+        v, gr, _ = g._eval(torch.from_numpy(X).cuda(), 3, tiled=True, sorted=True)
+        assert bool(torch.isnan(v).all()) and bool(torch.isnan(gr).all())
     finally:
         gb.profile_enable(False)
     gn = gb.InterpGrid(A, gb.BCnil, gb.InterpCubic)
     X = 5.0 + rng.random((5000, 3)) * 3.0
     X[3210, 1] = 77.0
     with pytest.raises(gb.ErrorException) as ei:
-        gn._eval(torch.from_numpy(X).cuda(), 3, tiled=True)
+        gn._eval(torch.from_numpy(X).cuda(), 3, tiled=True, sorted=True)
     assert "query 3210" in str(ei.value)
 
 
