@@ -620,7 +620,7 @@ template <int N> void fill_params(const EvalCall& c, EvalParams<N>& p) {
         p.total = g->total * g->nchan;
         p.cstride = 1;
     }
-    p.work = nullptr; p.nwork = nullptr;
+    p.work = nullptr; p.nwork = nullptr; p.use_tma = 0; p.by_query = 0;
     for (int d = 0; d < N; d++) { p.tile[d] = 1; p.ntile[d] = 1; }
 }
 template <int N> int launch_n(const EvalCall& c, cudaStream_t s) {

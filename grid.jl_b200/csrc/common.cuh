@@ -137,6 +137,7 @@ template <int N> struct EvalParams {
     const u32* nwork;     // device: [0] number of work items, [1] the ticket counter CTAs pull items from, [2] 1 = the batch arrived
                           // spatially coherent: the binning kernels exit and the plain kernel evaluates it in place
     int use_tma;          // bricks are staged by cp.async.bulk.tensor through the kernel's tensor map (else element-wise cp.async)
+    int by_query;         // brick path: the output record of a query goes to record q (its index in the batch) instead of its sorted slot
 };
 
 // One entry per (dtype, N, order) -- eval_inst.cu; each dispatches on (bc family, output mode, flags).

@@ -860,6 +860,9 @@ __global__ void __launch_bounds__(EVAL_BLOCK, 2) eval_kernel(const EvalParams<N>
 //                  no boundary condition needs special bricks and results are bit-identical to plain.
 //   unpermute      sorted slots -> the caller's order and arrays
 constexpr int BRICK_BLOCK = 256;
+#ifndef GB_OUT_BY_QUERY_DEFAULT
+#define GB_OUT_BY_QUERY_DEFAULT 1
+#endif
 constexpr u32 EVAL_CHUNK = 2048;  // queries per work item
 constexpr int SORT_BLOCK = 256;
 constexpr int SORT_UNROLL = 4;    // queries in flight per thread in the two sort passes
@@ -1087,7 +1090,7 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_scatter_kernel(const EvalPara
                 for (int d = 0; d < N; d++) x[d] = index_coord<T, N>(p, d, raw[u][d]);
                 const u32 slot = atomicAdd(s_cur + tile_key<T, N, ORDER, BCF>(p, x, shift, ntot), 1u);
                 store_record<T, N>(rec, slot, x, (u32)q);
-                inv[q] = slot;
+                if (inv) inv[q] = slot;
             }
         }
     }
@@ -1139,7 +1142,7 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_sort_global_kernel(const Eval
                 if (act) {
                     const u32 slot = base + __popc(peers & ((1u << lane) - 1));
                     store_record<T, N>(rec, slot, x, (u32)q);
-                    inv[q] = slot;
+                    if (inv) inv[q] = slot;
                 }
             }
         }
@@ -1284,7 +1287,7 @@ __device__ __forceinline__ void brick_eval_one(const EvalParams<N>& p, const T (
         defer_slot(defer, j);
         return;
     }
-    store_outputs<T, N, OUTMODE>(p, (i64)j, q, true, acc);
+    store_outputs<T, N, OUTMODE>(p, p.by_query ? q : (i64)j, q, true, acc);
 }
 
 // the deferred queries: plain evaluation (eval_one) of the slots listed
@@ -1297,7 +1300,7 @@ __global__ void __launch_bounds__(EVAL_BLOCK, 2) eval_deferred_kernel(const Eval
         u32 q;
         const u32 j = defer[1 + i];
         load_record<T, N>(rec, j, x, q);
-        eval_one<T, N, ORDER, BCF, OUTMODE, FAST>(p, x, (i64)j, (i64)q);
+        eval_one<T, N, ORDER, BCF, OUTMODE, FAST>(p, x, p.by_query ? (i64)q : (i64)j, (i64)q);
     }
 }
 
@@ -1530,7 +1533,7 @@ __global__ void __launch_bounds__(256) unpermute_kernel(const T* __restrict__ os
     if (nwork[2] != 0) return;  // coherent batch: the plain kernel wrote the outputs in place
     constexpr int W = out_words<N>(OUTMODE);
     for (i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (i64)gridDim.x * blockDim.x) {
-        const T* src = osorted + (size_t)inv[q] * W;
+        const T* src = osorted + (size_t)(inv ? inv[q] : (u32)q) * W;  // (inv == NULL: the records are in query order already)
         alignas(16) T o[W];
         if constexpr (W * sizeof(T) == 32) {
             reinterpret_cast<float4*>(o)[0] = __ldcs(reinterpret_cast<const float4*>(src));
@@ -1646,6 +1649,12 @@ int launch_tiled(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     if (!tma_off && make_brick_tensor_map(&tmap, dtype_of<T>::value, N, p.coefs, p.len, p.stride, box) == GB_OK) p.use_tma = 1;
     p.work = work;
     p.nwork = nwork;
+    // Where do the brick kernel's output records go?  To the query's sorted slot (coalesced writes, then un-permuted by a random
+    // 32-byte gather) or straight to record q (random full-sector writes hidden under the FP64-bound evaluation, then a
+    // streaming unpack).  GB_OUT_BY_QUERY selects (measured, profiles/README.md).
+    static const int by_query = [] { const char* e = getenv("GB_OUT_BY_QUERY"); return e ? atoi(e) : GB_OUT_BY_QUERY_DEFAULT; }();
+    p.by_query = by_query;
+    if (by_query) inv = nullptr;
     GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per device, cheap
     int bt = 0;
     GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt, kern, BRICK_BLOCK, smem));
@@ -1737,6 +1746,7 @@ int launch_one(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     if (tiled) tiled = choose_tile(N, L, sizeof(T), p.len, std::min<i64>(p.nq, tiled_max_batch()), forced, p.tile, p.ntile);
     p.aos = 0;
     p.use_tma = 0;
+    p.by_query = 0;
     if (!tiled) {
         for (int d = 0; d < N; d++) { p.tile[d] = 1; p.ntile[d] = 1; }
         int grid = 1;
