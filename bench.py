@@ -373,6 +373,8 @@ def c3_sharded(gb, torch, dist, np, O, peak, rank, world, dev):
         gb.synth_uniform(A, 3)
         G = gb.InterpGrid(A, gb.BCreflect, gb.InterpQuadratic)
         del A
+    D.default_comm()  # (NCCL communicator of the library, created once per process: ~0.5 s, not part of the broadcast)
+    dist.barrier()
     t0 = time.perf_counter()
     G = D.broadcast_grid(G, gb.BCreflect, gb.InterpQuadratic, src=0)
     torch.cuda.synchronize()

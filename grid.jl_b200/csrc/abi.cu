@@ -92,6 +92,18 @@ static void mark_ready(gb_grid* g, cudaStream_t s) {
     if (cudaEventRecord(g->ready, s) != cudaSuccess) cudaStreamSynchronize(s);
 }
 
+// every entry point that touches a grid's memory runs on the grid's device, whatever the calling thread's current one is
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+
 static int check_grid_args(int dtype, int ndim, const int64_t* dims, int bc, int order) {
     if (!ok_dtype(dtype)) return fail(GB_ERR_ARG, "dtype must be GB_F32 or GB_F64");
     if (ndim < 1) return fail(GB_ERR_ARG, "ndim must be >= 1");
@@ -531,6 +543,7 @@ int gb_grid_coefs_device(const gb_grid* g, void** device_ptr) {
 // G.coefs in the reference layout written to a caller-provided DEVICE buffer (any resident layout)
 int gb_grid_coefs_copy(const gb_grid* g, void* device_out, void* stream) {
     if (!g || !device_out) return fail(GB_ERR_ARG, "NULL argument");
+    DeviceGuard guard(g->device);
     cudaStream_t s = (cudaStream_t)stream;
     const size_t bytes = (size_t)g->total * (size_t)g->nchan * esize(g->dtype);
     int rcw = wait_ready(g, s);
@@ -542,6 +555,7 @@ int gb_grid_coefs_copy(const gb_grid* g, void* device_out, void* stream) {
 }
 int gb_grid_coefs_download(const gb_grid* g, void* host_out) {
     if (!g || !host_out) return fail(GB_ERR_ARG, "NULL argument");
+    DeviceGuard guard(g->device);
     const size_t bytes = (size_t)g->total * (size_t)g->nchan * esize(g->dtype);
     if (g->nchan > 1 || g->blocked) {  // resident layout is channel-interleaved / blocked; the caller gets the reference's array
         void* tmp = nullptr;
@@ -561,6 +575,7 @@ int gb_grid_coefs_download(const gb_grid* g, void* host_out) {
 }
 int gb_grid_destroy(gb_grid* g) {
     if (!g) return GB_OK;
+    DeviceGuard guard(g->device);
     coefs_free(g->coefs);
     if (g->ready) cudaEventDestroy(g->ready);
     delete g;
@@ -741,14 +756,19 @@ int check_affine(const gb_grid* g, const double* affine) {
     return GB_OK;
 }
 
-struct DeviceGuard {
-    int prev = -1;
-    bool switched = false;
-    explicit DeviceGuard(int dev) {
-        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+// page-locks host ranges that are not pinned yet; released (and only those) when the call returns
+struct HostPins {
+    std::vector<void*> mine;
+    void add(const void* p, size_t bytes) {
+        if (!p || bytes == 0) return;
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type != cudaMemoryTypeUnregistered) return;  // pinned / managed already
+        cudaGetLastError();
+        if (cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault) == cudaSuccess) mine.push_back(const_cast<void*>(p));
+        else cudaGetLastError();  // (overlapping ranges, read-only mappings, ...: fall back to pageable copies)
     }
-    ~DeviceGuard() {
-        if (switched) cudaSetDevice(prev);
+    ~HostPins() {
+        for (void* p : mine) cudaHostUnregister(p);
     }
 };
 
@@ -764,6 +784,24 @@ int eval_host(const gb_grid* g, int out_mask, int outmode, i64 nq, const void* c
         return (i64)(v > 0 ? v : (1ll << 20));
     }();
     const i64 chunk = std::max<i64>(1, std::min<i64>(chunk_env, nq));
+    // Pageable host buffers (a Julia Array, a numpy array): every cudaMemcpyAsync then goes through the driver's staging
+    // buffer and blocks the host, so the chunks stop overlapping (measured on C2: 44 ms against 7.7 ms with pinned buffers).
+    // Page-locking the caller's ranges for the duration of ONE call does not pay (cudaHostRegister pins ~9 MB per ms on the
+    // GPU box: 65 ms for the C2 batch, profiles/README.md) -- callers that reuse their buffers should pin them once
+    // (gb_host_register; GridB200.pin!).  GB_HOST_REGISTER=1 makes the call do it anyway (buffers that are not pinned yet).
+    HostPins pins;
+    {
+        static const int reg_env = [] { const char* e = getenv("GB_HOST_REGISTER"); return e ? atoi(e) : 0; }();
+        const size_t xbytes = (size_t)nq * N * xs, vbytes = (size_t)nq * es;
+        const bool want = reg_env == 1;
+        if (want) {
+            if (xaos) pins.add(xaos, xbytes);
+            else for (int d = 0; d < N; d++) pins.add(xcols[d], (size_t)nq * xs);
+            if (out_mask & GB_OUT_VAL) pins.add(val, vbytes);
+            if (out_mask & GB_OUT_GRAD) pins.add(grad, vbytes * N);
+            if (out_mask & GB_OUT_HESS) pins.add(hess, vbytes * N * N);
+        }
+    }
     constexpr int NSLOT = 3;
     const int nslot = (int)std::min<i64>(NSLOT, (nq + chunk - 1) / chunk);
     struct Slot {

@@ -10,7 +10,7 @@
 //                            lane r read row r as eight conflict-free 16-byte shared loads; results leave the same way
 //                            (swizzled tile -> cp.async.bulk.tensor store).  Four load stages and two store stages per
 //                            warp, mbarrier completion, no CTA-wide barrier anywhere.
-//   both                     fast_ends_kernel: the K rows at each end of every line from the dense end blocks.
+//   both                     fast_ends_*_kernel: the K rows at each end of every line from the dense end blocks.
 // A sweep the solver does not take -- lines shorter than 8K, so many lines that the exact kernel already fills the
 // machine, a row pitch TMA cannot address -- runs the exact in-place kernel (prefilter.cu) on the current buffer.
 #include <cuda.h>
@@ -61,18 +61,49 @@ __global__ void __launch_bounds__(128) fast_strided_kernel(const T* __restrict__
 }
 
 // ---- the K rows at both ends of every line ----------------------------------------------------------------------------
+// out[i] = sum_j W[i][j] f[j], double accumulation (FAST_K rows from FAST_COLS inputs per end).
+// Strided lines (the 32 lines of a warp adjacent in memory): a thread takes 8 rows of one end of one line -- every f[j] is a
+// coalesced row across the warp, W is warp-uniform.
 template <typename T>
-__global__ void __launch_bounds__(128) fast_ends_kernel(const T* __restrict__ src, T* __restrict__ dst, i64 n, i64 s, i64 inner, i64 nlines, const double* __restrict__ wtop,
-                                                        const double* __restrict__ wbot) {
+__global__ void __launch_bounds__(128) fast_ends_strided_kernel(const T* __restrict__ src, T* __restrict__ dst, i64 n, i64 s, i64 inner, i64 nlines,
+                                                                const double* __restrict__ wtop, const double* __restrict__ wbot) {
     const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= 2 * nlines) return;
+    if (idx >= 2 * (FAST_K / 8) * nlines) return;
     const i64 line = idx % nlines;
-    const int end = (int)(idx / nlines);
+    const int part = (int)(idx / nlines), end = part / (FAST_K / 8), i0 = (part % (FAST_K / 8)) * 8;
     const i64 base = (line % inner) + (line / inner) * inner * n;
-    const i64 in0 = end ? n - FAST_COLS : 0, out0 = end ? n - FAST_K : 0;
-    const T* f = src + base + in0 * s;
-    T* o = dst + base + out0 * s;
-    fast_end_rows<T>(end ? wbot : wtop, [&](int j) { return __ldg(f + (i64)j * s); }, [&](int i, T v) { o[(i64)i * s] = v; });
+    const T* f = src + base + (end ? n - FAST_COLS : 0) * s;
+    T* o = dst + base + ((end ? n - FAST_K : 0) + i0) * s;
+    const double* W = (end ? wbot : wtop) + (size_t)i0 * FAST_COLS;
+    double acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = 0.0;
+#pragma unroll 4
+    for (int j = 0; j < FAST_COLS; j++) {
+        const double fj = (double)__ldg(f + (i64)j * s);
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] = fma(__ldg(W + k * FAST_COLS + j), fj, acc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) o[(i64)k * s] = (T)acc[k];
+}
+// Contiguous lines: a warp takes one end of one line, lane = output row (FAST_K == 32): the inputs are one contiguous,
+// warp-uniform run of the line, the block is read transposed (wt[j][i]) so that the lanes' loads coalesce.
+static_assert(FAST_K == 32, "fast_ends_contig_kernel maps one output row to each lane of a warp");
+template <typename T>
+__global__ void __launch_bounds__(128) fast_ends_contig_kernel(const T* __restrict__ src, T* __restrict__ dst, i64 n, i64 nlines, const double* __restrict__ wtop_t,
+                                                               const double* __restrict__ wbot_t) {
+    const i64 w = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= 2 * nlines) return;
+    const i64 line = w >> 1;
+    const int end = (int)(w & 1);
+    const T* f = src + line * n + (end ? n - FAST_COLS : 0);
+    const double* Wt = end ? wbot_t : wtop_t;
+    double acc = 0.0;
+#pragma unroll 8
+    for (int j = 0; j < FAST_COLS; j++) acc = fma(__ldg(Wt + j * FAST_K + lane), (double)__ldg(f + j), acc);
+    dst[line * n + (end ? n - FAST_K : 0) + lane] = (T)acc;
 }
 
 // ---- contiguous lines: TMA-transposed tiles ---------------------------------------------------------------------------
@@ -225,9 +256,16 @@ template <typename T> int get_fast_sys(int bc, int order, i64 n, FastSys<T>& out
     s.l = h.l; s.rd = h.rd; s.periodic = h.periodic;
     double* d = nullptr;
     const size_t words = (size_t)FAST_K * FAST_COLS;
-    GB_CUDA(cudaMalloc((void**)&d, 2 * words * sizeof(double)));
-    cudaError_t e = cudaMemcpy(d, h.wtop.data(), words * sizeof(double), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(d + words, h.wbot.data(), words * sizeof(double), cudaMemcpyHostToDevice);
+    std::vector<double> all(4 * words);  // wtop | wbot | wtop transposed [j][i] | wbot transposed
+    for (size_t i = 0; i < (size_t)FAST_K; i++)
+        for (size_t j = 0; j < (size_t)FAST_COLS; j++) {
+            all[i * FAST_COLS + j] = h.wtop[i * FAST_COLS + j];
+            all[words + i * FAST_COLS + j] = h.wbot[i * FAST_COLS + j];
+            all[2 * words + j * FAST_K + i] = h.wtop[i * FAST_COLS + j];
+            all[3 * words + j * FAST_K + i] = h.wbot[i * FAST_COLS + j];
+        }
+    GB_CUDA(cudaMalloc((void**)&d, 4 * words * sizeof(double)));
+    cudaError_t e = cudaMemcpy(d, all.data(), 4 * words * sizeof(double), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(d); return cuda_fail(e, "cudaMemcpy (fast prefilter end blocks)"); }
     s.wtop = d;
     s.wbot = d + words;
@@ -326,8 +364,14 @@ template <typename T> int sweep_fast(const T* src, T* dst, int dtype, const Swee
     count_launch();
     GB_CUDA(cudaGetLastError());
     if (!fs.periodic) {
-        const i64 threads = 2 * g.nlines;
-        fast_ends_kernel<T><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(src, dst, g.n, g.str, g.str, g.nlines, fs.wtop, fs.wbot);
+        const size_t words = (size_t)FAST_K * FAST_COLS;
+        if (g.str == 1 && g.nlines > 1) {
+            const i64 threads = 2 * g.nlines * 32;
+            fast_ends_contig_kernel<T><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(src, dst, g.n, g.nlines, fs.wtop + 2 * words, fs.wtop + 3 * words);
+        } else {
+            const i64 threads = 2 * (FAST_K / 8) * g.nlines;
+            fast_ends_strided_kernel<T><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(src, dst, g.n, g.str, g.str, g.nlines, fs.wtop, fs.wbot);
+        }
         count_launch();
         GB_CUDA(cudaGetLastError());
     }

@@ -162,7 +162,8 @@ template <typename T, int E, int KB, typename IO> GB_FAST_FN void fast_segment(I
     }
 }
 
-// The K rows at one end of one line: out[i] = sum_j W[i][j] f[j] (double accumulation), 8 rows at a time.
+// The K rows at one end of one line: out[i] = sum_j W[i][j] f[j] (double accumulation), 8 rows at a time.  (The kernels spread
+// the same dot products over more threads -- fast_ends_*_kernel; this form serves the host-side arithmetic check.)
 // get(j) returns f[j] of the end's COLS-wide window, put(i, v) stores row i of the end.
 template <typename T, typename GET, typename PUT> GB_FAST_FN void fast_end_rows(const double* __restrict__ W, GET get, PUT put) {
     for (int i0 = 0; i0 < FAST_K; i0 += 8) {
