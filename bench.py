@@ -303,7 +303,7 @@ def extra_configs(gb, torch, np, O, peak, traffic, reps=5):
             continue  # library without the FAST prefilter
         rows.append(_row("C3 prefilter: interp_invert! of the 8192^2 f32 image, both sweeps, %s" % ("FAST (in-line parallel solver)" if fast else "EXACT (LU order)"),
                          n * n, "points", 16, max(best - b0, 1e-6), max(med - m0, 1e-6), peak, None,
-                         traffic.get("c3_prefilter_%s_bytes" % ("fast" if fast else "exact")), note="time of the device copy that precedes the in-place solve subtracted"))
+                         traffic.get("c3_prefilter_exact_bytes") if not fast else None, note="time of the device copy that precedes the in-place solve subtracted"))
     del A
 
     # ---- C4 ----------------------------------------------------------------------------------------------------
@@ -356,9 +356,9 @@ def extra_configs(gb, torch, np, O, peak, traffic, reps=5):
     par = par and bool(np.array_equal(O.prolong_sizes(gb.jl_to_numpy(levels[k + 1]), [129] * 3), gb.jl_to_numpy(gb.prolong(levels[k + 1], [129] * 3))))
     bpu = 8.0 * sum(a ** 3 + b ** 3 for a, b in zip(sizes[:-1], sizes[1:])) / n ** 3
     chain = "->".join(map(str, sizes))
-    rows.append(_row("C5 restrict chain %s f64 (fused 3-D marching kernel)" % chain, n ** 3, "points", bpu, best_d, med_d, peak, par, traffic.get("c5_restrict_chain_bytes"),
-                     note="unit = level-0 point; parity on the 129^3 level (full-size levels: tests/test_gpu_fullsize.py)"))
-    rows.append(_row("C5 prolong chain back up (fused 3-D marching kernel)", n ** 3, "points", bpu, best_u, med_u, peak, par, traffic.get("c5_prolong_chain_bytes")))
+    rows.append(_row("C5 restrict chain %s f64 (fused 3-D marching kernel)" % chain, n ** 3, "points", bpu, best_d, med_d, peak, par, traffic.get("c5_restrict_level0_bytes"),
+                     note="unit = level-0 point; traffic = the 1024^3 -> 513^3 launch alone (9.66 GB algorithmic); parity on the 129^3 level (full-size levels: tests/test_gpu_fullsize.py)"))
+    rows.append(_row("C5 prolong chain back up (fused 3-D marching kernel)", n ** 3, "points", bpu, best_u, med_u, peak, par, traffic.get("c5_prolong_level0_bytes"), note="traffic = the 513^3 -> 1024^3 launch alone"))
     return rows
 
 

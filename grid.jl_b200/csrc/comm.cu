@@ -14,10 +14,11 @@
 //
 // Sharded restrict / prolong (the reference's restrict(A, [true,true,true]) / prolong(A, sizes),
 // src/restrict_prolong.jl:181-185, 87-100): the array is split into slabs along dim 3.  Per call and local rank:
-//   1. the INTERIOR output planes -- those whose stencil stays inside the rank's own planes -- are launched
+//   1. the comm stream (highest stream priority) exchanges the <= 2-3 halo planes per side with the neighbours --
+//      grouped ncclSend / ncclRecv directly out of the slabs' plane ranges into a small halo buffer; enqueued FIRST
+//      so that its kernels hold their SM slots before the interior kernel fills the machine;
+//   2. meanwhile the INTERIOR output planes -- those whose stencil stays inside the rank's own planes -- are computed
 //      on the work stream straight from the caller's slab (no staging copy);
-//   2. meanwhile the comm stream exchanges the <= 2-3 halo planes per side with the neighbours (grouped
-//      ncclSend / ncclRecv directly out of / into the slabs' plane ranges);
 //   3. the few BOUNDARY output planes run after the halo has landed, from a small assembled buffer
 //      (halo planes + the adjoining own planes).
 // The element code is that of gb_restrict3_slab / gb_prolong3_slab, so the assembled result is bit-identical
@@ -182,7 +183,12 @@ struct DevGuard {
 
 int init_local(LocalRank& l) {
     DevGuard g(l.dev);
-    GB_CUDA(cudaStreamCreateWithFlags(&l.cs, cudaStreamNonBlocking));
+    // the communication stream outranks the work streams: the halo kernels' few CTAs are scheduled as soon as SM slots free up,
+    // instead of queueing behind every remaining block of the interior kernel (measured: the halo of level 0 landed 0.2 ms
+    // AFTER the interior kernel at 8 GPUs before this, profiles/README.md)
+    int lo_pri = 0, hi_pri = 0;
+    GB_CUDA(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+    GB_CUDA(cudaStreamCreateWithPriority(&l.cs, cudaStreamNonBlocking, hi_pri));
     GB_CUDA(cudaStreamCreateWithFlags(&l.ws, cudaStreamNonBlocking));
     GB_CUDA(cudaEventCreateWithFlags(&l.ev_in, cudaEventDisableTiming));
     GB_CUDA(cudaEventCreateWithFlags(&l.ev_halo, cudaEventDisableTiming));
@@ -225,7 +231,7 @@ int sharded_level(gb_comm* c, int kind, int dtype, const i64* gin, const i64* go
     const size_t in_plane = (size_t)gin[0] * (size_t)gin[1] * es, out_plane = (size_t)gout[0] * (size_t)gout[1] * es;
     NcclApi* api = c->api;
     std::vector<cudaStream_t> ws(nl);
-    // ---- 1. inputs ready; interior planes ---------------------------------------------------------------------
+    // ---- 1. inputs ready; which output planes are interior ------------------------------------------------------
     struct Piece { i64 k0, k1; bool interior; };
     std::vector<std::vector<Piece>> pieces(nl);
     for (int i = 0; i < nl; i++) {
@@ -265,15 +271,6 @@ int sharded_level(gb_comm* c, int kind, int dtype, const i64* gin, const i64* go
         } else if (k0 < k1) {
             pieces[i].push_back({k0, k1, false});
         }
-        for (const Piece& p : pieces[i]) {
-            if (!p.interior) continue;
-            const i64 dims[3] = {gin[0], gin[1], o1 - o0};
-            char* out = (char*)out_slabs[i] + (size_t)(p.k0 - k0) * out_plane;
-            if (kind == 0) rc = restrict3_slab_device(dtype, dims, in_slabs[i], scale, n_in, o0, p.k0, p.k1 - p.k0, out, ws[i]);
-            else rc = prolong3_slab_device(dtype, dims, in_slabs[i], gout, n_in, o0, p.k0, p.k1 - p.k0, out, ws[i]);
-            if (rc) return rc;
-        }
-        GB_CUDA(cudaEventRecord(l.ev_int, ws[i]));
     }
     // ---- 2. halo exchange on the comm streams ------------------------------------------------------------------
     for (int i = 0; i < nl; i++) {  // a send reads the source rank's slab: every comm stream waits for every local input
@@ -316,13 +313,35 @@ int sharded_level(gb_comm* c, int kind, int dtype, const i64* gin, const i64* go
         }
         if (!c->loopback) GB_NCCL(api, api->GroupEnd());
     }
+    for (int i = 0; i < nl; i++) {
+        LocalRank& l = c->loc[i];
+        DevGuard g(l.dev);
+        GB_CUDA(cudaEventRecord(l.ev_halo, l.cs));
+        GB_CUDA(cudaEventRecord(l.ev_h1, l.cs));
+    }
+    // ---- 2b. interior planes on the work streams, while the halo travels (the exchange was enqueued FIRST: its kernels
+    // take their SM slots before the interior kernel fills the machine) ------------------------------------------------
+    for (int i = 0; i < nl; i++) {
+        LocalRank& l = c->loc[i];
+        const int r = l.rank;
+        DevGuard g(l.dev);
+        const i64 o0 = plan.own0[r], o1 = plan.own1[r], k0 = plan.out0[r];
+        for (const Piece& p : pieces[i]) {
+            if (!p.interior) continue;
+            const i64 dims[3] = {gin[0], gin[1], o1 - o0};
+            char* out = (char*)out_slabs[i] + (size_t)(p.k0 - k0) * out_plane;
+            int rc;
+            if (kind == 0) rc = restrict3_slab_device(dtype, dims, in_slabs[i], scale, n_in, o0, p.k0, p.k1 - p.k0, out, ws[i]);
+            else rc = prolong3_slab_device(dtype, dims, in_slabs[i], gout, n_in, o0, p.k0, p.k1 - p.k0, out, ws[i]);
+            if (rc) return rc;
+        }
+        GB_CUDA(cudaEventRecord(l.ev_int, ws[i]));
+    }
     // ---- 3. boundary planes after the halo has landed ------------------------------------------------------------
     for (int i = 0; i < nl; i++) {
         LocalRank& l = c->loc[i];
         const int r = l.rank;
         DevGuard g(l.dev);
-        GB_CUDA(cudaEventRecord(l.ev_halo, l.cs));
-        GB_CUDA(cudaEventRecord(l.ev_h1, l.cs));
         GB_CUDA(cudaStreamWaitEvent(ws[i], l.ev_halo, 0));
         const i64 o0 = plan.own0[r], o1 = plan.own1[r], k0 = plan.out0[r];
         for (const Piece& p : pieces[i]) {

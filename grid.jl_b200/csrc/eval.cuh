@@ -20,7 +20,6 @@
 // plus the separable tensor-product path (outer_table_kernel / outer_eval_kernel).
 // Compiled with -fmad=false: plain * and + never fuse.
 #pragma once
-#include <cooperative_groups.h>
 #include <cuda.h>  // CUtensorMap (types only; the encoder is resolved through cudaGetDriverEntryPoint)
 
 #include <algorithm>
@@ -861,9 +860,6 @@ __global__ void __launch_bounds__(EVAL_BLOCK, 2) eval_kernel(const EvalParams<N>
 //                  no boundary condition needs special bricks and results are bit-identical to plain.
 //   unpermute      sorted slots -> the caller's order and arrays
 constexpr int BRICK_BLOCK = 256;
-#ifndef GB_SCATTER_CLUSTER_DEFAULT
-#define GB_SCATTER_CLUSTER_DEFAULT 0
-#endif
 #ifndef GB_OUT_BY_QUERY_DEFAULT
 #define GB_OUT_BY_QUERY_DEFAULT 1
 #endif
@@ -1098,65 +1094,6 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_scatter_kernel(const EvalPara
             }
         }
     }
-}
-
-// The scatter with the write cursors SHARED by a thread-block cluster (distributed shared memory): the SCATTER_CLUSTER CTAs of
-// a cluster own one contiguous range of the batch between them and bump one cursor per tile -- bin b lives in the shared
-// memory of CTA b mod SCATTER_CLUSTER, reached with a remote shared-memory atomic.  The records a cluster sends to one tile
-// then form one run four times as long as a single CTA's (14 records = 448 bytes on C2 instead of 3.5), and the set of
-// partially written 128-byte lines shrinks from 296 x 9.5k to 74 x 9.5k (45 MB: L2 holds it, lines leave complete).
-constexpr int SCATTER_CLUSTER = 4;
-template <typename T, int N, int ORDER, int BCF>
-__global__ void __launch_bounds__(SORT_BLOCK) tile_scatter_cluster_kernel(const EvalParams<N> p, const u32* __restrict__ boff, T* __restrict__ rec,
-                                                                          u32* __restrict__ inv, u32 nbins, i64 per_cta) {
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    if (p.nwork[2] != 0) return;  // coherent batch: the plain kernel takes it (every CTA of the cluster returns)
-    extern __shared__ u32 s_cur[];  // cursors of the bins b with b % SCATTER_CLUSTER == my rank
-    const u32 rank = cluster.block_rank();
-    const u32 cta0 = blockIdx.x - rank;  // first CTA of the cluster: the cluster's slots of bin b start where that CTA's would
-    for (u32 i = threadIdx.x; i * SCATTER_CLUSTER + rank < nbins; i += SORT_BLOCK) s_cur[i] = boff[(size_t)(i * SCATTER_CLUSTER + rank) * gridDim.x + cta0];
-    cluster.sync();
-    u32* cur[SCATTER_CLUSTER];
-#pragma unroll
-    for (int r = 0; r < SCATTER_CLUSTER; r++) cur[r] = cluster.map_shared_rank(s_cur, r);
-    int ntot = 1, shift[N];
-#pragma unroll
-    for (int d = 0; d < N; d++) { ntot *= p.ntile[d]; shift[d] = __ffs(p.tile[d]) - 1; }
-    const i64 q0 = (i64)blockIdx.x * per_cta;
-    const i64 q1 = q0 + per_cta < p.nq ? q0 + per_cta : p.nq;
-    for (i64 qb = q0 + threadIdx.x; qb < q1; qb += SORT_ITER) {
-        double raw[SORT_UNROLL][N];
-#pragma unroll
-        for (int u = 0; u < SORT_UNROLL; u++) {
-            const i64 q = qb + u * SORT_BLOCK;
-            if (q < q1) {
-#pragma unroll
-                for (int d = 0; d < N; d++) raw[u][d] = load_raw<N>(p, d, q);
-            }
-        }
-        T x[SORT_UNROLL][N];
-        u32 slot[SORT_UNROLL];
-#pragma unroll
-        for (int u = 0; u < SORT_UNROLL; u++) {  // the remote atomics of the thread's queries in flight together
-            const i64 q = qb + u * SORT_BLOCK;
-            if (q < q1) {
-#pragma unroll
-                for (int d = 0; d < N; d++) x[u][d] = index_coord<T, N>(p, d, raw[u][d]);
-                const u32 key = tile_key<T, N, ORDER, BCF>(p, x[u], shift, ntot);
-                slot[u] = atomicAdd(cur[key % SCATTER_CLUSTER] + key / SCATTER_CLUSTER, 1u);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < SORT_UNROLL; u++) {
-            const i64 q = qb + u * SORT_BLOCK;
-            if (q < q1) {
-                store_record<T, N>(rec, slot[u], x[u], (u32)q);
-                if (inv) inv[q] = slot[u];
-            }
-        }
-    }
-    cluster.sync();  // nobody leaves while its cursors may still be bumped
 }
 
 // ---- the two sort passes for grids with more tiles than a shared-memory histogram holds (> sort_smem_bins(), e.g.
@@ -1676,8 +1613,7 @@ int launch_tiled(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     size_t vol = 1;
     for (int d = 0; d < N; d++) vol *= (size_t)box[d];
     const size_t smem = 2 * ((vol + 31) & ~(size_t)31) * sizeof(T);
-    u32 nctas = (u32)std::max<i64>(1, std::min<i64>((i64)num_sms() * 2, (p.nq + 4095) / 4096));
-    if (nctas > SCATTER_CLUSTER) nctas = nctas / SCATTER_CLUSTER * SCATTER_CLUSTER;  // whole clusters (tile_scatter_cluster_kernel)
+    const u32 nctas = (u32)std::max<i64>(1, std::min<i64>((i64)num_sms() * 2, (p.nq + 4095) / 4096));
     const i64 per_cta = ((p.nq + nctas - 1) / nctas + SORT_BLOCK - 1) / SORT_BLOCK * SORT_BLOCK;
     const size_t max_items = (size_t)nbins + (size_t)(p.nq / EVAL_CHUNK) + 2;
     const size_t pitch = ((size_t)p.nq + 15) & ~(size_t)15;
@@ -1753,24 +1689,9 @@ int launch_tiled(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
         rc = tile_offsets(bh, nbins, nctas, hist, offs, boff, work, nwork, EVAL_CHUNK, geo, s);
         if (rc) return rc;
         prof_mark(2, s);
-        static const int use_cluster = [] { const char* e = getenv("GB_SCATTER_CLUSTER"); return e ? atoi(e) : GB_SCATTER_CLUSTER_DEFAULT; }();
-        if (use_cluster && nctas % SCATTER_CLUSTER == 0) {
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(nctas);
-            cfg.blockDim = dim3(SORT_BLOCK);
-            cfg.dynamicSmemBytes = ((size_t)(nbins + SCATTER_CLUSTER - 1) / SCATTER_CLUSTER) * sizeof(u32);
-            cfg.stream = s;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = SCATTER_CLUSTER;
-            at[0].val.clusterDim.y = 1;
-            at[0].val.clusterDim.z = 1;
-            cfg.attrs = at;
-            cfg.numAttrs = 1;
-            GB_CUDA(cudaLaunchKernelEx(&cfg, tile_scatter_cluster_kernel<T, N, ORDER, BCF>, p, (const u32*)boff, rec, inv, nbins, per_cta));
-        } else {
-            tile_scatter_kernel<T, N, ORDER, BCF><<<nctas, SORT_BLOCK, hsmem, s>>>(p, boff, rec, inv, nbins, per_cta);
-        }
+        // (write cursors shared by a 4-CTA cluster through distributed shared memory -- four times longer runs per tile -- were
+        // built and measured SLOWER: 0.36 vs 0.31 ms, the remote atomics' latency; profiles/README.md)
+        tile_scatter_kernel<T, N, ORDER, BCF><<<nctas, SORT_BLOCK, hsmem, s>>>(p, boff, rec, inv, nbins, per_cta);
         count_launch();
     }
     GB_CUDA(cudaGetLastError());
