@@ -243,7 +243,8 @@ def test_interp_irregular_batched_entry_points(gb):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-@pytest.mark.parametrize("shape,world", [((40, 36, 50), 2), ((33, 20, 64), 3), ((20, 18, 129), 5), ((12, 10, 17), 8), ((9, 8, 20), 4), ((66, 40, 128), 8)])
+@pytest.mark.parametrize("shape,world", [((40, 36, 50), 2), ((33, 20, 64), 3), ((20, 18, 129), 5), ((12, 10, 17), 8), ((9, 8, 20), 4), ((66, 40, 128), 8),
+                                         ((12, 10, 5), 8), ((9, 8, 6), 8)])  # (the last two: more ranks than planes -- ranks that own or produce nothing)
 def test_comm_loopback_sharded_multigrid(gb, oracle, dtype, shape, world):
     """gb_restrict3_sharded / gb_prolong3_sharded on `world` virtual ranks of one GPU (gb_comm_init_loopback): plan, halo
     planes, interior / boundary split and the slab kernels -- assembled slabs equal the unsharded oracle result bitwise."""
