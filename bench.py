@@ -258,7 +258,20 @@ def extra_configs(gb, torch, np, O, peak, traffic, reps=5):
             par = bool(np.array_equal(ov, sub(v, idx), equal_nan=True) and np.array_equal(og, sub(g, idx), equal_nan=True))
         rows.append(_row("C2 3-D InterpCubic BCnan 256^3 f64 valgrad, 1e7 queries sorted by 16x16x8-cell block (coherent: the probe hands them to the plain kernel), %s" % ("FAST" if fast else "EXACT"), nq, "points",
                          BYTES_PER_QUERY, best, med, peak, par, traffic.get("c2_sorted_%s_bytes_per_step" % ("fast" if fast else "exact"))))
-    del G, A, Xs, v, g
+    # the same valgrad on the RANDOM batch with the packed output layout (GB_OUT_PACKED: one (N+1)-element record per query)
+    X = torch.empty((nq, 3), dtype=torch.float64, device=dev)
+    gb.synth_uniform(X, SEED_Q, lo=1.0, hi=float(n))
+    vg = torch.empty((nq, 4), dtype=torch.float64, device=dev)
+    idx = torch.arange(0, nq, 200, device=dev)
+    for fast in (False, True):
+        best, med = _timed(torch, lambda: gb.valgrad_packed_(vg, G, X, fast=fast), reps)
+        par = None
+        if not fast:
+            ov, og, _, _ = O.evaluate(co, "nan", "cubic", sub(X, idx), 3)
+            par = bool(np.array_equal(np.concatenate([ov[:, None], og], axis=1), sub(vg, idx), equal_nan=True))
+        rows.append(_row("C2 3-D InterpCubic BCnan 256^3 f64 valgrad, 1e7 uniform queries, packed (N+1) x nq output (new layout: no unpack pass), %s"
+                         % ("FAST" if fast else "EXACT"), nq, "points", BYTES_PER_QUERY, best, med, peak, par))
+    del G, A, Xs, v, g, X, vg
 
     # ---- C3: the whole 1e9-query batch, 1e8 at a time; and the prefilter of the 8192^2 image --------------------------
     n, nq, nsl = 8192, 100_000_000, 10

@@ -14,7 +14,7 @@ from .api import (AbstractInterpGrid, BCfill, BCna, BCnan, BCnearest, BCnil, BCp
                   CoordInterpGrid, FloatRange, InterpBackward, InterpCubic, InterpForward, InterpGrid, InterpGridChannels, InterpIrregular, InterpLinear, InterpNearest, InterpQuadratic,
                   InterpType, StepRange, UnitRange, filledges_, frange, getindex_, getindex_batch, interp_invert_, jl_empty,
                   jl_from_numpy, jl_to_numpy, launch_count, npoints, PROFILE_STAGES, profile_enable, profile_read, pad1, prolong, prolongb, prolong_size, restrict, restrictb, restrict_extrap,
-                  restrict_size, synth_uniform, valgrad, valgrad_, valgrad_batch, valgradhess, valgradhess_,
+                  restrict_size, synth_uniform, valgrad, valgrad_, valgrad_batch, valgrad_packed, valgrad_packed_, valgradhess, valgradhess_,
                   valgradhess_batch, wrap)
 
 __version__ = "1.1.0"

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libgridb200.so")
 
 GB_F32, GB_F64 = 0, 1
 GB_HOST, GB_DEVICE = 0, 1
-GB_OUT_VAL, GB_OUT_GRAD, GB_OUT_HESS = 1, 2, 4
+GB_OUT_VAL, GB_OUT_GRAD, GB_OUT_HESS, GB_OUT_PACKED = 1, 2, 4, 8
 GB_EXACT, GB_FAST, GB_TILED, GB_PLAIN, GB_SORTED = 0, 1, 2, 4, 8
 (GB_OK, GB_ERR_ARG, GB_ERR_INVALID_LOCATION, GB_ERR_UNSUPPORTED, GB_ERR_CUDA, GB_ERR_DIM, GB_ERR_PROLONG_SIZE) = range(7)
 

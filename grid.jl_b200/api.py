@@ -551,6 +551,34 @@ class InterpGrid(AbstractInterpGrid):
         L.check(rc, bad.value)
         return val, grad, hess
 
+    def _eval_packed(self, X, mask, out=None, fast=False, affine=None, tiled=None, sorted=False):
+        """GB_OUT_PACKED: one record per query -- value, gradient, Hessian as in `mask` -- in an (nq, W) array (a Julia
+        W x nq Matrix); W = 1 [+ N [+ N*N]]."""
+        N = self.ndim
+        q = X if isinstance(X, _Queries) else _Queries(X, N)
+        dt = self.dtype_code
+        W = 1 + (N if mask & (L.GB_OUT_GRAD | L.GB_OUT_HESS) else 0) + (N * N if mask & L.GB_OUT_HESS else 0)
+        nch = getattr(self, "nchan", 1)
+        shape = (q.nq, W) if nch == 1 else (q.nq, nch, W)
+        if out is None:
+            out = _out_array(q, shape, dt)
+        po = _out_ptr(out, q, shape, dt, "packed output")
+        if mask & L.GB_OUT_HESS:
+            mask |= L.GB_OUT_GRAD
+        aff = None
+        if affine is not None:
+            aff = (C.c_double * (4 * N))(*[v for row in affine for v in row])
+        bad = C.c_int64(-1)
+        pbad = C.byref(bad) if self.BC is BCnil else None
+        flags = (L.GB_FAST if fast else L.GB_EXACT) | (0 if tiled is None else (L.GB_TILED if tiled else L.GB_PLAIN)) | (L.GB_SORTED if sorted else 0)
+        m = mask | L.GB_OUT_PACKED
+        if q.cols is not None:
+            rc = self._lib.gb_eval_soa(self._h, m, q.nq, q.ptrs, q.xdtype, aff, po, None, None, q.mem, flags, pbad, q.stream())
+        else:
+            rc = self._lib.gb_eval(self._h, m, q.nq, q.ptr, q.xdtype, N, 1, aff, po, None, None, q.mem, flags, pbad, q.stream())
+        L.check(rc, bad.value)
+        return out
+
     def _scalar_args(self, x):
         N = self.ndim
         if N == 1 and len(x) == 2:  # src/interp.jl:147-153
@@ -849,6 +877,16 @@ def valgradhess_(v, g, h, G, X, fast=False, tiled=None, sorted=False):
         raise MethodError(L.GB_ERR_UNSUPPORTED, "valgradhess has no method for CoordInterpGrid")
     G._eval(X, L.GB_OUT_VAL | L.GB_OUT_GRAD | L.GB_OUT_HESS, val=v, grad=g, hess=h, fast=fast, tiled=tiled, sorted=sorted)
     return v
+
+
+def valgrad_packed_(out, G, X, fast=False, tiled=None, sorted=False):
+    """New batched layout (GB_OUT_PACKED): out[q] = (value, gradient...) of query q, one (N+1)-element record per query --
+    a Julia (N+1) x nq Matrix.  One full-sector write per query; the tiled path skips its unpack pass."""
+    return _grid_of(G)._eval_packed(X, L.GB_OUT_VAL | L.GB_OUT_GRAD, out=out, fast=fast, affine=G.affine, tiled=tiled, sorted=sorted)
+
+
+def valgrad_packed(G, X, fast=False, tiled=None, sorted=False):
+    return valgrad_packed_(None, G, X, fast=fast, tiled=tiled, sorted=sorted)
 
 
 def getindex_batch(G, X, fast=False, tiled=None, sorted=False):

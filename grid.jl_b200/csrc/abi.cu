@@ -597,6 +597,7 @@ struct EvalCall {
     void *val, *grad, *hess;  // device
     u64* first_invalid;       // device or NULL
     i64 q0;
+    int packed = 0;           // GB_OUT_PACKED: words per output record at val (0: separate arrays)
 };
 
 template <int N> void fill_params(const EvalCall& c, EvalParams<N>& p) {
@@ -619,7 +620,7 @@ template <int N> void fill_params(const EvalCall& c, EvalParams<N>& p) {
     p.nq = c.nq;
     p.q0 = c.q0;
     p.first_invalid = c.first_invalid;
-    p.aos = 0;
+    p.aos = c.packed;
     p.blocked = g->blocked;
     {
         u32 bs = 1u << (2 * N);
@@ -736,14 +737,26 @@ int launch_eval(const EvalCall& c, cudaStream_t s) {
 }
 
 int outmode_of(const gb_grid* g, int out_mask, void* val, void* grad, void* hess, int* outmode) {
-    if (out_mask & ~(GB_OUT_VAL | GB_OUT_GRAD | GB_OUT_HESS) || out_mask == 0) return fail(GB_ERR_ARG, "bad out_mask");
+    if (out_mask & ~(GB_OUT_VAL | GB_OUT_GRAD | GB_OUT_HESS | GB_OUT_PACKED) || (out_mask & ~GB_OUT_PACKED) == 0) return fail(GB_ERR_ARG, "bad out_mask");
     *outmode = (out_mask & GB_OUT_HESS) ? 2 : (out_mask & GB_OUT_GRAD) ? 1 : 0;
+    if (out_mask & GB_OUT_PACKED) {  // one record per query at val
+        if ((out_mask & GB_OUT_HESS) && g->order < GB_QUADRATIC)
+            return fail(GB_ERR_UNSUPPORTED, "valgradhess is not defined for InterpNearest/InterpLinear (no interp_hcoefs_1d method)");
+        if (!val) return fail(GB_ERR_ARG, "val is NULL");
+        if (g->ndim > MAXD || (g->ndim == 4 && g->order >= GB_QUADRATIC)) return fail(GB_ERR_UNSUPPORTED, "GB_OUT_PACKED is provided for the dimension-specialised kernels (N <= 4; N = 4: InterpNearest / InterpLinear)");
+        return GB_OK;
+    }
     if ((out_mask & GB_OUT_HESS) && g->order < GB_QUADRATIC)
         return fail(GB_ERR_UNSUPPORTED, "valgradhess is not defined for InterpNearest/InterpLinear (no interp_hcoefs_1d method)");
     if ((out_mask & GB_OUT_VAL) && !val) return fail(GB_ERR_ARG, "val is NULL");
     if ((out_mask & GB_OUT_GRAD) && !grad) return fail(GB_ERR_ARG, "Wrong number of components for the gradient");
     if ((out_mask & GB_OUT_HESS) && !hess) return fail(GB_ERR_ARG, "Wrong number of components for the hessian");
     return GB_OK;
+}
+
+int packed_words(const gb_grid* g, int out_mask, int outmode) {
+    if (!(out_mask & GB_OUT_PACKED)) return 0;
+    return 1 + (outmode >= 1 ? g->ndim : 0) + (outmode >= 2 ? g->ndim * g->ndim : 0);
 }
 
 int check_affine(const gb_grid* g, const double* affine) {
@@ -797,9 +810,13 @@ int eval_host(const gb_grid* g, int out_mask, int outmode, i64 nq, const void* c
         if (want) {
             if (xaos) pins.add(xaos, xbytes);
             else for (int d = 0; d < N; d++) pins.add(xcols[d], (size_t)nq * xs);
-            if (out_mask & GB_OUT_VAL) pins.add(val, vbytes);
-            if (out_mask & GB_OUT_GRAD) pins.add(grad, vbytes * N);
-            if (out_mask & GB_OUT_HESS) pins.add(hess, vbytes * N * N);
+            const int pw = packed_words(g, out_mask, outmode);
+            if (pw) pins.add(val, vbytes * pw);
+            else {
+                if (out_mask & GB_OUT_VAL) pins.add(val, vbytes);
+                if (out_mask & GB_OUT_GRAD) pins.add(grad, vbytes * N);
+                if (out_mask & GB_OUT_HESS) pins.add(hess, vbytes * N * N);
+            }
         }
     }
     constexpr int NSLOT = 3;
@@ -814,11 +831,16 @@ int eval_host(const gb_grid* g, int out_mask, int outmode, i64 nq, const void* c
         if (e != cudaSuccess && rc == GB_OK) rc = cuda_fail(e, what);
         return e == cudaSuccess;
     };
+    const int packed = packed_words(g, out_mask, outmode);
     for (int i = 0; i < nslot && rc == GB_OK; i++) {
         Slot& sl = slots[i];
         if (!cu(cudaStreamCreateWithFlags(&sl.s, cudaStreamNonBlocking), "cudaStreamCreate")) break;
         if (g->ready) cu(cudaStreamWaitEvent(sl.s, g->ready, 0), "cudaStreamWaitEvent");  // a grid built on another stream
         cu(cudaMallocAsync(&sl.x, (size_t)chunk * N * xs, sl.s), "cudaMallocAsync");
+        if (packed) {
+            cu(cudaMallocAsync(&sl.v, (size_t)chunk * packed * es, sl.s), "cudaMallocAsync");
+            continue;
+        }
         if (out_mask & GB_OUT_VAL) cu(cudaMallocAsync(&sl.v, (size_t)chunk * es, sl.s), "cudaMallocAsync");
         if (out_mask & GB_OUT_GRAD) cu(cudaMallocAsync(&sl.gr, (size_t)chunk * N * es, sl.s), "cudaMallocAsync");
         if (out_mask & GB_OUT_HESS) cu(cudaMallocAsync(&sl.h, (size_t)chunk * N * N * es, sl.s), "cudaMallocAsync");
@@ -846,9 +868,14 @@ int eval_host(const gb_grid* g, int out_mask, int outmode, i64 nq, const void* c
             call.xqs = 1;
         }
         call.val = sl.v; call.grad = sl.gr; call.hess = sl.h;
+        call.packed = packed;
         if (rc != GB_OK) break;
         rc = launch_eval(call, sl.s);
         if (rc != GB_OK) break;
+        if (packed) {
+            cu(cudaMemcpyAsync((char*)val + (size_t)q0 * packed * es, sl.v, (size_t)n * packed * es, cudaMemcpyDeviceToHost, sl.s), "cudaMemcpyAsync D2H");
+            continue;
+        }
         if (sl.v) cu(cudaMemcpyAsync((char*)val + (size_t)q0 * es, sl.v, (size_t)n * es, cudaMemcpyDeviceToHost, sl.s), "cudaMemcpyAsync D2H");
         if (sl.gr) cu(cudaMemcpyAsync((char*)grad + (size_t)q0 * N * es, sl.gr, (size_t)n * N * es, cudaMemcpyDeviceToHost, sl.s), "cudaMemcpyAsync D2H");
         if (sl.h) cu(cudaMemcpyAsync((char*)hess + (size_t)q0 * N * N * es, sl.h, (size_t)n * N * N * es, cudaMemcpyDeviceToHost, sl.s), "cudaMemcpyAsync D2H");
@@ -878,8 +905,9 @@ int eval_host(const gb_grid* g, int out_mask, int outmode, i64 nq, const void* c
 }
 
 int eval_device(const gb_grid* g, int outmode, i64 nq, const void* const* xp, i64 xqs, int xdtype, const double* affine,
-                void* val, void* grad, void* hess, int flags, int64_t* first_invalid, cudaStream_t s) {
+                void* val, void* grad, void* hess, int flags, int64_t* first_invalid, cudaStream_t s, int packed = 0) {
     EvalCall call;
+    call.packed = packed;
     call.g = g; call.outmode = outmode; call.flags = flags; call.xdtype = xdtype; call.affine = affine;
     call.nq = nq; call.q0 = 0; call.xqs = xqs;
     for (int d = 0; d < g->ndim; d++) call.xp[d] = xp[d];
@@ -946,9 +974,12 @@ int gb_eval(const gb_grid* g, int out_mask, int64_t nq, const void* x, int xdtyp
     const int N = g->ndim;
     const void* cols[MAXG];
     for (int d = 0; d < N; d++) cols[d] = (const char*)x + (size_t)d * x_dstride * esize(xdtype);
-    if (mem == GB_DEVICE)
-        return eval_device(g, outmode, nq, cols, x_qstride, xdtype, affine, (out_mask & GB_OUT_VAL) ? val : nullptr,
-                           (out_mask & GB_OUT_GRAD) ? grad : nullptr, (out_mask & GB_OUT_HESS) ? hess : nullptr, flags, first_invalid, (cudaStream_t)stream);
+    if (mem == GB_DEVICE) {
+        const int pw = packed_words(g, out_mask, outmode);
+        return eval_device(g, outmode, nq, cols, x_qstride, xdtype, affine, (pw || (out_mask & GB_OUT_VAL)) ? val : nullptr,
+                           (!pw && (out_mask & GB_OUT_GRAD)) ? grad : nullptr, (!pw && (out_mask & GB_OUT_HESS)) ? hess : nullptr, flags, first_invalid,
+                           (cudaStream_t)stream, pw);
+    }
     if (x_qstride == N && x_dstride == 1)
         return eval_host(g, out_mask, outmode, nq, nullptr, x, xdtype, affine, val, grad, hess, flags, first_invalid);
     if (x_qstride == 1)
@@ -973,9 +1004,12 @@ int gb_eval_soa(const gb_grid* g, int out_mask, int64_t nq, const void* const* x
         if (!xs[d]) return fail(GB_ERR_ARG, "Incorrect number of dimensions supplied");
     DeviceGuard guard(g->device);
     pool_keep_memory();
-    if (mem == GB_DEVICE)
-        return eval_device(g, outmode, nq, xs, 1, xdtype, affine, (out_mask & GB_OUT_VAL) ? val : nullptr,
-                           (out_mask & GB_OUT_GRAD) ? grad : nullptr, (out_mask & GB_OUT_HESS) ? hess : nullptr, flags, first_invalid, (cudaStream_t)stream);
+    if (mem == GB_DEVICE) {
+        const int pw = packed_words(g, out_mask, outmode);
+        return eval_device(g, outmode, nq, xs, 1, xdtype, affine, (pw || (out_mask & GB_OUT_VAL)) ? val : nullptr,
+                           (!pw && (out_mask & GB_OUT_GRAD)) ? grad : nullptr, (!pw && (out_mask & GB_OUT_HESS)) ? hess : nullptr, flags, first_invalid,
+                           (cudaStream_t)stream, pw);
+    }
     return eval_host(g, out_mask, outmode, nq, xs, nullptr, xdtype, affine, val, grad, hess, flags, first_invalid);
 }
 

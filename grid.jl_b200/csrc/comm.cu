@@ -630,6 +630,8 @@ int gb_eval_sharded(gb_comm* c, gb_grid* const* grids, int out_mask, int64_t nq,
     if (rc) return rc;
     gb_grid_channels(grids[0], &nchan);
     const size_t xs = xdtype == GB_F64 ? 8 : 4, es = esz(dtype) * (size_t)nchan;
+    // GB_OUT_PACKED: one record of pw elements per query at val
+    const size_t pw = (out_mask & GB_OUT_PACKED) ? (size_t)(1 + ((out_mask & (GB_OUT_GRAD | GB_OUT_HESS)) ? ndim : 0) + ((out_mask & GB_OUT_HESS) ? ndim * ndim : 0)) : 1;
     std::vector<int> rcs(nl, GB_OK);
     std::vector<int64_t> bad(nl, -1);
     std::vector<std::string> msgs(nl);
@@ -641,7 +643,7 @@ int gb_eval_sharded(gb_comm* c, gb_grid* const* grids, int out_mask, int64_t nq,
             if (q1 <= q0) return;
             cudaSetDevice(c->loc[i].dev);
             const char* xp = (const char*)x + (size_t)q0 * ndim * xs;
-            rcs[i] = gb_eval(grids[i], out_mask, q1 - q0, xp, xdtype, ndim, 1, affine, val ? (char*)val + (size_t)q0 * es : nullptr,
+            rcs[i] = gb_eval(grids[i], out_mask, q1 - q0, xp, xdtype, ndim, 1, affine, val ? (char*)val + (size_t)q0 * es * pw : nullptr,
                              grad ? (char*)grad + (size_t)q0 * ndim * es : nullptr, hess ? (char*)hess + (size_t)q0 * ndim * ndim * es : nullptr, GB_HOST, flags,
                              first_invalid ? &bad[i] : nullptr, nullptr);
             if (rcs[i]) msgs[i] = gb_last_error();

@@ -1652,7 +1652,9 @@ int launch_tiled(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     // Where do the brick kernel's output records go?  To the query's sorted slot (coalesced writes, then un-permuted by a random
     // 32-byte gather) or straight to record q (random full-sector writes hidden under the FP64-bound evaluation, then a
     // streaming unpack).  GB_OUT_BY_QUERY selects (measured, profiles/README.md).
-    static const int by_query = [] { const char* e = getenv("GB_OUT_BY_QUERY"); return e ? atoi(e) : GB_OUT_BY_QUERY_DEFAULT; }();
+    static const int by_query_env = [] { const char* e = getenv("GB_OUT_BY_QUERY"); return e ? atoi(e) : GB_OUT_BY_QUERY_DEFAULT; }();
+    const bool packed = p_in.aos != 0;  // GB_OUT_PACKED: the caller's buffer IS the array of output records, in query order
+    const int by_query = packed ? 1 : by_query_env;
     p.by_query = by_query;
     if (by_query) inv = nullptr;
     GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per device, cheap
@@ -1699,10 +1701,10 @@ int launch_tiled(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     // the deferred-slot list (count first)
     u32* defer = keys;
     GB_CUDA(cudaMemsetAsync(defer, 0, sizeof(u32), s));
-    EvalParams<N> pp = p;  // the plain kernel's view: the caller's order and arrays
-    pp.aos = 0;
-    p.aos = W;  // both brick-path kernels write one output record per sorted slot ...
-    p.val = osorted;
+    EvalParams<N> pp = p;  // the plain kernel's view: the caller's order and arrays (or packed records)
+    pp.aos = p_in.aos;
+    p.aos = W;  // both brick-path kernels write one output record per slot / query ...
+    p.val = packed ? p_in.val : (void*)osorted;
     p.grad = nullptr;
     p.hess = nullptr;
     prof_mark(3, s);
@@ -1712,8 +1714,8 @@ int launch_tiled(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     prof_mark(5, s);
     // ... and the records go back to the caller's order and arrays
     const int ugrid = (int)std::min<i64>((p.nq + 255) / 256, (i64)num_sms() * 32);
-    unpermute_kernel<T, N, OUTMODE><<<ugrid, 256, 0, s>>>(osorted, inv, (T*)p_in.val, (T*)p_in.grad, (T*)p_in.hess, p.nq, nwork);
-    count_launch(3);
+    if (!packed) unpermute_kernel<T, N, OUTMODE><<<ugrid, 256, 0, s>>>(osorted, inv, (T*)p_in.val, (T*)p_in.grad, (T*)p_in.hess, p.nq, nwork);
+    count_launch(packed ? 2 : 3);
     if (probe) {  // coherent batch: evaluated in place by the plain kernel (exits at once otherwise)
         int pgrid = 1;
         rc = plain_grid<T, N, ORDER, BCF, OUTMODE, FAST>(p.nq, &pgrid);
@@ -1746,8 +1748,7 @@ int launch_one(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     if (p.nchan > 1 || p.blocked || !BRICK) tiled = false;  // multi-valued / blocked grids, light neighbourhoods: plain path
     if (N == 3 && (p.len[1] > 0x7fff || p.len[2] > 0x7fff)) tiled = false;  // (work items pack the brick corner: make_item)
     if (tiled) tiled = choose_tile(N, L, sizeof(T), p.len, std::min<i64>(p.nq, tiled_max_batch()), forced, p.tile, p.ntile);
-    p.aos = 0;
-    p.use_tma = 0;
+    p.use_tma = 0;  // (p.aos stays what the caller set: the words of a GB_OUT_PACKED record, 0 for separate arrays)
     p.by_query = 0;
     if (!tiled) {
         for (int d = 0; d < N; d++) { p.tile[d] = 1; p.ntile[d] = 1; }
@@ -1771,7 +1772,7 @@ int launch_one(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
             sp.nq = std::min<i64>(slice, p_in.nq - q0);
             sp.q0 = p_in.q0 + q0;
             for (int d = 0; d < N; d++) sp.xp[d] = (const char*)p.xp[d] + (size_t)q0 * (size_t)p.xqs * xs;
-            if (p.val) sp.val = (T*)p.val + q0;
+            if (p.val) sp.val = (T*)p.val + q0 * (p.aos ? p.aos : 1);
             if (p.grad) sp.grad = (T*)p.grad + q0 * N;
             if (p.hess) sp.hess = (T*)p.hess + q0 * N * N;
             const int rc = launch_tiled<T, N, ORDER, BCF, OUTMODE, FAST>(sp, flags, s);

@@ -13,7 +13,7 @@ module GridB200
 export BoundaryCondition, BCnil, BCnan, BCna, BCreflect, BCperiodic, BCnearest, BCfill,
        InterpType, InterpNearest, InterpLinear, InterpQuadratic, InterpCubic,
        AbstractInterpGrid, InterpGrid, CoordInterpGrid,
-       valgrad, valgradhess, getindex!, valgrad!, valgradhess!,
+       valgrad, valgradhess, getindex!, valgrad!, valgradhess!, valgrad_packed!,
        interp_invert!, pad1, restrict, prolong, restrict_size, prolong_size,
        restrictb, restrict_extrap, prolongb, interp_channels!, InterpIrregular, InterpForward, InterpBackward,
        filledges!, pin!, unpin!, GridComm, replicate, getindex_sharded!, valgrad_sharded!, restrict3_sharded, prolong3_sharded
@@ -39,7 +39,7 @@ bccode(::Type{BCreflect}) = 3; bccode(::Type{BCperiodic}) = 4; bccode(::Type{BCn
 itcode(::Type{InterpNearest}) = 0; itcode(::Type{InterpLinear}) = 1; itcode(::Type{InterpQuadratic}) = 2; itcode(::Type{InterpCubic}) = 3
 dtcode(::Type{Float32}) = 0; dtcode(::Type{Float64}) = 1
 const GB_HOST, GB_DEVICE = 0, 1
-const OUT_VAL, OUT_GRAD, OUT_HESS = 1, 2, 4
+const OUT_VAL, OUT_GRAD, OUT_HESS, OUT_PACKED = 1, 2, 4, 8
 const GB_FAST, GB_TILED, GB_PLAIN, GB_SORTED = 1, 2, 4, 8     # gb_eval flags (include/gridb200.h)
 
 lasterror() = unsafe_string(ccall((:gb_last_error, LIB), Cstring, ()))
@@ -100,6 +100,12 @@ getindex!(out::Vector{T}, G::InterpGrid{T,N}, X::Matrix) where {T,N} = (length(o
 function valgrad!(v::Vector{T}, g::Matrix{T}, G::InterpGrid{T,N}, X::Matrix) where {T,N}
     size(g) == (N, size(X, 2)) || error("Wrong number of components for the gradient")   # src/interp.jl:159-161
     _eval!(G, OUT_VAL | OUT_GRAD, X, v, g, nothing); v
+end
+# valgrad_packed!(VG, G, X): VG is (N+1) x nq -- VG[1,q] the value, VG[2:end,q] the gradient of query q (GB_OUT_PACKED: one
+# full-sector write per query on the device; the library's tiled path skips its unpack pass)
+function valgrad_packed!(VG::Matrix{T}, G::InterpGrid{T,N}, X::Matrix) where {T,N}
+    size(VG) == (N + 1, size(X, 2)) || error("Wrong number of components for the gradient")
+    _eval!(G, OUT_VAL | OUT_GRAD | OUT_PACKED, X, VG, nothing, nothing); VG
 end
 function valgradhess!(v::Vector{T}, g::Matrix{T}, h::Array{T,3}, G::InterpGrid{T,N}, X::Matrix) where {T,N}
     size(g) == (N, size(X, 2)) || error("Wrong number of components for the gradient")   # :206-208

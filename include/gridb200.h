@@ -41,7 +41,12 @@ enum { GB_BC_NIL = 0, GB_BC_NAN = 1, GB_BC_NA = 2, GB_BC_REFLECT = 3, GB_BC_PERI
 /* src/interpflags.jl:4-7 (npoints = order+1, src/interp.jl:579-582) */
 enum { GB_NEAREST = 0, GB_LINEAR = 1, GB_QUADRATIC = 2, GB_CUBIC = 3,
        GB_FORWARD = 4, GB_BACKWARD = 5 /* InterpForward / InterpBackward: gb_interp_irregular only */ };
-enum { GB_OUT_VAL = 1, GB_OUT_GRAD = 2, GB_OUT_HESS = 4 };
+enum { GB_OUT_VAL = 1, GB_OUT_GRAD = 2, GB_OUT_HESS = 4,
+       /* with GB_OUT_PACKED the requested outputs of a query form ONE record at val: value, gradient (N), Hessian (N x N,
+          both triangles) -- W = 1 [+ N [+ N*N]] contiguous elements per query, i.e. a Julia W x nq Matrix (W x nchan x nq
+          for multi-valued grids); grad / hess are ignored.  A new batched layout (absent upstream): one full-sector write
+          per query instead of two or three partial ones, and the tiled path skips its unpack pass. */
+       GB_OUT_PACKED = 8 };
 enum { GB_HOST = 0, GB_DEVICE = 1 };
 enum {
     GB_OK = 0,

@@ -303,3 +303,35 @@ def test_comm_loopback_replicate_and_sharded_eval(gb, oracle):
         assert same(v, ov) and same(gr, og) and bad.value == -1  # BCnan: NaN, no error
     finally:
         comm.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("bc,order,shape", [("nan", "cubic", (40, 37, 35)), ("reflect", "quadratic", (300, 200)), ("periodic", "linear", (9, 20, 17, 12)),
+                                            ("nearest", "nearest", (50,)), ("nan", "quadratic", (33, 31, 30))])
+def test_packed_output_layout(gb, oracle, dtype, bc, order, shape):
+    """GB_OUT_PACKED: one (value, gradient[, Hessian]) record per query -- the same bits as the separate arrays, on the plain
+    path, through the bins, on the probe's coherent route and through host buffers."""
+    import torch
+
+    BC = dict(nan=gb.BCnan, reflect=gb.BCreflect, periodic=gb.BCperiodic, nearest=gb.BCnearest)[bc]
+    IT = dict(cubic=gb.InterpCubic, quadratic=gb.InterpQuadratic, linear=gb.InterpLinear, nearest=gb.InterpNearest)[order]
+    rng = np.random.default_rng(71)
+    A = rng.standard_normal(shape).astype(dtype)
+    g = gb.InterpGrid(A, BC, IT)
+    N = len(shape)
+    X = (0.5 + rng.random((90_000, N)) * np.array(shape)).astype(dtype)
+    L = gb._lib
+    for mask in ((L.GB_OUT_VAL, L.GB_OUT_VAL | L.GB_OUT_GRAD) + ((L.GB_OUT_VAL | L.GB_OUT_GRAD | L.GB_OUT_HESS,) if order in ("quadratic", "cubic") else ())):
+        v, gr, h = g._eval(X, mask)
+        ref = np.concatenate([v[:, None]] + ([gr] if mask & L.GB_OUT_GRAD else []) + ([h.reshape(len(X), N * N)] if mask & L.GB_OUT_HESS else []), axis=1)
+        assert same(g._eval_packed(X, mask), ref)                                        # host buffers
+        Xd = torch.from_numpy(X).cuda()
+        for tiled, srt in ((False, False), (True, False), (True, True)):
+            assert same(g._eval_packed(Xd, mask, tiled=tiled, sorted=srt).cpu().numpy(), ref), (mask, tiled, srt)
+        Xs = np.ascontiguousarray(X[np.lexsort(tuple(np.floor(X[:, d]) for d in range(N)))])   # a coherent order: the probe's plain route
+        vs, gs, hs = g._eval(Xs, mask)
+        refs = np.concatenate([vs[:, None]] + ([gs] if mask & L.GB_OUT_GRAD else []) + ([hs.reshape(len(X), N * N)] if mask & L.GB_OUT_HESS else []), axis=1)
+        assert same(g._eval_packed(torch.from_numpy(Xs).cuda(), mask, tiled=True, sorted=True).cpu().numpy(), refs)
+    vg = gb.valgrad_packed(g, torch.from_numpy(X).cuda())
+    v, gr = gb.valgrad_batch(g, X)
+    assert same(vg.cpu().numpy(), np.concatenate([v[:, None], gr], axis=1))
