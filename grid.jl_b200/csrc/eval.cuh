@@ -952,17 +952,18 @@ __device__ __forceinline__ u32 tile_key(const EvalParams<N>& p, const T (&x)[N],
 // queries -- and calls a leaf coherent when the bounding box of its queries' first taps holds at most `vmax` cells (four brick
 // tiles).  Nearly all leaves coherent: nwork[2] = 1, the binning kernels exit at once and the plain kernel evaluates the
 // batch in place; else nwork[2] = 0 and the plain kernel exits.  Decided on the device: the host never waits.
-// nwork[3] coherent leaves, nwork[4] leaves, nwork[5] CTAs done (all zeroed by the launcher).
+// nwork[3] coherent leaves, nwork[4] leaves, nwork[5] CTAs done, nwork[6] queries sampled (all zeroed by the launcher).
 template <typename T, int N, int ORDER, int BCF>
-__global__ void __launch_bounds__(SORT_BLOCK) coherence_probe_kernel(const EvalParams<N> p, u32* __restrict__ nwork, i64 per_cta, u32 vmax, u32 need_percent) {
+__global__ void __launch_bounds__(SORT_BLOCK) coherence_probe_kernel(const EvalParams<N> p, u32* __restrict__ nwork, i64 per_cta, u32 vmax, u32 need_percent,
+                                                                     u32* __restrict__ shist) {
     __shared__ u32 s_last;
     const i64 q0 = (i64)blockIdx.x * per_cta;
     const i64 q1 = q0 + per_cta < p.nq ? q0 + per_cta : p.nq;
     const u32 lane = threadIdx.x & 31;
-    int shift[N];
+    int ntot = 1, shift[N];
 #pragma unroll
-    for (int d = 0; d < N; d++) shift[d] = 0;
-    u32 good = 0, seen = 0;
+    for (int d = 0; d < N; d++) { ntot *= p.ntile[d]; shift[d] = __ffs(p.tile[d]) - 1; }
+    u32 good = 0, seen = 0, sampled = 0;
     if (q0 < q1) {
         const i64 stride = ((q1 - q0) / SORT_UNROLL) & ~(i64)(SORT_BLOCK - 1);  // (groups start on multiples of 256 past q0)
         double raw[SORT_UNROLL][N];
@@ -986,8 +987,10 @@ __global__ void __launch_bounds__(SORT_BLOCK) coherence_probe_kernel(const EvalP
                 T x[N];
 #pragma unroll
                 for (int d = 0; d < N; d++) x[d] = index_coord<T, N>(p, d, raw[u][d]);
-                tile_key<T, N, ORDER, BCF>(p, x, shift, 0, first, ok);
+                const u32 key = tile_key<T, N, ORDER, BCF>(p, x, shift, ntot, first, ok);
+                if (shist) atomicAdd(shist + key, 1u);  // the sample's tile histogram: sizes the bins of the single-pass scatter
             }
+            sampled += (u32)__popc(__ballot_sync(0xffffffffu, act));
             if (!__any_sync(0xffffffffu, act)) continue;
             double vol = 1.0;
 #pragma unroll
@@ -1000,7 +1003,7 @@ __global__ void __launch_bounds__(SORT_BLOCK) coherence_probe_kernel(const EvalP
             good += vol <= (double)vmax ? 1u : 0u;
         }
     }
-    if (lane == 0 && seen) { atomicAdd(nwork + 3, good); atomicAdd(nwork + 4, seen); }
+    if (lane == 0 && seen) { atomicAdd(nwork + 3, good); atomicAdd(nwork + 4, seen); atomicAdd(nwork + 6, sampled); }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_last = atomicAdd(nwork + 5, 1u) == gridDim.x - 1 ? 1u : 0u;
@@ -1146,6 +1149,83 @@ __global__ void __launch_bounds__(SORT_BLOCK) tile_sort_global_kernel(const Eval
                 }
             }
         }
+    }
+}
+
+// ---- single-pass scatter into bins sized from the probe's sample -------------------------------------------------------
+// The counting sort reads the batch twice (histogram, scatter).  The probe already holds a ~3 % sample of the tile histogram:
+// tile_capacity (eval_tile.cu) gives bin b room for scale * (h_b + 4 sqrt(h_b + 1) + 4) records -- four standard
+// deviations of the sampling noise above the estimate -- and one pass scatters the records with one global cursor per bin
+// (warp-aggregated atomics).  A query that finds its bin full goes to an overflow list and is evaluated by the plain path
+// (a few in 10^7 for smooth distributions; correct for any).  The bins are not packed any more: work items are built from
+// (bin offset, records actually written) after the scatter.
+// MEASURED (C2, profiles/r2_time_single_pass.txt): the histogram pass goes (0.120 + 0.038 -> 0.046 ms) but the scatter slows from
+// 0.309 to 0.39 ms -- one L2 atomic per query instead of a shared-memory one, and more resident warps make it slower, not
+// faster (0.41-0.49 ms at 32 warps/SM: the L2 atomic units are the limit) -- 1.266 vs 1.288 ms per step for 1.8x the record
+// scratch.  Within run-to-run noise, so it is OPT-IN (GB_SORT_PASSES=1); the two-pass counting sort stays the default.
+template <typename T, int N, int ORDER, int BCF>
+__global__ void __launch_bounds__(SORT_BLOCK) tile_scatter_capped_kernel(const EvalParams<N> p, u32* __restrict__ cursor, const u32* __restrict__ offs,
+                                                                         const u32* __restrict__ cap, T* __restrict__ rec, u32* __restrict__ over, u32* __restrict__ nover,
+                                                                         i64 per_cta) {
+    if (p.nwork[2] != 0) return;  // coherent batch: the plain kernel takes it
+    int ntot = 1, shift[N];
+#pragma unroll
+    for (int d = 0; d < N; d++) { ntot *= p.ntile[d]; shift[d] = __ffs(p.tile[d]) - 1; }
+    const i64 q0 = (i64)blockIdx.x * per_cta;
+    const i64 q1 = q0 + per_cta < p.nq ? q0 + per_cta : p.nq;
+    const u32 lane = threadIdx.x & 31;
+    for (i64 qb0 = q0; qb0 < q1; qb0 += SORT_ITER) {  // (uniform trip count: the warp votes below need every lane)
+        const i64 qb = qb0 + threadIdx.x;
+        double raw[SORT_UNROLL][N];
+#pragma unroll
+        for (int u = 0; u < SORT_UNROLL; u++) {
+            const i64 q = qb + u * SORT_BLOCK;
+            if (q < q1) {
+#pragma unroll
+                for (int d = 0; d < N; d++) raw[u][d] = load_raw<N>(p, d, q);
+            }
+        }
+        // all the cursor atomics of the iteration in flight before the first result is needed (their round trip is the pass's latency)
+        T x[SORT_UNROLL][N];
+        u32 key[SORT_UNROLL], peers[SORT_UNROLL], base[SORT_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SORT_UNROLL; u++) {
+            const i64 q = qb + u * SORT_BLOCK;
+            key[u] = 0xffffffffu;
+            if (q < q1) {
+#pragma unroll
+                for (int d = 0; d < N; d++) x[u][d] = index_coord<T, N>(p, d, raw[u][d]);
+                key[u] = tile_key<T, N, ORDER, BCF>(p, x[u], shift, ntot);
+            }
+            peers[u] = __match_any_sync(0xffffffffu, key[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < SORT_UNROLL; u++) {
+            base[u] = 0;
+            if (key[u] != 0xffffffffu && lane == (u32)__ffs(peers[u]) - 1) base[u] = atomicAdd(cursor + key[u], (u32)__popc(peers[u]));
+        }
+#pragma unroll
+        for (int u = 0; u < SORT_UNROLL; u++) {
+            const i64 q = qb + u * SORT_BLOCK;
+            const u32 b = __shfl_sync(0xffffffffu, base[u], __ffs(peers[u]) - 1);
+            if (q < q1) {
+                const u32 slot = b + __popc(peers[u] & ((1u << lane) - 1));
+                if (slot < __ldg(cap + key[u])) store_record<T, N>(rec, __ldg(offs + key[u]) + slot, x[u], (u32)q);
+                else over[atomicAdd(nover, 1u)] = (u32)q;  // bin full: the plain path takes the query
+            }
+        }
+    }
+}
+// the queries that found their bin full: plain evaluation from the caller's coordinates, output record at the query's index
+template <typename T, int N, int ORDER, int BCF, int OUTMODE, bool FAST>
+__global__ void __launch_bounds__(EVAL_BLOCK, 2) eval_overflow_kernel(const EvalParams<N> p, const u32* __restrict__ over, const u32* __restrict__ nover) {
+    if (p.nwork[2] != 0) return;
+    const u32 n = *nover;
+    for (u32 i = blockIdx.x * EVAL_BLOCK + threadIdx.x; i < n; i += gridDim.x * EVAL_BLOCK) {
+        const u32 q = over[i];
+        T x[N];
+        load_index_coords<T, N>(p, (i64)q, x);
+        eval_one<T, N, ORDER, BCF, OUTMODE, FAST>(p, x, (i64)q, (i64)q);
     }
 }
 
@@ -1566,6 +1646,10 @@ int tile_offsets(const u32* bh, u32 nbins, u32 nctas, u32* hist, u32* offs, u32*
 int tile_offsets_global(const u32* hist, u32 nbins, u32* offs, u32* cursor, u32* work, u32* nwork, u32 chunk, const TileGeo& geo, cudaStream_t s);
 bool choose_tile(int N, int L, size_t esz, const int* len, i64 nq, bool forced, int* tile, int* ntile);
 u32 sort_smem_bins();  // 12000: per-CTA histograms live in shared memory (<= 48 KB); more tiles: tile_sort_global_kernel
+int tile_capacity(const u32* shist, u32 nbins, const u32* nwork, i64 nq, u32* offs, u32* cap, u32* cursor, cudaStream_t s);
+int tile_items(const u32* cursor, const u32* cap, const u32* offs, u32 nbins, u32* work, u32* nwork, u32 chunk, const TileGeo& geo, cudaStream_t s);
+size_t tile_capacity_bound(i64 nq, i64 nsample, u32 nbins);  // records the bins of tile_capacity can add up to
+bool sort_single_pass();
 u32 coherent_need_percent(bool hinted);  // share (percent) of the probed leaves that must be coherent for the plain path to take the batch; > 100: never
 int make_brick_tensor_map(CUtensorMap* m, int dtype, int N, const void* base, const int* len, const i64* stride, const int* box);
 // Larger batches are evaluated in slices: bounds the record scratch, and keeps the randomly written regions -- the
@@ -1621,7 +1705,28 @@ int launch_tiled(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     constexpr int W = out_words<N>(OUTMODE);
     const bool global_bins = nbins > sort_smem_bins();
     const size_t nbc = global_bins ? 16 : (size_t)nbins * nctas;
-    const size_t rec_bytes = (pitch * (N + 1) * sizeof(T) + 31) & ~(size_t)31;
+    // Where do the brick kernel's output records go?  To the query's sorted slot (coalesced writes, then un-permuted by a random
+    // 32-byte gather) or straight to record q (random full-sector writes hidden under the FP64-bound evaluation, then a
+    // streaming unpack).  GB_OUT_BY_QUERY selects (measured, profiles/README.md).
+    static const int by_query_env = [] { const char* e = getenv("GB_OUT_BY_QUERY"); return e ? atoi(e) : GB_OUT_BY_QUERY_DEFAULT; }();
+    const bool packed = p_in.aos != 0;  // GB_OUT_PACKED: the caller's buffer IS the array of output records, in query order
+    const int by_query = packed ? 1 : by_query_env;
+    // One pass over the batch instead of two (tile_scatter_capped_kernel): bins sized from the probe's sample.
+    const bool single = sort_single_pass() && !global_bins && by_query != 0;
+    size_t nrec = pitch;
+    if (single) {  // the probe's sample size, as the kernel will count it
+        i64 ns = 0;
+        for (u32 c = 0; c < nctas; c++) {
+            const i64 q0 = (i64)c * per_cta, q1 = std::min<i64>(q0 + per_cta, p.nq);
+            if (q0 >= q1) continue;
+            const i64 stride = ((q1 - q0) / SORT_UNROLL) & ~(i64)(SORT_BLOCK - 1);
+            for (int u = 0; u < SORT_UNROLL; u++)
+                if (u == 0 || stride > 0) ns += std::max<i64>(0, std::min<i64>(SORT_BLOCK, q1 - (q0 + u * stride)));
+        }
+        nrec = (tile_capacity_bound(p.nq, ns, nbins) + 15) & ~(size_t)15;
+        if (nrec >= (size_t)0xfffffff0u) return fail(GB_ERR_ARG, "tiled evaluation: batch slice too large");
+    }
+    const size_t rec_bytes = (nrec * (N + 1) * sizeof(T) + 31) & ~(size_t)31;
     const size_t out_bytes = (pitch * W * sizeof(T) + 31) & ~(size_t)31;
     const size_t words = (pitch + 16) + 4 * max_items + 2 * nbc + 2 * (size_t)(nbins + 4) + 8;
     AsyncBuf guard(s);  // released on every exit path
@@ -1636,7 +1741,7 @@ int launch_tiled(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     u32* boff = bh + nbc;
     u32* hist = boff + nbc;
     u32* offs = hist + (nbins + 4);
-    u32* nwork = offs + (nbins + 4);  // [0] items, [1] ticket counter, [2] coherent flag, [3..5] the probe's counters
+    u32* nwork = offs + (nbins + 4);  // [0] items, [1] ticket counter, [2] coherent flag, [3..5] the probe's counters, [6] queries sampled, [7] overflow count
     TileGeo geo;
     geo.N = N;
     for (int d = 0; d < MAXD; d++) { geo.tile[d] = d < N ? p.tile[d] : 1; geo.ntile[d] = d < N ? p.ntile[d] : 1; }
@@ -1649,13 +1754,8 @@ int launch_tiled(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     if (!tma_off && make_brick_tensor_map(&tmap, dtype_of<T>::value, N, p.coefs, p.len, p.stride, box) == GB_OK) p.use_tma = 1;
     p.work = work;
     p.nwork = nwork;
-    // Where do the brick kernel's output records go?  To the query's sorted slot (coalesced writes, then un-permuted by a random
-    // 32-byte gather) or straight to record q (random full-sector writes hidden under the FP64-bound evaluation, then a
-    // streaming unpack).  GB_OUT_BY_QUERY selects (measured, profiles/README.md).
-    static const int by_query_env = [] { const char* e = getenv("GB_OUT_BY_QUERY"); return e ? atoi(e) : GB_OUT_BY_QUERY_DEFAULT; }();
-    const bool packed = p_in.aos != 0;  // GB_OUT_PACKED: the caller's buffer IS the array of output records, in query order
-    const int by_query = packed ? 1 : by_query_env;
     p.by_query = by_query;
+    u32* over = inv;  // (single pass: the overflow list lives where the inverse permutation would)
     if (by_query) inv = nullptr;
     GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per device, cheap
     int bt = 0;
@@ -1667,14 +1767,28 @@ int launch_tiled(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     const bool probe = (!(flags & GB_TILED) || (flags & GB_SORTED)) && need > 0 && need <= 100;  // (GB_TILED | GB_SORTED: forced onto this path, probe on)
     prof_mark(0, s);
     GB_CUDA(cudaMemsetAsync(nwork, 0, 8 * sizeof(u32), s));
-    if (probe) {
+    if (single) GB_CUDA(cudaMemsetAsync(hist, 0, (size_t)nbins * sizeof(u32), s));
+    if (probe || single) {  // (single pass without the probe's verdict: a share no batch reaches)
         u32 vmax = 4;
         for (int d = 0; d < N; d++) vmax *= (u32)p.tile[d];
-        coherence_probe_kernel<T, N, ORDER, BCF><<<nctas, SORT_BLOCK, 0, s>>>(p, nwork, per_cta, vmax, need);
+        coherence_probe_kernel<T, N, ORDER, BCF><<<nctas, SORT_BLOCK, 0, s>>>(p, nwork, per_cta, vmax, probe ? need : 101u, single ? hist : nullptr);
         count_launch();
     }
     int rc;
-    if (global_bins) {  // hist doubles as the write cursors after the scan
+    if (single) {  // bh: bin capacities, boff: write cursors
+        prof_mark(1, s);
+        rc = tile_capacity(hist, nbins, nwork, p.nq, offs, bh, boff, s);
+        if (rc) return rc;
+        prof_mark(2, s);
+        // (no per-CTA state: more, smaller CTAs than the two-pass sort -- GB_SCATTER_CTAS per SM -- to cover the cursor round trips)
+        static const int sc_per_sm = [] { const char* e = getenv("GB_SCATTER_CTAS"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= 32 ? v : 16; }();
+        const u32 sc_ctas = (u32)std::max<i64>(1, std::min<i64>((i64)num_sms() * sc_per_sm, (p.nq + SORT_ITER - 1) / SORT_ITER));
+        const i64 sc_per = ((p.nq + sc_ctas - 1) / sc_ctas + SORT_BLOCK - 1) / SORT_BLOCK * SORT_BLOCK;
+        tile_scatter_capped_kernel<T, N, ORDER, BCF><<<sc_ctas, SORT_BLOCK, 0, s>>>(p, boff, offs, bh, rec, over, nwork + 7, sc_per);
+        count_launch();
+        rc = tile_items(boff, bh, offs, nbins, work, nwork, EVAL_CHUNK, geo, s);
+        if (rc) return rc;
+    } else if (global_bins) {  // hist doubles as the write cursors after the scan
         GB_CUDA(cudaMemsetAsync(hist, 0, (size_t)nbins * sizeof(u32), s));
         tile_sort_global_kernel<T, N, ORDER, BCF, false><<<nctas, SORT_BLOCK, 0, s>>>(p, hist, rec, inv, per_cta);
         count_launch();
@@ -1711,6 +1825,10 @@ int launch_tiled(const EvalParams<N>& p_in, int flags, cudaStream_t s) {
     kern<<<(int)grid, BRICK_BLOCK, smem, s>>>(p, rec, defer, tmap);
     prof_mark(4, s);
     eval_deferred_kernel<T, N, ORDER, BCF, OUTMODE, FAST><<<num_sms() * 2, EVAL_BLOCK, 0, s>>>(p, rec, defer);
+    if (single) {  // the queries that found their bin full
+        eval_overflow_kernel<T, N, ORDER, BCF, OUTMODE, FAST><<<num_sms() * 2, EVAL_BLOCK, 0, s>>>(p, over, nwork + 7);
+        count_launch();
+    }
     prof_mark(5, s);
     // ... and the records go back to the caller's order and arrays
     const int ugrid = (int)std::min<i64>((p.nq + 255) / 256, (i64)num_sms() * 32);

@@ -3,6 +3,7 @@
 // compute the keys and evaluate the bricks.
 #include <algorithm>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 
@@ -138,6 +139,135 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const u32* __restrict__
         __syncthreads();
     }
     if (t == 1023) { nwork[0] = s_base[1]; nwork[1] = 0; }  // item count, and the counter CTAs pull items from
+}
+
+// ---- single-pass scatter (eval.cuh: tile_scatter_capped_kernel) --------------------------------------------------------
+// exclusive scan of one value per thread across a 1024-thread CTA; s_w[32] scratch; returns the exclusive prefix, total in s_w[31]
+__device__ __forceinline__ u32 cta_scan_1024(u32 v, u32* s_w) {
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 a = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((int)lane >= o) inc += a;
+    }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        u32 w = s_w[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 a = __shfl_up_sync(0xffffffffu, w, o);
+            if ((int)lane >= o) w += a;
+        }
+        s_w[lane] = w;
+    }
+    __syncthreads();
+    return (warp ? s_w[warp - 1] : 0u) + inc - v;
+}
+// room of a bin whose sample count is h: the estimate plus four standard deviations of the sampling noise (the count of a
+// bin in the sample is ~Poisson(h)), rounded up.  Shared by the kernel and the host bound.
+__host__ __device__ __forceinline__ u32 bin_capacity(u32 h, float scale) { return (u32)(scale * ((float)h + 4.0f * sqrtf((float)h + 1.0f) + 4.0f)) + 1u; }
+// cap[b], offs[b] (exclusive scan of cap), cursor[b] = 0 from the probe's sampled histogram (nwork[6] = queries sampled)
+__global__ void __launch_bounds__(1024) tile_capacity_kernel(const u32* __restrict__ shist, u32 nbins, const u32* __restrict__ nwork, i64 nq, u32* __restrict__ offs,
+                                                             u32* __restrict__ cap, u32* __restrict__ cursor) {
+    if (nwork[2] != 0) return;
+    __shared__ u32 s_w[32], s_base;
+    const u32 t = threadIdx.x;
+    if (t == 0) s_base = 0;
+    __syncthreads();
+    const u32 ns = nwork[6] ? nwork[6] : 1u;
+    const float scale = (float)((double)nq / (double)ns);
+    for (u32 seg = 0; seg < nbins; seg += 1024 * SCAN_PER) {
+        const u32 nb = min(nbins - seg, 1024u * SCAN_PER);
+        const u32 per = (nb + 1023) / 1024;
+        const u32 b0 = min(t * per, nb);
+        u32 c[SCAN_PER], sum = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_PER; k++) {
+            const u32 b = b0 + k;
+            c[k] = ((u32)k < per && b < nb) ? bin_capacity(shist[seg + b], scale) : 0u;
+            sum += c[k];
+        }
+        u32 o = s_base + cta_scan_1024(sum, s_w);
+#pragma unroll
+        for (int k = 0; k < SCAN_PER; k++) {
+            const u32 b = b0 + k;
+            if ((u32)k < per && b < nb) {
+                offs[seg + b] = o;
+                cap[seg + b] = c[k];
+                cursor[seg + b] = 0;
+                o += c[k];
+            }
+        }
+        __syncthreads();
+        if (t == 1023) s_base += s_w[31];
+        __syncthreads();
+    }
+}
+// work items after the scatter: bin b holds min(cursor[b], cap[b]) records from offs[b]
+__global__ void __launch_bounds__(1024) tile_items_kernel(const u32* __restrict__ cursor, const u32* __restrict__ cap, const u32* __restrict__ offs, u32 nbins,
+                                                          u32* __restrict__ work, u32* __restrict__ nwork, u32 chunk, const TileGeo geo) {
+    if (nwork[2] != 0) return;
+    __shared__ u32 s_w[32], s_base;
+    const u32 t = threadIdx.x;
+    if (t == 0) s_base = 0;
+    __syncthreads();
+    for (u32 seg = 0; seg < nbins; seg += 1024 * SCAN_PER) {
+        const u32 nb = min(nbins - seg, 1024u * SCAN_PER);
+        const u32 per = (nb + 1023) / 1024;
+        const u32 b0 = min(t * per, nb);
+        u32 h[SCAN_PER], itm = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_PER; k++) {
+            const u32 b = b0 + k;
+            h[k] = ((u32)k < per && b < nb) ? min(cursor[seg + b], cap[seg + b]) : 0u;
+            itm += (h[k] + chunk - 1) / chunk;
+        }
+        u32 w = s_base + cta_scan_1024(itm, s_w);
+#pragma unroll
+        for (int k = 0; k < SCAN_PER; k++) {
+            const u32 b = b0 + k;
+            if ((u32)k < per && b < nb) {
+                const u32 o = offs[seg + b];
+                const u32 n = (h[k] + chunk - 1) / chunk;
+                const u32 sz = n ? (h[k] + n - 1) / n : 0;
+                for (u32 j = 0; j < n; j++) {
+                    reinterpret_cast<uint4*>(work)[w] = tile_item(geo, seg + b, nbins - 1, o + j * sz, o + min((j + 1) * sz, h[k]));
+                    w++;
+                }
+            }
+        }
+        __syncthreads();
+        if (t == 1023) s_base += s_w[31];
+        __syncthreads();
+    }
+    if (t == 1023) { nwork[0] = s_base; nwork[1] = 0; }
+}
+int tile_capacity(const u32* shist, u32 nbins, const u32* nwork, i64 nq, u32* offs, u32* cap, u32* cursor, cudaStream_t s) {
+    tile_capacity_kernel<<<1, 1024, 0, s>>>(shist, nbins, nwork, nq, offs, cap, cursor);
+    count_launch();
+    GB_CUDA(cudaGetLastError());
+    return GB_OK;
+}
+int tile_items(const u32* cursor, const u32* cap, const u32* offs, u32 nbins, u32* work, u32* nwork, u32 chunk, const TileGeo& geo, cudaStream_t s) {
+    tile_items_kernel<<<1, 1024, 0, s>>>(cursor, cap, offs, nbins, work, nwork, chunk, geo);
+    count_launch();
+    GB_CUDA(cudaGetLastError());
+    return GB_OK;
+}
+// Upper bound of sum_b bin_capacity(h_b) over any histogram with sum h_b = nsample: sum sqrt(h_b + 1) <= sqrt(nbins (nsample + nbins)) (Cauchy-Schwarz).
+size_t tile_capacity_bound(i64 nq, i64 nsample, u32 nbins) {
+    if (nsample < 1) nsample = 1;
+    const double scale = (double)nq / (double)nsample * (1.0 + 1e-6);  // the kernel's scale is rounded to float
+    const double b = (double)nbins;
+    return (size_t)(scale * ((double)nsample + 4.0 * sqrt(b * ((double)nsample + b)) + 4.0 * b) + 2.0 * b + 64.0);
+}
+// GB_SORT_PASSES=1 selects the single-pass scatter where it applies (measured 2 % faster on C2 for 1.8x the record scratch:
+// opt-in); default: the two-pass counting sort (histogram, scatter)
+bool sort_single_pass() {
+    static const bool v = [] { const char* e = getenv("GB_SORT_PASSES"); return e && atoi(e) == 1; }();
+    return v;
 }
 
 // hist[b] = sum over CTAs of bh[b][cta]; one warp per bin.

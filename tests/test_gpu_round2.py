@@ -132,6 +132,40 @@ print("ok")
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
 
 
+def test_single_pass_scatter(gb, oracle):
+    """GB_SORT_PASSES=1 (child process): bins sized from the probe's sample, one scatter pass, overflow list.  A uniform
+    batch (no or few overflows), and a batch whose SAMPLED positions (the first 256 of every 1024 queries, see
+    coherence_probe_kernel) all sit in one corner while the rest is uniform -- nearly every query finds its bin full and
+    goes through the overflow kernel.  Both bit-identical to the oracle, packed output included."""
+    code = r"""
+import sys; sys.path.insert(0, %r)
+import numpy as np, torch
+import grid_jl_b200 as gb
+from oracle import oracle as O
+rng = np.random.default_rng(23)
+for dtype, shape, bc, order in ((np.float64, (66, 41, 37), "nan", "cubic"), (np.float32, (130, 90), "reflect", "quadratic"), (np.float64, (40, 36, 70), "periodic", "quadratic")):
+    A = rng.standard_normal(shape).astype(dtype)
+    BC = dict(nan=gb.BCnan, reflect=gb.BCreflect, periodic=gb.BCperiodic)[bc]
+    g = gb.InterpGrid(A, BC, gb.InterpCubic if order == "cubic" else gb.InterpQuadratic)
+    co = O.make_coefs(A, bc, order)
+    nq = 200_000
+    Xu = (0.5 + rng.random((nq, len(shape))) * np.array(shape)).astype(dtype)
+    Xs = Xu.copy()
+    Xs[(np.arange(nq) %% 1024) < 256] = 1.25
+    for X in (Xu, Xs, Xu[:777], Xu[:4097]):
+        ov, og, _, _ = O.evaluate(co, bc, order, X, 3, raise_invalid=False)
+        v, gr, _ = g._eval(torch.from_numpy(X).cuda(), 3, tiled=True)
+        assert np.array_equal(v.cpu().numpy(), ov, equal_nan=True) and np.array_equal(gr.cpu().numpy(), og, equal_nan=True)
+        rec = gb.valgrad_packed(g, torch.from_numpy(X).cuda(), tiled=True) if hasattr(gb, "valgrad_packed") else None
+        if rec is not None:
+            r = rec.cpu().numpy()
+            assert np.array_equal(r[:, 0], ov, equal_nan=True) and np.array_equal(r[:, 1:1 + len(shape)], og, equal_nan=True)
+print("ok")
+""" % ROOT
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, GB_SORT_PASSES="1"), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("bc,order", [("nan", "quadratic"), ("reflect", "quadratic"), ("periodic", "quadratic"), ("nearest", "quadratic"), ("nan", "cubic")])
 def test_fast_prefilter_kernels(gb, oracle, dtype, bc, order):
