@@ -850,9 +850,19 @@ int eval_host(const gb_grid* g, int out_mask, int outmode, i64 nq, const void* c
         cu(cudaMemsetAsync(d_bad, 0xFF, sizeof(u64), slots[0].s), "cudaMemsetAsync");
         cu(cudaStreamSynchronize(slots[0].s), "cudaStreamSynchronize");
     }
+    // GB_EVAL_TRACE=1: CUDA events around every chunk's copy-in, evaluation and copy-out; the timeline goes to stderr
+    // (profiles/trace_e2e.py, profiles/r2_trace_e2e.txt)
+    static const bool trace = [] { const char* e = getenv("GB_EVAL_TRACE"); return e && *e == '1'; }();
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, st); tev.push_back(e); }
+    };
     for (i64 q0 = 0, c = 0; q0 < nq && rc == GB_OK; q0 += chunk, c++) {
         Slot& sl = slots[c % nslot];
         const i64 n = std::min(chunk, nq - q0);
+        mark(sl.s);
         EvalCall call;
         call.g = g; call.outmode = outmode; call.flags = flags; call.xdtype = xdtype; call.affine = affine;
         call.nq = n; call.q0 = q0; call.first_invalid = d_bad;
@@ -870,15 +880,18 @@ int eval_host(const gb_grid* g, int out_mask, int outmode, i64 nq, const void* c
         call.val = sl.v; call.grad = sl.gr; call.hess = sl.h;
         call.packed = packed;
         if (rc != GB_OK) break;
+        mark(sl.s);
         rc = launch_eval(call, sl.s);
         if (rc != GB_OK) break;
+        mark(sl.s);
         if (packed) {
             cu(cudaMemcpyAsync((char*)val + (size_t)q0 * packed * es, sl.v, (size_t)n * packed * es, cudaMemcpyDeviceToHost, sl.s), "cudaMemcpyAsync D2H");
-            continue;
+        } else {
+            if (sl.v) cu(cudaMemcpyAsync((char*)val + (size_t)q0 * es, sl.v, (size_t)n * es, cudaMemcpyDeviceToHost, sl.s), "cudaMemcpyAsync D2H");
+            if (sl.gr) cu(cudaMemcpyAsync((char*)grad + (size_t)q0 * N * es, sl.gr, (size_t)n * N * es, cudaMemcpyDeviceToHost, sl.s), "cudaMemcpyAsync D2H");
+            if (sl.h) cu(cudaMemcpyAsync((char*)hess + (size_t)q0 * N * N * es, sl.h, (size_t)n * N * N * es, cudaMemcpyDeviceToHost, sl.s), "cudaMemcpyAsync D2H");
         }
-        if (sl.v) cu(cudaMemcpyAsync((char*)val + (size_t)q0 * es, sl.v, (size_t)n * es, cudaMemcpyDeviceToHost, sl.s), "cudaMemcpyAsync D2H");
-        if (sl.gr) cu(cudaMemcpyAsync((char*)grad + (size_t)q0 * N * es, sl.gr, (size_t)n * N * es, cudaMemcpyDeviceToHost, sl.s), "cudaMemcpyAsync D2H");
-        if (sl.h) cu(cudaMemcpyAsync((char*)hess + (size_t)q0 * N * N * es, sl.h, (size_t)n * N * N * es, cudaMemcpyDeviceToHost, sl.s), "cudaMemcpyAsync D2H");
+        mark(sl.s);
     }
     for (int i = 0; i < nslot; i++) {
         Slot& sl = slots[i];
@@ -889,6 +902,15 @@ int eval_host(const gb_grid* g, int out_mask, int outmode, i64 nq, const void* c
         if (sl.h) cudaFreeAsync(sl.h, sl.s);
         cu(cudaStreamSynchronize(sl.s), "cudaStreamSynchronize");
     }
+    if (trace && tev.size() >= 4) {  // (every slot stream has been synchronised above)
+        fprintf(stderr, "[gb_eval trace] chunk: copy-in start .. end | eval end | copy-out end   (ms since the first copy-in)\n");
+        for (size_t c = 0; c + 3 < tev.size(); c += 4) {
+            float t[4] = {0, 0, 0, 0};
+            for (int k = 0; k < 4; k++) cudaEventElapsedTime(&t[k], tev[0], tev[c + k]);
+            fprintf(stderr, "[gb_eval trace] %2zu: %7.3f .. %7.3f | %7.3f | %7.3f\n", c / 4, t[0], t[1], t[2], t[3]);
+        }
+    }
+    for (cudaEvent_t e : tev) cudaEventDestroy(e);
     if (first_invalid) *first_invalid = -1;
     if (d_bad) {
         u64 bad = ~0ull;
