@@ -87,6 +87,19 @@ template <typename T> __device__ __forceinline__ T exact_div(T a, T d, T rd) {
     return a / d;
 }
 
+// x / 6 of the cubic weights (src/interp.jl: `/6`), bit for bit, in three operations instead of the ~12 plus a special-case
+// branch of the IEEE division sequence -- six of them per 3-D cubic query on the FP64-bound brick kernel.  Correctly rounded for
+// every finite x away from the subnormal range (the weights' arguments are 0 or >= 2^-159): x is a multiple of 4 or 8 ulp(q), so
+// x / 6 is a multiple of ulp(q) / 3 -- never within ulp(q) / 6 of a rounding midpoint; r is exact; q + r * RN(1/6) is within
+// 2^-53 ulp(q) of x / 6.  Checked against the hardware division on 10^9 numerators by tests/native/div6_check.c.  (x = -0 would
+// give +0; the arguments are products of non-negative factors.)
+__host__ __device__ __forceinline__ double div6_exact(double x) {
+    const double z = 1.0 / 6.0;
+    const double q = x * z;
+    const double r = fma(-6.0, q, x);
+    return fma(r, z, q);
+}
+
 // ---- brick geometry of the tiled evaluation (eval.cuh, eval_tile.cu) -------------------------------
 // fixed leading tile extents (cells), so that brick strides are compile-time constants; the extent
 // along the LAST dimension is chosen at run time (choose_tile): N=1 -, N=2 64, N=3 16x16, N=4 8x8x8

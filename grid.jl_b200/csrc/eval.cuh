@@ -208,10 +208,10 @@ __device__ __forceinline__ void weights(double dx, double (&w)[ORDER + 1], doubl
         if (H) { h[0] = 1.0; h[1] = -2.0; h[2] = 1.0; }
     } else {
         double t = 1 - dx, u = dx - 1, d2 = dx * dx;
-        w[0] = FW ? ((t * t) * t) * (1.0 / 6.0) : ((t * t) * t) / 6;
+        w[0] = FW ? ((t * t) * t) * (1.0 / 6.0) : div6_exact((t * t) * t);
         w[1] = 2.0 / 3.0 - (d2 * (2 - dx)) / 2;
         w[2] = 2.0 / 3.0 - ((u * u) * (1 + dx)) / 2;
-        w[3] = FW ? (d2 * dx) * (1.0 / 6.0) : (d2 * dx) / 6;
+        w[3] = FW ? (d2 * dx) * (1.0 / 6.0) : div6_exact(d2 * dx);
         if (G) {
             g[0] = (-(t * t)) / 2;
             g[1] = (3 * d2) / 2 - 2 * dx;

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import grid_jl_b200 as gb
 
-n, nq = 256, 10_000_000
+n, nq = 256, int(float(os.environ.get("NQ", "1e7")))
 A = gb.jl_empty((n, n, n), torch.float64); gb.synth_uniform(A, 2)
 G = gb.InterpGrid(A, gb.BCnan, gb.InterpCubic)
 X = torch.empty((nq, 3), dtype=torch.float64, device="cuda"); gb.synth_uniform(X, 12, lo=1.0, hi=float(n))
