@@ -7,6 +7,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -785,6 +787,183 @@ struct HostPins {
     }
 };
 
+// ---- pageable host buffers ---------------------------------------------------------------------------------------------
+// A Julia Array or a numpy array is pageable memory: cudaMemcpyAsync then goes through the driver's single staging thread and
+// blocks the caller (measured on the C2 batch: 40-46 ms against 7.5 ms with pinned buffers), and page-locking the caller's
+// ranges for one call costs more than it saves (cudaHostRegister: ~9 MB per ms).  So the library keeps its own small pinned
+// staging slots (allocated once, two per worker) and a few host threads do what the driver's one thread does: worker w takes
+// chunks w, w + T, ... of the batch -- memcpy of the chunk into a pinned slot, H2D, evaluation, D2H into a pinned slot, memcpy
+// out -- double-buffered, so its copies overlap its own GPU work and every other worker's.  profiles/README.md has the numbers.
+struct StageSlot {
+    void *in = nullptr, *out = nullptr;
+    size_t in_bytes = 0, out_bytes = 0;
+};
+struct StageCache {
+    std::mutex mu;  // one staged call at a time
+    std::vector<StageSlot> slots;
+};
+StageCache g_stage;
+bool is_pageable(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+int stage_threads() {
+    static const int v = [] {
+        const char* e = getenv("GB_HOST_THREADS");
+        if (e) return std::max(0, std::min(32, atoi(e)));  // 0: the driver's pageable copies
+        const unsigned hc = std::thread::hardware_concurrency();
+        return (int)std::max(1u, std::min(8u, hc / 2));
+    }();
+    return v;
+}
+int eval_host_staged(const gb_grid* g, int out_mask, int outmode, i64 nq, const void* const* xcols, const void* xaos, int xdtype, const double* affine,
+                     void* val, void* grad, void* hess, int flags, int64_t* first_invalid, int nthreads) {
+    const int N = g->ndim;
+    const size_t xs = esize(xdtype), es = esize(g->dtype) * (size_t)g->nchan;
+    const int packed = packed_words(g, out_mask, outmode);
+    static const i64 chunk_env = [] {
+        const char* e = getenv("GB_STAGE_CHUNK");
+        long long v = e ? atoll(e) : 0;
+        return (i64)(v > 0 ? v : (1ll << 18));
+    }();
+    const i64 chunk = std::max<i64>(1, std::min<i64>(chunk_env, nq));
+    const i64 nchunk = (nq + chunk - 1) / chunk;
+    const int T = (int)std::max<i64>(1, std::min<i64>(nthreads, nchunk));
+    // one output slot: [val | grad | hess] or the packed records
+    const size_t vw = packed ? (size_t)packed : ((out_mask & GB_OUT_VAL) ? 1 : 0), gw = packed ? 0 : ((out_mask & GB_OUT_GRAD) ? (size_t)N : 0),
+                 hw = packed ? 0 : ((out_mask & GB_OUT_HESS) ? (size_t)N * N : 0);
+    const size_t in_bytes = (size_t)chunk * N * xs, out_bytes = (size_t)chunk * (vw + gw + hw) * es;
+    const size_t off_g = (size_t)chunk * vw * es, off_h = off_g + (size_t)chunk * gw * es;
+    std::lock_guard<std::mutex> lock(g_stage.mu);
+    if (g_stage.slots.size() < (size_t)2 * T) g_stage.slots.resize((size_t)2 * T);
+    for (int i = 0; i < 2 * T; i++) {  // (grown lazily, kept for the life of the process: a few MB per slot)
+        StageSlot& sl = g_stage.slots[i];
+        if (sl.in_bytes < in_bytes) {
+            if (sl.in) cudaFreeHost(sl.in);
+            sl.in = nullptr; sl.in_bytes = 0;
+            if (cudaHostAlloc(&sl.in, in_bytes, cudaHostAllocDefault) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaHostAlloc (staging)");
+            sl.in_bytes = in_bytes;
+        }
+        if (sl.out_bytes < out_bytes) {
+            if (sl.out) cudaFreeHost(sl.out);
+            sl.out = nullptr; sl.out_bytes = 0;
+            if (cudaHostAlloc(&sl.out, out_bytes, cudaHostAllocDefault) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaHostAlloc (staging)");
+            sl.out_bytes = out_bytes;
+        }
+    }
+    u64* d_bad = nullptr;
+    if (first_invalid && g->bc == GB_BC_NIL) {
+        GB_CUDA(cudaMalloc((void**)&d_bad, sizeof(u64)));
+        GB_CUDA(cudaMemset(d_bad, 0xFF, sizeof(u64)));
+    }
+    std::vector<int> rcs(T, GB_OK);
+    std::vector<std::string> msgs(T);
+    auto worker = [&](int w) {
+        int rc = GB_OK;
+        auto cu = [&](cudaError_t e, const char* what) {
+            if (e != cudaSuccess && rc == GB_OK) rc = cuda_fail(e, what);
+            return e == cudaSuccess;
+        };
+        cu(cudaSetDevice(g->device), "cudaSetDevice");
+        cudaStream_t st = nullptr;
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        void *din[2] = {nullptr, nullptr}, *dout[2] = {nullptr, nullptr};
+        if (rc == GB_OK) cu(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate");
+        if (rc == GB_OK && g->ready) cu(cudaStreamWaitEvent(st, g->ready, 0), "cudaStreamWaitEvent");
+        for (int i = 0; i < 2 && rc == GB_OK; i++) {
+            cu(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming | cudaEventBlockingSync), "cudaEventCreate");
+            cu(cudaMallocAsync(&din[i], in_bytes, st), "cudaMallocAsync");
+            cu(cudaMallocAsync(&dout[i], out_bytes, st), "cudaMallocAsync");
+        }
+        i64 pend[2] = {-1, -1};
+        auto copy_out = [&](int sl) {  // pinned slot -> the caller's arrays
+            const i64 c = pend[sl];
+            if (c < 0) return;
+            cu(cudaEventSynchronize(ev[sl]), "cudaEventSynchronize");
+            const i64 q0 = c * chunk, n = std::min(chunk, nq - q0);
+            const char* src = (const char*)g_stage.slots[2 * w + sl].out;
+            if (rc == GB_OK) {
+                if (vw) std::memcpy((char*)val + (size_t)q0 * vw * es, src, (size_t)n * vw * es);
+                if (gw) std::memcpy((char*)grad + (size_t)q0 * gw * es, src + off_g, (size_t)n * gw * es);
+                if (hw) std::memcpy((char*)hess + (size_t)q0 * hw * es, src + off_h, (size_t)n * hw * es);
+            }
+            pend[sl] = -1;
+        };
+        int k = 0;
+        for (i64 c = w; c < nchunk && rc == GB_OK; c += T, k++) {
+            const int sl = k & 1;
+            copy_out(sl);  // (waits for the chunk that used this slot two rounds ago)
+            const i64 q0 = c * chunk, n = std::min(chunk, nq - q0);
+            char* pin = (char*)g_stage.slots[2 * w + sl].in;
+            EvalCall call;
+            call.g = g; call.outmode = outmode; call.flags = flags; call.xdtype = xdtype; call.affine = affine;
+            call.nq = n; call.q0 = q0; call.first_invalid = d_bad;
+            if (xaos) {
+                std::memcpy(pin, (const char*)xaos + (size_t)q0 * N * xs, (size_t)n * N * xs);
+                for (int d = 0; d < N; d++) call.xp[d] = (const char*)din[sl] + (size_t)d * xs;
+                call.xqs = N;
+            } else {
+                for (int d = 0; d < N; d++) {
+                    std::memcpy(pin + (size_t)d * n * xs, (const char*)xcols[d] + (size_t)q0 * xs, (size_t)n * xs);
+                    call.xp[d] = (const char*)din[sl] + (size_t)d * n * xs;
+                }
+                call.xqs = 1;
+            }
+            cu(cudaMemcpyAsync(din[sl], pin, (size_t)n * N * xs, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync H2D");
+            call.val = vw ? dout[sl] : nullptr;
+            call.grad = gw ? (char*)dout[sl] + off_g : nullptr;
+            call.hess = hw ? (char*)dout[sl] + off_h : nullptr;
+            call.packed = packed;
+            if (rc != GB_OK) break;
+            rc = launch_eval(call, st);
+            if (rc != GB_OK) break;
+            char* pout = (char*)g_stage.slots[2 * w + sl].out;
+            if (vw) cu(cudaMemcpyAsync(pout, dout[sl], (size_t)n * vw * es, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync D2H");
+            if (gw) cu(cudaMemcpyAsync(pout + off_g, (char*)dout[sl] + off_g, (size_t)n * gw * es, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync D2H");
+            if (hw) cu(cudaMemcpyAsync(pout + off_h, (char*)dout[sl] + off_h, (size_t)n * hw * es, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync D2H");
+            cu(cudaEventRecord(ev[sl], st), "cudaEventRecord");
+            pend[sl] = c;
+        }
+        copy_out(k & 1);        // the older of the two chunks still in flight ...
+        copy_out((k & 1) ^ 1);  // ... and the last one
+        if (st) {
+            for (int i = 0; i < 2; i++) {
+                if (din[i]) cudaFreeAsync(din[i], st);
+                if (dout[i]) cudaFreeAsync(dout[i], st);
+            }
+            cudaStreamSynchronize(st);
+            cudaStreamDestroy(st);
+        }
+        for (int i = 0; i < 2; i++)
+            if (ev[i]) cudaEventDestroy(ev[i]);
+        rcs[w] = rc;
+        if (rc != GB_OK) msgs[w] = gb_last_error();
+    };
+    std::vector<std::thread> th;
+    for (int w = 1; w < T; w++) th.emplace_back(worker, w);
+    worker(0);
+    for (auto& t : th) t.join();
+    int rc = GB_OK;
+    for (int w = 0; w < T && rc == GB_OK; w++)
+        if (rcs[w] != GB_OK) rc = fail(rcs[w], msgs[w]);
+    if (first_invalid) *first_invalid = -1;
+    if (d_bad) {
+        u64 bad = ~0ull;
+        if (cudaMemcpy(&bad, d_bad, sizeof(u64), cudaMemcpyDeviceToHost) != cudaSuccess && rc == GB_OK) rc = cuda_fail(cudaGetLastError(), "cudaMemcpy");
+        cudaFree(d_bad);
+        if (rc == GB_OK && bad != ~0ull) {
+            *first_invalid = (int64_t)bad;
+            rc = fail(GB_ERR_INVALID_LOCATION, "Invalid location");
+        }
+    }
+    return rc;
+}
+
 // Host-resident evaluation: chunks of the batch flow H2D -> kernel -> D2H over a ring of streams so
 // PCIe traffic in both directions overlaps the kernels.
 int eval_host(const gb_grid* g, int out_mask, int outmode, i64 nq, const void* const* xcols, const void* xaos, int xdtype,
@@ -797,6 +976,14 @@ int eval_host(const gb_grid* g, int out_mask, int outmode, i64 nq, const void* c
         return (i64)(v > 0 ? v : (1ll << 20));
     }();
     const i64 chunk = std::max<i64>(1, std::min<i64>(chunk_env, nq));
+    // pageable buffers, a batch worth the threads: the library's own pinned staging slots (eval_host_staged)
+    {
+        static const int reg_env0 = [] { const char* e = getenv("GB_HOST_REGISTER"); return e ? atoi(e) : 0; }();
+        const int nt = stage_threads();
+        if (nt > 0 && reg_env0 != 1 && nq >= (1ll << 19) && is_pageable(xaos ? xaos : xcols[0]) &&
+            is_pageable(val ? val : (grad ? grad : hess)))
+            return eval_host_staged(g, out_mask, outmode, nq, xcols, xaos, xdtype, affine, val, grad, hess, flags, first_invalid, nt);
+    }
     // Pageable host buffers (a Julia Array, a numpy array): every cudaMemcpyAsync then goes through the driver's staging
     // buffer and blocks the host, so the chunks stop overlapping (measured on C2: 44 ms against 7.7 ms with pinned buffers).
     // Page-locking the caller's ranges for the duration of ONE call does not pay (cudaHostRegister pins ~9 MB per ms on the

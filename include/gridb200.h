@@ -172,7 +172,11 @@ int gb_pad1(int dtype, int ndim, const int64_t* dims, const void* in, double fil
  * val/grad/hess may be NULL when not in out_mask.  Invalid locations produce NaN in every
  * requested output; for GB_BC_NIL the call additionally returns GB_ERR_INVALID_LOCATION and the
  * index of the first offending query in *first_invalid (-1 if none; pass NULL to skip the check
- * and keep a GB_DEVICE call fully asynchronous). */
+ * and keep a GB_DEVICE call fully asynchronous).
+ * mem == GB_HOST: the batch is streamed in chunks (copy-in, evaluation, copy-out overlapped).  Pinned buffers
+ * (gb_host_alloc_pinned / gb_host_register) run at the PCIe rate; pageable buffers of 2^19 queries or more are staged by
+ * the library through its own pinned slots with several host threads (environment: GB_HOST_THREADS, 0 = the driver's
+ * pageable copies; GB_EVAL_CHUNK / GB_STAGE_CHUNK = queries per chunk; GB_EVAL_TRACE=1 prints the chunk timeline). */
 int gb_eval(const gb_grid* g, int out_mask, int64_t nq, const void* x, int xdtype, int64_t x_qstride,
             int64_t x_dstride, const double* affine, void* val, void* grad, void* hess, int mem, int flags,
             int64_t* first_invalid, void* stream);

@@ -132,6 +132,45 @@ print("ok")
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
 
 
+def test_pageable_host_buffers_staged_path(gb):
+    """Pageable (numpy) host buffers above 2^19 queries go through the library's pinned staging slots with several host threads
+    (abi.cu: eval_host_staged).  Same bits as the device-resident call: AoS and column inputs, Float32 queries, value /
+    gradient / Hessian / packed outputs, a multi-valued grid, a ragged last chunk, and BCnil's first invalid query."""
+    import torch
+
+    rng = np.random.default_rng(41)
+    nq = (1 << 19) + 70_001
+    A = rng.standard_normal((40, 36, 30))
+    g = gb.InterpGrid(A, gb.BCnan, gb.InterpCubic)
+    X = 1.0 + rng.random((nq, 3)) * (np.array(A.shape) - 1.0)
+    Xd = torch.from_numpy(X).cuda()
+    dv, dg, _ = g._eval(Xd, 3)
+    hv, hg, _ = g._eval(X, 3)
+    assert isinstance(hv, np.ndarray) and same(hv, dv.cpu().numpy()) and same(hg, dg.cpu().numpy())
+    rec = gb.valgrad_packed(g, X)
+    assert same(rec[:, 0], hv) and same(rec[:, 1:4], hg)
+    # columns (one vector per dimension), Float32 queries
+    cols = [np.ascontiguousarray(X[:, d].astype(np.float32)) for d in range(3)]
+    cv = gb.getindex_batch(g, cols)
+    dvc = gb.getindex_batch(g, [torch.from_numpy(c).cuda() for c in cols])
+    assert same(cv, dvc.cpu().numpy())
+    # 2-D quadratic Float32 grid, valgradhess
+    B = rng.standard_normal((300, 200)).astype(np.float32)
+    g2 = gb.InterpGrid(B, gb.BCreflect, gb.InterpQuadratic)
+    X2 = (rng.random((nq, 2)) * np.array(B.shape) * 1.2).astype(np.float32)
+    hv2, hg2, hh2 = g2._eval(X2, 7)
+    dv2, dg2, dh2 = g2._eval(torch.from_numpy(X2).cuda(), 7)
+    assert same(hv2, dv2.cpu().numpy()) and same(hg2, dg2.cpu().numpy()) and same(hh2, dh2.cpu().numpy())
+    # BCnil: the first invalid query of the whole batch is reported whichever worker met it
+    gn = gb.InterpGrid(A, gb.BCnil, gb.InterpLinear)
+    Xn = X.copy()
+    Xn[590_123] = (0.25, 2.0, 2.0)
+    Xn[333_333] = (2.0, 99.0, 2.0)
+    with pytest.raises(gb.ErrorException) as ei:
+        gn._eval(Xn, 1)
+    assert "query 333333" in str(ei.value)
+
+
 def test_single_pass_scatter(gb, oracle):
     """GB_SORT_PASSES=1 (child process): bins sized from the probe's sample, one scatter pass, overflow list.  A uniform
     batch (no or few overflows), and a batch whose SAMPLED positions (the first 256 of every 1024 queries, see
