@@ -799,10 +799,12 @@ struct StageSlot {
     size_t in_bytes = 0, out_bytes = 0;
 };
 struct StageCache {
-    std::mutex mu;  // one staged call at a time
+    std::mutex mu;  // one staged call at a time per device
     std::vector<StageSlot> slots;
 };
-StageCache g_stage;
+constexpr int STAGE_MAX_DEV = 64;
+StageCache g_stage_dev[STAGE_MAX_DEV];  // per device: gb_eval_sharded runs one host-buffer call per device at the same time
+std::atomic<int> g_stage_calls{0};      // staged calls in flight (they share the host's cores)
 bool is_pageable(const void* p) {
     if (!p) return false;
     cudaPointerAttributes a;
@@ -833,7 +835,14 @@ int eval_host_staged(const gb_grid* g, int out_mask, int outmode, i64 nq, const 
     }();
     const i64 chunk = std::max<i64>(1, std::min<i64>(chunk_env, nq));
     const i64 nchunk = (nq + chunk - 1) / chunk;
-    const int T = (int)std::max<i64>(1, std::min<i64>(nthreads, nchunk));
+    struct InFlight {
+        int others;
+        InFlight() : others(g_stage_calls.fetch_add(1)) {}
+        ~InFlight() { g_stage_calls.fetch_sub(1); }
+    } inflight;
+    // (concurrent calls -- one per device under gb_eval_sharded -- split the host threads between them, two at least each)
+    const int T = (int)std::max<i64>(1, std::min<i64>(std::max(2, nthreads / (inflight.others + 1)), nchunk));
+    StageCache& g_stage = g_stage_dev[g->device >= 0 && g->device < STAGE_MAX_DEV ? g->device : 0];
     // one output slot: [val | grad | hess] or the packed records
     const size_t vw = packed ? (size_t)packed : ((out_mask & GB_OUT_VAL) ? 1 : 0), gw = packed ? 0 : ((out_mask & GB_OUT_GRAD) ? (size_t)N : 0),
                  hw = packed ? 0 : ((out_mask & GB_OUT_HESS) ? (size_t)N * N : 0);

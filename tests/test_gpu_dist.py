@@ -134,5 +134,12 @@ def test_single_process_all_devices():
         hs = (C.c_void_p * ndev)(*[g._h.value for g in grids])
         L.check(L.lib().gb_eval_sharded(comm._h, hs, 3, len(X), X.ctypes.data, L.GB_F64, None, v.ctypes.data, gr.ctypes.data, None, 0, None))
         assert np.array_equal(v, ov) and np.array_equal(gr, og)
+        # a batch large enough for every device's share to take the staged pageable path (>= 2^19 queries each), all at once
+        nbig = ndev * ((1 << 19) + 4097)
+        Xb = np.tile(X, (nbig // len(X) + 1, 1))[:nbig].copy()
+        vb, gb_ = np.empty(nbig), np.empty((nbig, 3))
+        L.check(L.lib().gb_eval_sharded(comm._h, hs, 3, nbig, Xb.ctypes.data, L.GB_F64, None, vb.ctypes.data, gb_.ctypes.data, None, 0, None))
+        idx = np.arange(nbig) % len(X)
+        assert np.array_equal(vb, ov[idx]) and np.array_equal(gb_, og[idx])
     finally:
         comm.close()
