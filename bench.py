@@ -656,6 +656,7 @@ def main():
         dtp = host_run(Xp, vp, gp, max(2, ksteps // 2))
         assert np.array_equal(vp, val.cpu().numpy()) or args.fast
         e2e_pageable = {"value": world * NQ / dtp / 1e9, "unit": "Gpoints/s", "ms_per_step": dtp * 1e3, "host_memory": "pageable (numpy / malloc)",
+                        "staging": "library-owned pinned slots, %s host threads (GB_HOST_THREADS)" % os.environ.get("GB_HOST_THREADS", "min(8, cores/2)"),
                         "h2d_bytes_per_step": NQ * 24, "d2h_bytes_per_step": NQ * 32}
         del Xp, vp, gp
 
