@@ -973,6 +973,89 @@ int eval_host_staged(const gb_grid* g, int out_mask, int outmode, i64 nq, const 
     return rc;
 }
 
+// ---- small host batches: the scalar API ----------------------------------------------------------------------------------
+// G[x], valgrad(G, x) and short batches arrive here one C call at a time (GridB200.jl evaluates a scalar query per ccall):
+// three stream creations, a dozen pool allocations and as many frees cost 150-170 us per call, ten times the work itself.
+// Up to SMALL_MAX queries therefore go through a per-thread, per-device context that is created once -- one stream, one pinned
+// and one device staging buffer (layout: coordinates | first-invalid word | outputs): memcpy in, ONE copy to the device, the
+// kernel, ONE copy back, synchronise, memcpy out.  (Deliberately never destroyed: thread-exit destructors must not call CUDA.)
+constexpr i64 SMALL_MAX = 1 << 15;
+struct SmallCtx {
+    cudaStream_t s;
+    char *pin, *dev;
+    size_t bytes;
+};
+int eval_host_small(const gb_grid* g, int out_mask, int outmode, i64 nq, const void* const* xcols, const void* xaos, int xdtype, const double* affine,
+                    void* val, void* grad, void* hess, int flags, int64_t* first_invalid) {
+    static thread_local SmallCtx ctxs[STAGE_MAX_DEV] = {};
+    if (g->device < 0 || g->device >= STAGE_MAX_DEV) return fail(GB_ERR_ARG, "device index out of range");
+    SmallCtx& c = ctxs[g->device];
+    const int N = g->ndim;
+    const size_t xs = esize(xdtype), es = esize(g->dtype) * (size_t)g->nchan;
+    const int packed = packed_words(g, out_mask, outmode);
+    const size_t vw = packed ? (size_t)packed : ((out_mask & GB_OUT_VAL) ? 1 : 0), gw = packed ? 0 : ((out_mask & GB_OUT_GRAD) ? (size_t)N : 0),
+                 hw = packed ? 0 : ((out_mask & GB_OUT_HESS) ? (size_t)N * N : 0);
+    const size_t bytes_x = (size_t)nq * N * xs;
+    const size_t off_bad = (bytes_x + 15) & ~(size_t)15, off_v = off_bad + 16;
+    const size_t off_g = off_v + (((size_t)nq * vw * es + 15) & ~(size_t)15), off_h = off_g + (((size_t)nq * gw * es + 15) & ~(size_t)15);
+    const size_t total = off_h + (size_t)nq * hw * es;
+    if (!c.s) GB_CUDA(cudaStreamCreateWithFlags(&c.s, cudaStreamNonBlocking));
+    if (c.bytes < total) {
+        size_t want = 1 << 16;
+        while (want < total) want <<= 1;
+        if (c.pin) cudaFreeHost(c.pin);
+        if (c.dev) cudaFree(c.dev);
+        c.pin = c.dev = nullptr;
+        c.bytes = 0;
+        GB_CUDA(cudaHostAlloc((void**)&c.pin, want, cudaHostAllocDefault));
+        GB_CUDA(cudaMalloc((void**)&c.dev, want));
+        c.bytes = want;
+    }
+    const bool check = first_invalid && g->bc == GB_BC_NIL;
+    EvalCall call;
+    call.g = g; call.outmode = outmode; call.flags = flags; call.xdtype = xdtype; call.affine = affine;
+    call.nq = nq; call.q0 = 0;
+    call.first_invalid = check ? reinterpret_cast<u64*>(c.dev + off_bad) : nullptr;
+    if (xaos) {
+        std::memcpy(c.pin, xaos, bytes_x);
+        for (int d = 0; d < N; d++) call.xp[d] = c.dev + (size_t)d * xs;
+        call.xqs = N;
+    } else {
+        for (int d = 0; d < N; d++) {
+            std::memcpy(c.pin + (size_t)d * nq * xs, xcols[d], (size_t)nq * xs);
+            call.xp[d] = c.dev + (size_t)d * nq * xs;
+        }
+        call.xqs = 1;
+    }
+    *reinterpret_cast<u64*>(c.pin + off_bad) = ~0ull;
+    call.val = vw ? c.dev + off_v : nullptr;
+    call.grad = gw ? c.dev + off_g : nullptr;
+    call.hess = hw ? c.dev + off_h : nullptr;
+    call.packed = packed;
+    if (g->ready) GB_CUDA(cudaStreamWaitEvent(c.s, g->ready, 0));  // a grid built on another stream
+    GB_CUDA(cudaMemcpyAsync(c.dev, c.pin, off_v, cudaMemcpyHostToDevice, c.s));
+    int rc = launch_eval(call, c.s);
+    if (rc == GB_OK) {
+        cudaError_t e = cudaMemcpyAsync(c.pin + off_bad, c.dev + off_bad, total - off_bad, cudaMemcpyDeviceToHost, c.s);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync D2H");
+    }
+    const cudaError_t es_ = cudaStreamSynchronize(c.s);
+    if (rc == GB_OK && es_ != cudaSuccess) rc = cuda_fail(es_, "cudaStreamSynchronize");
+    if (first_invalid) *first_invalid = -1;
+    if (rc != GB_OK) return rc;
+    if (vw) std::memcpy(val, c.pin + off_v, (size_t)nq * vw * es);
+    if (gw) std::memcpy(grad, c.pin + off_g, (size_t)nq * gw * es);
+    if (hw) std::memcpy(hess, c.pin + off_h, (size_t)nq * hw * es);
+    if (check) {
+        const u64 bad = *reinterpret_cast<const u64*>(c.pin + off_bad);
+        if (bad != ~0ull) {
+            *first_invalid = (int64_t)bad;
+            return fail(GB_ERR_INVALID_LOCATION, "Invalid location");
+        }
+    }
+    return GB_OK;
+}
+
 // Host-resident evaluation: chunks of the batch flow H2D -> kernel -> D2H over a ring of streams so
 // PCIe traffic in both directions overlaps the kernels.
 int eval_host(const gb_grid* g, int out_mask, int outmode, i64 nq, const void* const* xcols, const void* xaos, int xdtype,
@@ -985,6 +1068,10 @@ int eval_host(const gb_grid* g, int out_mask, int outmode, i64 nq, const void* c
         return (i64)(v > 0 ? v : (1ll << 20));
     }();
     const i64 chunk = std::max<i64>(1, std::min<i64>(chunk_env, nq));
+    {
+        static const bool small_off = [] { const char* e = getenv("GB_NO_SMALL_PATH"); return e && *e == '1'; }();
+        if (nq <= SMALL_MAX && !small_off) return eval_host_small(g, out_mask, outmode, nq, xcols, xaos, xdtype, affine, val, grad, hess, flags, first_invalid);
+    }
     // pageable buffers, a batch worth the threads: the library's own pinned staging slots (eval_host_staged)
     {
         static const int reg_env0 = [] { const char* e = getenv("GB_HOST_REGISTER"); return e ? atoi(e) : 0; }();

@@ -132,6 +132,67 @@ print("ok")
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
 
 
+def test_small_host_batches_fast_path(gb, oracle):
+    """Host batches up to 2^15 queries (the scalar API: one query per C call) run through a per-thread context that is
+    created once (abi.cu: eval_host_small).  Bits as the oracle's for scalar calls, short batches of every output kind,
+    column inputs, Float32, packed records, a multi-valued grid, growing and shrinking sizes, calls from several threads, and
+    BCnil's error with the first invalid query."""
+    import threading
+
+    rng = np.random.default_rng(43)
+    A = rng.standard_normal((30, 28, 26))
+    g = gb.InterpGrid(A, gb.BCnan, gb.InterpCubic)
+    co = oracle.make_coefs(A, "nan", "cubic")
+    for nq in (1, 2, 777, 1, 32768, 5):
+        X = 1.0 + rng.random((nq, 3)) * (np.array(A.shape) - 1.0)
+        ov, og, oh, _ = oracle.evaluate(co, "nan", "cubic", X, 7)
+        v, gr, h = g._eval(X, 7)
+        assert same(v, ov) and same(gr, og) and same(h, oh), nq
+        rec = gb.valgrad_packed(g, X)
+        assert same(rec[:, 0], ov) and same(rec[:, 1:4], og)
+        cv = gb.getindex_batch(g, [np.ascontiguousarray(X[:, d]) for d in range(3)])
+        assert same(cv, ov)
+    x = (3.25, 7.5, 11.125)
+    ov, og, _, _ = oracle.evaluate(co, "nan", "cubic", np.array([x]), 3)
+    assert g[x] == ov[0]
+    val, grad = gb.valgrad(g, *x)
+    assert val == ov[0] and same(np.asarray(grad), og[0])
+    # Float32 grid and queries, 2-D, reflect
+    B = rng.standard_normal((50, 40)).astype(np.float32)
+    g2 = gb.InterpGrid(B, gb.BCreflect, gb.InterpQuadratic)
+    c2 = oracle.make_coefs(B, "reflect", "quadratic")
+    X2 = (rng.random((900, 2)) * np.array(B.shape) * 1.3).astype(np.float32)
+    ov2, og2, oh2, _ = oracle.evaluate(c2, "reflect", "quadratic", X2, 7)
+    v2, gr2, h2 = g2._eval(X2, 7)
+    assert same(v2, ov2) and same(gr2, og2) and same(h2, oh2)
+    # several host threads, each with its own context
+    errs = []
+
+    def work(seed):
+        try:
+            r = np.random.default_rng(seed)
+            for _ in range(20):
+                Xt = 1.0 + r.random((int(r.integers(1, 400)), 3)) * (np.array(A.shape) - 1.0)
+                e, _, _, _ = oracle.evaluate(co, "nan", "cubic", Xt, 1)
+                vt, _, _ = g._eval(Xt, 1)
+                assert same(vt, e)
+        except Exception as ex:  # noqa: BLE001
+            errs.append(ex)
+
+    ts = [threading.Thread(target=work, args=(s,)) for s in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    gn = gb.InterpGrid(A, gb.BCnil, gb.InterpLinear)
+    Xn = 2.0 + rng.random((100, 3))
+    Xn[41] = (0.5, 2.0, 2.0)
+    with pytest.raises(gb.ErrorException) as ei:
+        gn._eval(Xn, 1)
+    assert "query 41" in str(ei.value)
+    v, _, _ = gn._eval(Xn[:41], 1)
+    assert np.isfinite(v).all()
+
+
 def test_pageable_host_buffers_staged_path(gb):
     """Pageable (numpy) host buffers above 2^19 queries go through the library's pinned staging slots with several host threads
     (abi.cu: eval_host_staged).  Same bits as the device-resident call: AoS and column inputs, Float32 queries, value /
