@@ -58,6 +58,8 @@ SIGNATURES = {
     "gb_restrict3_sharded": (i32, [vp, i32, p_i64, p_vp, f64, p_vp, p_vp]),
     "gb_prolong3_sharded": (i32, [vp, i32, p_i64, p_vp, p_i64, p_vp, p_vp]),
     "gb_comm_stats": (i32, [vp, p_f64, i32, p_i32]),
+    "gb_comm_peer_halo": (i32, [vp, i32, p_i32]),
+    "gb_comm_last_path": (i32, [vp, p_i32]),
     "gb_pad1": (i32, [i32, i32, p_i64, vp, f64, vp, i32, vp]),
     "gb_eval": (i32, [vp, i32, i64, vp, i32, i64, i64, p_f64, vp, vp, vp, i32, i32, p_i64, vp]),
     "gb_eval_soa": (i32, [vp, i32, i64, p_vp, i32, p_f64, vp, vp, vp, i32, i32, p_i64, vp]),

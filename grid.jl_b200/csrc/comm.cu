@@ -23,8 +23,16 @@
 //      (halo planes + the adjoining own planes).
 // The element code is that of gb_restrict3_slab / gb_prolong3_slab, so the assembled result is bit-identical
 // to the unsharded one.
+//
+// PEER mode (one process, every rank local, peer access between the devices -- gb_comm_init_all on an NVLink box; loopback):
+// there is no exchange at all.  The boundary kernel reads the halo planes IN PLACE from the neighbouring ranks' slabs through
+// peer pointers (multigrid.cu: Sides / slab_plane) -- the transfer is the kernel's own loads over NVLink, a few planes of a
+// tile at a time, overlapped with its arithmetic; no NCCL group, no halo buffer, no assembly copies (which is what the five
+// small levels of a chain pay for: ~40 us of fixed cost per level).  Falls back to the exchange when a rank's stencil reaches
+// past its immediate neighbours (slabs a plane or two thin) or a slab lives in a memory pool peers cannot map.
 #include <dlfcn.h>
 #include <nccl.h>  // types only; every entry point is resolved with dlsym
+#include <cuda.h>  // types only (cuPointerGetAttribute is resolved at run time)
 
 #include <algorithm>
 #include <cstring>
@@ -146,6 +154,7 @@ struct LocalRank {
     cudaStream_t cs = nullptr, ws = nullptr;      // communication stream, default work stream
     cudaEvent_t ev_in = nullptr, ev_halo = nullptr;  // inputs ready (work -> comm), halo landed (comm -> work)
     cudaEvent_t ev_t0 = nullptr, ev_int = nullptr, ev_t1 = nullptr, ev_h1 = nullptr;  // timing (created with timing enabled)
+    cudaEvent_t ev_done = nullptr;  // peer mode: this rank's kernels have read their neighbours' slabs
     void* halo = nullptr;  // [lo planes | hi planes]
     size_t halo_cap = 0;
     double halo_bytes = 0;  // last call
@@ -161,6 +170,8 @@ using namespace gb;
 struct gb_comm {
     int nranks = 0, first_rank = 0;
     int loopback = 0;
+    int peer_capable = 0, peer = 0;  // peer-pointer halo reads possible / in use (gb_comm_peer_halo)
+    int last_peer = 0;               // the last sharded call ran in peer mode
     NcclApi* api = nullptr;
     std::vector<LocalRank> loc;
     std::mutex mu;
@@ -196,7 +207,26 @@ int init_local(LocalRank& l) {
     GB_CUDA(cudaEventCreate(&l.ev_int));
     GB_CUDA(cudaEventCreate(&l.ev_t1));
     GB_CUDA(cudaEventCreate(&l.ev_h1));
+    GB_CUDA(cudaEventCreateWithFlags(&l.ev_done, cudaEventDisableTiming));
     return GB_OK;
+}
+bool peer_default() {
+    static const bool v = [] { const char* e = getenv("GB_PEER_HALO"); return !(e && *e == '0'); }();
+    return v;
+}
+// memory from a stream-ordered pool is mapped on peers only if the pool was told so: such slabs take the exchange
+bool peer_mappable(const void* p) {
+    typedef CUresult (*Fn)(void*, CUpointer_attribute, CUdeviceptr);
+    static Fn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuPointerGetAttribute", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+        return (Fn)f;
+    }();
+    if (!fn || !p) return false;
+    CUmemoryPool pool = nullptr;
+    if (fn(&pool, CU_POINTER_ATTRIBUTE_MEMPOOL_HANDLE, (CUdeviceptr)(uintptr_t)p) != CUDA_SUCCESS) return false;
+    return pool == nullptr;
 }
 
 size_t esz(int dtype) { return dtype == GB_F64 ? 8 : 4; }
@@ -272,8 +302,24 @@ int sharded_level(gb_comm* c, int kind, int dtype, const i64* gin, const i64* go
             pieces[i].push_back({k0, k1, false});
         }
     }
+    // ---- peer mode?  every rank local, non-empty, its boundary stencils within the immediate neighbours' slabs, slabs mappable
+    bool use_peer = c->peer != 0 && nl == W && W > 1;
+    for (int i = 0; i < nl && use_peer; i++) {
+        const int r = c->loc[i].rank;
+        const i64 o0 = plan.own0[r], o1 = plan.own1[r];
+        if (o1 <= o0 || r != i) { use_peer = false; break; }
+        const i64 zmin = i > 0 ? plan.own0[r - 1] : o0, zmax = i < nl - 1 ? plan.own1[r + 1] : o1;
+        for (const Piece& p : pieces[i]) {
+            if (p.interior) continue;
+            i64 lo, hi;
+            needs(kind, n_in, n_out, p.k0, p.k1, &lo, &hi);
+            if (lo < zmin || hi >= zmax) use_peer = false;
+        }
+        if (!c->loopback && !peer_mappable(in_slabs[i])) use_peer = false;
+    }
+    c->last_peer = use_peer ? 1 : 0;
     // ---- 2. halo exchange on the comm streams ------------------------------------------------------------------
-    for (int i = 0; i < nl; i++) {  // a send reads the source rank's slab: every comm stream waits for every local input
+    for (int i = 0; i < nl && !use_peer; i++) {  // a send reads the source rank's slab: every comm stream waits for every local input
         DevGuard g(c->loc[i].dev);
         for (int j = 0; j < nl; j++) GB_CUDA(cudaStreamWaitEvent(c->loc[i].cs, c->loc[j].ev_in, 0));
     }
@@ -286,7 +332,7 @@ int sharded_level(gb_comm* c, int kind, int dtype, const i64* gin, const i64* go
         if (plane < o0) return (char*)c->loc[i].halo + (size_t)(plane - e0) * in_plane;
         return (char*)c->loc[i].halo + (size_t)((o0 - e0) + (plane - o1)) * in_plane;
     };
-    if (!plan.xfers.empty()) {
+    if (!plan.xfers.empty() && !use_peer) {
         if (!c->loopback) GB_NCCL(api, api->GroupStart());
         for (const Transfer& t : plan.xfers) {
             const int si = local_of(t.src), di = local_of(t.dst);
@@ -313,6 +359,33 @@ int sharded_level(gb_comm* c, int kind, int dtype, const i64* gin, const i64* go
         }
         if (!c->loopback) GB_NCCL(api, api->GroupEnd());
     }
+    // ---- 2 (peer mode). no exchange: the BOUNDARY planes are computed on the priority stream by a kernel that reads the
+    // neighbours' planes in place through peer pointers, concurrently with the interior planes below -------------------------
+    for (int i = 0; i < nl && use_peer; i++) {
+        LocalRank& l = c->loc[i];
+        const int r = l.rank;
+        DevGuard g(l.dev);
+        const i64 o0 = plan.own0[r], o1 = plan.own1[r], k0 = plan.out0[r];
+        const i64 zmin = i > 0 ? plan.own0[r - 1] : o0, zmax = i < nl - 1 ? plan.own1[r + 1] : o1;
+        GB_CUDA(cudaStreamWaitEvent(l.cs, l.ev_in, 0));  // own slab and the neighbours' slabs are complete
+        if (i > 0) GB_CUDA(cudaStreamWaitEvent(l.cs, c->loc[i - 1].ev_in, 0));
+        if (i < nl - 1) GB_CUDA(cudaStreamWaitEvent(l.cs, c->loc[i + 1].ev_in, 0));
+        for (const Piece& p : pieces[i]) {
+            if (p.interior) continue;
+            i64 lo, hi;
+            needs(kind, n_in, n_out, p.k0, p.k1, &lo, &hi);
+            l.halo_bytes += (double)((size_t)(std::max<i64>(0, o0 - lo) + std::max<i64>(0, hi + 1 - o1)) * in_plane);  // read over the link
+            const i64 dims[3] = {gin[0], gin[1], o1 - o0};
+            const void* plo = i > 0 ? in_slabs[i - 1] : nullptr;
+            const void* phi = i < nl - 1 ? in_slabs[i + 1] : nullptr;
+            const i64 lo_first = i > 0 ? plan.own0[r - 1] : 0, hi_first = i < nl - 1 ? plan.own0[r + 1] : 0;
+            char* out = (char*)out_slabs[i] + (size_t)(p.k0 - k0) * out_plane;
+            int rc;
+            if (kind == 0) rc = restrict3_slab_peer_device(dtype, dims, in_slabs[i], scale, n_in, o0, plo, lo_first, phi, hi_first, zmin, zmax, p.k0, p.k1 - p.k0, out, l.cs);
+            else rc = prolong3_slab_peer_device(dtype, dims, in_slabs[i], gout, n_in, o0, plo, lo_first, phi, hi_first, zmin, zmax, p.k0, p.k1 - p.k0, out, l.cs);
+            if (rc) return rc;
+        }
+    }
     for (int i = 0; i < nl; i++) {
         LocalRank& l = c->loc[i];
         DevGuard g(l.dev);
@@ -337,8 +410,23 @@ int sharded_level(gb_comm* c, int kind, int dtype, const i64* gin, const i64* go
         }
         GB_CUDA(cudaEventRecord(l.ev_int, ws[i]));
     }
+    // ---- 3 (peer mode). join: results complete when both streams are; a slab may change once its readers are done ------------
+    if (use_peer) {
+        for (int i = 0; i < nl; i++) {
+            LocalRank& l = c->loc[i];
+            DevGuard g(l.dev);
+            GB_CUDA(cudaStreamWaitEvent(ws[i], l.ev_halo, 0));
+            GB_CUDA(cudaEventRecord(l.ev_t1, ws[i]));
+            GB_CUDA(cudaEventRecord(l.ev_done, ws[i]));
+        }
+        for (int i = 0; i < nl; i++) {
+            DevGuard g(c->loc[i].dev);
+            if (i > 0) GB_CUDA(cudaStreamWaitEvent(ws[i], c->loc[i - 1].ev_done, 0));
+            if (i < nl - 1) GB_CUDA(cudaStreamWaitEvent(ws[i], c->loc[i + 1].ev_done, 0));
+        }
+    }
     // ---- 3. boundary planes after the halo has landed ------------------------------------------------------------
-    for (int i = 0; i < nl; i++) {
+    for (int i = 0; i < nl && !use_peer; i++) {
         LocalRank& l = c->loc[i];
         const int r = l.rank;
         DevGuard g(l.dev);
@@ -468,6 +556,21 @@ int gb_comm_init_all(gb_comm** out, int ndev, const int* dev_ids) {
         int rc = init_local(c->loc[i]);
         if (rc) return rc;
     }
+    // peer access between every pair of devices (NVLink / NVSwitch boxes): the boundary kernels then read halo planes in place
+    bool ok = ndev > 1;
+    for (int i = 0; i < ndev && ok; i++) {
+        DevGuard g(devs[i]);
+        for (int j = 0; j < ndev && ok; j++) {
+            if (i == j || devs[i] == devs[j]) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, devs[i], devs[j]) != cudaSuccess || !can) { ok = false; break; }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(devs[j], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = false;
+            cudaGetLastError();
+        }
+    }
+    c->peer_capable = ok ? 1 : 0;
+    c->peer = ok && peer_default() ? 1 : 0;
     *out = c;
     return GB_OK;
 }
@@ -485,7 +588,27 @@ int gb_comm_init_loopback(gb_comm** out, int nranks) {
         int rc = init_local(c->loc[i]);
         if (rc) return rc;
     }
+    c->peer_capable = 1;  // one device: every "peer" pointer is local
+    c->peer = peer_default() ? 1 : 0;
     *out = c;
+    return GB_OK;
+}
+
+// Peer-pointer halo reads (see the header of this file): enable = 1 / 0 switches them on (if the communicator can) / off,
+// anything else leaves the setting; *enabled (may be NULL) receives the setting in force.
+int gb_comm_peer_halo(gb_comm* c, int enable, int* enabled) {
+    if (!c) return fail(GB_ERR_ARG, "comm is NULL");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (enable == 0) c->peer = 0;
+    else if (enable == 1) c->peer = c->peer_capable;
+    if (enabled) *enabled = c->peer;
+    return GB_OK;
+}
+
+int gb_comm_last_path(gb_comm* c, int* peer) {
+    if (!c || !peer) return fail(GB_ERR_ARG, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    *peer = c->last_peer;
     return GB_OK;
 }
 
@@ -505,7 +628,7 @@ int gb_comm_destroy(gb_comm* c) {
         if (l.ws) cudaStreamSynchronize(l.ws);
         if (l.comm && c->api) c->api->CommDestroy(l.comm);
         if (l.halo) cudaFree(l.halo);
-        for (cudaEvent_t e : {l.ev_in, l.ev_halo, l.ev_t0, l.ev_int, l.ev_t1, l.ev_h1})
+        for (cudaEvent_t e : {l.ev_in, l.ev_halo, l.ev_t0, l.ev_int, l.ev_t1, l.ev_h1, l.ev_done})
             if (e) cudaEventDestroy(e);
         if (l.cs) cudaStreamDestroy(l.cs);
         if (l.ws) cudaStreamDestroy(l.ws);

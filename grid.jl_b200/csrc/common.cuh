@@ -209,6 +209,10 @@ int restrict12_device(int dtype, i64 L1, i64 L2, i64 nz, const void* in, double 
 int prolong12_device(int dtype, i64 n1, i64 n2, i64 nz, const void* in, i64 m1, i64 m2, void* out, cudaStream_t s);
 int restrict3_slab_device(int dtype, const i64* dims, const void* in, double scale, i64 L3, i64 in_first, i64 out_first, i64 ocount, void* out, cudaStream_t s);
 int prolong3_slab_device(int dtype, const i64* dims, const void* in, const i64* m, i64 n3, i64 in_first, i64 out_first, i64 ocount, void* out, cudaStream_t s);
+int restrict3_slab_peer_device(int dtype, const i64* dims, const void* in, double scale, i64 L3, i64 in_first, const void* lo, i64 lo_first, const void* hi, i64 hi_first,
+                               i64 zmin, i64 zmax, i64 out_first, i64 ocount, void* out, cudaStream_t s);
+int prolong3_slab_peer_device(int dtype, const i64* dims, const void* in, const i64* m, i64 n3, i64 in_first, const void* lo, i64 lo_first, const void* hi, i64 hi_first,
+                              i64 zmin, i64 zmax, i64 out_first, i64 ocount, void* out, cudaStream_t s);
 int irregular_device(int dtype, const void* knots, const void* coefs, i64 n, int bc, int it, double fill, const void* x, void* out, i64 nq, u64* first_invalid,
                      cudaStream_t s);
 int interleave_device(int dtype, const void* in, void* out, i64 st, i64 nchan, int to_interleaved, cudaStream_t s);

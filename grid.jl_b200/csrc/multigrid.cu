@@ -383,11 +383,25 @@ template <typename T> __device__ __forceinline__ T restrict_full(bool even, T am
     }
     return acc;
 }
+// Slab form with PEER sides (multi-GPU, comm.cu): the input planes of a slab kernel come from up to three arrays -- the
+// rank's own slab (A, planes [zin0, zin0 + nzin)), and the slabs of the ranks below and above, read IN PLACE through peer
+// (NVLink) pointers: `lo` holds planes from lo0 on, `hi` planes from hi0 on.  [zmin, zmax) is the range of planes that exist
+// in one of the three.  No sides: lo = hi = NULL, zmin = zin0, zmax = zin0 + nzin -- the single-array slab form.
+template <typename T> struct Sides {
+    const T *lo, *hi;
+    int lo0, hi0, zmin, zmax;
+};
+template <typename T> __device__ __forceinline__ const T* slab_plane(const T* __restrict__ A, int zin0, int nzin, const Sides<T>& sd, int gz, size_t plane) {
+    if (gz < zin0) return sd.lo + (size_t)(gz - sd.lo0) * plane;
+    if (gz >= zin0 + nzin) return sd.hi + (size_t)(gz - sd.hi0) * plane;
+    return A + (size_t)(gz - zin0) * plane;
+}
+template <typename T> Sides<T> no_sides(i64 zin0, i64 nzin) { return Sides<T>{nullptr, nullptr, 0, 0, (int)zin0, (int)(zin0 + nzin)}; }
 // A lane owns outputs x = 2*lane, 2*lane+1 of the 64-wide tile: their eight taps are six consecutive inputs (three
 // aligned 16-byte loads), and shared memory moves pairs (one column per lane: 2.94 instead of 2.63 ms per chain).
 template <typename T, int BY, int NW, int UN, bool DO3> __global__ void __launch_bounds__(32 * NW) restrict3_march_kernel(const T* __restrict__ A, T* __restrict__ R, int L1, int L2, int L3, int n1,
                                                                                                         int n2, int n3, int zc, RCoef<T> c, int zin0, int nzin,
-                                                                                                        int zout0, int ocount, int xtiles) {
+                                                                                                        int zout0, int ocount, int xtiles, const Sides<T> sd) {
     // slab form: A holds input planes [zin0, zin0 + nzin) of the L3 global ones, R output planes [zout0, zout0 + ocount)
     // of the n3 global ones (whole array: 0, L3, 0, n3); plane indices below are global.
     // DO3 == false: dims 1 and 2 only (2-D arrays, restrict(A, [true,true,false])): plane gz of R comes from plane gz of A.
@@ -404,7 +418,8 @@ template <typename T, int BY, int NW, int UN, bool DO3> __global__ void __launch
     const int nzo = min(zc, zout0 + ocount - j3);
     const int y0 = 2 * j2 - 2, z0 = DO3 ? 2 * j3 - 2 : j3;
     const bool ev1 = !(L1 & 1), ev2 = !(L2 & 1), ev3 = !(L3 & 1);
-    const bool vec = !(L1 & 1) && ((reinterpret_cast<uintptr_t>(A) & (sizeof(V) - 1)) == 0);  // rows aligned to a pair (16 B for f64, 8 B for f32)
+    const bool vec = !(L1 & 1) && (((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(sd.lo) | reinterpret_cast<uintptr_t>(sd.hi)) & (sizeof(V) - 1)) ==
+                                   0);  // rows aligned to a pair (16 B for f64, 8 B for f32)
     const int gx = j1 + 2 * lane;
     const bool xfull = j1 >= 1 && j1 + BX - 1 <= n1 - 2;  // warp-uniform: every output of the tile has all four taps
     const bool vx0 = gx < n1, vx1 = gx + 1 < n1;
@@ -412,10 +427,10 @@ template <typename T, int BY, int NW, int UN, bool DO3> __global__ void __launch
     const size_t plane = (size_t)L2 * (size_t)L1;
     for (int p = 0; p < (DO3 ? 2 * nzo + 2 : nzo); p++) {
         const int gz = z0 + p;
-        const bool zok = gz >= zin0 && gz < zin0 + nzin;  // (planes a needed tap lies on are present: checked by the host)
+        const bool zok = gz >= sd.zmin && gz < sd.zmax;  // (planes a needed tap lies on are present: checked by the host)
         // ---- stage A: dim-1 restriction; inputs t[0..5] = A[2gx-2 .. 2gx+3]
         if (zok && j1 < n1) {
-            const T* Ac = A + (size_t)(gz - zin0) * plane + 2 * gx;
+            const T* Ac = slab_plane<T>(A, zin0, nzin, sd, gz, plane) + 2 * gx;
 #pragma unroll 1
             for (int k0 = 0; k0 < (IY + NW - 1) / NW; k0 += UN) {
                 T t[UN][6];
@@ -518,7 +533,8 @@ template <typename T, int BY, int NW, int UN, bool DO3> __global__ void __launch
     }
 }
 template <typename T, int BY, int NW, int UN, bool DO3 = true>
-int restrict3_march_launch(const T* in, T* out, i64 L1, i64 L2, i64 L3, i64 n1, i64 n2, i64 n3, double scale, i64 zin0, i64 nzin, i64 zout0, i64 ocount, cudaStream_t s) {
+int restrict3_march_launch(const T* in, T* out, i64 L1, i64 L2, i64 L3, i64 n1, i64 n2, i64 n3, double scale, i64 zin0, i64 nzin, i64 zout0, i64 ocount, cudaStream_t s,
+                           const Sides<T>* sides = nullptr) {
     constexpr int BX = 64, IY = 2 * BY + 2;
     const size_t smem = sizeof(T) * (size_t)(IY * BX + 4 * BY * BX);
     auto kern = restrict3_march_kernel<T, BY, NW, UN, DO3>;
@@ -531,7 +547,7 @@ int restrict3_march_launch(const T* in, T* out, i64 L1, i64 L2, i64 L3, i64 n1, 
     const bool lin = gy > 65535;
     const dim3 grid = lin ? dim3((unsigned)(gx * gy), (unsigned)((ocount + zc - 1) / zc), 1) : dim3((unsigned)gx, (unsigned)gy, (unsigned)((ocount + zc - 1) / zc));
     kern<<<grid, 32 * NW, smem, s>>>(in, out, (int)L1, (int)L2, (int)L3, (int)n1, (int)n2, (int)n3, (int)zc, make_coef<T>(scale), (int)zin0, (int)nzin, (int)zout0,
-                                     (int)ocount, lin ? (int)gx : 0);
+                                     (int)ocount, lin ? (int)gx : 0, sides ? *sides : no_sides<T>(zin0, nzin));
     count_launch();
     GB_CUDA(cudaGetLastError());
     return GB_OK;
@@ -574,7 +590,8 @@ template <typename T> int restrict12_impl(i64 L1, i64 L2, i64 nz, const T* in, d
 
 // restrict(A, [true,true,true], scale) on ONE SLAB of a 3-D array sharded along dim 3: `in` holds input planes
 // [in_first, in_first + dims[2]) of the L3 global ones, `out` receives output planes [out_first, out_first + ocount).
-template <typename T> int restrict3_slab_impl(const i64* dims, const T* in, double scale, i64 L3, i64 in_first, i64 out_first, i64 ocount, T* out, cudaStream_t s) {
+template <typename T> int restrict3_slab_impl(const i64* dims, const T* in, double scale, i64 L3, i64 in_first, i64 out_first, i64 ocount, T* out, cudaStream_t s,
+                                              const Sides<T>* sides = nullptr) {
     const i64 L1 = dims[0], L2 = dims[1], nloc = dims[2];
     const i64 n1 = rsize(L1), n2 = rsize(L2), n3 = rsize(L3);
     if (L1 < 2 || L2 < 2 || L3 < 2) return fail(GB_ERR_UNSUPPORTED, "restrict3 slab: extents below 2 (use gb_restrict_slab per dimension)");
@@ -584,8 +601,9 @@ template <typename T> int restrict3_slab_impl(const i64* dims, const T* in, doub
     if (ocount == 0) return GB_OK;
     i64 lo, hi;
     restrict_needs(L3, n3, out_first, out_first + ocount, &lo, &hi);
-    if (lo < in_first || hi >= in_first + nloc) return fail(GB_ERR_ARG, "restrict: the slab does not hold every input plane the requested outputs need");
-    return restrict3_march_launch<T, 4, 5, 2>(in, out, L1, L2, L3, n1, n2, n3, scale, in_first, nloc, out_first, ocount, s);
+    const i64 have0 = sides ? sides->zmin : in_first, have1 = sides ? sides->zmax : in_first + nloc;
+    if (lo < have0 || hi >= have1) return fail(GB_ERR_ARG, "restrict: the slab does not hold every input plane the requested outputs need");
+    return restrict3_march_launch<T, 4, 5, 2>(in, out, L1, L2, L3, n1, n2, n3, scale, in_first, nloc, out_first, ocount, s, sides);
 }
 
 // ---- fused 3-D prolong ------------------------------------------------------------------------
@@ -689,7 +707,8 @@ template <typename T, int BY, int BZ> __global__ void __launch_bounds__(256) pro
 // rows).  A lane owns the output pair x = 2*lane, 2*lane+1 for the whole kernel: both come from the same two
 // inputs, the parities are compile-time, and shared memory and (for even row lengths) global stores move pairs.  Same prolong_at calls in the same order as the brick kernel, hence the same bits.
 template <typename T, int BY, int NW, bool DO3> __global__ void __launch_bounds__(32 * NW) prolong3_march_kernel(const T* __restrict__ A, T* __restrict__ P, int n1, int n2, int n3, int m1, int m2,
-                                                                                               int m3, int zc, int zin0, int nzin, int zout0, int ocount, int xtiles) {
+                                                                                               int m3, int zc, int zin0, int nzin, int zout0, int ocount, int xtiles,
+                                                                                               const Sides<T> sd) {
     // slab form: A holds input planes [zin0, zin0 + nzin) (of the n3 global ones), P output planes [zout0, zout0 + ocount) of the
     // m3 global ones (whole array: 0, 0, m3); plane indices below are global
     constexpr int BX = 64, NY = BY / 2 + 1, HX = BX / 2;  // a lane owns the output pair x = 2*lane, 2*lane + 1 (input column `xi`)
@@ -709,10 +728,10 @@ template <typename T, int BY, int NW, bool DO3> __global__ void __launch_bounds_
     const size_t iplane = (size_t)n2 * (size_t)n1, oplane = (size_t)m2 * (size_t)m1;
     for (int ip = 0; DO3 ? 2 * (ip - 1) < nplanes : ip < nplanes; ip++) {
         const int lz = z0 + ip;
-        const bool zin = lz < n3 && lz < zin0 + nzin;  // (planes a needed tap lies on are present: checked by the host)
+        const bool zin = lz < n3 && lz < sd.zmax;  // (planes a needed tap lies on are present: checked by the host)
         // ---- stage A: dim-1 prolongation of input plane lz, rows y0 .. y0+NY-1
         if (zin) {
-            const T* Az = A + (size_t)(lz - zin0) * iplane + xi;
+            const T* Az = slab_plane<T>(A, zin0, nzin, sd, lz, iplane) + xi;
             for (int y = warp; y < NY; y += NW) {
                 const int gy = y0 + y;
                 V v{(T)0, (T)0};
@@ -784,7 +803,8 @@ template <typename T, int BY, int NW, bool DO3> __global__ void __launch_bounds_
         }
     }
 }
-template <typename T, int BY, int NW, bool DO3 = true> int prolong3_march_launch(const T* in, T* out, i64 n1, i64 n2, i64 n3, const i64* m, i64 zin0, i64 nzin, i64 zout0, i64 ocount, cudaStream_t s) {
+template <typename T, int BY, int NW, bool DO3 = true>
+int prolong3_march_launch(const T* in, T* out, i64 n1, i64 n2, i64 n3, const i64* m, i64 zin0, i64 nzin, i64 zout0, i64 ocount, cudaStream_t s, const Sides<T>* sides = nullptr) {
     constexpr int BX = 64, NY = BY / 2 + 1;
     const size_t smem = sizeof(T) * (size_t)(NY * BX + 2 * BY * BX);
     auto kern = prolong3_march_kernel<T, BY, NW, DO3>;
@@ -798,7 +818,7 @@ template <typename T, int BY, int NW, bool DO3 = true> int prolong3_march_launch
     const bool lin = gy > 65535;
     const dim3 grid = lin ? dim3((unsigned)(gx * gy), (unsigned)((span + zc - 1) / zc), 1) : dim3((unsigned)gx, (unsigned)gy, (unsigned)((span + zc - 1) / zc));
     kern<<<grid, 32 * NW, smem, s>>>(in, out, (int)n1, (int)n2, (int)n3, (int)m[0], (int)m[1], (int)m[2], (int)zc, (int)zin0, (int)nzin, (int)zout0, (int)ocount,
-                                     lin ? (int)gx : 0);
+                                     lin ? (int)gx : 0, sides ? *sides : no_sides<T>(zin0, nzin));
     count_launch();
     GB_CUDA(cudaGetLastError());
     return GB_OK;
@@ -854,7 +874,8 @@ template <typename T> int prolong12_impl(i64 n1, i64 n2, i64 nz, const T* in, i6
 
 // prolong(A, [m1,m2,m3]) (every dimension prolonged) on ONE SLAB of a 3-D array sharded along dim 3: `in` holds coarse
 // planes [in_first, in_first + dims[2]) of the n3 global ones, `out` receives fine planes [out_first, out_first + ocount).
-template <typename T> int prolong3_slab_impl(const i64* dims, const T* in, const i64* m, i64 n3, i64 in_first, i64 out_first, i64 ocount, T* out, cudaStream_t s) {
+template <typename T>
+int prolong3_slab_impl(const i64* dims, const T* in, const i64* m, i64 n3, i64 in_first, i64 out_first, i64 ocount, T* out, cudaStream_t s, const Sides<T>* sides = nullptr) {
     const i64 n1 = dims[0], n2 = dims[1], nloc = dims[2];
     const i64 nn[3] = {n1, n2, n3};
     for (int d = 0; d < 3; d++) {
@@ -868,8 +889,9 @@ template <typename T> int prolong3_slab_impl(const i64* dims, const T* in, const
     if (ocount == 0) return GB_OK;
     i64 lo, hi;
     prolong_needs(n3, m[2], out_first, out_first + ocount, &lo, &hi);
-    if (lo < in_first || hi >= in_first + nloc) return fail(GB_ERR_ARG, "prolong: the slab does not hold every input plane the requested outputs need");
-    return prolong3_march_launch<T, 8, 4>(in, out, n1, n2, n3, m, in_first, nloc, out_first, ocount, s);
+    const i64 have0 = sides ? sides->zmin : in_first, have1 = sides ? sides->zmax : in_first + nloc;
+    if (lo < have0 || hi >= have1) return fail(GB_ERR_ARG, "prolong: the slab does not hold every input plane the requested outputs need");
+    return prolong3_march_launch<T, 8, 4>(in, out, n1, n2, n3, m, in_first, nloc, out_first, ocount, s, sides);
 }
 
 // ---- synthetic inputs ---------------------------------------------------------------------------
@@ -1004,6 +1026,35 @@ int restrict3_slab_device(int dtype, const i64* dims, const void* in, double sca
 int prolong3_slab_device(int dtype, const i64* dims, const void* in, const i64* m, i64 n3, i64 in_first, i64 out_first, i64 ocount, void* out, cudaStream_t s) {
     if (dtype == GB_F64) return prolong3_slab_impl<double>(dims, (const double*)in, m, n3, in_first, out_first, ocount, (double*)out, s);
     if (dtype == GB_F32) return prolong3_slab_impl<float>(dims, (const float*)in, m, n3, in_first, out_first, ocount, (float*)out, s);
+    return fail(GB_ERR_ARG, "bad dtype");
+}
+// slab kernels whose halo planes are read in place from the neighbouring ranks' slabs (peer pointers; comm.cu): `lo` holds
+// input planes from lo_first on (NULL: none below), `hi` planes from hi_first on (NULL: none above), [zmin, zmax) exist in all
+template <typename T> Sides<T> make_sides(const void* lo, i64 lo_first, const void* hi, i64 hi_first, i64 zmin, i64 zmax) {
+    return Sides<T>{(const T*)lo, (const T*)hi, (int)lo_first, (int)hi_first, (int)zmin, (int)zmax};
+}
+int restrict3_slab_peer_device(int dtype, const i64* dims, const void* in, double scale, i64 L3, i64 in_first, const void* lo, i64 lo_first, const void* hi, i64 hi_first,
+                               i64 zmin, i64 zmax, i64 out_first, i64 ocount, void* out, cudaStream_t s) {
+    if (dtype == GB_F64) {
+        const Sides<double> sd = make_sides<double>(lo, lo_first, hi, hi_first, zmin, zmax);
+        return restrict3_slab_impl<double>(dims, (const double*)in, scale, L3, in_first, out_first, ocount, (double*)out, s, &sd);
+    }
+    if (dtype == GB_F32) {
+        const Sides<float> sd = make_sides<float>(lo, lo_first, hi, hi_first, zmin, zmax);
+        return restrict3_slab_impl<float>(dims, (const float*)in, scale, L3, in_first, out_first, ocount, (float*)out, s, &sd);
+    }
+    return fail(GB_ERR_ARG, "bad dtype");
+}
+int prolong3_slab_peer_device(int dtype, const i64* dims, const void* in, const i64* m, i64 n3, i64 in_first, const void* lo, i64 lo_first, const void* hi, i64 hi_first,
+                              i64 zmin, i64 zmax, i64 out_first, i64 ocount, void* out, cudaStream_t s) {
+    if (dtype == GB_F64) {
+        const Sides<double> sd = make_sides<double>(lo, lo_first, hi, hi_first, zmin, zmax);
+        return prolong3_slab_impl<double>(dims, (const double*)in, m, n3, in_first, out_first, ocount, (double*)out, s, &sd);
+    }
+    if (dtype == GB_F32) {
+        const Sides<float> sd = make_sides<float>(lo, lo_first, hi, hi_first, zmin, zmax);
+        return prolong3_slab_impl<float>(dims, (const float*)in, m, n3, in_first, out_first, ocount, (float*)out, s, &sd);
+    }
     return fail(GB_ERR_ARG, "bad dtype");
 }
 int prolong_slab_device(int dtype, int ndim, const i64* dims, const void* in, int dim, i64 n, i64 len, i64 in_first, i64 out_first, i64 ocount, void* out,

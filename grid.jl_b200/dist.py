@@ -185,6 +185,19 @@ class Comm:
         except Exception:
             pass
 
+    def peer_halo(self, enable=None):
+        """Peer-pointer halo reads (boundary kernels read the neighbours' slabs in place; single-process communicators with
+        peer access): enable True / False switches them, None only queries.  Returns the setting in force."""
+        on = C.c_int(0)
+        self._L.check(self._L.lib().gb_comm_peer_halo(self._h, -1 if enable is None else int(bool(enable)), C.byref(on)))
+        return bool(on.value)
+
+    def last_path(self):
+        """'peer' if the last sharded restrict / prolong read its halo planes through peer pointers, else 'exchange'."""
+        v = C.c_int(0)
+        self._L.check(self._L.lib().gb_comm_last_path(self._h, C.byref(v)))
+        return "peer" if v.value else "exchange"
+
     def stats(self):
         """Last sharded restrict / prolong, per local rank: dict(total_ms, interior_ms, halo_wait_ms, halo_bytes)."""
         out = (C.c_double * (4 * self.nlocal))()

@@ -309,6 +309,14 @@ int gb_prolong3_sharded(gb_comm* c, int dtype, const int64_t* global_dims, const
 /* Timing of the last sharded restrict / prolong call, 4 doubles per local rank: total ms, interior-kernel ms, time the
  * halo landed after the interior kernel had finished (ms; 0 = fully hidden), halo bytes received.  Waits for the call. */
 int gb_comm_stats(gb_comm* c, double* out, int n, int* nout);
+/* Peer mode of the sharded restrict / prolong: when one process drives every rank and the devices can map each other's
+ * memory (gb_comm_init_all on an NVLink box; loopback), there is no halo exchange -- the boundary kernel reads the
+ * neighbouring ranks' planes in place through peer pointers, on the priority stream, next to the interior kernel.  On by
+ * default where possible (GB_PEER_HALO=0 in the environment: off); enable = 1 / 0 switches it, any other value only
+ * queries; *enabled (may be NULL) receives the setting in force.  Calls whose stencils reach past the immediate neighbours,
+ * or whose slabs live in a memory pool peers cannot map (cudaMallocAsync), take the exchange on their own. */
+int gb_comm_peer_halo(gb_comm* c, int enable, int* enabled);
+int gb_comm_last_path(gb_comm* c, int* peer); /* 1: the last sharded restrict / prolong ran in peer mode, 0: it exchanged halos */
 
 /* ---- device / pinned memory helpers (device-resident query and output buffers) -------------- */
 int gb_device_alloc(void** ptr, size_t bytes);

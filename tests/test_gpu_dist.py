@@ -112,15 +112,21 @@ def test_single_process_all_devices():
     try:
         L3, n3 = shape[2], D.restrict_size(shape[2])
         fine = [gb.jl_from_numpy(np.asfortranarray(A[:, :, slice(*D.shard_range(L3, r, ndev))]), device="cuda:%d" % r) for r in range(ndev)]
-        coarse = comm.restrict3(fine, shape, 1.0, use_streams=False)
-        for r in range(ndev):
-            k0, k1 = D.shard_range(n3, r, ndev)
-            assert np.array_equal(gb.jl_to_numpy(coarse[r]), ref[:, :, k0:k1])
-        up = comm.prolong3(coarse, ref.shape, shape, use_streams=False)
-        for r in range(ndev):
-            f0, f1 = D.shard_range(L3, r, ndev)
-            assert np.array_equal(gb.jl_to_numpy(up[r]), refp[:, :, f0:f1])
-        assert sum(s["halo_bytes"] for s in comm.stats()) > 0
+        # both transports: peer pointers (boundary kernels read the neighbours' slabs over NVLink) and the NCCL exchange
+        capable = comm.peer_halo(True)
+        for peer in ([True, False] if capable else [False]):
+            assert comm.peer_halo(peer) == peer
+            coarse = comm.restrict3(fine, shape, 1.0, use_streams=False)
+            for r in range(ndev):
+                k0, k1 = D.shard_range(n3, r, ndev)
+                assert np.array_equal(gb.jl_to_numpy(coarse[r]), ref[:, :, k0:k1])
+            if min(L3, n3) >= 4 * ndev:
+                assert comm.last_path() == ("peer" if peer else "exchange")
+            up = comm.prolong3(coarse, ref.shape, shape, use_streams=False)
+            for r in range(ndev):
+                f0, f1 = D.shard_range(L3, r, ndev)
+                assert np.array_equal(gb.jl_to_numpy(up[r]), refp[:, :, f0:f1])
+            assert sum(s["halo_bytes"] for s in comm.stats()) > 0
         # replicate + host batch split over the devices
         co = O.make_coefs(A, "nan", "cubic")
         with torch.cuda.device(0):

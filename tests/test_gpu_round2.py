@@ -379,9 +379,12 @@ def test_interp_irregular_batched_entry_points(gb):
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("shape,world", [((40, 36, 50), 2), ((33, 20, 64), 3), ((20, 18, 129), 5), ((12, 10, 17), 8), ((9, 8, 20), 4), ((66, 40, 128), 8),
                                          ((12, 10, 5), 8), ((9, 8, 6), 8)])  # (the last two: more ranks than planes -- ranks that own or produce nothing)
-def test_comm_loopback_sharded_multigrid(gb, oracle, dtype, shape, world):
+@pytest.mark.parametrize("peer", [1, 0])
+def test_comm_loopback_sharded_multigrid(gb, oracle, dtype, shape, world, peer):
     """gb_restrict3_sharded / gb_prolong3_sharded on `world` virtual ranks of one GPU (gb_comm_init_loopback): plan, halo
-    planes, interior / boundary split and the slab kernels -- assembled slabs equal the unsharded oracle result bitwise."""
+    planes, interior / boundary split and the slab kernels -- assembled slabs equal the unsharded oracle result bitwise.
+    peer = 1: the boundary kernel reads the neighbours' planes in place through (here: same-device) peer pointers, falling
+    back to the exchange where a stencil reaches past the immediate neighbours; peer = 0: halo exchange + assembled buffers."""
     import torch
 
     import grid_jl_b200.dist as D
@@ -392,6 +395,7 @@ def test_comm_loopback_sharded_multigrid(gb, oracle, dtype, shape, world):
     comm = D.Comm.loopback(world)
     try:
         assert (comm.nranks, comm.nlocal, comm.first_rank) == (world, world, 0)
+        assert comm.peer_halo(peer) == bool(peer) and comm.peer_halo() == bool(peer)
         L3, n3 = shape[2], D.restrict_size(shape[2])
         fine = [gb.jl_from_numpy(np.asfortranarray(A[:, :, slice(*D.shard_range(L3, r, world))])) for r in range(world)]
         for use_streams in (True, False):
@@ -409,6 +413,9 @@ def test_comm_loopback_sharded_multigrid(gb, oracle, dtype, shape, world):
                 assert same(gb.jl_to_numpy(up[r]), np.asfortranarray(refp[:, :, f0:f1])), ("prolong", r)
         halo = sum(s["halo_bytes"] for s in comm.stats())
         assert (halo > 0) == (world > 1)
+        # slabs at least a few planes thick on every level: the peer route is really taken when it is on
+        if min(L3, n3) >= 4 * world:
+            assert comm.last_path() == ("peer" if peer else "exchange")
     finally:
         comm.close()
 
