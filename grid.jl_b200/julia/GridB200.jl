@@ -16,7 +16,7 @@ export BoundaryCondition, BCnil, BCnan, BCna, BCreflect, BCperiodic, BCnearest, 
        valgrad, valgradhess, getindex!, valgrad!, valgradhess!, valgrad_packed!,
        interp_invert!, pad1, restrict, prolong, restrict_size, prolong_size,
        restrictb, restrict_extrap, prolongb, interp_channels!, InterpIrregular, InterpForward, InterpBackward,
-       filledges!, pin!, unpin!, GridComm, replicate, getindex_sharded!, valgrad_sharded!, restrict3_sharded, prolong3_sharded
+       filledges!, pin!, unpin!, GridComm, replicate, getindex_sharded!, valgrad_sharded!, restrict3_sharded, prolong3_sharded, peer_halo!
 
 const LIB = get(ENV, "GRIDB200_LIB", joinpath(@__DIR__, "..", "libgridb200.so"))
 
@@ -416,6 +416,13 @@ function GridComm(ndev::Integer)
     c = GridComm(h[], ndev)
     finalizer(x -> ccall((:gb_comm_destroy, LIB), Cint, (Ptr{Cvoid},), x.handle), c)
     c
+end
+# peer_halo!(comm, on): sharded restrict / prolong read their halo planes in place from the neighbouring devices' slabs through
+# peer (NVLink) pointers -- no exchange; on by default where the devices can map each other's memory.  Returns the setting in force.
+function peer_halo!(c::GridComm, on::Bool)
+    e = Ref{Cint}(0)
+    check(ccall((:gb_comm_peer_halo, LIB), Cint, (Ptr{Cvoid}, Cint, Ref{Cint}), c.handle, on ? 1 : 0, e))
+    e[] != 0
 end
 # replicate(comm, G): G lives on device 0; returns one handle per device (the first is G's own)
 function replicate(c::GridComm, G::InterpGrid{T,N,BC,IT}) where {T,N,BC,IT}
