@@ -399,7 +399,7 @@ template <typename T> __device__ __forceinline__ const T* slab_plane(const T* __
 template <typename T> Sides<T> no_sides(i64 zin0, i64 nzin) { return Sides<T>{nullptr, nullptr, 0, 0, (int)zin0, (int)(zin0 + nzin)}; }
 // A lane owns outputs x = 2*lane, 2*lane+1 of the 64-wide tile: their eight taps are six consecutive inputs (three
 // aligned 16-byte loads), and shared memory moves pairs (one column per lane: 2.94 instead of 2.63 ms per chain).
-template <typename T, int BY, int NW, int UN, bool DO3> __global__ void __launch_bounds__(32 * NW) restrict3_march_kernel(const T* __restrict__ A, T* __restrict__ R, int L1, int L2, int L3, int n1,
+template <typename T, int BY, int NW, int UN, bool DO3, bool PEER> __global__ void __launch_bounds__(32 * NW) restrict3_march_kernel(const T* __restrict__ A, T* __restrict__ R, int L1, int L2, int L3, int n1,
                                                                                                         int n2, int n3, int zc, RCoef<T> c, int zin0, int nzin,
                                                                                                         int zout0, int ocount, int xtiles, const Sides<T> sd) {
     // slab form: A holds input planes [zin0, zin0 + nzin) of the L3 global ones, R output planes [zout0, zout0 + ocount)
@@ -418,8 +418,9 @@ template <typename T, int BY, int NW, int UN, bool DO3> __global__ void __launch
     const int nzo = min(zc, zout0 + ocount - j3);
     const int y0 = 2 * j2 - 2, z0 = DO3 ? 2 * j3 - 2 : j3;
     const bool ev1 = !(L1 & 1), ev2 = !(L2 & 1), ev3 = !(L3 & 1);
-    const bool vec = !(L1 & 1) && (((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(sd.lo) | reinterpret_cast<uintptr_t>(sd.hi)) & (sizeof(V) - 1)) ==
-                                   0);  // rows aligned to a pair (16 B for f64, 8 B for f32)
+    // rows aligned to a pair (16 B for f64, 8 B for f32); PEER (compile time): the side arrays too -- the single-array kernel is unchanged
+    const bool vec = !(L1 & 1) && (((reinterpret_cast<uintptr_t>(A) | (PEER ? reinterpret_cast<uintptr_t>(sd.lo) | reinterpret_cast<uintptr_t>(sd.hi) : 0)) &
+                                    (sizeof(V) - 1)) == 0);
     const int gx = j1 + 2 * lane;
     const bool xfull = j1 >= 1 && j1 + BX - 1 <= n1 - 2;  // warp-uniform: every output of the tile has all four taps
     const bool vx0 = gx < n1, vx1 = gx + 1 < n1;
@@ -427,10 +428,10 @@ template <typename T, int BY, int NW, int UN, bool DO3> __global__ void __launch
     const size_t plane = (size_t)L2 * (size_t)L1;
     for (int p = 0; p < (DO3 ? 2 * nzo + 2 : nzo); p++) {
         const int gz = z0 + p;
-        const bool zok = gz >= sd.zmin && gz < sd.zmax;  // (planes a needed tap lies on are present: checked by the host)
+        const bool zok = PEER ? (gz >= sd.zmin && gz < sd.zmax) : (gz >= zin0 && gz < zin0 + nzin);  // (planes a needed tap lies on are present: checked by the host)
         // ---- stage A: dim-1 restriction; inputs t[0..5] = A[2gx-2 .. 2gx+3]
         if (zok && j1 < n1) {
-            const T* Ac = slab_plane<T>(A, zin0, nzin, sd, gz, plane) + 2 * gx;
+            const T* Ac = (PEER ? slab_plane<T>(A, zin0, nzin, sd, gz, plane) : A + (size_t)(gz - zin0) * plane) + 2 * gx;
 #pragma unroll 1
             for (int k0 = 0; k0 < (IY + NW - 1) / NW; k0 += UN) {
                 T t[UN][6];
@@ -537,7 +538,7 @@ int restrict3_march_launch(const T* in, T* out, i64 L1, i64 L2, i64 L3, i64 n1, 
                            const Sides<T>* sides = nullptr) {
     constexpr int BX = 64, IY = 2 * BY + 2;
     const size_t smem = sizeof(T) * (size_t)(IY * BX + 4 * BY * BX);
-    auto kern = restrict3_march_kernel<T, BY, NW, UN, DO3>;
+    auto kern = sides ? restrict3_march_kernel<T, BY, NW, UN, DO3, true> : restrict3_march_kernel<T, BY, NW, UN, DO3, false>;
     GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const i64 gx = (n1 + BX - 1) / BX, gy = (n2 + BY - 1) / BY;
     i64 zc = 32;  // (16: 2.63, 32: 2.64, 64: 2.68, 128: 2.80, 256: 3.13 ms per chain)
@@ -706,7 +707,7 @@ template <typename T, int BY, int BZ> __global__ void __launch_bounds__(256) pro
 // slots S2[2][BY][64] (stage B); two consecutive slots then give two output planes (stage C, coalesced 512-byte
 // rows).  A lane owns the output pair x = 2*lane, 2*lane+1 for the whole kernel: both come from the same two
 // inputs, the parities are compile-time, and shared memory and (for even row lengths) global stores move pairs.  Same prolong_at calls in the same order as the brick kernel, hence the same bits.
-template <typename T, int BY, int NW, bool DO3> __global__ void __launch_bounds__(32 * NW) prolong3_march_kernel(const T* __restrict__ A, T* __restrict__ P, int n1, int n2, int n3, int m1, int m2,
+template <typename T, int BY, int NW, bool DO3, bool PEER> __global__ void __launch_bounds__(32 * NW) prolong3_march_kernel(const T* __restrict__ A, T* __restrict__ P, int n1, int n2, int n3, int m1, int m2,
                                                                                                int m3, int zc, int zin0, int nzin, int zout0, int ocount, int xtiles,
                                                                                                const Sides<T> sd) {
     // slab form: A holds input planes [zin0, zin0 + nzin) (of the n3 global ones), P output planes [zout0, zout0 + ocount) of the
@@ -728,10 +729,10 @@ template <typename T, int BY, int NW, bool DO3> __global__ void __launch_bounds_
     const size_t iplane = (size_t)n2 * (size_t)n1, oplane = (size_t)m2 * (size_t)m1;
     for (int ip = 0; DO3 ? 2 * (ip - 1) < nplanes : ip < nplanes; ip++) {
         const int lz = z0 + ip;
-        const bool zin = lz < n3 && lz < sd.zmax;  // (planes a needed tap lies on are present: checked by the host)
+        const bool zin = lz < n3 && lz < (PEER ? sd.zmax : zin0 + nzin);  // (planes a needed tap lies on are present: checked by the host)
         // ---- stage A: dim-1 prolongation of input plane lz, rows y0 .. y0+NY-1
         if (zin) {
-            const T* Az = slab_plane<T>(A, zin0, nzin, sd, lz, iplane) + xi;
+            const T* Az = (PEER ? slab_plane<T>(A, zin0, nzin, sd, lz, iplane) : A + (size_t)(lz - zin0) * iplane) + xi;
             for (int y = warp; y < NY; y += NW) {
                 const int gy = y0 + y;
                 V v{(T)0, (T)0};
@@ -807,7 +808,7 @@ template <typename T, int BY, int NW, bool DO3 = true>
 int prolong3_march_launch(const T* in, T* out, i64 n1, i64 n2, i64 n3, const i64* m, i64 zin0, i64 nzin, i64 zout0, i64 ocount, cudaStream_t s, const Sides<T>* sides = nullptr) {
     constexpr int BX = 64, NY = BY / 2 + 1;
     const size_t smem = sizeof(T) * (size_t)(NY * BX + 2 * BY * BX);
-    auto kern = prolong3_march_kernel<T, BY, NW, DO3>;
+    auto kern = sides ? prolong3_march_kernel<T, BY, NW, DO3, true> : prolong3_march_kernel<T, BY, NW, DO3, false>;
     GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const i64 gx = (m[0] + BX - 1) / BX, gy = (m[1] + BY - 1) / BY;
     i64 zc = 32;  // output planes per chunk (even): one extra input plane per chunk (16: 2.31, 32: 2.29, 64: 2.34, 128: 2.36, 256: 2.42 ms per chain)
