@@ -41,7 +41,24 @@ def chain(levels_stats=None):
     sync()
     return t1
 
+def snapshot():
+    """every level of one chain (restrict down, prolong up), as CPU tensors"""
+    cur, out = fine, []
+    for L in sizes[:-1]:
+        cur = comm.restrict3(cur, (L, L, L), 1.0)
+        if L <= 257: out += [c.cpu() for c in cur]
+    for L, Lf in zip(reversed(sizes[1:]), reversed(sizes[:-1])):
+        cur = comm.prolong3(cur, (L, L, L), (Lf, Lf, Lf))
+        if Lf <= 257: out += [c.cpu() for c in cur]
+    out += [c[:, :, :2].cpu() for c in cur] + [c[:, :, -2:].cpu() for c in cur]  # the finest level: the planes next to the slab faces
+    return out
+
 print("devices", ndev, "peer capable", comm.peer_halo(True))
+if comm.peer_halo(True):
+    a = snapshot(); assert comm.last_path() == "peer"
+    comm.peer_halo(False); b = snapshot(); assert comm.last_path() == "exchange"
+    assert len(a) == len(b) and all(torch.equal(x, y) for x, y in zip(a, b))
+    print("peer mode == exchange mode bitwise on", len(a), "arrays")
 for peer in ([True, False] if comm.peer_halo(True) else [False]):
     comm.peer_halo(peer)
     for _ in range(3): chain()
