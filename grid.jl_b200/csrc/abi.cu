@@ -954,8 +954,16 @@ int eval_host_staged(const gb_grid* g, int out_mask, int outmode, i64 nq, const 
         if (rc != GB_OK) msgs[w] = gb_last_error();
     };
     std::vector<std::thread> th;
-    for (int w = 1; w < T; w++) th.emplace_back(worker, w);
+    std::vector<int> inline_w;  // workers whose thread could not be created run here, one after the other
+    for (int w = 1; w < T; w++) {
+        try {
+            th.emplace_back(worker, w);
+        } catch (const std::exception&) {
+            inline_w.push_back(w);
+        }
+    }
     worker(0);
+    for (int w : inline_w) worker(w);
     for (auto& t : th) t.join();
     int rc = GB_OK;
     for (int w = 0; w < T && rc == GB_OK; w++)
@@ -976,20 +984,43 @@ int eval_host_staged(const gb_grid* g, int out_mask, int outmode, i64 nq, const 
 // ---- small host batches: the scalar API ----------------------------------------------------------------------------------
 // G[x], valgrad(G, x) and short batches arrive here one C call at a time (GridB200.jl evaluates a scalar query per ccall):
 // three stream creations, a dozen pool allocations and as many frees cost 150-170 us per call, ten times the work itself.
-// Up to SMALL_MAX queries therefore go through a per-thread, per-device context that is created once -- one stream, one pinned
-// and one device staging buffer (layout: coordinates | first-invalid word | outputs): memcpy in, ONE copy to the device, the
-// kernel, ONE copy back, synchronise, memcpy out.  (Deliberately never destroyed: thread-exit destructors must not call CUDA.)
+// Up to SMALL_MAX queries therefore go through a context that is created once and reused -- one stream, one pinned and one
+// device staging buffer (layout: coordinates | first-invalid word | outputs): memcpy in, ONE copy to the device, the kernel,
+// ONE copy back, synchronise, memcpy out.  Contexts live in a per-device free list (a call takes one, returns it): as many
+// exist as calls ever ran at the same time, whatever the number of host threads that come and go.  (Never destroyed: nothing
+// may call CUDA at process exit.)
 constexpr i64 SMALL_MAX = 1 << 15;
 struct SmallCtx {
     cudaStream_t s;
     char *pin, *dev;
     size_t bytes;
 };
+struct SmallPool {
+    std::mutex mu;
+    std::vector<SmallCtx*> free_list;
+};
+SmallPool g_small[STAGE_MAX_DEV];
+struct SmallLease {
+    SmallPool& pool;
+    SmallCtx* c;
+    explicit SmallLease(SmallPool& p) : pool(p), c(nullptr) {
+        std::lock_guard<std::mutex> lk(pool.mu);
+        if (!pool.free_list.empty()) {
+            c = pool.free_list.back();
+            pool.free_list.pop_back();
+        }
+        if (!c) c = new SmallCtx{nullptr, nullptr, nullptr, 0};
+    }
+    ~SmallLease() {
+        std::lock_guard<std::mutex> lk(pool.mu);
+        pool.free_list.push_back(c);
+    }
+};
 int eval_host_small(const gb_grid* g, int out_mask, int outmode, i64 nq, const void* const* xcols, const void* xaos, int xdtype, const double* affine,
                     void* val, void* grad, void* hess, int flags, int64_t* first_invalid) {
-    static thread_local SmallCtx ctxs[STAGE_MAX_DEV] = {};
     if (g->device < 0 || g->device >= STAGE_MAX_DEV) return fail(GB_ERR_ARG, "device index out of range");
-    SmallCtx& c = ctxs[g->device];
+    SmallLease lease(g_small[g->device]);
+    SmallCtx& c = *lease.c;
     const int N = g->ndim;
     const size_t xs = esize(xdtype), es = esize(g->dtype) * (size_t)g->nchan;
     const int packed = packed_words(g, out_mask, outmode);

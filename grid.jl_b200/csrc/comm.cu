@@ -759,8 +759,8 @@ int gb_eval_sharded(gb_comm* c, gb_grid* const* grids, int out_mask, int64_t nq,
     std::vector<int64_t> bad(nl, -1);
     std::vector<std::string> msgs(nl);
     std::vector<std::thread> th;
-    for (int i = 0; i < nl; i++) {
-        th.emplace_back([&, i] {
+    auto shard_eval = [&](int i) {
+        {
             i64 q0, q1;
             shard(nq, i, nl, &q0, &q1);
             if (q1 <= q0) return;
@@ -771,8 +771,21 @@ int gb_eval_sharded(gb_comm* c, gb_grid* const* grids, int out_mask, int64_t nq,
                              first_invalid ? &bad[i] : nullptr, nullptr);
             if (rcs[i]) msgs[i] = gb_last_error();
             if (bad[i] >= 0) bad[i] += q0;
-        });
+        }
+    };
+    std::vector<int> inline_i;  // (a thread that cannot be created: that shard runs on the calling thread)
+    for (int i = 1; i < nl; i++) {
+        try {
+            th.emplace_back(shard_eval, i);
+        } catch (const std::exception&) {
+            inline_i.push_back(i);
+        }
     }
+    int prev_dev = 0;
+    cudaGetDevice(&prev_dev);
+    shard_eval(0);
+    for (int i : inline_i) shard_eval(i);
+    cudaSetDevice(prev_dev);
     for (auto& t : th) t.join();
     for (int i = 0; i < nl; i++) {
         if (first_invalid && bad[i] >= 0 && (*first_invalid < 0 || bad[i] < *first_invalid)) *first_invalid = bad[i];
