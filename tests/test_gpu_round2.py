@@ -133,7 +133,7 @@ print("ok")
 
 
 def test_small_host_batches_fast_path(gb, oracle):
-    """Host batches up to 2^15 queries (the scalar API: one query per C call) run through a per-thread context that is
+    """Host batches up to 2^15 queries (the scalar API: one query per C call) run through a pooled context that is
     created once (abi.cu: eval_host_small).  Bits as the oracle's for scalar calls, short batches of every output kind,
     column inputs, Float32, packed records, a multi-valued grid, growing and shrinking sizes, calls from several threads, and
     BCnil's error with the first invalid query."""
