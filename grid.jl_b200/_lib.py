@@ -57,6 +57,8 @@ SIGNATURES = {
     "gb_eval_sharded": (i32, [vp, p_vp, i32, i64, vp, i32, p_f64, vp, vp, vp, i32, p_i64]),
     "gb_restrict3_sharded": (i32, [vp, i32, p_i64, p_vp, f64, p_vp, p_vp]),
     "gb_prolong3_sharded": (i32, [vp, i32, p_i64, p_vp, p_i64, p_vp, p_vp]),
+    "gb_restrict3_sharded_levels": (i32, [vp, i32, p_i64, i32, p_vp, f64, p_vp, p_vp]),
+    "gb_prolong3_sharded_levels": (i32, [vp, i32, p_i64, i32, p_i64, p_vp, p_vp, p_vp]),
     "gb_comm_stats": (i32, [vp, p_f64, i32, p_i32]),
     "gb_comm_peer_halo": (i32, [vp, i32, p_i32]),
     "gb_comm_last_path": (i32, [vp, p_i32]),

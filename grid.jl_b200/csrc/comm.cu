@@ -155,6 +155,10 @@ struct LocalRank {
     cudaEvent_t ev_in = nullptr, ev_halo = nullptr;  // inputs ready (work -> comm), halo landed (comm -> work)
     cudaEvent_t ev_t0 = nullptr, ev_int = nullptr, ev_t1 = nullptr, ev_h1 = nullptr;  // timing (created with timing enabled)
     cudaEvent_t ev_done = nullptr;  // peer mode: this rank's kernels have read their neighbours' slabs
+    void* scratch[2] = {nullptr, nullptr};  // intermediate levels of the multi-level calls (sharded_levels)
+    size_t scratch_cap[2] = {0, 0};
+    cudaEvent_t ev_scratch = nullptr;  // end of the last multi-level call on this rank
+    bool scratch_used = false;
     void* halo = nullptr;  // [lo planes | hi planes]
     size_t halo_cap = 0;
     double halo_bytes = 0;  // last call
@@ -208,6 +212,7 @@ int init_local(LocalRank& l) {
     GB_CUDA(cudaEventCreate(&l.ev_t1));
     GB_CUDA(cudaEventCreate(&l.ev_h1));
     GB_CUDA(cudaEventCreateWithFlags(&l.ev_done, cudaEventDisableTiming));
+    GB_CUDA(cudaEventCreateWithFlags(&l.ev_scratch, cudaEventDisableTiming));
     return GB_OK;
 }
 bool peer_default() {
@@ -249,11 +254,11 @@ int ensure_halo(LocalRank& l, size_t bytes) {
 
 // One sharded multigrid level.  kind 0: restrict3 (in: fine slabs, L = global fine extents), kind 1: prolong3 (in: coarse
 // slabs, n = global coarse extents, m = global target extents).
-int sharded_level(gb_comm* c, int kind, int dtype, const i64* gin, const i64* gout, const void* const* in_slabs, double scale, void* const* out_slabs,
-                  void* const* streams) {
+// (the caller holds c->mu; sync_end: with library-owned work streams, wait for the results before returning)
+int sharded_level_locked(gb_comm* c, int kind, int dtype, const i64* gin, const i64* gout, const void* const* in_slabs, double scale, void* const* out_slabs,
+                         void* const* streams, bool sync_end) {
     if (!c || !gin || !gout || !in_slabs || !out_slabs) return fail(GB_ERR_ARG, "NULL argument");
     if (dtype != GB_F32 && dtype != GB_F64) return fail(GB_ERR_ARG, "bad dtype");
-    std::lock_guard<std::mutex> lk(c->mu);
     const int W = c->nranks, nl = (int)c->loc.size();
     const i64 n_in = gin[2], n_out = gout[2];
     const Plan plan(kind, n_in, n_out, W);
@@ -460,10 +465,92 @@ int sharded_level(gb_comm* c, int kind, int dtype, const i64* gin, const i64* go
         }
         GB_CUDA(cudaEventRecord(l.ev_t1, ws[i]));
     }
-    if (!streams) {  // library-owned work streams: the call returns with the results in place
+    if (!use_peer && c->loopback) {  // the copies out of a source slab ran on the DESTINATION's comm stream: the source's work stream
+        for (const Transfer& t : plan.xfers) {  // (whatever the caller does to that slab next) waits for them
+            const int si = local_of(t.src), di = local_of(t.dst);
+            if (si < 0 || di < 0) continue;
+            DevGuard g(c->loc[si].dev);
+            GB_CUDA(cudaStreamWaitEvent(ws[si], c->loc[di].ev_halo, 0));
+        }
+    }
+    if (!streams && sync_end) {  // library-owned work streams: the call returns with the results in place
         for (int i = 0; i < nl; i++) {
             DevGuard g(c->loc[i].dev);
             GB_CUDA(cudaStreamSynchronize(ws[i]));
+        }
+    }
+    return GB_OK;
+}
+int sharded_level(gb_comm* c, int kind, int dtype, const i64* gin, const i64* gout, const void* const* in_slabs, double scale, void* const* out_slabs,
+                  void* const* streams) {
+    if (!c) return fail(GB_ERR_ARG, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    return sharded_level_locked(c, kind, dtype, gin, gout, in_slabs, scale, out_slabs, streams, true);
+}
+
+// Several levels in one call -- the reference's restrict(A, flags) with one all-true column per level / prolong(A, sizes) with
+// one column of sizes per level (mapdim, src/utilities.jl:7-20): the intermediate levels live in two scratch arrays per rank
+// that belong to the communicator (plain cudaMalloc, so neighbours can map them in peer mode), nothing returns to the host
+// language between levels, and only the last level lands in the caller's slabs.  dims_levels: 3 x (nlevels + 1) global
+// extents, column l = the array that enters level l (column nlevels = the result).
+int sharded_levels(gb_comm* c, int kind, int dtype, const i64* dims_levels, int nlevels, const void* const* in_slabs, double scale, void* const* out_slabs,
+                   void* const* streams) {
+    if (!c || !dims_levels || !in_slabs || !out_slabs) return fail(GB_ERR_ARG, "NULL argument");
+    if (nlevels < 1) return fail(GB_ERR_ARG, "nlevels < 1");
+    if (dtype != GB_F32 && dtype != GB_F64) return fail(GB_ERR_ARG, "bad dtype");
+    std::lock_guard<std::mutex> lk(c->mu);
+    const int W = c->nranks, nl = (int)c->loc.size();
+    const size_t es = esz(dtype);
+    // scratch for the intermediate levels: level l's output goes to scratch[l & 1]
+    if (nlevels > 1) {
+        for (int i = 0; i < nl; i++) {
+            LocalRank& l = c->loc[i];
+            size_t need[2] = {0, 0};
+            for (int lev = 0; lev + 1 < nlevels; lev++) {
+                const i64* d = dims_levels + 3 * (lev + 1);
+                i64 a, b;
+                shard(d[2], l.rank, W, &a, &b);
+                need[lev & 1] = std::max(need[lev & 1], (size_t)d[0] * (size_t)d[1] * (size_t)(b - a) * es);
+            }
+            DevGuard g(l.dev);
+            for (int k = 0; k < 2; k++) {
+                if (need[k] <= l.scratch_cap[k]) continue;
+                if (l.scratch[k]) {  // earlier calls (on any stream) may still use the old array
+                    GB_CUDA(cudaDeviceSynchronize());
+                    cudaFree(l.scratch[k]);
+                    l.scratch[k] = nullptr;
+                    l.scratch_cap[k] = 0;
+                }
+                GB_CUDA(cudaMalloc(&l.scratch[k], need[k]));
+                l.scratch_cap[k] = need[k];
+            }
+            // the scratch arrays may still be read by the previous call's last level (another stream, a neighbour)
+            cudaStream_t w = streams ? (cudaStream_t)streams[i] : l.ws;
+            if (l.scratch_used) GB_CUDA(cudaStreamWaitEvent(w, l.ev_scratch, 0));
+        }
+    }
+    std::vector<const void*> ins(nl);
+    std::vector<void*> outs(nl);
+    for (int i = 0; i < nl; i++) ins[i] = in_slabs[i];
+    int all_peer = 1;
+    for (int lev = 0; lev < nlevels; lev++) {
+        const bool last = lev + 1 == nlevels;
+        for (int i = 0; i < nl; i++) outs[i] = last ? out_slabs[i] : c->loc[i].scratch[lev & 1];
+        const i64* gin = dims_levels + 3 * lev;
+        const i64* gout = dims_levels + 3 * (lev + 1);
+        // (a rank that owns no plane of a level passes whatever pointer it has: nothing is read or written through it)
+        int rc = sharded_level_locked(c, kind, dtype, gin, gout, ins.data(), scale, outs.data(), streams, last);
+        if (rc) return rc;
+        all_peer &= c->last_peer;
+        for (int i = 0; i < nl; i++) ins[i] = outs[i];
+    }
+    c->last_peer = all_peer;
+    if (nlevels > 1) {
+        for (int i = 0; i < nl; i++) {
+            LocalRank& l = c->loc[i];
+            DevGuard g(l.dev);
+            GB_CUDA(cudaEventRecord(l.ev_scratch, streams ? (cudaStream_t)streams[i] : l.ws));
+            l.scratch_used = true;
         }
     }
     return GB_OK;
@@ -628,7 +715,9 @@ int gb_comm_destroy(gb_comm* c) {
         if (l.ws) cudaStreamSynchronize(l.ws);
         if (l.comm && c->api) c->api->CommDestroy(l.comm);
         if (l.halo) cudaFree(l.halo);
-        for (cudaEvent_t e : {l.ev_in, l.ev_halo, l.ev_t0, l.ev_int, l.ev_t1, l.ev_h1, l.ev_done})
+        for (void* p : l.scratch)
+            if (p) cudaFree(p);
+        for (cudaEvent_t e : {l.ev_in, l.ev_halo, l.ev_t0, l.ev_int, l.ev_t1, l.ev_h1, l.ev_done, l.ev_scratch})
             if (e) cudaEventDestroy(e);
         if (l.cs) cudaStreamDestroy(l.cs);
         if (l.ws) cudaStreamDestroy(l.ws);
@@ -679,6 +768,35 @@ int gb_prolong3_sharded(gb_comm* c, int dtype, const int64_t* global_dims, const
         if (out_dims[d] <= global_dims[d]) return fail(GB_ERR_UNSUPPORTED, "gb_prolong3_sharded: every dimension must grow (use gb_prolong_slab per dimension)");
     }
     return sharded_level(c, 1, dtype, (const i64*)global_dims, (const i64*)out_dims, in_slabs, 1.0, out_slabs, streams);
+}
+
+int gb_restrict3_sharded_levels(gb_comm* c, int dtype, const int64_t* global_dims, int nlevels, const void* const* in_slabs, double scale, void* const* out_slabs,
+                                void* const* streams) {
+    if (!global_dims || nlevels < 1 || nlevels > 64) return fail(GB_ERR_ARG, "gb_restrict3_sharded_levels: bad arguments");
+    std::vector<i64> dims(3 * (size_t)(nlevels + 1));
+    for (int d = 0; d < 3; d++) dims[d] = global_dims[d];
+    for (int l = 0; l < nlevels; l++)
+        for (int d = 0; d < 3; d++) {
+            if (dims[3 * l + d] < 2) return fail(GB_ERR_UNSUPPORTED, "gb_restrict3_sharded_levels: extents below 2 (use gb_restrict_slab per dimension)");
+            dims[3 * (l + 1) + d] = rsize1(dims[3 * l + d]);
+        }
+    return sharded_levels(c, 0, dtype, dims.data(), nlevels, in_slabs, scale, out_slabs, streams);
+}
+
+int gb_prolong3_sharded_levels(gb_comm* c, int dtype, const int64_t* global_dims, int nlevels, const int64_t* out_dims, const void* const* in_slabs,
+                               void* const* out_slabs, void* const* streams) {
+    if (!global_dims || !out_dims || nlevels < 1 || nlevels > 64) return fail(GB_ERR_ARG, "gb_prolong3_sharded_levels: bad arguments");
+    std::vector<i64> dims(3 * (size_t)(nlevels + 1));
+    for (int d = 0; d < 3; d++) dims[d] = global_dims[d];
+    for (int l = 0; l < nlevels; l++)
+        for (int d = 0; d < 3; d++) {
+            const i64 from = dims[3 * l + d], to = out_dims[3 * l + d];
+            int rc = gb_prolong_size(from, to, nullptr);
+            if (rc) return rc;
+            if (to <= from) return fail(GB_ERR_UNSUPPORTED, "gb_prolong3_sharded_levels: every dimension must grow at every level");
+            dims[3 * (l + 1) + d] = to;
+        }
+    return sharded_levels(c, 1, dtype, dims.data(), nlevels, in_slabs, 1.0, out_slabs, streams);
 }
 
 // Replicate a grid's coefficients from the rank that holds it to every rank: one ncclBroadcast of the stored array.

@@ -242,6 +242,54 @@ class Comm:
     def prolong3(self, slabs, global_dims, out_dims, use_streams=True):
         return self._level("prolong", slabs, tuple(int(v) for v in global_dims), tuple(int(v) for v in out_dims), 1.0, use_streams)
 
+    def restrict3_levels(self, slabs, global_dims, nlevels, scale=1.0, use_streams=True):
+        """restrict(A, flags) with `nlevels` all-true columns in ONE library call (intermediate levels stay in the
+        communicator's scratch arrays): returns the slabs of the last level."""
+        import torch
+
+        from .api import _Arr, _i64s, jl_empty
+
+        L = self._L
+        gd = tuple(int(v) for v in global_dims)
+        od = gd
+        for _ in range(int(nlevels)):
+            od = tuple(restrict_size(v) for v in od)
+        outs, ip, op, sp = self._levels_io(slabs, gd, od, torch, _Arr, jl_empty)
+        sps = (C.c_void_p * self.nlocal)(*[torch.cuda.current_stream(a.device).cuda_stream for a in slabs]) if use_streams else None
+        dt = L.GB_F32 if slabs[0].dtype == torch.float32 else L.GB_F64
+        L.check(L.lib().gb_restrict3_sharded_levels(self._h, dt, _i64s(gd), int(nlevels), ip, float(scale), op, sps))
+        return outs
+
+    def prolong3_levels(self, slabs, global_dims, sizes, use_streams=True):
+        """prolong(A, sizes) with one column of target sizes per level (`sizes`: list of 3-tuples) in ONE library call."""
+        import torch
+
+        from .api import _Arr, _i64s, jl_empty
+
+        L = self._L
+        gd = tuple(int(v) for v in global_dims)
+        cols = [tuple(int(v) for v in col) for col in sizes]
+        outs, ip, op, sp = self._levels_io(slabs, gd, cols[-1], torch, _Arr, jl_empty)
+        sps = (C.c_void_p * self.nlocal)(*[torch.cuda.current_stream(a.device).cuda_stream for a in slabs]) if use_streams else None
+        dt = L.GB_F32 if slabs[0].dtype == torch.float32 else L.GB_F64
+        L.check(L.lib().gb_prolong3_sharded_levels(self._h, dt, _i64s(gd), len(cols), _i64s([v for col in cols for v in col]), ip, op, sps))
+        return outs
+
+    def _levels_io(self, slabs, gd, od, torch, _Arr, jl_empty):
+        assert len(slabs) == self.nlocal
+        outs, ip, op = [], [], []
+        for i, a in enumerate(slabs):
+            r = self.first_rank + i
+            f0, f1 = shard_range(gd[2], r, self.nranks)
+            k0, k1 = shard_range(od[2], r, self.nranks)
+            assert tuple(a.shape) == (gd[0], gd[1], f1 - f0), "slab %d has the wrong shape" % r
+            with torch.cuda.device(a.device):
+                o = jl_empty((od[0], od[1], k1 - k0), a.dtype, a.device)
+            outs.append(o)
+            ip.append(_Arr(a, name="slab").ptr if f1 > f0 else None)
+            op.append(o.data_ptr() if k1 > k0 else None)
+        return outs, (C.c_void_p * self.nlocal)(*ip), (C.c_void_p * self.nlocal)(*op), None
+
     def replicate(self, grids, src_rank, meta):
         """grids: list (one per local rank; the source rank's entry an InterpGrid, the others None) -> list of InterpGrids.
         meta = (stored_shape, eltype, BC, IT, fill) -- every process passes the same."""

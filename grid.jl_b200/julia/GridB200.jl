@@ -16,7 +16,7 @@ export BoundaryCondition, BCnil, BCnan, BCna, BCreflect, BCperiodic, BCnearest, 
        valgrad, valgradhess, getindex!, valgrad!, valgradhess!, valgrad_packed!,
        interp_invert!, pad1, restrict, prolong, restrict_size, prolong_size,
        restrictb, restrict_extrap, prolongb, interp_channels!, InterpIrregular, InterpForward, InterpBackward,
-       filledges!, pin!, unpin!, GridComm, replicate, getindex_sharded!, valgrad_sharded!, restrict3_sharded, prolong3_sharded, peer_halo!
+       filledges!, pin!, unpin!, GridComm, replicate, getindex_sharded!, valgrad_sharded!, restrict3_sharded, prolong3_sharded, restrict3_sharded_levels, prolong3_sharded_levels, peer_halo!
 
 const LIB = get(ENV, "GRIDB200_LIB", joinpath(@__DIR__, "..", "libgridb200.so"))
 
@@ -456,6 +456,24 @@ function prolong3_sharded(c::GridComm, ::Type{T}, gdims::NTuple{3,Int}, target::
     dims = Int64[gdims...]; odims = Int64[target...]
     check(ccall((:gb_prolong3_sharded, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Int64}, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}),
                 c.handle, dtcode(T), dims, slabs, odims, outs, C_NULL))
+    outs
+end
+
+# Several levels in one call: restrict(A, flags) with `nlevels` all-true columns / prolong(A, sizes) with one column of sizes
+# per level (mapdim).  slabs: the devices' planes of the array that enters the first level; outs: device pointers for their
+# planes of the LAST level's result.  The levels in between never leave the library.
+function restrict3_sharded_levels(c::GridComm, ::Type{T}, gdims::NTuple{3,Int}, nlevels::Integer, slabs::Vector{Ptr{Cvoid}}, outs::Vector{Ptr{Cvoid}},
+                                  scale::Real = 1.0) where {T<:Union{Float32,Float64}}
+    dims = Int64[gdims...]
+    check(ccall((:gb_restrict3_sharded_levels, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Int64}, Cint, Ptr{Ptr{Cvoid}}, Cdouble, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}),
+                c.handle, dtcode(T), dims, nlevels, slabs, Float64(scale), outs, C_NULL))
+    outs
+end
+function prolong3_sharded_levels(c::GridComm, ::Type{T}, gdims::NTuple{3,Int}, sizes::Matrix{Int}, slabs::Vector{Ptr{Cvoid}}, outs::Vector{Ptr{Cvoid}}) where {T<:Union{Float32,Float64}}
+    size(sizes, 1) == 3 || error("Array of sizes must have as many rows as dimensions of A")
+    dims = Int64[gdims...]; sz = Int64[sizes...]
+    check(ccall((:gb_prolong3_sharded_levels, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Int64}, Cint, Ptr{Int64}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}),
+                c.handle, dtcode(T), dims, size(sizes, 2), sz, slabs, outs, C_NULL))
     outs
 end
 

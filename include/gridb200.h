@@ -308,6 +308,15 @@ int gb_prolong3_sharded(gb_comm* c, int dtype, const int64_t* global_dims, const
                         const int64_t* out_dims, void* const* out_slabs, void* const* streams);
 /* Timing of the last sharded restrict / prolong call, 4 doubles per local rank: total ms, interior-kernel ms, time the
  * halo landed after the interior kernel had finished (ms; 0 = fully hidden), halo bytes received.  Waits for the call. */
+/* Several levels in one call: restrict(A, flags) with one all-true column per level / prolong(A, sizes) with one column of
+ * sizes per level (mapdim, src/utilities.jl:7-20).  in_slabs hold the rank's planes of the array that enters the first level
+ * (global_dims), out_slabs receive its planes of the LAST level's result; the levels in between live in scratch arrays
+ * owned by the communicator and nothing returns to the host between levels.  gb_prolong3_sharded_levels: out_dims holds
+ * 3 x nlevels target extents, column l = the sizes after level l.  Bit-identical to nlevels single-level calls. */
+int gb_restrict3_sharded_levels(gb_comm* c, int dtype, const int64_t* global_dims, int nlevels, const void* const* in_slabs, double scale,
+                                void* const* out_slabs, void* const* streams);
+int gb_prolong3_sharded_levels(gb_comm* c, int dtype, const int64_t* global_dims, int nlevels, const int64_t* out_dims, const void* const* in_slabs,
+                               void* const* out_slabs, void* const* streams);
 int gb_comm_stats(gb_comm* c, double* out, int n, int* nout);
 /* Peer mode of the sharded restrict / prolong: when one process drives every rank and the devices can map each other's
  * memory (gb_comm_init_all on an NVLink box; loopback), there is no halo exchange -- the boundary kernel reads the

@@ -53,12 +53,29 @@ def snapshot():
     out += [c[:, :, :2].cpu() for c in cur] + [c[:, :, -2:].cpu() for c in cur]  # the finest level: the planes next to the slab faces
     return out
 
+def chain_one_call():
+    """the same chains as ONE library call each (gb_restrict3_sharded_levels / gb_prolong3_sharded_levels)"""
+    low = comm.restrict3_levels(fine, (n, n, n), len(sizes) - 1, 1.0)
+    sync(); t1 = time.perf_counter()
+    up = comm.prolong3_levels(low, (sizes[-1],) * 3, [(L,) * 3 for L in reversed(sizes[:-1])])
+    sync()
+    return t1, up
+
 print("devices", ndev, "peer capable", comm.peer_halo(True))
 if comm.peer_halo(True):
     a = snapshot(); assert comm.last_path() == "peer"
     comm.peer_halo(False); b = snapshot(); assert comm.last_path() == "exchange"
     assert len(a) == len(b) and all(torch.equal(x, y) for x, y in zip(a, b))
     print("peer mode == exchange mode bitwise on", len(a), "arrays")
+    comm.peer_halo(True)
+    cur = fine
+    for L in sizes[:-1]: cur = comm.restrict3(cur, (L, L, L), 1.0)
+    low = comm.restrict3_levels(fine, (n, n, n), len(sizes) - 1, 1.0)
+    assert all(torch.equal(x.cpu(), y.cpu()) for x, y in zip(cur, low))
+    for L, Lf in zip(reversed(sizes[1:]), reversed(sizes[:-1])): cur = comm.prolong3(cur, (L, L, L), (Lf, Lf, Lf))
+    _, up = chain_one_call()
+    assert all(torch.equal(x[:, :, ::37].cpu(), y[:, :, ::37].cpu()) for x, y in zip(cur, up))
+    print("one call per chain == one call per level bitwise")
 for peer in ([True, False] if comm.peer_halo(True) else [False]):
     comm.peer_halo(peer)
     for _ in range(3): chain()
@@ -66,6 +83,12 @@ for peer in ([True, False] if comm.peer_halo(True) else [False]):
     for _ in range(9):
         sync(); t0 = time.perf_counter(); t1 = chain(); t2 = time.perf_counter()
         tr.append((t1 - t0) * 1e3); tp.append((t2 - t1) * 1e3)
+    tr1, tp1 = [], []
+    for _ in range(3): chain_one_call()
+    for _ in range(9):
+        sync(); t0 = time.perf_counter(); t1, up = chain_one_call(); t2 = time.perf_counter()
+        tr1.append((t1 - t0) * 1e3); tp1.append((t2 - t1) * 1e3)
+    print("%-8s ONE CALL per chain: restrict %.3f ms  prolong %.3f ms" % ("peer" if peer else "exchange", sorted(tr1)[4], sorted(tp1)[4]))
     st = []
     chain(st)
     print("%-8s restrict chain %.3f ms  prolong chain %.3f ms (median of 9, wall, all devices synchronised)" % ("peer" if peer else "exchange", sorted(tr)[4], sorted(tp)[4]))

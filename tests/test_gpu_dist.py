@@ -127,6 +127,17 @@ def test_single_process_all_devices():
                 f0, f1 = D.shard_range(L3, r, ndev)
                 assert np.array_equal(gb.jl_to_numpy(up[r]), refp[:, :, f0:f1])
             assert sum(s["halo_bytes"] for s in comm.stats()) > 0
+            # two levels in one call each way (intermediate level in the communicator's scratch arrays)
+            ref2 = O.restrict_flags(ref, [True, True, True])
+            low = comm.restrict3_levels(fine, shape, 2, 1.0, use_streams=False)
+            for r in range(ndev):
+                k0, k1 = D.shard_range(ref2.shape[2], r, ndev)
+                assert np.array_equal(gb.jl_to_numpy(low[r]), ref2[:, :, k0:k1])
+            back = comm.prolong3_levels(low, ref2.shape, [ref.shape, shape], use_streams=False)
+            refb = O.prolong_sizes(O.prolong_sizes(ref2, list(ref.shape)), list(shape))
+            for r in range(ndev):
+                f0, f1 = D.shard_range(L3, r, ndev)
+                assert np.array_equal(gb.jl_to_numpy(back[r]), refb[:, :, f0:f1])
         # replicate + host batch split over the devices
         co = O.make_coefs(A, "nan", "cubic")
         with torch.cuda.device(0):

@@ -416,6 +416,28 @@ def test_comm_loopback_sharded_multigrid(gb, oracle, dtype, shape, world, peer):
         # slabs at least a few planes thick on every level: the peer route is really taken when it is on
         if min(L3, n3) >= 4 * world:
             assert comm.last_path() == ("peer" if peer else "exchange")
+        # several levels in one call (restrict(A, flags) with one column per level, prolong(A, sizes) likewise): same bits
+        sizes, cur_ref = [tuple(shape)], A
+        while min(sizes[-1]) >= 5 and len(sizes) < 4:
+            cur_ref = oracle.restrict_flags(cur_ref, [True, True, True])
+            sizes.append(tuple(cur_ref.shape))
+        nlev = len(sizes) - 1
+        if nlev >= 2:
+            for rep in range(2):  # (twice: the communicator's scratch arrays are reused)
+                low = comm.restrict3_levels(fine, shape, nlev, 1.0)
+                torch.cuda.synchronize()
+                for r in range(world):
+                    k0, k1 = D.shard_range(sizes[-1][2], r, world)
+                    assert same(gb.jl_to_numpy(low[r]), np.asfortranarray(cur_ref[:, :, k0:k1])), ("restrict levels", r)
+                back = comm.prolong3_levels(low, sizes[-1], list(reversed(sizes[:-1])))
+                torch.cuda.synchronize()
+                pref = cur_ref
+                for tgt in reversed(sizes[:-1]):
+                    pref = oracle.prolong_sizes(pref, list(tgt))
+                for r in range(world):
+                    f0, f1 = D.shard_range(L3, r, world)
+                    assert same(gb.jl_to_numpy(back[r]), np.asfortranarray(pref[:, :, f0:f1])), ("prolong levels", r)
+
     finally:
         comm.close()
 
