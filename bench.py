@@ -464,12 +464,36 @@ def c5_slab(gb, torch, dist, np, O, peak, rank, world, dev, reps=3):
             levels, coarse = lv, lv[-1]
         t = torch.tensor([best[0]], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        ms_levels = float(t.item())
+        # the same chain as ONE library call -- the reference's restrict(A, flags) / prolong(A, sizes) with one column per level
+        # (gb_restrict3_sharded_levels / gb_prolong3_sharded_levels): no per-level return to the host, no per-level statistics
+        comm = D.default_comm()
+        best1, res1 = None, None
+        for rep in range(reps + 1):
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if direction == "restrict":
+                res1 = comm.restrict3_levels([local], (n, n, n), len(sizes) - 1, 1.0)[0]
+            else:
+                res1 = comm.prolong3_levels([coarse], (sizes[-1],) * 3, [(s,) * 3 for s in reversed(sizes[:-1])])[0]
+            e1.record()
+            torch.cuda.synchronize()
+            if rep > 0:
+                best1 = e0.elapsed_time(e1) if best1 is None else min(best1, e0.elapsed_time(e1))
+        same_bits = bool(torch.equal(res1, cur))
+        t = torch.tensor([best1, 0.0 if same_bits else 1.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0].item())
+        one_call_ok = float(t[1].item()) == 0.0
         bpu = 8.0 * sum(a ** 3 + b ** 3 for a, b in zip(sizes[:-1], sizes[1:])) / n ** 3
         val = n ** 3 / (ms * 1e-3) / 1e9
         out[direction] = {"ms": ms, "value": val, "unit": "Gpoints/s (level-0 points)",
                           "roofline": {"bound": "hbm", "achieved": val * bpu / world, "peak": peak, "unit": "GB/s per GPU", "frac": val * bpu / world / peak},
-                          "levels_rank0": best[1]}
+                          "call": "one library call per chain (restrict(A, flags) / prolong(A, sizes) with one column per level)",
+                          "one_call_equals_level_calls_bitwise": one_call_ok,
+                          "ms_level_calls": ms_levels, "levels_rank0": best[1]}
     # parity: the 129^3 level gathered on rank 0 against the oracle applied to the gathered 257^3 level
     k = sizes.index(257)
     parts = [None] * world
