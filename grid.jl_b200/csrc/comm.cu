@@ -35,8 +35,13 @@
 #include <cuda.h>  // types only (cuPointerGetAttribute is resolved at run time)
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
+#include <memory>
 #include <mutex>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -148,6 +153,89 @@ struct Plan {
     }
 };
 
+// Host threads for communicators that drive several devices from one process: the ~20 runtime calls per device and level of
+// a sharded multigrid call are enqueued by one thread per device instead of one thread for all (which is what limits the
+// small levels of a chain: their kernels take 20-30 us).  Workers sleep between calls; inside a call (begin .. end) they
+// spin on a phase counter, so a phase costs a cache-line round trip, not a futex wake-up.
+class DevicePool {
+public:
+    explicit DevicePool(int n) : n_(n) {
+        for (int k = 1; k < n; k++) {
+            try {
+                th_.emplace_back([this, k] { loop(k); });
+            } catch (const std::exception&) {
+                break;  // fewer workers: run() covers the missing indices on the calling thread
+            }
+        }
+    }
+    ~DevicePool() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    void begin() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            base_phase_ = phase_.load(std::memory_order_relaxed);
+            open_.store(true, std::memory_order_release);
+        }
+        cv_.notify_all();
+    }
+    void end() { open_.store(false, std::memory_order_release); }
+    // fn(i) for every i in [0, n): worker k takes i = k, the caller i = 0 and the indices without a worker
+    void run(const std::function<void(int)>& fn) {
+        const int nw = (int)th_.size();
+        job_ = &fn;
+        done_.store(0, std::memory_order_relaxed);
+        phase_.fetch_add(1, std::memory_order_release);
+        fn(0);
+        for (int i = nw + 1; i < n_; i++) fn(i);
+        while (done_.load(std::memory_order_acquire) < nw) cpu_relax();
+    }
+
+private:
+    static void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#else
+        std::this_thread::yield();
+#endif
+    }
+    void loop(int k) {
+        for (;;) {
+            int seen;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return stop_ || open_.load(std::memory_order_acquire); });
+                if (stop_) return;
+                seen = base_phase_;
+            }
+            while (open_.load(std::memory_order_acquire)) {
+                const int p = phase_.load(std::memory_order_acquire);
+                if (p != seen) {
+                    seen = p;
+                    (*job_)(k);
+                    done_.fetch_add(1, std::memory_order_release);
+                } else {
+                    cpu_relax();
+                }
+            }
+        }
+    }
+    const int n_;
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    bool stop_ = false;
+    int base_phase_ = 0;
+    std::atomic<bool> open_{false};
+    std::atomic<int> phase_{0}, done_{0};
+    const std::function<void(int)>* job_ = nullptr;
+};
+
 struct LocalRank {
     int dev = 0, rank = 0;
     ncclComm_t comm = nullptr;
@@ -176,6 +264,7 @@ struct gb_comm {
     int loopback = 0;
     int peer_capable = 0, peer = 0;  // peer-pointer halo reads possible / in use (gb_comm_peer_halo)
     int last_peer = 0;               // the last sharded call ran in peer mode
+    std::unique_ptr<gb::DevicePool> pool;  // one host thread per local rank (communicators with several local ranks)
     NcclApi* api = nullptr;
     std::vector<LocalRank> loc;
     std::mutex mu;
@@ -214,6 +303,10 @@ int init_local(LocalRank& l) {
     GB_CUDA(cudaEventCreateWithFlags(&l.ev_done, cudaEventDisableTiming));
     GB_CUDA(cudaEventCreateWithFlags(&l.ev_scratch, cudaEventDisableTiming));
     return GB_OK;
+}
+bool host_threads_default() {  // GB_COMM_THREADS=0: one host thread enqueues for every local rank
+    static const bool v = [] { const char* e = getenv("GB_COMM_THREADS"); return !(e && *e == '0'); }();
+    return v;
 }
 bool peer_default() {
     static const bool v = [] { const char* e = getenv("GB_PEER_HALO"); return !(e && *e == '0'); }();
@@ -254,11 +347,33 @@ int ensure_halo(LocalRank& l, size_t bytes) {
 
 // One sharded multigrid level.  kind 0: restrict3 (in: fine slabs, L = global fine extents), kind 1: prolong3 (in: coarse
 // slabs, n = global coarse extents, m = global target extents).
+// fn(i) -> status for every local rank, one host thread per rank when the communicator has a pool; the first failure (by rank)
+int par_for(gb_comm* c, int nl, const std::function<int(int)>& fn) {
+    std::vector<int> rcs(nl, GB_OK);
+    std::vector<std::string> msgs(nl);
+    auto body = [&](int i) {
+        rcs[i] = fn(i);
+        if (rcs[i]) msgs[i] = gb_last_error();
+    };
+    if (c->pool && nl > 1) c->pool->run(body);
+    else for (int i = 0; i < nl; i++) body(i);
+    for (int i = 0; i < nl; i++)
+        if (rcs[i]) return fail(rcs[i], msgs[i]);
+    return GB_OK;
+}
+// the pool's workers spin only while a sharded call is in progress
+struct PoolRegion {
+    gb::DevicePool* p;
+    explicit PoolRegion(gb_comm* c, bool nested) : p(nested ? nullptr : c->pool.get()) { if (p) p->begin(); }
+    ~PoolRegion() { if (p) p->end(); }
+};
+
 // (the caller holds c->mu; sync_end: with library-owned work streams, wait for the results before returning)
 int sharded_level_locked(gb_comm* c, int kind, int dtype, const i64* gin, const i64* gout, const void* const* in_slabs, double scale, void* const* out_slabs,
-                         void* const* streams, bool sync_end) {
+                         void* const* streams, bool sync_end, bool in_region = false) {
     if (!c || !gin || !gout || !in_slabs || !out_slabs) return fail(GB_ERR_ARG, "NULL argument");
     if (dtype != GB_F32 && dtype != GB_F64) return fail(GB_ERR_ARG, "bad dtype");
+    PoolRegion region(c, in_region);
     const int W = c->nranks, nl = (int)c->loc.size();
     const i64 n_in = gin[2], n_out = gout[2];
     const Plan plan(kind, n_in, n_out, W);
@@ -269,7 +384,8 @@ int sharded_level_locked(gb_comm* c, int kind, int dtype, const i64* gin, const 
     // ---- 1. inputs ready; which output planes are interior ------------------------------------------------------
     struct Piece { i64 k0, k1; bool interior; };
     std::vector<std::vector<Piece>> pieces(nl);
-    for (int i = 0; i < nl; i++) {
+    const bool maybe_peer = c->peer != 0 && nl == W && W > 1;
+    int rc1 = par_for(c, nl, [&](int i) -> int {
         LocalRank& l = c->loc[i];
         const int r = l.rank;
         DevGuard g(l.dev);
@@ -277,8 +393,10 @@ int sharded_level_locked(gb_comm* c, int kind, int dtype, const i64* gin, const 
         i64 e0, e1;
         plan.ext(r, &e0, &e1);
         const i64 o0 = plan.own0[r], o1 = plan.own1[r], k0 = plan.out0[r], k1 = plan.out1[r];
-        int rc = ensure_halo(l, std::max<size_t>(1, (size_t)((o0 - e0) + (e1 - o1)) * in_plane));
-        if (rc) return rc;
+        if (!maybe_peer) {  // (peer mode needs no halo buffer; a call that falls back allocates it below)
+            int rc = ensure_halo(l, std::max<size_t>(1, (size_t)((o0 - e0) + (e1 - o1)) * in_plane));
+            if (rc) return rc;
+        }
         GB_CUDA(cudaEventRecord(l.ev_t0, ws[i]));
         GB_CUDA(cudaEventRecord(l.ev_in, ws[i]));
         l.timed = true;
@@ -306,9 +424,11 @@ int sharded_level_locked(gb_comm* c, int kind, int dtype, const i64* gin, const 
         } else if (k0 < k1) {
             pieces[i].push_back({k0, k1, false});
         }
-    }
+        return GB_OK;
+    });
+    if (rc1) return rc1;
     // ---- peer mode?  every rank local, non-empty, its boundary stencils within the immediate neighbours' slabs, slabs mappable
-    bool use_peer = c->peer != 0 && nl == W && W > 1;
+    bool use_peer = maybe_peer;
     for (int i = 0; i < nl && use_peer; i++) {
         const int r = c->loc[i].rank;
         const i64 o0 = plan.own0[r], o1 = plan.own1[r];
@@ -323,6 +443,17 @@ int sharded_level_locked(gb_comm* c, int kind, int dtype, const i64* gin, const 
         if (!c->loopback && !peer_mappable(in_slabs[i])) use_peer = false;
     }
     c->last_peer = use_peer ? 1 : 0;
+    if (maybe_peer && !use_peer) {  // fell back to the exchange: the halo buffers after all
+        for (int i = 0; i < nl; i++) {
+            LocalRank& l = c->loc[i];
+            const int r = l.rank;
+            DevGuard g(l.dev);
+            i64 e0, e1;
+            plan.ext(r, &e0, &e1);
+            int rc = ensure_halo(l, std::max<size_t>(1, (size_t)((plan.own0[r] - e0) + (e1 - plan.own1[r])) * in_plane));
+            if (rc) return rc;
+        }
+    }
     // ---- 2. halo exchange on the comm streams ------------------------------------------------------------------
     for (int i = 0; i < nl && !use_peer; i++) {  // a send reads the source rank's slab: every comm stream waits for every local input
         DevGuard g(c->loc[i].dev);
@@ -364,34 +495,59 @@ int sharded_level_locked(gb_comm* c, int kind, int dtype, const i64* gin, const 
         }
         if (!c->loopback) GB_NCCL(api, api->GroupEnd());
     }
-    // ---- 2 (peer mode). no exchange: the BOUNDARY planes are computed on the priority stream by a kernel that reads the
-    // neighbours' planes in place through peer pointers, concurrently with the interior planes below -------------------------
-    for (int i = 0; i < nl && use_peer; i++) {
-        LocalRank& l = c->loc[i];
-        const int r = l.rank;
-        DevGuard g(l.dev);
-        const i64 o0 = plan.own0[r], o1 = plan.own1[r], k0 = plan.out0[r];
-        const i64 zmin = i > 0 ? plan.own0[r - 1] : o0, zmax = i < nl - 1 ? plan.own1[r + 1] : o1;
-        GB_CUDA(cudaStreamWaitEvent(l.cs, l.ev_in, 0));  // own slab and the neighbours' slabs are complete
-        if (i > 0) GB_CUDA(cudaStreamWaitEvent(l.cs, c->loc[i - 1].ev_in, 0));
-        if (i < nl - 1) GB_CUDA(cudaStreamWaitEvent(l.cs, c->loc[i + 1].ev_in, 0));
-        for (const Piece& p : pieces[i]) {
-            if (p.interior) continue;
-            i64 lo, hi;
-            needs(kind, n_in, n_out, p.k0, p.k1, &lo, &hi);
-            l.halo_bytes += (double)((size_t)(std::max<i64>(0, o0 - lo) + std::max<i64>(0, hi + 1 - o1)) * in_plane);  // read over the link
+    // ---- peer mode: no exchange.  Per rank (one host thread each): the BOUNDARY planes on the priority stream, by a kernel
+    // that reads the neighbours' planes in place through peer pointers; the interior planes on the work stream meanwhile; join.
+    if (use_peer) {
+        int rc2 = par_for(c, nl, [&](int i) -> int {
+            LocalRank& l = c->loc[i];
+            const int r = l.rank;
+            DevGuard g(l.dev);
+            const i64 o0 = plan.own0[r], o1 = plan.own1[r], k0 = plan.out0[r];
+            const i64 zmin = i > 0 ? plan.own0[r - 1] : o0, zmax = i < nl - 1 ? plan.own1[r + 1] : o1;
             const i64 dims[3] = {gin[0], gin[1], o1 - o0};
-            const void* plo = i > 0 ? in_slabs[i - 1] : nullptr;
-            const void* phi = i < nl - 1 ? in_slabs[i + 1] : nullptr;
-            const i64 lo_first = i > 0 ? plan.own0[r - 1] : 0, hi_first = i < nl - 1 ? plan.own0[r + 1] : 0;
-            char* out = (char*)out_slabs[i] + (size_t)(p.k0 - k0) * out_plane;
-            int rc;
-            if (kind == 0) rc = restrict3_slab_peer_device(dtype, dims, in_slabs[i], scale, n_in, o0, plo, lo_first, phi, hi_first, zmin, zmax, p.k0, p.k1 - p.k0, out, l.cs);
-            else rc = prolong3_slab_peer_device(dtype, dims, in_slabs[i], gout, n_in, o0, plo, lo_first, phi, hi_first, zmin, zmax, p.k0, p.k1 - p.k0, out, l.cs);
-            if (rc) return rc;
-        }
+            GB_CUDA(cudaStreamWaitEvent(l.cs, l.ev_in, 0));  // own slab and the neighbours' slabs are complete
+            if (i > 0) GB_CUDA(cudaStreamWaitEvent(l.cs, c->loc[i - 1].ev_in, 0));
+            if (i < nl - 1) GB_CUDA(cudaStreamWaitEvent(l.cs, c->loc[i + 1].ev_in, 0));
+            for (const Piece& p : pieces[i]) {
+                if (p.interior) continue;
+                i64 lo, hi;
+                needs(kind, n_in, n_out, p.k0, p.k1, &lo, &hi);
+                l.halo_bytes += (double)((size_t)(std::max<i64>(0, o0 - lo) + std::max<i64>(0, hi + 1 - o1)) * in_plane);  // read over the link
+                const void* plo = i > 0 ? in_slabs[i - 1] : nullptr;
+                const void* phi = i < nl - 1 ? in_slabs[i + 1] : nullptr;
+                const i64 lo_first = i > 0 ? plan.own0[r - 1] : 0, hi_first = i < nl - 1 ? plan.own0[r + 1] : 0;
+                char* out = (char*)out_slabs[i] + (size_t)(p.k0 - k0) * out_plane;
+                int rc;
+                if (kind == 0) rc = restrict3_slab_peer_device(dtype, dims, in_slabs[i], scale, n_in, o0, plo, lo_first, phi, hi_first, zmin, zmax, p.k0, p.k1 - p.k0, out, l.cs);
+                else rc = prolong3_slab_peer_device(dtype, dims, in_slabs[i], gout, n_in, o0, plo, lo_first, phi, hi_first, zmin, zmax, p.k0, p.k1 - p.k0, out, l.cs);
+                if (rc) return rc;
+            }
+            GB_CUDA(cudaEventRecord(l.ev_halo, l.cs));
+            GB_CUDA(cudaEventRecord(l.ev_h1, l.cs));
+            for (const Piece& p : pieces[i]) {
+                if (!p.interior) continue;
+                char* out = (char*)out_slabs[i] + (size_t)(p.k0 - k0) * out_plane;
+                int rc;
+                if (kind == 0) rc = restrict3_slab_device(dtype, dims, in_slabs[i], scale, n_in, o0, p.k0, p.k1 - p.k0, out, ws[i]);
+                else rc = prolong3_slab_device(dtype, dims, in_slabs[i], gout, n_in, o0, p.k0, p.k1 - p.k0, out, ws[i]);
+                if (rc) return rc;
+            }
+            GB_CUDA(cudaEventRecord(l.ev_int, ws[i]));
+            GB_CUDA(cudaStreamWaitEvent(ws[i], l.ev_halo, 0));  // join: results complete when both streams are
+            GB_CUDA(cudaEventRecord(l.ev_t1, ws[i]));
+            GB_CUDA(cudaEventRecord(l.ev_done, ws[i]));
+            return GB_OK;
+        });
+        if (rc2) return rc2;
+        rc2 = par_for(c, nl, [&](int i) -> int {  // a slab may change once the neighbours that read it are done
+            DevGuard g(c->loc[i].dev);
+            if (i > 0) GB_CUDA(cudaStreamWaitEvent(ws[i], c->loc[i - 1].ev_done, 0));
+            if (i < nl - 1) GB_CUDA(cudaStreamWaitEvent(ws[i], c->loc[i + 1].ev_done, 0));
+            return GB_OK;
+        });
+        if (rc2) return rc2;
     }
-    for (int i = 0; i < nl; i++) {
+    for (int i = 0; i < nl && !use_peer; i++) {
         LocalRank& l = c->loc[i];
         DevGuard g(l.dev);
         GB_CUDA(cudaEventRecord(l.ev_halo, l.cs));
@@ -399,7 +555,7 @@ int sharded_level_locked(gb_comm* c, int kind, int dtype, const i64* gin, const 
     }
     // ---- 2b. interior planes on the work streams, while the halo travels (the exchange was enqueued FIRST: its kernels
     // take their SM slots before the interior kernel fills the machine) ------------------------------------------------
-    for (int i = 0; i < nl; i++) {
+    for (int i = 0; i < nl && !use_peer; i++) {
         LocalRank& l = c->loc[i];
         const int r = l.rank;
         DevGuard g(l.dev);
@@ -414,21 +570,6 @@ int sharded_level_locked(gb_comm* c, int kind, int dtype, const i64* gin, const 
             if (rc) return rc;
         }
         GB_CUDA(cudaEventRecord(l.ev_int, ws[i]));
-    }
-    // ---- 3 (peer mode). join: results complete when both streams are; a slab may change once its readers are done ------------
-    if (use_peer) {
-        for (int i = 0; i < nl; i++) {
-            LocalRank& l = c->loc[i];
-            DevGuard g(l.dev);
-            GB_CUDA(cudaStreamWaitEvent(ws[i], l.ev_halo, 0));
-            GB_CUDA(cudaEventRecord(l.ev_t1, ws[i]));
-            GB_CUDA(cudaEventRecord(l.ev_done, ws[i]));
-        }
-        for (int i = 0; i < nl; i++) {
-            DevGuard g(c->loc[i].dev);
-            if (i > 0) GB_CUDA(cudaStreamWaitEvent(ws[i], c->loc[i - 1].ev_done, 0));
-            if (i < nl - 1) GB_CUDA(cudaStreamWaitEvent(ws[i], c->loc[i + 1].ev_done, 0));
-        }
     }
     // ---- 3. boundary planes after the halo has landed ------------------------------------------------------------
     for (int i = 0; i < nl && !use_peer; i++) {
@@ -533,13 +674,14 @@ int sharded_levels(gb_comm* c, int kind, int dtype, const i64* dims_levels, int 
     std::vector<void*> outs(nl);
     for (int i = 0; i < nl; i++) ins[i] = in_slabs[i];
     int all_peer = 1;
+    PoolRegion region(c, false);  // the workers stay awake across the levels
     for (int lev = 0; lev < nlevels; lev++) {
         const bool last = lev + 1 == nlevels;
         for (int i = 0; i < nl; i++) outs[i] = last ? out_slabs[i] : c->loc[i].scratch[lev & 1];
         const i64* gin = dims_levels + 3 * lev;
         const i64* gout = dims_levels + 3 * (lev + 1);
         // (a rank that owns no plane of a level passes whatever pointer it has: nothing is read or written through it)
-        int rc = sharded_level_locked(c, kind, dtype, gin, gout, ins.data(), scale, outs.data(), streams, last);
+        int rc = sharded_level_locked(c, kind, dtype, gin, gout, ins.data(), scale, outs.data(), streams, last, true);
         if (rc) return rc;
         all_peer &= c->last_peer;
         for (int i = 0; i < nl; i++) ins[i] = outs[i];
@@ -658,6 +800,7 @@ int gb_comm_init_all(gb_comm** out, int ndev, const int* dev_ids) {
     }
     c->peer_capable = ok ? 1 : 0;
     c->peer = ok && peer_default() ? 1 : 0;
+    if (ndev > 1 && host_threads_default()) c->pool.reset(new gb::DevicePool(ndev));
     *out = c;
     return GB_OK;
 }
@@ -677,6 +820,7 @@ int gb_comm_init_loopback(gb_comm** out, int nranks) {
     }
     c->peer_capable = 1;  // one device: every "peer" pointer is local
     c->peer = peer_default() ? 1 : 0;
+    if (nranks > 1 && host_threads_default()) c->pool.reset(new gb::DevicePool(nranks));
     *out = c;
     return GB_OK;
 }
