@@ -1043,32 +1043,43 @@ int eval_host_small(const gb_grid* g, int out_mask, int outmode, i64 nq, const v
         c.bytes = want;
     }
     const bool check = first_invalid && g->bc == GB_BC_NIL;
+    // A handful of queries (the scalar API): no copies at all -- the kernel reads the coordinates from, and writes the results to,
+    // the pinned buffer itself (mapped into the device's address space: a few dozen bytes over PCIe each way), which saves
+    // two copy submissions per call.  BCnil's first-invalid word needs a device atomic: such calls copy.
+    static const i64 zc_max = [] { const char* e = getenv("GB_ZERO_COPY_MAX"); return (i64)(e ? atoll(e) : 64); }();
+    const bool zero_copy = nq <= zc_max && !check;
+    char* const base = zero_copy ? c.pin : c.dev;  // what the kernel reads and writes
     EvalCall call;
     call.g = g; call.outmode = outmode; call.flags = flags; call.xdtype = xdtype; call.affine = affine;
     call.nq = nq; call.q0 = 0;
     call.first_invalid = check ? reinterpret_cast<u64*>(c.dev + off_bad) : nullptr;
     if (xaos) {
         std::memcpy(c.pin, xaos, bytes_x);
-        for (int d = 0; d < N; d++) call.xp[d] = c.dev + (size_t)d * xs;
+        for (int d = 0; d < N; d++) call.xp[d] = base + (size_t)d * xs;
         call.xqs = N;
     } else {
         for (int d = 0; d < N; d++) {
             std::memcpy(c.pin + (size_t)d * nq * xs, xcols[d], (size_t)nq * xs);
-            call.xp[d] = c.dev + (size_t)d * nq * xs;
+            call.xp[d] = base + (size_t)d * nq * xs;
         }
         call.xqs = 1;
     }
     *reinterpret_cast<u64*>(c.pin + off_bad) = ~0ull;
-    call.val = vw ? c.dev + off_v : nullptr;
-    call.grad = gw ? c.dev + off_g : nullptr;
-    call.hess = hw ? c.dev + off_h : nullptr;
+    call.val = vw ? base + off_v : nullptr;
+    call.grad = gw ? base + off_g : nullptr;
+    call.hess = hw ? base + off_h : nullptr;
     call.packed = packed;
     if (g->ready) GB_CUDA(cudaStreamWaitEvent(c.s, g->ready, 0));  // a grid built on another stream
-    GB_CUDA(cudaMemcpyAsync(c.dev, c.pin, off_v, cudaMemcpyHostToDevice, c.s));
-    int rc = launch_eval(call, c.s);
-    if (rc == GB_OK) {
-        cudaError_t e = cudaMemcpyAsync(c.pin + off_bad, c.dev + off_bad, total - off_bad, cudaMemcpyDeviceToHost, c.s);
-        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync D2H");
+    int rc;
+    if (zero_copy) {
+        rc = launch_eval(call, c.s);
+    } else {
+        GB_CUDA(cudaMemcpyAsync(c.dev, c.pin, off_v, cudaMemcpyHostToDevice, c.s));
+        rc = launch_eval(call, c.s);
+        if (rc == GB_OK) {
+            cudaError_t e = cudaMemcpyAsync(c.pin + off_bad, c.dev + off_bad, total - off_bad, cudaMemcpyDeviceToHost, c.s);
+            if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync D2H");
+        }
     }
     const cudaError_t es_ = cudaStreamSynchronize(c.s);
     if (rc == GB_OK && es_ != cudaSuccess) rc = cuda_fail(es_, "cudaStreamSynchronize");
