@@ -356,11 +356,10 @@ def extra_configs(gb, torch, np, O, peak, traffic, reps=5):
     levels = down()
     coarse = levels[-1]
 
-    def up():
-        cur = coarse
-        for s in reversed(sizes[:-1]):
-            cur = gb.prolong(cur, [s, s, s])
-        return cur
+    up_sizes = np.array([[s, s, s] for s in reversed(sizes[:-1])]).T  # one column of target sizes per level
+
+    def up():  # prolong(A, sizes) with one column per level: one library call (gb_prolong3_levels)
+        return gb.prolong(coarse, up_sizes)
 
     best_u, med_u = _timed(torch, up, reps)
     k = sizes.index(129)

@@ -82,6 +82,8 @@ SIGNATURES = {
     "gb_prolong3_slab": (i32, [i32, p_i64, vp, p_i64, i64, i64, i64, i64, vp, i32, vp]),
     "gb_restrict3": (i32, [i32, p_i64, vp, f64, vp, i32, vp]),
     "gb_prolong3": (i32, [i32, p_i64, vp, p_i64, vp, i32, vp]),
+    "gb_restrict3_levels": (i32, [i32, p_i64, i32, vp, f64, vp, i32, vp]),
+    "gb_prolong3_levels": (i32, [i32, p_i64, i32, p_i64, vp, vp, i32, vp]),
     "gb_device_alloc": (i32, [p_vp, C.c_size_t]),
     "gb_device_free": (i32, [vp]),
     "gb_memcpy_h2d": (i32, [vp, vp, C.c_size_t, vp]),

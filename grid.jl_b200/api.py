@@ -1063,6 +1063,16 @@ def restrict(A, dim_or_flag, scale=1.0, fused=True):
     flag = _flags(dim_or_flag, a.ndim)
     cur, out = a, A
     lib = L.lib()
+    if fused and a.ndim == 3 and flag.shape[1] > 1 and flag.all():
+        # every column restricts every dimension: all levels in ONE library call (gb_restrict3_levels; the levels in between
+        # never leave the device)
+        shp = list(a.shape)
+        for _ in range(flag.shape[1]):
+            shp = [restrict_size(s) for s in shp]
+        out = a.empty_like_shape(shp)
+        o = _Arr(out, name="out")
+        L.check(lib.gb_restrict3_levels(a.dtype, _i64s(a.shape), int(flag.shape[1]), a.ptr, float(scale), o.ptr, a.mem, a.stream()))
+        return out
     for j in range(flag.shape[1]):
         if fused and cur.ndim == 3 and flag[:, j].all():
             shp = [restrict_size(s) for s in cur.shape]
@@ -1101,6 +1111,19 @@ def prolong(A, *args, fused=True):
         raise ErrorException(L.GB_ERR_ARG, "Array of sizes must have as many rows as dimensions of A")
     cur, out = a, A
     lib = L.lib()
+    if fused and a.ndim == 3 and sz.shape[1] > 1:
+        # several columns that each enlarge every dimension: all levels in ONE library call (gb_prolong3_levels)
+        shp, ok = list(a.shape), True
+        for j in range(sz.shape[1]):
+            ok = ok and all(int(sz[i, j]) > shp[i] for i in range(3))
+            if not ok:
+                break
+            shp = [prolong_size(shp[i], int(sz[i, j])) for i in range(3)]
+        if ok:
+            out = a.empty_like_shape(shp)
+            o = _Arr(out, name="out")
+            L.check(lib.gb_prolong3_levels(a.dtype, _i64s(a.shape), int(sz.shape[1]), _i64s([int(v) for v in sz.T.reshape(-1)]), a.ptr, o.ptr, a.mem, a.stream()))
+            return out
     for j in range(sz.shape[1]):
         grow = [sz[i, j] > cur.shape[i] for i in range(cur.ndim)]
         if fused and cur.ndim == 3 and grow == [True, True, False]:  # every plane in one pass (gb_prolong12)

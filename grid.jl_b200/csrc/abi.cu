@@ -1696,6 +1696,72 @@ int gb_prolong3(int dtype, const int64_t* dims, const void* in, const int64_t* o
     }, &ctx);
 }
 
+// Several fused 3-D levels in one call: restrict(A, flags) with one all-true column per level / prolong(A, sizes) with one
+// column of sizes per level (mapdim, src/utilities.jl:7-20).  The intermediate levels live in two stream-ordered scratch
+// arrays and never leave the device (host arrays: one copy in, one copy out, instead of a round trip per level).
+// dims_levels: 3 x (nlevels + 1) extents, column l = the array that enters level l.
+static int levels_device(int kind, int dtype, const i64* dims_levels, int nlevels, const void* in, double scale, void* out, cudaStream_t s) {
+    AsyncBuf t0(s), t1(s);
+    AsyncBuf* t[2] = {&t0, &t1};
+    size_t need[2] = {0, 0};
+    for (int lev = 0; lev + 1 < nlevels; lev++) {
+        const i64* d = dims_levels + 3 * (lev + 1);
+        need[lev & 1] = std::max(need[lev & 1], (size_t)d[0] * (size_t)d[1] * (size_t)d[2] * esize(dtype));
+    }
+    for (int k = 0; k < 2; k++)
+        if (need[k]) GB_CUDA(t[k]->alloc(need[k]));
+    const void* cur = in;
+    for (int lev = 0; lev < nlevels; lev++) {
+        void* dst = lev + 1 == nlevels ? out : t[lev & 1]->p;
+        const int rc = kind == 0 ? restrict3_device(dtype, dims_levels + 3 * lev, cur, scale, dst, s)
+                                 : prolong3_device(dtype, dims_levels + 3 * lev, cur, dims_levels + 3 * (lev + 1), dst, s);
+        if (rc) return rc;
+        cur = dst;
+    }
+    return GB_OK;
+}
+static int levels_call(int kind, int dtype, const std::vector<i64>& dl, int nlevels, const void* in, double scale, void* out, int mem, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    pool_keep_memory();
+    if (mem == GB_DEVICE) return levels_device(kind, dtype, dl.data(), nlevels, in, scale, out, s);
+    const i64* d0 = dl.data();
+    const i64* dn = dl.data() + 3 * nlevels;
+    struct Ctx { int kind, dtype, nlevels; const i64* dl; double scale; } ctx{kind, dtype, nlevels, dl.data(), scale};
+    return mg_host(dtype, d0[0] * d0[1] * d0[2], dn[0] * dn[1] * dn[2], in, out, s, [](void* c, const void* i, void* o, cudaStream_t st) {
+        Ctx* x = (Ctx*)c;
+        return levels_device(x->kind, x->dtype, x->dl, x->nlevels, i, x->scale, o, st);
+    }, &ctx);
+}
+int gb_restrict3_levels(int dtype, const int64_t* dims, int nlevels, const void* in, double scale, void* out, int mem, void* stream) {
+    if (!ok_dtype(dtype) || !dims || !in || !out || nlevels < 1 || nlevels > 64) return fail(GB_ERR_ARG, "bad arguments");
+    std::vector<i64> dl(3 * (size_t)(nlevels + 1));
+    for (int d = 0; d < 3; d++) dl[d] = dims[d];
+    for (int l = 0; l < nlevels; l++)
+        for (int d = 0; d < 3; d++) {
+            if (dl[3 * l + d] < 1) return fail(GB_ERR_ARG, "bad dims");
+            dl[3 * (l + 1) + d] = gb_restrict_size(dl[3 * l + d]);
+        }
+    return levels_call(0, dtype, dl, nlevels, in, scale, out, mem, stream);
+}
+int gb_prolong3_levels(int dtype, const int64_t* dims, int nlevels, const int64_t* out_dims, const void* in, void* out, int mem, void* stream) {
+    if (!ok_dtype(dtype) || !dims || !out_dims || !in || !out || nlevels < 1 || nlevels > 64) return fail(GB_ERR_ARG, "bad arguments");
+    std::vector<i64> dl(3 * (size_t)(nlevels + 1));
+    for (int d = 0; d < 3; d++) dl[d] = dims[d];
+    for (int l = 0; l < nlevels; l++)
+        for (int d = 0; d < 3; d++) {
+            const i64 from = dl[3 * l + d], to = out_dims[3 * l + d];
+            if (from < 1) return fail(GB_ERR_ARG, "bad dims");
+            i64 m = from;
+            if (to > from) {  // (a dimension whose target is not larger is kept, src/restrict_prolong.jl:94)
+                int rc = gb_prolong_size(from, to, nullptr);
+                if (rc) return rc;
+                m = to;
+            }
+            dl[3 * (l + 1) + d] = m;
+        }
+    return levels_call(1, dtype, dl, nlevels, in, 1.0, out, mem, stream);
+}
+
 // restrict / prolong along dims 1 and 2 of a 2-D array, or of every plane of a 3-D array, in one pass (the marching
 // kernels without their dim-3 stage); same bits as gb_restrict / gb_prolong applied to dim 0, then dim 1
 int gb_restrict12(int dtype, int ndim, const int64_t* dims, const void* in, double scale, void* out, int mem, void* stream) {

@@ -274,8 +274,22 @@ function restrict12(A::Array{T,2}, scale::Real = one(T)) where {T<:Union{Float32
         dtcode(T), 2, dims, A, Float64(scale), R, GB_HOST, C_NULL))
     R
 end
+# every column of flags all-true on a 3-D array: all levels in ONE library call, the levels in between stay on the device
+function restrict3_levels(A::Array{T,3}, nlevels::Integer, scale::Real = one(T)) where {T<:Union{Float32,Float64}}
+    sz = size(A)
+    for _ = 1:nlevels
+        sz = map(restrict_size, sz)
+    end
+    R = Array{T,3}(undef, sz...); dims = Int64[size(A)...]
+    GC.@preserve A R dims check(ccall((:gb_restrict3_levels, LIB), Cint, (Cint, Ptr{Int64}, Cint, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+        dtcode(T), dims, nlevels, A, Float64(scale), R, GB_HOST, C_NULL))
+    R
+end
 function restrict(A::Array, flag::Union{Array{Bool},BitArray}, scale::Real = one(eltype(A)))     # mapdim, src/utilities.jl:7-20
     ndims(A) == size(flag, 1) || error("Boolean flag must have as many rows as dimensions of A")
+    if ndims(A) == 3 && eltype(A) <: Union{Float32,Float64} && size(flag, 2) > 1 && all(flag)
+        return restrict3_levels(A, size(flag, 2), scale)
+    end
     for j = 1:size(flag, 2)
         if ndims(A) == 3 && eltype(A) <: Union{Float32,Float64} && all(flag[:, j])
             A = restrict3(A, scale)
@@ -309,8 +323,30 @@ function prolong12(A::Array{T,2}, m1::Integer, m2::Integer) where {T<:Union{Floa
         dtcode(T), 2, dims, A, Int64(m1), Int64(m2), P, GB_HOST, C_NULL))
     P
 end
+# every column of sizes enlarges every dimension of a 3-D array: all levels in ONE library call
+function prolong3_levels(A::Array{T,3}, sz::Matrix{Int}) where {T<:Union{Float32,Float64}}
+    cur = [size(A)...]
+    for j = 1:size(sz, 2), i = 1:3
+        cur[i] = prolong_size(cur[i], sz[i, j])
+    end
+    P = Array{T,3}(undef, cur...); dims = Int64[size(A)...]; od = Int64[sz...]
+    GC.@preserve A P dims od check(ccall((:gb_prolong3_levels, LIB), Cint, (Cint, Ptr{Int64}, Cint, Ptr{Int64}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+        dtcode(T), dims, size(sz, 2), od, A, P, GB_HOST, C_NULL))
+    P
+end
+function _all_grow(A::Array, sz::Array{Int})
+    cur = [size(A)...]
+    for j = 1:size(sz, 2)
+        all(sz[:, j] .> cur) || return false
+        cur = sz[:, j]
+    end
+    true
+end
 function prolong(A::Array, sz::Array{Int})
     ndims(A) == size(sz, 1) || error("Array of sizes must have as many rows as dimensions of A")
+    if ndims(A) == 3 && eltype(A) <: Union{Float32,Float64} && ndims(sz) == 2 && size(sz, 2) > 1 && _all_grow(A, sz)
+        return prolong3_levels(A, sz)
+    end
     for j = 1:size(sz, 2)
         if ndims(A) == 3 && eltype(A) <: Union{Float32,Float64}
             A = prolong3(A, sz[:, j])

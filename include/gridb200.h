@@ -242,6 +242,11 @@ int gb_prolong3_slab(int dtype, const int64_t* dims, const void* in, const int64
  * per-dim intermediates are rounded exactly as the staged reference does, so the result is
  * bit-identical to gb_restrict applied to dims 0,1,2 in turn (src/utilities.jl:7-20). */
 int gb_restrict3(int dtype, const int64_t* dims, const void* in, double scale, void* out, int mem, void* stream);
+/* nlevels fused 3-D levels in one call (restrict(A, flags) with one all-true column per level / prolong(A, sizes) with one
+ * column of sizes per level -- out_dims: 3 x nlevels): the intermediate levels stay on the device; `out` receives the last
+ * level (extents: gb_restrict_size applied nlevels times / the last column of out_dims).  Same bits as nlevels calls. */
+int gb_restrict3_levels(int dtype, const int64_t* dims, int nlevels, const void* in, double scale, void* out, int mem, void* stream);
+int gb_prolong3_levels(int dtype, const int64_t* dims, int nlevels, const int64_t* out_dims, const void* in, void* out, int mem, void* stream);
 /* prolong(A, [s1,s2,s3]) on a 3-D array as one pass (src/restrict_prolong.jl:87-100). */
 int gb_prolong3(int dtype, const int64_t* dims, const void* in, const int64_t* out_dims, void* out, int mem,
                 void* stream);

@@ -132,6 +132,38 @@ print("ok")
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_multi_level_restrict_prolong_one_call(gb, oracle, dtype):
+    """restrict(A, flags) with several all-true columns and prolong(A, sizes) with several columns run as ONE library call
+    (gb_restrict3_levels / gb_prolong3_levels; the intermediate levels stay on the device): same bits as the oracle's
+    column-by-column mapdim, device and host arrays, odd / even / degenerate extents."""
+    rng = np.random.default_rng(47)
+    for shape, nlev in (((40, 33, 26), 3), ((17, 16, 9), 2), ((9, 5, 3), 3), ((64, 64, 64), 4)):
+        A = np.asfortranarray(rng.standard_normal(shape).astype(dtype))
+        flags = np.ones((3, nlev), dtype=bool)
+        ref = oracle.restrict_flags(A, flags, 0.5)
+        sizes, cur = [list(shape)], list(shape)
+        for _ in range(nlev):
+            cur = [gb.restrict_size(v) for v in cur]
+            sizes.append(cur)
+        for dev in (True, False):
+            a = gb.jl_from_numpy(A) if dev else A
+            r = gb.restrict(a, flags, 0.5)
+            got = gb.jl_to_numpy(r) if dev else r
+            assert got.shape == tuple(sizes[-1]) and same(got, ref), (shape, dev)
+            r1 = a
+            for _ in range(nlev):
+                r1 = gb.restrict(r1, [True, True, True], 0.5)
+            assert same(gb.jl_to_numpy(r1) if dev else r1, ref)
+            if min(sizes[-1]) >= 2:
+                sz = np.array(list(reversed(sizes[:-1]))).T  # (3, nlev): the way back up
+                refp = oracle.prolong_sizes(ref, sz)
+                p = gb.prolong(r, sz)
+                assert same(gb.jl_to_numpy(p) if dev else p, refp), (shape, dev)
+    with pytest.raises(gb.ErrorException):
+        gb.prolong(gb.jl_from_numpy(np.asfortranarray(np.zeros((5, 5, 5), dtype=dtype))), np.array([[9, 18], [9, 17], [9, 17]]))
+
+
 def test_small_host_batches_fast_path(gb, oracle):
     """Host batches up to 2^15 queries (the scalar API: one query per C call) run through a pooled context that is
     created once (abi.cu: eval_host_small).  Bits as the oracle's for scalar calls, short batches of every output kind,
