@@ -26,8 +26,13 @@ int main(int argc, char** argv) {
     int (*p_p3s)(gb_comm*, int, const int64_t*, const void* const*, const int64_t*, void* const*, void* const*) = gb_prolong3_sharded;
     int (*p_evs)(gb_comm*, gb_grid* const*, int, int64_t, const void*, int, const double*, void*, void*, void*, int, int64_t*) = gb_eval_sharded;
     int (*p_repl)(gb_comm*, int, gb_grid**, int, int, const int64_t*, int, int, double) = gb_grid_replicate;
+    int (*p_r3l)(int, const int64_t*, int, const void*, double, void*, int, void*) = gb_restrict3_levels;
+    int (*p_p3l)(int, const int64_t*, int, const int64_t*, const void*, void*, int, void*) = gb_prolong3_levels;
+    int (*p_r3sl)(gb_comm*, int, const int64_t*, int, const void* const*, double, void* const*, void* const*) = gb_restrict3_sharded_levels;
+    int (*p_p3sl)(gb_comm*, int, const int64_t*, int, const int64_t*, const void* const*, void* const*, void* const*) = gb_prolong3_sharded_levels;
+    int (*p_peer)(gb_comm*, int, int*) = gb_comm_peer_halo;
     (void)p_create_opt; (void)p_outer; (void)p_invert; (void)p_restrict; (void)p_prolong; (void)p_filledges; (void)p_comm_all; (void)p_r3s; (void)p_p3s;
-    (void)p_evs; (void)p_repl;
+    (void)p_evs; (void)p_repl; (void)p_r3l; (void)p_p3l; (void)p_r3sl; (void)p_p3sl; (void)p_peer;
     printf("gridb200 %d\n", gb_version());
     if (gb_restrict_size(1024) != 513 || gb_restrict_size(513) != 257) return 2;
     if (argc < 2 || strcmp(argv[1], "run") != 0) return 0;
